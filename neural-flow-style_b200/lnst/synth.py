@@ -1,0 +1,108 @@
+"""Seeded synthetic inputs for tests and ``bench.py``.
+
+The reference's datasets come from external simulators (mantaflow / SPlisHSPlasH) and its
+loss-network weights from downloads; none of that exists offline, so every measurement uses
+the generators below.  All use ``numpy.random.RandomState`` / a CPU ``torch.Generator`` so the
+same arrays are produced on every machine.
+"""
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+_VGG_CFG = {
+    'vgg_19': [(2, 64), (2, 128), (4, 256), (4, 512), (4, 512)],
+    'vgg_16': [(2, 64), (2, 128), (3, 256), (3, 512), (3, 512)],
+}
+
+
+def smoke_particles(n, num_kernels=2, seed=123, centre=(0.5, 0.45, 0.5), radii=(0.30, 0.35, 0.30),
+                    num_frames=1, pad=0):
+    """Particles uniform inside an ellipsoid, normalised (z,y,x); r[:,0]~U(.2,1) and the
+    finer kernels ~U(-.1,.1).  ``pad`` extra rows are the drivers' p=-1 padding
+    (``test_smokegun.py:48``).  Later frames move by a small rigid swirl so ids persist."""
+    rng = np.random.RandomState(seed)
+    pts = np.zeros((0, 3))
+    while pts.shape[0] < n:
+        c = rng.uniform(-1, 1, size=(2 * n + 16, 3))
+        pts = np.concatenate([pts, c[(c ** 2).sum(-1) < 1.0]], 0)
+    pts = pts[:n] * np.array(radii) + np.array(centre)
+    r0 = np.concatenate([rng.uniform(0.2, 1.0, size=(n, 1)),
+                         rng.uniform(-0.1, 0.1, size=(n, max(num_kernels - 1, 0)))], -1)
+    p_list, r_list = [], []
+    for t in range(num_frames):
+        ang = 0.02 * t
+        c, s = np.cos(ang), np.sin(ang)
+        q = pts - np.array(centre)
+        q = np.stack([q[:, 0] * c - q[:, 2] * s, q[:, 1] + 0.002 * t, q[:, 0] * s + q[:, 2] * c], -1)
+        pt = (q + np.array(centre)).astype(np.float32)
+        rt = r0.astype(np.float32)
+        if pad:
+            pt = np.concatenate([pt, -np.ones((pad, 3), np.float32)], 0)
+            rt = np.concatenate([rt, np.zeros((pad, num_kernels), np.float32)], 0)
+        p_list.append(pt)
+        r_list.append(rt)
+    return p_list, r_list
+
+
+def liquid_particles(n, seed=123, num_frames=1):
+    """A liquid blob for the position mode ('p'): jittered lattice in a box, moved by an
+    analytic divergence-free swirl between frames (persistent ids)."""
+    rng = np.random.RandomState(seed)
+    m = int(np.ceil(n ** (1 / 3.0)))
+    g = np.stack(np.meshgrid(*[np.arange(m)] * 3, indexing='ij'), -1).reshape(-1, 3)[:n]
+    base = 0.3 + 0.4 * (g + 0.5) / m + rng.uniform(-0.2, 0.2, size=(n, 3)) * 0.4 / m
+    out = []
+    for t in range(num_frames):
+        ang = 0.03 * t
+        c, s = np.cos(ang), np.sin(ang)
+        q = base - 0.5
+        q = np.stack([q[:, 0], q[:, 1] * c - q[:, 2] * s, q[:, 1] * s + q[:, 2] * c], -1) + 0.5
+        out.append(q.astype(np.float32))
+    return out
+
+
+def dam_particles_2d(domain, spacing=0.05, seed=123, num_frames=1, rest_density=1000.0):
+    """2-D dam block (``test_dambreak2d.py`` style): lattice over x<.35 Dx, y<.6 Dy with
+    jitter; r = SPH density ~ rho0 (1 + .02 N)."""
+    rng = np.random.RandomState(seed)
+    dy, dx = float(domain[0]), float(domain[1])
+    ys = np.arange(spacing * 0.5, 0.6 * dy, spacing)
+    xs = np.arange(spacing * 0.5, 0.35 * dx, spacing)
+    g = np.stack(np.meshgrid(ys, xs, indexing='ij'), -1).reshape(-1, 2)
+    n = g.shape[0]
+    p_list, r_list = [], []
+    for t in range(num_frames):
+        pt = g + rng.uniform(-0.1 * spacing, 0.1 * spacing, size=g.shape) + np.array([0.0, 0.01 * t])
+        pt = (pt / np.array([dy, dx])).astype(np.float32)
+        p_list.append(pt)
+        r_list.append((rest_density * (1 + 0.02 * rng.randn(n, 1))).astype(np.float32))
+    return p_list, r_list
+
+
+def style_image(h, w, seed=7):
+    """Low-pass seeded noise, [h,w,3] float32 in 0..255 -- generated directly at the octave
+    size so no image resampling is involved in parity runs."""
+    from scipy.ndimage import gaussian_filter
+    rng = np.random.RandomState(seed)
+    img = rng.uniform(0, 1, size=(h, w, 3))
+    img = gaussian_filter(img, sigma=(2.0, 2.0, 0))
+    img = (img - img.min()) / (img.max() - img.min() + 1e-12)
+    return (img * 255).astype(np.float32)
+
+
+def vgg_weights(model='vgg_19', seed=19):
+    """Seeded He-normal weights in slim layout: {'conv1_1': (w[3,3,Cin,Cout], b[Cout]), ...}
+    (float32 CPU tensors).  Same recipe as ``oracle.vgg.synthetic_weights`` -- kept separate so
+    the product never imports the oracle; ``tests/test_synth.py`` checks they agree."""
+    g = torch.Generator().manual_seed(seed)
+    w = OrderedDict()
+    cin = 3
+    for b, (rep, cout) in enumerate(_VGG_CFG[model], start=1):
+        for i in range(1, rep + 1):
+            std = float(np.sqrt(2.0 / (9 * cin)))
+            wt = torch.randn(3, 3, cin, cout, generator=g, dtype=torch.float32) * std
+            bs = torch.randn(cout, generator=g, dtype=torch.float32)
+            w['conv%d_%d' % (b, i)] = (wt, bs)
+            cin = cout
+    return w
