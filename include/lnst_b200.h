@@ -1,0 +1,159 @@
+/* lnst_b200.h -- C-ABI of the B200-native LNST stylisation hot path.
+ *
+ * The reference (byungsook/neural-flow-style) has NO native code and no FFI: its hot path is
+ * a TensorFlow-1.15 graph executed by `sess.run([train_op, total_loss])`
+ * (styler_3p.py:331,354; styler_2p.py:257).  Each entry point below replaces the stock TF
+ * op(s) cited beside it.  The library is what a maintainer would bind in place of those ops
+ * (ctypes stub shown in INTEGRATION.md); `neural-flow-style_b200/lnst/_lib.py` is that binding.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer (fp32 unless stated), owned by the caller; the
+ *     library allocates nothing, keeps no global state, never synchronises the stream;
+ *   - `stream` is a cudaStream_t passed as void*;
+ *   - return 0 = ok; <0 = argument error (nothing launched); >0 = cudaError_t of the launch;
+ *   - volumes are contiguous [D,H,W] (one frame, one channel), images NHWC, particles AoS
+ *     [N,dim] in the reference's normalised ((z,)y,x) order, weights HWIO (slim layout).
+ */
+#ifndef LNST_B200_H
+#define LNST_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LNST_ABI_VERSION 1
+
+/* Grid description shared by the particle<->grid ops (transform.py:1316-1343). */
+typedef struct LnstGrid {
+  int32_t dim;        /* 2 or 3 */
+  int32_t res[3];     /* D,H,W (dim==2: res[0] = 1, positions are (y,x)) */
+  float domain[3];    /* domain size in the same order (dim==2: domain[0] unused) */
+  float cell;         /* float32(domain[first]) / float32(res[first]) (transform.py:1328-1330) */
+  int32_t nsize;      /* neighbour half-width: (2 nsize+1)^dim target cells */
+  int32_t clip;       /* 1: clamp positions to [0,domain-1e-6]; 0: drop outliers (:1320-1325) */
+} LnstGrid;
+
+int lnst_abi_version(void);
+
+/* ---- particle -> grid (transform.py:1310-1453 p2g, :1577-1704 p2g_wavg) ------------------ */
+/* SPH splat: out[cell] += scale * W(|x_p - x_cell|/h).  `disp` (may be NULL) is added to p
+ * (styler_3p.py:58).  With colours (pc != NULL, C channels, out is [cells,C]):
+ * out += scale*W*pc/pd (pd NULL => divide by rest_density).  `out` must be zeroed by the
+ * caller.  H axis is written flipped (:1404,:1452). */
+int lnst_splat_sph_fwd(const float* p, const float* disp, int64_t n, const LnstGrid* g, float h,
+                       float scale, const float* pc, const float* pd, int32_t C, float rest_density,
+                       float* out, void* stream);
+/* d loss / d p (normalised units) for the scalar SPH splat; g_p [n,dim] is overwritten. */
+int lnst_splat_sph_bwd_pos(const float* p, const float* disp, int64_t n, const LnstGrid* g, float h,
+                           float scale, const float* g_out, float* g_p, void* stream);
+/* d loss / d pc for the colour splat (styler_2p.py:74-75); g_pc [n,C] is overwritten. */
+int lnst_splat_sph_bwd_color(const float* p, int64_t n, const LnstGrid* g, float h, float scale,
+                             const float* pd, int32_t C, float rest_density, const float* g_out,
+                             float* g_pc, void* stream);
+/* Weighted-average splat, nk kernels with support radii h[k] (styler_3p.py:79-87).
+ * wmap [nk,cells]: sum of weights (positions are constant in density mode => computed once). */
+int lnst_splat_wavg_wmap(const float* p, int64_t n, const LnstGrid* g, const float* h, int32_t nk,
+                         float* wmap, void* stream);
+/* out[cell] = sum_k where(wmap_k>1e-6, num_k/wmap_k, num_k), num_k = sum W_k (r_k + clip(var_k,-1,1)).
+ * `num` [nk,cells] is workspace (zeroed inside). */
+int lnst_splat_wavg_fwd(const float* p, const float* r, const float* var, int64_t n, const LnstGrid* g,
+                        const float* h, int32_t nk, const float* wmap, float* num, float* out,
+                        void* stream);
+/* g_var [n,nk] overwritten; reproduces TF's where/div NaN rule (transform.py:1703). */
+int lnst_splat_wavg_bwd(const float* p, const float* var, int64_t n, const LnstGrid* g, const float* h,
+                        int32_t nk, const float* wmap, const float* g_out, float* g_var, void* stream);
+
+/* ---- field post-processing (styler_3p.py:112-125: conv3d [1,k,1]^3/sum SAME + max(d,0)) -- */
+/* out = relu(smooth(in)); cells whose pre-activation is < 0 are stored as -0.0f so that the
+ * backward pass can apply TF's maximum() gradient rule (passes at equality) without a mask. */
+int lnst_smooth3_relu_fwd(const float* in, float* out, int32_t D, int32_t H, int32_t W, int32_t k,
+                          void* stream);
+int lnst_smooth3_relu_bwd(const float* g_out, const float* out, float* g_in, int32_t D, int32_t H,
+                          int32_t W, int32_t k, void* stream);
+
+/* ---- rotate + render (transform.py:611-628,343-433; styler_3p.py:148-158) ---------------- */
+/* rot: [n_views,9] row-major rotation matrices, or NULL for the unrotated render. */
+int lnst_rotate_fwd(const float* vol, const float* rot, int32_t n_views, int32_t D, int32_t H,
+                    int32_t W, float* out, void* stream);
+/* Fused rotate + emission/absorption ray-march.  img [n_views,H,W] = sum_i d_i T_i (smoke) or
+ * 1-exp(-tau sum d) (liquid); stot [n_views,H,W] = sum_i d_i (saved for the backward). */
+int lnst_raymarch_fwd(const float* vol, const float* rot, int32_t n_views, int32_t D, int32_t H,
+                      int32_t W, float tau, int32_t liquid, float* img, float* stot, void* stream);
+/* g_vol [D,H,W] += d loss/d vol from g_img [n_views,H,W] (accumulates: zero it first). */
+int lnst_raymarch_bwd(const float* vol, const float* rot, int32_t n_views, int32_t D, int32_t H,
+                      int32_t W, float tau, int32_t liquid, const float* stot, const float* g_img,
+                      float* g_vol, void* stream);
+
+/* ---- image glue (styler_3p.py:158; styler_base.py:33-45; vgg.py:50-53) -------------------- */
+/* stats[2*v+0] = max over image v, stats[2*v+1] = number of pixels attaining it. */
+int lnst_image_max(const float* img, int32_t n_img, int64_t n_pix, float* stats, void* stream);
+/* gray[v,p] = img[v,p] / max_v  (smoke normalisation, :158). */
+int lnst_normalize_fwd(const float* img, const float* stats, int32_t n_img, int64_t n_pix, float* gray,
+                       void* stream);
+/* g_img from g_gray incl. the reduce_max gradient (split evenly among ties); `dots`
+ * [n_img] is workspace. */
+int lnst_normalize_bwd(const float* img, const float* stats, const float* g_gray, int32_t n_img,
+                       int64_t n_pix, float* dots, float* g_img, void* stream);
+/* tf.compat.v1.image.resize(BILINEAR), legacy coordinates, C channels NHWC. */
+int lnst_resize_bilinear_fwd(const float* in, int32_t n_img, int32_t H, int32_t W, int32_t C,
+                             int32_t OH, int32_t OW, float* out, void* stream);
+int lnst_resize_bilinear_bwd(const float* g_out, int32_t n_img, int32_t H, int32_t W, int32_t C,
+                             int32_t OH, int32_t OW, float* g_in, void* stream);
+/* d_img[v,p,c] = s*gray[v,p,(c)] (gray has Cg = 1 or 3 channels), x = d_img - mean_rgb. */
+int lnst_to_net_input_fwd(const float* gray, int32_t n_img, int64_t n_pix, int32_t Cg, float s,
+                          float* d_img, float* x, void* stream);
+/* g_gray[v,p,(c)] = s * (sum over the replicated channels of g_x). */
+int lnst_to_net_input_bwd(const float* g_x, int32_t n_img, int64_t n_pix, int32_t Cg, float s,
+                          float* g_gray, void* stream);
+
+/* ---- loss network, CUDA-core fp32 path (vgg.py:68-113) ------------------------------------ */
+/* y = [relu](conv3x3_SAME(x, w) + b); x [n,H,W,Cin], w [3,3,Cin,Cout] (HWIO), y [n,H,W,Cout].
+ * mask (may be NULL): y *= (mask > 0) elementwise (fused ReLU backward for dgrad chains). */
+int lnst_conv3x3_f32(const float* x, const float* w, const float* b, const float* mask, float* y,
+                     int32_t n, int32_t H, int32_t W, int32_t Cin, int32_t Cout, int32_t relu,
+                     void* stream);
+int lnst_avgpool2_fwd(const float* x, float* y, int32_t n, int32_t H, int32_t W, int32_t C, void* stream);
+/* g_x = pool_bwd(g_y) * (mask > 0) (mask may be NULL). */
+int lnst_avgpool2_bwd(const float* g_y, const float* mask, float* g_x, int32_t n, int32_t H, int32_t W,
+                      int32_t C, void* stream);
+
+/* ---- losses (styler_base.py:96-102,135-185,211-213) --------------------------------------- */
+/* G [C,C] = F^T F / denom - Gs (the difference is what both the loss and its gradient need);
+ * loss[0] += weight * sum(G^2).  F [P,C].  Gs NULL => G = F^T F / denom (style-target pass). */
+int lnst_gram_diff(const float* F, int64_t P, int32_t C, float denom, const float* Gs, float weight,
+                   float* G, float* loss, void* stream);
+/* g_F = (beta*g_F + coef * F G) [* (F > 0) when relu_mask: F is a post-ReLU conv output and
+ * g_F becomes the gradient w.r.t. the pre-activation] */
+int lnst_gram_bwd(const float* F, const float* G, int64_t P, int32_t C, float coef, float beta,
+                  int32_t relu_mask, float* g_F, void* stream);
+/* content loss without target image (styler_base.py:143-148): loss[0] += weight*L and
+ * g_F = beta*g_F + weight * dL/dF [* (F > 0) when relu_mask]; g_F may be NULL. */
+int lnst_content_loss(const float* F, int64_t P, int32_t C, int32_t channel, float weight, float* loss,
+                      float* g_F, float beta, int32_t relu_mask, void* stream);
+/* anisotropic L1 total variation of d_img [H,W,C]; g_img overwritten with weight * d tv. */
+int lnst_tv_loss(const float* d_img, int32_t H, int32_t W, int32_t C, float weight, float* loss,
+                 float* g_img, void* stream);
+
+/* ---- optimiser + loop glue (styler_3p.py:320-363) ----------------------------------------- */
+/* TF-1.15 ApplyAdam with g = grad*gscale; var is passed through nan_to_num afterwards. */
+int lnst_adam_step(float* var, const float* grad, float* m, float* v, int64_t n, float lr_t, float beta1,
+                   float beta2, float eps, float gscale, void* stream);
+/* acc = (first ? 0 : acc) + nan_to_num(var) */
+int lnst_iterate_accumulate(float* acc, const float* var, int64_t n, int32_t first, void* stream);
+/* delta[i] = (nan_to_num(g_new[i]*scale) - g_opt[i]) * (mask ? mask[(i/width)*mask_stride] : 1) */
+int lnst_iterate_delta(const float* g_new, float scale, const float* g_opt, const float* mask,
+                       int32_t width, int32_t mask_stride, int64_t n, float* delta, void* stream);
+/* scipy.ndimage.gaussian_filter along the first axis of x [T,M] (mode reflect, truncate 4). */
+int lnst_temporal_gauss(const float* x, float* y, int32_t T, int64_t M, float sigma, void* stream);
+/* y += a*x */
+int lnst_axpy(float* y, const float* x, float a, int64_t n, void* stream);
+
+/* ---- semi-Lagrangian advection, order 1 (transform.py:557-609) ---------------------------- */
+/* d [X,Y,(Z),C], vel [X,Y,(Z),dim] in normalised units; dims[0..dim-1]. */
+int lnst_advect(const float* d, const float* vel, int32_t dim, const int32_t* dims, int32_t C, float* out,
+                void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LNST_B200_H */

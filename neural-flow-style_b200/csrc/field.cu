@@ -1,0 +1,102 @@
+// Field post-processing: 3x3x3 separable smoothing (SAME zero padding) fused with max(d,0)
+// (reference: styler_3p.py:112-125, executed there as tf.nn.conv3d + tf.maximum).
+//
+// One thread produces FOUR consecutive outputs along W from a 3 x 3 x 6 register window, so
+// each input row is read as part of a contiguous, coalesced segment and reused by the four
+// outputs; rows above/below come from L1/L2.  The sign bit of a zero output records
+// "pre-activation < 0" (stored as -0.0f) so the backward pass can apply TF's maximum()
+// gradient (which passes at equality) without a separate mask volume.
+#include "common.cuh"
+
+#define SM_VEC 4
+
+__device__ __forceinline__ float ld_or_zero(const float* __restrict__ v, int z, int y, int x, int D, int H,
+                                            int W) {
+  if (z < 0 || z >= D || y < 0 || y >= H || x < 0 || x >= W) return 0.f;
+  return v[((int64_t)z * H + y) * W + x];
+}
+
+// mode 0: out = relu(conv(in)) with signed zero; mode 1: g_in = conv(g_out * pass(out))
+template <int MODE>
+__global__ void smooth3_k(const float* __restrict__ in, const float* __restrict__ aux,
+                          float* __restrict__ out, int D, int H, int W, float w_side, float w_mid,
+                          int do_conv) {
+  const int xw = (W + SM_VEC - 1) / SM_VEC;
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = (int64_t)D * H * xw;
+  if (t >= total) return;
+  const int x0 = (int)(t % xw) * SM_VEC;
+  const int y = (int)((t / xw) % H);
+  const int z = (int)(t / ((int64_t)xw * H));
+  float acc[SM_VEC] = {0.f, 0.f, 0.f, 0.f};
+  const int r = do_conv ? 1 : 0;
+  for (int dz = -r; dz <= r; ++dz) {
+    const float wz = do_conv ? (dz == 0 ? w_mid : w_side) : 1.f;
+    for (int dy = -r; dy <= r; ++dy) {
+      const float wy = do_conv ? (dy == 0 ? w_mid : w_side) : 1.f;
+      float row[SM_VEC + 2];
+#pragma unroll
+      for (int j = 0; j < SM_VEC + 2; ++j) {
+        const int x = x0 - 1 + j;
+        float v = 0.f;
+        if (do_conv || (j >= 1 && j <= SM_VEC)) {
+          v = ld_or_zero(in, z + dz, y + dy, x, D, H, W);
+          if (MODE == 1 && v != 0.f) {
+            // backward: mask the incoming gradient by the forward pre-activation sign
+            const float o = ld_or_zero(aux, z + dz, y + dy, x, D, H, W);
+            if (__float_as_uint(o) >> 31) v = 0.f;   // pre-activation < 0 (stored as -0.0f)
+          }
+        }
+        row[j] = v;
+      }
+      const float wzy = wz * wy;
+#pragma unroll
+      for (int j = 0; j < SM_VEC; ++j) {
+        if (do_conv)
+          acc[j] += wzy * (w_side * row[j] + w_mid * row[j + 1] + w_side * row[j + 2]);
+        else
+          acc[j] += row[j + 1];
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < SM_VEC; ++j) {
+    const int x = x0 + j;
+    if (x < W) {
+      float v = acc[j];
+      if (MODE == 0) v = (v < 0.f) ? -0.0f : v;
+      out[((int64_t)z * H + y) * W + x] = v;
+    }
+  }
+}
+
+static inline void smooth_weights(int k, float& side, float& mid) {
+  // k1 = [1,k,1], K = k1 x k1 x k1 / sum(K) with sum(K) = (k+2)^3 (styler_3p.py:115-120)
+  const float s = (float)(k + 2);
+  side = 1.f / s;
+  mid = (float)k / s;
+}
+
+extern "C" int lnst_smooth3_relu_fwd(const float* in, float* out, int32_t D, int32_t H, int32_t W,
+                                     int32_t k, void* stream) {
+  if (!in || !out || D < 1 || H < 1 || W < 1) return LNST_EARG;
+  float side = 0.f, mid = 1.f;
+  if (k > 0) smooth_weights(k, side, mid);
+  const int64_t total = (int64_t)D * H * ((W + SM_VEC - 1) / SM_VEC);
+  auto kern = smooth3_k<0>;
+  LNST_LAUNCH(kern, dim3(lnst_blocks(total, 256)), dim3(256), 0, lnst_stream(stream), in,
+              (const float*)nullptr, out, (int)D, (int)H, (int)W, side, mid, (int)(k > 0));
+  return lnst_status();
+}
+
+extern "C" int lnst_smooth3_relu_bwd(const float* g_out, const float* out, float* g_in, int32_t D,
+                                     int32_t H, int32_t W, int32_t k, void* stream) {
+  if (!g_out || !out || !g_in || D < 1 || H < 1 || W < 1) return LNST_EARG;
+  float side = 0.f, mid = 1.f;
+  if (k > 0) smooth_weights(k, side, mid);
+  const int64_t total = (int64_t)D * H * ((W + SM_VEC - 1) / SM_VEC);
+  auto kern = smooth3_k<1>;
+  LNST_LAUNCH(kern, dim3(lnst_blocks(total, 256)), dim3(256), 0, lnst_stream(stream), g_out, out, g_in,
+              (int)D, (int)H, (int)W, side, mid, (int)(k > 0));
+  return lnst_status();
+}

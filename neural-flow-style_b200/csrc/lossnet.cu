@@ -1,0 +1,319 @@
+// Loss network (CUDA-core fp32 path) and the losses on its features.
+//   reference: vgg.py:68-113 (slim VGG: 3x3 SAME conv + bias + ReLU, 2x2/2 avg-pool),
+//              styler_base.py:96-102 (Gram), :152-185 (style loss), :135-148 (content),
+//              :211-213 (TV).
+// This file is the exact-arithmetic (fp32 FMA) implementation used for the tight parity
+// tests and as the numerical reference of the tcgen05 path (conv_tc.cu).  One tiled SGEMM
+// engine (64x64x16 tiles, 4x4 register micro-tiles) serves the implicit-GEMM convolution,
+// the Gram matrix (split-K) and the Gram gradient; they differ only in operand loaders and
+// epilogues.
+#include "common.cuh"
+
+#define GBM 64
+#define GBN 64
+#define GBK 16
+
+// ---- operand loaders: element (row, k) of A [M,K] and (k, col) of B [K,N] ---------------
+struct ConvA {            // im2col view of x [n,H,W,Cin]: row = pixel, k = (ky*3+kx)*Cin + ci
+  const float* x;
+  int H, W, Cin;
+  static constexpr bool kContigM = false;
+  __device__ __forceinline__ float operator()(int m, int k) const {
+    const int ci = k % Cin, tap = k / Cin;
+    const int ky = tap / 3, kx = tap - 3 * ky;
+    const int px = m % W, t = m / W;
+    const int py = t % H, img = t / H;
+    const int yy = py + ky - 1, xx = px + kx - 1;
+    if (yy < 0 || yy >= H || xx < 0 || xx >= W) return 0.f;
+    return x[(((int64_t)img * H + yy) * W + xx) * Cin + ci];
+  }
+};
+struct RowMajorA {        // A [M,K] row-major with leading dimension ld
+  const float* a;
+  int ld;
+  static constexpr bool kContigM = false;
+  __device__ __forceinline__ float operator()(int m, int k) const { return a[(int64_t)m * ld + k]; }
+};
+struct TransposedA {      // A = X^T where X [K,M] row-major (Gram: F^T)
+  const float* a;
+  int ld;
+  static constexpr bool kContigM = true;
+  __device__ __forceinline__ float operator()(int m, int k) const { return a[(int64_t)k * ld + m]; }
+};
+struct RowMajorB {
+  const float* b;
+  int ld;
+  __device__ __forceinline__ float operator()(int k, int n) const { return b[(int64_t)k * ld + n]; }
+};
+
+// ---- epilogues ---------------------------------------------------------------------------
+struct ConvEpilogue {     // y = [relu](acc + bias) [* (mask > 0)]
+  float* y;
+  const float* bias;
+  const float* mask;
+  int ld, relu;
+  __device__ __forceinline__ void operator()(int m, int n, float acc) const {
+    float v = acc + (bias ? bias[n] : 0.f);
+    if (relu) v = fmaxf(v, 0.f);
+    const int64_t o = (int64_t)m * ld + n;
+    if (mask && !(mask[o] > 0.f)) v = 0.f;
+    y[o] = v;
+  }
+};
+struct AtomicEpilogue {   // split-K accumulation
+  float* c;
+  int ld;
+  __device__ __forceinline__ void operator()(int m, int n, float acc) const {
+    atomicAdd(c + (int64_t)m * ld + n, acc);
+  }
+};
+struct GramBwdEpilogue {  // g = (beta*g + coef*acc) * (F > 0)
+  float* g;
+  const float* F;
+  int ld;
+  float coef, beta;
+  int relu_mask;
+  __device__ __forceinline__ void operator()(int m, int n, float acc) const {
+    const int64_t o = (int64_t)m * ld + n;
+    float v = coef * acc;
+    if (beta != 0.f) v += beta * g[o];
+    g[o] = (!relu_mask || F[o] > 0.f) ? v : 0.f;
+  }
+};
+
+template <class AL, class BL, class EP>
+__global__ void __launch_bounds__(256) sgemm_k(AL A, BL B, EP ep, int M, int N, int K, int k_per_split) {
+  __shared__ float As[GBK][GBM + 4];
+  __shared__ float Bs[GBK][GBN + 4];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.y * GBM, n0 = blockIdx.x * GBN;
+  const int kbeg = blockIdx.z * k_per_split;
+  const int kend = min(K, kbeg + k_per_split);
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = kbeg; k0 < kend; k0 += GBK) {
+#pragma unroll
+    for (int e = tid; e < GBM * GBK; e += 256) {
+      int mm, kk;
+      if (AL::kContigM) { mm = e % GBM; kk = e / GBM; } else { kk = e % GBK; mm = e / GBK; }
+      const int m = m0 + mm, k = k0 + kk;
+      As[kk][mm] = (m < M && k < kend) ? A(m, k) : 0.f;
+    }
+#pragma unroll
+    for (int e = tid; e < GBN * GBK; e += 256) {
+      const int nn = e % GBN, kk = e / GBN;
+      const int n = n0 + nn, k = k0 + kk;
+      Bs[kk][nn] = (n < N && k < kend) ? B(k, n) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < GBK; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n < N) ep(m, n, acc[i][j]);
+    }
+  }
+}
+
+template <class AL, class BL, class EP>
+static int run_sgemm(AL A, BL B, EP ep, int M, int N, int K, int splits, cudaStream_t s) {
+  if (M <= 0 || N <= 0 || K <= 0) return LNST_OK;
+  if (splits < 1) splits = 1;
+  int kps = (K + splits - 1) / splits;
+  kps = ((kps + GBK - 1) / GBK) * GBK;
+  splits = (K + kps - 1) / kps;
+  auto k = sgemm_k<AL, BL, EP>;
+  LNST_LAUNCH(k, dim3((N + GBN - 1) / GBN, (M + GBM - 1) / GBM, splits), dim3(256), 0, s, A, B, ep, M, N, K, kps);
+  return lnst_status();
+}
+
+// ---- pooling -----------------------------------------------------------------------------
+__global__ void avgpool2_fwd_k(const float* __restrict__ x, float* __restrict__ y, int n, int H, int W, int C) {
+  const int OH = H / 2, OW = W / 2;
+  const int64_t total = (int64_t)n * OH * OW * C;
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int c = (int)(t % C);
+  const int ox = (int)((t / C) % OW);
+  const int oy = (int)((t / ((int64_t)C * OW)) % OH);
+  const int img = (int)(t / ((int64_t)C * OW * OH));
+  const float* b = x + (((int64_t)img * H + 2 * oy) * W + 2 * ox) * C + c;
+  y[t] = (b[0] + b[C] + b[(int64_t)W * C] + b[(int64_t)W * C + C]) * 0.25f;
+}
+__global__ void avgpool2_bwd_k(const float* __restrict__ gy, const float* __restrict__ mask,
+                               float* __restrict__ gx, int n, int H, int W, int C) {
+  const int OH = H / 2, OW = W / 2;
+  const int64_t total = (int64_t)n * H * W * C;
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int c = (int)(t % C);
+  const int xx = (int)((t / C) % W);
+  const int yy = (int)((t / ((int64_t)C * W)) % H);
+  const int img = (int)(t / ((int64_t)C * W * H));
+  float g = 0.f;
+  const int oy = yy >> 1, ox = xx >> 1;
+  if (oy < OH && ox < OW) g = 0.25f * gy[(((int64_t)img * OH + oy) * OW + ox) * C + c];
+  if (mask && !(mask[t] > 0.f)) g = 0.f;
+  gx[t] = g;
+}
+
+// ---- losses ------------------------------------------------------------------------------
+// G = G/denom - Gs ; loss += weight * sum(G^2)
+__global__ void gram_finish_k(float* __restrict__ G, const float* __restrict__ Gs, int n, float inv_denom,
+                              float weight, float* __restrict__ loss) {
+  float s = 0.f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    float d = G[i] * inv_denom;
+    if (Gs) { d -= Gs[i]; s += d * d; }
+    G[i] = d;
+  }
+  s = lnst_warp_sum(s);
+  if (loss && Gs && (threadIdx.x & 31) == 0 && s != 0.f) atomicAdd(loss, weight * s);
+}
+
+// styler_base.py:143-148: -mean(f[...,c]) + mean|f[...,:c]| + mean|f[...,c+1:]|, or -mean(f)
+__global__ void content_loss_k(const float* __restrict__ F, int64_t P, int C, int channel, float weight,
+                               float* __restrict__ loss, float* __restrict__ gF, float beta, int relu_mask) {
+  const int64_t total = P * C;
+  float s = 0.f;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(t % C);
+    const float f = F[t];
+    float l, g;
+    if (channel == 0) {
+      l = -f / (float)total; g = -1.f / (float)total;
+    } else if (c == channel) {
+      l = -f / (float)P; g = -1.f / (float)P;
+    } else {
+      const float cnt = (c < channel) ? (float)P * (float)channel : (float)P * (float)(C - channel - 1);
+      l = fabsf(f) / cnt;
+      g = (f > 0.f ? 1.f : (f < 0.f ? -1.f : 0.f)) / cnt;
+    }
+    s += l;
+    if (gF) gF[t] = (beta != 0.f ? beta * gF[t] : 0.f) + ((!relu_mask || f > 0.f) ? weight * g : 0.f);
+  }
+  s = lnst_warp_sum(s);
+  if (loss && (threadIdx.x & 31) == 0) atomicAdd(loss, weight * s);
+}
+
+// tf.image.total_variation on one image [H,W,C]
+__global__ void tv_loss_k(const float* __restrict__ d, int H, int W, int C, float weight,
+                          float* __restrict__ loss, float* __restrict__ g) {
+  const int64_t total = (int64_t)H * W * C;
+  float s = 0.f;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const int x = (int)((t / C) % W), y = (int)(t / ((int64_t)C * W));
+    const float v = d[t];
+    float gr = 0.f;
+    if (y + 1 < H) { const float e = d[t + (int64_t)W * C] - v; s += fabsf(e); gr -= (e > 0.f) - (e < 0.f); }
+    if (x + 1 < W) { const float e = d[t + C] - v; s += fabsf(e); gr -= (e > 0.f) - (e < 0.f); }
+    if (y > 0) { const float e = v - d[t - (int64_t)W * C]; gr += (e > 0.f) - (e < 0.f); }
+    if (x > 0) { const float e = v - d[t - C]; gr += (e > 0.f) - (e < 0.f); }
+    if (g) g[t] = weight * gr;
+  }
+  s = lnst_warp_sum(s);
+  if (loss && (threadIdx.x & 31) == 0) atomicAdd(loss, weight * s);
+}
+
+// ---------------------------------------------------------------------------------------
+// C-ABI
+// ---------------------------------------------------------------------------------------
+extern "C" int lnst_conv3x3_f32(const float* x, const float* w, const float* b, const float* mask, float* y,
+                                int32_t n, int32_t H, int32_t W, int32_t Cin, int32_t Cout, int32_t relu,
+                                void* stream) {
+  if (!x || !w || !y || n < 1 || H < 1 || W < 1 || Cin < 1 || Cout < 1) return LNST_EARG;
+  if ((int64_t)n * H * W > 0x7fffffff) return LNST_EARG;
+  ConvA A{x, (int)H, (int)W, (int)Cin};
+  RowMajorB B{w, (int)Cout};
+  ConvEpilogue ep{y, b, mask, (int)Cout, (int)relu};
+  return run_sgemm(A, B, ep, n * H * W, Cout, 9 * Cin, 1, lnst_stream(stream));
+}
+
+extern "C" int lnst_avgpool2_fwd(const float* x, float* y, int32_t n, int32_t H, int32_t W, int32_t C,
+                                 void* stream) {
+  if (!x || !y || n < 1 || H < 2 || W < 2 || C < 1) return LNST_EARG;
+  const int64_t total = (int64_t)n * (H / 2) * (W / 2) * C;
+  LNST_LAUNCH(avgpool2_fwd_k, dim3(lnst_blocks(total, 256)), dim3(256), 0, lnst_stream(stream), x, y, (int)n,
+              (int)H, (int)W, (int)C);
+  return lnst_status();
+}
+
+extern "C" int lnst_avgpool2_bwd(const float* g_y, const float* mask, float* g_x, int32_t n, int32_t H,
+                                 int32_t W, int32_t C, void* stream) {
+  if (!g_y || !g_x || n < 1 || H < 2 || W < 2 || C < 1) return LNST_EARG;
+  const int64_t total = (int64_t)n * H * W * C;
+  LNST_LAUNCH(avgpool2_bwd_k, dim3(lnst_blocks(total, 256)), dim3(256), 0, lnst_stream(stream), g_y, mask, g_x,
+              (int)n, (int)H, (int)W, (int)C);
+  return lnst_status();
+}
+
+extern "C" int lnst_gram_diff(const float* F, int64_t P, int32_t C, float denom, const float* Gs, float weight,
+                              float* G, float* loss, void* stream) {
+  if (!F || !G || P < 1 || C < 1 || !(denom > 0.f) || P > 0x7fffffff) return LNST_EARG;
+  cudaStream_t s = lnst_stream(stream);
+  cudaMemsetAsync(G, 0, sizeof(float) * (int64_t)C * C, s);
+  TransposedA A{F, (int)C};
+  RowMajorB B{F, (int)C};
+  AtomicEpilogue ep{G, (int)C};
+  const int tiles = ((C + GBM - 1) / GBM) * ((C + GBN - 1) / GBN);
+  int splits = (2 * 148 + tiles - 1) / tiles;             // ~2 waves of CTAs over the 148 SMs
+  const int max_splits = (int)((P + 4 * GBK - 1) / (4 * GBK));
+  if (splits > max_splits) splits = max_splits;
+  int rc = run_sgemm(A, B, ep, C, C, (int)P, splits, s);
+  if (rc) return rc;
+  LNST_LAUNCH(gram_finish_k, dim3(lnst_blocks((int64_t)C * C, 256) > 64 ? 64 : lnst_blocks((int64_t)C * C, 256)),
+              dim3(256), 0, s, G, Gs, (int)(C * C), 1.f / denom, weight, loss);
+  return lnst_status();
+}
+
+extern "C" int lnst_gram_bwd(const float* F, const float* G, int64_t P, int32_t C, float coef, float beta,
+                             int32_t relu_mask, float* g_F, void* stream) {
+  if (!F || !G || !g_F || P < 1 || C < 1 || P > 0x7fffffff) return LNST_EARG;
+  RowMajorA A{F, (int)C};
+  RowMajorB B{G, (int)C};
+  GramBwdEpilogue ep{g_F, F, (int)C, coef, beta, (int)relu_mask};
+  return run_sgemm(A, B, ep, (int)P, C, C, 1, lnst_stream(stream));
+}
+
+extern "C" int lnst_content_loss(const float* F, int64_t P, int32_t C, int32_t channel, float weight,
+                                 float* loss, float* g_F, float beta, int32_t relu_mask, void* stream) {
+  if (!F || P < 1 || C < 1 || channel < 0 || channel >= C) return LNST_EARG;
+  const unsigned nb = lnst_blocks(P * C, 256) > 296 ? 296 : lnst_blocks(P * C, 256);
+  LNST_LAUNCH(content_loss_k, dim3(nb), dim3(256), 0, lnst_stream(stream), F, P, (int)C, (int)channel, weight,
+              loss, g_F, beta, (int)relu_mask);
+  return lnst_status();
+}
+
+extern "C" int lnst_tv_loss(const float* d_img, int32_t H, int32_t W, int32_t C, float weight, float* loss,
+                            float* g_img, void* stream) {
+  if (!d_img || H < 1 || W < 1 || C < 1) return LNST_EARG;
+  const int64_t total = (int64_t)H * W * C;
+  const unsigned nb = lnst_blocks(total, 256) > 296 ? 296 : lnst_blocks(total, 256);
+  LNST_LAUNCH(tv_loss_k, dim3(nb), dim3(256), 0, lnst_stream(stream), d_img, (int)H, (int)W, (int)C, weight, loss,
+              g_img);
+  return lnst_status();
+}

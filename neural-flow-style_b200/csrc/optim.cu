@@ -1,0 +1,163 @@
+// Optimiser and per-iteration glue of the stylisation loop, plus semi-Lagrangian advection.
+//   reference: TF-1.15 ApplyAdam as created at styler_3p.py:320-323 / styler_2p.py:251-254;
+//              iterate bookkeeping styler_3p.py:336-363; temporal smoothing :382-383
+//              (util.py:169-170 -> scipy.ndimage.gaussian_filter); advect transform.py:557-609.
+#include "common.cuh"
+
+// m += (g-m)(1-b1); v += (g^2-v)(1-b2); var -= lr_t m/(sqrt(v)+eps)   (eps outside the bias
+// correction, lr_t = lr sqrt(1-b2^t)/(1-b1^t) computed by the caller).  A NaN gradient keeps
+// m and v NaN for good; the variable itself goes through nan_to_num.
+__global__ void adam_step_k(float* __restrict__ var, const float* __restrict__ grad, float* __restrict__ m,
+                            float* __restrict__ v, int64_t n, float lr_t, float b1, float b2, float eps,
+                            float gscale) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float g = grad[i] * gscale;
+  const float mi = m[i] + (g - m[i]) * (1.f - b1);
+  const float vi = v[i] + (g * g - v[i]) * (1.f - b2);
+  m[i] = mi;
+  v[i] = vi;
+  var[i] = lnst_nan_to_num(var[i] - lr_t * mi / (sqrtf(vi) + eps));
+}
+
+__global__ void iterate_accumulate_k(float* __restrict__ acc, const float* __restrict__ var, int64_t n, int first) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float x = lnst_nan_to_num(var[i]);
+  acc[i] = first ? x : acc[i] + x;
+}
+
+__global__ void iterate_delta_k(const float* __restrict__ g_new, float scale, const float* __restrict__ g_opt,
+                                const float* __restrict__ mask, int width, int mask_stride, int64_t n,
+                                float* __restrict__ delta) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float d = lnst_nan_to_num(g_new[i] * scale) - g_opt[i];
+  if (mask) d *= mask[(i / width) * mask_stride];
+  delta[i] = d;
+}
+
+__global__ void axpy_k(float* __restrict__ y, const float* __restrict__ x, float a, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] += a * x[i];
+}
+
+// 1-D Gaussian along axis 0 of x [T,M]; scipy 'reflect' boundary (d c b a | a b c d | d c b a)
+#define LNST_MAX_GAUSS_RADIUS 64
+struct GaussTaps { int radius; float w[LNST_MAX_GAUSS_RADIUS + 1]; };
+__global__ void temporal_gauss_k(const float* __restrict__ x, float* __restrict__ y, int T, int64_t M, GaussTaps g) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= M) return;
+  const int t = blockIdx.y;
+  float s = 0.f;
+  for (int o = -g.radius; o <= g.radius; ++o) {
+    int q = t + o;
+    // reflect (half-sample symmetric), repeated for radii larger than T
+    while (q < 0 || q >= T) { if (q < 0) q = -q - 1; if (q >= T) q = 2 * T - 1 - q; }
+    s += g.w[o < 0 ? -o : o] * x[(int64_t)q * M + j];
+  }
+  y[(int64_t)t * M + j] = s;
+}
+
+// ---- advection -----------------------------------------------------------------------------
+struct AdvDims { int n[3]; float step[3]; int dim; };
+__global__ void advect_k(const float* __restrict__ d, const float* __restrict__ vel, AdvDims a, int C,
+                         float* __restrict__ out) {
+  const int64_t cells = (int64_t)a.n[0] * a.n[1] * (a.dim == 3 ? a.n[2] : 1);
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= cells) return;
+  int idx[3];
+  if (a.dim == 3) { idx[2] = (int)(t % a.n[2]); idx[1] = (int)((t / a.n[2]) % a.n[1]); idx[0] = (int)(t / ((int64_t)a.n[2] * a.n[1])); }
+  else { idx[1] = (int)(t % a.n[1]); idx[0] = (int)(t / a.n[1]); idx[2] = 0; }
+  int lo[3], hi[3];
+  float fr[3];
+  for (int k = 0; k < a.dim; ++k) {
+    const float g = __fadd_rn(-1.f, __fmul_rn(a.step[k], (float)idx[k])) - vel[t * a.dim + k];   // p' = p - v
+    const float x = (g + 1.f) * ((float)a.n[k] - 1.f) * 0.5f;
+    const int f = (int)floorf(x);
+    lo[k] = min(max(f, 0), a.n[k] - 1);
+    hi[k] = min(max(f + 1, 0), a.n[k] - 1);
+    fr[k] = x - (float)lo[k];
+  }
+  for (int c = 0; c < C; ++c) {
+    float o = 0.f;
+    for (int corner = 0; corner < (1 << a.dim); ++corner) {
+      int64_t lin = 0;
+      float w = 1.f;
+      for (int k = 0; k < a.dim; ++k) {
+        const int bit = (corner >> (a.dim - 1 - k)) & 1;
+        lin = lin * a.n[k] + (bit ? hi[k] : lo[k]);
+        w *= bit ? fr[k] : (1.f - fr[k]);
+      }
+      o += w * d[lin * C + c];
+    }
+    out[t * C + c] = o;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+extern "C" int lnst_abi_version(void) { return LNST_ABI_VERSION; }
+
+extern "C" int lnst_adam_step(float* var, const float* grad, float* m, float* v, int64_t n, float lr_t,
+                              float beta1, float beta2, float eps, float gscale, void* stream) {
+  if (!var || !grad || !m || !v || n < 0) return LNST_EARG;
+  if (n == 0) return LNST_OK;
+  LNST_LAUNCH(adam_step_k, dim3(lnst_blocks(n, 256)), dim3(256), 0, lnst_stream(stream), var, grad, m, v, n, lr_t,
+              beta1, beta2, eps, gscale);
+  return lnst_status();
+}
+
+extern "C" int lnst_iterate_accumulate(float* acc, const float* var, int64_t n, int32_t first, void* stream) {
+  if (!acc || !var || n < 0) return LNST_EARG;
+  if (n == 0) return LNST_OK;
+  LNST_LAUNCH(iterate_accumulate_k, dim3(lnst_blocks(n, 256)), dim3(256), 0, lnst_stream(stream), acc, var, n,
+              (int)first);
+  return lnst_status();
+}
+
+extern "C" int lnst_iterate_delta(const float* g_new, float scale, const float* g_opt, const float* mask,
+                                  int32_t width, int32_t mask_stride, int64_t n, float* delta, void* stream) {
+  if (!g_new || !g_opt || !delta || n < 0 || width < 1) return LNST_EARG;
+  if (n == 0) return LNST_OK;
+  LNST_LAUNCH(iterate_delta_k, dim3(lnst_blocks(n, 256)), dim3(256), 0, lnst_stream(stream), g_new, scale, g_opt,
+              mask, (int)width, (int)mask_stride, n, delta);
+  return lnst_status();
+}
+
+extern "C" int lnst_axpy(float* y, const float* x, float a, int64_t n, void* stream) {
+  if (!y || !x || n < 0) return LNST_EARG;
+  if (n == 0) return LNST_OK;
+  LNST_LAUNCH(axpy_k, dim3(lnst_blocks(n, 256)), dim3(256), 0, lnst_stream(stream), y, x, a, n);
+  return lnst_status();
+}
+
+extern "C" int lnst_temporal_gauss(const float* x, float* y, int32_t T, int64_t M, float sigma, void* stream) {
+  if (!x || !y || T < 1 || M < 1 || !(sigma > 0.f)) return LNST_EARG;
+  GaussTaps g;
+  g.radius = (int)(4.0 * (double)sigma + 0.5);           // scipy: int(truncate*sd + 0.5)
+  if (g.radius > LNST_MAX_GAUSS_RADIUS) return LNST_EARG;
+  double w[LNST_MAX_GAUSS_RADIUS + 1], sum = 0.0;
+  for (int i = 0; i <= g.radius; ++i) {
+    w[i] = exp(-0.5 * (double)i * (double)i / ((double)sigma * (double)sigma));
+    sum += (i == 0 ? 1.0 : 2.0) * w[i];
+  }
+  for (int i = 0; i <= LNST_MAX_GAUSS_RADIUS; ++i) g.w[i] = i <= g.radius ? (float)(w[i] / sum) : 0.f;
+  LNST_LAUNCH(temporal_gauss_k, dim3(lnst_blocks(M, 256), T), dim3(256), 0, lnst_stream(stream), x, y, (int)T, M, g);
+  return lnst_status();
+}
+
+extern "C" int lnst_advect(const float* d, const float* vel, int32_t dim, const int32_t* dims, int32_t C,
+                           float* out, void* stream) {
+  if (!d || !vel || !out || !dims || (dim != 2 && dim != 3) || C < 1) return LNST_EARG;
+  AdvDims a;
+  a.dim = dim;
+  int64_t cells = 1;
+  for (int k = 0; k < 3; ++k) {
+    a.n[k] = k < dim ? dims[k] : 1;
+    if (a.n[k] < 1) return LNST_EARG;
+    a.step[k] = a.n[k] > 1 ? 2.0f / (float)(a.n[k] - 1) : 0.f;
+    cells *= a.n[k];
+  }
+  LNST_LAUNCH(advect_k, dim3(lnst_blocks(cells, 256)), dim3(256), 0, lnst_stream(stream), d, vel, a, (int)C, out);
+  return lnst_status();
+}

@@ -1,0 +1,370 @@
+// Differentiable rotation + emission/absorption volume rendering, and the image glue between
+// the render and the loss network.
+//   reference: transform.py:611-628 (rotate), :343-433 (_interpolate3d), :152-177 (mgrid);
+//              styler_3p.py:148-158 (render, /max); styler_base.py:33-45 (resize, x255, RGB);
+//              vgg.py:50-53 (mean subtraction).
+// The rotated volume of the reference ([n_views,D,H,W], 32 MB per view at 200^3) is never
+// materialised: each ray samples the source volume while it marches.
+#include "common.cuh"
+
+struct VolDims {
+  int D, H, W;
+  float sD, sH, sW;   // linspace steps 2/(L-1) (0 when L == 1), transform.py:175
+};
+static inline VolDims make_dims(int D, int H, int W) {
+  VolDims v;
+  v.D = D; v.H = H; v.W = W;
+  v.sD = D > 1 ? 2.0f / (float)(D - 1) : 0.f;
+  v.sH = H > 1 ? 2.0f / (float)(H - 1) : 0.f;
+  v.sW = W > 1 ? 2.0f / (float)(W - 1) : 0.f;
+  return v;
+}
+
+__device__ __forceinline__ float lin_coord(int i, float step) {
+  return __fadd_rn(-1.f, __fmul_rn(step, (float)i));   // tf.linspace: start + step*i
+}
+
+struct Corner8 {
+  int z0, z1, y0, y1, x0, x1;
+  float fz, fy, fx;
+};
+
+// rotated sample position of lattice point (gd,gh,gw) -> clamped corner indices + fractions
+__device__ __forceinline__ Corner8 rotate_sample(const float* __restrict__ R, float gd, float gh, float gw,
+                                                 const VolDims& v) {
+  const float u0 = fmaf(R[2], gw, fmaf(R[1], gh, R[0] * gd));
+  const float u1 = fmaf(R[5], gw, fmaf(R[4], gh, R[3] * gd));
+  const float u2 = fmaf(R[8], gw, fmaf(R[7], gh, R[6] * gd));
+  const float z = (u0 + 1.f) * ((float)v.D - 1.f) * 0.5f;
+  const float y = (u1 + 1.f) * ((float)v.H - 1.f) * 0.5f;
+  const float x = (u2 + 1.f) * ((float)v.W - 1.f) * 0.5f;
+  Corner8 c;
+  const int zf = (int)floorf(z), yf = (int)floorf(y), xf = (int)floorf(x);
+  c.z0 = min(max(zf, 0), v.D - 1); c.z1 = min(max(zf + 1, 0), v.D - 1);
+  c.y0 = min(max(yf, 0), v.H - 1); c.y1 = min(max(yf + 1, 0), v.H - 1);
+  c.x0 = min(max(xf, 0), v.W - 1); c.x1 = min(max(xf + 1, 0), v.W - 1);
+  c.fz = z - (float)c.z0; c.fy = y - (float)c.y0; c.fx = x - (float)c.x0;
+  return c;
+}
+
+__device__ __forceinline__ float sample8(const float* __restrict__ vol, const Corner8& c, const VolDims& v) {
+  const int64_t HW = (int64_t)v.H * v.W;
+  const int64_t b00 = c.z0 * HW + (int64_t)c.y0 * v.W, b01 = c.z0 * HW + (int64_t)c.y1 * v.W;
+  const int64_t b10 = c.z1 * HW + (int64_t)c.y0 * v.W, b11 = c.z1 * HW + (int64_t)c.y1 * v.W;
+  const float gz = 1.f - c.fz, gy = 1.f - c.fy, gx = 1.f - c.fx;
+  float o = gz * gy * gx * vol[b00 + c.x0];
+  o += gz * gy * c.fx * vol[b00 + c.x1];
+  o += gz * c.fy * gx * vol[b01 + c.x0];
+  o += gz * c.fy * c.fx * vol[b01 + c.x1];
+  o += c.fz * gy * gx * vol[b10 + c.x0];
+  o += c.fz * gy * c.fx * vol[b10 + c.x1];
+  o += c.fz * c.fy * gx * vol[b11 + c.x0];
+  o += c.fz * c.fy * c.fx * vol[b11 + c.x1];
+  return o;
+}
+
+__device__ __forceinline__ void scatter8(float* __restrict__ gv, const Corner8& c, const VolDims& v, float g) {
+  const int64_t HW = (int64_t)v.H * v.W;
+  const int64_t b00 = c.z0 * HW + (int64_t)c.y0 * v.W, b01 = c.z0 * HW + (int64_t)c.y1 * v.W;
+  const int64_t b10 = c.z1 * HW + (int64_t)c.y0 * v.W, b11 = c.z1 * HW + (int64_t)c.y1 * v.W;
+  const float gz = 1.f - c.fz, gy = 1.f - c.fy, gx = 1.f - c.fx;
+  atomicAdd(gv + b00 + c.x0, g * (gz * gy * gx));
+  atomicAdd(gv + b00 + c.x1, g * (gz * gy * c.fx));
+  atomicAdd(gv + b01 + c.x0, g * (gz * c.fy * gx));
+  atomicAdd(gv + b01 + c.x1, g * (gz * c.fy * c.fx));
+  atomicAdd(gv + b10 + c.x0, g * (c.fz * gy * gx));
+  atomicAdd(gv + b10 + c.x1, g * (c.fz * gy * c.fx));
+  atomicAdd(gv + b11 + c.x0, g * (c.fz * c.fy * gx));
+  atomicAdd(gv + b11 + c.x1, g * (c.fz * c.fy * c.fx));
+}
+
+__global__ void rotate_fwd_k(const float* __restrict__ vol, const float* __restrict__ rot, VolDims v,
+                             float* __restrict__ out) {
+  const int64_t V = (int64_t)v.D * v.H * v.W;
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= V) return;
+  const int view = blockIdx.y;
+  const int w = (int)(t % v.W), h = (int)((t / v.W) % v.H), i = (int)(t / ((int64_t)v.W * v.H));
+  const Corner8 c = rotate_sample(rot + 9 * view, lin_coord(i, v.sD), lin_coord(h, v.sH), lin_coord(w, v.sW), v);
+  out[view * V + t] = sample8(vol, c, v);
+}
+
+// one thread per pixel column (view, h, w); marches from the camera side (high D) down
+__global__ void raymarch_fwd_k(const float* __restrict__ vol, const float* __restrict__ rot, VolDims v,
+                               float tau, int liquid, float* __restrict__ img, float* __restrict__ stot) {
+  const int P = v.H * v.W;
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= P) return;
+  const int view = blockIdx.y;
+  const int h = pix / v.W, w = pix % v.W;
+  const float* R = rot ? rot + 9 * view : nullptr;
+  const float gh = lin_coord(h, v.sH), gw = lin_coord(w, v.sW);
+  float S = 0.f, I = 0.f;
+  for (int i = v.D - 1; i >= 0; --i) {
+    float d;
+    if (R) {
+      const Corner8 c = rotate_sample(R, lin_coord(i, v.sD), gh, gw, v);
+      d = sample8(vol, c, v);
+    } else {
+      d = vol[(int64_t)i * P + pix];
+    }
+    S += d;                                     // inclusive reverse cumsum, styler_3p.py:155
+    if (!liquid) I += d * expf(-S * tau);
+  }
+  if (liquid) I = 1.f - expf(-S * tau);         // styler_3p.py:150-152
+  img[(int64_t)view * P + pix] = I;
+  stot[(int64_t)view * P + pix] = S;
+}
+
+// d I / d d_k = T_k - tau * sum_{i<=k} d_i T_i  (smoke);  tau * exp(-tau * S_total) (liquid)
+__global__ void raymarch_bwd_k(const float* __restrict__ vol, const float* __restrict__ rot, VolDims v,
+                               float tau, int liquid, const float* __restrict__ stot,
+                               const float* __restrict__ g_img, float* __restrict__ g_vol, int use_atomic) {
+  const int P = v.H * v.W;
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= P) return;
+  const int view = blockIdx.y;
+  const int h = pix / v.W, w = pix % v.W;
+  const float* R = rot ? rot + 9 * view : nullptr;
+  const float gI = g_img[(int64_t)view * P + pix];
+  const float St = stot[(int64_t)view * P + pix];
+  if (gI == 0.f) return;
+  const float gh = lin_coord(h, v.sH), gw = lin_coord(w, v.sW);
+  const float gl = liquid ? gI * tau * expf(-St * tau) : 0.f;
+  float below = 0.f, Pk = 0.f;
+  for (int i = 0; i < v.D; ++i) {
+    Corner8 c;
+    float d;
+    if (R) {
+      c = rotate_sample(R, lin_coord(i, v.sD), gh, gw, v);
+      d = liquid ? 0.f : sample8(vol, c, v);
+    } else {
+      d = liquid ? 0.f : vol[(int64_t)i * P + pix];
+    }
+    float g;
+    if (liquid) {
+      g = gl;
+    } else {
+      const float T = expf(-(St - below) * tau);
+      Pk += d * T;
+      below += d;
+      g = gI * (T - tau * Pk);
+    }
+    if (R) scatter8(g_vol, c, v, g);
+    else if (use_atomic) atomicAdd(g_vol + (int64_t)i * P + pix, g);
+    else g_vol[(int64_t)i * P + pix] += g;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// image glue
+// ---------------------------------------------------------------------------------------
+// stats[2v] = max (images are >= 0: int compare on the bit pattern is order preserving)
+__global__ void image_max_k(const float* __restrict__ img, int64_t n_pix, float* __restrict__ stats) {
+  const int view = blockIdx.y;
+  float m = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_pix; i += (int64_t)gridDim.x * blockDim.x)
+    m = fmaxf(m, img[view * n_pix + i]);
+  m = lnst_warp_max(m);
+  if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(stats + 2 * view), __float_as_int(m));
+}
+__global__ void image_ties_k(const float* __restrict__ img, int64_t n_pix, float* __restrict__ stats) {
+  const int view = blockIdx.y;
+  const float m = stats[2 * view];
+  float c = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_pix; i += (int64_t)gridDim.x * blockDim.x)
+    c += (img[view * n_pix + i] == m) ? 1.f : 0.f;
+  c = lnst_warp_sum(c);
+  if ((threadIdx.x & 31) == 0 && c != 0.f) atomicAdd(stats + 2 * view + 1, c);
+}
+__global__ void normalize_fwd_k(const float* __restrict__ img, const float* __restrict__ stats, int64_t n_pix,
+                                float* __restrict__ gray) {
+  const int view = blockIdx.y;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_pix) return;
+  gray[view * n_pix + i] = img[view * n_pix + i] / stats[2 * view];
+}
+__global__ void dot_k(const float* __restrict__ a, const float* __restrict__ b, int64_t n_pix,
+                      float* __restrict__ dots) {
+  const int view = blockIdx.y;
+  float s = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_pix; i += (int64_t)gridDim.x * blockDim.x)
+    s += a[view * n_pix + i] * b[view * n_pix + i];
+  s = lnst_warp_sum(s);
+  if ((threadIdx.x & 31) == 0) atomicAdd(dots + view, s);
+}
+// y = x/m: dL/dx_p = g_p/m - [x_p == m] * (sum_q g_q x_q) / m^2 / ties
+__global__ void normalize_bwd_k(const float* __restrict__ img, const float* __restrict__ stats,
+                                const float* __restrict__ g_gray, const float* __restrict__ dots,
+                                int64_t n_pix, float* __restrict__ g_img) {
+  const int view = blockIdx.y;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_pix) return;
+  const float m = stats[2 * view], ties = stats[2 * view + 1];
+  const float x = img[view * n_pix + i];
+  float g = g_gray[view * n_pix + i] / m;
+  if (x == m) g -= dots[view] / (m * m) / ties;
+  g_img[view * n_pix + i] = g;
+}
+
+// legacy bilinear: src = dst * in/out, lower = floor, upper = min(lower+1, in-1)
+__global__ void resize_fwd_k(const float* __restrict__ in, int H, int W, int C, int OH, int OW, float sy,
+                             float sx, float* __restrict__ out) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = (int64_t)OH * OW * C;
+  if (t >= total) return;
+  const int img = blockIdx.y;
+  const int c = (int)(t % C), ox = (int)((t / C) % OW), oy = (int)(t / ((int64_t)C * OW));
+  const float fy = (float)oy * sy, fx = (float)ox * sx;
+  const int y0 = min((int)floorf(fy), H - 1), x0 = min((int)floorf(fx), W - 1);
+  const int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
+  const float ly = fy - (float)y0, lx = fx - (float)x0;
+  const float* b = in + (int64_t)img * H * W * C;
+  const float tl = b[((int64_t)y0 * W + x0) * C + c], tr = b[((int64_t)y0 * W + x1) * C + c];
+  const float bl = b[((int64_t)y1 * W + x0) * C + c], br = b[((int64_t)y1 * W + x1) * C + c];
+  const float top = tl + (tr - tl) * lx, bot = bl + (br - bl) * lx;
+  out[(int64_t)img * total + t] = top + (bot - top) * ly;
+}
+__global__ void resize_bwd_k(const float* __restrict__ g_out, int H, int W, int C, int OH, int OW, float sy,
+                             float sx, float* __restrict__ g_in) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = (int64_t)OH * OW * C;
+  if (t >= total) return;
+  const int img = blockIdx.y;
+  const int c = (int)(t % C), ox = (int)((t / C) % OW), oy = (int)(t / ((int64_t)C * OW));
+  const float fy = (float)oy * sy, fx = (float)ox * sx;
+  const int y0 = min((int)floorf(fy), H - 1), x0 = min((int)floorf(fx), W - 1);
+  const int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
+  const float ly = fy - (float)y0, lx = fx - (float)x0;
+  const float g = g_out[(int64_t)img * total + t];
+  float* b = g_in + (int64_t)img * H * W * C;
+  atomicAdd(b + ((int64_t)y0 * W + x0) * C + c, g * (1.f - ly) * (1.f - lx));
+  atomicAdd(b + ((int64_t)y0 * W + x1) * C + c, g * (1.f - ly) * lx);
+  atomicAdd(b + ((int64_t)y1 * W + x0) * C + c, g * ly * (1.f - lx));
+  atomicAdd(b + ((int64_t)y1 * W + x1) * C + c, g * ly * lx);
+}
+
+__constant__ float kMeanRGB[3] = {(float)(0.485 * 255), (float)(0.456 * 255), (float)(0.406 * 255)};   // vgg.py:16-18
+
+__global__ void to_net_input_fwd_k(const float* __restrict__ gray, int64_t total_pix, int Cg, float s,
+                                   float* __restrict__ d_img, float* __restrict__ x) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total_pix) return;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float v = gray[i * Cg + (Cg == 1 ? 0 : c)] * s;
+    d_img[i * 3 + c] = v;
+    if (x) x[i * 3 + c] = v - kMeanRGB[c];
+  }
+}
+__global__ void to_net_input_bwd_k(const float* __restrict__ g_x, int64_t total_pix, int Cg, float s,
+                                   float* __restrict__ g_gray) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total_pix) return;
+  const float a = g_x[i * 3], b = g_x[i * 3 + 1], c = g_x[i * 3 + 2];
+  if (Cg == 1) {
+    g_gray[i] = (a + b + c) * s;
+  } else {
+    g_gray[i * 3] = a * s; g_gray[i * 3 + 1] = b * s; g_gray[i * 3 + 2] = c * s;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// C-ABI
+// ---------------------------------------------------------------------------------------
+extern "C" int lnst_rotate_fwd(const float* vol, const float* rot, int32_t n_views, int32_t D, int32_t H,
+                               int32_t W, float* out, void* stream) {
+  if (!vol || !rot || !out || n_views < 1 || D < 1 || H < 1 || W < 1) return LNST_EARG;
+  const VolDims v = make_dims(D, H, W);
+  const int64_t V = (int64_t)D * H * W;
+  LNST_LAUNCH(rotate_fwd_k, dim3(lnst_blocks(V, 256), n_views), dim3(256), 0, lnst_stream(stream), vol, rot,
+              v, out);
+  return lnst_status();
+}
+
+extern "C" int lnst_raymarch_fwd(const float* vol, const float* rot, int32_t n_views, int32_t D, int32_t H,
+                                 int32_t W, float tau, int32_t liquid, float* img, float* stot,
+                                 void* stream) {
+  if (!vol || !img || !stot || n_views < 1 || D < 1 || H < 1 || W < 1) return LNST_EARG;
+  if (!rot && n_views != 1) return LNST_EARG;
+  const VolDims v = make_dims(D, H, W);
+  LNST_LAUNCH(raymarch_fwd_k, dim3(lnst_blocks((int64_t)H * W, 128), n_views), dim3(128), 0,
+              lnst_stream(stream), vol, rot, v, tau, (int)liquid, img, stot);
+  return lnst_status();
+}
+
+extern "C" int lnst_raymarch_bwd(const float* vol, const float* rot, int32_t n_views, int32_t D, int32_t H,
+                                 int32_t W, float tau, int32_t liquid, const float* stot,
+                                 const float* g_img, float* g_vol, void* stream) {
+  if (!vol || !stot || !g_img || !g_vol || n_views < 1 || D < 1 || H < 1 || W < 1) return LNST_EARG;
+  if (!rot && n_views != 1) return LNST_EARG;
+  const VolDims v = make_dims(D, H, W);
+  LNST_LAUNCH(raymarch_bwd_k, dim3(lnst_blocks((int64_t)H * W, 128), n_views), dim3(128), 0,
+              lnst_stream(stream), vol, rot, v, tau, (int)liquid, stot, g_img, g_vol, 0);
+  return lnst_status();
+}
+
+extern "C" int lnst_image_max(const float* img, int32_t n_img, int64_t n_pix, float* stats, void* stream) {
+  if (!img || !stats || n_img < 1 || n_pix < 1) return LNST_EARG;
+  cudaMemsetAsync(stats, 0, sizeof(float) * 2 * n_img, lnst_stream(stream));
+  const unsigned nb = (unsigned)((n_pix + 1023) / 1024 > 64 ? 64 : (n_pix + 1023) / 1024);
+  LNST_LAUNCH(image_max_k, dim3(nb, n_img), dim3(256), 0, lnst_stream(stream), img, n_pix, stats);
+  LNST_LAUNCH(image_ties_k, dim3(nb, n_img), dim3(256), 0, lnst_stream(stream), img, n_pix, stats);
+  return lnst_status();
+}
+
+extern "C" int lnst_normalize_fwd(const float* img, const float* stats, int32_t n_img, int64_t n_pix,
+                                  float* gray, void* stream) {
+  if (!img || !stats || !gray || n_img < 1 || n_pix < 1) return LNST_EARG;
+  LNST_LAUNCH(normalize_fwd_k, dim3(lnst_blocks(n_pix, 256), n_img), dim3(256), 0, lnst_stream(stream), img,
+              stats, n_pix, gray);
+  return lnst_status();
+}
+
+extern "C" int lnst_normalize_bwd(const float* img, const float* stats, const float* g_gray, int32_t n_img,
+                                  int64_t n_pix, float* dots, float* g_img, void* stream) {
+  if (!img || !stats || !g_gray || !dots || !g_img || n_img < 1 || n_pix < 1) return LNST_EARG;
+  cudaMemsetAsync(dots, 0, sizeof(float) * n_img, lnst_stream(stream));
+  const unsigned nb = (unsigned)((n_pix + 1023) / 1024 > 64 ? 64 : (n_pix + 1023) / 1024);
+  LNST_LAUNCH(dot_k, dim3(nb, n_img), dim3(256), 0, lnst_stream(stream), g_gray, img, n_pix, dots);
+  LNST_LAUNCH(normalize_bwd_k, dim3(lnst_blocks(n_pix, 256), n_img), dim3(256), 0, lnst_stream(stream), img,
+              stats, g_gray, (const float*)dots, n_pix, g_img);
+  return lnst_status();
+}
+
+extern "C" int lnst_resize_bilinear_fwd(const float* in, int32_t n_img, int32_t H, int32_t W, int32_t C,
+                                        int32_t OH, int32_t OW, float* out, void* stream) {
+  if (!in || !out || n_img < 1 || H < 1 || W < 1 || C < 1 || OH < 1 || OW < 1) return LNST_EARG;
+  const float sy = (float)H / (float)OH, sx = (float)W / (float)OW;
+  LNST_LAUNCH(resize_fwd_k, dim3(lnst_blocks((int64_t)OH * OW * C, 256), n_img), dim3(256), 0,
+              lnst_stream(stream), in, (int)H, (int)W, (int)C, (int)OH, (int)OW, sy, sx, out);
+  return lnst_status();
+}
+
+extern "C" int lnst_resize_bilinear_bwd(const float* g_out, int32_t n_img, int32_t H, int32_t W, int32_t C,
+                                        int32_t OH, int32_t OW, float* g_in, void* stream) {
+  if (!g_out || !g_in || n_img < 1 || H < 1 || W < 1 || C < 1 || OH < 1 || OW < 1) return LNST_EARG;
+  const float sy = (float)H / (float)OH, sx = (float)W / (float)OW;
+  cudaMemsetAsync(g_in, 0, sizeof(float) * (int64_t)n_img * H * W * C, lnst_stream(stream));
+  LNST_LAUNCH(resize_bwd_k, dim3(lnst_blocks((int64_t)OH * OW * C, 256), n_img), dim3(256), 0,
+              lnst_stream(stream), g_out, (int)H, (int)W, (int)C, (int)OH, (int)OW, sy, sx, g_in);
+  return lnst_status();
+}
+
+extern "C" int lnst_to_net_input_fwd(const float* gray, int32_t n_img, int64_t n_pix, int32_t Cg, float s,
+                                     float* d_img, float* x, void* stream) {
+  if (!gray || !d_img || n_img < 1 || n_pix < 1 || (Cg != 1 && Cg != 3)) return LNST_EARG;
+  const int64_t total = (int64_t)n_img * n_pix;
+  LNST_LAUNCH(to_net_input_fwd_k, dim3(lnst_blocks(total, 256)), dim3(256), 0, lnst_stream(stream), gray,
+              total, (int)Cg, s, d_img, x);
+  return lnst_status();
+}
+
+extern "C" int lnst_to_net_input_bwd(const float* g_x, int32_t n_img, int64_t n_pix, int32_t Cg, float s,
+                                     float* g_gray, void* stream) {
+  if (!g_x || !g_gray || n_img < 1 || n_pix < 1 || (Cg != 1 && Cg != 3)) return LNST_EARG;
+  const int64_t total = (int64_t)n_img * n_pix;
+  LNST_LAUNCH(to_net_input_bwd_k, dim3(lnst_blocks(total, 256)), dim3(256), 0, lnst_stream(stream), g_x, total,
+              (int)Cg, s, g_gray);
+  return lnst_status();
+}

@@ -1,0 +1,407 @@
+// Particle -> grid splatting kernels (reference: transform.py:1233-1245 W, :1310-1453 p2g,
+// :1577-1704 p2g_wavg).  One thread per particle; the (2 nsize+1)^dim target cells are
+// visited in registers, the H axis is written flipped (transform.py:1404,1452).
+//
+// Arithmetic notes (parity with the fp32 oracle): the position -> (cell, offset) part uses
+// explicitly un-fused multiplies/adds (__fmul_rn/__fadd_rn) because a contracted FMA changes
+// the offset by up to one ulp of the (large) domain coordinate.
+#include "common.cuh"
+
+#define LNST_MAX_NK 4
+struct SplatKernels {
+  float h[LNST_MAX_NK];
+  float sigma[LNST_MAX_NK];
+};
+
+template <int DIM>
+struct Particle {
+  bool valid;
+  int idx[DIM];
+  float r[DIM];    // offset from the centre of the particle's own cell (domain units)
+  float dpd[DIM];  // d(domain coordinate)/d(normalised coordinate): domain, or 0 where clamped
+};
+
+template <int DIM>
+__device__ __forceinline__ Particle<DIM> load_particle(const float* __restrict__ p,
+                                                       const float* __restrict__ disp, int64_t i,
+                                                       const LnstGrid& g) {
+  Particle<DIM> o;
+  o.valid = true;
+  const int off = 3 - DIM;
+#pragma unroll
+  for (int a = 0; a < DIM; ++a) {
+    float pn = p[i * DIM + a];
+    if (disp != nullptr) pn = __fadd_rn(pn, disp[i * DIM + a]);
+    const float dom = g.domain[off + a];
+    float pd = __fmul_rn(pn, dom);
+    float gs = dom;
+    if (g.clip) {
+      const float hi = __fadd_rn(dom, -1e-6f);
+      if (pd < 0.f) { pd = 0.f; gs = 0.f; }
+      if (pd > hi) { pd = hi; gs = 0.f; }
+      if (pd != pd) o.valid = false;
+    } else if (!(pd >= 0.f && pd < dom)) {
+      o.valid = false;
+    }
+    const float f = floorf(pd / g.cell);
+    o.idx[a] = (int)f;
+    o.r[a] = __fadd_rn(pd, -__fmul_rn(f + 0.5f, g.cell));
+    o.dpd[a] = gs;
+  }
+  return o;
+}
+
+__device__ __forceinline__ float cubic_w(float q, float sigma) {
+  if (q > 1.f) return 0.f;
+  const float a = 6.f * (q * q * q - q * q) + 1.f;
+  const float omq = 1.f - q;
+  const float b = 2.f * omq * omq * omq;
+  return sigma * (q <= 0.5f ? a : b);
+}
+__device__ __forceinline__ float cubic_dw(float q, float sigma) {
+  if (q > 1.f) return 0.f;
+  const float omq = 1.f - q;
+  return sigma * (q <= 0.5f ? (18.f * q * q - 12.f * q) : (-6.f * omq * omq));
+}
+
+// Visit every in-range target cell of a particle: f(cell_linear_index_with_H_flip, d[DIM], |d|)
+template <int DIM, class F>
+__device__ __forceinline__ void for_each_target(const Particle<DIM>& pt, const LnstGrid& g, F f) {
+  const int ns = g.nsize;
+  const int H = g.res[1], W = g.res[2];
+  if (DIM == 3) {
+    const int D = g.res[0];
+    for (int sz = -ns; sz <= ns; ++sz) {
+      const int z = pt.idx[0] + sz;
+      const float dz = __fadd_rn(pt.r[0], -__fmul_rn((float)sz, g.cell));
+      for (int sy = -ns; sy <= ns; ++sy) {
+        const int y = pt.idx[1] + sy;
+        const float dy = __fadd_rn(pt.r[1], -__fmul_rn((float)sy, g.cell));
+        for (int sx = -ns; sx <= ns; ++sx) {
+          const int x = pt.idx[2] + sx;
+          if (z < 0 || z >= D || y < 0 || y >= H || x < 0 || x >= W) continue;
+          const float dx = __fadd_rn(pt.r[2], -__fmul_rn((float)sx, g.cell));
+          float d[3] = {dz, dy, dx};
+          const float len = sqrtf(dx * dx + dy * dy + dz * dz);
+          f(((int64_t)z * H + (H - 1 - y)) * W + x, d, len);
+        }
+      }
+    }
+  } else {
+    for (int sy = -ns; sy <= ns; ++sy) {
+      const int y = pt.idx[0] + sy;
+      const float dy = __fadd_rn(pt.r[0], -__fmul_rn((float)sy, g.cell));
+      for (int sx = -ns; sx <= ns; ++sx) {
+        const int x = pt.idx[1] + sx;
+        if (y < 0 || y >= H || x < 0 || x >= W) continue;
+        const float dx = __fadd_rn(pt.r[1], -__fmul_rn((float)sx, g.cell));
+        float d[3] = {dy, dx, 0.f};
+        const float len = sqrtf(dx * dx + dy * dy);
+        f((int64_t)(H - 1 - y) * W + x, d, len);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// SPH splat (p2g)
+// ---------------------------------------------------------------------------------------
+template <int DIM>
+__global__ void splat_sph_fwd_k(const float* __restrict__ p, const float* __restrict__ disp, int64_t n,
+                                LnstGrid g, float h, float sigma, float scale,
+                                const float* __restrict__ pc, const float* __restrict__ pd, int C,
+                                float rho, float* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const Particle<DIM> pt = load_particle<DIM>(p, disp, i, g);
+  if (!pt.valid) return;
+  const float inv_h = 1.f / h;
+  if (pc == nullptr) {
+    for_each_target<DIM>(pt, g, [&](int64_t cell, const float*, float len) {
+      const float w = cubic_w(len * inv_h, sigma);
+      if (w != 0.f) atomicAdd(out + cell, scale * w);
+    });
+  } else {
+    const float den = pd ? pd[i] : rho;
+    for_each_target<DIM>(pt, g, [&](int64_t cell, const float*, float len) {
+      const float w = cubic_w(len * inv_h, sigma);
+      if (w != 0.f)
+        for (int c = 0; c < C; ++c) atomicAdd(out + cell * C + c, scale * w * pc[i * C + c] / den);
+    });
+  }
+}
+
+template <int DIM>
+__global__ void splat_sph_bwd_pos_k(const float* __restrict__ p, const float* __restrict__ disp,
+                                    int64_t n, LnstGrid g, float h, float sigma, float scale,
+                                    const float* __restrict__ g_out, float* __restrict__ g_p) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const Particle<DIM> pt = load_particle<DIM>(p, disp, i, g);
+  float acc[3] = {0.f, 0.f, 0.f};
+  if (pt.valid) {
+    const float inv_h = 1.f / h;
+    for_each_target<DIM>(pt, g, [&](int64_t cell, const float* d, float len) {
+      if (len > 0.f) {   // sqrt'(0): TF gives NaN, defined as 0 here
+        const float dw = cubic_dw(len * inv_h, sigma);
+        const float c = g_out[cell] * scale * dw * inv_h / len;
+        acc[0] += c * d[0];
+        acc[1] += c * d[1];
+        acc[2] += c * d[2];
+      }
+    });
+  }
+#pragma unroll
+  for (int a = 0; a < DIM; ++a) g_p[i * DIM + a] = acc[a] * pt.dpd[a];
+}
+
+template <int DIM>
+__global__ void splat_sph_bwd_color_k(const float* __restrict__ p, int64_t n, LnstGrid g, float h,
+                                      float sigma, float scale, const float* __restrict__ pd, int C,
+                                      float rho, const float* __restrict__ g_out,
+                                      float* __restrict__ g_pc) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const Particle<DIM> pt = load_particle<DIM>(p, nullptr, i, g);
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  if (pt.valid) {
+    const float inv_h = 1.f / h;
+    const float den = pd ? pd[i] : rho;
+    for_each_target<DIM>(pt, g, [&](int64_t cell, const float*, float len) {
+      const float w = cubic_w(len * inv_h, sigma);
+      if (w != 0.f)
+        for (int c = 0; c < C; ++c) acc[c] += g_out[cell * C + c] * (scale * w / den);
+    });
+  }
+  for (int c = 0; c < C; ++c) g_pc[i * C + c] = acc[c];
+}
+
+// ---------------------------------------------------------------------------------------
+// weighted-average splat (p2g_wavg)
+// ---------------------------------------------------------------------------------------
+template <int DIM>
+__global__ void splat_wavg_wmap_k(const float* __restrict__ p, int64_t n, LnstGrid g, SplatKernels ks,
+                                  int nk, int64_t cells, float* __restrict__ wmap) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const Particle<DIM> pt = load_particle<DIM>(p, nullptr, i, g);
+  if (!pt.valid) return;
+  for_each_target<DIM>(pt, g, [&](int64_t cell, const float*, float len) {
+    for (int k = 0; k < nk; ++k) {
+      const float w = cubic_w(len / ks.h[k], ks.sigma[k]);
+      if (w != 0.f) atomicAdd(wmap + k * cells + cell, w);
+    }
+  });
+}
+
+template <int DIM>
+__global__ void splat_wavg_num_k(const float* __restrict__ p, const float* __restrict__ r,
+                                 const float* __restrict__ var, int64_t n, LnstGrid g, SplatKernels ks,
+                                 int nk, int64_t cells, float* __restrict__ num) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const Particle<DIM> pt = load_particle<DIM>(p, nullptr, i, g);
+  if (!pt.valid) return;
+  float x[LNST_MAX_NK];
+  for (int k = 0; k < nk; ++k) {
+    float v = var ? var[i * nk + k] : 0.f;
+    v = fminf(fmaxf(v, -1.f), 1.f);               // styler_3p.py:74
+    x[k] = r[i * nk + k] + v;                     // :76
+  }
+  for_each_target<DIM>(pt, g, [&](int64_t cell, const float*, float len) {
+    for (int k = 0; k < nk; ++k) {
+      const float w = cubic_w(len / ks.h[k], ks.sigma[k]);
+      if (w != 0.f) atomicAdd(num + k * cells + cell, w * x[k]);
+    }
+  });
+}
+
+__global__ void splat_wavg_combine_k(const float* __restrict__ wmap, const float* __restrict__ num,
+                                     int nk, int64_t cells, float* __restrict__ out) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cells) return;
+  float s = 0.f;
+  for (int k = 0; k < nk; ++k) {
+    const float w = wmap[k * cells + c];
+    const float v = num[k * cells + c];
+    s += (w > 1e-6f) ? v / w : v;                 // transform.py:1703
+  }
+  out[c] = s;
+}
+
+template <int DIM>
+__global__ void splat_wavg_bwd_k(const float* __restrict__ p, const float* __restrict__ var, int64_t n,
+                                 LnstGrid g, SplatKernels ks, int nk, int64_t cells,
+                                 const float* __restrict__ wmap, const float* __restrict__ g_out,
+                                 float* __restrict__ g_var) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const Particle<DIM> pt = load_particle<DIM>(p, nullptr, i, g);
+  float acc[LNST_MAX_NK] = {0.f, 0.f, 0.f, 0.f};
+  if (pt.valid) {
+    for_each_target<DIM>(pt, g, [&](int64_t cell, const float*, float len) {
+      const float go = g_out[cell];
+      for (int k = 0; k < nk; ++k) {
+        const float w = cubic_w(len / ks.h[k], ks.sigma[k]);
+        const float wm = wmap[k * cells + cell];
+        // gradient of where(wm>eps, num/wm, num) w.r.t. num as TF computes it: the untaken
+        // division branch contributes 0/wm, which is NaN when wm == 0 (transform.py:1703).
+        const float coef = (wm > 1e-6f) ? 1.f / wm : (wm == 0.f ? __int_as_float(0x7fc00000) : 1.f);
+        acc[k] += w * (coef * go);
+      }
+    });
+  }
+  for (int k = 0; k < nk; ++k) {
+    const float v = var ? var[i * nk + k] : 0.f;
+    const float pass = (v >= -1.f && v <= 1.f) ? 1.f : 0.f;   // clip_by_value gradient
+    g_var[i * nk + k] = (pass != 0.f) ? acc[k] : 0.f;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// C-ABI
+// ---------------------------------------------------------------------------------------
+static inline float sigma_for(int dim, float h) {
+  const double pi = 3.14159265358979323846;
+  return dim == 3 ? (float)(8.0 / pi / ((double)h * h * h)) : (float)(40.0 / 7.0 / pi / ((double)h * h));
+}
+static inline bool grid_ok(const LnstGrid* g) {
+  return g && (g->dim == 2 || g->dim == 3) && g->res[1] > 0 && g->res[2] > 0 &&
+         (g->dim == 2 || g->res[0] > 0) && g->cell > 0.f && g->nsize >= 0 && g->nsize <= 8;
+}
+static inline int64_t grid_cells(const LnstGrid* g) {
+  return (int64_t)(g->dim == 3 ? g->res[0] : 1) * g->res[1] * g->res[2];
+}
+static inline bool fill_kernels(SplatKernels& ks, int dim, const float* h, int nk) {
+  if (!h || nk < 1 || nk > LNST_MAX_NK) return false;
+  for (int k = 0; k < LNST_MAX_NK; ++k) {
+    ks.h[k] = k < nk ? h[k] : 1.f;
+    ks.sigma[k] = k < nk ? sigma_for(dim, h[k]) : 0.f;
+    if (!(ks.h[k] > 0.f)) return false;
+  }
+  return true;
+}
+
+extern "C" int lnst_splat_sph_fwd(const float* p, const float* disp, int64_t n, const LnstGrid* g,
+                                  float h, float scale, const float* pc, const float* pd, int32_t C,
+                                  float rest_density, float* out, void* stream) {
+  if (!grid_ok(g) || !p || !out || n < 0 || !(h > 0.f) || (pc && (C < 1 || C > 4))) return LNST_EARG;
+  if (n == 0) return LNST_OK;
+  const float sigma = sigma_for(g->dim, h);
+  const int T = 256;
+  if (g->dim == 3) {
+    auto k = splat_sph_fwd_k<3>;
+    LNST_LAUNCH(k, dim3(lnst_blocks(n, T)), dim3(T), 0, lnst_stream(stream), p, disp, n, *g, h, sigma,
+                scale, pc, pd, (int)C, rest_density, out);
+  } else {
+    auto k = splat_sph_fwd_k<2>;
+    LNST_LAUNCH(k, dim3(lnst_blocks(n, T)), dim3(T), 0, lnst_stream(stream), p, disp, n, *g, h, sigma,
+                scale, pc, pd, (int)C, rest_density, out);
+  }
+  return lnst_status();
+}
+
+extern "C" int lnst_splat_sph_bwd_pos(const float* p, const float* disp, int64_t n, const LnstGrid* g,
+                                      float h, float scale, const float* g_out, float* g_p,
+                                      void* stream) {
+  if (!grid_ok(g) || !p || !g_out || !g_p || n < 0 || !(h > 0.f)) return LNST_EARG;
+  if (n == 0) return LNST_OK;
+  const float sigma = sigma_for(g->dim, h);
+  const int T = 256;
+  if (g->dim == 3) {
+    auto k = splat_sph_bwd_pos_k<3>;
+    LNST_LAUNCH(k, dim3(lnst_blocks(n, T)), dim3(T), 0, lnst_stream(stream), p, disp, n, *g, h, sigma,
+                scale, g_out, g_p);
+  } else {
+    auto k = splat_sph_bwd_pos_k<2>;
+    LNST_LAUNCH(k, dim3(lnst_blocks(n, T)), dim3(T), 0, lnst_stream(stream), p, disp, n, *g, h, sigma,
+                scale, g_out, g_p);
+  }
+  return lnst_status();
+}
+
+extern "C" int lnst_splat_sph_bwd_color(const float* p, int64_t n, const LnstGrid* g, float h,
+                                        float scale, const float* pd, int32_t C, float rest_density,
+                                        const float* g_out, float* g_pc, void* stream) {
+  if (!grid_ok(g) || !p || !g_out || !g_pc || n < 0 || !(h > 0.f) || C < 1 || C > 4) return LNST_EARG;
+  if (n == 0) return LNST_OK;
+  const float sigma = sigma_for(g->dim, h);
+  const int T = 256;
+  if (g->dim == 3) {
+    auto k = splat_sph_bwd_color_k<3>;
+    LNST_LAUNCH(k, dim3(lnst_blocks(n, T)), dim3(T), 0, lnst_stream(stream), p, n, *g, h, sigma, scale,
+                pd, (int)C, rest_density, g_out, g_pc);
+  } else {
+    auto k = splat_sph_bwd_color_k<2>;
+    LNST_LAUNCH(k, dim3(lnst_blocks(n, T)), dim3(T), 0, lnst_stream(stream), p, n, *g, h, sigma, scale,
+                pd, (int)C, rest_density, g_out, g_pc);
+  }
+  return lnst_status();
+}
+
+extern "C" int lnst_splat_wavg_wmap(const float* p, int64_t n, const LnstGrid* g, const float* h,
+                                    int32_t nk, float* wmap, void* stream) {
+  SplatKernels ks;
+  if (!grid_ok(g) || !p || !wmap || n < 0 || !fill_kernels(ks, g ? g->dim : 3, h, nk)) return LNST_EARG;
+  const int64_t cells = grid_cells(g);
+  cudaMemsetAsync(wmap, 0, sizeof(float) * cells * nk, lnst_stream(stream));
+  if (n == 0) return lnst_status();
+  const int T = 256;
+  if (g->dim == 3) {
+    auto k = splat_wavg_wmap_k<3>;
+    LNST_LAUNCH(k, dim3(lnst_blocks(n, T)), dim3(T), 0, lnst_stream(stream), p, n, *g, ks, (int)nk, cells,
+                wmap);
+  } else {
+    auto k = splat_wavg_wmap_k<2>;
+    LNST_LAUNCH(k, dim3(lnst_blocks(n, T)), dim3(T), 0, lnst_stream(stream), p, n, *g, ks, (int)nk, cells,
+                wmap);
+  }
+  return lnst_status();
+}
+
+extern "C" int lnst_splat_wavg_fwd(const float* p, const float* r, const float* var, int64_t n,
+                                   const LnstGrid* g, const float* h, int32_t nk, const float* wmap,
+                                   float* num, float* out, void* stream) {
+  SplatKernels ks;
+  if (!grid_ok(g) || !p || !r || !wmap || !num || !out || n < 0 ||
+      !fill_kernels(ks, g ? g->dim : 3, h, nk))
+    return LNST_EARG;
+  const int64_t cells = grid_cells(g);
+  cudaMemsetAsync(num, 0, sizeof(float) * cells * nk, lnst_stream(stream));
+  const int T = 256;
+  if (n > 0) {
+    if (g->dim == 3) {
+      auto k = splat_wavg_num_k<3>;
+      LNST_LAUNCH(k, dim3(lnst_blocks(n, T)), dim3(T), 0, lnst_stream(stream), p, r, var, n, *g, ks,
+                  (int)nk, cells, num);
+    } else {
+      auto k = splat_wavg_num_k<2>;
+      LNST_LAUNCH(k, dim3(lnst_blocks(n, T)), dim3(T), 0, lnst_stream(stream), p, r, var, n, *g, ks,
+                  (int)nk, cells, num);
+    }
+  }
+  LNST_LAUNCH(splat_wavg_combine_k, dim3(lnst_blocks(cells, T)), dim3(T), 0, lnst_stream(stream), wmap,
+              (const float*)num, (int)nk, cells, out);
+  return lnst_status();
+}
+
+extern "C" int lnst_splat_wavg_bwd(const float* p, const float* var, int64_t n, const LnstGrid* g,
+                                   const float* h, int32_t nk, const float* wmap, const float* g_out,
+                                   float* g_var, void* stream) {
+  SplatKernels ks;
+  if (!grid_ok(g) || !p || !wmap || !g_out || !g_var || n < 0 || !fill_kernels(ks, g ? g->dim : 3, h, nk))
+    return LNST_EARG;
+  if (n == 0) return LNST_OK;
+  const int64_t cells = grid_cells(g);
+  const int T = 256;
+  if (g->dim == 3) {
+    auto k = splat_wavg_bwd_k<3>;
+    LNST_LAUNCH(k, dim3(lnst_blocks(n, T)), dim3(T), 0, lnst_stream(stream), p, var, n, *g, ks, (int)nk,
+                cells, wmap, g_out, g_var);
+  } else {
+    auto k = splat_wavg_bwd_k<2>;
+    LNST_LAUNCH(k, dim3(lnst_blocks(n, T)), dim3(T), 0, lnst_stream(stream), p, var, n, *g, ks, (int)nk,
+                cells, wmap, g_out, g_var);
+  }
+  return lnst_status();
+}

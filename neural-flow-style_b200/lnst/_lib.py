@@ -1,0 +1,163 @@
+"""ctypes binding of ``liblnst_b200.so`` (the C-ABI declared in ``include/lnst_b200.h``).
+
+This is the only place the native library is loaded.  There is NO fallback: if the CUDA
+library is missing or no CUDA device is present the engine raises.  (Tests that exercise the
+kernels through the CPU interpreter under ``tools/cpu_emu`` install it explicitly with
+``set_for_testing``; nothing in the package ever does.)
+"""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'liblnst_b200.so')
+
+i32, i64, f32, vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
+
+
+class LnstGrid(C.Structure):
+    _fields_ = [('dim', i32), ('res', i32 * 3), ('domain', f32 * 3), ('cell', f32), ('nsize', i32),
+                ('clip', i32)]
+
+
+GP = C.POINTER(LnstGrid)
+FP = C.POINTER(f32)      # host float array
+IP = C.POINTER(i32)      # host int array
+
+# name -> argtypes (return type is always int)
+SIGNATURES = {
+    'lnst_abi_version': [],
+    'lnst_splat_sph_fwd': [vp, vp, i64, GP, f32, f32, vp, vp, i32, f32, vp, vp],
+    'lnst_splat_sph_bwd_pos': [vp, vp, i64, GP, f32, f32, vp, vp, vp],
+    'lnst_splat_sph_bwd_color': [vp, i64, GP, f32, f32, vp, i32, f32, vp, vp, vp],
+    'lnst_splat_wavg_wmap': [vp, i64, GP, FP, i32, vp, vp],
+    'lnst_splat_wavg_fwd': [vp, vp, vp, i64, GP, FP, i32, vp, vp, vp, vp],
+    'lnst_splat_wavg_bwd': [vp, vp, i64, GP, FP, i32, vp, vp, vp, vp],
+    'lnst_smooth3_relu_fwd': [vp, vp, i32, i32, i32, i32, vp],
+    'lnst_smooth3_relu_bwd': [vp, vp, vp, i32, i32, i32, i32, vp],
+    'lnst_rotate_fwd': [vp, vp, i32, i32, i32, i32, vp, vp],
+    'lnst_raymarch_fwd': [vp, vp, i32, i32, i32, i32, f32, i32, vp, vp, vp],
+    'lnst_raymarch_bwd': [vp, vp, i32, i32, i32, i32, f32, i32, vp, vp, vp, vp],
+    'lnst_image_max': [vp, i32, i64, vp, vp],
+    'lnst_normalize_fwd': [vp, vp, i32, i64, vp, vp],
+    'lnst_normalize_bwd': [vp, vp, vp, i32, i64, vp, vp, vp],
+    'lnst_resize_bilinear_fwd': [vp, i32, i32, i32, i32, i32, i32, vp, vp],
+    'lnst_resize_bilinear_bwd': [vp, i32, i32, i32, i32, i32, i32, vp, vp],
+    'lnst_to_net_input_fwd': [vp, i32, i64, i32, f32, vp, vp, vp],
+    'lnst_to_net_input_bwd': [vp, i32, i64, i32, f32, vp, vp],
+    'lnst_conv3x3_f32': [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp],
+    'lnst_avgpool2_fwd': [vp, vp, i32, i32, i32, i32, vp],
+    'lnst_avgpool2_bwd': [vp, vp, vp, i32, i32, i32, i32, vp],
+    'lnst_gram_diff': [vp, i64, i32, f32, vp, f32, vp, vp, vp],
+    'lnst_gram_bwd': [vp, vp, i64, i32, f32, f32, i32, vp, vp],
+    'lnst_content_loss': [vp, i64, i32, i32, f32, vp, vp, f32, i32, vp],
+    'lnst_tv_loss': [vp, i32, i32, i32, f32, vp, vp, vp],
+    'lnst_adam_step': [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, vp],
+    'lnst_iterate_accumulate': [vp, vp, i64, i32, vp],
+    'lnst_iterate_delta': [vp, f32, vp, vp, i32, i32, i64, vp, vp],
+    'lnst_temporal_gauss': [vp, vp, i32, i64, f32, vp],
+    'lnst_axpy': [vp, vp, f32, i64, vp],
+    'lnst_advect': [vp, vp, i32, IP, i32, vp, vp],
+}
+# entry points that only exist in the CUDA build (tcgen05 / TMA); filled in by conv_tc.cu
+CUDA_ONLY = {
+    'lnst_tc_supported': [],
+    'lnst_conv3x3_bf16_tc': [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp],
+    'lnst_f32_to_bf16': [vp, vp, i64, vp],
+    'lnst_bf16_to_f32': [vp, vp, i64, vp],
+}
+
+
+class LnstError(RuntimeError):
+    pass
+
+
+class Lib:
+    """A loaded native library with typed entry points; ``kind`` is 'cuda' or 'emu'."""
+
+    def __init__(self, path, kind='cuda'):
+        if not os.path.exists(path):
+            raise LnstError('native library not found: %s (run __graft_entry__.build())' % path)
+        self.path, self.kind = path, kind
+        self.dll = C.CDLL(path)
+        self.launches = 0
+        for name, args in SIGNATURES.items():
+            fn = getattr(self.dll, name)
+            fn.argtypes = args
+            fn.restype = C.c_int
+        self.has_tc = False
+        if kind == 'cuda':
+            for name, args in CUDA_ONLY.items():
+                fn = getattr(self.dll, name)
+                fn.argtypes = args
+                fn.restype = C.c_int
+            self.has_tc = True
+        if self.dll.lnst_abi_version() != 1:
+            raise LnstError('ABI version mismatch in %s' % path)
+
+    def call(self, name, *args):
+        rc = getattr(self.dll, name)(*args)
+        self.launches += 1
+        if rc != 0:
+            what = 'bad argument' if rc < 0 else 'cudaError %d' % rc
+            raise LnstError('%s failed: %s' % (name, what))
+
+
+_lib = None
+
+
+def get():
+    """The CUDA library (loaded on first use).  Raises if it or a CUDA device is missing."""
+    global _lib
+    if _lib is None:
+        if not torch.cuda.is_available():
+            raise LnstError('lnst needs a CUDA device (sm_100a); there is no CPU fallback')
+        _lib = Lib(LIB_PATH, 'cuda')
+    return _lib
+
+
+def set_for_testing(lib):
+    """Install an explicit library handle (used by tests with the CPU interpreter)."""
+    global _lib
+    _lib = lib
+
+
+def stream_ptr(device):
+    if device.type != 'cuda':
+        return None
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def ptr(t):
+    """Device pointer of a contiguous fp32/bf16 tensor (None -> NULL)."""
+    if t is None:
+        return None
+    lib = get()
+    if lib.kind == 'cuda' and not t.is_cuda:
+        raise LnstError('CPU tensor passed to the CUDA library')
+    if lib.kind == 'emu' and t.is_cuda:
+        raise LnstError('CUDA tensor passed to the CPU interpreter')
+    if not t.is_contiguous():
+        raise LnstError('non-contiguous tensor')
+    return C.c_void_p(t.data_ptr())
+
+
+def make_grid(dim, res, domain, nsize, clip):
+    """LnstGrid from the reference's (domain, res) lists ((z,)y,x order, transform.py:1316-1330)."""
+    import numpy as np
+    g = LnstGrid()
+    g.dim = dim
+    res = [int(r) for r in res]
+    dom = [float(d) for d in domain]
+    if dim == 2:
+        res3, dom3 = [1] + res, [1.0] + dom
+    else:
+        res3, dom3 = res, dom
+    for a in range(3):
+        g.res[a] = res3[a]
+        g.domain[a] = dom3[a]
+    g.cell = float(np.float32(dom[0]) / np.float32(res[0]))
+    g.nsize = int(nsize)
+    g.clip = 1 if clip else 0
+    return g

@@ -1,0 +1,240 @@
+"""Tensor-level wrappers over the C-ABI (``_lib``): allocate outputs with torch, pass raw
+pointers + the current CUDA stream.  No arithmetic happens here."""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import ptr
+
+f32 = torch.float32
+
+
+def _s(t):
+    return _lib.stream_ptr(t.device)
+
+
+def _harr(vals):
+    return (C.c_float * len(vals))(*[float(v) for v in vals])
+
+
+def cells(grid):
+    return (grid.res[0] if grid.dim == 3 else 1) * grid.res[1] * grid.res[2]
+
+
+# ---- splats --------------------------------------------------------------------------------
+def splat_sph_fwd(p, disp, grid, h, scale, out=None, pc=None, pd=None, rest_density=1000.0):
+    n = p.shape[0]
+    ch = 1 if pc is None else pc.shape[-1]
+    shape = ([grid.res[0]] if grid.dim == 3 else []) + [grid.res[1], grid.res[2]] + ([ch] if pc is not None else [])
+    if out is None:
+        out = torch.zeros(shape, dtype=f32, device=p.device)
+    else:
+        out.zero_()
+    _lib.get().call('lnst_splat_sph_fwd', ptr(p), ptr(disp), n, C.byref(grid), h, scale, ptr(pc), ptr(pd), ch,
+                    rest_density, ptr(out), _s(p))
+    return out
+
+
+def splat_sph_bwd_pos(p, disp, grid, h, scale, g_out):
+    g_p = torch.empty_like(p)
+    _lib.get().call('lnst_splat_sph_bwd_pos', ptr(p), ptr(disp), p.shape[0], C.byref(grid), h, scale, ptr(g_out),
+                    ptr(g_p), _s(p))
+    return g_p
+
+
+def splat_sph_bwd_color(p, grid, h, scale, pd, ch, rest_density, g_out):
+    g_pc = torch.empty(p.shape[0], ch, dtype=f32, device=p.device)
+    _lib.get().call('lnst_splat_sph_bwd_color', ptr(p), p.shape[0], C.byref(grid), h, scale, ptr(pd), ch,
+                    rest_density, ptr(g_out), ptr(g_pc), _s(p))
+    return g_pc
+
+
+def splat_wavg_wmap(p, grid, hs):
+    wmap = torch.empty(len(hs), cells(grid), dtype=f32, device=p.device)
+    _lib.get().call('lnst_splat_wavg_wmap', ptr(p), p.shape[0], C.byref(grid), _harr(hs), len(hs), ptr(wmap), _s(p))
+    return wmap
+
+
+def splat_wavg_fwd(p, r, var, grid, hs, wmap, num, out):
+    _lib.get().call('lnst_splat_wavg_fwd', ptr(p), ptr(r), ptr(var), p.shape[0], C.byref(grid), _harr(hs), len(hs),
+                    ptr(wmap), ptr(num), ptr(out), _s(p))
+    return out
+
+
+def splat_wavg_bwd(p, var, grid, hs, wmap, g_out, g_var):
+    _lib.get().call('lnst_splat_wavg_bwd', ptr(p), ptr(var), p.shape[0], C.byref(grid), _harr(hs), len(hs),
+                    ptr(wmap), ptr(g_out), ptr(g_var), _s(p))
+    return g_var
+
+
+# ---- field ---------------------------------------------------------------------------------
+def smooth3_relu_fwd(d, out, k):
+    D, H, W = d.shape
+    _lib.get().call('lnst_smooth3_relu_fwd', ptr(d), ptr(out), D, H, W, int(k), _s(d))
+    return out
+
+
+def smooth3_relu_bwd(g_out, out, g_in, k):
+    D, H, W = out.shape
+    _lib.get().call('lnst_smooth3_relu_bwd', ptr(g_out), ptr(out), ptr(g_in), D, H, W, int(k), _s(out))
+    return g_in
+
+
+# ---- render --------------------------------------------------------------------------------
+def rotate_fwd(vol, rot):
+    D, H, W = vol.shape
+    nv = rot.shape[0]
+    out = torch.empty(nv, D, H, W, dtype=f32, device=vol.device)
+    _lib.get().call('lnst_rotate_fwd', ptr(vol), ptr(rot), nv, D, H, W, ptr(out), _s(vol))
+    return out
+
+
+def raymarch_fwd(vol, rot, tau, liquid, img, stot):
+    D, H, W = vol.shape
+    nv = 1 if rot is None else rot.shape[0]
+    _lib.get().call('lnst_raymarch_fwd', ptr(vol), ptr(rot), nv, D, H, W, float(tau), int(bool(liquid)), ptr(img),
+                    ptr(stot), _s(vol))
+    return img, stot
+
+
+def raymarch_bwd(vol, rot, tau, liquid, stot, g_img, g_vol):
+    D, H, W = vol.shape
+    nv = 1 if rot is None else rot.shape[0]
+    _lib.get().call('lnst_raymarch_bwd', ptr(vol), ptr(rot), nv, D, H, W, float(tau), int(bool(liquid)), ptr(stot),
+                    ptr(g_img), ptr(g_vol), _s(vol))
+    return g_vol
+
+
+def image_max(img, stats):
+    nv = img.shape[0]
+    _lib.get().call('lnst_image_max', ptr(img), nv, img[0].numel(), ptr(stats), _s(img))
+    return stats
+
+
+def normalize_fwd(img, stats, gray):
+    _lib.get().call('lnst_normalize_fwd', ptr(img), ptr(stats), img.shape[0], img[0].numel(), ptr(gray), _s(img))
+    return gray
+
+
+def normalize_bwd(img, stats, g_gray, dots, g_img):
+    _lib.get().call('lnst_normalize_bwd', ptr(img), ptr(stats), ptr(g_gray), img.shape[0], img[0].numel(),
+                    ptr(dots), ptr(g_img), _s(img))
+    return g_img
+
+
+def resize_bilinear_fwd(x, oh, ow):
+    n, H, W, ch = x.shape
+    out = torch.empty(n, oh, ow, ch, dtype=f32, device=x.device)
+    _lib.get().call('lnst_resize_bilinear_fwd', ptr(x), n, H, W, ch, oh, ow, ptr(out), _s(x))
+    return out
+
+
+def resize_bilinear_bwd(g_out, H, W):
+    n, oh, ow, ch = g_out.shape
+    g_in = torch.empty(n, H, W, ch, dtype=f32, device=g_out.device)
+    _lib.get().call('lnst_resize_bilinear_bwd', ptr(g_out), n, H, W, ch, oh, ow, ptr(g_in), _s(g_out))
+    return g_in
+
+
+def to_net_input_fwd(gray, s, d_img, x):
+    """gray [n,H,W,Cg] -> d_img, x [n,H,W,3]"""
+    n = gray.shape[0]
+    _lib.get().call('lnst_to_net_input_fwd', ptr(gray), n, gray[0].numel() // gray.shape[-1], gray.shape[-1],
+                    float(s), ptr(d_img), ptr(x), _s(gray))
+    return d_img, x
+
+
+def to_net_input_bwd(g_x, cg, s, g_gray):
+    n = g_x.shape[0]
+    _lib.get().call('lnst_to_net_input_bwd', ptr(g_x), n, g_x[0].numel() // 3, cg, float(s), ptr(g_gray), _s(g_x))
+    return g_gray
+
+
+# ---- loss net (fp32) -------------------------------------------------------------------------
+def conv3x3_f32(x, w, b, relu, mask=None, y=None):
+    n, H, W, cin = x.shape
+    cout = w.shape[-1]
+    if y is None:
+        y = torch.empty(n, H, W, cout, dtype=f32, device=x.device)
+    _lib.get().call('lnst_conv3x3_f32', ptr(x), ptr(w), ptr(b), ptr(mask), ptr(y), n, H, W, cin, cout, int(relu),
+                    _s(x))
+    return y
+
+
+def avgpool2_fwd(x, y=None):
+    n, H, W, ch = x.shape
+    if y is None:
+        y = torch.empty(n, H // 2, W // 2, ch, dtype=f32, device=x.device)
+    _lib.get().call('lnst_avgpool2_fwd', ptr(x), ptr(y), n, H, W, ch, _s(x))
+    return y
+
+
+def avgpool2_bwd(g_y, mask, shape, g_x=None):
+    n, H, W, ch = shape
+    if g_x is None:
+        g_x = torch.empty(n, H, W, ch, dtype=f32, device=g_y.device)
+    _lib.get().call('lnst_avgpool2_bwd', ptr(g_y), ptr(mask), ptr(g_x), n, H, W, ch, _s(g_y))
+    return g_x
+
+
+# ---- losses --------------------------------------------------------------------------------
+def gram_diff(F, denom, Gs, weight, G, loss):
+    """F [P,C] (one image).  G = F^T F/denom - Gs; loss += weight*sum(G^2)."""
+    P, ch = F.shape
+    _lib.get().call('lnst_gram_diff', ptr(F), P, ch, float(denom), ptr(Gs), float(weight), ptr(G), ptr(loss), _s(F))
+    return G
+
+
+def gram_bwd(F, G, coef, beta, relu_mask, g_F):
+    P, ch = F.shape
+    _lib.get().call('lnst_gram_bwd', ptr(F), ptr(G), P, ch, float(coef), float(beta), int(relu_mask), ptr(g_F), _s(F))
+    return g_F
+
+
+def content_loss(F, channel, weight, loss, g_F, beta, relu_mask):
+    P, ch = F.shape
+    _lib.get().call('lnst_content_loss', ptr(F), P, ch, int(channel), float(weight), ptr(loss), ptr(g_F), float(beta),
+                    int(relu_mask), _s(F))
+
+
+def tv_loss(d_img, weight, loss, g_img):
+    H, W, ch = d_img.shape
+    _lib.get().call('lnst_tv_loss', ptr(d_img), H, W, ch, float(weight), ptr(loss), ptr(g_img), _s(d_img))
+
+
+# ---- optimiser / glue ------------------------------------------------------------------------
+def adam_step(var, grad, m, v, lr_t, gscale=1.0, beta1=0.9, beta2=0.999, eps=1e-8):
+    _lib.get().call('lnst_adam_step', ptr(var), ptr(grad), ptr(m), ptr(v), var.numel(), float(lr_t), beta1, beta2,
+                    eps, float(gscale), _s(var))
+
+
+def iterate_accumulate(acc, var, first):
+    _lib.get().call('lnst_iterate_accumulate', ptr(acc), ptr(var), var.numel(), int(first), _s(var))
+
+
+def iterate_delta(g_new, scale, g_opt, mask, mask_stride, delta):
+    width = g_new.shape[-1]
+    _lib.get().call('lnst_iterate_delta', ptr(g_new), float(scale), ptr(g_opt), ptr(mask), width, int(mask_stride),
+                    g_new.numel(), ptr(delta), _s(g_new))
+    return delta
+
+
+def temporal_gauss(x, sigma):
+    """x [T, ...] -> gaussian_filter along axis 0"""
+    y = torch.empty_like(x)
+    _lib.get().call('lnst_temporal_gauss', ptr(x), ptr(y), x.shape[0], x[0].numel(), float(sigma), _s(x))
+    return y
+
+
+def axpy(y, x, a):
+    _lib.get().call('lnst_axpy', ptr(y), ptr(x), float(a), y.numel(), _s(y))
+
+
+def advect(d, vel):
+    """d [X,Y,(Z),C], vel [X,Y,(Z),dim] (normalised units)"""
+    dim = vel.shape[-1]
+    dims = (C.c_int32 * 3)(*([int(s) for s in d.shape[:dim]] + [1] * (3 - dim)))
+    out = torch.empty_like(d)
+    _lib.get().call('lnst_advect', ptr(d), ptr(vel), dim, dims, d.shape[-1], ptr(out), _s(d))
+    return out
