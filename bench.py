@@ -1,0 +1,382 @@
+#!/usr/bin/env python
+"""Style-optimisation iterations/sec on BASELINE.json's headline workload.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one pass of the reference's ``for step in range(iter)`` body (``styler_3p.py:301``)
+for one frame: 9 rotated views of a 200^3 smoke volume (N = 2^20 particles, 2 kernels,
+VGG-19 style loss on conv2_1 + conv3_1), mean view gradient, one Adam update
+(``view_mode='allreduce'``; views are sharded over the ranks and the particle gradient is
+all-reduced over NCCL).  Prints ONE JSON line (rank 0).  See DESIGN.md section "Measurement".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, 'neural-flow-style_b200'), os.path.join(ROOT, 'tests')):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+WORKLOADS = {
+    # name: (res, n_particles, rotate, n_views)
+    'C3': dict(res=200, n=1 << 20, rotate=True, n_views=9,
+               desc='smokegun-like 200^3, N=2^20 particles x 2 kernels, 9 rotated views, VGG-19 conv2_1+conv3_1'),
+    'C2': dict(res=128, n=1 << 18, rotate=False, n_views=1,
+               desc='smokegun-like 128^3, N=2^18 particles x 2 kernels, 1 view, VGG-19 conv2_1+conv3_1'),
+    'tiny': dict(res=32, n=1 << 13, rotate=True, n_views=9, desc='debug 32^3'),
+}
+KERNELS_PER_CALL = {'lnst_splat_wavg_fwd': 2, 'lnst_image_max': 2, 'lnst_normalize_bwd': 2, 'lnst_gram_diff': 2}
+TENSOR_BOUND = ('lnst_conv3x3_f32', 'lnst_conv3x3_bf16_tc', 'lnst_gram_diff', 'lnst_gram_bwd')
+
+
+def make_cfg(wl, view_mode, conv_math):
+    from helpers import smoke_cfg
+    w = WORKLOADS[wl]
+    return smoke_cfg(res=w['res'], iter=1, rotate=w['rotate'], n_views=w['n_views'], view_mode=view_mode,
+                     conv_math=conv_math, transmit=0.01, style_layer=['conv2_1', 'conv3_1'], w_style_layer=[0.5, 0.5])
+
+
+def make_scene(wl):
+    from lnst import synth
+    w = WORKLOADS[wl]
+    p, r = synth.smoke_particles(w['n'], 2, seed=123)
+    sty = synth.style_image(w['res'], w['res'])
+    return p, r, sty
+
+
+def algorithmic_units(name, a, nk=2):
+    """(bytes, flops) one launch of entry point ``name`` must move/compute (fp32; compulsory inputs
+    read once, outputs written once -- SURVEY.md section 8d; DESIGN.md 'Roofline model')."""
+    def v(x):
+        return x.value if hasattr(x, 'value') else x
+    if name in ('lnst_raymarch_fwd', 'lnst_raymarch_bwd'):
+        nv, D, H, W = [v(x) for x in a[2:6]]
+        V, P = D * H * W, H * W
+        return (nv * (4 * V + 8 * P), 0) if name.endswith('fwd') else (nv * (8 * V + 8 * P), 0)
+    if name in ('lnst_smooth3_relu_fwd', 'lnst_smooth3_relu_bwd'):
+        D, H, W = [v(x) for x in (a[2:5] if name.endswith('fwd') else a[3:6])]
+        return ((8 if name.endswith('fwd') else 12) * D * H * W, 0)
+    if name in ('lnst_splat_wavg_fwd', 'lnst_splat_wavg_bwd'):
+        n = v(a[3] if name.endswith('fwd') else a[2])
+        g = a[4] if name.endswith('fwd') else a[3]
+        g = g._obj
+        V = g.res[0] * g.res[1] * g.res[2]
+        return (n * (12 + 8 * nk) + 4 * V, 0)
+    if name == 'lnst_adam_step':
+        return (28 * v(a[4]), 0)
+    if name in ('lnst_conv3x3_f32', 'lnst_conv3x3_bf16_tc'):
+        n, H, W, ci, co = [v(x) for x in a[5:10]]
+        eb = 4 if name.endswith('f32') else 2
+        return (eb * n * H * W * (ci + co) + eb * 9 * ci * co, 2 * n * H * W * 9 * ci * co)
+    if name == 'lnst_gram_diff':
+        P, ch = v(a[1]), v(a[2])
+        return (4 * P * ch + 4 * ch * ch, 2 * P * ch * ch)
+    if name == 'lnst_gram_bwd':
+        P, ch = v(a[2]), v(a[3])
+        return (8 * P * ch + 4 * ch * ch, 2 * P * ch * ch)
+    return (0, 0)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(',')]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx = float(f[2])
+            except ValueError:
+                continue
+            for name, val in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[5:9]):
+                if val.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': mx, 'reasons': sorted(reasons),
+                'samples': len(sm)}
+
+
+def peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return p['hbm_gbs'], p.get('bf16_tflops_sustained', p['bf16_tflops']), 'measured'
+    return 6650.0, 1400.0, 'fallback'
+
+
+# ---------------------------------------------------------------------------------------------
+def run_engine(args):
+    import torch.distributed as dist
+    from lnst import _lib, ops, synth
+    from lnst.styler_3p import Styler, _Adam
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    dev = torch.device('cuda', local)
+    lib = _lib.get()
+    conv_math = args.conv_math or ('bf16' if lib.has_tc else 'fp32')
+    wl = args.workload
+    cfg = make_cfg(wl, args.view_mode, conv_math)
+    p, r, sty = make_scene(wl)
+    styler = Styler(cfg, weights=synth.vgg_weights(), device=dev)
+    styler.style_img = sty
+    res = [WORKLOADS[wl]['res']] * 3
+    ws = styler._workspace(res)
+    grams = styler._style_feature(sty, res[1:])
+    fr = {'id': 0, 'p': torch.tensor(p[0], device=dev), 'r': torch.tensor(r[0], device=dev)}
+    g_opt = torch.zeros(fr['p'].shape[0], 2, device=dev)
+    adam = _Adam()
+    lr = cfg.lr
+
+    def step():
+        var, loss, delta = styler.frame_step(fr, g_opt, adam, ws, grams, lr)
+        ops.axpy(g_opt, delta, 1.0)
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up; the last warm-up step is timed per entry point to find the dominant kernel ----
+    prof = {}
+    orig_call = lib.call
+
+    def profiling_call(name, *a):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        orig_call(name, *a)
+        e1.record()
+        prof.setdefault(name, []).append((e0, e1, algorithmic_units(name, a)))
+
+    for i in range(max(args.warmup, 3)):
+        if i == max(args.warmup, 3) - 1:
+            lib.call = profiling_call
+        step()
+    barrier()
+    lib.call = orig_call
+    table = {}
+    for name, evs in prof.items():
+        ms = [a.elapsed_time(b) for a, b, _ in evs]
+        table[name] = {'calls': len(ms), 'ms': float(sum(ms)), 'bytes': int(sum(u[0] for _, _, u in evs)),
+                       'flops': int(sum(u[1] for _, _, u in evs))}
+    dominant = max(table, key=lambda k: table[k]['ms'])
+
+    # ---- timed region: exactly K steps; only the dominant entry point carries events ------------
+    dom = []
+
+    def dominant_call(name, *a):
+        if name != dominant:
+            return orig_call(name, *a)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        orig_call(name, *a)
+        e1.record()
+        dom.append((e0, e1, algorithmic_units(name, a)))
+
+    lib.call = dominant_call
+    clocks = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        clocks.start()
+    launches0 = lib.launches
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(args.steps):
+        loss = step()
+    t1.record()
+    barrier()
+    clk = clocks.stop() if rank == 0 else None
+    lib.call = orig_call
+    ms_total = torch.tensor([t0.elapsed_time(t1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms_total, op=dist.ReduceOp.MAX)
+    ms_step = float(ms_total.item()) / args.steps
+    calls = lib.launches - launches0
+    kernel_launches = calls  # refined below with the per-call kernel counts
+    loss_val = float(loss)
+
+    # ---- end-to-end: host buffers in, host result out, every step (the reference's sess.run boundary) --
+    hp = torch.tensor(p[0]).pin_memory()
+    hr = torch.tensor(r[0]).pin_memory()
+    hg = torch.zeros(fr['p'].shape[0], 2).pin_memory()
+    hl = torch.zeros(1).pin_memory()
+    e2e_steps = max(3, min(args.steps, 10))
+    barrier()
+    w0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        fr['p'].copy_(hp, non_blocking=True)
+        fr['r'].copy_(hr, non_blocking=True)
+        g_opt.copy_(hg, non_blocking=True)
+        l = step()
+        hg.copy_(g_opt, non_blocking=True)
+        hl.copy_(l.reshape(1), non_blocking=True)
+        torch.cuda.synchronize()
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - w0], device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_val = e2e_steps / float(e2e_s.item())
+    h2d = hp.numel() * 4 + hr.numel() * 4 + hg.numel() * 4
+    d2h = hg.numel() * 4 + 4
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    hbm_peak, tf_peak, src = peaks()
+    dms = [a.elapsed_time(b) for a, b, _ in dom]
+    dbytes = sum(u[0] for _, _, u in dom) / max(len(dom), 1)
+    dflops = sum(u[1] for _, _, u in dom) / max(len(dom), 1)
+    avg_ms = sum(dms) / max(len(dms), 1)
+    if dominant in TENSOR_BOUND:
+        achieved = dflops / (avg_ms * 1e-3) / 1e12 if avg_ms else 0.0
+        roof = {'kernel': dominant, 'bound': 'tensor', 'achieved': achieved, 'peak': tf_peak, 'unit': 'TFLOP/s',
+                'frac': achieved / tf_peak}
+    else:
+        achieved = dbytes / (avg_ms * 1e-3) / 1e9 if avg_ms else 0.0
+        roof = {'kernel': dominant, 'bound': 'hbm', 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s',
+                'frac': achieved / hbm_peak}
+    roof.update({'traffic': None, 'peak_source': src, 'avg_launch_ms': avg_ms, 'launches_timed': len(dms),
+                 'share_of_step': sum(dms) / (ms_step * args.steps)})
+    per_step_calls = calls / args.steps
+    kl = 0
+    for name, t in table.items():
+        kl += t['calls'] * KERNELS_PER_CALL.get(name, 1)
+    out = {
+        'metric': 'style-opt iters/sec, 200^3 smoke x9 views', 'value': 1000.0 / ms_step, 'unit': 'iters/s',
+        'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms_step,
+        'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
+        'dtype': 'f32 (loss-net convolutions: %s)' % ('bf16 operands, f32 accumulate' if conv_math == 'bf16' else 'f32'),
+        'data': 'synthetic (seeded ellipsoid particle cloud, He-normal VGG-19 weights, low-pass noise style image)',
+        'config': {'workload': '%s: %s' % (wl, WORKLOADS[wl]['desc']), 'view_mode': args.view_mode,
+                   'conv_math': conv_math, 'views_per_rank': [len(range(k, WORKLOADS[wl]['n_views'], world)) for k in range(world)],
+                   'l2': 'per-step working set (8 volumes x %.0f MB + activations) exceeds the 126 MB L2; no flush'
+                         % (4e-6 * res[0] ** 3)},
+        'e2e': {'value': e2e_val, 'unit': 'iters/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                'steps': e2e_steps},
+        'gpu_launches': int(kl * args.steps), 'abi_calls_per_step': per_step_calls,
+        'clocks': clk, 'roofline': roof, 'final_loss': loss_val,
+        'kernel_table_ms_per_step': {k: round(v['ms'], 4) for k, v in sorted(table.items(), key=lambda kv: -kv[1]['ms'])},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        out['cpu_baseline'] = cpu_baseline(wl, budget_s=args.cpu_budget)
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------------------
+def cpu_baseline(wl, budget_s=25.0, steps=1, warmup=0):
+    """The oracle (CPU restatement of the reference's TF-1.15 graph) on this box's host cores.
+    One sample = ONE view of one iteration at full size (forward + backward + Adam); the
+    reference-exact iteration is n_views such passes (styler_3p.py:329-340)."""
+    import oracle.vgg
+    from oracle.styler import Oracle3P
+    from oracle.adam import TFAdam
+    torch.set_num_threads(os.cpu_count() or 1)
+    w = WORKLOADS[wl]
+    cfg = make_cfg(wl, 'sequential', 'fp32')
+    p, r, sty = make_scene(wl)
+    o = Oracle3P(cfg, oracle.vgg.synthetic_weights())
+    res = [w['res']] * 3
+    sf = o.style_features(sty)
+    pt, rt = torch.tensor(p[0]), torch.tensor(r[0])
+    var = torch.zeros(pt.shape[0], 2)
+    rot = o.views()[0] if w['rotate'] else None
+    adam = TFAdam()
+    times = []
+    t_all = time.perf_counter()
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        _, gr = o.loss_and_grad([pt], [rt], [var], res, rot[:1] if rot is not None else None, sf, None)
+        var = torch.nan_to_num(adam.step(var, gr[0], cfg.lr))
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+        if time.perf_counter() - t_all > budget_s and times:
+            break
+    t_view = float(np.mean(times))
+    return {'value': 1.0 / (t_view * w['n_views']), 'unit': 'iters/s', 'cores': torch.get_num_threads(),
+            'kind': 'port', 'seconds_per_view_pass': t_view, 'samples': len(times),
+            'sample': '%d x one view pass (fwd+bwd+Adam) of %s at full size; an iteration = %d such passes; '
+                      'PyTorch-CPU fp32 restatement of the TF-1.15 graph (TF itself cannot run here)'
+                      % (len(times), wl, w['n_views'])}
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    cb = cpu_baseline(args.workload, budget_s=args.cpu_budget * 4, steps=max(1, min(args.steps, 4)),
+                      warmup=1 if args.warmup else 0)
+    wl = args.workload
+    out = {'impl': 'reference', 'metric': 'style-opt iters/sec, 200^3 smoke x9 views', 'value': cb['value'],
+           'unit': 'iters/s', 'n_gpus': 0, 'steps': cb['samples'], 'warmup': 1 if args.warmup else 0,
+           'ms_per_step': 1000.0 / cb['value'], 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
+           'dtype': 'f32', 'data': 'synthetic (same seeded inputs as the engine arm)',
+           'config': {'workload': '%s: %s' % (wl, WORKLOADS[wl]['desc']), 'view_mode': 'sequential (reference semantics)'},
+           'cpu_baseline': cb,
+           'e2e': {'value': cb['value'], 'unit': 'iters/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='engine', choices=['engine', 'reference'])
+    ap.add_argument('--workload', default='C3', choices=list(WORKLOADS))
+    ap.add_argument('--view-mode', dest='view_mode', default='allreduce', choices=['allreduce', 'sequential'])
+    ap.add_argument('--conv-math', dest='conv_math', default=None, choices=['bf16', 'fp32'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--cpu-budget', type=float, default=25.0)
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_engine(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -87,7 +87,7 @@ class Lib:
             fn.argtypes = args
             fn.restype = C.c_int
         self.has_tc = False
-        if kind == 'cuda':
+        if kind == 'cuda' and hasattr(self.dll, 'lnst_tc_supported'):
             for name, args in CUDA_ONLY.items():
                 fn = getattr(self.dll, name)
                 fn.argtypes = args

@@ -1,0 +1,300 @@
+"""3-D particle styler -- drop-in for the reference's ``styler_3p.Styler`` (``styler_3p.py:14-438``).
+
+Same constructor / ``load_img`` / ``run(params)`` / result-dict contract; underneath, the TF graph
+and its three ``sess.run`` round trips per (frame, view, iteration) are replaced by a fixed
+sequence of sm_100a kernels on one stream.  Particle data, the optimisation variables, Adam
+moments and the loss history stay resident in HBM for the whole run; the host sees them
+once, at the end.
+
+Per (frame, view-batch) step:   var -> splat -> smooth+ReLU -> [rotate+]ray-march -> /max ->
+[resize] -> x255, RGB, -mean -> VGG fwd -> Gram/content/TV losses -> VGG dgrad -> ... -> d loss/d var
+-> [all-reduce over ranks] -> Adam.
+"""
+import numpy as np
+import torch
+
+from . import _lib, ops
+from .styler_base import StylerBase, f32
+from .transform import rot_mat
+from .util import octave_sizes
+
+
+class _Adam:
+    """Slots of one tf.compat.v1.train.AdamOptimizer (styler_3p.py:320-323): m, v per variable
+    and the fp32 beta-power accumulators, kept across frames of the group and across octaves."""
+
+    def __init__(self):
+        self.m = self.v = None
+        self.b1p, self.b2p = np.float32(0.9), np.float32(0.999)
+
+    def step(self, var, grad, lr, gscale=1.0):
+        if self.m is None:
+            self.m, self.v = torch.zeros_like(var), torch.zeros_like(var)
+        lr_t = np.float32(lr) * np.sqrt(np.float32(1) - self.b2p) / (np.float32(1) - self.b1p)
+        ops.adam_step(var, grad, self.m, self.v, float(lr_t), gscale)
+        self.b1p = np.float32(self.b1p * np.float32(0.9))
+        self.b2p = np.float32(self.b2p * np.float32(0.999))
+
+
+class Styler(StylerBase):
+    def __init__(self, self_dict, weights=None, device=None):
+        StylerBase.__init__(self, self_dict, weights=weights, device=device)
+        if self.target_field not in ('d', 'p'):
+            raise ValueError("styler_3p handles target_field 'd' or 'p'")
+        if 'd' in self.target_field and self.num_kernels > 4:
+            raise NotImplementedError('num_kernels > 4')
+        if self.style_mask:
+            raise NotImplementedError('style_mask (styler_base.py:165-173) is not built yet')
+        self.rot_mat_, self.views = None, None
+        if self.rotate:                                            # styler_3p.py:137-145
+            self.rot_mat_, self.views = rot_mat(self.phi0, self.phi1, self.phi_unit, self.theta0, self.theta1,
+                                                self.theta_unit, sample_type=self.sample_type, rng=self.rng,
+                                                nv=self.n_views)
+            if self.n_views is None:
+                self.n_views = len(self.views)
+            assert self.n_views % self.v_batch == 0
+            if self.v_batch != 1:
+                raise NotImplementedError('v_batch > 1 is not built (its loss ignores all but the first view, '
+                                          'styler_base.py:98)')
+        self._frame_cache = {}
+
+    # ---- geometry ------------------------------------------------------------------------------
+    def _grid(self, res):
+        return _lib.make_grid(3, res, self.domain, self.nsize, self.clip)
+
+    def _supports(self):
+        if 'd' in self.target_field:                               # styler_3p.py:80-81
+            return [self.radius * self.support / (self.kernel_scale ** k) for k in range(self.num_kernels)]
+        return [self.radius * self.support]
+
+    def _rot_tensor(self, mats):
+        return torch.tensor(np.asarray(mats, dtype=np.float64).reshape(-1, 9), dtype=f32, device=self.device)
+
+    # ---- forward pieces ------------------------------------------------------------------------
+    def _density(self, fr, var, res, ws):
+        """var -> density field d [D,H,W] (styler_3p.py:49-91)."""
+        grid = ws['grid']
+        if 'd' in self.target_field:
+            key = (fr['id'], tuple(res))
+            if key not in self._frame_cache:                       # positions are constant: W-sums once
+                self._frame_cache[key] = ops.splat_wavg_wmap(fr['p'], grid, self._supports())
+            wmap = self._frame_cache[key]
+            ops.splat_wavg_fwd(fr['p'], fr['r'], var, grid, self._supports(), wmap, ws['num'], ws['d'])
+        else:
+            scale = 0.8 * (2 * self.radius) ** 3 * self.rest_density / self.rest_density
+            ops.splat_sph_fwd(fr['p'], var, grid, self._supports()[0], scale, out=ws['d'])
+        return ws['d']
+
+    def _workspace(self, res):
+        D, H, W = res
+        dev = self.device
+        nk = self.num_kernels if 'd' in self.target_field else 1
+        return {'grid': self._grid(res), 'res': res,
+                'num': torch.empty(nk, D * H * W, dtype=f32, device=dev),
+                'd': torch.empty(D, H, W, dtype=f32, device=dev),
+                'ds': torch.empty(D, H, W, dtype=f32, device=dev),
+                'g_ds': torch.empty(D, H, W, dtype=f32, device=dev),
+                'g_d': torch.empty(D, H, W, dtype=f32, device=dev)}
+
+    def _render(self, ds, rot):
+        """ds [D,H,W] -> gray [nv,H,W,1] in [0,1] plus what the backward needs."""
+        D, H, W = ds.shape
+        nv = 1 if rot is None else rot.shape[0]
+        dev = self.device
+        img = torch.empty(nv, H, W, dtype=f32, device=dev)
+        stot = torch.empty(nv, H, W, dtype=f32, device=dev)
+        ops.raymarch_fwd(ds, rot, self.transmit, self.render_liquid, img, stot)
+        st = {'img': img, 'stot': stot, 'rot': rot}
+        if self.render_liquid:
+            gray = img
+        else:                                                     # styler_3p.py:158
+            st['stats'] = ops.image_max(img, torch.empty(2 * nv, dtype=f32, device=dev))
+            gray = ops.normalize_fwd(img, st['stats'], torch.empty_like(img))
+        gray = gray.reshape(nv, H, W, 1)
+        nh, nw = self._net_hw((H, W))
+        if (nh, nw) != (H, W):                                    # styler_base.py:35-38
+            gray = ops.resize_bilinear_fwd(gray, nh, nw)
+        d_img = torch.empty(nv, nh, nw, 3, dtype=f32, device=dev)
+        x = torch.empty(nv, nh, nw, 3, dtype=f32, device=dev)
+        ops.to_net_input_fwd(gray, 255.0, d_img, x)               # styler_base.py:41-45, vgg.py:50-53
+        st.update(d_img=d_img, x=x, hw=(H, W))
+        return st
+
+    def _render_bwd(self, st, g_x, ds, g_ds):
+        """d loss / d x -> accumulated into g_ds (which the caller zeroed)."""
+        nv = g_x.shape[0]
+        H, W = st['hw']
+        g_gray = ops.to_net_input_bwd(g_x, 1, 255.0, torch.empty(nv, g_x.shape[1], g_x.shape[2], 1, dtype=f32,
+                                                                  device=self.device))
+        if (g_x.shape[1], g_x.shape[2]) != (H, W):
+            g_gray = ops.resize_bilinear_bwd(g_gray, H, W)
+        g_gray = g_gray.reshape(nv, H, W)
+        if self.render_liquid:
+            g_img = g_gray
+        else:
+            g_img = ops.normalize_bwd(st['img'], st['stats'], g_gray, torch.empty(nv, dtype=f32, device=self.device),
+                                      torch.empty_like(g_gray))
+        ops.raymarch_bwd(ds, st['rot'], self.transmit, self.render_liquid, st['stot'], g_img, g_ds)
+
+    # ---- one loss + gradient evaluation (= one sess.run([train_op, total_loss]) without Adam) ----
+    def loss_and_grad(self, fr, var, ws, rot, style_grams):
+        """Sum over the given views of total_loss, and d(sum)/d var.  Returns (loss [nv], grad)."""
+        res = ws['res']
+        d = self._density(fr, var, res, ws)
+        ds = ops.smooth3_relu_fwd(d, ws['ds'], self.k)             # styler_3p.py:112-125
+        st = self._render(ds, rot)
+        nv = st['x'].shape[0]
+        loss = torch.zeros(nv, dtype=f32, device=self.device)
+        g_x = self.image_loss_and_grad(st['x'], st['d_img'], style_grams, loss)
+        g_ds = ws['g_ds'].zero_()
+        self._render_bwd(st, g_x, ds, g_ds)
+        g_d = ops.smooth3_relu_bwd(g_ds, ds, ws['g_d'], self.k)
+        if self.w_pressure > 0 and 'p' in self.target_field:       # styler_3p.py:96-98, styler_base.py:228-230
+            pos = d > 0
+            pr = torch.where(pos, d - 1, torch.zeros_like(d))
+            loss += self.w_pressure * (pr * pr).mean()
+            g_d += (nv * self.w_pressure * 2.0 / d.numel()) * pr
+        if 'd' in self.target_field:
+            key = (fr['id'], tuple(res))
+            grad = torch.empty_like(var)
+            ops.splat_wavg_bwd(fr['p'], var, ws['grid'], self._supports(), self._frame_cache[key], g_d, grad)
+            if self.w_density > 0:                                 # styler_base.py:217-223
+                dv = torch.clamp(var, -1, 1)
+                inside = ((var >= -1) & (var <= 1)).to(f32)
+                loss += self.w_density * (dv.sum() ** 2 + 1e3 * (-torch.log(dv.abs() + 1e-6)).sum())
+                grad += nv * self.w_density * inside * (2 * dv.sum() - 1e3 * torch.sign(dv) / (dv.abs() + 1e-6))
+        else:
+            scale = 0.8 * (2 * self.radius) ** 3 * self.rest_density / self.rest_density
+            grad = ops.splat_sph_bwd_pos(fr['p'], var, ws['grid'], self._supports()[0], scale, g_d)
+        return loss, grad
+
+    def infer(self, fr, var, ws, identity_view):
+        """Forward only: (p_out, d_out [D,H,W], d_img [H',W',3]) -- styler_3p.py:409-431."""
+        d = self._density(fr, var, ws['res'], ws)
+        ds = ops.smooth3_relu_fwd(d, ws['ds'], self.k)
+        rot = self._rot_tensor([np.identity(3)]) if identity_view else None
+        st = self._render(ds, rot)
+        p_out = fr['p'] + var if 'p' in self.target_field else fr['p']
+        return p_out, ds + 0.0, st['d_img'][0]                     # "+0.0" folds the -0.0 markers
+
+    # ---- one pass of the loop body for one frame (styler_3p.py:304-363) --------------------------
+    def frame_step(self, fr, g_opt_t, adam, ws, style_grams, lr):
+        """var <- g_opt[t]; Adam step(s) over the views; returns (var, loss, delta) with
+        delta = (nan_to_num(mean iterate) - g_opt[t]) [* r[:,0:1]].  Everything stays on device."""
+        dev = self.device
+        var = g_opt_t.clone()                                      # :312 (device copy, no H2D)
+        if self.rotate:
+            n_step_views = self.n_views // self.v_batch
+            if self.view_mode == 'sequential':                     # :329-340
+                acc = torch.empty_like(var)
+                losses = []
+                for i in range(0, self.n_views, self.v_batch):
+                    l, grad = self.loss_and_grad(fr, var, ws, self._rot_tensor(self.rot_mat_[i:i + 1]), style_grams)
+                    adam.step(var, grad, lr)
+                    ops.iterate_accumulate(acc, var, i == 0)
+                    losses.append(l)
+                loss_t = torch.cat(losses).mean()                  # :342
+                g_new, scale = acc, 1.0 / n_step_views             # :351-352
+            else:                                                  # mean view gradient, views sharded over ranks
+                mine = list(range(self.rank, self.n_views, self.world))
+                if mine:
+                    l, grad = self.loss_and_grad(fr, var, ws, self._rot_tensor([self.rot_mat_[i] for i in mine]),
+                                                 style_grams)
+                    lsum = l.sum().reshape(1)
+                else:
+                    grad, lsum = torch.zeros_like(var), torch.zeros(1, dtype=f32, device=dev)
+                if self.world > 1:
+                    torch.distributed.all_reduce(grad)
+                    torch.distributed.all_reduce(lsum)
+                adam.step(var, grad, lr, gscale=1.0 / self.n_views)
+                loss_t = lsum[0] / self.n_views
+                g_new, scale = var, 1.0
+            if 'uniform' not in self.sample_type:                  # :344-349
+                self.rot_mat_, self.views = rot_mat(self.phi0, self.phi1, self.phi_unit, self.theta0, self.theta1,
+                                                    self.theta_unit, sample_type=self.sample_type, rng=self.rng,
+                                                    nv=self.n_views)
+        else:                                                      # :354-357
+            l, grad = self.loss_and_grad(fr, var, ws, None, style_grams)
+            adam.step(var, grad, lr)
+            loss_t = l[0]
+            g_new, scale = var, 1.0
+        mask = fr['r'] if 'd' in self.target_field else None       # :359-363
+        delta = ops.iterate_delta(g_new, scale, g_opt_t, mask, self.num_kernels if mask is not None else 0,
+                                  torch.empty_like(var))
+        return var, loss_t, delta
+
+    # ---- the optimisation loop (styler_3p.py:229-438) ----------------------------------------------
+    def run(self, params):
+        dev = self.device
+        nf = self.num_frames
+        lr_list = None
+        if abs(self.lr_scale - 1) > 1e-7:                          # :237-238
+            lr_list = [self.lr / self.lr_scale ** i for i in range(self.octave_n)]
+        oct_size = octave_sizes(self.resolution, self.octave_n, self.octave_scale)
+
+        frames = []
+        for i in range(nf):
+            fr = {'id': i, 'p': torch.as_tensor(np.asarray(params['p'][i]), dtype=f32).to(dev).contiguous()}
+            if 'd' in self.target_field:
+                fr['r'] = torch.as_tensor(np.asarray(params['r'][i]), dtype=f32).to(dev).contiguous()
+            frames.append(fr)
+        width = 3 if 'p' in self.target_field else self.num_kernels
+        g_opt = [torch.zeros(fr['p'].shape[0], width, dtype=f32, device=dev) for fr in frames]
+        eye = True if self.rotate else False
+
+        loss_history, d_intm, opt_ = [], [], {}
+        for octave in range(self.octave_n):
+            res = oct_size[octave]
+            ws = self._workspace(res)
+            self._frame_cache = {}
+            style_grams = None
+            if self.w_style and self.style_img is not None:        # :281-286
+                style_grams = self._style_feature(self.style_img, res[1:])
+            lr = lr_list[octave] if lr_list is not None else (self.lr[octave] if isinstance(self.lr, list) else self.lr)
+            loss_o, intm_o = [], []
+            for step in range(self.iter):
+                deltas = {}
+                for t in range(0, nf, self.batch_size * self.interp):
+                    fr = frames[t]
+                    adam = opt_.setdefault(t // self.frames_per_opt, _Adam())   # :315-323
+                    var, loss_t, deltas[t] = self.frame_step(fr, g_opt[t], adam, ws, style_grams, lr)
+                    loss_o.append(loss_t)
+                    if step == self.iter - 1 and octave < self.octave_n - 1:   # :365-370
+                        _, _, d_img = self.infer(fr, var, ws, eye)
+                        intm_o.append(d_img)
+                key = list(range(0, nf, self.interp))
+                if self.window_sigma > 0 and nf > 1:               # :382-383
+                    sm = ops.temporal_gauss(torch.stack([deltas[t] for t in key], 0), self.window_sigma)
+                    for j, t in enumerate(key):
+                        deltas[t] = sm[j]
+                for t in key:                                      # :385-386
+                    ops.axpy(g_opt[t], deltas[t].contiguous(), 1.0)
+            loss_history.append([float(v) for v in torch.stack(loss_o).cpu().tolist()] if loss_o else [])
+            if octave < self.octave_n - 1:
+                d_intm.append(torch.stack(intm_o, 0).cpu().numpy().astype(np.uint8))
+
+        if self.interp > 1:                                        # :392-397
+            w = np.linspace(0, 1, self.interp + 1)
+            for t in range(0, nf - 1, self.interp):
+                for i in range(1, self.interp):
+                    g_opt[t + i] = g_opt[t] * float(1 - w[i]) + g_opt[t + self.interp] * float(w[i])
+
+        # final inference (:404-438)
+        result = {'l': loss_history, 'd_intm': d_intm, 'v': None, 'c': None}
+        res = oct_size[-1]
+        ws = self._workspace(res)
+        self._frame_cache = {}
+        p_sty, v_sty, d_sty, r_sty = [], [], [], []
+        for t in range(nf):
+            p_out, d_out, d_img = self.infer(frames[t], g_opt[t], ws, eye)
+            p_sty.append(p_out.cpu().numpy())
+            v_sty.append(g_opt[t].cpu().numpy())
+            d_sty.append(d_out.cpu().numpy()[..., None])
+            r_sty.append(d_img.cpu().numpy().astype(np.uint8))
+        result['p'] = p_sty
+        if 'p' in self.target_field:
+            result['v'] = v_sty
+        result['d'] = np.array(d_sty)
+        result['r'] = np.array(r_sty)
+        result['g_opt'] = [g.cpu().numpy() for g in g_opt]         # engine extra: final variables
+        return result

@@ -1,0 +1,163 @@
+"""StylerBase: what the 2-D and 3-D stylers share -- configuration copy, loss network, style /
+content targets and the feature-space losses (reference ``styler_base.py:11-345``).
+
+The reference builds a TF graph and lets autodiff produce d(loss)/d(image); here the same
+chain is an explicit sequence of kernel launches (``image_loss_and_grad``), all on one CUDA
+stream with no host synchronisation.
+"""
+import os
+
+import numpy as np
+import torch
+from PIL import Image
+
+from . import _lib, ops
+from .util import crop_ratio, resize
+from .vgg import LossNet, load_weights, model_name
+
+f32 = torch.float32
+
+
+class StylerBase(object):
+    def __init__(self, self_dict, weights=None, device=None):
+        # styler_base.py:14-15 -- every config attribute becomes an attribute of the styler
+        for arg in vars(self_dict):
+            setattr(self, arg, getattr(self_dict, arg))
+        if not hasattr(self, 'view_mode'):
+            self.view_mode = 'sequential'
+        if not hasattr(self, 'conv_math'):
+            self.conv_math = 'bf16'
+        lib = _lib.get()                          # raises without the CUDA library / a GPU
+        if device is None:
+            device = torch.device('cuda', torch.cuda.current_device()) if lib.kind == 'cuda' else torch.device('cpu')
+        self.device = torch.device(device)
+        self.model_path = os.path.join(self.data_dir, self.model_dir, self.network)   # :18
+        if 'vgg' not in self.model_path:
+            raise NotImplementedError(
+                'only the VGG loss networks are built (vgg.py); the inception5h GraphDef '
+                '(styler_base.py:19-31) is not in the reference repository')
+        if self.batch_size != 1:
+            raise NotImplementedError('batch_size > 1 is not built yet (every reference driver uses 1)')
+        if weights is None:
+            weights = load_weights(self.model_path, model_name(self.network))
+        self.net = LossNet(weights, model_name(self.network), self.device, math=self.conv_math)
+        self.content_img = None
+        self.style_img = None
+        self.rank, self.world = 0, 1
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            self.rank, self.world = torch.distributed.get_rank(), torch.distributed.get_world_size()
+
+    # ---- targets (styler_base.py:311-345) ------------------------------------------------------
+    def load_img(self, hw=None):
+        self.content_img = None
+        self.style_img = None
+        if self.w_content > 0 and self.content_target:
+            img = np.float32(Image.open(self.content_target))
+            if img.shape[-1] == 4:
+                img = img[..., :-1]
+            if hw is not None:
+                img = crop_ratio(img, hw[1] / hw[0])
+            self.content_img = img
+        if self.w_style > 0 and self.style_target:
+            img = np.float32(Image.open(self.style_target))
+            if self.style_tiling > 1:
+                img = np.tile(img, (self.style_tiling, self.style_tiling, 1))
+            if hw is not None:
+                img = crop_ratio(img, hw[1] / hw[0])
+            self.style_img = img
+
+    # ---- end points needed -----------------------------------------------------------------------
+    def _wanted(self):
+        w = []
+        if self.w_style and self.style_img is not None:
+            w += list(self.style_layer)
+        if self.w_content:
+            w.append(self.content_layer)
+        return w
+
+    def _net_hw(self, hw):
+        """Size of the image fed to the net for a render of size hw (styler_base.py:35-37)."""
+        if np.isclose(self.resize_scale, 1):
+            return int(hw[0]), int(hw[1])
+        s = np.float32(self.resize_scale)
+        return int(np.float32(hw[0]) * s), int(np.float32(hw[1]) * s)
+
+    def _target_tensor(self, img, hw):
+        """Style / content target resampled to the net input size (styler_base.py:257-262)."""
+        img = np.asarray(img, dtype=np.float32)
+        if img.shape[-1] == 4:                                  # :252-255
+            img = img[..., :-1] * (img[..., -1:] / 255)
+        img = resize(img, self._net_hw(hw), order=3)
+        x = torch.tensor(img, dtype=f32, device=self.device).reshape(1, img.shape[0], img.shape[1], 3)
+        mean = torch.tensor([0.485 * 255, 0.456 * 255, 0.406 * 255], dtype=f32, device=self.device)
+        return (x - mean).contiguous()
+
+    def _style_feature(self, style_target, style_shp):
+        """Gram matrices of the style target, one per style layer, already divided by
+        2*h*w*C (styler_base.py:157-162,178-179, 249-278).  Returned as device tensors."""
+        x = self._target_tensor(style_target, style_shp)
+        acts = self.net.forward(x, list(self.style_layer))
+        grams = []
+        for l in self.style_layer:
+            f = x[0] if 'input' in l else acts[l][0]
+            P, ch = f.shape[0] * f.shape[1], f.shape[2]
+            G = torch.empty(ch, ch, dtype=f32, device=self.device)
+            ops.gram_diff(f.reshape(P, ch), 2.0 * P * ch, None, 0.0, G, None)
+            grams.append(G)
+        return grams
+
+    def _content_feature(self, content_target, content_shp):
+        raise NotImplementedError('content target images (styler_base.py:233-247) are not built yet; '
+                                  'the channel-activation content loss (:143-148) is')
+
+    # ---- feature-space losses + their gradient w.r.t. the net input ---------------------------------
+    def image_loss_and_grad(self, x, d_img, style_grams, loss):
+        """x [n,H,W,3] net input (one image per view), d_img the same before mean subtraction.
+        Adds each image's total feature/TV loss into ``loss[v]`` and returns d loss_v / d x_v
+        stacked [n,H,W,3] (styler_base.py:127-213)."""
+        n = x.shape[0]
+        wanted = self._wanted()
+        style_on = bool(self.w_style) and style_grams is not None
+        acts = self.net.forward(x, wanted) if wanted else {}
+        diffs = {}
+        if style_on:
+            for li, l in enumerate(self.style_layer):
+                f = acts[l]
+                P, ch = f.shape[1] * f.shape[2], f.shape[3]
+                for v in range(n):
+                    G = torch.empty(ch, ch, dtype=f32, device=self.device)
+                    ops.gram_diff(f[v].reshape(P, ch), 2.0 * P * ch, style_grams[li],
+                                  self.w_style * self.w_style_layer[li], G, loss[v:v + 1])
+                    diffs[(l, v)] = G
+
+        def add_loss_grad(name, act, g):
+            is_conv = 1 if name.startswith('conv') else 0
+            P, ch = act.shape[1] * act.shape[2], act.shape[3]
+            if style_on:
+                for li, l in enumerate(self.style_layer):
+                    if l != name:
+                        continue
+                    beta = 1.0
+                    if g is None:
+                        g, beta = torch.empty_like(act), 0.0
+                    coef = self.w_style * self.w_style_layer[li] * 4.0 / (2.0 * P * ch)
+                    for v in range(n):
+                        ops.gram_bwd(act[v].reshape(P, ch), diffs[(l, v)], coef, beta, is_conv, g[v].reshape(P, ch))
+            if self.w_content and self.content_layer == name:
+                beta = 1.0
+                if g is None:
+                    g, beta = torch.empty_like(act), 0.0
+                for v in range(n):
+                    ops.content_loss(act[v].reshape(P, ch), self.content_channel, self.w_content,
+                                     loss[v:v + 1], g[v].reshape(P, ch), beta, is_conv)
+            return g
+
+        g_x = self.net.backward(x, acts, wanted, add_loss_grad) if wanted else None
+        if g_x is None:
+            g_x = torch.zeros_like(x)
+        if self.w_tv:
+            g_tv = torch.empty_like(d_img[0])
+            for v in range(n):
+                ops.tv_loss(d_img[v], self.w_tv, loss[v:v + 1], g_tv)
+                ops.axpy(g_x[v], g_tv, 1.0)
+        return g_x

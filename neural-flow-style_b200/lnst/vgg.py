@@ -1,0 +1,129 @@
+"""Loss network: slim-style VGG-16/19 with **average** pooling and post-ReLU end points
+(reference ``vgg.py:68-120``), forward + data-gradient only (the weights are frozen).
+
+Weights are in slim layout ``{'conv1_1': (w[3,3,Cin,Cout], b[Cout]), ...}``.  ``load_weights``
+reads them from ``<model_path>`` (an ``.npz`` with ``vgg_19/conv1/conv1_1/weights`` style keys, or
+plain ``conv1_1/weights``); the TF checkpoint itself cannot be parsed offline.
+
+Two arithmetic back ends share this class:
+  * ``fp32``  -- CUDA-core implicit-GEMM kernels (``csrc/lossnet.cu``), exact fp32 FMA;
+  * ``bf16``  -- tcgen05 tensor-core kernels (``csrc/conv_tc.cu``), bf16 operands / fp32 accumulate.
+"""
+import os
+
+import numpy as np
+import torch
+
+from . import ops
+
+# vgg.py:16-18
+_R_MEAN, _G_MEAN, _B_MEAN = 0.485 * 255, 0.456 * 255, 0.406 * 255
+
+_BLOCKS = {
+    'vgg_19': [(2, 64), (2, 128), (4, 256), (4, 512), (4, 512)],
+    'vgg_16': [(2, 64), (2, 128), (3, 256), (3, 512), (3, 512)],
+}
+
+
+def layer_order(model='vgg_19'):
+    """End points in network order: conv1_1, conv1_2, pool1, conv2_1, ..."""
+    out = []
+    for b, (rep, _) in enumerate(_BLOCKS[model], start=1):
+        out += ['conv%d_%d' % (b, i) for i in range(1, rep + 1)] + ['pool%d' % b]
+    return out
+
+
+def model_name(network):
+    return 'vgg_16' if '16' in os.path.basename(str(network)) else 'vgg_19'
+
+
+def load_weights(path, model='vgg_19'):
+    """Slim-layout weights from an .npz export of the slim checkpoint."""
+    if not os.path.exists(path):
+        alt = os.path.splitext(path)[0] + '.npz'
+        if not os.path.exists(alt):
+            raise FileNotFoundError(
+                'loss-network weights not found: %s (or %s).  Export vgg_19.ckpt to .npz with keys '
+                '"vgg_19/conv1/conv1_1/weights" or pass weights= to Styler.' % (path, alt))
+        path = alt
+    blob = np.load(path)
+    out = {}
+    for name in layer_order(model):
+        if not name.startswith('conv'):
+            continue
+        cands = ['%s/%s/%s' % (model, name.split('_')[0], name), name]
+        for c in cands:
+            if c + '/weights' in blob:
+                out[name] = (torch.tensor(blob[c + '/weights'], dtype=torch.float32),
+                             torch.tensor(blob[c + '/biases'], dtype=torch.float32))
+                break
+        else:
+            raise KeyError('no weights for %s in %s' % (name, path))
+    return out
+
+
+class LossNet:
+    """Forward/backward through the prefix of the network that the requested end points need."""
+
+    def __init__(self, weights, model, device, math='fp32'):
+        self.model, self.device, self.math = model, device, math
+        self.order = layer_order(model)
+        self.w, self.b, self.wd = {}, {}, {}
+        for name, (w, b) in weights.items():
+            w = w.to(device=device, dtype=torch.float32).contiguous()
+            self.w[name] = w
+            self.b[name] = b.to(device=device, dtype=torch.float32).contiguous()
+            # data-gradient weights: flip taps, swap in/out channels (HWIO with I=Cout, O=Cin)
+            self.wd[name] = w.flip(0, 1).permute(0, 1, 3, 2).contiguous()
+        if math == 'bf16':
+            from . import vgg_tc
+            self.tc = vgg_tc.TensorCoreConvs(self)
+        elif math != 'fp32':
+            raise ValueError('conv_math must be fp32 or bf16')
+
+    def prefix(self, wanted):
+        wanted = [w for w in wanted if w != 'input']
+        for w in wanted:
+            if w not in self.order:
+                raise KeyError('%s is not a %s end point' % (w, self.model))
+        last = max([self.order.index(w) for w in wanted]) if wanted else -1
+        return self.order[:last + 1]
+
+    # ---- forward ---------------------------------------------------------------------------
+    def forward(self, x, wanted):
+        """x [n,H,W,3] (mean-subtracted).  Returns {end point: activation [n,h,w,C] fp32}."""
+        if self.math == 'bf16':
+            return self.tc.forward(x, self.prefix(wanted))
+        acts = {}
+        cur = x
+        for name in self.prefix(wanted):
+            if name.startswith('conv'):
+                cur = ops.conv3x3_f32(cur, self.w[name], self.b[name], relu=True)
+            else:
+                cur = ops.avgpool2_fwd(cur)
+            acts[name] = cur
+        return acts
+
+    # ---- backward --------------------------------------------------------------------------
+    def backward(self, x, acts, wanted, add_loss_grad):
+        """d loss / d x.  ``add_loss_grad(name, act, g)`` adds the loss terms that live on end
+        point ``name`` into ``g`` (None = nothing accumulated yet; it must then allocate) and
+        returns the buffer (or None).  Gradients held for conv end points are w.r.t. the
+        PRE-activation (ReLU mask already applied)."""
+        if self.math == 'bf16':
+            return self.tc.backward(x, acts, self.prefix(wanted), add_loss_grad)
+        layers = self.prefix(wanted)
+        g = None
+        for i in range(len(layers) - 1, -1, -1):
+            name = layers[i]
+            g = add_loss_grad(name, acts[name], g)
+            if g is None:
+                continue
+            prev = layers[i - 1] if i > 0 else None
+            prev_act = acts[prev] if prev is not None else None
+            mask = prev_act if (prev is not None and prev.startswith('conv')) else None
+            if name.startswith('conv'):
+                g = ops.conv3x3_f32(g, self.wd[name], None, relu=False, mask=mask)
+            else:
+                g = ops.avgpool2_bwd(g, mask, prev_act.shape)
+        return g
