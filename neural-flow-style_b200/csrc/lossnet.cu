@@ -9,145 +9,7 @@
 // epilogues.
 #include "common.cuh"
 
-#define GBM 64
-#define GBN 64
-#define GBK 16
-
-// ---- operand loaders: element (row, k) of A [M,K] and (k, col) of B [K,N] ---------------
-struct ConvA {            // im2col view of x [n,H,W,Cin]: row = pixel, k = (ky*3+kx)*Cin + ci
-  const float* x;
-  int H, W, Cin;
-  static constexpr bool kContigM = false;
-  __device__ __forceinline__ float operator()(int m, int k) const {
-    const int ci = k % Cin, tap = k / Cin;
-    const int ky = tap / 3, kx = tap - 3 * ky;
-    const int px = m % W, t = m / W;
-    const int py = t % H, img = t / H;
-    const int yy = py + ky - 1, xx = px + kx - 1;
-    if (yy < 0 || yy >= H || xx < 0 || xx >= W) return 0.f;
-    return x[(((int64_t)img * H + yy) * W + xx) * Cin + ci];
-  }
-};
-struct RowMajorA {        // A [M,K] row-major with leading dimension ld
-  const float* a;
-  int ld;
-  static constexpr bool kContigM = false;
-  __device__ __forceinline__ float operator()(int m, int k) const { return a[(int64_t)m * ld + k]; }
-};
-struct TransposedA {      // A = X^T where X [K,M] row-major (Gram: F^T)
-  const float* a;
-  int ld;
-  static constexpr bool kContigM = true;
-  __device__ __forceinline__ float operator()(int m, int k) const { return a[(int64_t)k * ld + m]; }
-};
-struct RowMajorB {
-  const float* b;
-  int ld;
-  __device__ __forceinline__ float operator()(int k, int n) const { return b[(int64_t)k * ld + n]; }
-};
-
-// ---- epilogues ---------------------------------------------------------------------------
-struct ConvEpilogue {     // y = [relu](acc + bias) [* (mask > 0)]
-  float* y;
-  const float* bias;
-  const float* mask;
-  int ld, relu;
-  __device__ __forceinline__ void operator()(int m, int n, float acc) const {
-    float v = acc + (bias ? bias[n] : 0.f);
-    if (relu) v = fmaxf(v, 0.f);
-    const int64_t o = (int64_t)m * ld + n;
-    if (mask && !(mask[o] > 0.f)) v = 0.f;
-    y[o] = v;
-  }
-};
-struct AtomicEpilogue {   // split-K accumulation
-  float* c;
-  int ld;
-  __device__ __forceinline__ void operator()(int m, int n, float acc) const {
-    atomicAdd(c + (int64_t)m * ld + n, acc);
-  }
-};
-struct GramBwdEpilogue {  // g = (beta*g + coef*acc) * (F > 0)
-  float* g;
-  const float* F;
-  int ld;
-  float coef, beta;
-  int relu_mask;
-  __device__ __forceinline__ void operator()(int m, int n, float acc) const {
-    const int64_t o = (int64_t)m * ld + n;
-    float v = coef * acc;
-    if (beta != 0.f) v += beta * g[o];
-    g[o] = (!relu_mask || F[o] > 0.f) ? v : 0.f;
-  }
-};
-
-template <class AL, class BL, class EP>
-__global__ void __launch_bounds__(256) sgemm_k(AL A, BL B, EP ep, int M, int N, int K, int k_per_split) {
-  __shared__ float As[GBK][GBM + 4];
-  __shared__ float Bs[GBK][GBN + 4];
-  const int tid = threadIdx.x;
-  const int tx = tid & 15, ty = tid >> 4;
-  const int m0 = blockIdx.y * GBM, n0 = blockIdx.x * GBN;
-  const int kbeg = blockIdx.z * k_per_split;
-  const int kend = min(K, kbeg + k_per_split);
-  float acc[4][4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-
-  for (int k0 = kbeg; k0 < kend; k0 += GBK) {
-#pragma unroll
-    for (int e = tid; e < GBM * GBK; e += 256) {
-      int mm, kk;
-      if (AL::kContigM) { mm = e % GBM; kk = e / GBM; } else { kk = e % GBK; mm = e / GBK; }
-      const int m = m0 + mm, k = k0 + kk;
-      As[kk][mm] = (m < M && k < kend) ? A(m, k) : 0.f;
-    }
-#pragma unroll
-    for (int e = tid; e < GBN * GBK; e += 256) {
-      const int nn = e % GBN, kk = e / GBN;
-      const int n = n0 + nn, k = k0 + kk;
-      Bs[kk][nn] = (n < N && k < kend) ? B(k, n) : 0.f;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int kk = 0; kk < GBK; ++kk) {
-      float a[4], b[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
-    }
-    __syncthreads();
-  }
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int m = m0 + ty * 4 + i;
-    if (m >= M) continue;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int n = n0 + tx * 4 + j;
-      if (n < N) ep(m, n, acc[i][j]);
-    }
-  }
-}
-
-template <class AL, class BL, class EP>
-static int run_sgemm(AL A, BL B, EP ep, int M, int N, int K, int splits, cudaStream_t s) {
-  if (M <= 0 || N <= 0 || K <= 0) return LNST_OK;
-  if (splits < 1) splits = 1;
-  int kps = (K + splits - 1) / splits;
-  kps = ((kps + GBK - 1) / GBK) * GBK;
-  splits = (K + kps - 1) / kps;
-  auto k = sgemm_k<AL, BL, EP>;
-  LNST_LAUNCH(k, dim3((N + GBN - 1) / GBN, (M + GBM - 1) / GBM, splits), dim3(256), 0, s, A, B, ep, M, N, K, kps);
-  return lnst_status();
-}
+#include "sgemm.cuh"
 
 // ---- pooling -----------------------------------------------------------------------------
 __global__ void avgpool2_fwd_k(const float* __restrict__ x, float* __restrict__ y, int n, int H, int W, int C) {
