@@ -117,6 +117,27 @@ int lnst_avgpool2_fwd(const float* x, float* y, int32_t n, int32_t H, int32_t W,
 int lnst_avgpool2_bwd(const float* g_y, const float* mask, float* g_x, int32_t n, int32_t H, int32_t W,
                       int32_t C, void* stream);
 
+/* ---- loss network, tensor-core path (same reference lines; bf16 NHWC activations) ---------- */
+/* 1 when the driver exposes cuTensorMapEncodeTiled (TMA descriptors can be built). */
+int lnst_tc_supported(void);
+/* tcgen05 + TMA implicit-GEMM 3x3 SAME convolution.  x [n,H,W,Cin] bf16, w_packed
+ * [9,Cout,Cin] bf16 (tap-major, K-major rows), bias fp32 [Cout] or NULL, mask bf16 like y or
+ * NULL, y [n,H,W,Cout] bf16.  Cin and Cout must be multiples of 64.  fp32 accumulation. */
+int lnst_conv3x3_bf16_tc(const void* x, const void* w_packed, const float* bias, const void* mask,
+                         void* y, int32_t n, int32_t H, int32_t W, int32_t Cin, int32_t Cout,
+                         int32_t relu, void* stream);
+/* CUDA-core convolution with bf16 <-> fp32 I/O for the thin edge layers (conv1_1, Cin = 3, and
+ * its data gradient, Cout = 3).  w fp32 HWIO; x_bf16 / y_bf16 select the element types; mask bf16. */
+int lnst_conv3x3_mixed(const void* x, int32_t x_bf16, const float* w, const float* b, const void* mask,
+                       void* y, int32_t y_bf16, int32_t n, int32_t H, int32_t W, int32_t Cin,
+                       int32_t Cout, int32_t relu, void* stream);
+int lnst_avgpool2_bf16_fwd(const void* x, void* y, int32_t n, int32_t H, int32_t W, int32_t C,
+                           void* stream);
+int lnst_avgpool2_bf16_bwd(const void* g_y, const void* mask, void* g_x, int32_t n, int32_t H,
+                           int32_t W, int32_t C, void* stream);
+int lnst_f32_to_bf16(const float* x, void* y, int64_t n, void* stream);
+int lnst_bf16_to_f32(const void* x, float* y, int64_t n, void* stream);
+
 /* ---- losses (styler_base.py:96-102,135-185,211-213) --------------------------------------- */
 /* G [C,C] = F^T F / denom - Gs (the difference is what both the loss and its gradient need);
  * loss[0] += weight * sum(G^2).  F [P,C].  Gs NULL => G = F^T F / denom (style-target pass). */

@@ -1,0 +1,475 @@
+// Loss-network convolutions on the 5th-generation tensor cores (tcgen05) fed by TMA.
+//   reference: vgg.py:68-113 -- slim.conv2d 3x3 SAME + bias + ReLU, executed there by cuDNN.
+//
+// 3x3 convolution as an implicit GEMM without im2col in memory:
+//   D[pixel, co] = sum_{tap=(ky,kx)} sum_{ci} X[pixel + (ky-1,kx-1), ci] * Wt[tap][co][ci]
+// * M tile = 128 output pixels = a TH x TW spatial patch of one image; N tile = 64/128 output
+//   channels; K is walked as 9 taps x (Cin/64) channel chunks.
+// * A operand: for every (tap, chunk) ONE 4-D tiled TMA load of the box
+//   {64 ch, TW, TH, 1} at coordinates (c0, w0+kx-1, h0+ky-1, img) of the NHWC bf16 activation.
+//   TMA zero-fills out-of-bounds coordinates (incl. negative ones), which IS the SAME
+//   padding; the box lands in shared memory as 128 rows x 128 B = the K-major SWIZZLE_128B
+//   UMMA operand layout, so no thread ever touches operand data.
+// * B operand: weights pre-packed [tap][Cout][Cin] bf16 (K-major), 3-D TMA box {64, BN, 1}.
+// * tcgen05.mma (cta_group::1, kind::f16, M=128, N=BN, K=16) issued by one thread, fp32
+//   accumulators in TMEM; smem ring of 3 stages with mbarrier full/empty pairs
+//   (tcgen05.commit releases a stage); 2 CTAs per SM overlap one tile's epilogue with the
+//   other's main loop.
+// * Epilogue: 4 warps tcgen05.ld their TMEM sub-partition, add bias, ReLU (forward) or apply
+//   the ReLU mask of the layer below (data-gradient chain), convert to bf16, 16-byte stores.
+// The data gradient is the same kernel on flipped/transposed weights (wd[ky,kx,co,ci] =
+// w[2-ky,2-kx,ci,co]).  Layers with fewer than 64 input or output channels (conv1_1 and its
+// gradient) run on the CUDA-core engine of sgemm.cuh with bf16 <-> fp32 I/O.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include "sgemm.cuh"
+
+namespace tc {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;          // bf16 elements = 128 bytes = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr int STAGES = 3;
+constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;   // 16 KiB
+constexpr int NUM_THREADS = 192;     // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-5: epilogue
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "LAB_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, 0x989680;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra LAB_WAIT;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                            int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                            int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
+// start>>4 [0,14) | LBO>>4 [16,30) (unused for swizzled K-major, 1) | SBO>>4 [32,46) = 1024 B between
+// 8-row groups | version=1 [46,48) | base_offset=0 (tiles are 1024 B aligned) | layout=2 [61,64)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// cute::UMMA::InstrDescriptor for kind::f16: c_format=F32 [4,6), a/b_format=BF16 [7,10)/[10,13),
+// a/b K-major (bits 15,16 = 0), N>>3 [17,23), M>>4 [24,29)
+__device__ __forceinline__ uint32_t umma_idesc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+struct ConvShape {
+  int H, W, Cin, Cout;
+  int TH, TW, tiles_w, tiles_h;
+  int relu;
+};
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(NUM_THREADS, 2)
+conv3x3_tc_k(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
+             const float* __restrict__ bias, const __nv_bfloat16* __restrict__ mask,
+             __nv_bfloat16* __restrict__ y, ConvShape s) {
+  constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B operand tiles need 1024-byte alignment
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t smem_a = base;
+  const uint32_t smem_b = base + STAGES * A_BYTES;
+  const uint32_t bars = smem_b + STAGES * B_BYTES;      // full[STAGES], empty[STAGES], tmem_full
+  const uint32_t tmem_slot = bars + 8 * (2 * STAGES + 1);
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = blockIdx.x;
+  const int tw = tile % s.tiles_w, th = (tile / s.tiles_w) % s.tiles_h, img = tile / (s.tiles_w * s.tiles_h);
+  const int h0 = th * s.TH, w0 = tw * s.TW, n0 = blockIdx.y * BLOCK_N;
+  const int kchunks = s.Cin / BLOCK_K;
+  const int num_kb = 9 * kchunks;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&map_x);
+    prefetch_tmap(&map_w);
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(bars + 8 * i, 1);
+      mbar_init(bars + 8 * (STAGES + i), 1);
+    }
+    mbar_init(bars + 8 * (2 * STAGES), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {   // whole warp: allocate BLOCK_N TMEM columns (power of two >= 32)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(BLOCK_N));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_d = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int st = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(bars + 8 * (STAGES + st), ph ^ 1);                 // slot free
+        const uint32_t full = bars + 8 * st;
+        mbar_expect_tx(full, A_BYTES + B_BYTES);
+        const int tap = kb / kchunks, c0 = (kb - tap * kchunks) * BLOCK_K;
+        const int ky = tap / 3, kx = tap - 3 * ky;
+        tma_load_4d(smem_a + st * A_BYTES, &map_x, full, c0, w0 + kx - 1, h0 + ky - 1, img);
+        tma_load_3d(smem_b + st * B_BYTES, &map_w, full, c0, n0, tap);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      const uint32_t idesc = umma_idesc_bf16(BLOCK_M, BLOCK_N);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int st = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(bars + 8 * st, ph);                                // operands landed
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t a0 = smem_a + st * A_BYTES, b0 = smem_b + st * B_BYTES;
+#pragma unroll
+        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+          // advancing 16 bf16 = 32 B inside the 128 B swizzle row
+          umma_bf16(tmem_d, umma_desc_sw128(a0 + k * UMMA_K * 2), umma_desc_sw128(b0 + k * UMMA_K * 2), idesc,
+                    (kb | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(bars + 8 * (STAGES + st));                       // frees the slot when the MMAs retire
+      }
+      umma_commit(bars + 8 * (2 * STAGES));                          // accumulator complete
+    }
+  } else {
+    // ===== epilogue: warps 2..5, TMEM sub-partition = warp % 4 =====
+    const int q = warp & 3;
+    const int r = q * 32 + lane;                                      // row of the tile = pixel
+    const int ph_ = h0 + r / s.TW, pw_ = w0 + r % s.TW;
+    const bool valid = ph_ < s.H && pw_ < s.W;
+    const int64_t pix = ((int64_t)img * s.H + ph_) * s.W + pw_;
+    mbar_wait(bars + 8 * (2 * STAGES), 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+    for (int c = 0; c < BLOCK_N / 32; ++c) {
+      uint32_t v[32];
+      tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+      if (valid) {
+        const int co = n0 + c * 32;
+        __nv_bfloat16* dst = y + pix * s.Cout + co;
+        const __nv_bfloat16* msk = mask ? mask + pix * s.Cout + co : nullptr;
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          uint4 mv = make_uint4(0, 0, 0, 0);
+          if (msk) mv = *reinterpret_cast<const uint4*>(msk + j);
+          const __nv_bfloat16* mh = reinterpret_cast<const __nv_bfloat16*>(&mv);
+          uint4 ov;
+          __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&ov);
+#pragma unroll
+          for (int e = 0; e < 8; e += 2) {
+            float f0 = __uint_as_float(v[j + e]), f1 = __uint_as_float(v[j + e + 1]);
+            if (bias) { f0 += bias[co + j + e]; f1 += bias[co + j + e + 1]; }
+            if (s.relu) { f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); }
+            if (msk) {
+              if (!(__bfloat162float(mh[e]) > 0.f)) f0 = 0.f;
+              if (!(__bfloat162float(mh[e + 1]) > 0.f)) f1 = 0.f;
+            }
+            oh[e >> 1] = __floats2bfloat162_rn(f0, f1);
+          }
+          *reinterpret_cast<uint4*>(dst + j) = ov;
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(BLOCK_N));
+  }
+}
+
+// ---- host side: tensor maps ------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+static bool make_map(CUtensorMap* m, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
+                     const cuuint32_t* box) {
+  cuuint32_t ones[5] = {1, 1, 1, 1, 1};
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return false;
+  return fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides, box, ones,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int BLOCK_N>
+static int launch_conv(const CUtensorMap& mx, const CUtensorMap& mw, const float* bias, const __nv_bfloat16* mask,
+                       __nv_bfloat16* y, const ConvShape& s, int n_img, cudaStream_t stream) {
+  const int smem = STAGES * (A_BYTES + BLOCK_N * BLOCK_K * 2) + 8 * (2 * STAGES + 1) + 16 + 1024;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_k<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  dim3 grid(s.tiles_w * s.tiles_h * n_img, s.Cout / BLOCK_N);
+  conv3x3_tc_k<BLOCK_N><<<grid, NUM_THREADS, smem, stream>>>(mx, mw, bias, mask, y, s);
+  return (int)cudaGetLastError();
+}
+
+// choose the TH x TW = 128 patch that wastes the fewest pixels
+static void pick_tile(int H, int W, int& TH, int& TW) {
+  long best = -1;
+  for (int tw = 8; tw <= 128; tw *= 2) {
+    const int th = 128 / tw;
+    const long cover = (long)((H + th - 1) / th) * th * ((W + tw - 1) / tw) * tw;
+    if (best < 0 || cover < best || (cover == best && tw == 16)) { best = cover; TH = th; TW = tw; }
+  }
+}
+
+// ---- elementwise helpers on bf16 ---------------------------------------------------------------
+__global__ void f32_to_bf16_k(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int64_t n) {
+  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i + 3 < n) {
+    const float4 v = *reinterpret_cast<const float4*>(x + i);
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 o;
+    o.x = *reinterpret_cast<uint32_t*>(&a);
+    o.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(y + i) = o;
+  } else {
+    for (int64_t j = i; j < n; ++j) y[j] = __float2bfloat16_rn(x[j]);
+  }
+}
+__global__ void bf16_to_f32_k(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, int64_t n) {
+  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i + 3 < n) {
+    const uint2 v = *reinterpret_cast<const uint2*>(x + i);
+    const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&v.x);
+    const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&v.y);
+    const float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
+    *reinterpret_cast<float4*>(y + i) = make_float4(fa.x, fa.y, fb.x, fb.y);
+  } else {
+    for (int64_t j = i; j < n; ++j) y[j] = __bfloat162float(x[j]);
+  }
+}
+// 2x2/2 average pool on NHWC bf16, 8 channels (16 bytes) per thread
+__global__ void avgpool2_bf16_fwd_k(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int n, int H,
+                                    int W, int C) {
+  const int OH = H / 2, OW = W / 2, C8 = C / 8;
+  const int64_t total = (int64_t)n * OH * OW * C8;
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int c = (int)(t % C8) * 8;
+  const int ox = (int)((t / C8) % OW);
+  const int oy = (int)((t / ((int64_t)C8 * OW)) % OH);
+  const int img = (int)(t / ((int64_t)C8 * OW * OH));
+  const __nv_bfloat16* b = x + (((int64_t)img * H + 2 * oy) * W + 2 * ox) * C + c;
+  const uint4 v00 = *reinterpret_cast<const uint4*>(b), v01 = *reinterpret_cast<const uint4*>(b + C);
+  const uint4 v10 = *reinterpret_cast<const uint4*>(b + (int64_t)W * C);
+  const uint4 v11 = *reinterpret_cast<const uint4*>(b + (int64_t)W * C + C);
+  const __nv_bfloat162* a0 = reinterpret_cast<const __nv_bfloat162*>(&v00);
+  const __nv_bfloat162* a1 = reinterpret_cast<const __nv_bfloat162*>(&v01);
+  const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&v10);
+  const __nv_bfloat162* a3 = reinterpret_cast<const __nv_bfloat162*>(&v11);
+  uint4 o;
+  __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float2 f0 = __bfloat1622float2(a0[e]), f1 = __bfloat1622float2(a1[e]);
+    const float2 f2 = __bfloat1622float2(a2[e]), f3 = __bfloat1622float2(a3[e]);
+    oh[e] = __floats2bfloat162_rn((f0.x + f1.x + f2.x + f3.x) * 0.25f, (f0.y + f1.y + f2.y + f3.y) * 0.25f);
+  }
+  *reinterpret_cast<uint4*>(y + (((int64_t)img * OH + oy) * OW + ox) * C + c) = o;
+}
+__global__ void avgpool2_bf16_bwd_k(const __nv_bfloat16* __restrict__ gy, const __nv_bfloat16* __restrict__ mask,
+                                    __nv_bfloat16* __restrict__ gx, int n, int H, int W, int C) {
+  const int OH = H / 2, OW = W / 2, C8 = C / 8;
+  const int64_t total = (int64_t)n * H * W * C8;
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int c = (int)(t % C8) * 8;
+  const int xx = (int)((t / C8) % W);
+  const int yy = (int)((t / ((int64_t)C8 * W)) % H);
+  const int img = (int)(t / ((int64_t)C8 * W * H));
+  const int64_t o = (((int64_t)img * H + yy) * W + xx) * C + c;
+  uint4 g = make_uint4(0, 0, 0, 0);
+  const int oy = yy >> 1, ox = xx >> 1;
+  if (oy < OH && ox < OW) g = *reinterpret_cast<const uint4*>(gy + (((int64_t)img * OH + oy) * OW + ox) * C + c);
+  uint4 mv = make_uint4(0, 0, 0, 0);
+  if (mask) mv = *reinterpret_cast<const uint4*>(mask + o);
+  const __nv_bfloat16* gh = reinterpret_cast<const __nv_bfloat16*>(&g);
+  const __nv_bfloat16* mh = reinterpret_cast<const __nv_bfloat16*>(&mv);
+  uint4 ov;
+  __nv_bfloat16* oh = reinterpret_cast<__nv_bfloat16*>(&ov);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    float f = 0.25f * __bfloat162float(gh[e]);
+    if (mask && !(__bfloat162float(mh[e]) > 0.f)) f = 0.f;
+    oh[e] = __float2bfloat16_rn(f);
+  }
+  *reinterpret_cast<uint4*>(gx + o) = ov;
+}
+
+}  // namespace tc
+
+// ---------------------------------------------------------------------------------------
+// C-ABI
+// ---------------------------------------------------------------------------------------
+extern "C" int lnst_tc_supported(void) { return tc::encode_fn() != nullptr ? 1 : 0; }
+
+extern "C" int lnst_conv3x3_bf16_tc(const void* x, const void* w_packed, const float* bias, const void* mask,
+                                    void* y, int32_t n, int32_t H, int32_t W, int32_t Cin, int32_t Cout,
+                                    int32_t relu, void* stream) {
+  using namespace tc;
+  if (!x || !w_packed || !y || n < 1 || H < 1 || W < 1 || Cin < 64 || Cout < 64 || Cin % 64 || Cout % 64)
+    return LNST_EARG;
+  ConvShape s;
+  s.H = H; s.W = W; s.Cin = Cin; s.Cout = Cout; s.relu = relu;
+  pick_tile(H, W, s.TH, s.TW);
+  s.tiles_w = (W + s.TW - 1) / s.TW;
+  s.tiles_h = (H + s.TH - 1) / s.TH;
+  const int BN = (Cout % 128 == 0) ? 128 : 64;
+  CUtensorMap mx, mw;
+  {
+    const cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n};
+    const cuuint64_t strides[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2};
+    const cuuint32_t box[4] = {(cuuint32_t)BLOCK_K, (cuuint32_t)s.TW, (cuuint32_t)s.TH, 1};
+    if (!make_map(&mx, x, 4, dims, strides, box)) return LNST_EARG;
+  }
+  {
+    const cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)Cout, 9};
+    const cuuint64_t strides[2] = {(cuuint64_t)Cin * 2, (cuuint64_t)Cout * Cin * 2};
+    const cuuint32_t box[3] = {(cuuint32_t)BLOCK_K, (cuuint32_t)BN, 1};
+    if (!make_map(&mw, w_packed, 3, dims, strides, box)) return LNST_EARG;
+  }
+  if (BN == 128)
+    return launch_conv<128>(mx, mw, bias, (const __nv_bfloat16*)mask, (__nv_bfloat16*)y, s, n, lnst_stream(stream));
+  return launch_conv<64>(mx, mw, bias, (const __nv_bfloat16*)mask, (__nv_bfloat16*)y, s, n, lnst_stream(stream));
+}
+
+// CUDA-core convolution with mixed I/O types for the thin edge layers (conv1_1: Cin = 3; its
+// data gradient: Cout = 3).  w is fp32 HWIO like lnst_conv3x3_f32.
+extern "C" int lnst_conv3x3_mixed(const void* x, int32_t x_bf16, const float* w, const float* b, const void* mask,
+                                  void* y, int32_t y_bf16, int32_t n, int32_t H, int32_t W, int32_t Cin,
+                                  int32_t Cout, int32_t relu, void* stream) {
+  if (!x || !w || !y || n < 1 || H < 1 || W < 1 || Cin < 1 || Cout < 1) return LNST_EARG;
+  if ((int64_t)n * H * W > 0x7fffffff) return LNST_EARG;
+  const int M = n * H * W, K = 9 * Cin;
+  RowMajorB B{w, (int)Cout};
+  typedef __nv_bfloat16 bf;
+  cudaStream_t s = lnst_stream(stream);
+  if (!x_bf16 && y_bf16) {
+    ConvAT<float> A{(const float*)x, (int)H, (int)W, (int)Cin};
+    ConvEpilogueT<bf, bf> ep{(bf*)y, b, (const bf*)mask, (int)Cout, (int)relu};
+    return run_sgemm(A, B, ep, M, Cout, K, 1, s);
+  }
+  if (x_bf16 && !y_bf16) {
+    ConvAT<bf> A{(const bf*)x, (int)H, (int)W, (int)Cin};
+    ConvEpilogueT<float, bf> ep{(float*)y, b, (const bf*)mask, (int)Cout, (int)relu};
+    return run_sgemm(A, B, ep, M, Cout, K, 1, s);
+  }
+  if (x_bf16 && y_bf16) {
+    ConvAT<bf> A{(const bf*)x, (int)H, (int)W, (int)Cin};
+    ConvEpilogueT<bf, bf> ep{(bf*)y, b, (const bf*)mask, (int)Cout, (int)relu};
+    return run_sgemm(A, B, ep, M, Cout, K, 1, s);
+  }
+  return LNST_EARG;
+}
+
+extern "C" int lnst_avgpool2_bf16_fwd(const void* x, void* y, int32_t n, int32_t H, int32_t W, int32_t C,
+                                      void* stream) {
+  if (!x || !y || n < 1 || H < 2 || W < 2 || C < 8 || C % 8) return LNST_EARG;
+  const int64_t total = (int64_t)n * (H / 2) * (W / 2) * (C / 8);
+  tc::avgpool2_bf16_fwd_k<<<lnst_blocks(total, 256), 256, 0, lnst_stream(stream)>>>(
+      (const __nv_bfloat16*)x, (__nv_bfloat16*)y, n, H, W, C);
+  return lnst_status();
+}
+
+extern "C" int lnst_avgpool2_bf16_bwd(const void* g_y, const void* mask, void* g_x, int32_t n, int32_t H, int32_t W,
+                                      int32_t C, void* stream) {
+  if (!g_y || !g_x || n < 1 || H < 2 || W < 2 || C < 8 || C % 8) return LNST_EARG;
+  const int64_t total = (int64_t)n * H * W * (C / 8);
+  tc::avgpool2_bf16_bwd_k<<<lnst_blocks(total, 256), 256, 0, lnst_stream(stream)>>>(
+      (const __nv_bfloat16*)g_y, (const __nv_bfloat16*)mask, (__nv_bfloat16*)g_x, n, H, W, C);
+  return lnst_status();
+}
+
+extern "C" int lnst_f32_to_bf16(const float* x, void* y, int64_t n, void* stream) {
+  if (!x || !y || n < 0) return LNST_EARG;
+  if (n == 0) return LNST_OK;
+  tc::f32_to_bf16_k<<<lnst_blocks((n + 3) / 4, 256), 256, 0, lnst_stream(stream)>>>(x, (__nv_bfloat16*)y, n);
+  return lnst_status();
+}
+
+extern "C" int lnst_bf16_to_f32(const void* x, float* y, int64_t n, void* stream) {
+  if (!x || !y || n < 0) return LNST_EARG;
+  if (n == 0) return LNST_OK;
+  tc::bf16_to_f32_k<<<lnst_blocks((n + 3) / 4, 256), 256, 0, lnst_stream(stream)>>>((const __nv_bfloat16*)x, y, n);
+  return lnst_status();
+}

@@ -9,8 +9,17 @@
 #define GBK 16
 
 // ---- operand loaders: element (row, k) of A [M,K] and (k, col) of B [K,N] ---------------
-struct ConvA {            // im2col view of x [n,H,W,Cin]: row = pixel, k = (ky*3+kx)*Cin + ci
-  const float* x;
+__device__ __forceinline__ float lnst_to_f32(float v) { return v; }
+__device__ __forceinline__ void lnst_from_f32(float* p, float v) { *p = v; }
+#ifndef LNST_CPU_EMU
+#include <cuda_bf16.h>
+__device__ __forceinline__ float lnst_to_f32(__nv_bfloat16 v) { return __bfloat162float(v); }
+__device__ __forceinline__ void lnst_from_f32(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+#endif
+
+template <class TIn>
+struct ConvAT {           // im2col view of x [n,H,W,Cin]: row = pixel, k = (ky*3+kx)*Cin + ci
+  const TIn* x;
   int H, W, Cin;
   static constexpr bool kContigM = false;
   __device__ __forceinline__ float operator()(int m, int k) const {
@@ -20,9 +29,10 @@ struct ConvA {            // im2col view of x [n,H,W,Cin]: row = pixel, k = (ky*
     const int py = t % H, img = t / H;
     const int yy = py + ky - 1, xx = px + kx - 1;
     if (yy < 0 || yy >= H || xx < 0 || xx >= W) return 0.f;
-    return x[(((int64_t)img * H + yy) * W + xx) * Cin + ci];
+    return lnst_to_f32(x[(((int64_t)img * H + yy) * W + xx) * Cin + ci]);
   }
 };
+typedef ConvAT<float> ConvA;
 struct RowMajorA {        // A [M,K] row-major with leading dimension ld
   const float* a;
   int ld;
@@ -42,19 +52,21 @@ struct RowMajorB {
 };
 
 // ---- epilogues ---------------------------------------------------------------------------
-struct ConvEpilogue {     // y = [relu](acc + bias) [* (mask > 0)]
-  float* y;
+template <class TOut, class TMask>
+struct ConvEpilogueT {    // y = [relu](acc + bias) [* (mask > 0)]
+  TOut* y;
   const float* bias;
-  const float* mask;
+  const TMask* mask;
   int ld, relu;
   __device__ __forceinline__ void operator()(int m, int n, float acc) const {
     float v = acc + (bias ? bias[n] : 0.f);
     if (relu) v = fmaxf(v, 0.f);
     const int64_t o = (int64_t)m * ld + n;
-    if (mask && !(mask[o] > 0.f)) v = 0.f;
-    y[o] = v;
+    if (mask && !(lnst_to_f32(mask[o]) > 0.f)) v = 0.f;
+    lnst_from_f32(y + o, v);
   }
 };
+typedef ConvEpilogueT<float, float> ConvEpilogue;
 struct AtomicEpilogue {   // split-K accumulation
   float* c;
   int ld;

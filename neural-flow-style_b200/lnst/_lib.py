@@ -64,6 +64,9 @@ SIGNATURES = {
 CUDA_ONLY = {
     'lnst_tc_supported': [],
     'lnst_conv3x3_bf16_tc': [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp],
+    'lnst_conv3x3_mixed': [vp, i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp],
+    'lnst_avgpool2_bf16_fwd': [vp, vp, i32, i32, i32, i32, vp],
+    'lnst_avgpool2_bf16_bwd': [vp, vp, vp, i32, i32, i32, i32, vp],
     'lnst_f32_to_bf16': [vp, vp, i64, vp],
     'lnst_bf16_to_f32': [vp, vp, i64, vp],
 }

@@ -238,3 +238,52 @@ def advect(d, vel):
     out = torch.empty_like(d)
     _lib.get().call('lnst_advect', ptr(d), ptr(vel), dim, dims, d.shape[-1], ptr(out), _s(d))
     return out
+
+
+# ---- loss net (tensor-core path, bf16 NHWC) ---------------------------------------------------
+bf16 = torch.bfloat16
+
+
+def conv3x3_bf16_tc(x, w_packed, bias, relu, mask=None, y=None):
+    n, H, W, cin = x.shape
+    cout = w_packed.shape[1]
+    if y is None:
+        y = torch.empty(n, H, W, cout, dtype=bf16, device=x.device)
+    _lib.get().call('lnst_conv3x3_bf16_tc', ptr(x), ptr(w_packed), ptr(bias), ptr(mask), ptr(y), n, H, W, cin, cout,
+                    int(relu), _s(x))
+    return y
+
+
+def conv3x3_mixed(x, w, b, relu, out_bf16, mask=None):
+    n, H, W, cin = x.shape
+    cout = w.shape[-1]
+    y = torch.empty(n, H, W, cout, dtype=bf16 if out_bf16 else f32, device=x.device)
+    _lib.get().call('lnst_conv3x3_mixed', ptr(x), int(x.dtype == bf16), ptr(w), ptr(b), ptr(mask), ptr(y),
+                    int(out_bf16), n, H, W, cin, cout, int(relu), _s(x))
+    return y
+
+
+def avgpool2_bf16_fwd(x):
+    n, H, W, ch = x.shape
+    y = torch.empty(n, H // 2, W // 2, ch, dtype=bf16, device=x.device)
+    _lib.get().call('lnst_avgpool2_bf16_fwd', ptr(x), ptr(y), n, H, W, ch, _s(x))
+    return y
+
+
+def avgpool2_bf16_bwd(g_y, mask, shape):
+    n, H, W, ch = shape
+    g_x = torch.empty(n, H, W, ch, dtype=bf16, device=g_y.device)
+    _lib.get().call('lnst_avgpool2_bf16_bwd', ptr(g_y), ptr(mask), ptr(g_x), n, H, W, ch, _s(g_y))
+    return g_x
+
+
+def to_bf16(x):
+    y = torch.empty(x.shape, dtype=bf16, device=x.device)
+    _lib.get().call('lnst_f32_to_bf16', ptr(x), ptr(y), x.numel(), _s(x))
+    return y
+
+
+def to_f32(x):
+    y = torch.empty(x.shape, dtype=f32, device=x.device)
+    _lib.get().call('lnst_bf16_to_f32', ptr(x), ptr(y), x.numel(), _s(x))
+    return y

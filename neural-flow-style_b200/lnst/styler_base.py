@@ -152,7 +152,7 @@ class StylerBase(object):
                                      loss[v:v + 1], g[v].reshape(P, ch), beta, is_conv)
             return g
 
-        g_x = self.net.backward(x, acts, wanted, add_loss_grad) if wanted else None
+        g_x = self.net.backward(x, acts, wanted, add_loss_grad, set(wanted)) if wanted else None
         if g_x is None:
             g_x = torch.zeros_like(x)
         if self.w_tv:

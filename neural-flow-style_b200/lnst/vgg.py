@@ -105,18 +105,19 @@ class LossNet:
         return acts
 
     # ---- backward --------------------------------------------------------------------------
-    def backward(self, x, acts, wanted, add_loss_grad):
-        """d loss / d x.  ``add_loss_grad(name, act, g)`` adds the loss terms that live on end
-        point ``name`` into ``g`` (None = nothing accumulated yet; it must then allocate) and
-        returns the buffer (or None).  Gradients held for conv end points are w.r.t. the
+    def backward(self, x, acts, wanted, add_loss_grad, loss_layers):
+        """d loss / d x.  For every end point in ``loss_layers``, ``add_loss_grad(name, act, g)``
+        adds the loss terms that live there into ``g`` (None = nothing accumulated yet; it then
+        allocates) and returns the buffer.  Gradients held for conv end points are w.r.t. the
         PRE-activation (ReLU mask already applied)."""
         if self.math == 'bf16':
-            return self.tc.backward(x, acts, self.prefix(wanted), add_loss_grad)
+            return self.tc.backward(x, acts, self.prefix(wanted), add_loss_grad, loss_layers)
         layers = self.prefix(wanted)
         g = None
         for i in range(len(layers) - 1, -1, -1):
             name = layers[i]
-            g = add_loss_grad(name, acts[name], g)
+            if name in loss_layers:
+                g = add_loss_grad(name, acts[name], g)
             if g is None:
                 continue
             prev = layers[i - 1] if i > 0 else None
