@@ -163,7 +163,9 @@ def run_engine(args):
     res = [WORKLOADS[wl]['res']] * 3
     ws = styler._workspace(res)
     grams = styler._style_feature(sty, res[1:])
-    fr = {'id': 0, 'p': torch.tensor(p[0], device=dev), 'r': torch.tensor(r[0], device=dev)}
+    styler.num_frames = 1
+    frames, _ = styler.upload({'p': p, 'r': r})          # device-resident, cell-sorted particles
+    fr = frames[0]
     g_opt = torch.zeros(fr['p'].shape[0], 2, device=dev)
     adam = _Adam()
     lr = cfg.lr

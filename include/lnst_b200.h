@@ -131,6 +131,13 @@ int lnst_conv3x3_bf16_tc(const void* x, const void* w_packed, const float* bias,
 int lnst_conv3x3_mixed(const void* x, int32_t x_bf16, const float* w, const float* b, const void* mask,
                        void* y, int32_t y_bf16, int32_t n, int32_t H, int32_t W, int32_t Cin,
                        int32_t Cout, int32_t relu, void* stream);
+/* Dedicated kernels for VGG's conv1_1 (3 -> 64, K = 27): forward x fp32 [n,H,W,3] -> y bf16
+ * [n,H,W,64] with bias + ReLU (w fp32 HWIO [3,3,3,64]); data gradient g bf16 [n,H,W,64] -> gx fp32
+ * [n,H,W,3] (wd fp32 [3,3,64,3] = flipped/transposed w). */
+int lnst_conv_first_fwd(const float* x, const float* w, const float* b, void* y, int32_t n, int32_t H,
+                        int32_t W, void* stream);
+int lnst_conv_first_bwd(const void* g, const float* wd, float* gx, int32_t n, int32_t H, int32_t W,
+                        void* stream);
 int lnst_avgpool2_bf16_fwd(const void* x, void* y, int32_t n, int32_t H, int32_t W, int32_t C,
                            void* stream);
 int lnst_avgpool2_bf16_bwd(const void* g_y, const void* mask, void* g_x, int32_t n, int32_t H,
@@ -168,6 +175,12 @@ int lnst_iterate_delta(const float* g_new, float scale, const float* g_opt, cons
 int lnst_temporal_gauss(const float* x, float* y, int32_t T, int64_t M, float sigma, void* stream);
 /* y += a*x */
 int lnst_axpy(float* y, const float* x, float a, int64_t n, void* stream);
+/* tf.clip_by_value (styler_2p.py:68,88,94) and its gradient gx = scale*g inside [lo,hi], 0 outside. */
+int lnst_clip_fwd(const float* x, float lo, float hi, float* y, int64_t n, void* stream);
+int lnst_clip_bwd(const float* g, const float* x, float lo, float hi, float scale, float* gx, int64_t n,
+                  void* stream);
+/* out[i] = a[i] * b[i / C]  (colour field x density mask, styler_2p.py:71,100); n = elements of a. */
+int lnst_mul_bcast(const float* a, const float* b, int32_t C, float* out, int64_t n, void* stream);
 
 /* ---- semi-Lagrangian advection, order 1 (transform.py:557-609) ---------------------------- */
 /* d [X,Y,(Z),C], vel [X,Y,(Z),dim] in normalised units; dims[0..dim-1]. */

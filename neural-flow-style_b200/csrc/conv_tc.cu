@@ -376,11 +376,111 @@ __global__ void avgpool2_bf16_bwd_k(const __nv_bfloat16* __restrict__ gy, const 
   *reinterpret_cast<uint4*>(gx + o) = ov;
 }
 
+// ---- conv1_1 (3 -> 64) and its data gradient (64 -> 3): K = 27, far too thin for an MMA tile ----
+// forward: 8 threads per pixel, 8 output channels each; the 27 inputs are shared by the 8 lanes.
+__global__ void __launch_bounds__(256) conv_first_fwd_k(const float* __restrict__ x, const float* __restrict__ w,
+                                                        const float* __restrict__ b, __nv_bfloat16* __restrict__ y,
+                                                        int n, int H, int W) {
+  __shared__ float ws[27 * 64];
+  __shared__ float bs[64];
+  for (int i = threadIdx.x; i < 27 * 64; i += blockDim.x) ws[i] = w[i];
+  if (threadIdx.x < 64) bs[threadIdx.x] = b ? b[threadIdx.x] : 0.f;
+  __syncthreads();
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t pix = t >> 3;
+  const int cg = (int)(t & 7) * 8;
+  if (pix >= (int64_t)n * H * W) return;
+  const int px = (int)(pix % W), py = (int)((pix / W) % H);
+  const int64_t img = pix / ((int64_t)W * H);
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = bs[cg + j];
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky) {
+    const int yy = py + ky - 1;
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const int xx = px + kx - 1;
+      if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+      const float* src = x + ((img * H + yy) * W + xx) * 3;
+#pragma unroll
+      for (int ci = 0; ci < 3; ++ci) {
+        const float xv = src[ci];
+        const float4* wr = reinterpret_cast<const float4*>(ws + ((ky * 3 + kx) * 3 + ci) * 64 + cg);
+        const float4 w0 = wr[0], w1 = wr[1];
+        acc[0] = fmaf(xv, w0.x, acc[0]); acc[1] = fmaf(xv, w0.y, acc[1]);
+        acc[2] = fmaf(xv, w0.z, acc[2]); acc[3] = fmaf(xv, w0.w, acc[3]);
+        acc[4] = fmaf(xv, w1.x, acc[4]); acc[5] = fmaf(xv, w1.y, acc[5]);
+        acc[6] = fmaf(xv, w1.z, acc[6]); acc[7] = fmaf(xv, w1.w, acc[7]);
+      }
+    }
+  }
+  uint4 o;
+  __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) oh[j] = __floats2bfloat162_rn(fmaxf(acc[2 * j], 0.f), fmaxf(acc[2 * j + 1], 0.f));
+  *reinterpret_cast<uint4*>(y + pix * 64 + cg) = o;
+}
+
+// data gradient: one thread per pixel, 9 taps x 64 channels x 3 outputs; wd fp32 [3,3,64,3]
+__global__ void __launch_bounds__(128) conv_first_bwd_k(const __nv_bfloat16* __restrict__ g,
+                                                        const float* __restrict__ wd, float* __restrict__ gx,
+                                                        int n, int H, int W) {
+  __shared__ float ws[9 * 64 * 3];
+  for (int i = threadIdx.x; i < 9 * 64 * 3; i += blockDim.x) ws[i] = wd[i];
+  __syncthreads();
+  const int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= (int64_t)n * H * W) return;
+  const int px = (int)(pix % W), py = (int)((pix / W) % H);
+  const int64_t img = pix / ((int64_t)W * H);
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+  for (int ky = 0; ky < 3; ++ky) {
+    const int yy = py + ky - 1;
+    if (yy < 0 || yy >= H) continue;
+    for (int kx = 0; kx < 3; ++kx) {
+      const int xx = px + kx - 1;
+      if (xx < 0 || xx >= W) continue;
+      const uint4* src = reinterpret_cast<const uint4*>(g + ((img * H + yy) * W + xx) * 64);
+      const float* wt = ws + (ky * 3 + kx) * 64 * 3;
+#pragma unroll
+      for (int v = 0; v < 8; ++v) {
+        const uint4 q = src[v];
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = __bfloat1622float2(h[e]);
+          const float* w0 = wt + (v * 8 + e * 2) * 3;
+          a0 = fmaf(f.x, w0[0], a0); a1 = fmaf(f.x, w0[1], a1); a2 = fmaf(f.x, w0[2], a2);
+          a0 = fmaf(f.y, w0[3], a0); a1 = fmaf(f.y, w0[4], a1); a2 = fmaf(f.y, w0[5], a2);
+        }
+      }
+    }
+  }
+  gx[pix * 3] = a0; gx[pix * 3 + 1] = a1; gx[pix * 3 + 2] = a2;
+}
+
 }  // namespace tc
 
 // ---------------------------------------------------------------------------------------
 // C-ABI
 // ---------------------------------------------------------------------------------------
+extern "C" int lnst_conv_first_fwd(const float* x, const float* w, const float* b, void* y, int32_t n, int32_t H,
+                                   int32_t W, void* stream) {
+  if (!x || !w || !y || n < 1 || H < 1 || W < 1) return LNST_EARG;
+  const int64_t threads = (int64_t)n * H * W * 8;
+  tc::conv_first_fwd_k<<<lnst_blocks(threads, 256), 256, 0, lnst_stream(stream)>>>(x, w, b, (__nv_bfloat16*)y, n, H, W);
+  return lnst_status();
+}
+
+extern "C" int lnst_conv_first_bwd(const void* g, const float* wd, float* gx, int32_t n, int32_t H, int32_t W,
+                                   void* stream) {
+  if (!g || !wd || !gx || n < 1 || H < 1 || W < 1) return LNST_EARG;
+  const int64_t threads = (int64_t)n * H * W;
+  tc::conv_first_bwd_k<<<lnst_blocks(threads, 128), 128, 0, lnst_stream(stream)>>>((const __nv_bfloat16*)g, wd, gx, n,
+                                                                                     H, W);
+  return lnst_status();
+}
+
 extern "C" int lnst_tc_supported(void) { return tc::encode_fn() != nullptr ? 1 : 0; }
 
 extern "C" int lnst_conv3x3_bf16_tc(const void* x, const void* w_packed, const float* bias, const void* mask,

@@ -42,6 +42,23 @@ __global__ void axpy_k(float* __restrict__ y, const float* __restrict__ x, float
   if (i < n) y[i] += a * x[i];
 }
 
+// tf.clip_by_value and its gradient (zero strictly outside [lo,hi]); styler_2p.py:68,88,94
+__global__ void clip_fwd_k(const float* __restrict__ x, float lo, float hi, float* __restrict__ y, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = fminf(fmaxf(x[i], lo), hi);
+}
+__global__ void clip_bwd_k(const float* __restrict__ g, const float* __restrict__ x, float lo, float hi, float scale,
+                           float* __restrict__ gx, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) gx[i] = (x[i] >= lo && x[i] <= hi) ? g[i] * scale : 0.f;
+}
+// out[i*C+c] = a[i*C+c] * b[i]   (colour field x density mask, styler_2p.py:71,100)
+__global__ void mul_bcast_k(const float* __restrict__ a, const float* __restrict__ b, int C, float* __restrict__ out,
+                            int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = a[i] * b[i / C];
+}
+
 // 1-D Gaussian along axis 0 of x [T,M]; scipy 'reflect' boundary (d c b a | a b c d | d c b a)
 #define LNST_MAX_GAUSS_RADIUS 64
 struct GaussTaps { int radius; float w[LNST_MAX_GAUSS_RADIUS + 1]; };
@@ -128,6 +145,28 @@ extern "C" int lnst_axpy(float* y, const float* x, float a, int64_t n, void* str
   if (!y || !x || n < 0) return LNST_EARG;
   if (n == 0) return LNST_OK;
   LNST_LAUNCH(axpy_k, dim3(lnst_blocks(n, 256)), dim3(256), 0, lnst_stream(stream), y, x, a, n);
+  return lnst_status();
+}
+
+extern "C" int lnst_clip_fwd(const float* x, float lo, float hi, float* y, int64_t n, void* stream) {
+  if (!x || !y || n < 0) return LNST_EARG;
+  if (n == 0) return LNST_OK;
+  LNST_LAUNCH(clip_fwd_k, dim3(lnst_blocks(n, 256)), dim3(256), 0, lnst_stream(stream), x, lo, hi, y, n);
+  return lnst_status();
+}
+
+extern "C" int lnst_clip_bwd(const float* g, const float* x, float lo, float hi, float scale, float* gx, int64_t n,
+                             void* stream) {
+  if (!g || !x || !gx || n < 0) return LNST_EARG;
+  if (n == 0) return LNST_OK;
+  LNST_LAUNCH(clip_bwd_k, dim3(lnst_blocks(n, 256)), dim3(256), 0, lnst_stream(stream), g, x, lo, hi, scale, gx, n);
+  return lnst_status();
+}
+
+extern "C" int lnst_mul_bcast(const float* a, const float* b, int32_t C, float* out, int64_t n, void* stream) {
+  if (!a || !b || !out || n < 0 || C < 1) return LNST_EARG;
+  if (n == 0) return LNST_OK;
+  LNST_LAUNCH(mul_bcast_k, dim3(lnst_blocks(n, 256)), dim3(256), 0, lnst_stream(stream), a, b, (int)C, out, n);
   return lnst_status();
 }
 

@@ -7,6 +7,8 @@
 // materialised: each ray samples the source volume while it marches.
 #include "common.cuh"
 
+#define RM_UNROLL 4
+
 struct VolDims {
   int D, H, W;
   float sD, sH, sW;   // linspace steps 2/(L-1) (0 when L == 1), transform.py:175
@@ -100,16 +102,30 @@ __global__ void raymarch_fwd_k(const float* __restrict__ vol, const float* __res
   const float* R = rot ? rot + 9 * view : nullptr;
   const float gh = lin_coord(h, v.sH), gw = lin_coord(w, v.sW);
   float S = 0.f, I = 0.f;
-  for (int i = v.D - 1; i >= 0; --i) {
-    float d;
-    if (R) {
-      const Corner8 c = rotate_sample(R, lin_coord(i, v.sD), gh, gw, v);
-      d = sample8(vol, c, v);
-    } else {
-      d = vol[(int64_t)i * P + pix];
+  // RM_UNROLL depth steps are sampled before any of them is consumed, so their (independent)
+  // loads are in flight together; only the running transmittance is sequential.
+  for (int i0 = v.D - 1; i0 >= 0; i0 -= RM_UNROLL) {
+    float d[RM_UNROLL];
+#pragma unroll
+    for (int u = 0; u < RM_UNROLL; ++u) {
+      const int i = i0 - u;
+      d[u] = 0.f;
+      if (i >= 0) {
+        if (R) {
+          const Corner8 c = rotate_sample(R, lin_coord(i, v.sD), gh, gw, v);
+          d[u] = sample8(vol, c, v);
+        } else {
+          d[u] = vol[(int64_t)i * P + pix];
+        }
+      }
     }
-    S += d;                                     // inclusive reverse cumsum, styler_3p.py:155
-    if (!liquid) I += d * expf(-S * tau);
+#pragma unroll
+    for (int u = 0; u < RM_UNROLL; ++u) {
+      if (i0 - u >= 0) {
+        S += d[u];                              // inclusive reverse cumsum, styler_3p.py:155
+        if (!liquid) I += d[u] * expf(-S * tau);
+      }
+    }
   }
   if (liquid) I = 1.f - expf(-S * tau);         // styler_3p.py:150-152
   img[(int64_t)view * P + pix] = I;
@@ -132,27 +148,40 @@ __global__ void raymarch_bwd_k(const float* __restrict__ vol, const float* __res
   const float gh = lin_coord(h, v.sH), gw = lin_coord(w, v.sW);
   const float gl = liquid ? gI * tau * expf(-St * tau) : 0.f;
   float below = 0.f, Pk = 0.f;
-  for (int i = 0; i < v.D; ++i) {
-    Corner8 c;
-    float d;
-    if (R) {
-      c = rotate_sample(R, lin_coord(i, v.sD), gh, gw, v);
-      d = liquid ? 0.f : sample8(vol, c, v);
-    } else {
-      d = liquid ? 0.f : vol[(int64_t)i * P + pix];
+  for (int i0 = 0; i0 < v.D; i0 += RM_UNROLL) {
+    Corner8 c[RM_UNROLL];
+    float d[RM_UNROLL];
+#pragma unroll
+    for (int u = 0; u < RM_UNROLL; ++u) {
+      const int i = i0 + u;
+      d[u] = 0.f;
+      if (i < v.D) {
+        if (R) {
+          c[u] = rotate_sample(R, lin_coord(i, v.sD), gh, gw, v);
+          if (!liquid) d[u] = sample8(vol, c[u], v);
+        } else if (!liquid) {
+          d[u] = vol[(int64_t)i * P + pix];
+        }
+      }
     }
-    float g;
-    if (liquid) {
-      g = gl;
-    } else {
-      const float T = expf(-(St - below) * tau);
-      Pk += d * T;
-      below += d;
-      g = gI * (T - tau * Pk);
+#pragma unroll
+    for (int u = 0; u < RM_UNROLL; ++u) {
+      const int i = i0 + u;
+      if (i < v.D) {
+        float g;
+        if (liquid) {
+          g = gl;
+        } else {
+          const float T = expf(-(St - below) * tau);
+          Pk += d[u] * T;
+          below += d[u];
+          g = gI * (T - tau * Pk);
+        }
+        if (R) scatter8(g_vol, c[u], v, g);
+        else if (use_atomic) atomicAdd(g_vol + (int64_t)i * P + pix, g);
+        else g_vol[(int64_t)i * P + pix] += g;
+      }
     }
-    if (R) scatter8(g_vol, c, v, g);
-    else if (use_atomic) atomicAdd(g_vol + (int64_t)i * P + pix, g);
-    else g_vol[(int64_t)i * P + pix] += g;
   }
 }
 

@@ -58,6 +58,9 @@ SIGNATURES = {
     'lnst_iterate_delta': [vp, f32, vp, vp, i32, i32, i64, vp, vp],
     'lnst_temporal_gauss': [vp, vp, i32, i64, f32, vp],
     'lnst_axpy': [vp, vp, f32, i64, vp],
+    'lnst_clip_fwd': [vp, f32, f32, vp, i64, vp],
+    'lnst_clip_bwd': [vp, vp, f32, f32, f32, vp, i64, vp],
+    'lnst_mul_bcast': [vp, vp, i32, vp, i64, vp],
     'lnst_advect': [vp, vp, i32, IP, i32, vp, vp],
 }
 # entry points that only exist in the CUDA build (tcgen05 / TMA); filled in by conv_tc.cu
@@ -65,6 +68,8 @@ CUDA_ONLY = {
     'lnst_tc_supported': [],
     'lnst_conv3x3_bf16_tc': [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp],
     'lnst_conv3x3_mixed': [vp, i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp],
+    'lnst_conv_first_fwd': [vp, vp, vp, vp, i32, i32, i32, vp],
+    'lnst_conv_first_bwd': [vp, vp, vp, i32, i32, i32, vp],
     'lnst_avgpool2_bf16_fwd': [vp, vp, i32, i32, i32, i32, vp],
     'lnst_avgpool2_bf16_bwd': [vp, vp, vp, i32, i32, i32, i32, vp],
     'lnst_f32_to_bf16': [vp, vp, i64, vp],

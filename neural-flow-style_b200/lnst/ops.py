@@ -231,6 +231,25 @@ def axpy(y, x, a):
     _lib.get().call('lnst_axpy', ptr(y), ptr(x), float(a), y.numel(), _s(y))
 
 
+def clip_fwd(x, lo, hi):
+    y = torch.empty_like(x)
+    _lib.get().call('lnst_clip_fwd', ptr(x), float(lo), float(hi), ptr(y), x.numel(), _s(x))
+    return y
+
+
+def clip_bwd(g, x, lo, hi, scale=1.0):
+    gx = torch.empty_like(x)
+    _lib.get().call('lnst_clip_bwd', ptr(g), ptr(x), float(lo), float(hi), float(scale), ptr(gx), x.numel(), _s(x))
+    return gx
+
+
+def mul_bcast(a, b):
+    """a [..., C] * b [...] (b broadcast over the last axis of a)"""
+    out = torch.empty_like(a)
+    _lib.get().call('lnst_mul_bcast', ptr(a), ptr(b), a.shape[-1], ptr(out), a.numel(), _s(a))
+    return out
+
+
 def advect(d, vel):
     """d [X,Y,(Z),C], vel [X,Y,(Z),dim] (normalised units)"""
     dim = vel.shape[-1]
@@ -261,6 +280,22 @@ def conv3x3_mixed(x, w, b, relu, out_bf16, mask=None):
     _lib.get().call('lnst_conv3x3_mixed', ptr(x), int(x.dtype == bf16), ptr(w), ptr(b), ptr(mask), ptr(y),
                     int(out_bf16), n, H, W, cin, cout, int(relu), _s(x))
     return y
+
+
+def conv_first_fwd(x, w, b):
+    """VGG conv1_1: x fp32 [n,H,W,3] -> bf16 [n,H,W,64] (bias + ReLU)."""
+    n, H, W, _ = x.shape
+    y = torch.empty(n, H, W, 64, dtype=bf16, device=x.device)
+    _lib.get().call('lnst_conv_first_fwd', ptr(x), ptr(w), ptr(b), ptr(y), n, H, W, _s(x))
+    return y
+
+
+def conv_first_bwd(g, wd):
+    """data gradient of conv1_1: g bf16 [n,H,W,64] -> fp32 [n,H,W,3]."""
+    n, H, W, _ = g.shape
+    gx = torch.empty(n, H, W, 3, dtype=f32, device=g.device)
+    _lib.get().call('lnst_conv_first_bwd', ptr(g), ptr(wd), ptr(gx), n, H, W, _s(g))
+    return gx
 
 
 def avgpool2_bf16_fwd(x):

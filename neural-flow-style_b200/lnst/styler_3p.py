@@ -223,6 +223,37 @@ class Styler(StylerBase):
                                   torch.empty_like(var))
         return var, loss_t, delta
 
+    # ---- device residency -----------------------------------------------------------------------
+    def upload(self, params):
+        """Host particle lists -> device frames.  When every frame has the same particle count the
+        particles are re-ordered ONCE by the linear index of their cell in frame 0 (same permutation
+        for all frames, so per-particle state -- variables, Adam moments, the temporal filter --
+        stays aligned); neighbouring threads then splat into / gather from neighbouring cells.
+        Returns (frames, inverse permutation or None)."""
+        dev = self.device
+        nf = self.num_frames
+        ps = [torch.as_tensor(np.asarray(params['p'][i]), dtype=f32).to(dev) for i in range(nf)]
+        rs = None
+        if 'd' in self.target_field:
+            rs = [torch.as_tensor(np.asarray(params['r'][i]), dtype=f32).to(dev) for i in range(nf)]
+        perm = inv = None
+        if getattr(self, 'sort_particles', True) and len({p.shape[0] for p in ps}) == 1 and ps[0].shape[0] > 0:
+            res = torch.tensor([float(v) for v in self.resolution], dtype=f32, device=dev)
+            c = torch.floor(ps[0] * res).clamp_(min=-1)
+            c = torch.minimum(c, res).to(torch.float64)             # out-of-domain / padding rows sort to the ends
+            r64 = res.to(torch.float64)
+            key = (c[:, 0] * (r64[1] + 2) + c[:, 1]) * (r64[2] + 2) + c[:, 2]
+            perm = torch.argsort(key, stable=True)
+            inv = torch.empty_like(perm)
+            inv[perm] = torch.arange(perm.numel(), device=dev)
+        frames = []
+        for i in range(nf):
+            fr = {'id': i, 'p': (ps[i][perm] if perm is not None else ps[i]).contiguous()}
+            if rs is not None:
+                fr['r'] = (rs[i][perm] if perm is not None else rs[i]).contiguous()
+            frames.append(fr)
+        return frames, inv
+
     # ---- the optimisation loop (styler_3p.py:229-438) ----------------------------------------------
     def run(self, params):
         dev = self.device
@@ -232,12 +263,7 @@ class Styler(StylerBase):
             lr_list = [self.lr / self.lr_scale ** i for i in range(self.octave_n)]
         oct_size = octave_sizes(self.resolution, self.octave_n, self.octave_scale)
 
-        frames = []
-        for i in range(nf):
-            fr = {'id': i, 'p': torch.as_tensor(np.asarray(params['p'][i]), dtype=f32).to(dev).contiguous()}
-            if 'd' in self.target_field:
-                fr['r'] = torch.as_tensor(np.asarray(params['r'][i]), dtype=f32).to(dev).contiguous()
-            frames.append(fr)
+        frames, inv = self.upload(params)
         width = 3 if 'p' in self.target_field else self.num_kernels
         g_opt = [torch.zeros(fr['p'].shape[0], width, dtype=f32, device=dev) for fr in frames]
         eye = True if self.rotate else False
@@ -287,6 +313,8 @@ class Styler(StylerBase):
         p_sty, v_sty, d_sty, r_sty = [], [], [], []
         for t in range(nf):
             p_out, d_out, d_img = self.infer(frames[t], g_opt[t], ws, eye)
+            if inv is not None:                                    # back to the caller's particle order
+                p_out, g_opt[t] = p_out[inv], g_opt[t][inv]
             p_sty.append(p_out.cpu().numpy())
             v_sty.append(g_opt[t].cpu().numpy())
             d_sty.append(d_out.cpu().numpy()[..., None])

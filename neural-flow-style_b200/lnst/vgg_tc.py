@@ -29,6 +29,8 @@ class TensorCoreConvs:
             if name.startswith('conv'):
                 if name in self.wp and cur.dtype == torch.bfloat16:
                     cur = ops.conv3x3_bf16_tc(cur, self.wp[name], self.net.b[name], relu=True)
+                elif cur.dtype == torch.float32 and tuple(self.net.w[name].shape[2:]) == (3, 64):
+                    cur = ops.conv_first_fwd(cur, self.net.w[name], self.net.b[name])
                 else:
                     cur = ops.conv3x3_mixed(cur, self.net.w[name], self.net.b[name], relu=True, out_bf16=True)
             else:
@@ -53,6 +55,8 @@ class TensorCoreConvs:
             if name.startswith('conv'):
                 if name in self.wdp and prev is not None:
                     g = ops.conv3x3_bf16_tc(g, self.wdp[name], None, relu=False, mask=mask)
+                elif prev is None and tuple(self.net.w[name].shape[2:]) == (3, 64):
+                    g = ops.conv_first_bwd(g, self.net.wd[name])
                 else:
                     g = ops.conv3x3_mixed(g, self.net.wd[name], None, relu=False, out_bf16=(prev is not None), mask=mask)
             else:

@@ -76,6 +76,13 @@ def test_edge_layers_pool_and_conversions():
     gx = ops.conv3x3_mixed(gy.to(dev), wd.to(dev), None, relu=False, out_bf16=False)
     want = ref_conv(gy.float(), wd, None, False)
     assert gx.dtype == torch.float32 and (gx.cpu() - want).abs().max() <= 1e-4 * want.abs().max()
+    # dedicated conv1_1 kernels
+    y1 = ops.conv_first_fwd(x.to(dev), w.to(dev), b.to(dev))
+    want = ref_conv(x, w, b, True)
+    assert (y1.float().cpu() - want).abs().max() <= 2 ** -7 * want.abs().max()
+    gx1 = ops.conv_first_bwd(gy.to(dev), wd.to(dev))
+    want = ref_conv(gy.float(), wd, None, False)
+    assert (gx1.cpu() - want).abs().max() <= 1e-4 * want.abs().max()
     a = torch.randn(2, 9, 12, 64, generator=g).to(torch.bfloat16)
     p = ops.avgpool2_bf16_fwd(a.to(dev))
     wantp = torch.nn.functional.avg_pool2d(a.float().permute(0, 3, 1, 2), 2, 2).permute(0, 2, 3, 1)
