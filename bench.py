@@ -34,8 +34,10 @@ WORKLOADS = {
                desc='smokegun-like 128^3, N=2^18 particles x 2 kernels, 1 view, VGG-19 conv2_1+conv3_1'),
     'tiny': dict(res=32, n=1 << 13, rotate=True, n_views=9, desc='debug 32^3'),
 }
-KERNELS_PER_CALL = {'lnst_splat_wavg_fwd': 2, 'lnst_image_max': 2, 'lnst_normalize_bwd': 2, 'lnst_gram_diff': 2}
-TENSOR_BOUND = ('lnst_conv3x3_f32', 'lnst_conv3x3_bf16_tc', 'lnst_gram_diff', 'lnst_gram_bwd')
+KERNELS_PER_CALL = {'lnst_splat_wavg_fwd': 2, 'lnst_image_max': 2, 'lnst_normalize_bwd': 2, 'lnst_gram_diff': 2,
+                    'lnst_gram_diff_bf16_tc': 2}
+TENSOR_BOUND = ('lnst_conv3x3_f32', 'lnst_conv3x3_bf16_tc', 'lnst_gram_diff', 'lnst_gram_bwd', 'lnst_gram_diff_bf16_tc',
+                'lnst_gram_bwd_bf16_tc')
 
 
 def make_cfg(wl, view_mode, conv_math):
@@ -77,6 +79,12 @@ def algorithmic_units(name, a, nk=2):
         n, H, W, ci, co = [v(x) for x in a[5:10]]
         eb = 4 if name.endswith('f32') else 2
         return (eb * n * H * W * (ci + co) + eb * 9 * ci * co, 2 * n * H * W * 9 * ci * co)
+    if name == 'lnst_gram_diff_bf16_tc':
+        n, P, ch = v(a[1]), v(a[2]), v(a[3])
+        return (n * (2 * P * ch + 6 * ch * ch), 2 * n * P * ch * ch)
+    if name == 'lnst_gram_bwd_bf16_tc':
+        n, H, W, ch = [v(x) for x in a[6:10]]
+        return (n * (6 * H * W * ch + 2 * ch * ch), 2 * n * H * W * ch * ch)
     if name == 'lnst_gram_diff':
         P, ch = v(a[1]), v(a[2])
         return (4 * P * ch + 4 * ch * ch, 2 * P * ch * ch)
@@ -239,9 +247,9 @@ def run_engine(args):
     loss_val = float(loss)
 
     # ---- end-to-end: host buffers in, host result out, every step (the reference's sess.run boundary) --
-    hp = torch.tensor(p[0]).pin_memory()
-    hr = torch.tensor(r[0]).pin_memory()
-    hg = torch.zeros(fr['p'].shape[0], 2).pin_memory()
+    hp = fr['p'].cpu().pin_memory()                      # host copies in the engine's (cell-sorted) order
+    hr = fr['r'].cpu().pin_memory()
+    hg = g_opt.cpu().pin_memory()
     hl = torch.zeros(1).pin_memory()
     e2e_steps = max(3, min(args.steps, 10))
     barrier()

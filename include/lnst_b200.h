@@ -138,6 +138,16 @@ int lnst_conv_first_fwd(const float* x, const float* w, const float* b, void* y,
                         int32_t W, void* stream);
 int lnst_conv_first_bwd(const void* g, const float* wd, float* gx, int32_t n, int32_t H, int32_t W,
                         void* stream);
+/* Gram matrices on tensor cores, batched over images (styler_base.py:96-102,152-185):
+ * G[i] = F[i]^T F[i] / denom - Gs (fp32 [n,C,C]; Gs NULL => no subtraction), Gd = bf16 copy of G,
+ * loss[i] += weight * sum(G[i]^2).  F bf16 [n,P,C], C a multiple of 64.  tcgen05 with MN-major
+ * operands, split-K over the pixels. */
+int lnst_gram_diff_bf16_tc(const void* F, int32_t n, int64_t P, int32_t C, float denom, const float* Gs,
+                           float weight, float* G, void* Gd, float* loss, void* stream);
+/* Gram-loss gradient on tensor cores: g = (addend + coef * F x Gd) [* (F > 0) if relu_mask].
+ * F, addend (may be NULL or == g), g: bf16 [n,H,W,C]; Gd bf16 [n,C,C] (symmetric). */
+int lnst_gram_bwd_bf16_tc(const void* F, const void* Gd, float coef, const void* addend, int32_t relu_mask,
+                          void* g, int32_t n, int32_t H, int32_t W, int32_t C, void* stream);
 int lnst_avgpool2_bf16_fwd(const void* x, void* y, int32_t n, int32_t H, int32_t W, int32_t C,
                            void* stream);
 int lnst_avgpool2_bf16_bwd(const void* g_y, const void* mask, void* g_x, int32_t n, int32_t H,

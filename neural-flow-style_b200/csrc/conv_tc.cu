@@ -113,13 +113,17 @@ struct ConvShape {
   int H, W, Cin, Cout;
   int TH, TW, tiles_w, tiles_h;
   int relu;
+  int taps;      // 9: 3x3 convolution; 1: per-pixel GEMM (Gram gradient F x G)
+  int w_img;     // 1: third coordinate of the weight map is the image index (per-image B matrix)
+  float scale;   // multiplies the accumulator before addend / bias
 };
 
+// y = mask( relu?( scale * (X (*) W) + addend + bias ) )
 template <int BLOCK_N>
 __global__ void __launch_bounds__(NUM_THREADS, 2)
 conv3x3_tc_k(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
              const float* __restrict__ bias, const __nv_bfloat16* __restrict__ mask,
-             __nv_bfloat16* __restrict__ y, ConvShape s) {
+             const __nv_bfloat16* __restrict__ addend, __nv_bfloat16* __restrict__ y, ConvShape s) {
   constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B operand tiles need 1024-byte alignment
@@ -135,7 +139,7 @@ conv3x3_tc_k(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ 
   const int tw = tile % s.tiles_w, th = (tile / s.tiles_w) % s.tiles_h, img = tile / (s.tiles_w * s.tiles_h);
   const int h0 = th * s.TH, w0 = tw * s.TW, n0 = blockIdx.y * BLOCK_N;
   const int kchunks = s.Cin / BLOCK_K;
-  const int num_kb = 9 * kchunks;
+  const int num_kb = s.taps * kchunks;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&map_x);
@@ -166,9 +170,10 @@ conv3x3_tc_k(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ 
         const uint32_t full = bars + 8 * st;
         mbar_expect_tx(full, A_BYTES + B_BYTES);
         const int tap = kb / kchunks, c0 = (kb - tap * kchunks) * BLOCK_K;
-        const int ky = tap / 3, kx = tap - 3 * ky;
+        int ky = 1, kx = 1;
+        if (s.taps == 9) { ky = tap / 3; kx = tap - 3 * ky; }
         tma_load_4d(smem_a + st * A_BYTES, &map_x, full, c0, w0 + kx - 1, h0 + ky - 1, img);
-        tma_load_3d(smem_b + st * B_BYTES, &map_w, full, c0, n0, tap);
+        tma_load_3d(smem_b + st * B_BYTES, &map_w, full, c0, n0, s.w_img ? img : tap);
       }
     }
   } else if (warp == 1) {
@@ -208,16 +213,20 @@ conv3x3_tc_k(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ 
         const int co = n0 + c * 32;
         __nv_bfloat16* dst = y + pix * s.Cout + co;
         const __nv_bfloat16* msk = mask ? mask + pix * s.Cout + co : nullptr;
+        const __nv_bfloat16* add = addend ? addend + pix * s.Cout + co : nullptr;
 #pragma unroll
         for (int j = 0; j < 32; j += 8) {
-          uint4 mv = make_uint4(0, 0, 0, 0);
+          uint4 mv = make_uint4(0, 0, 0, 0), av = make_uint4(0, 0, 0, 0);
           if (msk) mv = *reinterpret_cast<const uint4*>(msk + j);
+          if (add) av = *reinterpret_cast<const uint4*>(add + j);
           const __nv_bfloat16* mh = reinterpret_cast<const __nv_bfloat16*>(&mv);
+          const __nv_bfloat16* ah = reinterpret_cast<const __nv_bfloat16*>(&av);
           uint4 ov;
           __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&ov);
 #pragma unroll
           for (int e = 0; e < 8; e += 2) {
-            float f0 = __uint_as_float(v[j + e]), f1 = __uint_as_float(v[j + e + 1]);
+            float f0 = __uint_as_float(v[j + e]) * s.scale, f1 = __uint_as_float(v[j + e + 1]) * s.scale;
+            if (add) { f0 += __bfloat162float(ah[e]); f1 += __bfloat162float(ah[e + 1]); }
             if (bias) { f0 += bias[co + j + e]; f1 += bias[co + j + e + 1]; }
             if (s.relu) { f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); }
             if (msk) {
@@ -237,6 +246,145 @@ conv3x3_tc_k(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ 
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(BLOCK_N));
   }
+}
+
+// ---- Gram matrix G = F^T F on tensor cores ---------------------------------------------------
+// F bf16 [n, P, C] is the NHWC activation seen as P = h*w rows of C channels.  Both operands of
+// F^T F are "MN-major" for the MMA (the contraction index p is the slow one in memory), so the
+// TMA box {64 channels, 64 pixels} lands as 64 K-rows x 128 B and is consumed through an
+// MN-major SWIZZLE_128B descriptor: 64-channel groups are LBO = 8 KiB apart, 8-pixel groups
+// SBO = 1 KiB apart, one K=16 MMA step advances 2 KiB.  The pixel range is split over CTAs
+// (split-K); partial 128x128 tiles are reduced with coalesced fp32 atomics, written transposed
+// (G is symmetric) so that consecutive TMEM lanes hit consecutive addresses.
+constexpr int G_STAGES = 4;
+constexpr int G_BOX_BYTES = 64 * 128;             // one {64 ch, 64 px} box
+constexpr int G_OP_BYTES = 2 * G_BOX_BYTES;       // 128 channels x 64 pixels
+
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)(G_BOX_BYTES >> 4) << 16;        // LBO: next 64-element group along M/N
+  d |= (uint64_t)(1024 >> 4) << 32;               // SBO: next 8-row group along K
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gram_tc_k(const __grid_constant__ CUtensorMap map_f, float* __restrict__ G, int P, int C, int tiles_n,
+          int k_per_split) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t smem_a = base;
+  const uint32_t smem_b = base + G_STAGES * G_OP_BYTES;
+  const uint32_t bars = smem_b + G_STAGES * G_OP_BYTES;
+  const uint32_t tmem_slot = bars + 8 * (2 * G_STAGES + 1);
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = (blockIdx.x / tiles_n) * 128, n0 = (blockIdx.x % tiles_n) * 128;
+  const int img = blockIdx.z;
+  const int p_beg = blockIdx.y * k_per_split;
+  const int p_end = min(P, p_beg + k_per_split);
+  const int num_kb = (p_end - p_beg + 63) / 64;
+  const bool diag = (m0 == n0);
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&map_f);
+    for (int i = 0; i < G_STAGES; ++i) {
+      mbar_init(bars + 8 * i, 1);
+      mbar_init(bars + 8 * (G_STAGES + i), 1);
+    }
+    mbar_init(bars + 8 * (2 * G_STAGES), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(128));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_d = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int st = kb % G_STAGES;
+        const uint32_t ph = (kb / G_STAGES) & 1;
+        mbar_wait(bars + 8 * (G_STAGES + st), ph ^ 1);
+        const uint32_t full = bars + 8 * st;
+        mbar_expect_tx(full, diag ? G_OP_BYTES : 2 * G_OP_BYTES);
+        const int p0 = p_beg + kb * 64;
+        // rows beyond P (or beyond this split's share of a partial block) must not be counted twice:
+        // k_per_split is a multiple of 64, so only the global tail is partial and TMA zero-fills it.
+        tma_load_3d(smem_a + st * G_OP_BYTES, &map_f, full, m0, p0, img);
+        tma_load_3d(smem_a + st * G_OP_BYTES + G_BOX_BYTES, &map_f, full, m0 + 64, p0, img);
+        if (!diag) {
+          tma_load_3d(smem_b + st * G_OP_BYTES, &map_f, full, n0, p0, img);
+          tma_load_3d(smem_b + st * G_OP_BYTES + G_BOX_BYTES, &map_f, full, n0 + 64, p0, img);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // kind::f16, BF16 x BF16 -> F32, both operands MN-major (bits 15 and 16), M = N = 128
+      const uint32_t idesc = umma_idesc_bf16(128, 128) | (1u << 15) | (1u << 16);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int st = kb % G_STAGES;
+        const uint32_t ph = (kb / G_STAGES) & 1;
+        mbar_wait(bars + 8 * st, ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t a0 = smem_a + st * G_OP_BYTES;
+        const uint32_t b0 = diag ? a0 : smem_b + st * G_OP_BYTES;
+#pragma unroll
+        for (int k = 0; k < 64 / UMMA_K; ++k)
+          umma_bf16(tmem_d, umma_desc_mn_sw128(a0 + k * 2048), umma_desc_mn_sw128(b0 + k * 2048), idesc,
+                    (kb | k) != 0 ? 1u : 0u);
+        umma_commit(bars + 8 * (G_STAGES + st));
+      }
+      umma_commit(bars + 8 * (2 * G_STAGES));
+    }
+  } else if (num_kb > 0) {
+    const int q = warp & 3;
+    const int m = m0 + q * 32 + lane;
+    mbar_wait(bars + 8 * (2 * G_STAGES), 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    float* Gi = G + (int64_t)img * C * C;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      uint32_t v[32];
+      tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+      if (m < C) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int nn = n0 + c * 32 + j;
+          if (nn < C) atomicAdd(Gi + (int64_t)nn * C + m, __uint_as_float(v[j]));   // transposed: G symmetric
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(128));
+  }
+}
+
+// G <- G/denom - Gs (fp32, in place), bf16 copy for the gradient GEMM, loss[img] += weight * sum(G^2)
+__global__ void gram_finish_bf16_k(float* __restrict__ G, const float* __restrict__ Gs, __nv_bfloat16* __restrict__ Gd,
+                                   int n_el, float inv_denom, float weight, float* __restrict__ loss) {
+  const int img = blockIdx.y;
+  float s = 0.f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_el; i += gridDim.x * blockDim.x) {
+    float d = G[(int64_t)img * n_el + i] * inv_denom;
+    if (Gs) { d -= Gs[i]; s += d * d; }
+    G[(int64_t)img * n_el + i] = d;
+    if (Gd) Gd[(int64_t)img * n_el + i] = __float2bfloat16_rn(d);
+  }
+  s = lnst_warp_sum(s);
+  if (loss && Gs && (threadIdx.x & 31) == 0 && s != 0.f) atomicAdd(loss + img, weight * s);
 }
 
 // ---- host side: tensor maps ------------------------------------------------------------------
@@ -269,7 +417,8 @@ static bool make_map(CUtensorMap* m, const void* ptr, int rank, const cuuint64_t
 
 template <int BLOCK_N>
 static int launch_conv(const CUtensorMap& mx, const CUtensorMap& mw, const float* bias, const __nv_bfloat16* mask,
-                       __nv_bfloat16* y, const ConvShape& s, int n_img, cudaStream_t stream) {
+                       const __nv_bfloat16* addend, __nv_bfloat16* y, const ConvShape& s, int n_img,
+                       cudaStream_t stream) {
   const int smem = STAGES * (A_BYTES + BLOCK_N * BLOCK_K * 2) + 8 * (2 * STAGES + 1) + 16 + 1024;
   static bool configured = false;
   if (!configured) {
@@ -278,7 +427,7 @@ static int launch_conv(const CUtensorMap& mx, const CUtensorMap& mw, const float
     configured = true;
   }
   dim3 grid(s.tiles_w * s.tiles_h * n_img, s.Cout / BLOCK_N);
-  conv3x3_tc_k<BLOCK_N><<<grid, NUM_THREADS, smem, stream>>>(mx, mw, bias, mask, y, s);
+  conv3x3_tc_k<BLOCK_N><<<grid, NUM_THREADS, smem, stream>>>(mx, mw, bias, mask, addend, y, s);
   return (int)cudaGetLastError();
 }
 
@@ -483,14 +632,17 @@ extern "C" int lnst_conv_first_bwd(const void* g, const float* wd, float* gx, in
 
 extern "C" int lnst_tc_supported(void) { return tc::encode_fn() != nullptr ? 1 : 0; }
 
-extern "C" int lnst_conv3x3_bf16_tc(const void* x, const void* w_packed, const float* bias, const void* mask,
-                                    void* y, int32_t n, int32_t H, int32_t W, int32_t Cin, int32_t Cout,
-                                    int32_t relu, void* stream) {
+// shared host path of the 3x3 convolution (taps = 9, one weight set) and the per-pixel GEMM
+// (taps = 1, one B matrix per image)
+static int run_tc_gemm(const void* x, const void* wmat, const float* bias, const void* mask, const void* addend,
+                       void* y, int n, int H, int W, int Cin, int Cout, int relu, int taps, int w_img, float scale,
+                       void* stream) {
   using namespace tc;
-  if (!x || !w_packed || !y || n < 1 || H < 1 || W < 1 || Cin < 64 || Cout < 64 || Cin % 64 || Cout % 64)
+  if (!x || !wmat || !y || n < 1 || H < 1 || W < 1 || Cin < 64 || Cout < 64 || Cin % 64 || Cout % 64)
     return LNST_EARG;
   ConvShape s;
   s.H = H; s.W = W; s.Cin = Cin; s.Cout = Cout; s.relu = relu;
+  s.taps = taps; s.w_img = w_img; s.scale = scale;
   pick_tile(H, W, s.TH, s.TW);
   s.tiles_w = (W + s.TW - 1) / s.TW;
   s.tiles_h = (H + s.TH - 1) / s.TH;
@@ -503,14 +655,69 @@ extern "C" int lnst_conv3x3_bf16_tc(const void* x, const void* w_packed, const f
     if (!make_map(&mx, x, 4, dims, strides, box)) return LNST_EARG;
   }
   {
-    const cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)Cout, 9};
+    const cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)Cout, (cuuint64_t)(w_img ? n : taps)};
     const cuuint64_t strides[2] = {(cuuint64_t)Cin * 2, (cuuint64_t)Cout * Cin * 2};
     const cuuint32_t box[3] = {(cuuint32_t)BLOCK_K, (cuuint32_t)BN, 1};
-    if (!make_map(&mw, w_packed, 3, dims, strides, box)) return LNST_EARG;
+    if (!make_map(&mw, wmat, 3, dims, strides, box)) return LNST_EARG;
   }
   if (BN == 128)
-    return launch_conv<128>(mx, mw, bias, (const __nv_bfloat16*)mask, (__nv_bfloat16*)y, s, n, lnst_stream(stream));
-  return launch_conv<64>(mx, mw, bias, (const __nv_bfloat16*)mask, (__nv_bfloat16*)y, s, n, lnst_stream(stream));
+    return launch_conv<128>(mx, mw, bias, (const __nv_bfloat16*)mask, (const __nv_bfloat16*)addend,
+                            (__nv_bfloat16*)y, s, n, lnst_stream(stream));
+  return launch_conv<64>(mx, mw, bias, (const __nv_bfloat16*)mask, (const __nv_bfloat16*)addend, (__nv_bfloat16*)y,
+                         s, n, lnst_stream(stream));
+}
+
+extern "C" int lnst_conv3x3_bf16_tc(const void* x, const void* w_packed, const float* bias, const void* mask,
+                                    void* y, int32_t n, int32_t H, int32_t W, int32_t Cin, int32_t Cout,
+                                    int32_t relu, void* stream) {
+  return run_tc_gemm(x, w_packed, bias, mask, nullptr, y, n, H, W, Cin, Cout, relu, 9, 0, 1.0f, stream);
+}
+
+// Gram-loss gradient on tensor cores: g[img] = (addend + coef * F[img] x Gd[img]) * (F > 0 if relu_mask).
+// F bf16 [n,H,W,C] (post-ReLU features), Gd bf16 [n,C,C] (symmetric: rows are K-major), g bf16.
+extern "C" int lnst_gram_bwd_bf16_tc(const void* F, const void* Gd, float coef, const void* addend,
+                                     int32_t relu_mask, void* g, int32_t n, int32_t H, int32_t W, int32_t C,
+                                     void* stream) {
+  return run_tc_gemm(F, Gd, nullptr, relu_mask ? F : nullptr, addend, g, n, H, W, C, C, 0, 1, 1, coef, stream);
+}
+
+// Gram difference on tensor cores, batched over images: G[i] = F[i]^T F[i] / denom - Gs (fp32, [n,C,C]),
+// Gd = bf16 copy of G (operand of lnst_gram_bwd_bf16_tc), loss[i] += weight * sum(G[i]^2).
+// F bf16 [n,P,C]; Gs fp32 [C,C] or NULL (then G = F^T F / denom: the style-target pass).
+extern "C" int lnst_gram_diff_bf16_tc(const void* F, int32_t n, int64_t P, int32_t C, float denom, const float* Gs,
+                                      float weight, float* G, void* Gd, float* loss, void* stream) {
+  using namespace tc;
+  if (!F || !G || n < 1 || P < 1 || C < 64 || C % 64 || !(denom > 0.f) || P > 0x7fffffff) return LNST_EARG;
+  cudaStream_t st = lnst_stream(stream);
+  CUtensorMap mf;
+  {
+    const cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)P, (cuuint64_t)n};
+    const cuuint64_t strides[2] = {(cuuint64_t)C * 2, (cuuint64_t)P * C * 2};
+    const cuuint32_t box[3] = {64, 64, 1};
+    if (!make_map(&mf, F, 3, dims, strides, box)) return LNST_EARG;
+  }
+  const int tiles_n = (C + 127) / 128;
+  const int tiles = tiles_n * tiles_n;
+  int splits = (2 * 148 + tiles * n - 1) / (tiles * n);
+  const int max_splits = (int)((P + 255) / 256);              // at least 4 K-blocks per CTA
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  int kps = (int)((P + splits - 1) / splits);
+  kps = ((kps + 63) / 64) * 64;
+  splits = (int)((P + kps - 1) / kps);
+  const int smem = 2 * G_STAGES * G_OP_BYTES + 8 * (2 * G_STAGES + 1) + 16 + 1024;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gram_tc_k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  cudaMemsetAsync(G, 0, sizeof(float) * (size_t)n * C * C, st);
+  gram_tc_k<<<dim3(tiles, splits, n), NUM_THREADS, smem, st>>>(mf, G, (int)P, (int)C, tiles_n, kps);
+  const int n_el = C * C;
+  const unsigned nb = lnst_blocks(n_el, 256) > 32 ? 32 : lnst_blocks(n_el, 256);
+  gram_finish_bf16_k<<<dim3(nb, n), 256, 0, st>>>(G, Gs, (__nv_bfloat16*)Gd, n_el, 1.f / denom, weight, loss);
+  return lnst_status();
 }
 
 // CUDA-core convolution with mixed I/O types for the thin edge layers (conv1_1: Cin = 3; its

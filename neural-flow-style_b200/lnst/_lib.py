@@ -68,6 +68,8 @@ CUDA_ONLY = {
     'lnst_tc_supported': [],
     'lnst_conv3x3_bf16_tc': [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp],
     'lnst_conv3x3_mixed': [vp, i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp],
+    'lnst_gram_diff_bf16_tc': [vp, i32, i64, i32, f32, vp, f32, vp, vp, vp, vp],
+    'lnst_gram_bwd_bf16_tc': [vp, vp, f32, vp, i32, vp, i32, i32, i32, i32, vp],
     'lnst_conv_first_fwd': [vp, vp, vp, vp, i32, i32, i32, vp],
     'lnst_conv_first_bwd': [vp, vp, vp, i32, i32, i32, vp],
     'lnst_avgpool2_bf16_fwd': [vp, vp, i32, i32, i32, i32, vp],

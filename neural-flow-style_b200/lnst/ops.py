@@ -282,6 +282,25 @@ def conv3x3_mixed(x, w, b, relu, out_bf16, mask=None):
     return y
 
 
+def gram_diff_bf16_tc(F, denom, Gs, weight, loss, want_bf16=True):
+    """F bf16 [n,h,w,C] -> (G fp32 [n,C,C] = F^T F/denom - Gs, Gd bf16 copy); loss[n] += weight*sum(G^2)."""
+    n, h, w, ch = F.shape
+    G = torch.empty(n, ch, ch, dtype=f32, device=F.device)
+    Gd = torch.empty(n, ch, ch, dtype=bf16, device=F.device) if want_bf16 else None
+    _lib.get().call('lnst_gram_diff_bf16_tc', ptr(F), n, h * w, ch, float(denom), ptr(Gs), float(weight), ptr(G),
+                    ptr(Gd), ptr(loss), _s(F))
+    return G, Gd
+
+
+def gram_bwd_bf16_tc(F, Gd, coef, addend, relu_mask, g=None):
+    n, h, w, ch = F.shape
+    if g is None:
+        g = torch.empty_like(F)
+    _lib.get().call('lnst_gram_bwd_bf16_tc', ptr(F), ptr(Gd), float(coef), ptr(addend), int(relu_mask), ptr(g), n, h,
+                    w, ch, _s(F))
+    return g
+
+
 def conv_first_fwd(x, w, b):
     """VGG conv1_1: x fp32 [n,H,W,3] -> bf16 [n,H,W,64] (bias + ReLU)."""
     n, H, W, _ = x.shape

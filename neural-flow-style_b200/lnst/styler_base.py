@@ -99,12 +99,19 @@ class StylerBase(object):
         acts = self.net.forward(x, list(self.style_layer))
         grams = []
         for l in self.style_layer:
-            f = x[0] if 'input' in l else acts[l][0]
-            P, ch = f.shape[0] * f.shape[1], f.shape[2]
-            G = torch.empty(ch, ch, dtype=f32, device=self.device)
-            ops.gram_diff(f.reshape(P, ch), 2.0 * P * ch, None, 0.0, G, None)
-            grams.append(G)
+            if 'input' in l:
+                raise NotImplementedError("style layer 'input' is not built")
+            handle = self.net.gram(acts, l, None, 0.0, None)
+            grams.append(self.net.gram_values(handle)[0].contiguous())
         return grams
+
+    @staticmethod
+    def _feature_pixels(h, w, name):
+        """h*w of end point ``name`` for an h x w input (2x2/2 VALID pooling between blocks)."""
+        block = int(name[4]) if name.startswith('conv') else int(name[4]) + 1
+        for _ in range(block - 1):
+            h, w = h // 2, w // 2
+        return h * w
 
     def _content_feature(self, content_target, content_shp):
         raise NotImplementedError('content target images (styler_base.py:233-247) are not built yet; '
@@ -119,37 +126,24 @@ class StylerBase(object):
         wanted = self._wanted()
         style_on = bool(self.w_style) and style_grams is not None
         acts = self.net.forward(x, wanted) if wanted else {}
-        diffs = {}
+        shapes = {}
+        handles = {}
         if style_on:
             for li, l in enumerate(self.style_layer):
-                f = acts[l]
-                P, ch = f.shape[1] * f.shape[2], f.shape[3]
-                for v in range(n):
-                    G = torch.empty(ch, ch, dtype=f32, device=self.device)
-                    ops.gram_diff(f[v].reshape(P, ch), 2.0 * P * ch, style_grams[li],
-                                  self.w_style * self.w_style_layer[li], G, loss[v:v + 1])
-                    diffs[(l, v)] = G
+                handles[l] = self.net.gram(acts, l, style_grams[li], self.w_style * self.w_style_layer[li], loss)
 
-        def add_loss_grad(name, act, g):
+        def add_loss_grad(name, g):
             is_conv = 1 if name.startswith('conv') else 0
-            P, ch = act.shape[1] * act.shape[2], act.shape[3]
             if style_on:
                 for li, l in enumerate(self.style_layer):
                     if l != name:
                         continue
-                    beta = 1.0
-                    if g is None:
-                        g, beta = torch.empty_like(act), 0.0
+                    ch = style_grams[li].shape[0]
+                    P = self._feature_pixels(x.shape[1], x.shape[2], name)
                     coef = self.w_style * self.w_style_layer[li] * 4.0 / (2.0 * P * ch)
-                    for v in range(n):
-                        ops.gram_bwd(act[v].reshape(P, ch), diffs[(l, v)], coef, beta, is_conv, g[v].reshape(P, ch))
+                    g = self.net.gram_grad(acts, name, handles[l], coef, g, is_conv)
             if self.w_content and self.content_layer == name:
-                beta = 1.0
-                if g is None:
-                    g, beta = torch.empty_like(act), 0.0
-                for v in range(n):
-                    ops.content_loss(act[v].reshape(P, ch), self.content_channel, self.w_content,
-                                     loss[v:v + 1], g[v].reshape(P, ch), beta, is_conv)
+                g = self.net.content(acts, name, self.content_channel, self.w_content, loss, g, is_conv)
             return g
 
         g_x = self.net.backward(x, acts, wanted, add_loss_grad, set(wanted)) if wanted else None

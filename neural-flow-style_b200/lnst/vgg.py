@@ -106,10 +106,11 @@ class LossNet:
 
     # ---- backward --------------------------------------------------------------------------
     def backward(self, x, acts, wanted, add_loss_grad, loss_layers):
-        """d loss / d x.  For every end point in ``loss_layers``, ``add_loss_grad(name, act, g)``
-        adds the loss terms that live there into ``g`` (None = nothing accumulated yet; it then
-        allocates) and returns the buffer.  Gradients held for conv end points are w.r.t. the
-        PRE-activation (ReLU mask already applied)."""
+        """d loss / d x.  For every end point in ``loss_layers``, ``add_loss_grad(name, g)`` adds
+        the loss terms that live there into ``g`` (None = nothing accumulated yet) through
+        ``gram_grad`` / ``content`` below and returns the buffer.  Gradients held for conv end
+        points are w.r.t. the PRE-activation (ReLU mask already applied).  ``g`` is in the back
+        end's native type (fp32 or bf16)."""
         if self.math == 'bf16':
             return self.tc.backward(x, acts, self.prefix(wanted), add_loss_grad, loss_layers)
         layers = self.prefix(wanted)
@@ -117,7 +118,7 @@ class LossNet:
         for i in range(len(layers) - 1, -1, -1):
             name = layers[i]
             if name in loss_layers:
-                g = add_loss_grad(name, acts[name], g)
+                g = add_loss_grad(name, g)
             if g is None:
                 continue
             prev = layers[i - 1] if i > 0 else None
@@ -127,4 +128,52 @@ class LossNet:
                 g = ops.conv3x3_f32(g, self.wd[name], None, relu=False, mask=mask)
             else:
                 g = ops.avgpool2_bwd(g, mask, prev_act.shape)
+        return g
+
+    # ---- losses on end points (styler_base.py:96-102,135-185) -------------------------------------
+    def features_f32(self, acts, name):
+        return acts[name]            # fp32 in both back ends (the tensor-core store converts on demand)
+
+    def gram(self, acts, name, Gs, weight, loss):
+        """Per image v: G_v = F_v^T F_v/(2 h w C) - Gs; loss[v] += weight*sum(G_v^2).  Gs None: no
+        subtraction (style-target pass).  Returns a handle for ``gram_grad`` / ``gram_values``."""
+        if self.math == 'bf16':
+            return self.tc.gram(acts, name, Gs, weight, loss)
+        f = acts[name]
+        n, P, ch = f.shape[0], f.shape[1] * f.shape[2], f.shape[3]
+        out = []
+        for v in range(n):
+            G = torch.empty(ch, ch, dtype=torch.float32, device=self.device)
+            ops.gram_diff(f[v].reshape(P, ch), 2.0 * P * ch, Gs, weight, G, loss[v:v + 1] if loss is not None else None)
+            out.append(G)
+        return out
+
+    def gram_values(self, handle):
+        """fp32 [n,C,C] view of a ``gram`` handle."""
+        return handle[0] if self.math == 'bf16' else torch.stack(handle, 0)
+
+    def gram_grad(self, acts, name, handle, coef, g, relu_mask):
+        """g <- (g + coef * F G) [* (F > 0)]; allocates g when None."""
+        if self.math == 'bf16':
+            return self.tc.gram_grad(acts, name, handle, coef, g, relu_mask)
+        f = acts[name]
+        n, P, ch = f.shape[0], f.shape[1] * f.shape[2], f.shape[3]
+        beta = 1.0
+        if g is None:
+            g, beta = torch.empty_like(f), 0.0
+        for v in range(n):
+            ops.gram_bwd(f[v].reshape(P, ch), handle[v], coef, beta, relu_mask, g[v].reshape(P, ch))
+        return g
+
+    def content(self, acts, name, channel, weight, loss, g, relu_mask):
+        """Channel-activation content loss (styler_base.py:143-148) on end point ``name``."""
+        if self.math == 'bf16':
+            return self.tc.content(acts, name, channel, weight, loss, g, relu_mask)
+        f = acts[name]
+        n, P, ch = f.shape[0], f.shape[1] * f.shape[2], f.shape[3]
+        beta = 1.0
+        if g is None:
+            g, beta = torch.empty_like(f), 0.0
+        for v in range(n):
+            ops.content_loss(f[v].reshape(P, ch), channel, weight, loss[v:v + 1], g[v].reshape(P, ch), beta, relu_mask)
         return g

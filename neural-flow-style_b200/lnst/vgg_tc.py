@@ -1,7 +1,9 @@
 """Tensor-core back end of the loss network (``csrc/conv_tc.cu``): bf16 NHWC activations, tcgen05
-implicit-GEMM convolutions for every layer with >= 64 input and output channels, CUDA-core
-mixed-precision kernels for conv1_1 and its data gradient.  Loss kernels work on fp32 copies of the
-(few) style/content end points."""
+implicit-GEMM convolutions for every layer with >= 64 input and output channels, dedicated
+CUDA-core kernels for conv1_1 (K = 27) and its data gradient, tcgen05 Gram matrices (F^T F,
+MN-major operands, split-K) and Gram gradients (F x G, same kernel as the convolution with one
+tap and a per-image B matrix).  Activations and gradients stay bf16 end to end; Gram matrices
+and losses are fp32."""
 import torch
 
 from . import ops
@@ -21,8 +23,9 @@ class TensorCoreConvs:
                 self.wp[name] = _pack(w)
                 self.wdp[name] = _pack(net.wd[name])
 
+    # ---- network ----------------------------------------------------------------------------------
     def forward(self, x, layers):
-        """x fp32 [n,H,W,3].  Returns {name: bf16 activation}; fp32 views are made on demand."""
+        """x fp32 [n,H,W,3].  Returns the activation store (bf16 tensors, fp32 copies on demand)."""
         acts = {}
         cur = x
         for name in layers:
@@ -43,10 +46,7 @@ class TensorCoreConvs:
         for i in range(len(layers) - 1, -1, -1):
             name = layers[i]
             if name in loss_layers:
-                # loss terms live in fp32: convert, accumulate, convert back (style layers only)
-                g32 = add_loss_grad(name, acts[name], ops.to_f32(g) if g is not None else None)
-                if g32 is not None:
-                    g = ops.to_bf16(g32)
+                g = add_loss_grad(name, g)
             if g is None:
                 continue
             prev = layers[i - 1] if i > 0 else None
@@ -63,10 +63,30 @@ class TensorCoreConvs:
                 g = ops.avgpool2_bf16_bwd(g, mask, prev_act.shape)
         return g
 
+    # ---- losses -------------------------------------------------------------------------------------
+    def gram(self, acts, name, Gs, weight, loss):
+        F = acts.raw[name]
+        P, ch = F.shape[1] * F.shape[2], F.shape[3]
+        if ch % 64:
+            raise NotImplementedError('tensor-core Gram needs a channel count that is a multiple of 64')
+        return ops.gram_diff_bf16_tc(F, 2.0 * P * ch, Gs, weight, loss)
+
+    def gram_grad(self, acts, name, handle, coef, g, relu_mask):
+        return ops.gram_bwd_bf16_tc(acts.raw[name], handle[1], coef, g, relu_mask, g)
+
+    def content(self, acts, name, channel, weight, loss, g, relu_mask):
+        f = acts[name]                                          # fp32 copy
+        n, P, ch = f.shape[0], f.shape[1] * f.shape[2], f.shape[3]
+        g32 = ops.to_f32(g) if g is not None else torch.empty_like(f)
+        for v in range(n):
+            ops.content_loss(f[v].reshape(P, ch), channel, weight, loss[v:v + 1], g32[v].reshape(P, ch),
+                             1.0 if g is not None else 0.0, relu_mask)
+        return ops.to_bf16(g32)
+
 
 class _Acts:
-    """Activation store: ``raw`` holds the bf16 tensors; ``acts[name]`` hands the loss kernels an
-    fp32 copy (made on first use, cached)."""
+    """Activation store: ``raw`` holds the bf16 tensors; ``acts[name]`` hands out an fp32 copy
+    (made on first use, cached)."""
 
     def __init__(self, raw):
         self.raw, self._f32 = raw, {}

@@ -98,6 +98,34 @@ def test_edge_layers_pool_and_conversions():
     assert torch.equal(ops.to_f32(z.to(torch.bfloat16).to(dev)).cpu(), z.to(torch.bfloat16).float())
 
 
+@pytest.mark.parametrize('n,h,w,ch', [(1, 8, 8, 64), (2, 50, 50, 256), (3, 100, 100, 128), (1, 13, 7, 512)])
+def test_gram_tc_forward_and_gradient(n, h, w, ch):
+    """F^T F on tensor cores (MN-major operands, split-K) and its gradient F x G."""
+    dev = torch.device('cuda:0')
+    g = torch.Generator().manual_seed(h * 7 + ch)
+    F = torch.relu(torch.randn(n, h, w, ch, generator=g)).to(torch.bfloat16)
+    Fs = torch.relu(torch.randn(1, h, w, ch, generator=g)).to(torch.bfloat16)
+    P = h * w
+    den = 2.0 * P * ch
+    Gs, _ = ops.gram_diff_bf16_tc(Fs.to(dev), den, None, 0.0, None, want_bf16=False)
+    want_s = torch.einsum('pc,pd->cd', Fs.float().reshape(P, ch), Fs.float().reshape(P, ch)) / den
+    assert (Gs[0].cpu() - want_s).abs().max() <= 1e-4 * want_s.abs().max()
+    loss = torch.zeros(n, device=dev)
+    G, Gd = ops.gram_diff_bf16_tc(F.to(dev), den, Gs[0].contiguous(), 0.7, loss)
+    Ff = F.float().reshape(n, P, ch)
+    want = torch.einsum('npc,npd->ncd', Ff, Ff) / den - want_s
+    assert (G.cpu() - want).abs().max() <= 2e-4 * (want.abs().max() + want_s.abs().max())
+    want_loss = 0.7 * (want ** 2).sum(dim=(1, 2))
+    np.testing.assert_allclose(loss.cpu().numpy(), want_loss.numpy(), rtol=2e-3)
+    # gradient: (addend + coef * F G) * (F > 0), with G rounded to bf16 like the kernel's operand
+    add = torch.randn(n, h, w, ch, generator=g).to(torch.bfloat16)
+    coef = 0.37
+    out = ops.gram_bwd_bf16_tc(F.to(dev), Gd, coef, add.to(dev), 1)
+    ref = (add.float().reshape(n, P, ch) + coef * torch.einsum('npc,ncd->npd', Ff, Gd.float().cpu())) * (Ff > 0)
+    err = (out.float().cpu().reshape(n, P, ch) - ref).abs().max().item()
+    assert err <= 2 ** -7 * ref.abs().max().item(), err
+
+
 def test_lossnet_bf16_against_fp32_features_and_gradient():
     """Whole prefix to conv3_1 on tensor cores vs the fp32 CUDA-core path on the same input."""
     from lnst.vgg import LossNet
@@ -112,13 +140,17 @@ def test_lossnet_bf16_against_fp32_features_and_gradient():
         rel = (a16[l] - a32[l]).norm() / a32[l].norm()
         assert rel < 2e-2, (l, rel.item())
 
-    def top_grad(name, act, g):
-        if name != 'conv3_1':
-            return g
-        return (act > 0).float() * torch.sin(torch.arange(act.numel(), device=dev).reshape(act.shape) * 0.37)
+    def top_grad(acts, as_bf16):
+        def fn(name, g):
+            if name != 'conv3_1':
+                return g
+            act = acts[name]                                        # fp32 view in both back ends
+            t = (act > 0).float() * torch.sin(torch.arange(act.numel(), device=dev).reshape(act.shape) * 0.37)
+            return t.to(torch.bfloat16) if as_bf16 else t
+        return fn
 
-    g32 = n32.backward(x, a32, wanted, top_grad, {'conv3_1'})
-    g16 = n16.backward(x, a16, wanted, top_grad, {'conv3_1'})
+    g32 = n32.backward(x, a32, wanted, top_grad(a32, False), {'conv3_1'})
+    g16 = n16.backward(x, a16, wanted, top_grad(a16, True), {'conv3_1'})
     # bf16 perturbs activations by ~1e-2 relative; the ~1% of units whose pre-activation sits that
     # close to zero flip their ReLU mask, which alone is ~sqrt(0.01) = 10% L2 noise on a noise-like
     # top gradient (the gradient of a ReLU net is discontinuous); measured 0.09.
