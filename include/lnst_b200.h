@@ -84,6 +84,10 @@ int lnst_raymarch_bwd(const float* vol, const float* rot, int32_t n_views, int32
                       int32_t W, float tau, int32_t liquid, const float* stot, const float* g_img,
                       float* g_vol, void* stream);
 
+/* Tuning switch for lnst_raymarch_bwd (process-wide, default 1): 1 = neighbouring lanes merge their
+ * shared x-corner contributions by warp shuffle before the atomics; 0 = eight atomics per sample. */
+int lnst_set_raymarch_merge(int32_t on);
+
 /* ---- image glue (styler_3p.py:158; styler_base.py:33-45; vgg.py:50-53) -------------------- */
 /* stats[2*v+0] = max over image v, stats[2*v+1] = number of pixels attaining it. */
 int lnst_image_max(const float* img, int32_t n_img, int64_t n_pix, float* stats, void* stream);

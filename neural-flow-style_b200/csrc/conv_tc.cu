@@ -526,86 +526,136 @@ __global__ void avgpool2_bf16_bwd_k(const __nv_bfloat16* __restrict__ gy, const 
 }
 
 // ---- conv1_1 (3 -> 64) and its data gradient (64 -> 3): K = 27, far too thin for an MMA tile ----
-// forward: 8 threads per pixel, 8 output channels each; the 27 inputs are shared by the 8 lanes.
+// forward: a thread computes FP x 8 outputs (FP consecutive pixels of a row, 8 channels); every weight
+// float4 fetched from shared memory feeds FP FMAs per lane, the (FP+2) x 3 x 3 input window is read
+// once per tap row (the 8 lanes of a pixel group read the same addresses: one broadcast transaction).
+constexpr int FP = 4;
 __global__ void __launch_bounds__(256) conv_first_fwd_k(const float* __restrict__ x, const float* __restrict__ w,
                                                         const float* __restrict__ b, __nv_bfloat16* __restrict__ y,
                                                         int n, int H, int W) {
-  __shared__ float ws[27 * 64];
+  __shared__ __align__(16) float ws[27 * 64];
   __shared__ float bs[64];
   for (int i = threadIdx.x; i < 27 * 64; i += blockDim.x) ws[i] = w[i];
   if (threadIdx.x < 64) bs[threadIdx.x] = b ? b[threadIdx.x] : 0.f;
   __syncthreads();
+  const int WG = (W + FP - 1) / FP;
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t pix = t >> 3;
+  const int64_t grp = t >> 3;
   const int cg = (int)(t & 7) * 8;
-  if (pix >= (int64_t)n * H * W) return;
-  const int px = (int)(pix % W), py = (int)((pix / W) % H);
-  const int64_t img = pix / ((int64_t)W * H);
-  float acc[8];
+  if (grp >= (int64_t)n * H * WG) return;
+  const int px = (int)(grp % WG) * FP, py = (int)((grp / WG) % H);
+  const int64_t img = grp / ((int64_t)WG * H);
+  float acc[FP][8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) acc[j] = bs[cg + j];
+  for (int p = 0; p < FP; ++p)
 #pragma unroll
-  for (int ky = 0; ky < 3; ++ky) {
-    const int yy = py + ky - 1;
+    for (int j = 0; j < 8; ++j) acc[p][j] = bs[cg + j];
 #pragma unroll
-    for (int kx = 0; kx < 3; ++kx) {
-      const int xx = px + kx - 1;
-      if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
-      const float* src = x + ((img * H + yy) * W + xx) * 3;
-#pragma unroll
-      for (int ci = 0; ci < 3; ++ci) {
-        const float xv = src[ci];
-        const float4* wr = reinterpret_cast<const float4*>(ws + ((ky * 3 + kx) * 3 + ci) * 64 + cg);
-        const float4 w0 = wr[0], w1 = wr[1];
-        acc[0] = fmaf(xv, w0.x, acc[0]); acc[1] = fmaf(xv, w0.y, acc[1]);
-        acc[2] = fmaf(xv, w0.z, acc[2]); acc[3] = fmaf(xv, w0.w, acc[3]);
-        acc[4] = fmaf(xv, w1.x, acc[4]); acc[5] = fmaf(xv, w1.y, acc[5]);
-        acc[6] = fmaf(xv, w1.z, acc[6]); acc[7] = fmaf(xv, w1.w, acc[7]);
-      }
-    }
-  }
-  uint4 o;
-  __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
-#pragma unroll
-  for (int j = 0; j < 4; ++j) oh[j] = __floats2bfloat162_rn(fmaxf(acc[2 * j], 0.f), fmaxf(acc[2 * j + 1], 0.f));
-  *reinterpret_cast<uint4*>(y + pix * 64 + cg) = o;
-}
-
-// data gradient: one thread per pixel, 9 taps x 64 channels x 3 outputs; wd fp32 [3,3,64,3]
-__global__ void __launch_bounds__(128) conv_first_bwd_k(const __nv_bfloat16* __restrict__ g,
-                                                        const float* __restrict__ wd, float* __restrict__ gx,
-                                                        int n, int H, int W) {
-  __shared__ float ws[9 * 64 * 3];
-  for (int i = threadIdx.x; i < 9 * 64 * 3; i += blockDim.x) ws[i] = wd[i];
-  __syncthreads();
-  const int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (pix >= (int64_t)n * H * W) return;
-  const int px = (int)(pix % W), py = (int)((pix / W) % H);
-  const int64_t img = pix / ((int64_t)W * H);
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f;
   for (int ky = 0; ky < 3; ++ky) {
     const int yy = py + ky - 1;
     if (yy < 0 || yy >= H) continue;
+    const float* row = x + (img * H + yy) * (int64_t)W * 3;
+    float in[(FP + 2) * 3];
+#pragma unroll
+    for (int c = 0; c < FP + 2; ++c) {
+      const int xx = px + c - 1;
+      const bool ok = xx >= 0 && xx < W;
+#pragma unroll
+      for (int ci = 0; ci < 3; ++ci) in[c * 3 + ci] = ok ? row[xx * 3 + ci] : 0.f;
+    }
+#pragma unroll
     for (int kx = 0; kx < 3; ++kx) {
-      const int xx = px + kx - 1;
-      if (xx < 0 || xx >= W) continue;
-      const uint4* src = reinterpret_cast<const uint4*>(g + ((img * H + yy) * W + xx) * 64);
-      const float* wt = ws + (ky * 3 + kx) * 64 * 3;
 #pragma unroll
-      for (int v = 0; v < 8; ++v) {
-        const uint4 q = src[v];
-        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+      for (int ci = 0; ci < 3; ++ci) {
+        const float4* wr = reinterpret_cast<const float4*>(ws + ((ky * 3 + kx) * 3 + ci) * 64 + cg);
+        const float4 w0 = wr[0], w1 = wr[1];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float2 f = __bfloat1622float2(h[e]);
-          const float* w0 = wt + (v * 8 + e * 2) * 3;
-          a0 = fmaf(f.x, w0[0], a0); a1 = fmaf(f.x, w0[1], a1); a2 = fmaf(f.x, w0[2], a2);
-          a0 = fmaf(f.y, w0[3], a0); a1 = fmaf(f.y, w0[4], a1); a2 = fmaf(f.y, w0[5], a2);
+        for (int p = 0; p < FP; ++p) {
+          const float xv = in[(p + kx) * 3 + ci];
+          acc[p][0] = fmaf(xv, w0.x, acc[p][0]); acc[p][1] = fmaf(xv, w0.y, acc[p][1]);
+          acc[p][2] = fmaf(xv, w0.z, acc[p][2]); acc[p][3] = fmaf(xv, w0.w, acc[p][3]);
+          acc[p][4] = fmaf(xv, w1.x, acc[p][4]); acc[p][5] = fmaf(xv, w1.y, acc[p][5]);
+          acc[p][6] = fmaf(xv, w1.z, acc[p][6]); acc[p][7] = fmaf(xv, w1.w, acc[p][7]);
         }
       }
     }
   }
-  gx[pix * 3] = a0; gx[pix * 3 + 1] = a1; gx[pix * 3 + 2] = a2;
+#pragma unroll
+  for (int p = 0; p < FP; ++p) {
+    if (px + p >= W) break;
+    uint4 o;
+    __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) oh[j] = __floats2bfloat162_rn(fmaxf(acc[p][2 * j], 0.f), fmaxf(acc[p][2 * j + 1], 0.f));
+    *reinterpret_cast<uint4*>(y + (((img * H + py) * (int64_t)W + px + p) * 64 + cg)) = o;
+  }
+}
+
+// data gradient: a thread computes BP consecutive pixels x 3 outputs, walking the 64 gradient channels
+// in chunks of 8 (one 16-byte load per window column); each chunk's 3 x 8 x 3 weights come from
+// shared memory as broadcast float4s and feed BP x 72 FMAs.  wd fp32 [3,3,64,3].
+constexpr int BP = 2;
+__global__ void __launch_bounds__(128) conv_first_bwd_k(const __nv_bfloat16* __restrict__ g,
+                                                        const float* __restrict__ wd, float* __restrict__ gx,
+                                                        int n, int H, int W) {
+  __shared__ __align__(16) float ws[9 * 64 * 3];
+  for (int i = threadIdx.x; i < 9 * 64 * 3; i += blockDim.x) ws[i] = wd[i];
+  __syncthreads();
+  const int WG = (W + BP - 1) / BP;
+  const int64_t grp = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (grp >= (int64_t)n * H * WG) return;
+  const int px = (int)(grp % WG) * BP, py = (int)((grp / WG) % H);
+  const int64_t img = grp / ((int64_t)WG * H);
+  float acc[BP][3];
+#pragma unroll
+  for (int p = 0; p < BP; ++p) acc[p][0] = acc[p][1] = acc[p][2] = 0.f;
+  for (int ky = 0; ky < 3; ++ky) {
+    const int yy = py + ky - 1;
+    if (yy < 0 || yy >= H) continue;
+    const __nv_bfloat16* row = g + (img * H + yy) * (int64_t)W * 64;
+#pragma unroll 2
+    for (int c8 = 0; c8 < 8; ++c8) {
+      float gv[BP + 2][8];
+#pragma unroll
+      for (int c = 0; c < BP + 2; ++c) {
+        const int xx = px + c - 1;
+        uint4 q = make_uint4(0, 0, 0, 0);
+        if (xx >= 0 && xx < W) q = *reinterpret_cast<const uint4*>(row + (int64_t)xx * 64 + c8 * 8);
+        const __nv_bfloat162* hq = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = __bfloat1622float2(hq[e]);
+          gv[c][2 * e] = f.x; gv[c][2 * e + 1] = f.y;
+        }
+      }
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        // 8 channels x 3 outputs = 24 consecutive floats = 6 float4
+        const float4* wt = reinterpret_cast<const float4*>(ws + ((ky * 3 + kx) * 64 + c8 * 8) * 3);
+        float wv[24];
+#pragma unroll
+        for (int q4 = 0; q4 < 6; ++q4) {
+          const float4 t4 = wt[q4];
+          wv[4 * q4] = t4.x; wv[4 * q4 + 1] = t4.y; wv[4 * q4 + 2] = t4.z; wv[4 * q4 + 3] = t4.w;
+        }
+#pragma unroll
+        for (int p = 0; p < BP; ++p)
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float f = gv[p + kx][e];
+            acc[p][0] = fmaf(f, wv[e * 3], acc[p][0]);
+            acc[p][1] = fmaf(f, wv[e * 3 + 1], acc[p][1]);
+            acc[p][2] = fmaf(f, wv[e * 3 + 2], acc[p][2]);
+          }
+      }
+    }
+  }
+#pragma unroll
+  for (int p = 0; p < BP; ++p) {
+    if (px + p >= W) break;
+    float* o = gx + ((img * H + py) * (int64_t)W + px + p) * 3;
+    o[0] = acc[p][0]; o[1] = acc[p][1]; o[2] = acc[p][2];
+  }
 }
 
 }  // namespace tc
@@ -616,7 +666,7 @@ __global__ void __launch_bounds__(128) conv_first_bwd_k(const __nv_bfloat16* __r
 extern "C" int lnst_conv_first_fwd(const float* x, const float* w, const float* b, void* y, int32_t n, int32_t H,
                                    int32_t W, void* stream) {
   if (!x || !w || !y || n < 1 || H < 1 || W < 1) return LNST_EARG;
-  const int64_t threads = (int64_t)n * H * W * 8;
+  const int64_t threads = (int64_t)n * H * ((W + tc::FP - 1) / tc::FP) * 8;
   tc::conv_first_fwd_k<<<lnst_blocks(threads, 256), 256, 0, lnst_stream(stream)>>>(x, w, b, (__nv_bfloat16*)y, n, H, W);
   return lnst_status();
 }
@@ -624,7 +674,7 @@ extern "C" int lnst_conv_first_fwd(const float* x, const float* w, const float* 
 extern "C" int lnst_conv_first_bwd(const void* g, const float* wd, float* gx, int32_t n, int32_t H, int32_t W,
                                    void* stream) {
   if (!g || !wd || !gx || n < 1 || H < 1 || W < 1) return LNST_EARG;
-  const int64_t threads = (int64_t)n * H * W;
+  const int64_t threads = (int64_t)n * H * ((W + tc::BP - 1) / tc::BP);
   tc::conv_first_bwd_k<<<lnst_blocks(threads, 128), 128, 0, lnst_stream(stream)>>>((const __nv_bfloat16*)g, wd, gx, n,
                                                                                      H, W);
   return lnst_status();

@@ -39,6 +39,7 @@ SIGNATURES = {
     'lnst_rotate_fwd': [vp, vp, i32, i32, i32, i32, vp, vp],
     'lnst_raymarch_fwd': [vp, vp, i32, i32, i32, i32, f32, i32, vp, vp, vp],
     'lnst_raymarch_bwd': [vp, vp, i32, i32, i32, i32, f32, i32, vp, vp, vp, vp],
+    'lnst_set_raymarch_merge': [i32],
     'lnst_image_max': [vp, i32, i64, vp, vp],
     'lnst_normalize_fwd': [vp, vp, i32, i64, vp, vp],
     'lnst_normalize_bwd': [vp, vp, vp, i32, i64, vp, vp, vp],

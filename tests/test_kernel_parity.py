@@ -147,13 +147,19 @@ def test_rotate_fwd(dev):
 
 
 @pytest.mark.parametrize('liquid', [False, True])
-@pytest.mark.parametrize('rotated', [False, True])
+@pytest.mark.parametrize('rotated', [False, True, 'merge-off', 'wide'])
 def test_raymarch_fwd_bwd(dev, liquid, rotated):
+    """Fused rotate + render against transform.rotate + the cumsum render of the oracle.  'wide': rows
+    longer than a warp and not a multiple of it (lanes of one warp straddle rows), large and small
+    angles, a ray with zero incoming gradient; 'merge-off': the plain eight-atomics backward."""
+    from lnst import _lib
     rng = np.random.RandomState(8)
-    D, H, W = 9, 7, 8
+    D, H, W = (11, 6, 45) if rotated == 'wide' else (9, 7, 8)
     vol = torch.tensor((rng.rand(D, H, W) * (rng.rand(D, H, W) > 0.3)).astype(np.float32), requires_grad=True)
     tau = 0.2
     mats = (_rots()[:2] + [np.matmul(T.rot_y_3d(33.0), T.rot_z_3d(-21.0))]) if rotated else None
+    if rotated == 'wide':
+        mats = mats + [np.identity(3), np.matmul(T.rot_y_3d(-80.0), T.rot_z_3d(100.0))]
     nv = len(mats) if rotated else 1
     rot = torch.tensor(np.asarray(mats), dtype=torch.float32).reshape(-1, 9).to(dev) if rotated else None
     img = torch.empty(nv, H, W, dtype=torch.float32, device=dev)
@@ -168,9 +174,14 @@ def test_raymarch_fwd_bwd(dev, liquid, rotated):
     want = want[..., 0]
     close(img, want, what='raymarch fwd')
     g = torch.tensor(rng.randn(nv, H, W).astype(np.float32))
+    g[:, 2, 3:6] = 0.0
     (want * g).sum().backward()
     g_vol = torch.zeros(D, H, W, dtype=torch.float32, device=dev)
-    ops.raymarch_bwd(vol.detach().to(dev), rot, tau, liquid, stot, g.to(dev), g_vol)
+    _lib.get().call('lnst_set_raymarch_merge', 0 if rotated == 'merge-off' else 1)
+    try:
+        ops.raymarch_bwd(vol.detach().to(dev), rot, tau, liquid, stot, g.to(dev), g_vol)
+    finally:
+        _lib.get().call('lnst_set_raymarch_merge', 1)
     close(g_vol, vol.grad, tol=2e-5, what='raymarch bwd')
 
 

@@ -65,13 +65,13 @@ def test_conv3x3_tc_matches_fp32_reference(n, H, W, cin, cout):
 def test_edge_layers_pool_and_conversions():
     dev = torch.device('cuda:0')
     g = torch.Generator().manual_seed(5)
-    x = torch.randn(2, 11, 14, 3, generator=g) * 50
+    x = torch.randn(2, 11, 15, 3, generator=g) * 50
     w = torch.randn(3, 3, 3, 64, generator=g) / 5
     b = torch.randn(64, generator=g)
     y = ops.conv3x3_mixed(x.to(dev), w.to(dev), b.to(dev), relu=True, out_bf16=True)
     want = ref_conv(x, w, b, True)
     assert (y.float().cpu() - want).abs().max() <= 2 ** -7 * want.abs().max()
-    gy = torch.randn(2, 11, 14, 64, generator=g).to(torch.bfloat16)
+    gy = torch.randn(2, 11, 15, 64, generator=g).to(torch.bfloat16)
     wd = w.flip(0, 1).permute(0, 1, 3, 2).contiguous()
     gx = ops.conv3x3_mixed(gy.to(dev), wd.to(dev), None, relu=False, out_bf16=False)
     want = ref_conv(gy.float(), wd, None, False)

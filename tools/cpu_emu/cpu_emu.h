@@ -175,6 +175,13 @@ static inline float __shfl_xor_sync(unsigned, float v, int m) { int l = emu::lin
 static inline int __shfl_xor_sync(unsigned, int v, int m) { int l = emu::linear_tid() % 32; return emu_exchange<int>(v, l ^ m, emu::B()->shfl_i); }
 static inline float __shfl_down_sync(unsigned, float v, int d) { int l = emu::linear_tid() % 32; return emu_exchange<float>(v, l + d, emu::B()->shfl_f); }
 static inline int __shfl_down_sync(unsigned, int v, int d) { int l = emu::linear_tid() % 32; return emu_exchange<int>(v, l + d, emu::B()->shfl_i); }
+static inline float __shfl_up_sync(unsigned, float v, int d) { int l = emu::linear_tid() % 32; return emu_exchange<float>(v, l - d, emu::B()->shfl_f); }
+static inline int __shfl_up_sync(unsigned, int v, int d) { int l = emu::linear_tid() % 32; return emu_exchange<int>(v, l - d, emu::B()->shfl_i); }
+static inline bool __any_sync(unsigned, bool p) {
+  int r = p ? 1 : 0;
+  for (int o = 16; o > 0; o >>= 1) r |= emu_exchange<int>(r, (emu::linear_tid() % 32) ^ o, emu::B()->shfl_i);
+  return r != 0;
+}
 static inline float __shfl_sync(unsigned, float v, int s) { return emu_exchange<float>(v, s, emu::B()->shfl_f); }
 static inline int __shfl_sync(unsigned, int v, int s) { return emu_exchange<int>(v, s, emu::B()->shfl_i); }
 

@@ -1,0 +1,111 @@
+#!/usr/bin/env python
+"""Per-kernel micro-benchmark at a bench workload's shapes (developer tool; GPU only).
+
+    python tools/kbench.py [--workload C3] [--reps 10] [--only raymarch]
+
+Builds the scene exactly like bench.py, runs one loss+gradient evaluation to obtain realistic
+intermediate tensors, then times each hot entry point alone with CUDA events (mean of --reps
+back-to-back launches after 2 warm-ups) and prints algorithmic GB/s next
+to the measured HBM peak.
+"""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for _p in (ROOT, os.path.join(ROOT, 'neural-flow-style_b200'), os.path.join(ROOT, 'tests')):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import torch  # noqa: E402
+
+import bench  # noqa: E402
+
+
+def timeit(fn, reps):
+    for _ in range(2):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--workload', default='C3')
+    ap.add_argument('--reps', type=int, default=10)
+    ap.add_argument('--only', default='')
+    args = ap.parse_args()
+    from lnst import _lib, ops, synth
+    from lnst.styler_3p import Styler
+    dev = torch.device('cuda:0')
+    lib = _lib.get()
+    wl = bench.WORKLOADS[args.workload]
+    cfg = bench.make_cfg(args.workload, 'allreduce', 'bf16')
+    p, r, sty = bench.make_scene(args.workload)
+    st = Styler(cfg, weights=synth.vgg_weights(), device=dev)
+    st.style_img = sty
+    res = [wl['res']] * 3
+    ws = st._workspace(res)
+    grams = st._style_feature(sty, res[1:])
+    st.num_frames = 1
+    frames, _ = st.upload({'p': p, 'r': r})
+    fr = frames[0]
+    var = torch.zeros(fr['p'].shape[0], 2, device=dev)
+    rot = st._rot_tensor(st.rot_mat_) if wl['rotate'] else None
+    loss, grad = st.loss_and_grad(fr, var, ws, rot, grams)
+    torch.cuda.synchronize()
+    D, H, W = res
+    V, P, N = D * H * W, H * W, fr['p'].shape[0]
+    nv = 1 if rot is None else rot.shape[0]
+    ds = ws['ds']
+    img = torch.empty(nv, H, W, device=dev)
+    stot = torch.empty(nv, H, W, device=dev)
+    ops.raymarch_fwd(ds, rot, st.transmit, False, img, stot)
+    g_img = torch.randn(nv, H, W, device=dev)
+    g_ds = torch.zeros(D, H, W, device=dev)
+    key = (fr['id'], tuple(res))
+    wmap = st._frame_cache[key]
+    hs = st._supports()
+    g_d = torch.randn(D, H, W, device=dev)
+    gvar = torch.empty_like(var)
+    out = {}
+
+    def add(name, fn, nbytes):
+        if args.only and args.only not in name:
+            return
+        ms = timeit(fn, args.reps)
+        out[name] = {'ms': round(ms, 4), 'alg_GBps': round(nbytes / ms / 1e6, 1), 'alg_MB': round(nbytes / 1e6, 1)}
+        print('%-28s %8.4f ms  %8.1f GB/s algorithmic (%.1f MB)' % (name, ms, nbytes / ms / 1e6, nbytes / 1e6), flush=True)
+
+    add('raymarch_fwd', lambda: ops.raymarch_fwd(ds, rot, st.transmit, False, img, stot), nv * (4 * V + 8 * P))
+    if rot is not None:
+        lib.call('lnst_set_raymarch_merge', 0)
+        add('raymarch_bwd(merge=0)', lambda: ops.raymarch_bwd(ds, rot, st.transmit, False, stot, g_img, g_ds),
+            nv * (8 * V + 8 * P))
+        lib.call('lnst_set_raymarch_merge', 1)
+    add('raymarch_bwd', lambda: ops.raymarch_bwd(ds, rot, st.transmit, False, stot, g_img, g_ds), nv * (8 * V + 8 * P))
+    add('splat_wavg_fwd', lambda: ops.splat_wavg_fwd(fr['p'], fr['r'], var, ws['grid'], hs, wmap, ws['num'], ws['d']),
+        N * (12 + 16) + 4 * V)
+    add('splat_wavg_bwd', lambda: ops.splat_wavg_bwd(fr['p'], var, ws['grid'], hs, wmap, g_d, gvar), N * (12 + 16) + 4 * V)
+    add('smooth3_relu_fwd', lambda: ops.smooth3_relu_fwd(ws['d'], ws['ds'], st.k), 8 * V)
+    add('smooth3_relu_bwd', lambda: ops.smooth3_relu_bwd(g_ds, ds, ws['g_d'], st.k), 12 * V)
+    x = torch.randn(nv, H, W, 3, device=dev)
+    d_img = torch.empty_like(x)
+
+    def lossnet():
+        l = torch.zeros(nv, device=dev)
+        return st.image_loss_and_grad(x, d_img, grams, l)
+    add('lossnet fwd+bwd (all views)', lossnet, 0)
+    add('zero g_ds', lambda: g_ds.zero_(), 4 * V)
+    print(json.dumps(out))
+
+
+if __name__ == '__main__':
+    main()
