@@ -94,6 +94,27 @@ def algorithmic_units(name, a, nk=2):
     return (0, 0)
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures
+# (profiles/), keyed by (workload, entry point); None where no capture exists.
+TRAFFIC = {}
+
+
+def roofline_all(table, hbm_peak, tf_peak):
+    """Per entry point: achieved algorithmic GB/s or TFLOP/s and its fraction of the measured peak."""
+    out = {}
+    for name, d in table.items():
+        ms = d['ms'] / d['calls']
+        if not ms:
+            continue
+        if name in TENSOR_BOUND and d['flops']:
+            a = d['flops'] / (ms * 1e-3) / 1e12
+            out[name] = {'bound': 'tensor', 'achieved_tflops': round(a, 2), 'frac': round(a / tf_peak, 4)}
+        elif d['bytes']:
+            a = d['bytes'] / (ms * 1e-3) / 1e9
+            out[name] = {'bound': 'hbm', 'achieved_gbs': round(a, 1), 'frac': round(a / hbm_peak, 4)}
+    return out
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
     Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
@@ -178,8 +199,10 @@ def run_engine(args):
     adam = _Adam()
     lr = cfg.lr
 
+    runner = styler.step_runner(fr, g_opt, adam, ws, grams, lr)   # eager once, then one CUDA graph per step
+
     def step():
-        var, loss, delta = styler.frame_step(fr, g_opt, adam, ws, grams, lr)
+        var, loss, delta = runner()
         ops.axpy(g_opt, delta, 1.0)
         return loss
 
@@ -188,43 +211,11 @@ def run_engine(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- warm-up; the last warm-up step is timed per entry point to find the dominant kernel ----
-    prof = {}
-    orig_call = lib.call
-
-    def profiling_call(name, *a):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        orig_call(name, *a)
-        e1.record()
-        prof.setdefault(name, []).append((e0, e1, algorithmic_units(name, a)))
-
-    for i in range(max(args.warmup, 3)):
-        if i == max(args.warmup, 3) - 1:
-            lib.call = profiling_call
+    for _ in range(max(args.warmup, 3)):
         step()
     barrier()
-    lib.call = orig_call
-    table = {}
-    for name, evs in prof.items():
-        ms = [a.elapsed_time(b) for a, b, _ in evs]
-        table[name] = {'calls': len(ms), 'ms': float(sum(ms)), 'bytes': int(sum(u[0] for _, _, u in evs)),
-                       'flops': int(sum(u[1] for _, _, u in evs))}
-    dominant = max(table, key=lambda k: table[k]['ms'])
 
-    # ---- timed region: exactly K steps; only the dominant entry point carries events ------------
-    dom = []
-
-    def dominant_call(name, *a):
-        if name != dominant:
-            return orig_call(name, *a)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        orig_call(name, *a)
-        e1.record()
-        dom.append((e0, e1, algorithmic_units(name, a)))
-
-    lib.call = dominant_call
+    # ---- timed region: exactly K steps -------------------------------------------------------------
     clocks = ClockSampler(local)
     barrier()
     if rank == 0:
@@ -237,13 +228,11 @@ def run_engine(args):
     t1.record()
     barrier()
     clk = clocks.stop() if rank == 0 else None
-    lib.call = orig_call
     ms_total = torch.tensor([t0.elapsed_time(t1)], device=dev)
     if world > 1:
         dist.all_reduce(ms_total, op=dist.ReduceOp.MAX)
     ms_step = float(ms_total.item()) / args.steps
     calls = lib.launches - launches0
-    kernel_launches = calls  # refined below with the per-call kernel counts
     loss_val = float(loss)
 
     # ---- end-to-end: host buffers in, host result out, every step (the reference's sess.run boundary) --
@@ -270,29 +259,60 @@ def run_engine(args):
     h2d = hp.numel() * 4 + hr.numel() * 4 + hg.numel() * 4
     d2h = hg.numel() * 4 + 4
 
+    # ---- per-kernel timing: the same steps issued eagerly (a graph replay cannot carry events), every
+    # entry point bracketed by CUDA events on the launching stream -----------------------------------
+    prof = {}
+    orig_call = lib.call
+
+    def profiling_call(name, *a):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        orig_call(name, *a)
+        e1.record()
+        prof.setdefault(name, []).append((e0, e1, algorithmic_units(name, a)))
+
+    prof_steps = max(3, min(args.steps, 10))
+    lib.call = profiling_call
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record()
+    for _ in range(prof_steps):
+        var, loss_e, delta = styler.frame_step(fr, g_opt, adam, ws, grams, lr)
+        ops.axpy(g_opt, delta, 1.0)
+    p1.record()
+    barrier()
+    lib.call = orig_call
+    eager_ms_step = p0.elapsed_time(p1) / prof_steps
+    table = {}
+    for name, evs in prof.items():
+        ms = [a.elapsed_time(b) for a, b, _ in evs]
+        table[name] = {'calls': len(ms) / prof_steps, 'ms': float(sum(ms)) / prof_steps,
+                       'bytes': sum(u[0] for _, _, u in evs) / len(evs), 'flops': sum(u[1] for _, _, u in evs) / len(evs)}
+    dominant = max(table, key=lambda k: table[k]['ms'])
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
     hbm_peak, tf_peak, src = peaks()
-    dms = [a.elapsed_time(b) for a, b, _ in dom]
-    dbytes = sum(u[0] for _, _, u in dom) / max(len(dom), 1)
-    dflops = sum(u[1] for _, _, u in dom) / max(len(dom), 1)
-    avg_ms = sum(dms) / max(len(dms), 1)
+    d = table[dominant]
+    avg_ms = d['ms'] / d['calls']
     if dominant in TENSOR_BOUND:
-        achieved = dflops / (avg_ms * 1e-3) / 1e12 if avg_ms else 0.0
+        achieved = d['flops'] / (avg_ms * 1e-3) / 1e12
         roof = {'kernel': dominant, 'bound': 'tensor', 'achieved': achieved, 'peak': tf_peak, 'unit': 'TFLOP/s',
                 'frac': achieved / tf_peak}
     else:
-        achieved = dbytes / (avg_ms * 1e-3) / 1e9 if avg_ms else 0.0
+        achieved = d['bytes'] / (avg_ms * 1e-3) / 1e9
         roof = {'kernel': dominant, 'bound': 'hbm', 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s',
                 'frac': achieved / hbm_peak}
-    roof.update({'traffic': None, 'peak_source': src, 'avg_launch_ms': avg_ms, 'launches_timed': len(dms),
-                 'share_of_step': sum(dms) / (ms_step * args.steps)})
+    roof.update({'traffic': TRAFFIC.get((wl, dominant)), 'peak_source': src, 'avg_launch_ms': avg_ms,
+                 'launches_timed': int(d['calls'] * prof_steps), 'share_of_step': d['ms'] / ms_step,
+                 'timed_in': 'eager re-issue of %d steps after the timed region (graph replays cannot carry events); '
+                             'eager step = %.3f ms' % (prof_steps, eager_ms_step)})
     per_step_calls = calls / args.steps
     kl = 0
     for name, t in table.items():
         kl += t['calls'] * KERNELS_PER_CALL.get(name, 1)
+    kl += 1  # axpy
     out = {
         'metric': 'style-opt iters/sec, 200^3 smoke x9 views', 'value': 1000.0 / ms_step, 'unit': 'iters/s',
         'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms_step,
@@ -306,8 +326,10 @@ def run_engine(args):
         'e2e': {'value': e2e_val, 'unit': 'iters/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                 'steps': e2e_steps},
         'gpu_launches': int(kl * args.steps), 'abi_calls_per_step': per_step_calls,
+        'cuda_graph': bool(runner.graph is not None),
         'clocks': clk, 'roofline': roof, 'final_loss': loss_val,
         'kernel_table_ms_per_step': {k: round(v['ms'], 4) for k, v in sorted(table.items(), key=lambda kv: -kv[1]['ms'])},
+        'roofline_all': roofline_all(table, hbm_peak, tf_peak),
     }
     if world == 1 and not args.no_cpu_baseline:
         out['cpu_baseline'] = cpu_baseline(wl, budget_s=args.cpu_budget)

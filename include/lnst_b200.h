@@ -180,6 +180,11 @@ int lnst_tv_loss(const float* d_img, int32_t H, int32_t W, int32_t C, float weig
 /* TF-1.15 ApplyAdam with g = grad*gscale; var is passed through nan_to_num afterwards. */
 int lnst_adam_step(float* var, const float* grad, float* m, float* v, int64_t n, float lr_t, float beta1,
                    float beta2, float eps, float gscale, void* stream);
+/* Same update with the step counter resident on the device (CUDA-graph replayable): state[3] =
+ * {beta1^t, beta2^t, lr_t}, initialised by the caller to {beta1, beta2, 0}.  Computes lr_t =
+ * lr*sqrt(1-beta2^t)/(1-beta1^t) in fp32, applies the update, then advances the powers. */
+int lnst_adam_step_dev(float* var, const float* grad, float* m, float* v, int64_t n, float* state, float lr,
+                       float beta1, float beta2, float eps, float gscale, void* stream);
 /* acc = (first ? 0 : acc) + nan_to_num(var) */
 int lnst_iterate_accumulate(float* acc, const float* var, int64_t n, int32_t first, void* stream);
 /* delta[i] = (nan_to_num(g_new[i]*scale) - g_opt[i]) * (mask ? mask[(i/width)*mask_stride] : 1) */

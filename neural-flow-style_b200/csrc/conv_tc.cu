@@ -203,41 +203,74 @@ conv3x3_tc_k(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ 
     const int ph_ = h0 + r / s.TW, pw_ = w0 + r % s.TW;
     const bool valid = ph_ < s.H && pw_ < s.W;
     const int64_t pix = ((int64_t)img * s.H + ph_) * s.W + pw_;
+    // The ReLU mask of this thread's row does not depend on the accumulator: fetch it while the
+    // main loop runs (all loads of a 32-channel chunk in flight together) and keep one bit per channel.
+    uint32_t mbits[BLOCK_N / 32];
+#pragma unroll
+    for (int c = 0; c < BLOCK_N / 32; ++c) mbits[c] = 0xffffffffu;
+    if (mask && valid) {
+      const uint4* msk = reinterpret_cast<const uint4*>(mask + pix * s.Cout + n0);
+#pragma unroll
+      for (int c = 0; c < BLOCK_N / 32; ++c) {
+        uint4 mv[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) mv[j] = msk[c * 4 + j];
+        uint32_t bits = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const __nv_bfloat16* mh = reinterpret_cast<const __nv_bfloat16*>(&mv[j]);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) bits |= (__bfloat162float(mh[e]) > 0.f ? 1u : 0u) << (j * 8 + e);
+        }
+        mbits[c] = bits;
+      }
+    }
+    // first addend chunk: also independent of the accumulator
+    uint4 av[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) av[j] = make_uint4(0, 0, 0, 0);
+    const uint4* add = (addend && valid) ? reinterpret_cast<const uint4*>(addend + pix * s.Cout + n0) : nullptr;
+    if (add) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) av[j] = add[j];
+    }
     mbar_wait(bars + 8 * (2 * STAGES), 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
     for (int c = 0; c < BLOCK_N / 32; ++c) {
       uint32_t v[32];
       tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+      uint4 an[4];                                                     // next chunk's addend, in flight during the math
+#pragma unroll
+      for (int j = 0; j < 4; ++j) an[j] = make_uint4(0, 0, 0, 0);
+      if (add && c + 1 < BLOCK_N / 32) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) an[j] = add[(c + 1) * 4 + j];
+      }
       if (valid) {
         const int co = n0 + c * 32;
         __nv_bfloat16* dst = y + pix * s.Cout + co;
-        const __nv_bfloat16* msk = mask ? mask + pix * s.Cout + co : nullptr;
-        const __nv_bfloat16* add = addend ? addend + pix * s.Cout + co : nullptr;
+        uint4 ov[4];
 #pragma unroll
-        for (int j = 0; j < 32; j += 8) {
-          uint4 mv = make_uint4(0, 0, 0, 0), av = make_uint4(0, 0, 0, 0);
-          if (msk) mv = *reinterpret_cast<const uint4*>(msk + j);
-          if (add) av = *reinterpret_cast<const uint4*>(add + j);
-          const __nv_bfloat16* mh = reinterpret_cast<const __nv_bfloat16*>(&mv);
-          const __nv_bfloat16* ah = reinterpret_cast<const __nv_bfloat16*>(&av);
-          uint4 ov;
-          __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&ov);
+        for (int j = 0; j < 4; ++j) {
+          const __nv_bfloat16* ah = reinterpret_cast<const __nv_bfloat16*>(&av[j]);
+          __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&ov[j]);
 #pragma unroll
           for (int e = 0; e < 8; e += 2) {
-            float f0 = __uint_as_float(v[j + e]) * s.scale, f1 = __uint_as_float(v[j + e + 1]) * s.scale;
-            if (add) { f0 += __bfloat162float(ah[e]); f1 += __bfloat162float(ah[e + 1]); }
-            if (bias) { f0 += bias[co + j + e]; f1 += bias[co + j + e + 1]; }
+            float f0 = __uint_as_float(v[j * 8 + e]) * s.scale, f1 = __uint_as_float(v[j * 8 + e + 1]) * s.scale;
+            if (addend) { f0 += __bfloat162float(ah[e]); f1 += __bfloat162float(ah[e + 1]); }
+            if (bias) { f0 += bias[co + j * 8 + e]; f1 += bias[co + j * 8 + e + 1]; }
             if (s.relu) { f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); }
-            if (msk) {
-              if (!(__bfloat162float(mh[e]) > 0.f)) f0 = 0.f;
-              if (!(__bfloat162float(mh[e + 1]) > 0.f)) f1 = 0.f;
-            }
+            if (!((mbits[c] >> (j * 8 + e)) & 1u)) f0 = 0.f;
+            if (!((mbits[c] >> (j * 8 + e + 1)) & 1u)) f1 = 0.f;
             oh[e >> 1] = __floats2bfloat162_rn(f0, f1);
           }
-          *reinterpret_cast<uint4*>(dst + j) = ov;
         }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(dst + j * 8) = ov[j];
       }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) av[j] = an[j];
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

@@ -20,6 +20,32 @@ __global__ void adam_step_k(float* __restrict__ var, const float* __restrict__ g
   var[i] = lnst_nan_to_num(var[i] - lr_t * mi / (sqrtf(vi) + eps));
 }
 
+// Device-resident step counter of one AdamOptimizer (state = {beta1^t, beta2^t, lr_t}): computes
+// lr_t = lr * sqrt(1 - beta2^t) / (1 - beta1^t) in fp32 like TF's _prepare/_apply_dense and advances
+// the powers, so that a whole optimisation step can be replayed from a CUDA graph with no host
+// scalar changing between replays.
+__global__ void adam_tick_k(float* __restrict__ state, float lr, float b1, float b2) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  const float b1p = state[0], b2p = state[1];
+  state[2] = __fdiv_rn(__fmul_rn(lr, __fsqrt_rn(__fadd_rn(1.f, -b2p))), __fadd_rn(1.f, -b1p));
+  state[0] = __fmul_rn(b1p, b1);
+  state[1] = __fmul_rn(b2p, b2);
+}
+
+__global__ void adam_step_dev_k(float* __restrict__ var, const float* __restrict__ grad, float* __restrict__ m,
+                                float* __restrict__ v, int64_t n, const float* __restrict__ state, float b1,
+                                float b2, float eps, float gscale) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float lr_t = state[2];
+  const float g = grad[i] * gscale;
+  const float mi = m[i] + (g - m[i]) * (1.f - b1);
+  const float vi = v[i] + (g * g - v[i]) * (1.f - b2);
+  m[i] = mi;
+  v[i] = vi;
+  var[i] = lnst_nan_to_num(var[i] - lr_t * mi / (sqrtf(vi) + eps));
+}
+
 __global__ void iterate_accumulate_k(float* __restrict__ acc, const float* __restrict__ var, int64_t n, int first) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -121,6 +147,16 @@ extern "C" int lnst_adam_step(float* var, const float* grad, float* m, float* v,
   if (n == 0) return LNST_OK;
   LNST_LAUNCH(adam_step_k, dim3(lnst_blocks(n, 256)), dim3(256), 0, lnst_stream(stream), var, grad, m, v, n, lr_t,
               beta1, beta2, eps, gscale);
+  return lnst_status();
+}
+
+extern "C" int lnst_adam_step_dev(float* var, const float* grad, float* m, float* v, int64_t n, float* state,
+                                  float lr, float beta1, float beta2, float eps, float gscale, void* stream) {
+  if (!var || !grad || !m || !v || !state || n < 0) return LNST_EARG;
+  LNST_LAUNCH(adam_tick_k, dim3(1), dim3(32), 0, lnst_stream(stream), state, lr, beta1, beta2);
+  if (n > 0)
+    LNST_LAUNCH(adam_step_dev_k, dim3(lnst_blocks(n, 256)), dim3(256), 0, lnst_stream(stream), var, grad, m, v, n,
+                (const float*)state, beta1, beta2, eps, gscale);
   return lnst_status();
 }
 

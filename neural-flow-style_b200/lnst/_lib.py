@@ -55,6 +55,7 @@ SIGNATURES = {
     'lnst_content_loss': [vp, i64, i32, i32, f32, vp, vp, f32, i32, vp],
     'lnst_tv_loss': [vp, i32, i32, i32, f32, vp, vp, vp],
     'lnst_adam_step': [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, vp],
+    'lnst_adam_step_dev': [vp, vp, vp, vp, i64, vp, f32, f32, f32, f32, f32, vp],
     'lnst_iterate_accumulate': [vp, vp, i64, i32, vp],
     'lnst_iterate_delta': [vp, f32, vp, vp, i32, i32, i64, vp, vp],
     'lnst_temporal_gauss': [vp, vp, i32, i64, f32, vp],

@@ -204,6 +204,13 @@ def tv_loss(d_img, weight, loss, g_img):
 
 
 # ---- optimiser / glue ------------------------------------------------------------------------
+def adam_step_dev(var, grad, m, v, state, lr, gscale=1.0, beta1=0.9, beta2=0.999, eps=1e-8):
+    """TF ApplyAdam with the beta powers / lr_t in the device tensor ``state`` [3] (graph-replayable)."""
+    _lib.get().call('lnst_adam_step_dev', ptr(var), ptr(grad), ptr(m), ptr(v), var.numel(), ptr(state), float(lr),
+                    beta1, beta2, eps, float(gscale), _s(var))
+    return var
+
+
 def adam_step(var, grad, m, v, lr_t, gscale=1.0, beta1=0.9, beta2=0.999, eps=1e-8):
     _lib.get().call('lnst_adam_step', ptr(var), ptr(grad), ptr(m), ptr(v), var.numel(), float(lr_t), beta1, beta2,
                     eps, float(gscale), _s(var))

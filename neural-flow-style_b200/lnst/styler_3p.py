@@ -21,19 +21,51 @@ from .util import octave_sizes
 
 class _Adam:
     """Slots of one tf.compat.v1.train.AdamOptimizer (styler_3p.py:320-323): m, v per variable
-    and the fp32 beta-power accumulators, kept across frames of the group and across octaves."""
+    and the fp32 beta-power accumulators, kept across frames of the group and across octaves.
+    The accumulators live on the device (``state`` = {beta1^t, beta2^t, lr_t}) so that a step
+    replays from a CUDA graph."""
 
     def __init__(self):
-        self.m = self.v = None
-        self.b1p, self.b2p = np.float32(0.9), np.float32(0.999)
+        self.m = self.v = self.state = None
 
     def step(self, var, grad, lr, gscale=1.0):
         if self.m is None:
             self.m, self.v = torch.zeros_like(var), torch.zeros_like(var)
-        lr_t = np.float32(lr) * np.sqrt(np.float32(1) - self.b2p) / (np.float32(1) - self.b1p)
-        ops.adam_step(var, grad, self.m, self.v, float(lr_t), gscale)
-        self.b1p = np.float32(self.b1p * np.float32(0.9))
-        self.b2p = np.float32(self.b2p * np.float32(0.999))
+            self.state = torch.tensor([0.9, 0.999, 0.0], dtype=f32).to(var.device)
+        ops.adam_step_dev(var, grad, self.m, self.v, self.state, lr, gscale)
+
+
+class StepRunner:
+    """One frame's loop body (``Styler.frame_step``) as a callable.  The first call runs eagerly
+    (it fills the per-frame caches and allocates the Adam slots); the second call captures the same
+    launch sequence into a CUDA graph, and every later call is a single graph replay -- the
+    reference pays three ``sess.run`` round trips here (styler_3p.py:312,331,334).
+    Returns (var, loss, delta): static buffers, overwritten by the next call."""
+
+    def __init__(self, styler, fr, g_opt_t, adam, ws, style_grams, lr, use_graph=True):
+        self.args = (fr, g_opt_t, adam, ws, style_grams, lr)
+        self.styler, self.calls, self.graph, self.out, self.n_abi = styler, 0, None, None, 0
+        self.use_graph = bool(use_graph) and styler.device.type == 'cuda'
+
+    def __call__(self):
+        st = self.styler
+        if not self.use_graph or self.calls < 1:
+            self.calls += 1
+            out = st.frame_step(*self.args)
+        else:
+            lib = _lib.get()
+            if self.graph is None:
+                n0 = lib.launches
+                torch.cuda.synchronize(st.device)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, pool=st._graph_pool()):
+                    self.out = st.frame_step(*self.args)
+                self.n_abi, lib.launches, self.graph = lib.launches - n0, n0, g
+            self.graph.replay()
+            lib.launches += self.n_abi
+            out = self.out
+        st._advance_views()
+        return out
 
 
 class Styler(StylerBase):
@@ -57,6 +89,47 @@ class Styler(StylerBase):
                 raise NotImplementedError('v_batch > 1 is not built (its loss ignores all but the first view, '
                                           'styler_base.py:98)')
         self._frame_cache = {}
+        self._pool = None
+        self._rot_all = self._rot_mine = None
+        self._eye = self._rot_tensor([np.identity(3)])
+        if self.rotate:
+            self._upload_views()
+
+    def _graph_pool(self):
+        if self._pool is None:
+            self._pool = torch.cuda.graph_pool_handle()
+        return self._pool
+
+    def _upload_views(self):
+        """Host view matrices -> the persistent device buffers the kernels (and graphs) read."""
+        allv = self._rot_tensor(self.rot_mat_)
+        mine = self._rot_tensor([self.rot_mat_[i] for i in range(self.rank, self.n_views, self.world)]) \
+            if self.n_views > self.rank else None
+        if self._rot_all is None or (mine is not None) != (self._rot_mine is not None) or \
+                (mine is not None and mine.shape != self._rot_mine.shape):
+            self._rot_all, self._rot_mine = allv, mine
+        else:
+            self._rot_all.copy_(allv)
+            if mine is not None:
+                self._rot_mine.copy_(mine)
+
+    def set_world(self, rank, world):
+        """Override the (rank, world) taken from torch.distributed at construction (tests)."""
+        self.rank, self.world = rank, world
+        if self.rotate:
+            self._upload_views()
+
+    def _advance_views(self):
+        """Poisson-disc view sets are re-drawn after every frame pass (styler_3p.py:344-349)."""
+        if self.rotate and 'uniform' not in self.sample_type:
+            self.rot_mat_, self.views = rot_mat(self.phi0, self.phi1, self.phi_unit, self.theta0, self.theta1,
+                                                self.theta_unit, sample_type=self.sample_type, rng=self.rng,
+                                                nv=self.n_views)
+            self._upload_views()
+
+    def step_runner(self, fr, g_opt_t, adam, ws, style_grams, lr):
+        return StepRunner(self, fr, g_opt_t, adam, ws, style_grams, lr,
+                          use_graph=getattr(self, 'cuda_graphs', self.world == 1))
 
     # ---- geometry ------------------------------------------------------------------------------
     def _grid(self, res):
@@ -172,7 +245,7 @@ class Styler(StylerBase):
         """Forward only: (p_out, d_out [D,H,W], d_img [H',W',3]) -- styler_3p.py:409-431."""
         d = self._density(fr, var, ws['res'], ws)
         ds = ops.smooth3_relu_fwd(d, ws['ds'], self.k)
-        rot = self._rot_tensor([np.identity(3)]) if identity_view else None
+        rot = self._eye if identity_view else None
         st = self._render(ds, rot)
         p_out = fr['p'] + var if 'p' in self.target_field else fr['p']
         return p_out, ds + 0.0, st['d_img'][0]                     # "+0.0" folds the -0.0 markers
@@ -180,7 +253,9 @@ class Styler(StylerBase):
     # ---- one pass of the loop body for one frame (styler_3p.py:304-363) --------------------------
     def frame_step(self, fr, g_opt_t, adam, ws, style_grams, lr):
         """var <- g_opt[t]; Adam step(s) over the views; returns (var, loss, delta) with
-        delta = (nan_to_num(mean iterate) - g_opt[t]) [* r[:,0:1]].  Everything stays on device."""
+        delta = (nan_to_num(mean iterate) - g_opt[t]) [* r[:,0:1]].  Everything stays on device and the
+        launch sequence is fixed, so ``StepRunner`` can capture it into a CUDA graph (the view set is
+        re-drawn by ``_advance_views`` after the call, outside the graph)."""
         dev = self.device
         var = g_opt_t.clone()                                      # :312 (device copy, no H2D)
         if self.rotate:
@@ -189,17 +264,15 @@ class Styler(StylerBase):
                 acc = torch.empty_like(var)
                 losses = []
                 for i in range(0, self.n_views, self.v_batch):
-                    l, grad = self.loss_and_grad(fr, var, ws, self._rot_tensor(self.rot_mat_[i:i + 1]), style_grams)
+                    l, grad = self.loss_and_grad(fr, var, ws, self._rot_all[i:i + 1], style_grams)
                     adam.step(var, grad, lr)
                     ops.iterate_accumulate(acc, var, i == 0)
                     losses.append(l)
                 loss_t = torch.cat(losses).mean()                  # :342
                 g_new, scale = acc, 1.0 / n_step_views             # :351-352
             else:                                                  # mean view gradient, views sharded over ranks
-                mine = list(range(self.rank, self.n_views, self.world))
-                if mine:
-                    l, grad = self.loss_and_grad(fr, var, ws, self._rot_tensor([self.rot_mat_[i] for i in mine]),
-                                                 style_grams)
+                if self._rot_mine is not None:
+                    l, grad = self.loss_and_grad(fr, var, ws, self._rot_mine, style_grams)
                     lsum = l.sum().reshape(1)
                 else:
                     grad, lsum = torch.zeros_like(var), torch.zeros(1, dtype=f32, device=dev)
@@ -209,10 +282,6 @@ class Styler(StylerBase):
                 adam.step(var, grad, lr, gscale=1.0 / self.n_views)
                 loss_t = lsum[0] / self.n_views
                 g_new, scale = var, 1.0
-            if 'uniform' not in self.sample_type:                  # :344-349
-                self.rot_mat_, self.views = rot_mat(self.phi0, self.phi1, self.phi_unit, self.theta0, self.theta1,
-                                                    self.theta_unit, sample_type=self.sample_type, rng=self.rng,
-                                                    nv=self.n_views)
         else:                                                      # :354-357
             l, grad = self.loss_and_grad(fr, var, ws, None, style_grams)
             adam.step(var, grad, lr)
@@ -278,13 +347,16 @@ class Styler(StylerBase):
                 style_grams = self._style_feature(self.style_img, res[1:])
             lr = lr_list[octave] if lr_list is not None else (self.lr[octave] if isinstance(self.lr, list) else self.lr)
             loss_o, intm_o = [], []
+            runners = {}
             for step in range(self.iter):
                 deltas = {}
                 for t in range(0, nf, self.batch_size * self.interp):
                     fr = frames[t]
                     adam = opt_.setdefault(t // self.frames_per_opt, _Adam())   # :315-323
-                    var, loss_t, deltas[t] = self.frame_step(fr, g_opt[t], adam, ws, style_grams, lr)
-                    loss_o.append(loss_t)
+                    if t not in runners:
+                        runners[t] = self.step_runner(fr, g_opt[t], adam, ws, style_grams, lr)
+                    var, loss_t, deltas[t] = runners[t]()
+                    loss_o.append(loss_t.clone())
                     if step == self.iter - 1 and octave < self.octave_n - 1:   # :365-370
                         _, _, d_img = self.infer(fr, var, ws, eye)
                         intm_o.append(d_img)
@@ -298,6 +370,7 @@ class Styler(StylerBase):
             loss_history.append([float(v) for v in torch.stack(loss_o).cpu().tolist()] if loss_o else [])
             if octave < self.octave_n - 1:
                 d_intm.append(torch.stack(intm_o, 0).cpu().numpy().astype(np.uint8))
+            runners.clear()                                        # graphs hold this octave's workspaces
 
         if self.interp > 1:                                        # :392-397
             w = np.linspace(0, 1, self.interp + 1)

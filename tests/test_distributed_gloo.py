@@ -35,7 +35,7 @@ def _worker(rank, world, port, out_path):
     out = st.run({'p': p, 'r': r})
     if rank == 0:
         solo = Styler(smoke_cfg(**kw), weights=synth.vgg_weights())
-        solo.rank, solo.world = 0, 1              # same process, no sharding
+        solo.set_world(0, 1)                      # same process, no sharding
         solo.style_img = sty
         ref = solo.run({'p': p, 'r': r})
         np.savez(out_path, l=np.array(out['l']), l_ref=np.array(ref['l']), g=out['g_opt'][0], g_ref=ref['g_opt'][0],

@@ -314,6 +314,23 @@ def test_adam_matches_tf_formula_with_nan(dev):
     assert var[3, 1].item() == 0.0 and torch.isnan(m[3, 1]).item()
 
 
+def test_adam_device_step_counter(dev):
+    """lnst_adam_step_dev: beta powers and lr_t live on the device (CUDA-graph replayable)."""
+    rng = np.random.RandomState(17)
+    var0 = torch.tensor(rng.randn(33, 3).astype(np.float32))
+    var = var0.clone().to(dev)
+    m, v = torch.zeros_like(var), torch.zeros_like(var)
+    state = torch.tensor([0.9, 0.999, 0.0], dtype=torch.float32).to(dev)
+    ref = TFAdam()
+    want = var0.clone()
+    for t in range(1, 6):
+        g = torch.tensor(rng.randn(33, 3).astype(np.float32))
+        ops.adam_step_dev(var, g.to(dev), m, v, state, 0.05, gscale=0.5)
+        want = torch.nan_to_num(ref.step(want, g * 0.5, 0.05))
+    close(var, want, what='adam dev')
+    np.testing.assert_allclose(state.cpu().numpy()[:2], [np.float32(0.9) ** 6, np.float32(0.999) ** 6], rtol=1e-6)
+
+
 def test_iterate_glue_and_temporal_gauss(dev):
     from scipy.ndimage import gaussian_filter
     rng = np.random.RandomState(16)

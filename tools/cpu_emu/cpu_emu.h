@@ -201,6 +201,8 @@ static inline float __fdividef(float a, float b) { return a / b; }
 static inline float __saturatef(float x) { return x < 0 ? 0 : (x > 1 ? 1 : x); }
 static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
 static inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }
+static inline float __fdiv_rn(float a, float b) { volatile float r = a / b; return r; }
+static inline float __fsqrt_rn(float a) { volatile float r = sqrtf(a); return r; }
 static inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
 static inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }
 template <class T> static inline T __ldg(const T* p) { return *p; }
