@@ -33,6 +33,17 @@ typedef struct LnstGrid {
   int32_t clip;       /* 1: clamp positions to [0,domain-1e-6]; 0: drop outliers (:1320-1325) */
 } LnstGrid;
 
+/* Active region of a volume: inclusive voxel bounds in the stored [D,H,W] layout.  The `_box` entry
+ * points below take one (NULL = whole volume) when the caller knows that the density is exactly zero
+ * outside it and that no gradient is needed there -- in density mode the particle positions are
+ * constants (styler_3p.py:60-76), so the bounding box of sum-of-weights > 0, grown by one voxel for
+ * the 3x3x3 blur, is fixed for a whole run.  Results inside the box are identical to the full-volume
+ * call; nothing outside the box is read or written (the caller keeps those voxels zero). */
+typedef struct LnstBox {
+  int32_t lo[3];
+  int32_t hi[3];
+} LnstBox;
+
 int lnst_abi_version(void);
 
 /* ---- particle -> grid (transform.py:1310-1453 p2g, :1577-1704 p2g_wavg) ------------------ */
@@ -59,6 +70,11 @@ int lnst_splat_wavg_wmap(const float* p, int64_t n, const LnstGrid* g, const flo
 int lnst_splat_wavg_fwd(const float* p, const float* r, const float* var, int64_t n, const LnstGrid* g,
                         const float* h, int32_t nk, const float* wmap, float* num, float* out,
                         void* stream);
+/* Box variant: only cells inside `box` are combined; `num` must be zero on entry and is zero again on
+ * exit (the combine pass clears what it reads), so no per-step memset of the workspace is needed. */
+int lnst_splat_wavg_fwd_box(const float* p, const float* r, const float* var, int64_t n, const LnstGrid* g,
+                            const float* h, int32_t nk, const float* wmap, float* num, float* out,
+                            const LnstBox* box, void* stream);
 /* g_var [n,nk] overwritten; reproduces TF's where/div NaN rule (transform.py:1703). */
 int lnst_splat_wavg_bwd(const float* p, const float* var, int64_t n, const LnstGrid* g, const float* h,
                         int32_t nk, const float* wmap, const float* g_out, float* g_var, void* stream);
@@ -70,6 +86,13 @@ int lnst_smooth3_relu_fwd(const float* in, float* out, int32_t D, int32_t H, int
                           void* stream);
 int lnst_smooth3_relu_bwd(const float* g_out, const float* out, float* g_in, int32_t D, int32_t H,
                           int32_t W, int32_t k, void* stream);
+
+int lnst_smooth3_relu_fwd_box(const float* in, float* out, int32_t D, int32_t H, int32_t W, int32_t k,
+                              const LnstBox* box, void* stream);
+int lnst_smooth3_relu_bwd_box(const float* g_out, const float* out, float* g_in, int32_t D, int32_t H,
+                              int32_t W, int32_t k, const LnstBox* box, void* stream);
+/* vol[box] = value */
+int lnst_fill_box(float* vol, int32_t D, int32_t H, int32_t W, const LnstBox* box, float value, void* stream);
 
 /* ---- rotate + render (transform.py:611-628,343-433; styler_3p.py:148-158) ---------------- */
 /* rot: [n_views,9] row-major rotation matrices, or NULL for the unrotated render. */
@@ -84,6 +107,15 @@ int lnst_raymarch_bwd(const float* vol, const float* rot, int32_t n_views, int32
                       int32_t W, float tau, int32_t liquid, const float* stot, const float* g_img,
                       float* g_vol, void* stream);
 
+/* Box variants: rays are marched only through the depth interval whose trilinear footprints can touch
+ * the box (density is zero elsewhere, so img/stot are bit-identical to the full march; g_vol receives
+ * the exact gradient for every voxel inside the box and nothing outside it). */
+int lnst_raymarch_fwd_box(const float* vol, const float* rot, int32_t n_views, int32_t D, int32_t H,
+                          int32_t W, float tau, int32_t liquid, const LnstBox* box, float* img, float* stot,
+                          void* stream);
+int lnst_raymarch_bwd_box(const float* vol, const float* rot, int32_t n_views, int32_t D, int32_t H,
+                          int32_t W, float tau, int32_t liquid, const LnstBox* box, const float* stot,
+                          const float* g_img, float* g_vol, void* stream);
 /* Tuning switch for lnst_raymarch_bwd (process-wide, default 1): 1 = neighbouring lanes merge their
  * shared x-corner contributions by warp shuffle before the atomics; 0 = eight atomics per sample. */
 int lnst_set_raymarch_merge(int32_t on);

@@ -24,6 +24,21 @@ static inline unsigned lnst_blocks(int64_t n, int threads) {
   return (unsigned)((n + threads - 1) / threads);
 }
 
+struct SubVol { int oz, oy, ox, ez, ey, ex; };   // origin and extent of the region a launch covers
+static inline SubVol make_subvol(const LnstBox* b, int D, int H, int W) {
+  SubVol s = {0, 0, 0, D, H, W};
+  if (b) {
+    s.oz = b->lo[0]; s.oy = b->lo[1]; s.ox = b->lo[2];
+    s.ez = b->hi[0] - b->lo[0] + 1; s.ey = b->hi[1] - b->lo[1] + 1; s.ex = b->hi[2] - b->lo[2] + 1;
+  }
+  return s;
+}
+static inline bool box_ok(const LnstBox* b, int D, int H, int W) {
+  if (!b) return true;
+  return b->lo[0] >= 0 && b->lo[1] >= 0 && b->lo[2] >= 0 && b->hi[0] < D && b->hi[1] < H && b->hi[2] < W &&
+         b->lo[0] <= b->hi[0] && b->lo[1] <= b->hi[1] && b->lo[2] <= b->hi[2];
+}
+
 // np.nan_to_num for float32: NaN -> 0, +-inf -> +-FLT_MAX
 __device__ __forceinline__ float lnst_nan_to_num(float x) {
   if (x != x) return 0.0f;

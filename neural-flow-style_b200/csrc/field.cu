@@ -19,15 +19,16 @@ __device__ __forceinline__ float ld_or_zero(const float* __restrict__ v, int z, 
 // mode 0: out = relu(conv(in)) with signed zero; mode 1: g_in = conv(g_out * pass(out))
 template <int MODE>
 __global__ void smooth3_k(const float* __restrict__ in, const float* __restrict__ aux,
-                          float* __restrict__ out, int D, int H, int W, float w_side, float w_mid,
+                          float* __restrict__ out, int D, int H, int W, SubVol sv, float w_side, float w_mid,
                           int do_conv) {
-  const int xw = (W + SM_VEC - 1) / SM_VEC;
+  const int xw = (sv.ex + SM_VEC - 1) / SM_VEC;
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t total = (int64_t)D * H * xw;
+  const int64_t total = (int64_t)sv.ez * sv.ey * xw;
   if (t >= total) return;
-  const int x0 = (int)(t % xw) * SM_VEC;
-  const int y = (int)((t / xw) % H);
-  const int z = (int)(t / ((int64_t)xw * H));
+  const int x0 = sv.ox + (int)(t % xw) * SM_VEC;
+  const int y = sv.oy + (int)((t / xw) % sv.ey);
+  const int z = sv.oz + (int)(t / ((int64_t)xw * sv.ey));
+  const int x_end = sv.ox + sv.ex;
   float acc[SM_VEC] = {0.f, 0.f, 0.f, 0.f};
   const int r = do_conv ? 1 : 0;
   for (int dz = -r; dz <= r; ++dz) {
@@ -62,7 +63,7 @@ __global__ void smooth3_k(const float* __restrict__ in, const float* __restrict_
 #pragma unroll
   for (int j = 0; j < SM_VEC; ++j) {
     const int x = x0 + j;
-    if (x < W) {
+    if (x < x_end) {
       float v = acc[j];
       if (MODE == 0) v = (v < 0.f) ? -0.0f : v;
       out[((int64_t)z * H + y) * W + x] = v;
@@ -77,26 +78,56 @@ static inline void smooth_weights(int k, float& side, float& mid) {
   mid = (float)k / s;
 }
 
-extern "C" int lnst_smooth3_relu_fwd(const float* in, float* out, int32_t D, int32_t H, int32_t W,
-                                     int32_t k, void* stream) {
-  if (!in || !out || D < 1 || H < 1 || W < 1) return LNST_EARG;
+__global__ void fill_box_k(float* __restrict__ vol, int H, int W, SubVol sv, float value) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (int64_t)sv.ez * sv.ey * sv.ex) return;
+  const int x = sv.ox + (int)(t % sv.ex), y = sv.oy + (int)((t / sv.ex) % sv.ey);
+  const int z = sv.oz + (int)(t / ((int64_t)sv.ex * sv.ey));
+  vol[((int64_t)z * H + y) * W + x] = value;
+}
+
+extern "C" int lnst_fill_box(float* vol, int32_t D, int32_t H, int32_t W, const LnstBox* box, float value,
+                             void* stream) {
+  if (!vol || D < 1 || H < 1 || W < 1 || !box_ok(box, D, H, W)) return LNST_EARG;
+  const SubVol sv = make_subvol(box, D, H, W);
+  const int64_t total = (int64_t)sv.ez * sv.ey * sv.ex;
+  LNST_LAUNCH(fill_box_k, dim3(lnst_blocks(total, 256)), dim3(256), 0, lnst_stream(stream), vol, (int)H, (int)W, sv,
+              value);
+  return lnst_status();
+}
+
+extern "C" int lnst_smooth3_relu_fwd_box(const float* in, float* out, int32_t D, int32_t H, int32_t W,
+                                         int32_t k, const LnstBox* box, void* stream) {
+  if (!in || !out || D < 1 || H < 1 || W < 1 || !box_ok(box, D, H, W)) return LNST_EARG;
   float side = 0.f, mid = 1.f;
   if (k > 0) smooth_weights(k, side, mid);
-  const int64_t total = (int64_t)D * H * ((W + SM_VEC - 1) / SM_VEC);
+  const SubVol sv = make_subvol(box, D, H, W);
+  const int64_t total = (int64_t)sv.ez * sv.ey * ((sv.ex + SM_VEC - 1) / SM_VEC);
   auto kern = smooth3_k<0>;
   LNST_LAUNCH(kern, dim3(lnst_blocks(total, 256)), dim3(256), 0, lnst_stream(stream), in,
-              (const float*)nullptr, out, (int)D, (int)H, (int)W, side, mid, (int)(k > 0));
+              (const float*)nullptr, out, (int)D, (int)H, (int)W, sv, side, mid, (int)(k > 0));
   return lnst_status();
+}
+
+extern "C" int lnst_smooth3_relu_bwd_box(const float* g_out, const float* out, float* g_in, int32_t D,
+                                         int32_t H, int32_t W, int32_t k, const LnstBox* box, void* stream) {
+  if (!g_out || !out || !g_in || D < 1 || H < 1 || W < 1 || !box_ok(box, D, H, W)) return LNST_EARG;
+  float side = 0.f, mid = 1.f;
+  if (k > 0) smooth_weights(k, side, mid);
+  const SubVol sv = make_subvol(box, D, H, W);
+  const int64_t total = (int64_t)sv.ez * sv.ey * ((sv.ex + SM_VEC - 1) / SM_VEC);
+  auto kern = smooth3_k<1>;
+  LNST_LAUNCH(kern, dim3(lnst_blocks(total, 256)), dim3(256), 0, lnst_stream(stream), g_out, out, g_in,
+              (int)D, (int)H, (int)W, sv, side, mid, (int)(k > 0));
+  return lnst_status();
+}
+
+extern "C" int lnst_smooth3_relu_fwd(const float* in, float* out, int32_t D, int32_t H, int32_t W,
+                                     int32_t k, void* stream) {
+  return lnst_smooth3_relu_fwd_box(in, out, D, H, W, k, nullptr, stream);
 }
 
 extern "C" int lnst_smooth3_relu_bwd(const float* g_out, const float* out, float* g_in, int32_t D,
                                      int32_t H, int32_t W, int32_t k, void* stream) {
-  if (!g_out || !out || !g_in || D < 1 || H < 1 || W < 1) return LNST_EARG;
-  float side = 0.f, mid = 1.f;
-  if (k > 0) smooth_weights(k, side, mid);
-  const int64_t total = (int64_t)D * H * ((W + SM_VEC - 1) / SM_VEC);
-  auto kern = smooth3_k<1>;
-  LNST_LAUNCH(kern, dim3(lnst_blocks(total, 256)), dim3(256), 0, lnst_stream(stream), g_out, out, g_in,
-              (int)D, (int)H, (int)W, side, mid, (int)(k > 0));
-  return lnst_status();
+  return lnst_smooth3_relu_bwd_box(g_out, out, g_in, D, H, W, k, nullptr, stream);
 }

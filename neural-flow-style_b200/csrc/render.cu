@@ -93,7 +93,8 @@ __global__ void rotate_fwd_k(const float* __restrict__ vol, const float* __restr
 
 // one thread per pixel column (view, h, w); marches from the camera side (high D) down
 __global__ void raymarch_fwd_k(const float* __restrict__ vol, const float* __restrict__ rot, VolDims v,
-                               float tau, int liquid, float* __restrict__ img, float* __restrict__ stot) {
+                               SubVol sv, float tau, int liquid, float* __restrict__ img,
+                               float* __restrict__ stot) {
   const int P = v.H * v.W;
   const int pix = blockIdx.x * blockDim.x + threadIdx.x;
   if (pix >= P) return;
@@ -102,15 +103,21 @@ __global__ void raymarch_fwd_k(const float* __restrict__ vol, const float* __res
   const float* R = rot ? rot + 9 * view : nullptr;
   const float gh = lin_coord(h, v.sH), gw = lin_coord(w, v.sW);
   float S = 0.f, I = 0.f;
+  // active sub-volume (unrotated rays only): the density is zero outside it
+  int i_lo = 0, i_hi = v.D - 1;
+  if (!R) {
+    i_lo = sv.oz; i_hi = sv.oz + sv.ez - 1;
+    if (h < sv.oy || h >= sv.oy + sv.ey || w < sv.ox || w >= sv.ox + sv.ex) i_hi = i_lo - 1;
+  }
   // RM_UNROLL depth steps are sampled before any of them is consumed, so their (independent)
   // loads are in flight together; only the running transmittance is sequential.
-  for (int i0 = v.D - 1; i0 >= 0; i0 -= RM_UNROLL) {
+  for (int i0 = i_hi; i0 >= i_lo; i0 -= RM_UNROLL) {
     float d[RM_UNROLL];
 #pragma unroll
     for (int u = 0; u < RM_UNROLL; ++u) {
       const int i = i0 - u;
       d[u] = 0.f;
-      if (i >= 0) {
+      if (i >= i_lo) {
         if (R) {
           const Corner8 c = rotate_sample(R, lin_coord(i, v.sD), gh, gw, v);
           d[u] = sample8(vol, c, v);
@@ -121,7 +128,7 @@ __global__ void raymarch_fwd_k(const float* __restrict__ vol, const float* __res
     }
 #pragma unroll
     for (int u = 0; u < RM_UNROLL; ++u) {
-      if (i0 - u >= 0) {
+      if (i0 - u >= i_lo) {
         S += d[u];                              // inclusive reverse cumsum, styler_3p.py:155
         if (!liquid) I += d[u] * expf(-S * tau);
       }
@@ -134,7 +141,7 @@ __global__ void raymarch_fwd_k(const float* __restrict__ vol, const float* __res
 
 // d I / d d_k = T_k - tau * sum_{i<=k} d_i T_i  (smoke);  tau * exp(-tau * S_total) (liquid)
 __global__ void raymarch_bwd_k(const float* __restrict__ vol, const float* __restrict__ rot, VolDims v,
-                               float tau, int liquid, const float* __restrict__ stot,
+                               SubVol sv, float tau, int liquid, const float* __restrict__ stot,
                                const float* __restrict__ g_img, float* __restrict__ g_vol, int use_atomic) {
   const int P = v.H * v.W;
   const int pix = blockIdx.x * blockDim.x + threadIdx.x;
@@ -148,14 +155,19 @@ __global__ void raymarch_bwd_k(const float* __restrict__ vol, const float* __res
   const float gh = lin_coord(h, v.sH), gw = lin_coord(w, v.sW);
   const float gl = liquid ? gI * tau * expf(-St * tau) : 0.f;
   float below = 0.f, Pk = 0.f;
-  for (int i0 = 0; i0 < v.D; i0 += RM_UNROLL) {
+  int i_lo = 0, i_end = v.D;
+  if (!R) {
+    i_lo = sv.oz; i_end = sv.oz + sv.ez;
+    if (h < sv.oy || h >= sv.oy + sv.ey || w < sv.ox || w >= sv.ox + sv.ex) return;
+  }
+  for (int i0 = i_lo; i0 < i_end; i0 += RM_UNROLL) {
     Corner8 c[RM_UNROLL];
     float d[RM_UNROLL];
 #pragma unroll
     for (int u = 0; u < RM_UNROLL; ++u) {
       const int i = i0 + u;
       d[u] = 0.f;
-      if (i < v.D) {
+      if (i < i_end) {
         if (R) {
           c[u] = rotate_sample(R, lin_coord(i, v.sD), gh, gw, v);
           if (!liquid) d[u] = sample8(vol, c[u], v);
@@ -167,7 +179,7 @@ __global__ void raymarch_bwd_k(const float* __restrict__ vol, const float* __res
 #pragma unroll
     for (int u = 0; u < RM_UNROLL; ++u) {
       const int i = i0 + u;
-      if (i < v.D) {
+      if (i < i_end) {
         float g;
         if (liquid) {
           g = gl;
@@ -225,6 +237,41 @@ __device__ __forceinline__ RayLine ray_line(const float* __restrict__ R, float g
   return l;
 }
 
+// Box in float form for the interval test: a sample at position z touches voxels floor(z), floor(z)+1,
+// so it matters iff lo-1 < z < hi+1; a bound on a face of the volume is open-ended because positions
+// beyond the face are clamped onto it (edge replication).
+struct BoxF { float lo[3], hi[3]; };
+static inline BoxF make_boxf(const LnstBox* b, int D, int H, int W) {
+  const float inf = __builtin_huge_valf();
+  BoxF f;
+  const int L[3] = {D, H, W};
+  for (int a = 0; a < 3; ++a) {
+    f.lo[a] = (!b || b->lo[a] <= 0) ? -inf : (float)(b->lo[a] - 1);
+    f.hi[a] = (!b || b->hi[a] >= L[a] - 1) ? inf : (float)(b->hi[a] + 1);
+  }
+  return f;
+}
+__device__ __forceinline__ void axis_interval(float c, float k, float lo, float hi, float& t0, float& t1) {
+  if (fabsf(k) < 1e-12f) {
+    if (!(c > lo && c < hi)) { t0 = 1e30f; t1 = -1e30f; }
+    return;
+  }
+  float a = (lo - c) / k, b = (hi - c) / k;
+  if (k < 0.f) { const float t = a; a = b; b = t; }
+  t0 = fmaxf(t0, a);
+  t1 = fminf(t1, b);
+}
+// inclusive depth-index range of the samples that can touch the box (empty: lo > hi)
+__device__ __forceinline__ void ray_interval(const RayLine& l, const RayGeo& g, const BoxF& bf, int& ilo, int& ihi) {
+  float t0 = 0.f, t1 = g.mD;
+  axis_interval(l.cz, l.kz, bf.lo[0], bf.hi[0], t0, t1);
+  axis_interval(l.cy, l.ky, bf.lo[1], bf.hi[1], t0, t1);
+  axis_interval(l.cx, l.kx, bf.lo[2], bf.hi[2], t0, t1);
+  if (!(t0 <= t1 + 2.f)) { ilo = 1; ihi = 0; return; }
+  ilo = max(0, (int)ceilf(t0) - 1);
+  ihi = min(g.D - 1, (int)floorf(t1) + 1);
+}
+
 struct Cell { int idx; float fz, fy, fx; };
 
 __device__ __forceinline__ Cell locate(const RayLine& l, float fi, const RayGeo& g) {
@@ -260,7 +307,7 @@ __device__ __forceinline__ float fast_exp2(float x) {
 }
 
 __global__ void __launch_bounds__(128) raymarch_rot_fwd_k(const float* __restrict__ vol, const float* __restrict__ rot,
-                                                           RayGeo g, float ntl2, int liquid,
+                                                           RayGeo g, BoxF bf, float ntl2, int liquid,
                                                            float* __restrict__ img, float* __restrict__ stot) {
   const int pix = blockIdx.x * blockDim.x + threadIdx.x;
   if (pix >= g.HW) return;
@@ -268,8 +315,9 @@ __global__ void __launch_bounds__(128) raymarch_rot_fwd_k(const float* __restric
   const int h = pix / g.W, w = pix - h * g.W;
   const RayLine l = ray_line(rot + 9 * view, lin_coord(h, g.sH), lin_coord(w, g.sW), g);
   float S = 0.f, I = 0.f;
-  int i0 = g.D - 1;
-  for (; i0 >= RM_UNROLL - 1; i0 -= RM_UNROLL) {      // full groups: no per-sample bounds checks
+  int i_lo, i0;
+  ray_interval(l, g, bf, i_lo, i0);                    // the density is zero outside [i_lo, i0]
+  for (; i0 >= i_lo + RM_UNROLL - 1; i0 -= RM_UNROLL) {   // full groups: no per-sample bounds checks
     float d[RM_UNROLL];
 #pragma unroll
     for (int u = 0; u < RM_UNROLL; ++u) d[u] = sample_cell(vol, locate(l, (float)(i0 - u), g), g);
@@ -279,7 +327,7 @@ __global__ void __launch_bounds__(128) raymarch_rot_fwd_k(const float* __restric
       I = fmaf(d[u], fast_exp2(S * ntl2), I);
     }
   }
-  for (; i0 >= 0; --i0) {
+  for (; i0 >= i_lo; --i0) {
     const float d = sample_cell(vol, locate(l, (float)i0, g), g);
     S += d;
     I = fmaf(d, fast_exp2(S * ntl2), I);
@@ -292,7 +340,7 @@ __global__ void __launch_bounds__(128) raymarch_rot_fwd_k(const float* __restric
 // d I / d d_k = T_k - tau * sum_{i<=k} d_i T_i  (smoke);  tau * exp(-tau * S_total) (liquid)
 template <bool MERGE>
 __global__ void __launch_bounds__(128) raymarch_rot_bwd_k(const float* __restrict__ vol, const float* __restrict__ rot,
-                                                           RayGeo g, float tau, float ntl2, int liquid,
+                                                           RayGeo g, BoxF bf, float tau, float ntl2, int liquid,
                                                            const float* __restrict__ stot,
                                                            const float* __restrict__ g_img, float* __restrict__ g_vol) {
   const int pix = blockIdx.x * blockDim.x + threadIdx.x;
@@ -312,18 +360,31 @@ __global__ void __launch_bounds__(128) raymarch_rot_bwd_k(const float* __restric
   const RayLine l = ray_line(rot + 9 * view, lin_coord(h, g.sH), lin_coord(w, g.sW), g);
   const float gl = liquid ? gI * tau * fast_exp2(St * ntl2) : 0.f;
   float below = 0.f, Pk = 0.f;
-  for (int i0 = 0; i0 < g.D; i0 += RM_UNROLL) {
+  // samples below the interval have zero density (below = Pk = 0 there) and, like those above it,
+  // no footprint inside the box
+  int i_lo, i_hi;
+  ray_interval(l, g, bf, i_lo, i_hi);
+  if (!active) { i_lo = 0x7fffffff; i_hi = -1; }
+  int w_lo = i_lo, w_hi = i_hi;                        // warp-uniform loop bounds (the merge shuffles)
+  if (MERGE) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      w_lo = min(w_lo, __shfl_xor_sync(0xffffffffu, w_lo, o));
+      w_hi = max(w_hi, __shfl_xor_sync(0xffffffffu, w_hi, o));
+    }
+  }
+  for (int i0 = w_lo; i0 <= w_hi; i0 += RM_UNROLL) {
     Cell c[RM_UNROLL];
     float d[RM_UNROLL];
 #pragma unroll
     for (int u = 0; u < RM_UNROLL; ++u) {
       const int i = min(i0 + u, g.D - 1);              // tail: a repeated sample, masked below
       c[u] = locate(l, (float)i, g);
-      d[u] = (liquid || !active) ? 0.f : sample_cell(vol, c[u], g);
+      d[u] = (liquid || i0 + u < i_lo || i0 + u > i_hi) ? 0.f : sample_cell(vol, c[u], g);
     }
 #pragma unroll
     for (int u = 0; u < RM_UNROLL; ++u) {
-      const bool live = active && (i0 + u < g.D);
+      const bool live = i0 + u >= i_lo && i0 + u <= i_hi;
       float gk;
       if (liquid) {
         gk = gl;
@@ -494,43 +555,58 @@ extern "C" int lnst_rotate_fwd(const float* vol, const float* rot, int32_t n_vie
 static int lnst_raymarch_merge = 1;
 extern "C" int lnst_set_raymarch_merge(int32_t on) { lnst_raymarch_merge = on ? 1 : 0; return LNST_OK; }
 
-extern "C" int lnst_raymarch_fwd(const float* vol, const float* rot, int32_t n_views, int32_t D, int32_t H,
-                                 int32_t W, float tau, int32_t liquid, float* img, float* stot,
-                                 void* stream) {
-  if (!vol || !img || !stot || n_views < 1 || D < 1 || H < 1 || W < 1) return LNST_EARG;
+extern "C" int lnst_raymarch_fwd_box(const float* vol, const float* rot, int32_t n_views, int32_t D, int32_t H,
+                                     int32_t W, float tau, int32_t liquid, const LnstBox* box, float* img,
+                                     float* stot, void* stream) {
+  if (!vol || !img || !stot || n_views < 1 || D < 1 || H < 1 || W < 1 || !box_ok(box, D, H, W)) return LNST_EARG;
   if (!rot && n_views != 1) return LNST_EARG;
   if (rot && D >= 2 && H >= 2 && W >= 2 && (int64_t)D * H * W < 0x7fffffff) {
     const RayGeo g = make_geo(D, H, W);
     LNST_LAUNCH(raymarch_rot_fwd_k, dim3(lnst_blocks((int64_t)H * W, 128), n_views), dim3(128), 0,
-                lnst_stream(stream), vol, rot, g, -tau * 1.4426950408889634f, (int)liquid, img, stot);
+                lnst_stream(stream), vol, rot, g, make_boxf(box, D, H, W), -tau * 1.4426950408889634f, (int)liquid,
+                img, stot);
     return lnst_status();
   }
   const VolDims v = make_dims(D, H, W);
   LNST_LAUNCH(raymarch_fwd_k, dim3(lnst_blocks((int64_t)H * W, 128), n_views), dim3(128), 0,
-              lnst_stream(stream), vol, rot, v, tau, (int)liquid, img, stot);
+              lnst_stream(stream), vol, rot, v, make_subvol(box, D, H, W), tau, (int)liquid, img, stot);
+  return lnst_status();
+}
+
+extern "C" int lnst_raymarch_fwd(const float* vol, const float* rot, int32_t n_views, int32_t D, int32_t H,
+                                 int32_t W, float tau, int32_t liquid, float* img, float* stot,
+                                 void* stream) {
+  return lnst_raymarch_fwd_box(vol, rot, n_views, D, H, W, tau, liquid, nullptr, img, stot, stream);
+}
+
+extern "C" int lnst_raymarch_bwd_box(const float* vol, const float* rot, int32_t n_views, int32_t D, int32_t H,
+                                     int32_t W, float tau, int32_t liquid, const LnstBox* box, const float* stot,
+                                     const float* g_img, float* g_vol, void* stream) {
+  if (!vol || !stot || !g_img || !g_vol || n_views < 1 || D < 1 || H < 1 || W < 1 || !box_ok(box, D, H, W))
+    return LNST_EARG;
+  if (!rot && n_views != 1) return LNST_EARG;
+  if (rot && D >= 2 && H >= 2 && W >= 2 && (int64_t)D * H * W < 0x7fffffff) {
+    const RayGeo g = make_geo(D, H, W);
+    const BoxF bf = make_boxf(box, D, H, W);
+    const float ntl2 = -tau * 1.4426950408889634f;
+    if (lnst_raymarch_merge)
+      LNST_LAUNCH(raymarch_rot_bwd_k<true>, dim3(lnst_blocks((int64_t)H * W, 128), n_views), dim3(128), 0,
+                  lnst_stream(stream), vol, rot, g, bf, tau, ntl2, (int)liquid, stot, g_img, g_vol);
+    else
+      LNST_LAUNCH(raymarch_rot_bwd_k<false>, dim3(lnst_blocks((int64_t)H * W, 128), n_views), dim3(128), 0,
+                  lnst_stream(stream), vol, rot, g, bf, tau, ntl2, (int)liquid, stot, g_img, g_vol);
+    return lnst_status();
+  }
+  const VolDims v = make_dims(D, H, W);
+  LNST_LAUNCH(raymarch_bwd_k, dim3(lnst_blocks((int64_t)H * W, 128), n_views), dim3(128), 0,
+              lnst_stream(stream), vol, rot, v, make_subvol(box, D, H, W), tau, (int)liquid, stot, g_img, g_vol, 0);
   return lnst_status();
 }
 
 extern "C" int lnst_raymarch_bwd(const float* vol, const float* rot, int32_t n_views, int32_t D, int32_t H,
                                  int32_t W, float tau, int32_t liquid, const float* stot,
                                  const float* g_img, float* g_vol, void* stream) {
-  if (!vol || !stot || !g_img || !g_vol || n_views < 1 || D < 1 || H < 1 || W < 1) return LNST_EARG;
-  if (!rot && n_views != 1) return LNST_EARG;
-  if (rot && D >= 2 && H >= 2 && W >= 2 && (int64_t)D * H * W < 0x7fffffff) {
-    const RayGeo g = make_geo(D, H, W);
-    const float ntl2 = -tau * 1.4426950408889634f;
-    if (lnst_raymarch_merge)
-      LNST_LAUNCH(raymarch_rot_bwd_k<true>, dim3(lnst_blocks((int64_t)H * W, 128), n_views), dim3(128), 0,
-                  lnst_stream(stream), vol, rot, g, tau, ntl2, (int)liquid, stot, g_img, g_vol);
-    else
-      LNST_LAUNCH(raymarch_rot_bwd_k<false>, dim3(lnst_blocks((int64_t)H * W, 128), n_views), dim3(128), 0,
-                  lnst_stream(stream), vol, rot, g, tau, ntl2, (int)liquid, stot, g_img, g_vol);
-    return lnst_status();
-  }
-  const VolDims v = make_dims(D, H, W);
-  LNST_LAUNCH(raymarch_bwd_k, dim3(lnst_blocks((int64_t)H * W, 128), n_views), dim3(128), 0,
-              lnst_stream(stream), vol, rot, v, tau, (int)liquid, stot, g_img, g_vol, 0);
-  return lnst_status();
+  return lnst_raymarch_bwd_box(vol, rot, n_views, D, H, W, tau, liquid, nullptr, stot, g_img, g_vol, stream);
 }
 
 extern "C" int lnst_image_max(const float* img, int32_t n_img, int64_t n_pix, float* stats, void* stream) {

@@ -229,6 +229,24 @@ __global__ void splat_wavg_combine_k(const float* __restrict__ wmap, const float
   out[c] = s;
 }
 
+// box variant: combines only the cells of the sub-volume and clears the num it consumed
+__global__ void splat_wavg_combine_box_k(const float* __restrict__ wmap, float* __restrict__ num, int nk,
+                                         int64_t cells, int H, int W, SubVol sv, float* __restrict__ out) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (int64_t)sv.ez * sv.ey * sv.ex) return;
+  const int x = sv.ox + (int)(t % sv.ex), y = sv.oy + (int)((t / sv.ex) % sv.ey);
+  const int z = sv.oz + (int)(t / ((int64_t)sv.ex * sv.ey));
+  const int64_t c = ((int64_t)z * H + y) * W + x;
+  float s = 0.f;
+  for (int k = 0; k < nk; ++k) {
+    const float w = wmap[k * cells + c];
+    const float v = num[k * cells + c];
+    if (v != 0.f) num[k * cells + c] = 0.f;
+    s += (w > 1e-6f) ? v / w : v;                 // transform.py:1703
+  }
+  out[c] = s;
+}
+
 template <int DIM>
 __global__ void splat_wavg_bwd_k(const float* __restrict__ p, const float* __restrict__ var, int64_t n,
                                  LnstGrid g, SplatKernels ks, int nk, int64_t cells,
@@ -362,12 +380,20 @@ extern "C" int lnst_splat_wavg_wmap(const float* p, int64_t n, const LnstGrid* g
 extern "C" int lnst_splat_wavg_fwd(const float* p, const float* r, const float* var, int64_t n,
                                    const LnstGrid* g, const float* h, int32_t nk, const float* wmap,
                                    float* num, float* out, void* stream) {
+  return lnst_splat_wavg_fwd_box(p, r, var, n, g, h, nk, wmap, num, out, nullptr, stream);
+}
+
+extern "C" int lnst_splat_wavg_fwd_box(const float* p, const float* r, const float* var, int64_t n,
+                                       const LnstGrid* g, const float* h, int32_t nk, const float* wmap,
+                                       float* num, float* out, const LnstBox* box, void* stream) {
   SplatKernels ks;
   if (!grid_ok(g) || !p || !r || !wmap || !num || !out || n < 0 ||
       !fill_kernels(ks, g ? g->dim : 3, h, nk))
     return LNST_EARG;
+  const int Dz = g->dim == 3 ? g->res[0] : 1;
+  if (!box_ok(box, Dz, g->res[1], g->res[2])) return LNST_EARG;
   const int64_t cells = grid_cells(g);
-  cudaMemsetAsync(num, 0, sizeof(float) * cells * nk, lnst_stream(stream));
+  if (!box) cudaMemsetAsync(num, 0, sizeof(float) * cells * nk, lnst_stream(stream));
   const int T = 256;
   if (n > 0) {
     if (g->dim == 3) {
@@ -379,6 +405,12 @@ extern "C" int lnst_splat_wavg_fwd(const float* p, const float* r, const float* 
       LNST_LAUNCH(k, dim3(lnst_blocks(n, T)), dim3(T), 0, lnst_stream(stream), p, r, var, n, *g, ks,
                   (int)nk, cells, num);
     }
+  }
+  if (box) {
+    const SubVol sv = make_subvol(box, Dz, g->res[1], g->res[2]);
+    LNST_LAUNCH(splat_wavg_combine_box_k, dim3(lnst_blocks((int64_t)sv.ez * sv.ey * sv.ex, T)), dim3(T), 0,
+                lnst_stream(stream), wmap, num, (int)nk, cells, (int)g->res[1], (int)g->res[2], sv, out);
+    return lnst_status();
   }
   LNST_LAUNCH(splat_wavg_combine_k, dim3(lnst_blocks(cells, T)), dim3(T), 0, lnst_stream(stream), wmap,
               (const float*)num, (int)nk, cells, out);

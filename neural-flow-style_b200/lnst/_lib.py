@@ -21,7 +21,12 @@ class LnstGrid(C.Structure):
                 ('clip', i32)]
 
 
+class LnstBox(C.Structure):
+    _fields_ = [('lo', i32 * 3), ('hi', i32 * 3)]
+
+
 GP = C.POINTER(LnstGrid)
+BP = C.POINTER(LnstBox)
 FP = C.POINTER(f32)      # host float array
 IP = C.POINTER(i32)      # host int array
 
@@ -33,12 +38,18 @@ SIGNATURES = {
     'lnst_splat_sph_bwd_color': [vp, i64, GP, f32, f32, vp, i32, f32, vp, vp, vp],
     'lnst_splat_wavg_wmap': [vp, i64, GP, FP, i32, vp, vp],
     'lnst_splat_wavg_fwd': [vp, vp, vp, i64, GP, FP, i32, vp, vp, vp, vp],
+    'lnst_splat_wavg_fwd_box': [vp, vp, vp, i64, GP, FP, i32, vp, vp, vp, BP, vp],
     'lnst_splat_wavg_bwd': [vp, vp, i64, GP, FP, i32, vp, vp, vp, vp],
     'lnst_smooth3_relu_fwd': [vp, vp, i32, i32, i32, i32, vp],
     'lnst_smooth3_relu_bwd': [vp, vp, vp, i32, i32, i32, i32, vp],
+    'lnst_smooth3_relu_fwd_box': [vp, vp, i32, i32, i32, i32, BP, vp],
+    'lnst_smooth3_relu_bwd_box': [vp, vp, vp, i32, i32, i32, i32, BP, vp],
+    'lnst_fill_box': [vp, i32, i32, i32, BP, f32, vp],
     'lnst_rotate_fwd': [vp, vp, i32, i32, i32, i32, vp, vp],
     'lnst_raymarch_fwd': [vp, vp, i32, i32, i32, i32, f32, i32, vp, vp, vp],
     'lnst_raymarch_bwd': [vp, vp, i32, i32, i32, i32, f32, i32, vp, vp, vp, vp],
+    'lnst_raymarch_fwd_box': [vp, vp, i32, i32, i32, i32, f32, i32, BP, vp, vp, vp],
+    'lnst_raymarch_bwd_box': [vp, vp, i32, i32, i32, i32, f32, i32, BP, vp, vp, vp, vp],
     'lnst_set_raymarch_merge': [i32],
     'lnst_image_max': [vp, i32, i64, vp, vp],
     'lnst_normalize_fwd': [vp, vp, i32, i64, vp, vp],
@@ -153,6 +164,15 @@ def ptr(t):
     if not t.is_contiguous():
         raise LnstError('non-contiguous tensor')
     return C.c_void_p(t.data_ptr())
+
+
+def make_box(lo, hi):
+    """LnstBox from inclusive (z,y,x) voxel bounds."""
+    b = LnstBox()
+    for a in range(3):
+        b.lo[a] = int(lo[a])
+        b.hi[a] = int(hi[a])
+    return b
 
 
 def make_grid(dim, res, domain, nsize, clip):

@@ -56,9 +56,14 @@ def splat_wavg_wmap(p, grid, hs):
     return wmap
 
 
-def splat_wavg_fwd(p, r, var, grid, hs, wmap, num, out):
-    _lib.get().call('lnst_splat_wavg_fwd', ptr(p), ptr(r), ptr(var), p.shape[0], C.byref(grid), _harr(hs), len(hs),
-                    ptr(wmap), ptr(num), ptr(out), _s(p))
+def _b(box):
+    return C.byref(box) if box is not None else None
+
+
+def splat_wavg_fwd(p, r, var, grid, hs, wmap, num, out, box=None):
+    """With ``box``: only its cells are combined; ``num`` must be zero on entry and is zero again on exit."""
+    _lib.get().call('lnst_splat_wavg_fwd_box', ptr(p), ptr(r), ptr(var), p.shape[0], C.byref(grid), _harr(hs),
+                    len(hs), ptr(wmap), ptr(num), ptr(out), _b(box), _s(p))
     return out
 
 
@@ -69,16 +74,22 @@ def splat_wavg_bwd(p, var, grid, hs, wmap, g_out, g_var):
 
 
 # ---- field ---------------------------------------------------------------------------------
-def smooth3_relu_fwd(d, out, k):
+def smooth3_relu_fwd(d, out, k, box=None):
     D, H, W = d.shape
-    _lib.get().call('lnst_smooth3_relu_fwd', ptr(d), ptr(out), D, H, W, int(k), _s(d))
+    _lib.get().call('lnst_smooth3_relu_fwd_box', ptr(d), ptr(out), D, H, W, int(k), _b(box), _s(d))
     return out
 
 
-def smooth3_relu_bwd(g_out, out, g_in, k):
+def smooth3_relu_bwd(g_out, out, g_in, k, box=None):
     D, H, W = out.shape
-    _lib.get().call('lnst_smooth3_relu_bwd', ptr(g_out), ptr(out), ptr(g_in), D, H, W, int(k), _s(out))
+    _lib.get().call('lnst_smooth3_relu_bwd_box', ptr(g_out), ptr(out), ptr(g_in), D, H, W, int(k), _b(box), _s(out))
     return g_in
+
+
+def fill_box(vol, box, value=0.0):
+    D, H, W = vol.shape
+    _lib.get().call('lnst_fill_box', ptr(vol), D, H, W, _b(box), float(value), _s(vol))
+    return vol
 
 
 # ---- render --------------------------------------------------------------------------------
@@ -90,19 +101,19 @@ def rotate_fwd(vol, rot):
     return out
 
 
-def raymarch_fwd(vol, rot, tau, liquid, img, stot):
+def raymarch_fwd(vol, rot, tau, liquid, img, stot, box=None):
     D, H, W = vol.shape
     nv = 1 if rot is None else rot.shape[0]
-    _lib.get().call('lnst_raymarch_fwd', ptr(vol), ptr(rot), nv, D, H, W, float(tau), int(bool(liquid)), ptr(img),
-                    ptr(stot), _s(vol))
+    _lib.get().call('lnst_raymarch_fwd_box', ptr(vol), ptr(rot), nv, D, H, W, float(tau), int(bool(liquid)), _b(box),
+                    ptr(img), ptr(stot), _s(vol))
     return img, stot
 
 
-def raymarch_bwd(vol, rot, tau, liquid, stot, g_img, g_vol):
+def raymarch_bwd(vol, rot, tau, liquid, stot, g_img, g_vol, box=None):
     D, H, W = vol.shape
     nv = 1 if rot is None else rot.shape[0]
-    _lib.get().call('lnst_raymarch_bwd', ptr(vol), ptr(rot), nv, D, H, W, float(tau), int(bool(liquid)), ptr(stot),
-                    ptr(g_img), ptr(g_vol), _s(vol))
+    _lib.get().call('lnst_raymarch_bwd_box', ptr(vol), ptr(rot), nv, D, H, W, float(tau), int(bool(liquid)), _b(box),
+                    ptr(stot), ptr(g_img), ptr(g_vol), _s(vol))
     return g_vol
 
 

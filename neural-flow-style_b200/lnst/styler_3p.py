@@ -148,36 +148,59 @@ class Styler(StylerBase):
         """var -> density field d [D,H,W] (styler_3p.py:49-91)."""
         grid = ws['grid']
         if 'd' in self.target_field:
-            key = (fr['id'], tuple(res))
-            if key not in self._frame_cache:                       # positions are constant: W-sums once
-                self._frame_cache[key] = ops.splat_wavg_wmap(fr['p'], grid, self._supports())
-            wmap = self._frame_cache[key]
-            ops.splat_wavg_fwd(fr['p'], fr['r'], var, grid, self._supports(), wmap, ws['num'], ws['d'])
+            wmap = self._wmap(fr, res, grid)
+            ops.splat_wavg_fwd(fr['p'], fr['r'], var, grid, self._supports(), wmap, ws['num'], ws['d'], ws['box'])
         else:
             scale = 0.8 * (2 * self.radius) ** 3 * self.rest_density / self.rest_density
             ops.splat_sph_fwd(fr['p'], var, grid, self._supports()[0], scale, out=ws['d'])
         return ws['d']
 
-    def _workspace(self, res):
+    def _wmap(self, fr, res, grid):
+        """Sum of splat weights per kernel and cell; positions are constants in density mode
+        (styler_3p.py:60-76), so it is computed once per (frame, octave)."""
+        key = (fr['id'], tuple(res))
+        if key not in self._frame_cache:
+            self._frame_cache[key] = ops.splat_wavg_wmap(fr['p'], grid, self._supports())
+        return self._frame_cache[key]
+
+    def _workspace(self, res, frames=None):
+        """Per-octave volumes.  With ``frames`` (density mode) the active box is set: the bounding box
+        of every cell any frame's particles can reach (sum of weights > 0), grown by one voxel for the
+        3x3x3 blur.  Density and the needed gradients are zero / unused outside it, so the volume
+        kernels only visit the box; the volumes are zero-initialised and stay zero elsewhere."""
         D, H, W = res
         dev = self.device
         nk = self.num_kernels if 'd' in self.target_field else 1
-        return {'grid': self._grid(res), 'res': res,
-                'num': torch.empty(nk, D * H * W, dtype=f32, device=dev),
-                'd': torch.empty(D, H, W, dtype=f32, device=dev),
-                'ds': torch.empty(D, H, W, dtype=f32, device=dev),
-                'g_ds': torch.empty(D, H, W, dtype=f32, device=dev),
-                'g_d': torch.empty(D, H, W, dtype=f32, device=dev)}
+        ws = {'grid': self._grid(res), 'res': res, 'box': None,
+              'num': torch.zeros(nk, D * H * W, dtype=f32, device=dev),
+              'd': torch.zeros(D, H, W, dtype=f32, device=dev),
+              'ds': torch.zeros(D, H, W, dtype=f32, device=dev),
+              'g_ds': torch.zeros(D, H, W, dtype=f32, device=dev),
+              'g_d': torch.zeros(D, H, W, dtype=f32, device=dev)}
+        if frames is not None and 'd' in self.target_field and getattr(self, 'active_box', True):
+            occ = None
+            for fr in frames:
+                o = (self._wmap(fr, res, ws['grid']) > 0).any(0).reshape(D, H, W)
+                occ = o if occ is None else (occ | o)
+            lo, hi = [0, 0, 0], [0, 0, 0]
+            if occ is not None and bool(occ.any()):
+                for a, other in enumerate(((1, 2), (0, 2), (0, 1))):
+                    idx = torch.nonzero(occ.any(other[1]).any(other[0])).flatten()
+                    lo[a] = max(int(idx.min()) - 1, 0)
+                    hi[a] = min(int(idx.max()) + 1, res[a] - 1)
+            ws['box'] = _lib.make_box(lo, hi)
+            ws['box_cells'] = (hi[0] - lo[0] + 1) * (hi[1] - lo[1] + 1) * (hi[2] - lo[2] + 1)
+        return ws
 
-    def _render(self, ds, rot):
+    def _render(self, ds, rot, box=None):
         """ds [D,H,W] -> gray [nv,H,W,1] in [0,1] plus what the backward needs."""
         D, H, W = ds.shape
         nv = 1 if rot is None else rot.shape[0]
         dev = self.device
         img = torch.empty(nv, H, W, dtype=f32, device=dev)
         stot = torch.empty(nv, H, W, dtype=f32, device=dev)
-        ops.raymarch_fwd(ds, rot, self.transmit, self.render_liquid, img, stot)
-        st = {'img': img, 'stot': stot, 'rot': rot}
+        ops.raymarch_fwd(ds, rot, self.transmit, self.render_liquid, img, stot, box)
+        st = {'img': img, 'stot': stot, 'rot': rot, 'box': box}
         if self.render_liquid:
             gray = img
         else:                                                     # styler_3p.py:158
@@ -207,30 +230,30 @@ class Styler(StylerBase):
         else:
             g_img = ops.normalize_bwd(st['img'], st['stats'], g_gray, torch.empty(nv, dtype=f32, device=self.device),
                                       torch.empty_like(g_gray))
-        ops.raymarch_bwd(ds, st['rot'], self.transmit, self.render_liquid, st['stot'], g_img, g_ds)
+        ops.raymarch_bwd(ds, st['rot'], self.transmit, self.render_liquid, st['stot'], g_img, g_ds, st['box'])
 
     # ---- one loss + gradient evaluation (= one sess.run([train_op, total_loss]) without Adam) ----
     def loss_and_grad(self, fr, var, ws, rot, style_grams):
         """Sum over the given views of total_loss, and d(sum)/d var.  Returns (loss [nv], grad)."""
         res = ws['res']
         d = self._density(fr, var, res, ws)
-        ds = ops.smooth3_relu_fwd(d, ws['ds'], self.k)             # styler_3p.py:112-125
-        st = self._render(ds, rot)
+        box = ws['box']
+        ds = ops.smooth3_relu_fwd(d, ws['ds'], self.k, box)        # styler_3p.py:112-125
+        st = self._render(ds, rot, box)
         nv = st['x'].shape[0]
         loss = torch.zeros(nv, dtype=f32, device=self.device)
         g_x = self.image_loss_and_grad(st['x'], st['d_img'], style_grams, loss)
-        g_ds = ws['g_ds'].zero_()
+        g_ds = ops.fill_box(ws['g_ds'], box, 0.0)
         self._render_bwd(st, g_x, ds, g_ds)
-        g_d = ops.smooth3_relu_bwd(g_ds, ds, ws['g_d'], self.k)
+        g_d = ops.smooth3_relu_bwd(g_ds, ds, ws['g_d'], self.k, box)
         if self.w_pressure > 0 and 'p' in self.target_field:       # styler_3p.py:96-98, styler_base.py:228-230
             pos = d > 0
             pr = torch.where(pos, d - 1, torch.zeros_like(d))
             loss += self.w_pressure * (pr * pr).mean()
             g_d += (nv * self.w_pressure * 2.0 / d.numel()) * pr
         if 'd' in self.target_field:
-            key = (fr['id'], tuple(res))
             grad = torch.empty_like(var)
-            ops.splat_wavg_bwd(fr['p'], var, ws['grid'], self._supports(), self._frame_cache[key], g_d, grad)
+            ops.splat_wavg_bwd(fr['p'], var, ws['grid'], self._supports(), self._wmap(fr, res, ws['grid']), g_d, grad)
             if self.w_density > 0:                                 # styler_base.py:217-223
                 dv = torch.clamp(var, -1, 1)
                 inside = ((var >= -1) & (var <= 1)).to(f32)
@@ -244,9 +267,9 @@ class Styler(StylerBase):
     def infer(self, fr, var, ws, identity_view):
         """Forward only: (p_out, d_out [D,H,W], d_img [H',W',3]) -- styler_3p.py:409-431."""
         d = self._density(fr, var, ws['res'], ws)
-        ds = ops.smooth3_relu_fwd(d, ws['ds'], self.k)
+        ds = ops.smooth3_relu_fwd(d, ws['ds'], self.k, ws['box'])
         rot = self._eye if identity_view else None
-        st = self._render(ds, rot)
+        st = self._render(ds, rot, ws['box'])
         p_out = fr['p'] + var if 'p' in self.target_field else fr['p']
         return p_out, ds + 0.0, st['d_img'][0]                     # "+0.0" folds the -0.0 markers
 
@@ -340,8 +363,8 @@ class Styler(StylerBase):
         loss_history, d_intm, opt_ = [], [], {}
         for octave in range(self.octave_n):
             res = oct_size[octave]
-            ws = self._workspace(res)
             self._frame_cache = {}
+            ws = self._workspace(res, frames)
             style_grams = None
             if self.w_style and self.style_img is not None:        # :281-286
                 style_grams = self._style_feature(self.style_img, res[1:])
@@ -381,8 +404,8 @@ class Styler(StylerBase):
         # final inference (:404-438)
         result = {'l': loss_history, 'd_intm': d_intm, 'v': None, 'c': None}
         res = oct_size[-1]
-        ws = self._workspace(res)
         self._frame_cache = {}
+        ws = self._workspace(res, frames)
         p_sty, v_sty, d_sty, r_sty = [], [], [], []
         for t in range(nf):
             p_out, d_out, d_img = self.infer(frames[t], g_opt[t], ws, eye)

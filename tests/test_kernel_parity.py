@@ -295,6 +295,91 @@ def test_content_and_tv_loss(dev):
     close(g, img.grad[0], what='tv bwd')
 
 
+# ---- active-box variants: same results inside the box, nothing touched outside it ------------------
+def _box_volume(rng, shape, lo, hi):
+    vol = np.zeros(shape, np.float32)
+    sl = tuple(slice(a, b + 1) for a, b in zip(lo, hi))
+    vol[sl] = rng.rand(*[b - a + 1 for a, b in zip(lo, hi)]) * (rng.rand(*[b - a + 1 for a, b in zip(lo, hi)]) > 0.3)
+    return vol, sl
+
+
+@pytest.mark.parametrize('liquid', [False, True])
+@pytest.mark.parametrize('case', ['rot-inner', 'rot-face', 'plain'])
+def test_raymarch_box_equals_full_inside(dev, liquid, case):
+    """Rays marched only through the interval that can touch the active box: image bit-identical to
+    the full march (the density is zero outside), gradient identical inside the box, zero outside.
+    'rot-face': the box touches volume faces, where clamped out-of-volume samples still land in it."""
+    rng = np.random.RandomState(21)
+    D, H, W = 14, 9, 37
+    lo, hi = ((4, 2, 9), (10, 6, 27)) if case != 'rot-face' else ((0, 2, 20), (9, 8, 36))
+    vol_np, sl = _box_volume(rng, (D, H, W), lo, hi)
+    vol = torch.tensor(vol_np).to(dev)
+    box = _lib.make_box(lo, hi)
+    mats = _rots()[:3] + [np.matmul(T.rot_y_3d(35.0), T.rot_z_3d(-50.0)), np.identity(3)]
+    rot = None if case == 'plain' else torch.tensor(np.asarray(mats), dtype=torch.float32).reshape(-1, 9).to(dev)
+    nv = 1 if rot is None else rot.shape[0]
+    tau = 0.3
+    img_f, st_f = torch.empty(nv, H, W, device=dev), torch.empty(nv, H, W, device=dev)
+    img_b, st_b = torch.empty(nv, H, W, device=dev), torch.empty(nv, H, W, device=dev)
+    ops.raymarch_fwd(vol, rot, tau, liquid, img_f, st_f)
+    ops.raymarch_fwd(vol, rot, tau, liquid, img_b, st_b, box)
+    assert torch.equal(img_f.cpu(), img_b.cpu()) and torch.equal(st_f.cpu(), st_b.cpu())
+    g = torch.tensor(rng.randn(nv, H, W).astype(np.float32)).to(dev)
+    g_full = torch.zeros(D, H, W, device=dev)
+    g_box = torch.zeros(D, H, W, device=dev)
+    ops.raymarch_bwd(vol, rot, tau, liquid, st_f, g, g_full)
+    ops.raymarch_bwd(vol, rot, tau, liquid, st_f, g, g_box, box)
+    close(g_box[sl], g_full[sl], tol=2e-5, what='box gradient inside')
+    if case == 'plain':
+        outside = g_box.clone()
+        outside[sl] = 0
+        assert float(outside.abs().max()) == 0.0
+
+
+def test_smooth_fill_and_wavg_box_variants(dev):
+    rng = np.random.RandomState(22)
+    shape, lo, hi = (9, 11, 13), (2, 1, 3), (6, 9, 10)
+    box = _lib.make_box(lo, hi)
+    d_np, sl = _box_volume(rng, shape, (3, 2, 4), (5, 8, 9))           # support one voxel inside the box
+    d_np = d_np - 0.2 * (d_np > 0)
+    d = torch.tensor(d_np).to(dev)
+    full, part = torch.empty(shape, device=dev), torch.full(shape, 7.0, device=dev)
+    ops.smooth3_relu_fwd(d, full, 3)
+    ops.smooth3_relu_fwd(d, part, 3, box)
+    bsl = tuple(slice(a, b + 1) for a, b in zip(lo, hi))
+    assert torch.equal(part[bsl].cpu(), full[bsl].cpu())
+    rest = part.clone()
+    rest[bsl] = 7.0
+    assert bool((rest == 7.0).all())                                  # nothing written outside the box
+    g = torch.zeros(shape)
+    g[bsl] = torch.tensor(rng.randn(*[b - a + 1 for a, b in zip(lo, hi)]).astype(np.float32))
+    g = g.to(dev)
+    gf, gp = torch.empty(shape, device=dev), torch.zeros(shape, device=dev)
+    ops.smooth3_relu_bwd(g, full, gf, 3)
+    ops.smooth3_relu_bwd(g, full, gp, 3, box)
+    assert torch.equal(gp[bsl].cpu(), gf[bsl].cpu())
+    ops.fill_box(part, box, 0.0)
+    assert float(part[bsl].abs().max()) == 0.0 and float(part[0, 0, 0]) == 7.0
+    # weighted-average splat: combine only inside the box, workspace left zero
+    res, domain = [10, 10, 10], [10, 10, 10]
+    p = torch.tensor(rng.uniform(0.35, 0.65, (800, 3)).astype(np.float32)).to(dev)
+    r = torch.tensor(rng.uniform(0.2, 1, (800, 2)).astype(np.float32)).to(dev)
+    var = torch.tensor(rng.uniform(-1.3, 1.3, (800, 2)).astype(np.float32)).to(dev)
+    hs = [2.0, 1.0]
+    grid = _lib.make_grid(3, res, domain, 1, False)
+    wmap = ops.splat_wavg_wmap(p, grid, hs)
+    occ = (wmap > 0).any(0).reshape(res)
+    idx = torch.nonzero(occ)
+    wb = _lib.make_box(idx.min(0).values.tolist(), idx.max(0).values.tolist())
+    num = torch.zeros_like(wmap)
+    out_f, out_b = torch.empty(res, device=dev), torch.zeros(res, device=dev)
+    ops.splat_wavg_fwd(p, r, var, grid, hs, wmap, torch.empty_like(wmap), out_f)
+    for _ in range(2):                                                # second pass: num was left clean
+        ops.splat_wavg_fwd(p, r, var, grid, hs, wmap, num, out_b, wb)
+        close(out_b, out_f, what='wavg box')
+        assert float(num.abs().max()) == 0.0
+
+
 # ---- optimiser / glue -----------------------------------------------------------------------
 def test_adam_matches_tf_formula_with_nan(dev):
     rng = np.random.RandomState(15)

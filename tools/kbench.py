@@ -52,13 +52,15 @@ def main():
     st = Styler(cfg, weights=synth.vgg_weights(), device=dev)
     st.style_img = sty
     res = [wl['res']] * 3
-    ws = st._workspace(res)
     grams = st._style_feature(sty, res[1:])
     st.num_frames = 1
     frames, _ = st.upload({'p': p, 'r': r})
+    ws = st._workspace(res, frames)
+    box = ws['box']
+    Vb = ws.get('box_cells', res[0] ** 3)
     fr = frames[0]
     var = torch.zeros(fr['p'].shape[0], 2, device=dev)
-    rot = st._rot_tensor(st.rot_mat_) if wl['rotate'] else None
+    rot = st._rot_all if wl['rotate'] else None
     loss, grad = st.loss_and_grad(fr, var, ws, rot, grams)
     torch.cuda.synchronize()
     D, H, W = res
@@ -71,7 +73,7 @@ def main():
     g_img = torch.randn(nv, H, W, device=dev)
     g_ds = torch.zeros(D, H, W, device=dev)
     key = (fr['id'], tuple(res))
-    wmap = st._frame_cache[key]
+    wmap = st._wmap(fr, res, ws['grid'])
     hs = st._supports()
     g_d = torch.randn(D, H, W, device=dev)
     gvar = torch.empty_like(var)
@@ -84,18 +86,21 @@ def main():
         out[name] = {'ms': round(ms, 4), 'alg_GBps': round(nbytes / ms / 1e6, 1), 'alg_MB': round(nbytes / 1e6, 1)}
         print('%-28s %8.4f ms  %8.1f GB/s algorithmic (%.1f MB)' % (name, ms, nbytes / ms / 1e6, nbytes / 1e6), flush=True)
 
-    add('raymarch_fwd', lambda: ops.raymarch_fwd(ds, rot, st.transmit, False, img, stot), nv * (4 * V + 8 * P))
+    print('active box cells %d of %d (%.3f)' % (Vb, V, Vb / V))
+    add('raymarch_fwd(full)', lambda: ops.raymarch_fwd(ds, rot, st.transmit, False, img, stot), nv * (4 * V + 8 * P))
+    add('raymarch_bwd(full)', lambda: ops.raymarch_bwd(ds, rot, st.transmit, False, stot, g_img, g_ds), nv * (8 * V + 8 * P))
+    add('raymarch_fwd', lambda: ops.raymarch_fwd(ds, rot, st.transmit, False, img, stot, box), nv * (4 * Vb + 8 * P))
     if rot is not None:
         lib.call('lnst_set_raymarch_merge', 0)
-        add('raymarch_bwd(merge=0)', lambda: ops.raymarch_bwd(ds, rot, st.transmit, False, stot, g_img, g_ds),
-            nv * (8 * V + 8 * P))
+        add('raymarch_bwd(merge=0)', lambda: ops.raymarch_bwd(ds, rot, st.transmit, False, stot, g_img, g_ds, box),
+            nv * (8 * Vb + 8 * P))
         lib.call('lnst_set_raymarch_merge', 1)
-    add('raymarch_bwd', lambda: ops.raymarch_bwd(ds, rot, st.transmit, False, stot, g_img, g_ds), nv * (8 * V + 8 * P))
-    add('splat_wavg_fwd', lambda: ops.splat_wavg_fwd(fr['p'], fr['r'], var, ws['grid'], hs, wmap, ws['num'], ws['d']),
-        N * (12 + 16) + 4 * V)
-    add('splat_wavg_bwd', lambda: ops.splat_wavg_bwd(fr['p'], var, ws['grid'], hs, wmap, g_d, gvar), N * (12 + 16) + 4 * V)
-    add('smooth3_relu_fwd', lambda: ops.smooth3_relu_fwd(ws['d'], ws['ds'], st.k), 8 * V)
-    add('smooth3_relu_bwd', lambda: ops.smooth3_relu_bwd(g_ds, ds, ws['g_d'], st.k), 12 * V)
+    add('raymarch_bwd', lambda: ops.raymarch_bwd(ds, rot, st.transmit, False, stot, g_img, g_ds, box), nv * (8 * Vb + 8 * P))
+    add('splat_wavg_fwd', lambda: ops.splat_wavg_fwd(fr['p'], fr['r'], var, ws['grid'], hs, wmap, ws['num'], ws['d'], box),
+        N * (12 + 16) + 4 * Vb)
+    add('splat_wavg_bwd', lambda: ops.splat_wavg_bwd(fr['p'], var, ws['grid'], hs, wmap, g_d, gvar), N * (12 + 16) + 4 * Vb)
+    add('smooth3_relu_fwd', lambda: ops.smooth3_relu_fwd(ws['d'], ws['ds'], st.k, box), 8 * Vb)
+    add('smooth3_relu_bwd', lambda: ops.smooth3_relu_bwd(g_ds, ds, ws['g_d'], st.k, box), 12 * Vb)
     x = torch.randn(nv, H, W, 3, device=dev)
     d_img = torch.empty_like(x)
 
@@ -103,7 +108,7 @@ def main():
         l = torch.zeros(nv, device=dev)
         return st.image_loss_and_grad(x, d_img, grams, l)
     add('lossnet fwd+bwd (all views)', lossnet, 0)
-    add('zero g_ds', lambda: g_ds.zero_(), 4 * V)
+    add('zero g_ds', lambda: ops.fill_box(g_ds, box, 0.0), 4 * Vb)
     print(json.dumps(out))
 
 
