@@ -182,6 +182,17 @@ def peaks():
     return 6650.0, 1400.0, 'fallback'
 
 
+def _finish(world, dist):
+    """End of a rank's work.  With several ranks: meet at a barrier, then leave without tearing the NCCL
+    communicator down (ncclCommDestroy with captured collectives alive has been seen to block at exit)."""
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
+
+
 # ---------------------------------------------------------------------------------------------
 def run_engine(args):
     import torch.distributed as dist
@@ -310,8 +321,7 @@ def run_engine(args):
     dominant = max(table, key=lambda k: table[k]['ms'])
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        _finish(world, dist)
         return
     hbm_peak, tf_peak, src = peaks()
     d = table[dominant]
@@ -355,8 +365,7 @@ def run_engine(args):
     if world == 1 and not args.no_cpu_baseline:
         out['cpu_baseline'] = cpu_baseline(wl, budget_s=args.cpu_budget)
     print(json.dumps(out), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    _finish(world, dist)
 
 
 # ---------------------------------------------------------------------------------------------

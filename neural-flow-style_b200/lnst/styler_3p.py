@@ -129,7 +129,7 @@ class Styler(StylerBase):
 
     def step_runner(self, fr, g_opt_t, adam, ws, style_grams, lr):
         return StepRunner(self, fr, g_opt_t, adam, ws, style_grams, lr,
-                          use_graph=getattr(self, 'cuda_graphs', self.world == 1))
+                          use_graph=getattr(self, 'cuda_graphs', True))
 
     # ---- geometry ------------------------------------------------------------------------------
     def _grid(self, res):
@@ -299,9 +299,10 @@ class Styler(StylerBase):
                     lsum = l.sum().reshape(1)
                 else:
                     grad, lsum = torch.zeros_like(var), torch.zeros(1, dtype=f32, device=dev)
-                if self.world > 1:
-                    torch.distributed.all_reduce(grad)
-                    torch.distributed.all_reduce(lsum)
+                if self.world > 1:                                 # ONE all-reduce: gradient + loss scalar
+                    buf = torch.cat([grad.reshape(-1), lsum])
+                    torch.distributed.all_reduce(buf)
+                    grad, lsum = buf[:-1].view_as(var), buf[-1:]
                 adam.step(var, grad, lr, gscale=1.0 / self.n_views)
                 loss_t = lsum[0] / self.n_views
                 g_new, scale = var, 1.0
