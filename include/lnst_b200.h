@@ -174,6 +174,9 @@ int lnst_conv_first_fwd(const float* x, const float* w, const float* b, void* y,
                         int32_t W, void* stream);
 int lnst_conv_first_bwd(const void* g, const float* wd, float* gx, int32_t n, int32_t H, int32_t W,
                         void* stream);
+/* Tuning switch (process-wide, default 1): 1 = persistent convolution kernel (one CTA per SM walks the
+ * tile list, TMEM double-buffered), 0 = one CTA per tile. */
+int lnst_set_conv_persistent(int32_t on);
 /* Gram matrices on tensor cores, batched over images (styler_base.py:96-102,152-185):
  * G[i] = F[i]^T F[i] / denom - Gs (fp32 [n,C,C]; Gs NULL => no subtraction), Gd = bf16 copy of G,
  * loss[i] += weight * sum(G[i]^2).  F bf16 [n,P,C], C a multiple of 64.  tcgen05 with MN-major

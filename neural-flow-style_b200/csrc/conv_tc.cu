@@ -281,6 +281,206 @@ conv3x3_tc_k(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ 
   }
 }
 
+// ---- persistent variant --------------------------------------------------------------------------
+// One CTA per SM walks the tile list (tile = 128 pixels x BLOCK_N channels).  The TMA producer and the
+// MMA issuer keep one smem ring (PSTAGES deep, ~192 KB) running ACROSS tile boundaries, and the
+// accumulator is double-buffered in TMEM (2 x BLOCK_N columns): while the four epilogue warps drain
+// tile i (tcgen05.ld, bias/ReLU/mask/addend, bf16 stores), the tensor pipe already works on tile i+1.
+// Per-CTA set-up (barrier init, TMEM allocation, descriptor prefetch) is paid once per SM instead of
+// once per tile, and the mask / addend rows of the next tile are fetched before its accumulator is
+// complete.
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv3x3_tc_persist_k(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
+                     const float* __restrict__ bias, const __nv_bfloat16* __restrict__ mask,
+                     const __nv_bfloat16* __restrict__ addend, __nv_bfloat16* __restrict__ y, ConvShape s,
+                     int n_blocks_n, int n_tiles) {
+  constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
+  constexpr int PSTAGES = (BLOCK_N == 128) ? 6 : 8;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t smem_a = base;
+  const uint32_t smem_b = base + PSTAGES * A_BYTES;
+  const uint32_t bars = smem_b + PSTAGES * B_BYTES;     // full[P], empty[P], tfull[2], tempty[2]
+  const uint32_t bar_tfull = bars + 8 * (2 * PSTAGES);
+  const uint32_t bar_tempty = bar_tfull + 16;
+  const uint32_t tmem_slot = bar_tempty + 16;
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kchunks = s.Cin / BLOCK_K;
+  const int num_kb = s.taps * kchunks;
+  const int tiles_sp = s.tiles_w * s.tiles_h;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&map_x);
+    prefetch_tmap(&map_w);
+    for (int i = 0; i < PSTAGES; ++i) {
+      mbar_init(bars + 8 * i, 1);
+      mbar_init(bars + 8 * (PSTAGES + i), 1);
+    }
+    mbar_init(bar_tfull, 1); mbar_init(bar_tfull + 8, 1);
+    mbar_init(bar_tempty, 4); mbar_init(bar_tempty + 8, 4);          // one arrival per epilogue warp
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(2 * BLOCK_N));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_d = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      uint32_t it = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const int nb = t % n_blocks_n, sp = t / n_blocks_n;
+        const int img = sp / tiles_sp, rem = sp - img * tiles_sp;
+        const int th = rem / s.tiles_w, tw = rem - th * s.tiles_w;
+        const int h0 = th * s.TH, w0 = tw * s.TW, n0 = nb * BLOCK_N;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int st = it % PSTAGES;
+          const uint32_t ph = (it / PSTAGES) & 1;
+          mbar_wait(bars + 8 * (PSTAGES + st), ph ^ 1);
+          const uint32_t full = bars + 8 * st;
+          mbar_expect_tx(full, A_BYTES + B_BYTES);
+          const int tap = kb / kchunks, c0 = (kb - tap * kchunks) * BLOCK_K;
+          int ky = 1, kx = 1;
+          if (s.taps == 9) { ky = tap / 3; kx = tap - 3 * ky; }
+          tma_load_4d(smem_a + st * A_BYTES, &map_x, full, c0, w0 + kx - 1, h0 + ky - 1, img);
+          tma_load_3d(smem_b + st * B_BYTES, &map_w, full, c0, n0, s.w_img ? img : tap);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      const uint32_t idesc = umma_idesc_bf16(BLOCK_M, BLOCK_N);
+      uint32_t it = 0, lt = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++lt) {
+        const uint32_t buf = lt & 1, bph = (lt >> 1) & 1;
+        mbar_wait(bar_tempty + 8 * buf, bph ^ 1);                      // epilogue has drained this buffer
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t acc = tmem_d + buf * BLOCK_N;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int st = it % PSTAGES;
+          const uint32_t ph = (it / PSTAGES) & 1;
+          mbar_wait(bars + 8 * st, ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t a0 = smem_a + st * A_BYTES, b0 = smem_b + st * B_BYTES;
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+            umma_bf16(acc, umma_desc_sw128(a0 + k * UMMA_K * 2), umma_desc_sw128(b0 + k * UMMA_K * 2), idesc,
+                      (kb | k) != 0 ? 1u : 0u);
+          umma_commit(bars + 8 * (PSTAGES + st));
+        }
+        umma_commit(bar_tfull + 8 * buf);
+      }
+    }
+  } else {
+    // ===== epilogue: warps 2..5, TMEM sub-partition = warp % 4 =====
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    uint32_t lt = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++lt) {
+      const int nb = t % n_blocks_n, sp = t / n_blocks_n;
+      const int img = sp / tiles_sp, rem = sp - img * tiles_sp;
+      const int th = rem / s.tiles_w, tw = rem - th * s.tiles_w;
+      const int n0 = nb * BLOCK_N;
+      const int ph_ = th * s.TH + r / s.TW, pw_ = tw * s.TW + r % s.TW;
+      const bool valid = ph_ < s.H && pw_ < s.W;
+      const int64_t pix = ((int64_t)img * s.H + ph_) * s.W + pw_;
+      uint32_t mbits[BLOCK_N / 32];
+#pragma unroll
+      for (int c = 0; c < BLOCK_N / 32; ++c) mbits[c] = 0xffffffffu;
+      if (mask && valid) {
+        const uint4* msk = reinterpret_cast<const uint4*>(mask + pix * s.Cout + n0);
+#pragma unroll
+        for (int c = 0; c < BLOCK_N / 32; ++c) {
+          uint4 mv[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) mv[j] = msk[c * 4 + j];
+          uint32_t bits = 0;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const __nv_bfloat16* mh = reinterpret_cast<const __nv_bfloat16*>(&mv[j]);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) bits |= (__bfloat162float(mh[e]) > 0.f ? 1u : 0u) << (j * 8 + e);
+          }
+          mbits[c] = bits;
+        }
+      }
+      uint4 av[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) av[j] = make_uint4(0, 0, 0, 0);
+      const uint4* add = (addend && valid) ? reinterpret_cast<const uint4*>(addend + pix * s.Cout + n0) : nullptr;
+      if (add) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) av[j] = add[j];
+      }
+      const uint32_t buf = lt & 1, bph = (lt >> 1) & 1;
+      mbar_wait(bar_tfull + 8 * buf, bph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t acc = tmem_d + buf * BLOCK_N + ((uint32_t)(q * 32) << 16);
+#pragma unroll
+      for (int c = 0; c < BLOCK_N / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld32(acc + (uint32_t)(c * 32), v);
+        if (c == BLOCK_N / 32 - 1) {
+          // every TMEM read of this warp has completed: hand the buffer back to the MMA issuer
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
+        }
+        uint4 an[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) an[j] = make_uint4(0, 0, 0, 0);
+        if (add && c + 1 < BLOCK_N / 32) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) an[j] = add[(c + 1) * 4 + j];
+        }
+        if (valid) {
+          const int co = n0 + c * 32;
+          __nv_bfloat16* dst = y + pix * s.Cout + co;
+          uint4 ov[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const __nv_bfloat16* ah = reinterpret_cast<const __nv_bfloat16*>(&av[j]);
+            __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&ov[j]);
+#pragma unroll
+            for (int e = 0; e < 8; e += 2) {
+              float f0 = __uint_as_float(v[j * 8 + e]) * s.scale, f1 = __uint_as_float(v[j * 8 + e + 1]) * s.scale;
+              if (addend) { f0 += __bfloat162float(ah[e]); f1 += __bfloat162float(ah[e + 1]); }
+              if (bias) { f0 += bias[co + j * 8 + e]; f1 += bias[co + j * 8 + e + 1]; }
+              if (s.relu) { f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); }
+              if (!((mbits[c] >> (j * 8 + e)) & 1u)) f0 = 0.f;
+              if (!((mbits[c] >> (j * 8 + e + 1)) & 1u)) f1 = 0.f;
+              oh[e >> 1] = __floats2bfloat162_rn(f0, f1);
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(dst + j * 8) = ov[j];
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) av[j] = an[j];
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(2 * BLOCK_N));
+  }
+}
+
 // ---- Gram matrix G = F^T F on tensor cores ---------------------------------------------------
 // F bf16 [n, P, C] is the NHWC activation seen as P = h*w rows of C channels.  Both operands of
 // F^T F are "MN-major" for the MMA (the contraction index p is the slow one in memory), so the
@@ -448,6 +648,8 @@ static bool make_map(CUtensorMap* m, const void* ptr, int rank, const cuuint64_t
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+static int conv_persistent = 1;   // tuning switch: 1 = persistent kernel, 0 = one CTA per tile
+
 template <int BLOCK_N>
 static int launch_conv(const CUtensorMap& mx, const CUtensorMap& mw, const float* bias, const __nv_bfloat16* mask,
                        const __nv_bfloat16* addend, __nv_bfloat16* y, const ConvShape& s, int n_img,
@@ -458,6 +660,27 @@ static int launch_conv(const CUtensorMap& mx, const CUtensorMap& mw, const float
     cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_k<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return (int)e;
     configured = true;
+  }
+  if (conv_persistent) {
+    constexpr int PSTAGES = (BLOCK_N == 128) ? 6 : 8;
+    const int psmem = PSTAGES * (A_BYTES + BLOCK_N * BLOCK_K * 2) + 8 * (2 * PSTAGES + 4) + 16 + 1024;
+    static bool pconfigured = false;
+    static int sms = 148;
+    if (!pconfigured) {
+      cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_persist_k<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           psmem);
+      if (e != cudaSuccess) return (int)e;
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      pconfigured = true;
+    }
+    const int n_blocks_n = s.Cout / BLOCK_N;
+    const int n_tiles = s.tiles_w * s.tiles_h * n_img * n_blocks_n;
+    const int grid = n_tiles < sms ? n_tiles : sms;
+    conv3x3_tc_persist_k<BLOCK_N><<<grid, NUM_THREADS, psmem, stream>>>(mx, mw, bias, mask, addend, y, s, n_blocks_n,
+                                                                        n_tiles);
+    return (int)cudaGetLastError();
   }
   dim3 grid(s.tiles_w * s.tiles_h * n_img, s.Cout / BLOCK_N);
   conv3x3_tc_k<BLOCK_N><<<grid, NUM_THREADS, smem, stream>>>(mx, mw, bias, mask, addend, y, s);
@@ -712,6 +935,8 @@ extern "C" int lnst_conv_first_bwd(const void* g, const float* wd, float* gx, in
                                                                                      H, W);
   return lnst_status();
 }
+
+extern "C" int lnst_set_conv_persistent(int32_t on) { tc::conv_persistent = on ? 1 : 0; return LNST_OK; }
 
 extern "C" int lnst_tc_supported(void) { return tc::encode_fn() != nullptr ? 1 : 0; }
 
