@@ -91,6 +91,9 @@ class Styler(StylerBase):
         self._frame_cache = {}
         self._pool = None
         self._rot_all = self._rot_mine = None
+        # what the ranks split: 'views' (mean-gradient mode), 'frames' (sequences) or
+        # nothing (replicas); decided per run() by _set_shard
+        self.view_rank, self.view_world = (self.rank, self.world) if self.view_mode == 'allreduce' else (0, 1)
         self._eye = self._rot_tensor([np.identity(3)])
         if self.rotate:
             self._upload_views()
@@ -103,8 +106,8 @@ class Styler(StylerBase):
     def _upload_views(self):
         """Host view matrices -> the persistent device buffers the kernels (and graphs) read."""
         allv = self._rot_tensor(self.rot_mat_)
-        mine = self._rot_tensor([self.rot_mat_[i] for i in range(self.rank, self.n_views, self.world)]) \
-            if self.n_views > self.rank else None
+        mine = self._rot_tensor([self.rot_mat_[i] for i in range(self.view_rank, self.n_views, self.view_world)]) \
+            if self.n_views > self.view_rank else None
         if self._rot_all is None or (mine is not None) != (self._rot_mine is not None) or \
                 (mine is not None and mine.shape != self._rot_mine.shape):
             self._rot_all, self._rot_mine = allv, mine
@@ -116,8 +119,49 @@ class Styler(StylerBase):
     def set_world(self, rank, world):
         """Override the (rank, world) taken from torch.distributed at construction (tests)."""
         self.rank, self.world = rank, world
+        self.view_rank, self.view_world = (rank, world) if self.view_mode == 'allreduce' else (0, 1)
         if self.rotate:
             self._upload_views()
+
+    def _set_shard(self, nf):
+        """Pick what this run splits over the ranks.  Views shard only in the mean-gradient mode (in the
+        reference-exact sequential mode each view's Adam step depends on the previous one); frames
+        shard whenever there are several (their only coupling is the temporal filter on the updates,
+        one all-gather per iteration); otherwise every rank is a replica."""
+        mode = getattr(self, 'shard', None)
+        if mode is None:
+            if self.world == 1:
+                mode = 'none'
+            elif self.rotate and self.view_mode == 'allreduce':
+                mode = 'views'
+            else:
+                mode = 'frames' if nf > 1 else 'none'
+        vr, vw = (self.rank, self.world) if mode == 'views' else (0, 1)
+        if (vr, vw) != (self.view_rank, self.view_world):
+            self.view_rank, self.view_world = vr, vw
+            if self.rotate:
+                self._upload_views()
+        return mode
+
+    def _frame_owners(self, key_frames):
+        """rank owning each key frame: contiguous blocks of Adam groups (frames sharing one optimizer,
+        styler_3p.py:315-323, are order-dependent and stay together)."""
+        groups = sorted({t // self.frames_per_opt for t in key_frames})
+        chunks = np.array_split(np.arange(len(groups)), self.world)
+        owner_of_group = {groups[i]: r for r, c in enumerate(chunks) for i in c}
+        return {t: owner_of_group[t // self.frames_per_opt] for t in key_frames}
+
+    def _gather_frames(self, local, owners, keys, shape):
+        """{t: tensor of ``shape``} held by the owners -> the same for every key frame on every rank
+        (one all_gather of a buffer padded to the largest share)."""
+        per_rank = [[t for t in keys if owners[t] == r] for r in range(self.world)]
+        most = max(len(x) for x in per_rank)
+        buf = torch.zeros([most] + [int(v) for v in shape], dtype=f32, device=self.device)
+        for j, t in enumerate(per_rank[self.rank]):
+            buf[j].copy_(local[t])
+        out = [torch.empty_like(buf) for _ in range(self.world)]
+        torch.distributed.all_gather(out, buf)
+        return {t: out[r][j] for r in range(self.world) for j, t in enumerate(per_rank[r])}
 
     def _advance_views(self):
         """Poisson-disc view sets are re-drawn after every frame pass (styler_3p.py:344-349)."""
@@ -299,7 +343,7 @@ class Styler(StylerBase):
                     lsum = l.sum().reshape(1)
                 else:
                     grad, lsum = torch.zeros_like(var), torch.zeros(1, dtype=f32, device=dev)
-                if self.world > 1:                                 # ONE all-reduce: gradient + loss scalar
+                if self.view_world > 1:                            # ONE all-reduce: gradient + loss scalar
                     buf = torch.cat([grad.reshape(-1), lsum])
                     torch.distributed.all_reduce(buf)
                     grad, lsum = buf[:-1].view_as(var), buf[-1:]
@@ -361,6 +405,11 @@ class Styler(StylerBase):
         g_opt = [torch.zeros(fr['p'].shape[0], width, dtype=f32, device=dev) for fr in frames]
         eye = True if self.rotate else False
 
+        key_frames = list(range(0, nf, self.batch_size * self.interp))
+        shard = self._set_shard(nf)
+        owners = self._frame_owners(key_frames) if shard == 'frames' else {t: self.rank for t in key_frames}
+        mine = [t for t in key_frames if owners[t] == self.rank]
+
         loss_history, d_intm, opt_ = [], [], {}
         for octave in range(self.octave_n):
             res = oct_size[octave]
@@ -370,31 +419,45 @@ class Styler(StylerBase):
             if self.w_style and self.style_img is not None:        # :281-286
                 style_grams = self._style_feature(self.style_img, res[1:])
             lr = lr_list[octave] if lr_list is not None else (self.lr[octave] if isinstance(self.lr, list) else self.lr)
-            loss_o, intm_o = [], []
+            loss_o, intm_o = {t: [] for t in mine}, {}
             runners = {}
             for step in range(self.iter):
                 deltas = {}
-                for t in range(0, nf, self.batch_size * self.interp):
+                for t in mine:
                     fr = frames[t]
                     adam = opt_.setdefault(t // self.frames_per_opt, _Adam())   # :315-323
                     if t not in runners:
                         runners[t] = self.step_runner(fr, g_opt[t], adam, ws, style_grams, lr)
                     var, loss_t, deltas[t] = runners[t]()
-                    loss_o.append(loss_t.clone())
+                    loss_o[t].append(loss_t.clone())
                     if step == self.iter - 1 and octave < self.octave_n - 1:   # :365-370
                         _, _, d_img = self.infer(fr, var, ws, eye)
-                        intm_o.append(d_img)
-                key = list(range(0, nf, self.interp))
+                        intm_o[t] = d_img
                 if self.window_sigma > 0 and nf > 1:               # :382-383
-                    sm = ops.temporal_gauss(torch.stack([deltas[t] for t in key], 0), self.window_sigma)
-                    for j, t in enumerate(key):
+                    if shard == 'frames':                          # the one exchange step of a sharded sequence
+                        deltas = self._gather_frames(deltas, owners, key_frames, g_opt[key_frames[0]].shape)
+                    sm = ops.temporal_gauss(torch.stack([deltas[t] for t in key_frames], 0), self.window_sigma)
+                    for j, t in enumerate(key_frames):
                         deltas[t] = sm[j]
-                for t in key:                                      # :385-386
+                for t in mine:                                     # :385-386
                     ops.axpy(g_opt[t], deltas[t].contiguous(), 1.0)
-            loss_history.append([float(v) for v in torch.stack(loss_o).cpu().tolist()] if loss_o else [])
+            hist = {t: torch.stack(v) for t, v in loss_o.items() if v}
+            if shard == 'frames':
+                hist = self._gather_frames(hist, owners, key_frames, (self.iter,)) if self.iter else {}
+                if octave < self.octave_n - 1:
+                    intm_o = self._gather_frames({t: v.to(f32) for t, v in intm_o.items()}, owners, key_frames,
+                                                 tuple(self._net_hw(res[1:])) + (3,))
+            # the reference appends one loss per (step, frame) in that order (:342,355,388)
+            loss_history.append([float(v) for v in torch.stack([hist[t] for t in key_frames], 1).reshape(-1).cpu().tolist()]
+                                if hist else [])
             if octave < self.octave_n - 1:
-                d_intm.append(torch.stack(intm_o, 0).cpu().numpy().astype(np.uint8))
+                d_intm.append(torch.stack([intm_o[t] for t in key_frames], 0).cpu().numpy().astype(np.uint8))
             runners.clear()                                        # graphs hold this octave's workspaces
+
+        if shard == 'frames':                                      # every rank finishes with every frame's variables
+            got = self._gather_frames({t: g_opt[t] for t in mine}, owners, key_frames, g_opt[key_frames[0]].shape)
+            for t in key_frames:
+                g_opt[t] = got[t].contiguous()
 
         if self.interp > 1:                                        # :392-397
             w = np.linspace(0, 1, self.interp + 1)

@@ -41,6 +41,48 @@ def _worker(rank, world, port, out_path):
     dist.destroy_process_group()
 
 
+def _frames_worker(rank, world, port, out_path):
+    sys.path[:0] = [ROOT, os.path.join(ROOT, 'neural-flow-style_b200'), os.path.join(ROOT, 'tests')]
+    import torch.distributed as dist
+    from helpers import liquid_cfg
+    from lnst import synth
+    from lnst.styler_3p import Styler
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', init_method='tcp://127.0.0.1:%d' % port, rank=rank, world_size=world,
+                            device_id=torch.device('cuda', rank))
+    res = 16
+    # C4 shape, scaled down: position mode, liquid render, 6 frames, per-frame Adam, temporal filter
+    kw = dict(res=res, iter=3, conv_math='fp32', num_frames=6, window_sigma=2.0, frames_per_opt=1,
+              style_layer=['conv1_2', 'conv2_1'], w_style_layer=[0.5, 0.5])
+    p = synth.liquid_particles(1500, num_frames=6)
+    sty = synth.style_image(res, res)
+    st = Styler(liquid_cfg(**kw), weights=synth.vgg_weights())
+    st.style_img = sty
+    out = st.run({'p': p})
+    if rank == 0:
+        solo = Styler(liquid_cfg(**kw), weights=synth.vgg_weights())
+        solo.set_world(0, 1)
+        solo.style_img = sty
+        ref = solo.run({'p': p})
+        np.savez(out_path, l=np.array(out['l']), l_ref=np.array(ref['l']), g=np.stack(out['g_opt']),
+                 g_ref=np.stack(ref['g_opt']), d=out['d'], d_ref=ref['d'])
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_frames_sharded_over_two_gpus_match_one(tmp_path):
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    out = str(tmp_path / 'res.npz')
+    port = 29700 + (os.getpid() % 2000)
+    mp.spawn(_frames_worker, args=(2, port, out), nprocs=2, join=True)
+    z = np.load(out)
+    np.testing.assert_allclose(z['l'], z['l_ref'], rtol=1e-3)
+    assert np.linalg.norm(z['g'] - z['g_ref']) <= 1e-2 * np.linalg.norm(z['g_ref'])
+    assert np.abs(z['d'] - z['d_ref']).max() <= 1e-2 * np.abs(z['d_ref']).max()
+
+
 @pytest.mark.gpu
 def test_two_gpus_match_one(tmp_path):
     if torch.cuda.device_count() < 2:
