@@ -75,7 +75,7 @@ def algorithmic_units(name, a, nk=2):
         fwd = 'fwd' in name
         D, H, W = [v(x) for x in (a[2:5] if fwd else a[3:6])]
         return ((8 if fwd else 12) * box_cells(a[6] if fwd else a[7], D * H * W), 0)
-    if name in ('lnst_splat_wavg_fwd_box', 'lnst_splat_wavg_bwd'):
+    if name in ('lnst_splat_wavg_fwd_box', 'lnst_splat_wavg_bwd', 'lnst_splat_wavg_bwd_coef'):
         fwd = 'fwd' in name
         n = v(a[3] if fwd else a[2])
         g = (a[4] if fwd else a[3])._obj

@@ -79,6 +79,13 @@ int lnst_splat_wavg_fwd_box(const float* p, const float* r, const float* var, in
 int lnst_splat_wavg_bwd(const float* p, const float* var, int64_t n, const LnstGrid* g, const float* h,
                         int32_t nk, const float* wmap, const float* g_out, float* g_var, void* stream);
 
+/* Density-mode fast path (3-D, nsize = 1): coef [nk,cells] = d out/d num per cell (1/wmap, 1, or NaN where
+ * wmap == 0 -- TF's where/div rule), computed once per (frame, octave) like wmap; the gradient kernel
+ * then needs no division.  Same result as lnst_splat_wavg_bwd. */
+int lnst_splat_wavg_coef(const float* wmap, int32_t nk, int64_t cells, float* coef, void* stream);
+int lnst_splat_wavg_bwd_coef(const float* p, const float* var, int64_t n, const LnstGrid* g, const float* h,
+                             int32_t nk, const float* coef, const float* g_out, float* g_var, void* stream);
+
 /* ---- field post-processing (styler_3p.py:112-125: conv3d [1,k,1]^3/sum SAME + max(d,0)) -- */
 /* out = relu(smooth(in)); cells whose pre-activation is < 0 are stored as -0.0f so that the
  * backward pass can apply TF's maximum() gradient rule (passes at equality) without a mask. */

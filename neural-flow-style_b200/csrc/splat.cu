@@ -10,6 +10,7 @@
 #define LNST_MAX_NK 4
 struct SplatKernels {
   float h[LNST_MAX_NK];
+  float inv_h[LNST_MAX_NK];
   float sigma[LNST_MAX_NK];
 };
 
@@ -188,7 +189,7 @@ __global__ void splat_wavg_wmap_k(const float* __restrict__ p, int64_t n, LnstGr
   if (!pt.valid) return;
   for_each_target<DIM>(pt, g, [&](int64_t cell, const float*, float len) {
     for (int k = 0; k < nk; ++k) {
-      const float w = cubic_w(len / ks.h[k], ks.sigma[k]);
+      const float w = cubic_w(len * ks.inv_h[k], ks.sigma[k]);
       if (w != 0.f) atomicAdd(wmap + k * cells + cell, w);
     }
   });
@@ -210,7 +211,7 @@ __global__ void splat_wavg_num_k(const float* __restrict__ p, const float* __res
   }
   for_each_target<DIM>(pt, g, [&](int64_t cell, const float*, float len) {
     for (int k = 0; k < nk; ++k) {
-      const float w = cubic_w(len / ks.h[k], ks.sigma[k]);
+      const float w = cubic_w(len * ks.inv_h[k], ks.sigma[k]);
       if (w != 0.f) atomicAdd(num + k * cells + cell, w * x[k]);
     }
   });
@@ -227,6 +228,116 @@ __global__ void splat_wavg_combine_k(const float* __restrict__ wmap, const float
     s += (w > 1e-6f) ? v / w : v;                 // transform.py:1703
   }
   out[c] = s;
+}
+
+// ---- 3-D, nsize = 1, NK kernels: the density-mode hot path (styler_3p.py:79-87) -------------------
+// Fully unrolled 27-cell stencil with one 32-bit anchor; particles whose stencil leaves the grid take
+// the generic path.  Same arithmetic as for_each_target (offsets, sum of squares, sqrtf), so a cell
+// gets the same weight from either path and from the wmap / num / gradient kernels alike.
+template <class F>
+__device__ __forceinline__ void stencil27(const Particle<3>& pt, const LnstGrid& g, F f) {
+  const int H = g.res[1], W = g.res[2];
+  const int base = (pt.idx[0] * H + (H - 1 - pt.idx[1])) * W + pt.idx[2];
+  float dz[3], dy[3], dx[3];
+#pragma unroll
+  for (int s = 0; s < 3; ++s) {
+    const float o = __fmul_rn((float)(s - 1), g.cell);
+    dz[s] = __fadd_rn(pt.r[0], -o);
+    dy[s] = __fadd_rn(pt.r[1], -o);
+    dx[s] = __fadd_rn(pt.r[2], -o);
+  }
+#pragma unroll
+  for (int sz = 0; sz < 3; ++sz)
+#pragma unroll
+    for (int sy = 0; sy < 3; ++sy)
+#pragma unroll
+      for (int sx = 0; sx < 3; ++sx) {
+        const float len = sqrtf(dx[sx] * dx[sx] + dy[sy] * dy[sy] + dz[sz] * dz[sz]);
+        f(base + (sz - 1) * H * W - (sy - 1) * W + (sx - 1), len);
+      }
+}
+__device__ __forceinline__ bool stencil_inside(const Particle<3>& pt, const LnstGrid& g) {
+  return pt.idx[0] >= 1 && pt.idx[0] < g.res[0] - 1 && pt.idx[1] >= 1 && pt.idx[1] < g.res[1] - 1 &&
+         pt.idx[2] >= 1 && pt.idx[2] < g.res[2] - 1;
+}
+
+template <int NK>
+__global__ void __launch_bounds__(256) splat_wavg_num3_k(const float* __restrict__ p, const float* __restrict__ r,
+                                                         const float* __restrict__ var, int64_t n, LnstGrid g,
+                                                         SplatKernels ks, int64_t cells, float* __restrict__ num) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const Particle<3> pt = load_particle<3>(p, nullptr, i, g);
+  if (!pt.valid) return;
+  float x[NK];
+#pragma unroll
+  for (int k = 0; k < NK; ++k) {
+    float v = var ? var[i * NK + k] : 0.f;
+    v = fminf(fmaxf(v, -1.f), 1.f);               // styler_3p.py:74
+    x[k] = r[i * NK + k] + v;                     // :76
+  }
+  if (stencil_inside(pt, g)) {
+    stencil27(pt, g, [&](int cell, float len) {
+#pragma unroll
+      for (int k = 0; k < NK; ++k) {
+        const float w = cubic_w(len * ks.inv_h[k], ks.sigma[k]);
+        if (w != 0.f) atomicAdd(num + k * cells + cell, w * x[k]);
+      }
+    });
+  } else {
+    for_each_target<3>(pt, g, [&](int64_t cell, const float*, float len) {
+#pragma unroll
+      for (int k = 0; k < NK; ++k) {
+        const float w = cubic_w(len * ks.inv_h[k], ks.sigma[k]);
+        if (w != 0.f) atomicAdd(num + k * cells + cell, w * x[k]);
+      }
+    });
+  }
+}
+
+// coef = d where(wm > eps, num/wm, num) / d num as TF computes it (transform.py:1703): 1/wm, 1, or NaN
+// where wm == 0 (the untaken division branch contributes 0/0).  Positions are constants in density
+// mode, so this is computed once per (frame, octave) next to wmap.
+__global__ void splat_wavg_coef_k(const float* __restrict__ wmap, int64_t total, float* __restrict__ coef) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const float wm = wmap[i];
+  coef[i] = (wm > 1e-6f) ? 1.f / wm : (wm == 0.f ? __int_as_float(0x7fc00000) : 1.f);
+}
+
+template <int NK>
+__global__ void __launch_bounds__(256) splat_wavg_bwd3_k(const float* __restrict__ p, const float* __restrict__ var,
+                                                         int64_t n, LnstGrid g, SplatKernels ks, int64_t cells,
+                                                         const float* __restrict__ coef,
+                                                         const float* __restrict__ g_out, float* __restrict__ g_var) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const Particle<3> pt = load_particle<3>(p, nullptr, i, g);
+  float acc[NK];
+#pragma unroll
+  for (int k = 0; k < NK; ++k) acc[k] = 0.f;
+  if (pt.valid) {
+    if (stencil_inside(pt, g)) {
+      stencil27(pt, g, [&](int cell, float len) {
+        const float go = g_out[cell];
+#pragma unroll
+        for (int k = 0; k < NK; ++k)
+          acc[k] += cubic_w(len * ks.inv_h[k], ks.sigma[k]) * (coef[k * cells + cell] * go);
+      });
+    } else {
+      for_each_target<3>(pt, g, [&](int64_t cell, const float*, float len) {
+        const float go = g_out[cell];
+#pragma unroll
+        for (int k = 0; k < NK; ++k)
+          acc[k] += cubic_w(len * ks.inv_h[k], ks.sigma[k]) * (coef[k * cells + cell] * go);
+      });
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < NK; ++k) {
+    const float v = var ? var[i * NK + k] : 0.f;
+    g_var[i * NK + k] = (v >= -1.f && v <= 1.f) ? acc[k] : 0.f;   // clip_by_value gradient
+  }
 }
 
 // box variant: combines only the cells of the sub-volume and clears the num it consumed
@@ -260,7 +371,7 @@ __global__ void splat_wavg_bwd_k(const float* __restrict__ p, const float* __res
     for_each_target<DIM>(pt, g, [&](int64_t cell, const float*, float len) {
       const float go = g_out[cell];
       for (int k = 0; k < nk; ++k) {
-        const float w = cubic_w(len / ks.h[k], ks.sigma[k]);
+        const float w = cubic_w(len * ks.inv_h[k], ks.sigma[k]);
         const float wm = wmap[k * cells + cell];
         // gradient of where(wm>eps, num/wm, num) w.r.t. num as TF computes it: the untaken
         // division branch contributes 0/wm, which is NaN when wm == 0 (transform.py:1703).
@@ -294,6 +405,7 @@ static inline bool fill_kernels(SplatKernels& ks, int dim, const float* h, int n
   if (!h || nk < 1 || nk > LNST_MAX_NK) return false;
   for (int k = 0; k < LNST_MAX_NK; ++k) {
     ks.h[k] = k < nk ? h[k] : 1.f;
+    ks.inv_h[k] = 1.f / ks.h[k];
     ks.sigma[k] = k < nk ? sigma_for(dim, h[k]) : 0.f;
     if (!(ks.h[k] > 0.f)) return false;
   }
@@ -395,7 +507,15 @@ extern "C" int lnst_splat_wavg_fwd_box(const float* p, const float* r, const flo
   const int64_t cells = grid_cells(g);
   if (!box) cudaMemsetAsync(num, 0, sizeof(float) * cells * nk, lnst_stream(stream));
   const int T = 256;
-  if (n > 0) {
+  if (n > 0 && g->dim == 3 && g->nsize == 1) {
+    const dim3 grid_(lnst_blocks(n, T)), blk(T);
+    switch (nk) {
+      case 1: { auto k = splat_wavg_num3_k<1>; LNST_LAUNCH(k, grid_, blk, 0, lnst_stream(stream), p, r, var, n, *g, ks, cells, num); break; }
+      case 2: { auto k = splat_wavg_num3_k<2>; LNST_LAUNCH(k, grid_, blk, 0, lnst_stream(stream), p, r, var, n, *g, ks, cells, num); break; }
+      case 3: { auto k = splat_wavg_num3_k<3>; LNST_LAUNCH(k, grid_, blk, 0, lnst_stream(stream), p, r, var, n, *g, ks, cells, num); break; }
+      default: { auto k = splat_wavg_num3_k<4>; LNST_LAUNCH(k, grid_, blk, 0, lnst_stream(stream), p, r, var, n, *g, ks, cells, num); break; }
+    }
+  } else if (n > 0) {
     if (g->dim == 3) {
       auto k = splat_wavg_num_k<3>;
       LNST_LAUNCH(k, dim3(lnst_blocks(n, T)), dim3(T), 0, lnst_stream(stream), p, r, var, n, *g, ks,
@@ -414,6 +534,32 @@ extern "C" int lnst_splat_wavg_fwd_box(const float* p, const float* r, const flo
   }
   LNST_LAUNCH(splat_wavg_combine_k, dim3(lnst_blocks(cells, T)), dim3(T), 0, lnst_stream(stream), wmap,
               (const float*)num, (int)nk, cells, out);
+  return lnst_status();
+}
+
+extern "C" int lnst_splat_wavg_coef(const float* wmap, int32_t nk, int64_t cells, float* coef, void* stream) {
+  if (!wmap || !coef || nk < 1 || nk > LNST_MAX_NK || cells < 1) return LNST_EARG;
+  LNST_LAUNCH(splat_wavg_coef_k, dim3(lnst_blocks(cells * nk, 256)), dim3(256), 0, lnst_stream(stream), wmap,
+              cells * nk, coef);
+  return lnst_status();
+}
+
+extern "C" int lnst_splat_wavg_bwd_coef(const float* p, const float* var, int64_t n, const LnstGrid* g,
+                                        const float* h, int32_t nk, const float* coef, const float* g_out,
+                                        float* g_var, void* stream) {
+  SplatKernels ks;
+  if (!grid_ok(g) || !p || !coef || !g_out || !g_var || n < 0 || !fill_kernels(ks, g ? g->dim : 3, h, nk))
+    return LNST_EARG;
+  if (g->dim != 3 || g->nsize != 1) return LNST_EARG;
+  if (n == 0) return LNST_OK;
+  const int64_t cells = grid_cells(g);
+  const dim3 grid_(lnst_blocks(n, 256)), blk(256);
+  switch (nk) {
+    case 1: { auto k = splat_wavg_bwd3_k<1>; LNST_LAUNCH(k, grid_, blk, 0, lnst_stream(stream), p, var, n, *g, ks, cells, coef, g_out, g_var); break; }
+    case 2: { auto k = splat_wavg_bwd3_k<2>; LNST_LAUNCH(k, grid_, blk, 0, lnst_stream(stream), p, var, n, *g, ks, cells, coef, g_out, g_var); break; }
+    case 3: { auto k = splat_wavg_bwd3_k<3>; LNST_LAUNCH(k, grid_, blk, 0, lnst_stream(stream), p, var, n, *g, ks, cells, coef, g_out, g_var); break; }
+    default: { auto k = splat_wavg_bwd3_k<4>; LNST_LAUNCH(k, grid_, blk, 0, lnst_stream(stream), p, var, n, *g, ks, cells, coef, g_out, g_var); break; }
+  }
   return lnst_status();
 }
 

@@ -40,6 +40,8 @@ SIGNATURES = {
     'lnst_splat_wavg_fwd': [vp, vp, vp, i64, GP, FP, i32, vp, vp, vp, vp],
     'lnst_splat_wavg_fwd_box': [vp, vp, vp, i64, GP, FP, i32, vp, vp, vp, BP, vp],
     'lnst_splat_wavg_bwd': [vp, vp, i64, GP, FP, i32, vp, vp, vp, vp],
+    'lnst_splat_wavg_coef': [vp, i32, i64, vp, vp],
+    'lnst_splat_wavg_bwd_coef': [vp, vp, i64, GP, FP, i32, vp, vp, vp, vp],
     'lnst_smooth3_relu_fwd': [vp, vp, i32, i32, i32, i32, vp],
     'lnst_smooth3_relu_bwd': [vp, vp, vp, i32, i32, i32, i32, vp],
     'lnst_smooth3_relu_fwd_box': [vp, vp, i32, i32, i32, i32, BP, vp],

@@ -73,6 +73,18 @@ def splat_wavg_bwd(p, var, grid, hs, wmap, g_out, g_var):
     return g_var
 
 
+def splat_wavg_coef(wmap):
+    coef = torch.empty_like(wmap)
+    _lib.get().call('lnst_splat_wavg_coef', ptr(wmap), wmap.shape[0], wmap.shape[1], ptr(coef), _s(wmap))
+    return coef
+
+
+def splat_wavg_bwd_coef(p, var, grid, hs, coef, g_out, g_var):
+    _lib.get().call('lnst_splat_wavg_bwd_coef', ptr(p), ptr(var), p.shape[0], C.byref(grid), _harr(hs), len(hs),
+                    ptr(coef), ptr(g_out), ptr(g_var), _s(p))
+    return g_var
+
+
 # ---- field ---------------------------------------------------------------------------------
 def smooth3_relu_fwd(d, out, k, box=None):
     D, H, W = d.shape

@@ -207,6 +207,13 @@ class Styler(StylerBase):
             self._frame_cache[key] = ops.splat_wavg_wmap(fr['p'], grid, self._supports())
         return self._frame_cache[key]
 
+    def _coef(self, fr, res, grid):
+        """d out/d num per kernel and cell (1/wmap with TF's where/div NaN rule): constant like wmap."""
+        key = (fr['id'], tuple(res), 'coef')
+        if key not in self._frame_cache:
+            self._frame_cache[key] = ops.splat_wavg_coef(self._wmap(fr, res, grid))
+        return self._frame_cache[key]
+
     def _workspace(self, res, frames=None):
         """Per-octave volumes.  With ``frames`` (density mode) the active box is set: the bounding box
         of every cell any frame's particles can reach (sum of weights > 0), grown by one voxel for the
@@ -297,7 +304,12 @@ class Styler(StylerBase):
             g_d += (nv * self.w_pressure * 2.0 / d.numel()) * pr
         if 'd' in self.target_field:
             grad = torch.empty_like(var)
-            ops.splat_wavg_bwd(fr['p'], var, ws['grid'], self._supports(), self._wmap(fr, res, ws['grid']), g_d, grad)
+            if self.nsize == 1:
+                ops.splat_wavg_bwd_coef(fr['p'], var, ws['grid'], self._supports(), self._coef(fr, res, ws['grid']),
+                                        g_d, grad)
+            else:
+                ops.splat_wavg_bwd(fr['p'], var, ws['grid'], self._supports(), self._wmap(fr, res, ws['grid']), g_d,
+                                   grad)
             if self.w_density > 0:                                 # styler_base.py:217-223
                 dv = torch.clamp(var, -1, 1)
                 inside = ((var >= -1) & (var <= 1)).to(f32)

@@ -110,6 +110,10 @@ def test_splat_wavg_fwd_bwd_with_nan_rule(dev):
     ops.splat_wavg_bwd(p.to(dev), var.detach().to(dev), grid, hs, wmap, g_out.to(dev), g_var)
     assert torch.isnan(var.grad).any() and not torch.isnan(var.grad).all()
     close(g_var, var.grad, tol=2e-5, what='wavg bwd')
+    # density-mode fast path: unrolled 27-cell stencil + precomputed d out/d num (same NaN rule)
+    g_fast = torch.empty(n, 2, dtype=torch.float32, device=dev)
+    ops.splat_wavg_bwd_coef(p.to(dev), var.detach().to(dev), grid, hs, ops.splat_wavg_coef(wmap), g_out.to(dev), g_fast)
+    close(g_fast, var.grad, tol=2e-5, what='wavg bwd (coef)')
 
 
 # ---- field ----------------------------------------------------------------------------------

@@ -98,7 +98,9 @@ def main():
     add('raymarch_bwd', lambda: ops.raymarch_bwd(ds, rot, st.transmit, False, stot, g_img, g_ds, box), nv * (8 * Vb + 8 * P))
     add('splat_wavg_fwd', lambda: ops.splat_wavg_fwd(fr['p'], fr['r'], var, ws['grid'], hs, wmap, ws['num'], ws['d'], box),
         N * (12 + 16) + 4 * Vb)
-    add('splat_wavg_bwd', lambda: ops.splat_wavg_bwd(fr['p'], var, ws['grid'], hs, wmap, g_d, gvar), N * (12 + 16) + 4 * Vb)
+    add('splat_wavg_bwd(generic)', lambda: ops.splat_wavg_bwd(fr['p'], var, ws['grid'], hs, wmap, g_d, gvar), N * (12 + 16) + 4 * Vb)
+    coef = ops.splat_wavg_coef(wmap)
+    add('splat_wavg_bwd', lambda: ops.splat_wavg_bwd_coef(fr['p'], var, ws['grid'], hs, coef, g_d, gvar), N * (12 + 16) + 4 * Vb)
     add('smooth3_relu_fwd', lambda: ops.smooth3_relu_fwd(ws['d'], ws['ds'], st.k, box), 8 * Vb)
     add('smooth3_relu_bwd', lambda: ops.smooth3_relu_bwd(g_ds, ds, ws['g_d'], st.k, box), 12 * Vb)
     x = torch.randn(nv, H, W, 3, device=dev)
