@@ -184,6 +184,14 @@ int lnst_conv_first_bwd(const void* g, const float* wd, float* gx, int32_t n, in
 /* Tuning switch (process-wide, default 1): 1 = persistent convolution kernel (one CTA per SM walks the
  * tile list, TMEM double-buffered), 0 = one CTA per tile. */
 int lnst_set_conv_persistent(int32_t on);
+/* Tuning switch (default 1): 1 = layers whose weights fit in shared memory load one halo'd patch per tile
+ * and read the 9 taps through descriptor offsets; 2 = every layer does (weights streamed when they do not
+ * fit); 0 = one TMA tile per tap everywhere. */
+int lnst_set_conv_halo(int32_t on);
+/* Data gradient of conv1_1 on tensor cores: g bf16 [n,H,W,64], wd16 bf16 [9,16,64] (rows 0..2 = the
+ * flipped/transposed 64->3 weights, rows 3..15 zero) -> gx fp32 [n,H,W,3]. */
+int lnst_conv_first_bwd_tc(const void* g, const void* wd16, float* gx, int32_t n, int32_t H, int32_t W,
+                           void* stream);
 /* Gram matrices on tensor cores, batched over images (styler_base.py:96-102,152-185):
  * G[i] = F[i]^T F[i] / denom - Gs (fp32 [n,C,C]; Gs NULL => no subtraction), Gd = bf16 copy of G,
  * loss[i] += weight * sum(G[i]^2).  F bf16 [n,P,C], C a multiple of 64.  tcgen05 with MN-major

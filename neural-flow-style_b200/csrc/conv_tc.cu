@@ -93,6 +93,28 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
       "}" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
 }
+// Descriptors split into a constant high word and a low word that only carries the start address
+// (>>4): advancing an operand is ONE 32-bit add in the single issuing thread.  (Rebuilding the 64-bit
+// descriptor with shifts/ors for every MMA cost ~150 issue cycles per instruction -- more than the
+// 32-64 cycles the tensor pipe needs for it -- and capped every kernel here at 30-45 % tensor-active.)
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) {
+  return ((saddr & 0x3FFFFu) >> 4) | ((lbo_bytes >> 4) << 16);
+}
+__device__ __forceinline__ uint32_t desc_hi_sw128(uint32_t sbo_bytes) {
+  return (sbo_bytes >> 4) | (1u << 14) | (2u << 29);      // SBO | version=1 (bit 46) | SWIZZLE_128B (bits 61-63)
+}
+__device__ __forceinline__ void umma_bf16_lh(uint32_t tmem_d, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi,
+                                             uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+      "}" ::"r"(tmem_d), "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "r"(accumulate) : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -108,6 +130,20 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+
+// the same load without the wait: several can be in flight before one tcgen05.wait::ld
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 struct ConvShape {
   int H, W, Cin, Cout;
@@ -185,13 +221,11 @@ conv3x3_tc_k(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ 
         const uint32_t ph = (kb / STAGES) & 1;
         mbar_wait(bars + 8 * st, ph);                                // operands landed
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t a0 = smem_a + st * A_BYTES, b0 = smem_b + st * B_BYTES;
+        const uint32_t alo = desc_lo(smem_a + st * A_BYTES, 16), blo = desc_lo(smem_b + st * B_BYTES, 16);
+        const uint32_t hi = desc_hi_sw128(1024);
 #pragma unroll
-        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-          // advancing 16 bf16 = 32 B inside the 128 B swizzle row
-          umma_bf16(tmem_d, umma_desc_sw128(a0 + k * UMMA_K * 2), umma_desc_sw128(b0 + k * UMMA_K * 2), idesc,
-                    (kb | k) != 0 ? 1u : 0u);
-        }
+        for (int k = 0; k < BLOCK_K / UMMA_K; ++k)   // advancing 16 bf16 = 32 B inside the 128 B swizzle row
+          umma_bf16_lh(tmem_d, alo + k * 2, hi, blo + k * 2, hi, idesc, (kb | k) != 0 ? 1u : 0u);
         umma_commit(bars + 8 * (STAGES + st));                       // frees the slot when the MMAs retire
       }
       umma_commit(bars + 8 * (2 * STAGES));                          // accumulator complete
@@ -374,11 +408,11 @@ conv3x3_tc_persist_k(const __grid_constant__ CUtensorMap map_x, const __grid_con
           const uint32_t ph = (it / PSTAGES) & 1;
           mbar_wait(bars + 8 * st, ph);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t a0 = smem_a + st * A_BYTES, b0 = smem_b + st * B_BYTES;
+          const uint32_t alo = desc_lo(smem_a + st * A_BYTES, 16), blo = desc_lo(smem_b + st * B_BYTES, 16);
+          const uint32_t hi = desc_hi_sw128(1024);
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-            umma_bf16(acc, umma_desc_sw128(a0 + k * UMMA_K * 2), umma_desc_sw128(b0 + k * UMMA_K * 2), idesc,
-                      (kb | k) != 0 ? 1u : 0u);
+            umma_bf16_lh(acc, alo + k * 2, hi, blo + k * 2, hi, idesc, (kb | k) != 0 ? 1u : 0u);
           umma_commit(bars + 8 * (PSTAGES + st));
         }
         umma_commit(bar_tfull + 8 * buf);
@@ -481,6 +515,336 @@ conv3x3_tc_persist_k(const __grid_constant__ CUtensorMap map_x, const __grid_con
   }
 }
 
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ uint64_t umma_desc_sw128_ex(uint32_t saddr, uint32_t sbo_bytes, uint32_t base_off) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)(base_off & 7u) << 49;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ---- halo'd-patch variant: every input byte crosses L2 -> smem ONCE per tile ------------------------
+// The per-tap kernel above re-reads its 128 x 64 A tile for each of the 9 taps (ncu: lts sectors ~16x
+// the input, tensor pipe 24-43 % active at Cin = 64).  Here the tile is TH x TW = 16 x 8 pixels and ONE
+// TMA box {64 ch, TW+2, TH+2} per 64-channel chunk brings the halo'd patch (180 rows of 128 B,
+// SWIZZLE_128B, OOB = zero = SAME padding).  The A operand of tap (ky,kx) is the same patch seen through
+// another descriptor: start + (ky*(TW+2) + kx)*128 B, SBO = (TW+2)*128 B (one 8-row core group = one
+// tile row) -- the swizzle is a function of the absolute smem address, so no base offset is needed
+// (verified on the device by tools/umma_probe.py).  Weights stay RESIDENT in smem for the whole kernel
+// when the layer's 9*Cin*Cout*2 B fit beside the patch ring, else they stream through their own ring.
+// Persistent, TMEM double-buffered, epilogue as above.  OUT3: BLOCK_N = 16, fp32 [pixel,3] output of
+// columns 0..2 (the data gradient of conv1_1).
+constexpr int HTH = 16, HTW = 8;
+constexpr int PATCH_ROWS = (HTH + 2) * (HTW + 2);          // 180
+constexpr int PATCH_BYTES = PATCH_ROWS * 128;              // 23040
+constexpr int PATCH_STRIDE = 23 * 1024;                    // stage stride, keeps every stage 1024 B aligned
+
+struct HaloCfg {
+  int sa, sb;          // patch stages, weight stages (sb = 0: weights resident)
+  int n_blocks_n, n_tiles;
+};
+
+template <int BLOCK_N, bool OUT3>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv3x3_halo_k(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
+               const float* __restrict__ bias, const __nv_bfloat16* __restrict__ mask,
+               __nv_bfloat16* __restrict__ y, float* __restrict__ y3, ConvShape s, HaloCfg cfg) {
+  constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
+  constexpr int TCOLS = (2 * BLOCK_N < 32) ? 32 : 2 * BLOCK_N;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(16) float sbias[512];              // the layer's bias, read as broadcast float4s
+  if (bias)
+    for (int i = threadIdx.x; i < s.Cout && i < 512; i += blockDim.x) sbias[i] = bias[i];
+  const int kchunks = s.Cin / BLOCK_K;
+  const bool resident = cfg.sb == 0;
+  const int n_wslots = resident ? 9 * kchunks : cfg.sb;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t smem_a = base;
+  const uint32_t smem_b = base + cfg.sa * PATCH_STRIDE;
+  const uint32_t bars = smem_b + n_wslots * B_BYTES;
+  const uint32_t bar_afull = bars, bar_aempty = bars + 8 * cfg.sa;
+  const uint32_t bar_bfull = bar_aempty + 8 * cfg.sa, bar_bempty = bar_bfull + 8 * (resident ? 1 : cfg.sb);
+  const uint32_t bar_tfull = bar_bempty + 8 * (resident ? 1 : cfg.sb), bar_tempty = bar_tfull + 16;
+  const uint32_t tmem_slot = bar_tempty + 16;
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_sp = s.tiles_w * s.tiles_h;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&map_x);
+    prefetch_tmap(&map_w);
+    for (int i = 0; i < cfg.sa; ++i) { mbar_init(bar_afull + 8 * i, 1); mbar_init(bar_aempty + 8 * i, 1); }
+    for (int i = 0; i < (resident ? 1 : cfg.sb); ++i) { mbar_init(bar_bfull + 8 * i, 1); mbar_init(bar_bempty + 8 * i, 1); }
+    mbar_init(bar_tfull, 1); mbar_init(bar_tfull + 8, 1);
+    mbar_init(bar_tempty, 4); mbar_init(bar_tempty + 8, 4);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TCOLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_d = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      if (resident) {                                   // all 9 x kchunks weight tiles, once (n0 = 0)
+        mbar_expect_tx(bar_bfull, 9 * kchunks * B_BYTES);
+        for (int tap = 0; tap < 9; ++tap)
+          for (int c = 0; c < kchunks; ++c)
+            tma_load_3d(smem_b + (tap * kchunks + c) * B_BYTES, &map_w, bar_bfull, c * BLOCK_K, 0, tap);
+      }
+      uint32_t ita = 0, itb = 0;
+      for (int t = blockIdx.x; t < cfg.n_tiles; t += gridDim.x) {
+        const int nb = t % cfg.n_blocks_n, sp = t / cfg.n_blocks_n;
+        const int img = sp / tiles_sp, rem = sp - img * tiles_sp;
+        const int th = rem / s.tiles_w, tw = rem - th * s.tiles_w;
+        const int h0 = th * HTH, w0 = tw * HTW, n0 = nb * BLOCK_N;
+        for (int c = 0; c < kchunks; ++c, ++ita) {
+          const int st = ita % cfg.sa;
+          mbar_wait(bar_aempty + 8 * st, ((ita / cfg.sa) & 1) ^ 1);
+          mbar_expect_tx(bar_afull + 8 * st, PATCH_BYTES);
+          tma_load_4d(smem_a + st * PATCH_STRIDE, &map_x, bar_afull + 8 * st, c * BLOCK_K, w0 - 1, h0 - 1, img);
+          if (!resident) {
+            for (int tap = 0; tap < 9; ++tap, ++itb) {
+              const int sb = itb % cfg.sb;
+              mbar_wait(bar_bempty + 8 * sb, ((itb / cfg.sb) & 1) ^ 1);
+              mbar_expect_tx(bar_bfull + 8 * sb, B_BYTES);
+              tma_load_3d(smem_b + sb * B_BYTES, &map_w, bar_bfull + 8 * sb, c * BLOCK_K, n0, tap);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      const uint32_t idesc = umma_idesc_bf16(BLOCK_M, BLOCK_N);
+      uint32_t ita = 0, itb = 0, lt = 0;
+      if (resident) {
+        mbar_wait(bar_bfull, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      }
+      for (int t = blockIdx.x; t < cfg.n_tiles; t += gridDim.x, ++lt) {
+        const uint32_t buf = lt & 1, bph = (lt >> 1) & 1;
+        mbar_wait(bar_tempty + 8 * buf, bph ^ 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t acc = tmem_d + buf * BLOCK_N;
+        for (int c = 0; c < kchunks; ++c, ++ita) {
+          const int st = ita % cfg.sa;
+          mbar_wait(bar_afull + 8 * st, (ita / cfg.sa) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t alo0 = desc_lo(smem_a + st * PATCH_STRIDE, 16);
+          const uint32_t ahi = desc_hi_sw128((HTW + 2) * 128), bhi = desc_hi_sw128(1024);
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap) {
+            const int ky = tap / 3, kx = tap - 3 * ky;                 // compile-time after unrolling
+            uint32_t blo;
+            if (resident) {
+              blo = desc_lo(smem_b + (tap * kchunks + c) * B_BYTES, 16);
+            } else {
+              const int sb = itb % cfg.sb;
+              mbar_wait(bar_bfull + 8 * sb, (itb / cfg.sb) & 1);
+              asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+              blo = desc_lo(smem_b + sb * B_BYTES, 16);
+            }
+            const uint32_t alo = alo0 + ((ky * (HTW + 2) + kx) * 128 >> 4);
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+              umma_bf16_lh(acc, alo + k * 2, ahi, blo + k * 2, bhi, idesc, (c | tap | k) != 0 ? 1u : 0u);
+            if (!resident) {
+              umma_commit(bar_bempty + 8 * (itb % cfg.sb));
+              ++itb;
+            }
+          }
+          umma_commit(bar_aempty + 8 * st);
+        }
+        umma_commit(bar_tfull + 8 * buf);
+      }
+    }
+  } else {
+    // ===== epilogue: warps 2..5, TMEM sub-partition = warp % 4 =====
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    uint32_t lt = 0;
+    for (int t = blockIdx.x; t < cfg.n_tiles; t += gridDim.x, ++lt) {
+      const int nb = t % cfg.n_blocks_n, sp = t / cfg.n_blocks_n;
+      const int img = sp / tiles_sp, rem = sp - img * tiles_sp;
+      const int th = rem / s.tiles_w, tw = rem - th * s.tiles_w;
+      const int n0 = nb * BLOCK_N;
+      const int ph_ = th * HTH + (r >> 3), pw_ = tw * HTW + (r & 7);
+      const bool valid = ph_ < s.H && pw_ < s.W;
+      const int64_t pix = ((int64_t)img * s.H + ph_) * s.W + pw_;
+      const uint32_t buf = lt & 1, bph = (lt >> 1) & 1;
+      const uint32_t acc = tmem_d + buf * BLOCK_N + ((uint32_t)(q * 32) << 16);
+      if (OUT3) {
+        mbar_wait(bar_tfull + 8 * buf, bph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        uint32_t v[16];
+        tmem_ld16(acc, v);
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
+        if (valid) {
+          float* o = y3 + pix * 3;
+          o[0] = __uint_as_float(v[0]) * s.scale; o[1] = __uint_as_float(v[1]) * s.scale; o[2] = __uint_as_float(v[2]) * s.scale;
+        }
+      } else {
+        constexpr int NCH = (BLOCK_N >= 32) ? BLOCK_N / 32 : 1;
+        uint32_t mbits[NCH];
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) mbits[c] = 0xffffffffu;
+        if (mask && valid) {
+          const uint4* msk = reinterpret_cast<const uint4*>(mask + pix * s.Cout + n0);
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) {
+            uint4 mv[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) mv[j] = msk[c * 4 + j];
+            uint32_t bits = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const __nv_bfloat16* mh = reinterpret_cast<const __nv_bfloat16*>(&mv[j]);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) bits |= (__bfloat162float(mh[e]) > 0.f ? 1u : 0u) << (j * 8 + e);
+            }
+            mbits[c] = bits;
+          }
+        }
+        mbar_wait(bar_tfull + 8 * buf, bph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // whole accumulator row into registers (1 CTA/SM: registers are plentiful), then hand the TMEM
+        // buffer straight back: the MMAs of the tile after next never wait for this tile's stores
+        uint32_t v[NCH * 32];
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) tmem_ld32_nowait(acc + (uint32_t)(c * 32), v + c * 32);
+        tmem_ld_wait();
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
+        if (valid) {
+          __nv_bfloat16* dst = y + pix * s.Cout + n0;
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) {
+            uint4 ov[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&ov[j]);
+              const float4 b0 = bias ? *reinterpret_cast<const float4*>(sbias + n0 + c * 32 + j * 8) : make_float4(0, 0, 0, 0);
+              const float4 b1 = bias ? *reinterpret_cast<const float4*>(sbias + n0 + c * 32 + j * 8 + 4) : make_float4(0, 0, 0, 0);
+              const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+              for (int e = 0; e < 8; e += 2) {
+                float f0 = fmaf(__uint_as_float(v[c * 32 + j * 8 + e]), s.scale, bb[e]);
+                float f1 = fmaf(__uint_as_float(v[c * 32 + j * 8 + e + 1]), s.scale, bb[e + 1]);
+                if (s.relu) { f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); }
+                if (!((mbits[c] >> (j * 8 + e)) & 1u)) f0 = 0.f;
+                if (!((mbits[c] >> (j * 8 + e + 1)) & 1u)) f1 = 0.f;
+                oh[e >> 1] = __floats2bfloat162_rn(f0, f1);
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(dst + c * 32 + j * 8) = ov[j];
+          }
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(TCOLS));
+  }
+}
+
+// ---- descriptor probe (developer tool, tools/umma_probe.py) -------------------------------------------
+// One CTA: TMA-load a (TH+2) x (TW+2) = 18 x 10 pixel patch of 64 channels (rows of 128 B, SWIZZLE_128B)
+// either densely (row pitch 10) or one image row per 2048 B slot (row pitch 16), then run ONE
+// M=128,N=16,K=64 MMA whose A operand is tap (ky,kx) of the patch, addressed only through the
+// descriptor (start offset, SBO = pitch, base_offset).  Tells which addressing the hardware accepts
+// for reading the 9 taps of a 3x3 convolution out of one halo'd patch.
+__global__ void __launch_bounds__(128, 1)
+umma_probe_k(const __grid_constant__ CUtensorMap map_dense, const __grid_constant__ CUtensorMap map_row,
+             const __grid_constant__ CUtensorMap map_b, float* __restrict__ out, int pitched, int ky, int kx,
+             int base_mode) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t smem_a = base;                       // up to 18 * 2048 = 36 KiB
+  const uint32_t smem_b = base + 40 * 1024;           // 16 rows x 128 B
+  const uint32_t bars = smem_b + 2048;
+  const uint32_t tmem_slot = bars + 16;
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(bars, 1);
+    mbar_init(bars + 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(32));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_d = *tmem_slot_ptr;
+  const int pitch_rows = pitched ? 16 : 10;
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(bars, 180 * 128 + 16 * 128);
+    if (!pitched) {
+      tma_load_2d(smem_a, &map_dense, bars, 0, 0);
+    } else {
+      for (int r = 0; r < 18; ++r) tma_load_2d(smem_a + r * 2048, &map_row, bars, 0, r * 10);
+    }
+    tma_load_2d(smem_b, &map_b, bars, 0, 0);
+    mbar_wait(bars, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t idesc = umma_idesc_bf16(128, 16);
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t a = smem_a + (ky * pitch_rows + kx) * 128 + k * 32;
+      const uint32_t bo = base_mode == 1 ? ((a >> 7) & 7u) : (base_mode == 2 ? (uint32_t)kx : 0u);
+      umma_bf16(tmem_d, umma_desc_sw128_ex(a, pitch_rows * 128, bo), umma_desc_sw128(smem_b + k * 32), idesc,
+                k != 0 ? 1u : 0u);
+    }
+    umma_commit(bars + 8);
+  }
+  __syncwarp();
+  mbar_wait(bars + 8, 0);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  uint32_t v[16];
+  tmem_ld16(tmem_d + ((uint32_t)(warp * 32) << 16), v);
+  const int row = warp * 32 + lane;
+  for (int j = 0; j < 16; ++j) out[row * 16 + j] = __uint_as_float(v[j]);
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(32));
+  }
+}
+
 // ---- Gram matrix G = F^T F on tensor cores ---------------------------------------------------
 // F bf16 [n, P, C] is the NHWC activation seen as P = h*w rows of C channels.  Both operands of
 // F^T F are "MN-major" for the MMA (the contraction index p is the slow one in memory), so the
@@ -570,10 +934,11 @@ gram_tc_k(const __grid_constant__ CUtensorMap map_f, float* __restrict__ G, int 
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t a0 = smem_a + st * G_OP_BYTES;
         const uint32_t b0 = diag ? a0 : smem_b + st * G_OP_BYTES;
+        const uint32_t alo = desc_lo(a0, G_BOX_BYTES), blo = desc_lo(b0, G_BOX_BYTES);   // LBO: next 64-ch group
+        const uint32_t hi = desc_hi_sw128(1024);                                        // SBO: next 8 pixels
 #pragma unroll
         for (int k = 0; k < 64 / UMMA_K; ++k)
-          umma_bf16(tmem_d, umma_desc_mn_sw128(a0 + k * 2048), umma_desc_mn_sw128(b0 + k * 2048), idesc,
-                    (kb | k) != 0 ? 1u : 0u);
+          umma_bf16_lh(tmem_d, alo + k * (2048 >> 4), hi, blo + k * (2048 >> 4), hi, idesc, (kb | k) != 0 ? 1u : 0u);
         umma_commit(bars + 8 * (G_STAGES + st));
       }
       umma_commit(bars + 8 * (2 * G_STAGES));
@@ -695,6 +1060,67 @@ static void pick_tile(int H, int W, int& TH, int& TW) {
     const long cover = (long)((H + th - 1) / th) * th * ((W + tw - 1) / tw) * tw;
     if (best < 0 || cover < best || (cover == best && tw == 16)) { best = cover; TH = th; TW = tw; }
   }
+}
+
+static int conv_halo = 1;         // tuning switch: 1 = halo'd-patch kernel for the 3x3 convolutions
+
+// smem plan of the halo kernel: weights resident when they fit beside >= 3 patch stages
+template <int BLOCK_N, bool OUT3>
+static int launch_halo(const void* x, const void* wmat, const float* bias, const __nv_bfloat16* mask,
+                       __nv_bfloat16* y, float* y3, int n, int H, int W, int Cin, int Cout, int relu, float scale,
+                       cudaStream_t stream) {
+  constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
+  constexpr int MAX_SMEM = 232448;                        // 227 KiB opt-in limit per CTA
+  const int budget = MAX_SMEM - 2048 - 1024 - 512;          // static bias table, alignment slack, barriers
+  ConvShape s;
+  s.H = H; s.W = W; s.Cin = Cin; s.Cout = Cout; s.relu = relu; s.taps = 9; s.w_img = 0; s.scale = scale;
+  s.TH = HTH; s.TW = HTW;
+  s.tiles_w = (W + HTW - 1) / HTW;
+  s.tiles_h = (H + HTH - 1) / HTH;
+  const int kchunks = Cin / BLOCK_K;
+  HaloCfg cfg;
+  cfg.n_blocks_n = OUT3 ? 1 : Cout / BLOCK_N;
+  cfg.n_tiles = s.tiles_w * s.tiles_h * n * cfg.n_blocks_n;
+  const int wres = 9 * kchunks * B_BYTES;
+  if (cfg.n_blocks_n == 1 && wres + 3 * PATCH_STRIDE <= budget) {
+    cfg.sb = 0;
+    cfg.sa = (budget - wres) / PATCH_STRIDE;
+  } else {
+    cfg.sb = BLOCK_N == 128 ? 8 : 9;
+    cfg.sa = (budget - cfg.sb * B_BYTES) / PATCH_STRIDE;
+  }
+  if (cfg.sa > 6) cfg.sa = 6;
+  if (cfg.sa < 2) return LNST_EARG;
+  const int n_wslots = cfg.sb == 0 ? 9 * kchunks : cfg.sb;
+  const int smem = cfg.sa * PATCH_STRIDE + n_wslots * B_BYTES + 8 * (2 * cfg.sa + 2 * (cfg.sb ? cfg.sb : 1) + 4) + 16 + 1024;
+  CUtensorMap mx, mw;
+  {
+    const cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n};
+    const cuuint64_t strides[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2};
+    const cuuint32_t box[4] = {(cuuint32_t)BLOCK_K, (cuuint32_t)(HTW + 2), (cuuint32_t)(HTH + 2), 1};
+    if (!make_map(&mx, x, 4, dims, strides, box)) return LNST_EARG;
+  }
+  {
+    const int rows = OUT3 ? BLOCK_N : Cout;
+    const cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)rows, 9};
+    const cuuint64_t strides[2] = {(cuuint64_t)Cin * 2, (cuuint64_t)rows * Cin * 2};
+    const cuuint32_t box[3] = {(cuuint32_t)BLOCK_K, (cuuint32_t)BLOCK_N, 1};
+    if (!make_map(&mw, wmat, 3, dims, strides, box)) return LNST_EARG;
+  }
+  static bool configured = false;
+  static int sms = 148;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv3x3_halo_k<BLOCK_N, OUT3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         MAX_SMEM - 2048);
+    if (e != cudaSuccess) return (int)e;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    configured = true;
+  }
+  const int grid = cfg.n_tiles < sms ? cfg.n_tiles : sms;
+  conv3x3_halo_k<BLOCK_N, OUT3><<<grid, NUM_THREADS, smem, stream>>>(mx, mw, bias, mask, y, y3, s, cfg);
+  return (int)cudaGetLastError();
 }
 
 // ---- elementwise helpers on bf16 ---------------------------------------------------------------
@@ -936,6 +1362,33 @@ extern "C" int lnst_conv_first_bwd(const void* g, const float* wd, float* gx, in
   return lnst_status();
 }
 
+// developer probe: x bf16 [180,64] (18 x 10 patch rows), b bf16 [16,64], out fp32 [128,16]
+extern "C" int lnst_umma_probe(const void* x, const void* b, float* out, int32_t pitched, int32_t ky, int32_t kx,
+                               int32_t base_mode, void* stream) {
+  using namespace tc;
+  CUtensorMap md, mr, mb;
+  const cuuint64_t dx[2] = {64, 180}, sx[1] = {128};
+  const cuuint32_t bd[2] = {64, 180}, br[2] = {64, 10}, bb[2] = {64, 16};
+  const cuuint64_t db[2] = {64, 16};
+  if (!make_map(&md, x, 2, dx, sx, bd) || !make_map(&mr, x, 2, dx, sx, br) || !make_map(&mb, b, 2, db, sx, bb))
+    return LNST_EARG;
+  const int smem = 44 * 1024 + 1024;
+  cudaFuncSetAttribute(umma_probe_k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  umma_probe_k<<<1, 128, smem, lnst_stream(stream)>>>(md, mr, mb, out, pitched, ky, kx, base_mode);
+  return lnst_status();
+}
+
+extern "C" int lnst_set_conv_halo(int32_t on) { tc::conv_halo = on; return LNST_OK; }   // 2 = also with streamed weights
+
+// Data gradient of conv1_1 on tensor cores: g bf16 [n,H,W,64] (x) wd16 bf16 [9,16,64] (rows 0..2 = the three
+// input channels, rows 3..15 zero) -> gx fp32 [n,H,W,3].
+extern "C" int lnst_conv_first_bwd_tc(const void* g, const void* wd16, float* gx, int32_t n, int32_t H, int32_t W,
+                                      void* stream) {
+  if (!g || !wd16 || !gx || n < 1 || H < 1 || W < 1) return LNST_EARG;
+  return tc::launch_halo<16, true>(g, wd16, nullptr, nullptr, nullptr, gx, n, H, W, 64, 16, 0, 1.0f,
+                                   lnst_stream(stream));
+}
+
 extern "C" int lnst_set_conv_persistent(int32_t on) { tc::conv_persistent = on ? 1 : 0; return LNST_OK; }
 
 extern "C" int lnst_tc_supported(void) { return tc::encode_fn() != nullptr ? 1 : 0; }
@@ -948,6 +1401,18 @@ static int run_tc_gemm(const void* x, const void* wmat, const float* bias, const
   using namespace tc;
   if (!x || !wmat || !y || n < 1 || H < 1 || W < 1 || Cin < 64 || Cout < 64 || Cin % 64 || Cout % 64)
     return LNST_EARG;
+  // The halo'd-patch kernel wins when the layer's weights stay resident in shared memory (9*Cin*Cout*2 B
+  // beside >= 3 patch stages: conv1_2, conv2_1 and their data gradients); with streamed weights the
+  // per-tap kernels are faster (measured, tools/convbench.py), so those layers keep them.
+  const int bn_ = (Cout % 128 == 0) ? 128 : 64;
+  const bool resident = (Cout == bn_) && (9 * (Cin / 64) * bn_ * 128 + 3 * PATCH_STRIDE <= 232448 - 2048 - 1024 - 512);
+  if (taps == 9 && !w_img && !addend && conv_halo && (resident || conv_halo == 2)) {
+    if (Cout % 128 == 0)
+      return launch_halo<128, false>(x, wmat, bias, (const __nv_bfloat16*)mask, (__nv_bfloat16*)y, nullptr, n, H, W,
+                                     Cin, Cout, relu, scale, lnst_stream(stream));
+    return launch_halo<64, false>(x, wmat, bias, (const __nv_bfloat16*)mask, (__nv_bfloat16*)y, nullptr, n, H, W, Cin,
+                                  Cout, relu, scale, lnst_stream(stream));
+  }
   ConvShape s;
   s.H = H; s.W = W; s.Cin = Cin; s.Cout = Cout; s.relu = relu;
   s.taps = taps; s.w_img = w_img; s.scale = scale;

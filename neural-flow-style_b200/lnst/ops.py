@@ -347,6 +347,14 @@ def conv_first_bwd(g, wd):
     return gx
 
 
+def conv_first_bwd_tc(g, wd16):
+    """data gradient of conv1_1 on tensor cores: g bf16 [n,H,W,64], wd16 bf16 [9,16,64] -> fp32 [n,H,W,3]."""
+    n, H, W, _ = g.shape
+    gx = torch.empty(n, H, W, 3, dtype=f32, device=g.device)
+    _lib.get().call('lnst_conv_first_bwd_tc', ptr(g), ptr(wd16), ptr(gx), n, H, W, _s(g))
+    return gx
+
+
 def avgpool2_bf16_fwd(x):
     n, H, W, ch = x.shape
     y = torch.empty(n, H // 2, W // 2, ch, dtype=bf16, device=x.device)

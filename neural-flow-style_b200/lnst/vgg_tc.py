@@ -18,10 +18,16 @@ class TensorCoreConvs:
     def __init__(self, net):
         self.net = net
         self.wp, self.wdp = {}, {}
+        self.first_bwd_tc = True
         for name, w in net.w.items():
             if w.shape[2] % 64 == 0 and w.shape[3] % 64 == 0:
                 self.wp[name] = _pack(w)
                 self.wdp[name] = _pack(net.wd[name])
+            elif tuple(w.shape[2:]) == (3, 64):
+                # conv1_1's data gradient (64 -> 3) as a 64 -> 16 tensor-core convolution: rows 3..15 zero
+                wd16 = torch.zeros(9, 16, 64, dtype=torch.bfloat16, device=w.device)
+                wd16[:, :3] = _pack(net.wd[name])
+                self.wd16 = wd16.contiguous()
 
     # ---- network ----------------------------------------------------------------------------------
     def forward(self, x, layers):
@@ -56,7 +62,7 @@ class TensorCoreConvs:
                 if name in self.wdp and prev is not None:
                     g = ops.conv3x3_bf16_tc(g, self.wdp[name], None, relu=False, mask=mask)
                 elif prev is None and tuple(self.net.w[name].shape[2:]) == (3, 64):
-                    g = ops.conv_first_bwd(g, self.net.wd[name])
+                    g = ops.conv_first_bwd_tc(g, self.wd16) if self.first_bwd_tc else ops.conv_first_bwd(g, self.net.wd[name])
                 else:
                     g = ops.conv3x3_mixed(g, self.net.wd[name], None, relu=False, out_bf16=(prev is not None), mask=mask)
             else:

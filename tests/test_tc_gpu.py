@@ -62,6 +62,32 @@ def test_conv3x3_tc_matches_fp32_reference(n, H, W, cin, cout):
     assert err2 <= 2 ** -7 * want2.abs().max().item(), err2
 
 
+@pytest.mark.parametrize('n,h,w,cin,cout', [(2, 37, 29, 64, 64), (1, 50, 50, 128, 256), (3, 16, 8, 64, 128),
+                                            (1, 100, 100, 128, 128), (2, 25, 25, 256, 128)])
+def test_halo_kernel_equals_per_tap_kernel(n, h, w, cin, cout):
+    """3x3 convolution through one halo'd patch per tile (taps via descriptor offsets; weights resident or
+    streamed depending on the layer) against the one-TMA-tile-per-tap kernel: same bf16 output."""
+    from lnst import _lib
+    dev = torch.device('cuda:0')
+    g = torch.Generator().manual_seed(n * 1000 + h + cin)
+    x = torch.randn(n, h, w, cin, generator=g).to(torch.bfloat16).to(dev)
+    wp = (torch.randn(9, cout, cin, generator=g) / (3 * cin ** 0.5)).to(torch.bfloat16).to(dev)
+    b = torch.randn(cout, generator=g).to(dev)
+    mask = torch.randn(n, h, w, cout, generator=g).to(torch.bfloat16).to(dev)
+    lib = _lib.get()
+    outs = []
+    for halo in (0, 2):                      # 2: the halo kernel for every layer (resident or streamed weights)
+        lib.call('lnst_set_conv_halo', halo)
+        try:
+            outs.append((ops.conv3x3_bf16_tc(x, wp, b, relu=True).float().cpu(),
+                         ops.conv3x3_bf16_tc(x, wp, None, relu=False, mask=mask).float().cpu()))
+        finally:
+            lib.call('lnst_set_conv_halo', 1)
+    for a, c in zip(outs[0], outs[1]):
+        assert (a - c).abs().max() <= 2 ** -7 * a.abs().max()
+        assert (a - c).abs().mean() <= 1e-3 * a.abs().mean()
+
+
 def test_edge_layers_pool_and_conversions():
     dev = torch.device('cuda:0')
     g = torch.Generator().manual_seed(5)
@@ -83,6 +109,12 @@ def test_edge_layers_pool_and_conversions():
     gx1 = ops.conv_first_bwd(gy.to(dev), wd.to(dev))
     want = ref_conv(gy.float(), wd, None, False)
     assert (gx1.cpu() - want).abs().max() <= 1e-4 * want.abs().max()
+    # the same data gradient as a 64 -> 16 tensor-core convolution (halo'd-patch kernel, fp32 [.,3] epilogue)
+    wd16 = torch.zeros(9, 16, 64, dtype=torch.bfloat16)
+    wd16[:, :3] = wd.permute(0, 1, 3, 2).reshape(9, 3, 64).to(torch.bfloat16)
+    gx2 = ops.conv_first_bwd_tc(gy.to(dev), wd16.to(dev))
+    want16 = ref_conv(gy.float(), wd.to(torch.bfloat16).float(), None, False)
+    assert (gx2.cpu() - want16).abs().max() <= 1e-3 * want16.abs().max()
     a = torch.randn(2, 9, 12, 64, generator=g).to(torch.bfloat16)
     p = ops.avgpool2_bf16_fwd(a.to(dev))
     wantp = torch.nn.functional.avg_pool2d(a.float().permute(0, 3, 1, 2), 2, 2).permute(0, 2, 3, 1)

@@ -109,9 +109,11 @@ def main():
     def lossnet():
         l = torch.zeros(nv, device=dev)
         return st.image_loss_and_grad(x, d_img, grams, l)
-    lib.call('lnst_set_conv_persistent', 0)
-    add('lossnet fwd+bwd (tile-per-CTA convs)', lossnet, 0)
-    lib.call('lnst_set_conv_persistent', 1)
+    lib.call('lnst_set_conv_halo', 0)
+    st.net.tc.first_bwd_tc = False
+    add('lossnet fwd+bwd (per-tap convs)', lossnet, 0)
+    lib.call('lnst_set_conv_halo', 1)
+    st.net.tc.first_bwd_tc = True
     add('lossnet fwd+bwd (all views)', lossnet, 0)
     add('zero g_ds', lambda: ops.fill_box(g_ds, box, 0.0), 4 * Vb)
     print(json.dumps(out))
