@@ -222,6 +222,10 @@ int lnst_gram_bwd(const float* F, const float* G, int64_t P, int32_t C, float co
  * g_F = beta*g_F + weight * dL/dF [* (F > 0) when relu_mask]; g_F may be NULL. */
 int lnst_content_loss(const float* F, int64_t P, int32_t C, int32_t channel, float weight, float* loss,
                       float* g_F, float beta, int32_t relu_mask, void* stream);
+/* Content loss against a target image's feature (styler_base.py:137-141): loss += weight *
+ * mean((F - target*amp)^2) over the n_el elements; g_F = beta*g_F + weight * d/dF [* (F > 0)]. */
+int lnst_content_mse(const float* F, const float* target, int64_t n_el, float amp, float weight, float* loss,
+                     float* g_F, float beta, int32_t relu_mask, void* stream);
 /* anisotropic L1 total variation of d_img [H,W,C]; g_img overwritten with weight * d tv. */
 int lnst_tv_loss(const float* d_img, int32_t H, int32_t W, int32_t C, float weight, float* loss,
                  float* g_img, void* stream);

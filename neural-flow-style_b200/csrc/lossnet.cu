@@ -81,6 +81,23 @@ __global__ void content_loss_k(const float* __restrict__ F, int64_t P, int C, in
   if (loss && (threadIdx.x & 31) == 0) atomicAdd(loss, weight * s);
 }
 
+// styler_base.py:137-141: mean((f - target*amp)^2) over the feature map (content target image)
+__global__ void content_mse_k(const float* __restrict__ F, const float* __restrict__ T, int64_t total, float amp,
+                              float weight, float* __restrict__ loss, float* __restrict__ gF, float beta,
+                              int relu_mask) {
+  float s = 0.f;
+  const float inv = 1.f / (float)total;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const float f = F[t];
+    const float d = f - T[t] * amp;
+    s += d * d * inv;
+    if (gF) gF[t] = (beta != 0.f ? beta * gF[t] : 0.f) + ((!relu_mask || f > 0.f) ? weight * 2.f * d * inv : 0.f);
+  }
+  s = lnst_warp_sum(s);
+  if (loss && (threadIdx.x & 31) == 0) atomicAdd(loss, weight * s);
+}
+
 // tf.image.total_variation on one image [H,W,C]
 __global__ void tv_loss_k(const float* __restrict__ d, int H, int W, int C, float weight,
                           float* __restrict__ loss, float* __restrict__ g) {
@@ -167,6 +184,15 @@ extern "C" int lnst_content_loss(const float* F, int64_t P, int32_t C, int32_t c
   const unsigned nb = lnst_blocks(P * C, 256) > 296 ? 296 : lnst_blocks(P * C, 256);
   LNST_LAUNCH(content_loss_k, dim3(nb), dim3(256), 0, lnst_stream(stream), F, P, (int)C, (int)channel, weight,
               loss, g_F, beta, (int)relu_mask);
+  return lnst_status();
+}
+
+extern "C" int lnst_content_mse(const float* F, const float* target, int64_t n_el, float amp, float weight,
+                                float* loss, float* g_F, float beta, int32_t relu_mask, void* stream) {
+  if (!F || !target || n_el < 1) return LNST_EARG;
+  const unsigned nb = lnst_blocks(n_el, 256) > 296 ? 296 : lnst_blocks(n_el, 256);
+  LNST_LAUNCH(content_mse_k, dim3(nb), dim3(256), 0, lnst_stream(stream), F, target, n_el, amp, weight, loss, g_F,
+              beta, (int)relu_mask);
   return lnst_status();
 }
 

@@ -66,6 +66,7 @@ SIGNATURES = {
     'lnst_gram_diff': [vp, i64, i32, f32, vp, f32, vp, vp, vp],
     'lnst_gram_bwd': [vp, vp, i64, i32, f32, f32, i32, vp, vp],
     'lnst_content_loss': [vp, i64, i32, i32, f32, vp, vp, f32, i32, vp],
+    'lnst_content_mse': [vp, vp, i64, f32, f32, vp, vp, f32, i32, vp],
     'lnst_tv_loss': [vp, i32, i32, i32, f32, vp, vp, vp],
     'lnst_adam_step': [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, vp],
     'lnst_adam_step_dev': [vp, vp, vp, vp, i64, vp, f32, f32, f32, f32, f32, vp],

@@ -221,6 +221,12 @@ def content_loss(F, channel, weight, loss, g_F, beta, relu_mask):
                     int(relu_mask), _s(F))
 
 
+def content_mse(F, target, amp, weight, loss, g_F, beta, relu_mask):
+    """loss += weight*mean((F - target*amp)^2); g_F = beta*g_F + weight*grad [* (F>0)]."""
+    _lib.get().call('lnst_content_mse', ptr(F), ptr(target), F.numel(), float(amp), float(weight), ptr(loss), ptr(g_F),
+                    float(beta), int(relu_mask), _s(F))
+
+
 def tv_loss(d_img, weight, loss, g_img):
     H, W, ch = d_img.shape
     _lib.get().call('lnst_tv_loss', ptr(d_img), H, W, ch, float(weight), ptr(loss), ptr(g_img), _s(d_img))

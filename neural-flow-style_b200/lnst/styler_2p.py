@@ -96,6 +96,9 @@ class Styler(StylerBase):
             style_grams = None
             if self.w_style and self.style_img is not None:
                 style_grams = self._style_feature(self.style_img, res)
+            self._content_feat = None
+            if self.w_content and self.content_img is not None:
+                self._content_feat = self._content_feature(self.content_img, res)
             lr = self.lr[octave] if isinstance(self.lr, list) else self.lr
             loss_o, intm_o = [], []
             for step in range(self.iter):

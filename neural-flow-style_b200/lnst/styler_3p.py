@@ -430,6 +430,9 @@ class Styler(StylerBase):
             style_grams = None
             if self.w_style and self.style_img is not None:        # :281-286
                 style_grams = self._style_feature(self.style_img, res[1:])
+            self._content_feat = None
+            if self.w_content and self.content_img is not None:    # :276-279
+                self._content_feat = self._content_feature(self.content_img, res[1:])
             lr = lr_list[octave] if lr_list is not None else (self.lr[octave] if isinstance(self.lr, list) else self.lr)
             loss_o, intm_o = {t: [] for t in mine}, {}
             runners = {}

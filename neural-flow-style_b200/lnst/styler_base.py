@@ -43,6 +43,7 @@ class StylerBase(object):
         self.net = LossNet(weights, model_name(self.network), self.device, math=self.conv_math)
         self.content_img = None
         self.style_img = None
+        self._content_feat = None              # set per octave by run() when a content target image is given
         self.rank, self.world = 0, 1
         if torch.distributed.is_available() and torch.distributed.is_initialized():
             self.rank, self.world = torch.distributed.get_rank(), torch.distributed.get_world_size()
@@ -114,8 +115,11 @@ class StylerBase(object):
         return h * w
 
     def _content_feature(self, content_target, content_shp):
-        raise NotImplementedError('content target images (styler_base.py:233-247) are not built yet; '
-                                  'the channel-activation content loss (:143-148) is')
+        """Feature of the content target at ``content_layer`` (styler_base.py:233-247): fp32 [h,w,C] on the
+        device; ``image_loss_and_grad`` compares every view's feature with it."""
+        x = self._target_tensor(content_target, content_shp)
+        acts = self.net.forward(x, [self.content_layer])
+        return self.net.features_f32(acts, self.content_layer)[0].contiguous()
 
     # ---- feature-space losses + their gradient w.r.t. the net input ---------------------------------
     def image_loss_and_grad(self, x, d_img, style_grams, loss):
@@ -143,7 +147,8 @@ class StylerBase(object):
                     coef = self.w_style * self.w_style_layer[li] * 4.0 / (2.0 * P * ch)
                     g = self.net.gram_grad(acts, name, handles[l], coef, g, is_conv)
             if self.w_content and self.content_layer == name:
-                g = self.net.content(acts, name, self.content_channel, self.w_content, loss, g, is_conv)
+                g = self.net.content(acts, name, self.content_channel, self.w_content, loss, g, is_conv,
+                                     target=getattr(self, '_content_feat', None), amp=self.w_content_amp)
             return g
 
         g_x = self.net.backward(x, acts, wanted, add_loss_grad, set(wanted)) if wanted else None

@@ -165,15 +165,20 @@ class LossNet:
             ops.gram_bwd(f[v].reshape(P, ch), handle[v], coef, beta, relu_mask, g[v].reshape(P, ch))
         return g
 
-    def content(self, acts, name, channel, weight, loss, g, relu_mask):
-        """Channel-activation content loss (styler_base.py:143-148) on end point ``name``."""
+    def content(self, acts, name, channel, weight, loss, g, relu_mask, target=None, amp=1.0):
+        """Content loss on end point ``name``: channel activation (styler_base.py:143-148), or, with
+        ``target`` (the content image's feature, fp32 [h,w,C]), mean((f - target*amp)^2) (:137-141)."""
         if self.math == 'bf16':
-            return self.tc.content(acts, name, channel, weight, loss, g, relu_mask)
+            return self.tc.content(acts, name, channel, weight, loss, g, relu_mask, target, amp)
         f = acts[name]
         n, P, ch = f.shape[0], f.shape[1] * f.shape[2], f.shape[3]
         beta = 1.0
         if g is None:
             g, beta = torch.empty_like(f), 0.0
         for v in range(n):
-            ops.content_loss(f[v].reshape(P, ch), channel, weight, loss[v:v + 1], g[v].reshape(P, ch), beta, relu_mask)
+            if target is not None:
+                ops.content_mse(f[v], target, amp, weight, loss[v:v + 1], g[v], beta, relu_mask)
+            else:
+                ops.content_loss(f[v].reshape(P, ch), channel, weight, loss[v:v + 1], g[v].reshape(P, ch), beta,
+                                 relu_mask)
         return g

@@ -80,13 +80,17 @@ class TensorCoreConvs:
     def gram_grad(self, acts, name, handle, coef, g, relu_mask):
         return ops.gram_bwd_bf16_tc(acts.raw[name], handle[1], coef, g, relu_mask, g)
 
-    def content(self, acts, name, channel, weight, loss, g, relu_mask):
+    def content(self, acts, name, channel, weight, loss, g, relu_mask, target=None, amp=1.0):
         f = acts[name]                                          # fp32 copy
         n, P, ch = f.shape[0], f.shape[1] * f.shape[2], f.shape[3]
         g32 = ops.to_f32(g) if g is not None else torch.empty_like(f)
+        beta = 1.0 if g is not None else 0.0
         for v in range(n):
-            ops.content_loss(f[v].reshape(P, ch), channel, weight, loss[v:v + 1], g32[v].reshape(P, ch),
-                             1.0 if g is not None else 0.0, relu_mask)
+            if target is not None:
+                ops.content_mse(f[v], target, amp, weight, loss[v:v + 1], g32[v], beta, relu_mask)
+            else:
+                ops.content_loss(f[v].reshape(P, ch), channel, weight, loss[v:v + 1], g32[v].reshape(P, ch), beta,
+                                 relu_mask)
         return ops.to_bf16(g32)
 
 

@@ -106,3 +106,22 @@ def test_multi_frame_temporal_smoothing(dev):
     out_ref = ref.run(params, style_targets=[sty])
     check_run(out_new, out_ref)
     assert out_new['d'].shape[0] == 4
+
+
+def test_content_target_image_and_style(dev):
+    """Content loss against a target IMAGE's feature (styler_base.py:137-141, 233-247) together with the
+    style loss, single view, density mode."""
+    res = 12
+    kw = dict(res=res, iter=3, rotate=False, conv_math='fp32', w_content=0.7, w_content_amp=1.5,
+              content_layer='conv2_1', style_layer=['conv1_2'], w_style_layer=[1.0])
+    params = scene(res, 900)
+    sty = synth.style_image(res, res)
+    con = synth.style_image(res, res, seed=11)
+    new = Styler(smoke_cfg(**kw), weights=synth.vgg_weights())
+    new.style_img, new.content_img = sty, con
+    out_new = new.run(params)
+    ref = Oracle3P(smoke_cfg(**kw), oracle.vgg.synthetic_weights())
+    out_ref = ref.run(params, style_targets=[sty], content_targets=[con])
+    check_run(out_new, out_ref)
+    off = Oracle3P(smoke_cfg(**dict(kw, w_content=0)), oracle.vgg.synthetic_weights()).run(params, style_targets=[sty])
+    assert abs(off['l'][0][0] - out_ref['l'][0][0]) > 1e-3 * abs(out_ref['l'][0][0])   # the content term matters
