@@ -142,6 +142,10 @@ int lnst_resize_bilinear_fwd(const float* in, int32_t n_img, int32_t H, int32_t 
                              int32_t OH, int32_t OW, float* out, void* stream);
 int lnst_resize_bilinear_bwd(const float* g_out, int32_t n_img, int32_t H, int32_t W, int32_t C,
                              int32_t OH, int32_t OW, float* g_in, void* stream);
+/* tf.compat.v1.image.resize(BICUBIC) with legacy coordinates (Keys a = -0.75, clamped taps): the style
+ * mask of styler_base.py:165-169.  in [n,H,W,C] -> out [n,OH,OW,C]. */
+int lnst_resize_bicubic_fwd(const float* in, int32_t n_img, int32_t H, int32_t W, int32_t C, int32_t OH,
+                            int32_t OW, float* out, void* stream);
 /* d_img[v,p,c] = s*gray[v,p,(c)] (gray has Cg = 1 or 3 channels), x = d_img - mean_rgb. */
 int lnst_to_net_input_fwd(const float* gray, int32_t n_img, int64_t n_pix, int32_t Cg, float s,
                           float* d_img, float* x, void* stream);
@@ -244,6 +248,10 @@ int lnst_iterate_accumulate(float* acc, const float* var, int64_t n, int32_t fir
 /* delta[i] = (nan_to_num(g_new[i]*scale) - g_opt[i]) * (mask ? mask[(i/width)*mask_stride] : 1) */
 int lnst_iterate_delta(const float* g_new, float scale, const float* g_opt, const float* mask,
                        int32_t width, int32_t mask_stride, int64_t n, float* delta, void* stream);
+/* g[i,c] = beta*g[i,c] + t[i,c]*m[i] [* (f[i,c] > 0)]: gradient of a masked Gram loss back onto the
+ * unmasked feature (styler_base.py:167). */
+int lnst_masked_accumulate(const float* t, const float* m, const float* f, int32_t relu, int32_t C, float beta,
+                           float* g, int64_t n, void* stream);
 /* scipy.ndimage.gaussian_filter along the first axis of x [T,M] (mode reflect, truncate 4). */
 int lnst_temporal_gauss(const float* x, float* y, int32_t T, int64_t M, float sigma, void* stream);
 /* y += a*x */

@@ -85,6 +85,17 @@ __global__ void mul_bcast_k(const float* __restrict__ a, const float* __restrict
   if (i < n) out[i] = a[i] * b[i / C];
 }
 
+// g[i*C+c] = beta*g + t[i*C+c] * m[i] [* (f > 0)]: the masked-Gram gradient back onto the unmasked feature
+__global__ void masked_accumulate_k(const float* __restrict__ t, const float* __restrict__ m,
+                                    const float* __restrict__ f, int relu, int C, float beta, float* __restrict__ g,
+                                    int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float v = t[i] * m[i / C];
+  if (relu && !(f[i] > 0.f)) v = 0.f;
+  g[i] = (beta != 0.f ? beta * g[i] : 0.f) + v;
+}
+
 // 1-D Gaussian along axis 0 of x [T,M]; scipy 'reflect' boundary (d c b a | a b c d | d c b a)
 #define LNST_MAX_GAUSS_RADIUS 64
 struct GaussTaps { int radius; float w[LNST_MAX_GAUSS_RADIUS + 1]; };
@@ -203,6 +214,15 @@ extern "C" int lnst_mul_bcast(const float* a, const float* b, int32_t C, float* 
   if (!a || !b || !out || n < 0 || C < 1) return LNST_EARG;
   if (n == 0) return LNST_OK;
   LNST_LAUNCH(mul_bcast_k, dim3(lnst_blocks(n, 256)), dim3(256), 0, lnst_stream(stream), a, b, (int)C, out, n);
+  return lnst_status();
+}
+
+extern "C" int lnst_masked_accumulate(const float* t, const float* m, const float* f, int32_t relu, int32_t C,
+                                      float beta, float* g, int64_t n, void* stream) {
+  if (!t || !m || !g || (relu && !f) || n < 0 || C < 1) return LNST_EARG;
+  if (n == 0) return LNST_OK;
+  LNST_LAUNCH(masked_accumulate_k, dim3(lnst_blocks(n, 256)), dim3(256), 0, lnst_stream(stream), t, m, f, (int)relu,
+              (int)C, beta, g, n);
   return lnst_status();
 }
 

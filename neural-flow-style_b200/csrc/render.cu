@@ -513,6 +513,45 @@ __global__ void resize_bwd_k(const float* __restrict__ g_out, int H, int W, int 
   atomicAdd(b + ((int64_t)y1 * W + x1) * C + c, g * ly * lx);
 }
 
+// tf.compat.v1.image.resize(BICUBIC), align_corners=False, legacy coordinates src = dst*in/out, Keys kernel
+// a = -0.75, taps clamped to the image (styler_base.py:166: the style mask).  Closed-form weights (TF reads
+// them from a 1024-entry table; the difference is below fp32 noise of the loss -- DESIGN.md section 5).
+__device__ __forceinline__ float keys_w(float t) {
+  const float a = -0.75f;
+  t = fabsf(t);
+  if (t <= 1.f) return ((a + 2.f) * t - (a + 3.f)) * t * t + 1.f;
+  if (t < 2.f) return ((a * t - 5.f * a) * t + 8.f * a) * t - 4.f * a;
+  return 0.f;
+}
+__global__ void resize_bicubic_fwd_k(const float* __restrict__ in, int H, int W, int C, int OH, int OW, float sy,
+                                     float sx, float* __restrict__ out) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = (int64_t)OH * OW * C;
+  if (t >= total) return;
+  const int img = blockIdx.y;
+  const int c = (int)(t % C), ox = (int)((t / C) % OW), oy = (int)(t / ((int64_t)C * OW));
+  const float fy = (float)oy * sy, fx = (float)ox * sx;
+  const float by = floorf(fy), bx = floorf(fx);
+  const float* b = in + (int64_t)img * H * W * C;
+  // rows first, then columns: the summation order of the separable restatement
+  float colv[4];
+#pragma unroll
+  for (int kx = 0; kx < 4; ++kx) colv[kx] = 0.f;
+  float acc = 0.f;
+#pragma unroll
+  for (int kx = 0; kx < 4; ++kx) {
+    const int xx = min(max((int)bx + kx - 1, 0), W - 1);
+    float r = 0.f;
+#pragma unroll
+    for (int ky = 0; ky < 4; ++ky) {
+      const int yy = min(max((int)by + ky - 1, 0), H - 1);
+      r += b[((int64_t)yy * W + xx) * C + c] * keys_w(fy - (by + (float)(ky - 1)));
+    }
+    acc += r * keys_w(fx - (bx + (float)(kx - 1)));
+  }
+  out[(int64_t)img * total + t] = acc;
+}
+
 __constant__ float kMeanRGB[3] = {(float)(0.485 * 255), (float)(0.456 * 255), (float)(0.406 * 255)};   // vgg.py:16-18
 
 __global__ void to_net_input_fwd_k(const float* __restrict__ gray, int64_t total_pix, int Cg, float s,
@@ -653,6 +692,15 @@ extern "C" int lnst_resize_bilinear_bwd(const float* g_out, int32_t n_img, int32
   cudaMemsetAsync(g_in, 0, sizeof(float) * (int64_t)n_img * H * W * C, lnst_stream(stream));
   LNST_LAUNCH(resize_bwd_k, dim3(lnst_blocks((int64_t)OH * OW * C, 256), n_img), dim3(256), 0,
               lnst_stream(stream), g_out, (int)H, (int)W, (int)C, (int)OH, (int)OW, sy, sx, g_in);
+  return lnst_status();
+}
+
+extern "C" int lnst_resize_bicubic_fwd(const float* in, int32_t n_img, int32_t H, int32_t W, int32_t C, int32_t OH,
+                                       int32_t OW, float* out, void* stream) {
+  if (!in || !out || n_img < 1 || H < 1 || W < 1 || C < 1 || OH < 1 || OW < 1) return LNST_EARG;
+  const float sy = (float)H / (float)OH, sx = (float)W / (float)OW;
+  LNST_LAUNCH(resize_bicubic_fwd_k, dim3(lnst_blocks((int64_t)OH * OW * C, 256), n_img), dim3(256), 0,
+              lnst_stream(stream), in, (int)H, (int)W, (int)C, (int)OH, (int)OW, sy, sx, out);
   return lnst_status();
 }
 

@@ -58,6 +58,7 @@ SIGNATURES = {
     'lnst_normalize_bwd': [vp, vp, vp, i32, i64, vp, vp, vp],
     'lnst_resize_bilinear_fwd': [vp, i32, i32, i32, i32, i32, i32, vp, vp],
     'lnst_resize_bilinear_bwd': [vp, i32, i32, i32, i32, i32, i32, vp, vp],
+    'lnst_resize_bicubic_fwd': [vp, i32, i32, i32, i32, i32, i32, vp, vp],
     'lnst_to_net_input_fwd': [vp, i32, i64, i32, f32, vp, vp, vp],
     'lnst_to_net_input_bwd': [vp, i32, i64, i32, f32, vp, vp],
     'lnst_conv3x3_f32': [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp],
@@ -72,6 +73,7 @@ SIGNATURES = {
     'lnst_adam_step_dev': [vp, vp, vp, vp, i64, vp, f32, f32, f32, f32, f32, vp],
     'lnst_iterate_accumulate': [vp, vp, i64, i32, vp],
     'lnst_iterate_delta': [vp, f32, vp, vp, i32, i32, i64, vp, vp],
+    'lnst_masked_accumulate': [vp, vp, vp, i32, i32, f32, vp, i64, vp],
     'lnst_temporal_gauss': [vp, vp, i32, i64, f32, vp],
     'lnst_axpy': [vp, vp, f32, i64, vp],
     'lnst_clip_fwd': [vp, f32, f32, vp, i64, vp],

@@ -160,6 +160,20 @@ def resize_bilinear_bwd(g_out, H, W):
     return g_in
 
 
+def resize_bicubic_fwd(x, oh, ow):
+    n, H, W, ch = x.shape
+    out = torch.empty(n, oh, ow, ch, dtype=f32, device=x.device)
+    _lib.get().call('lnst_resize_bicubic_fwd', ptr(x), n, H, W, ch, oh, ow, ptr(out), _s(x))
+    return out
+
+
+def masked_accumulate(t, m, f, relu, g, beta):
+    """g = beta*g + t * m[..., None] [* (f > 0)]"""
+    _lib.get().call('lnst_masked_accumulate', ptr(t), ptr(m), ptr(f), int(relu), t.shape[-1], float(beta), ptr(g),
+                    t.numel(), _s(t))
+    return g
+
+
 def to_net_input_fwd(gray, s, d_img, x):
     """gray [n,H,W,Cg] -> d_img, x [n,H,W,3]"""
     n = gray.shape[0]

@@ -18,8 +18,10 @@ from .vgg import _R_MEAN, _G_MEAN, _B_MEAN
 class Styler(StylerBase):
     def __init__(self, self_dict, weights=None, device=None):
         StylerBase.__init__(self, self_dict, weights=weights, device=device)
-        if self.style_mask:
-            raise NotImplementedError('style_mask (styler_base.py:165-173) is not built yet')
+        if self.style_mask and self.style_mask_on_ref:
+            raise NotImplementedError('style_mask_on_ref (styler_base.py:171-173) is not built')
+        if self.style_mask and self.conv_math != 'fp32':
+            raise NotImplementedError("style_mask needs conv_math='fp32' (the masked Gram runs on the fp32 path)")
 
     # ---- graph pieces ----------------------------------------------------------------------------
     def _grid(self, res):
@@ -56,7 +58,15 @@ class Styler(StylerBase):
     def loss_and_grad(self, fr, var, res, style_grams):
         st = self._forward(fr, var, res)
         loss = torch.zeros(1, dtype=f32, device=self.device)
-        g_x = self.image_loss_and_grad(st['x'], st['d_img'], style_grams, loss)
+        masks = None
+        if self.style_mask and style_grams is not None:           # styler_base.py:165-169, test_dambreak2d.py:189
+            key = (fr['id'], tuple(res), 'mask')
+            if key not in self._cache:                             # d_gray is constant per (frame, octave)
+                H_, W_ = res
+                self._cache[key] = self.style_masks_for(self._gray(fr, res).reshape(1, H_, W_),
+                                                        (st['x'].shape[1], st['x'].shape[2]))
+            masks = self._cache[key]
+        g_x = self.image_loss_and_grad(st['x'], st['d_img'], style_grams, loss, style_masks=masks)
         H, W = st['hw']
         g_d3 = ops.to_net_input_bwd(g_x, 3, 255.0, torch.empty(1, g_x.shape[1], g_x.shape[2], 3, dtype=f32,
                                                                 device=self.device))

@@ -76,7 +76,8 @@ class Styler(StylerBase):
         if 'd' in self.target_field and self.num_kernels > 4:
             raise NotImplementedError('num_kernels > 4')
         if self.style_mask:
-            raise NotImplementedError('style_mask (styler_base.py:165-173) is not built yet')
+            raise NotImplementedError('style_mask in the 3-D styler (the mask depends on the optimised density: '
+                                      'styler_base.py:165-169) is not built; the 2-D colour styler has it')
         self.rot_mat_, self.views = None, None
         if self.rotate:                                            # styler_3p.py:137-145
             self.rot_mat_, self.views = rot_mat(self.phi0, self.phi1, self.phi_unit, self.theta0, self.theta1,

@@ -122,7 +122,22 @@ class StylerBase(object):
         return self.net.features_f32(acts, self.content_layer)[0].contiguous()
 
     # ---- feature-space losses + their gradient w.r.t. the net input ---------------------------------
-    def image_loss_and_grad(self, x, d_img, style_grams, loss):
+    def style_masks_for(self, d_gray, net_hw):
+        """Per style layer: (m [n,h,w], area [n]) with m = d_gray resized to the layer's feature size by
+        TF's legacy bicubic (styler_base.py:165-169).  d_gray [n,H,W] must not depend on the optimised
+        variable (2-D colour mode); the areas are read back once, here."""
+        out = {}
+        for l in self.style_layer:
+            h, w = net_hw
+            block = int(l[4]) if l.startswith('conv') else int(l[4]) + 1
+            for _ in range(block - 1):
+                h, w = h // 2, w // 2
+            m = ops.resize_bicubic_fwd(d_gray.reshape(d_gray.shape[0], d_gray.shape[1], d_gray.shape[2], 1).contiguous(),
+                                       h, w)[..., 0].contiguous()
+            out[l] = (m, [float(a) for a in m.sum(dim=(1, 2)).cpu().tolist()])
+        return out
+
+    def image_loss_and_grad(self, x, d_img, style_grams, loss, style_masks=None):
         """x [n,H,W,3] net input (one image per view), d_img the same before mean subtraction.
         Adds each image's total feature/TV loss into ``loss[v]`` and returns d loss_v / d x_v
         stacked [n,H,W,3] (styler_base.py:127-213)."""
@@ -134,7 +149,8 @@ class StylerBase(object):
         handles = {}
         if style_on:
             for li, l in enumerate(self.style_layer):
-                handles[l] = self.net.gram(acts, l, style_grams[li], self.w_style * self.w_style_layer[li], loss)
+                handles[l] = self.net.gram(acts, l, style_grams[li], self.w_style * self.w_style_layer[li], loss,
+                                           mask=style_masks[l] if style_masks else None)
 
         def add_loss_grad(name, g):
             is_conv = 1 if name.startswith('conv') else 0

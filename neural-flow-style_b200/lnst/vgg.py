@@ -134,26 +134,38 @@ class LossNet:
     def features_f32(self, acts, name):
         return acts[name]            # fp32 in both back ends (the tensor-core store converts on demand)
 
-    def gram(self, acts, name, Gs, weight, loss):
-        """Per image v: G_v = F_v^T F_v/(2 h w C) - Gs; loss[v] += weight*sum(G_v^2).  Gs None: no
-        subtraction (style-target pass).  Returns a handle for ``gram_grad`` / ``gram_values``."""
+    def gram(self, acts, name, Gs, weight, loss, mask=None):
+        """Per image v: G_v = F_v^T F_v/den_v - Gs; loss[v] += weight*sum(G_v^2), den_v = 2 h w C.  Gs None:
+        no subtraction (style-target pass).  ``mask`` = (m [n,h,w] fp32, area [n] host floats): the masked
+        variant of styler_base.py:165-169 -- F_v is the feature times m, den_v = 2 area_v C; m is a constant
+        here (2-D colour mode: the density mask does not depend on the colours).  Returns a handle for
+        ``gram_grad`` / ``gram_values``."""
         if self.math == 'bf16':
+            if mask is not None:
+                raise NotImplementedError("style_mask needs conv_math='fp32'")
             return self.tc.gram(acts, name, Gs, weight, loss)
         f = acts[name]
         n, P, ch = f.shape[0], f.shape[1] * f.shape[2], f.shape[3]
-        out = []
+        out = {'G': [], 'den': [], 'Fm': [], 'mask': mask, 'weight': weight}
         for v in range(n):
             G = torch.empty(ch, ch, dtype=torch.float32, device=self.device)
-            ops.gram_diff(f[v].reshape(P, ch), 2.0 * P * ch, Gs, weight, G, loss[v:v + 1] if loss is not None else None)
-            out.append(G)
+            Fv, den = f[v].reshape(P, ch), 2.0 * P * ch
+            if mask is not None:
+                Fv = ops.mul_bcast(f[v], mask[0][v]).reshape(P, ch)
+                den = 2.0 * float(mask[1][v]) * ch
+            ops.gram_diff(Fv, den, Gs, weight, G, loss[v:v + 1] if loss is not None else None)
+            out['G'].append(G)
+            out['den'].append(den)
+            out['Fm'].append(Fv)
         return out
 
     def gram_values(self, handle):
         """fp32 [n,C,C] view of a ``gram`` handle."""
-        return handle[0] if self.math == 'bf16' else torch.stack(handle, 0)
+        return handle[0] if self.math == 'bf16' else torch.stack(handle['G'], 0)
 
     def gram_grad(self, acts, name, handle, coef, g, relu_mask):
-        """g <- (g + coef * F G) [* (F > 0)]; allocates g when None."""
+        """g <- (g + coef_v * F G) [* (F > 0)] with coef_v = 4 weight / den_v (``coef`` is that value for the
+        unmasked denominator; the fp32 handle carries its own); allocates g when None."""
         if self.math == 'bf16':
             return self.tc.gram_grad(acts, name, handle, coef, g, relu_mask)
         f = acts[name]
@@ -162,7 +174,13 @@ class LossNet:
         if g is None:
             g, beta = torch.empty_like(f), 0.0
         for v in range(n):
-            ops.gram_bwd(f[v].reshape(P, ch), handle[v], coef, beta, relu_mask, g[v].reshape(P, ch))
+            cv = 4.0 * handle['weight'] / handle['den'][v]
+            if handle['mask'] is None:
+                ops.gram_bwd(f[v].reshape(P, ch), handle['G'][v], cv, beta, relu_mask, g[v].reshape(P, ch))
+            else:
+                tmp = torch.empty(P, ch, dtype=torch.float32, device=self.device)
+                ops.gram_bwd(handle['Fm'][v], handle['G'][v], cv, 0.0, 0, tmp)
+                ops.masked_accumulate(tmp.reshape(f[v].shape), handle['mask'][0][v], f[v], relu_mask, g[v], beta)
         return g
 
     def content(self, acts, name, channel, weight, loss, g, relu_mask, target=None, amp=1.0):

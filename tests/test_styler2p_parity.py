@@ -56,3 +56,12 @@ def test_colour_mode_frames_octaves(dev):
     out_new, out_ref = run_pair(dict(octave_n=2, octave_scale=1.5, window_sigma=1.0, iter=2), nf=3)
     check(out_new, out_ref)
     assert len(out_new['d_intm']) == 1 and out_new['d_intm'][0].shape == out_ref['d_intm'][0].shape
+
+
+def test_colour_mode_style_mask(dev):
+    """The dambreak2d driver's setting (test_dambreak2d.py:189): Gram of the feature times the density mask
+    (bicubic-resized to the feature size), normalised by the mask area (styler_base.py:165-169)."""
+    out_new, out_ref = run_pair(dict(style_mask=True, style_layer=['conv1_1', 'conv2_1'], w_style_layer=[0.5, 0.5]))
+    check(out_new, out_ref)
+    plain, _ = run_pair(dict(style_mask=False, style_layer=['conv1_1', 'conv2_1'], w_style_layer=[0.5, 0.5]))
+    assert abs(plain['l'][0][0] - out_new['l'][0][0]) > 1e-3 * abs(plain['l'][0][0])      # the mask matters
