@@ -188,6 +188,11 @@ int lnst_conv_first_bwd(const void* g, const float* wd, float* gx, int32_t n, in
 /* Tuning switch (process-wide, default 1): 1 = persistent convolution kernel (one CTA per SM walks the
  * tile list, TMEM double-buffered), 0 = one CTA per tile. */
 int lnst_set_conv_persistent(int32_t on);
+/* Developer probe (tools/umma_probe.py): one M=128,N=16,K=64 MMA whose A operand is tap (ky,kx) of an 18x10
+ * pixel patch addressed only through the shared-memory descriptor; x bf16 [180,64], b bf16 [16,64], out
+ * fp32 [128,16]. */
+int lnst_umma_probe(const void* x, const void* b, float* out, int32_t pitched, int32_t ky, int32_t kx,
+                    int32_t base_mode, void* stream);
 /* Tuning switch (default 1): 1 = layers whose weights fit in shared memory load one halo'd patch per tile
  * and read the 9 taps through descriptor offsets; 2 = every layer does (weights streamed when they do not
  * fit); 0 = one TMA tile per tap everywhere. */
