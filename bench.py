@@ -70,7 +70,7 @@ def algorithmic_units(name, a, nk=2):
     if name in ('lnst_raymarch_fwd_box', 'lnst_raymarch_bwd_box'):
         nv, D, H, W = [v(x) for x in a[2:6]]
         V, P = box_cells(a[8], D * H * W), H * W
-        return (nv * (4 * V + 8 * P), 0) if 'fwd' in name else (nv * (8 * V + 8 * P), 0)
+        return (nv * (4 * V + 8 * P), 0) if 'fwd' in name else (nv * (8 * V + 8 * P), 0)   # box cells, not bricks
     if name in ('lnst_smooth3_relu_fwd_box', 'lnst_smooth3_relu_bwd_box'):
         fwd = 'fwd' in name
         D, H, W = [v(x) for x in (a[2:5] if fwd else a[3:6])]
@@ -263,22 +263,43 @@ def run_engine(args):
     calls = lib.launches - launches0
     loss_val = float(loss)
 
-    # ---- end-to-end: host buffers in, host result out, every step (the reference's sess.run boundary) --
+    # ---- end-to-end: host buffers in, host result out, every step (the reference's sess.run boundary:
+    # p, r fed and the variable initialised from the host every step, the variable and the loss read
+    # back, styler_3p.py:312,331,334).  p and r do not depend on the previous step, so their upload for
+    # step i+1 runs on a copy stream under step i (into staging buffers, then one device copy into the
+    # buffers the step's graph reads); the variable's round trip is sequential by construction.
     hp = fr['p'].cpu().pin_memory()                      # host copies in the engine's (cell-sorted) order
     hr = fr['r'].cpu().pin_memory()
     hg = g_opt.cpu().pin_memory()
     hl = torch.zeros(1).pin_memory()
+    sp, sr = torch.empty_like(fr['p']), torch.empty_like(fr['r'])
+    cs = torch.cuda.Stream(device=dev)
+    main = torch.cuda.current_stream(dev)
     e2e_steps = max(3, min(args.steps, 10))
     barrier()
     w0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        fr['p'].copy_(hp, non_blocking=True)
-        fr['r'].copy_(hr, non_blocking=True)
+    uploaded, consumed = torch.cuda.Event(), torch.cuda.Event()
+    with torch.cuda.stream(cs):
+        sp.copy_(hp, non_blocking=True)
+        sr.copy_(hr, non_blocking=True)
+        uploaded.record(cs)
+    for i in range(e2e_steps):
+        main.wait_event(uploaded)
+        fr['p'].copy_(sp, non_blocking=True)
+        fr['r'].copy_(sr, non_blocking=True)
+        consumed.record(main)
+        if i + 1 < e2e_steps:                            # next step's particle upload, under this step
+            with torch.cuda.stream(cs):
+                cs.wait_event(consumed)
+                sp.copy_(hp, non_blocking=True)
+                sr.copy_(hr, non_blocking=True)
+                uploaded.record(cs)
         g_opt.copy_(hg, non_blocking=True)
         l = step()
         hg.copy_(g_opt, non_blocking=True)
         hl.copy_(l.reshape(1), non_blocking=True)
-        torch.cuda.synchronize()
+        main.synchronize()
+    torch.cuda.synchronize()
     barrier()
     e2e_s = torch.tensor([time.perf_counter() - w0], device=dev)
     if world > 1:
@@ -370,7 +391,7 @@ def run_engine(args):
 
 
 # ---------------------------------------------------------------------------------------------
-def cpu_baseline(wl, budget_s=25.0, steps=1, warmup=0):
+def cpu_baseline(wl, budget_s=25.0, steps=None, warmup=0):
     """The oracle (CPU restatement of the reference's TF-1.15 graph) on this box's host cores.
     One sample = ONE view of one iteration at full size (forward + backward + Adam); the
     reference-exact iteration is n_views such passes (styler_3p.py:329-340)."""
@@ -379,6 +400,8 @@ def cpu_baseline(wl, budget_s=25.0, steps=1, warmup=0):
     from oracle.adam import TFAdam
     torch.set_num_threads(os.cpu_count() or 1)
     w = WORKLOADS[wl]
+    if steps is None:
+        steps = w['n_views']                      # one whole iteration, unless the time budget ends it earlier
     cfg = make_cfg(wl, 'sequential', 'fp32')
     p, r, sty = make_scene(wl)
     o = Oracle3P(cfg, oracle.vgg.synthetic_weights())
@@ -392,7 +415,8 @@ def cpu_baseline(wl, budget_s=25.0, steps=1, warmup=0):
     t_all = time.perf_counter()
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        _, gr = o.loss_and_grad([pt], [rt], [var], res, rot[:1] if rot is not None else None, sf, None)
+        rv = rot[(i - warmup) % len(rot):(i - warmup) % len(rot) + 1] if rot is not None else None
+        _, gr = o.loss_and_grad([pt], [rt], [var], res, rv, sf, None)
         var = torch.nan_to_num(adam.step(var, gr[0], cfg.lr))
         if i >= warmup:
             times.append(time.perf_counter() - t0)
@@ -401,7 +425,7 @@ def cpu_baseline(wl, budget_s=25.0, steps=1, warmup=0):
     t_view = float(np.mean(times))
     return {'value': 1.0 / (t_view * w['n_views']), 'unit': 'iters/s', 'cores': torch.get_num_threads(),
             'kind': 'port', 'seconds_per_view_pass': t_view, 'samples': len(times),
-            'sample': '%d x one view pass (fwd+bwd+Adam) of %s at full size; an iteration = %d such passes; '
+            'sample': '%d view passes (each fwd+bwd+Adam) of %s at full size; an iteration = %d such passes; '
                       'PyTorch-CPU fp32 restatement of the TF-1.15 graph (TF itself cannot run here)'
                       % (len(times), wl, w['n_views'])}
 

@@ -116,13 +116,22 @@ int lnst_raymarch_bwd(const float* vol, const float* rot, int32_t n_views, int32
 
 /* Box variants: rays are marched only through the depth interval whose trilinear footprints can touch
  * the box (density is zero elsewhere, so img/stot are bit-identical to the full march; g_vol receives
- * the exact gradient for every voxel inside the box and nothing outside it). */
+ * the exact gradient for every ACTIVE voxel inside the box and nothing outside it).
+ * `intervals` (may be NULL): int32 [n_views,H,W,2] = the inclusive depth-index range of every ray, from
+ * lnst_ray_intervals; NULL = derive it from the box inside the kernel. */
 int lnst_raymarch_fwd_box(const float* vol, const float* rot, int32_t n_views, int32_t D, int32_t H,
-                          int32_t W, float tau, int32_t liquid, const LnstBox* box, float* img, float* stot,
-                          void* stream);
+                          int32_t W, float tau, int32_t liquid, const LnstBox* box, const int32_t* intervals,
+                          float* img, float* stot, void* stream);
 int lnst_raymarch_bwd_box(const float* vol, const float* rot, int32_t n_views, int32_t D, int32_t H,
-                          int32_t W, float tau, int32_t liquid, const LnstBox* box, const float* stot,
-                          const float* g_img, float* g_vol, void* stream);
+                          int32_t W, float tau, int32_t liquid, const LnstBox* box, const int32_t* intervals,
+                          const float* stot, const float* g_img, float* g_vol, void* stream);
+/* Ray intervals for a set of views: the slab test against `box`, then shrunk from both ends while the ray
+ * runs through empty occupancy bricks.  `bricks` (may be NULL): one byte per 4x4x4-voxel brick,
+ * [ceil(D/4), ceil(H/4), ceil(W/4)], non-zero where the brick or anything within two voxels plus one brick
+ * of it is active.  Depends on the views, not on the density: run it once per view set.  Only zeros are
+ * skipped, so images stay bit-identical and every ACTIVE voxel still receives its exact gradient. */
+int lnst_ray_intervals(const float* rot, int32_t n_views, int32_t D, int32_t H, int32_t W, const LnstBox* box,
+                       const unsigned char* bricks, int32_t* intervals, void* stream);
 /* Tuning switch for lnst_raymarch_bwd (process-wide, default 1): 1 = neighbouring lanes merge their
  * shared x-corner contributions by warp shuffle before the atomics; 0 = eight atomics per sample. */
 int lnst_set_raymarch_merge(int32_t on);

@@ -272,6 +272,34 @@ __device__ __forceinline__ void ray_interval(const RayLine& l, const RayGeo& g, 
   ihi = min(g.D - 1, (int)floorf(t1) + 1);
 }
 
+// Occupancy bricks (4^3 voxels, one byte each; set where any voxel within reach of the brick is active --
+// the caller dilates by two voxels and one brick, see Styler._workspace): shrink [ilo, ihi] from both
+// ends while the ray is in empty bricks, testing every `stride`-th sample (stride * max|k| <= 4 voxels, so
+// no sample between two tested ones can touch an active voxel the tests missed).
+#define LNST_BRICK 4
+struct Bricks { const unsigned char* occ; int by, bx; };
+__device__ __forceinline__ bool brick_hit(float cz, float cy, float cx, float kz, float ky, float kx, float fi,
+                                          float mD, float mH, float mW, const unsigned char* __restrict__ occ,
+                                          int by, int bx) {
+  const int z = (int)fminf(fmaxf(fmaf(kz, fi, cz), 0.f), mD);
+  const int y = (int)fminf(fmaxf(fmaf(ky, fi, cy), 0.f), mH);
+  const int x = (int)fminf(fmaxf(fmaf(kx, fi, cx), 0.f), mW);
+  return occ[((z / LNST_BRICK) * by + (y / LNST_BRICK)) * bx + (x / LNST_BRICK)] != 0;
+}
+__device__ __forceinline__ void refine_interval(const RayLine l, const RayGeo g, const unsigned char* occ, int by, int bx,
+                                                int& ilo, int& ihi) {
+  if (occ == nullptr || ilo > ihi) return;
+  const float km = fmaxf(fmaxf(fabsf(l.kz), fabsf(l.ky)), fmaxf(fabsf(l.kx), 1e-6f));
+  const int stride = max(1, (int)(4.f / km));
+  const int lo0 = ilo, hi0 = ihi;
+  int a = ilo, b = ihi;
+  while (a <= b && !brick_hit(l.cz, l.cy, l.cx, l.kz, l.ky, l.kx, (float)a, g.mD, g.mH, g.mW, occ, by, bx)) a += stride;
+  if (a > b) { ilo = 1; ihi = 0; return; }
+  while (b > a && !brick_hit(l.cz, l.cy, l.cx, l.kz, l.ky, l.kx, (float)b, g.mD, g.mH, g.mW, occ, by, bx)) b -= stride;
+  ilo = max(lo0, a - stride + 1);
+  ihi = min(hi0, b + stride - 1);
+}
+
 struct Cell { int idx; float fz, fy, fx; };
 
 __device__ __forceinline__ Cell locate(const RayLine& l, float fi, const RayGeo& g) {
@@ -306,9 +334,25 @@ __device__ __forceinline__ float fast_exp2(float x) {
 #endif
 }
 
+// [i_lo, i_hi] of every ray of every view: the box slab test, then the brick refinement.  Depends only on
+// the view matrices, the box and the bricks -- not on the density -- so it runs once per view set.
+__global__ void __launch_bounds__(128) ray_intervals_k(const float* __restrict__ rot, RayGeo g, BoxF bf, Bricks br,
+                                                        int2* __restrict__ iv) {
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= g.HW) return;
+  const int view = blockIdx.y;
+  const int h = pix / g.W, w = pix - h * g.W;
+  const RayLine l = ray_line(rot + 9 * view, lin_coord(h, g.sH), lin_coord(w, g.sW), g);
+  int lo, hi;
+  ray_interval(l, g, bf, lo, hi);
+  refine_interval(l, g, br.occ, br.by, br.bx, lo, hi);
+  iv[(int64_t)view * g.HW + pix] = make_int2(lo, hi);
+}
+
 __global__ void __launch_bounds__(128) raymarch_rot_fwd_k(const float* __restrict__ vol, const float* __restrict__ rot,
-                                                           RayGeo g, BoxF bf, float ntl2, int liquid,
-                                                           float* __restrict__ img, float* __restrict__ stot) {
+                                                           RayGeo g, BoxF bf, const int2* __restrict__ iv,
+                                                           float ntl2, int liquid, float* __restrict__ img,
+                                                           float* __restrict__ stot) {
   const int pix = blockIdx.x * blockDim.x + threadIdx.x;
   if (pix >= g.HW) return;
   const int view = blockIdx.y;
@@ -316,7 +360,12 @@ __global__ void __launch_bounds__(128) raymarch_rot_fwd_k(const float* __restric
   const RayLine l = ray_line(rot + 9 * view, lin_coord(h, g.sH), lin_coord(w, g.sW), g);
   float S = 0.f, I = 0.f;
   int i_lo, i0;
-  ray_interval(l, g, bf, i_lo, i0);                    // the density is zero outside [i_lo, i0]
+  if (iv) {                                            // precomputed by ray_intervals_k (box + bricks)
+    const int2 r = iv[(int64_t)view * g.HW + pix];
+    i_lo = r.x; i0 = r.y;
+  } else {
+    ray_interval(l, g, bf, i_lo, i0);                  // the density is zero outside [i_lo, i0]
+  }
   for (; i0 >= i_lo + RM_UNROLL - 1; i0 -= RM_UNROLL) {   // full groups: no per-sample bounds checks
     float d[RM_UNROLL];
 #pragma unroll
@@ -340,7 +389,8 @@ __global__ void __launch_bounds__(128) raymarch_rot_fwd_k(const float* __restric
 // d I / d d_k = T_k - tau * sum_{i<=k} d_i T_i  (smoke);  tau * exp(-tau * S_total) (liquid)
 template <bool MERGE>
 __global__ void __launch_bounds__(128) raymarch_rot_bwd_k(const float* __restrict__ vol, const float* __restrict__ rot,
-                                                           RayGeo g, BoxF bf, float tau, float ntl2, int liquid,
+                                                           RayGeo g, BoxF bf, const int2* __restrict__ iv,
+                                                           float tau, float ntl2, int liquid,
                                                            const float* __restrict__ stot,
                                                            const float* __restrict__ g_img, float* __restrict__ g_vol) {
   const int pix = blockIdx.x * blockDim.x + threadIdx.x;
@@ -363,8 +413,13 @@ __global__ void __launch_bounds__(128) raymarch_rot_bwd_k(const float* __restric
   // samples below the interval have zero density (below = Pk = 0 there) and, like those above it,
   // no footprint inside the box
   int i_lo, i_hi;
-  ray_interval(l, g, bf, i_lo, i_hi);
-  if (!active) { i_lo = 0x7fffffff; i_hi = -1; }
+  if (iv) {
+    const int2 r = iv[(int64_t)view * g.HW + pc];
+    i_lo = r.x; i_hi = r.y;
+  } else {
+    ray_interval(l, g, bf, i_lo, i_hi);
+  }
+  if (!active || i_lo > i_hi) { i_lo = 0x7fffffff; i_hi = -1; }
   int w_lo = i_lo, w_hi = i_hi;                        // warp-uniform loop bounds (the merge shuffles)
   if (MERGE) {
 #pragma unroll
@@ -594,16 +649,34 @@ extern "C" int lnst_rotate_fwd(const float* vol, const float* rot, int32_t n_vie
 static int lnst_raymarch_merge = 1;
 extern "C" int lnst_set_raymarch_merge(int32_t on) { lnst_raymarch_merge = on ? 1 : 0; return LNST_OK; }
 
+static inline Bricks make_bricks(const unsigned char* occ, int H, int W) {
+  Bricks b;
+  b.occ = occ;
+  b.by = (H + LNST_BRICK - 1) / LNST_BRICK;
+  b.bx = (W + LNST_BRICK - 1) / LNST_BRICK;
+  return b;
+}
+
+extern "C" int lnst_ray_intervals(const float* rot, int32_t n_views, int32_t D, int32_t H, int32_t W,
+                                  const LnstBox* box, const unsigned char* bricks, int32_t* intervals, void* stream) {
+  if (!rot || !intervals || n_views < 1 || D < 2 || H < 2 || W < 2 || !box_ok(box, D, H, W)) return LNST_EARG;
+  if ((int64_t)D * H * W >= 0x7fffffff) return LNST_EARG;
+  const RayGeo g = make_geo(D, H, W);
+  LNST_LAUNCH(ray_intervals_k, dim3(lnst_blocks((int64_t)H * W, 128), n_views), dim3(128), 0, lnst_stream(stream), rot,
+              g, make_boxf(box, D, H, W), make_bricks(bricks, H, W), reinterpret_cast<int2*>(intervals));
+  return lnst_status();
+}
+
 extern "C" int lnst_raymarch_fwd_box(const float* vol, const float* rot, int32_t n_views, int32_t D, int32_t H,
-                                     int32_t W, float tau, int32_t liquid, const LnstBox* box, float* img,
-                                     float* stot, void* stream) {
+                                     int32_t W, float tau, int32_t liquid, const LnstBox* box,
+                                     const int32_t* intervals, float* img, float* stot, void* stream) {
   if (!vol || !img || !stot || n_views < 1 || D < 1 || H < 1 || W < 1 || !box_ok(box, D, H, W)) return LNST_EARG;
   if (!rot && n_views != 1) return LNST_EARG;
   if (rot && D >= 2 && H >= 2 && W >= 2 && (int64_t)D * H * W < 0x7fffffff) {
     const RayGeo g = make_geo(D, H, W);
     LNST_LAUNCH(raymarch_rot_fwd_k, dim3(lnst_blocks((int64_t)H * W, 128), n_views), dim3(128), 0,
-                lnst_stream(stream), vol, rot, g, make_boxf(box, D, H, W), -tau * 1.4426950408889634f, (int)liquid,
-                img, stot);
+                lnst_stream(stream), vol, rot, g, make_boxf(box, D, H, W), reinterpret_cast<const int2*>(intervals),
+                -tau * 1.4426950408889634f, (int)liquid, img, stot);
     return lnst_status();
   }
   const VolDims v = make_dims(D, H, W);
@@ -615,25 +688,27 @@ extern "C" int lnst_raymarch_fwd_box(const float* vol, const float* rot, int32_t
 extern "C" int lnst_raymarch_fwd(const float* vol, const float* rot, int32_t n_views, int32_t D, int32_t H,
                                  int32_t W, float tau, int32_t liquid, float* img, float* stot,
                                  void* stream) {
-  return lnst_raymarch_fwd_box(vol, rot, n_views, D, H, W, tau, liquid, nullptr, img, stot, stream);
+  return lnst_raymarch_fwd_box(vol, rot, n_views, D, H, W, tau, liquid, nullptr, nullptr, img, stot, stream);
 }
 
 extern "C" int lnst_raymarch_bwd_box(const float* vol, const float* rot, int32_t n_views, int32_t D, int32_t H,
-                                     int32_t W, float tau, int32_t liquid, const LnstBox* box, const float* stot,
-                                     const float* g_img, float* g_vol, void* stream) {
+                                     int32_t W, float tau, int32_t liquid, const LnstBox* box,
+                                     const int32_t* intervals, const float* stot, const float* g_img,
+                                     float* g_vol, void* stream) {
   if (!vol || !stot || !g_img || !g_vol || n_views < 1 || D < 1 || H < 1 || W < 1 || !box_ok(box, D, H, W))
     return LNST_EARG;
   if (!rot && n_views != 1) return LNST_EARG;
   if (rot && D >= 2 && H >= 2 && W >= 2 && (int64_t)D * H * W < 0x7fffffff) {
     const RayGeo g = make_geo(D, H, W);
     const BoxF bf = make_boxf(box, D, H, W);
+    const int2* br = reinterpret_cast<const int2*>(intervals);
     const float ntl2 = -tau * 1.4426950408889634f;
     if (lnst_raymarch_merge)
       LNST_LAUNCH(raymarch_rot_bwd_k<true>, dim3(lnst_blocks((int64_t)H * W, 128), n_views), dim3(128), 0,
-                  lnst_stream(stream), vol, rot, g, bf, tau, ntl2, (int)liquid, stot, g_img, g_vol);
+                  lnst_stream(stream), vol, rot, g, bf, br, tau, ntl2, (int)liquid, stot, g_img, g_vol);
     else
       LNST_LAUNCH(raymarch_rot_bwd_k<false>, dim3(lnst_blocks((int64_t)H * W, 128), n_views), dim3(128), 0,
-                  lnst_stream(stream), vol, rot, g, bf, tau, ntl2, (int)liquid, stot, g_img, g_vol);
+                  lnst_stream(stream), vol, rot, g, bf, br, tau, ntl2, (int)liquid, stot, g_img, g_vol);
     return lnst_status();
   }
   const VolDims v = make_dims(D, H, W);
@@ -645,7 +720,7 @@ extern "C" int lnst_raymarch_bwd_box(const float* vol, const float* rot, int32_t
 extern "C" int lnst_raymarch_bwd(const float* vol, const float* rot, int32_t n_views, int32_t D, int32_t H,
                                  int32_t W, float tau, int32_t liquid, const float* stot,
                                  const float* g_img, float* g_vol, void* stream) {
-  return lnst_raymarch_bwd_box(vol, rot, n_views, D, H, W, tau, liquid, nullptr, stot, g_img, g_vol, stream);
+  return lnst_raymarch_bwd_box(vol, rot, n_views, D, H, W, tau, liquid, nullptr, nullptr, stot, g_img, g_vol, stream);
 }
 
 extern "C" int lnst_image_max(const float* img, int32_t n_img, int64_t n_pix, float* stats, void* stream) {

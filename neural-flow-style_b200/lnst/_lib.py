@@ -50,8 +50,9 @@ SIGNATURES = {
     'lnst_rotate_fwd': [vp, vp, i32, i32, i32, i32, vp, vp],
     'lnst_raymarch_fwd': [vp, vp, i32, i32, i32, i32, f32, i32, vp, vp, vp],
     'lnst_raymarch_bwd': [vp, vp, i32, i32, i32, i32, f32, i32, vp, vp, vp, vp],
-    'lnst_raymarch_fwd_box': [vp, vp, i32, i32, i32, i32, f32, i32, BP, vp, vp, vp],
-    'lnst_raymarch_bwd_box': [vp, vp, i32, i32, i32, i32, f32, i32, BP, vp, vp, vp, vp],
+    'lnst_raymarch_fwd_box': [vp, vp, i32, i32, i32, i32, f32, i32, BP, vp, vp, vp, vp],
+    'lnst_raymarch_bwd_box': [vp, vp, i32, i32, i32, i32, f32, i32, BP, vp, vp, vp, vp, vp],
+    'lnst_ray_intervals': [vp, i32, i32, i32, i32, BP, vp, vp, vp],
     'lnst_set_raymarch_merge': [i32],
     'lnst_image_max': [vp, i32, i64, vp, vp],
     'lnst_normalize_fwd': [vp, vp, i32, i64, vp, vp],

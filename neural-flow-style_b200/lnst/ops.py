@@ -113,19 +113,33 @@ def rotate_fwd(vol, rot):
     return out
 
 
-def raymarch_fwd(vol, rot, tau, liquid, img, stot, box=None):
+def _u8(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def ray_intervals(rot, shape, box, bricks, out=None):
+    """int32 [n_views,H,W,2]: inclusive depth range of every ray that can touch the box / occupied bricks."""
+    D, H, W = shape
+    nv = rot.shape[0]
+    if out is None:
+        out = torch.empty(nv, H, W, 2, dtype=torch.int32, device=rot.device)
+    _lib.get().call('lnst_ray_intervals', ptr(rot), nv, D, H, W, _b(box), _u8(bricks), _u8(out), _s(rot))
+    return out
+
+
+def raymarch_fwd(vol, rot, tau, liquid, img, stot, box=None, intervals=None):
     D, H, W = vol.shape
     nv = 1 if rot is None else rot.shape[0]
     _lib.get().call('lnst_raymarch_fwd_box', ptr(vol), ptr(rot), nv, D, H, W, float(tau), int(bool(liquid)), _b(box),
-                    ptr(img), ptr(stot), _s(vol))
+                    _u8(intervals), ptr(img), ptr(stot), _s(vol))
     return img, stot
 
 
-def raymarch_bwd(vol, rot, tau, liquid, stot, g_img, g_vol, box=None):
+def raymarch_bwd(vol, rot, tau, liquid, stot, g_img, g_vol, box=None, intervals=None):
     D, H, W = vol.shape
     nv = 1 if rot is None else rot.shape[0]
     _lib.get().call('lnst_raymarch_bwd_box', ptr(vol), ptr(rot), nv, D, H, W, float(tau), int(bool(liquid)), _b(box),
-                    ptr(stot), ptr(g_img), ptr(g_vol), _s(vol))
+                    _u8(intervals), ptr(stot), ptr(g_img), ptr(g_vol), _s(vol))
     return g_vol
 
 

@@ -90,6 +90,7 @@ class Styler(StylerBase):
                 raise NotImplementedError('v_batch > 1 is not built (its loss ignores all but the first view, '
                                           'styler_base.py:98)')
         self._frame_cache = {}
+        self._iv_cache = {}
         self._pool = None
         self._rot_all = self._rot_mine = None
         # what the ranks split: 'views' (mean-gradient mode), 'frames' (sequences) or
@@ -106,6 +107,7 @@ class Styler(StylerBase):
 
     def _upload_views(self):
         """Host view matrices -> the persistent device buffers the kernels (and graphs) read."""
+        self._iv_cache = {}                                        # ray intervals belong to the old views
         allv = self._rot_tensor(self.rot_mat_)
         mine = self._rot_tensor([self.rot_mat_[i] for i in range(self.view_rank, self.n_views, self.view_world)]) \
             if self.n_views > self.view_rank else None
@@ -223,7 +225,7 @@ class Styler(StylerBase):
         D, H, W = res
         dev = self.device
         nk = self.num_kernels if 'd' in self.target_field else 1
-        ws = {'grid': self._grid(res), 'res': res, 'box': None,
+        ws = {'grid': self._grid(res), 'res': res, 'box': None, 'bricks': None,
               'num': torch.zeros(nk, D * H * W, dtype=f32, device=dev),
               'd': torch.zeros(D, H, W, dtype=f32, device=dev),
               'ds': torch.zeros(D, H, W, dtype=f32, device=dev),
@@ -241,18 +243,38 @@ class Styler(StylerBase):
                     lo[a] = max(int(idx.min()) - 1, 0)
                     hi[a] = min(int(idx.max()) + 1, res[a] - 1)
             ws['box'] = _lib.make_box(lo, hi)
+            if occ is not None and min(res) >= 8:
+                # occupancy bricks for the ray-march (4^3 voxels): active = within one voxel of a reachable
+                # cell (the blur); marked = any voxel within two voxels of an active one, then one more brick
+                mp = torch.nn.functional.max_pool3d
+                o = occ.to(f32)[None, None]
+                o = mp(o, 3, 1, 1)                                        # active voxels
+                o = mp(o, 5, 1, 2)                                        # + two voxels
+                o = mp(o, 4, 4, 0, ceil_mode=True)                        # bricks
+                o = mp(o, 3, 1, 1)                                        # + one brick
+                ws['bricks'] = (o[0, 0] > 0).to(torch.uint8).contiguous()
             ws['box_cells'] = (hi[0] - lo[0] + 1) * (hi[1] - lo[1] + 1) * (hi[2] - lo[2] + 1)
         return ws
 
-    def _render(self, ds, rot, box=None):
+    def _render(self, ds, rot, box=None, bricks=None):
         """ds [D,H,W] -> gray [nv,H,W,1] in [0,1] plus what the backward needs."""
         D, H, W = ds.shape
         nv = 1 if rot is None else rot.shape[0]
         dev = self.device
         img = torch.empty(nv, H, W, dtype=f32, device=dev)
         stot = torch.empty(nv, H, W, dtype=f32, device=dev)
-        ops.raymarch_fwd(ds, rot, self.transmit, self.render_liquid, img, stot, box)
-        st = {'img': img, 'stot': stot, 'rot': rot, 'box': box}
+        iv = None
+        if bricks is not None and rot is not None and min(ds.shape) >= 2:
+            # per view set and independent of the density: computed once while the views are fixed
+            key = (rot.data_ptr(), tuple(ds.shape), bricks.data_ptr())
+            if 'uniform' in self.sample_type and key in self._iv_cache:
+                iv = self._iv_cache[key]
+            else:
+                iv = ops.ray_intervals(rot, ds.shape, box, bricks)
+                if 'uniform' in self.sample_type:
+                    self._iv_cache[key] = iv
+        ops.raymarch_fwd(ds, rot, self.transmit, self.render_liquid, img, stot, box, iv)
+        st = {'img': img, 'stot': stot, 'rot': rot, 'box': box, 'iv': iv}
         if self.render_liquid:
             gray = img
         else:                                                     # styler_3p.py:158
@@ -282,7 +304,7 @@ class Styler(StylerBase):
         else:
             g_img = ops.normalize_bwd(st['img'], st['stats'], g_gray, torch.empty(nv, dtype=f32, device=self.device),
                                       torch.empty_like(g_gray))
-        ops.raymarch_bwd(ds, st['rot'], self.transmit, self.render_liquid, st['stot'], g_img, g_ds, st['box'])
+        ops.raymarch_bwd(ds, st['rot'], self.transmit, self.render_liquid, st['stot'], g_img, g_ds, st['box'], st['iv'])
 
     # ---- one loss + gradient evaluation (= one sess.run([train_op, total_loss]) without Adam) ----
     def loss_and_grad(self, fr, var, ws, rot, style_grams):
@@ -291,7 +313,7 @@ class Styler(StylerBase):
         d = self._density(fr, var, res, ws)
         box = ws['box']
         ds = ops.smooth3_relu_fwd(d, ws['ds'], self.k, box)        # styler_3p.py:112-125
-        st = self._render(ds, rot, box)
+        st = self._render(ds, rot, box, ws['bricks'])
         nv = st['x'].shape[0]
         loss = torch.zeros(nv, dtype=f32, device=self.device)
         g_x = self.image_loss_and_grad(st['x'], st['d_img'], style_grams, loss)
@@ -326,7 +348,7 @@ class Styler(StylerBase):
         d = self._density(fr, var, ws['res'], ws)
         ds = ops.smooth3_relu_fwd(d, ws['ds'], self.k, ws['box'])
         rot = self._eye if identity_view else None
-        st = self._render(ds, rot, ws['box'])
+        st = self._render(ds, rot, ws['box'], ws['bricks'])
         p_out = fr['p'] + var if 'p' in self.target_field else fr['p']
         return p_out, ds + 0.0, st['d_img'][0]                     # "+0.0" folds the -0.0 markers
 

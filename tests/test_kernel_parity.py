@@ -340,6 +340,47 @@ def test_raymarch_box_equals_full_inside(dev, liquid, case):
         assert float(outside.abs().max()) == 0.0
 
 
+@pytest.mark.parametrize('liquid', [False, True])
+def test_raymarch_bricks_skip_only_zeros(dev, liquid):
+    """Occupancy bricks (built like Styler._workspace does): rays also skip the empty bricks at both ends of
+    their box interval.  Image bit-identical; gradient identical on every active voxel."""
+    rng = np.random.RandomState(23)
+    D, H, W = 56, 52, 60
+    z, y, x = np.meshgrid(np.arange(D), np.arange(H), np.arange(W), indexing='ij')
+    # two blobs in opposite corners: their bounding box is most of the volume, most bricks are empty
+    reach = (((z - 12) / 7.0) ** 2 + ((y - 11) / 6.0) ** 2 + ((x - 13) / 8.0) ** 2 <= 1.0) | \
+            (((z - 44) / 6.0) ** 2 + ((y - 40) / 7.0) ** 2 + ((x - 47) / 6.0) ** 2 <= 1.0)          # "wmap > 0"
+    mp = torch.nn.functional.max_pool3d
+    o = torch.tensor(reach.astype(np.float32))[None, None]
+    active = mp(o, 3, 1, 1)
+    bricks = (mp(mp(mp(active, 5, 1, 2), 4, 4, 0, ceil_mode=True), 3, 1, 1)[0, 0] > 0).to(torch.uint8).contiguous()
+    active = active[0, 0] > 0
+    vol_np = (rng.rand(D, H, W) * (rng.rand(D, H, W) > 0.3)).astype(np.float32) * active.numpy()
+    idx = np.argwhere(reach)
+    lo, hi = np.maximum(idx.min(0) - 1, 0), np.minimum(idx.max(0) + 1, [D - 1, H - 1, W - 1])
+    box = _lib.make_box(lo.tolist(), hi.tolist())
+    vol = torch.tensor(vol_np).to(dev)
+    mats = _rots()[:3] + [np.matmul(T.rot_y_3d(35.0), T.rot_z_3d(-50.0)), np.matmul(T.rot_y_3d(90.0), T.rot_z_3d(0.0))]
+    rot = torch.tensor(np.asarray(mats), dtype=torch.float32).reshape(-1, 9).to(dev)
+    nv, tau = rot.shape[0], 0.3
+    img_f, st_f = torch.empty(nv, H, W, device=dev), torch.empty(nv, H, W, device=dev)
+    img_b, st_b = torch.empty(nv, H, W, device=dev), torch.empty(nv, H, W, device=dev)
+    ops.raymarch_fwd(vol, rot, tau, liquid, img_f, st_f)
+    iv = ops.ray_intervals(rot, (D, H, W), box, bricks.to(dev))
+    iv_box = ops.ray_intervals(rot, (D, H, W), box, None)
+    n_box = (iv_box[..., 1] - iv_box[..., 0] + 1).clamp(min=0).sum().item()
+    n_br = (iv[..., 1] - iv[..., 0] + 1).clamp(min=0).sum().item()
+    assert 0 < n_br < 0.9 * n_box                                       # the bricks shorten the intervals
+    ops.raymarch_fwd(vol, rot, tau, liquid, img_b, st_b, box, iv)
+    assert torch.equal(img_f.cpu(), img_b.cpu()) and torch.equal(st_f.cpu(), st_b.cpu())
+    g = torch.tensor(rng.randn(nv, H, W).astype(np.float32)).to(dev)
+    g_full, g_br = torch.zeros(D, H, W, device=dev), torch.zeros(D, H, W, device=dev)
+    ops.raymarch_bwd(vol, rot, tau, liquid, st_f, g, g_full)
+    ops.raymarch_bwd(vol, rot, tau, liquid, st_f, g, g_br, box, iv)
+    close(g_br.cpu()[active], g_full.cpu()[active], tol=2e-5, what='brick gradient on active voxels')
+    assert float(g_br.abs().sum()) < float(g_full.abs().sum())          # work was actually skipped
+
+
 def test_smooth_fill_and_wavg_box_variants(dev):
     rng = np.random.RandomState(22)
     shape, lo, hi = (9, 11, 13), (2, 1, 3), (6, 9, 10)

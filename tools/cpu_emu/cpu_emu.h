@@ -34,6 +34,7 @@ static inline float2 make_float2(float a, float b) { return {a, b}; }
 static inline float3 make_float3(float a, float b, float c) { return {a, b, c}; }
 static inline float4 make_float4(float a, float b, float c, float d) { return {a, b, c, d}; }
 static inline int3 make_int3(int a, int b, int c) { return {a, b, c}; }
+static inline int2 make_int2(int a, int b) { return {a, b}; }
 
 typedef void* cudaStream_t;
 typedef int cudaError_t;

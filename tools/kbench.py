@@ -89,13 +89,17 @@ def main():
     print('active box cells %d of %d (%.3f)' % (Vb, V, Vb / V))
     add('raymarch_fwd(full)', lambda: ops.raymarch_fwd(ds, rot, st.transmit, False, img, stot), nv * (4 * V + 8 * P))
     add('raymarch_bwd(full)', lambda: ops.raymarch_bwd(ds, rot, st.transmit, False, stot, g_img, g_ds), nv * (8 * V + 8 * P))
-    add('raymarch_fwd', lambda: ops.raymarch_fwd(ds, rot, st.transmit, False, img, stot, box), nv * (4 * Vb + 8 * P))
+    add('raymarch_fwd(box only)', lambda: ops.raymarch_fwd(ds, rot, st.transmit, False, img, stot, box), nv * (4 * Vb + 8 * P))
+    bricks = ops.ray_intervals(rot, ds.shape, box, ws['bricks']) if rot is not None else None
+    add('ray_intervals', lambda: ops.ray_intervals(rot, ds.shape, box, ws['bricks']), nv * 8 * P)
+    add('raymarch_fwd', lambda: ops.raymarch_fwd(ds, rot, st.transmit, False, img, stot, box, bricks), nv * (4 * Vb + 8 * P))
     if rot is not None:
         lib.call('lnst_set_raymarch_merge', 0)
         add('raymarch_bwd(merge=0)', lambda: ops.raymarch_bwd(ds, rot, st.transmit, False, stot, g_img, g_ds, box),
             nv * (8 * Vb + 8 * P))
         lib.call('lnst_set_raymarch_merge', 1)
-    add('raymarch_bwd', lambda: ops.raymarch_bwd(ds, rot, st.transmit, False, stot, g_img, g_ds, box), nv * (8 * Vb + 8 * P))
+    add('raymarch_bwd(box only)', lambda: ops.raymarch_bwd(ds, rot, st.transmit, False, stot, g_img, g_ds, box), nv * (8 * Vb + 8 * P))
+    add('raymarch_bwd', lambda: ops.raymarch_bwd(ds, rot, st.transmit, False, stot, g_img, g_ds, box, bricks), nv * (8 * Vb + 8 * P))
     add('splat_wavg_fwd', lambda: ops.splat_wavg_fwd(fr['p'], fr['r'], var, ws['grid'], hs, wmap, ws['num'], ws['d'], box),
         N * (12 + 16) + 4 * Vb)
     add('splat_wavg_bwd(generic)', lambda: ops.splat_wavg_bwd(fr['p'], var, ws['grid'], hs, wmap, g_d, gvar), N * (12 + 16) + 4 * Vb)
