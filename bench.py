@@ -110,7 +110,13 @@ def algorithmic_units(name, a, nk=2):
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures
 # (profiles/), keyed by (workload, entry point); None where no capture exists.
-TRAFFIC = {}
+TRAFFIC = {   # bytes per launch, profiles/r1_ncu_full_final.csv (mean over the entry point's launches of one C3 step)
+    ('C3', 'lnst_conv3x3_bf16_tc'): 34.7e6,
+    ('C3', 'lnst_raymarch_bwd_box'): 25.4e6,
+    ('C3', 'lnst_raymarch_fwd_box'): 13.1e6,
+    ('C3', 'lnst_splat_wavg_fwd_box'): 86.4e6,
+    ('C3', 'lnst_splat_wavg_bwd_coef'): 39.9e6,
+}
 
 
 def roofline_all(table, hbm_peak, tf_peak):
