@@ -125,3 +125,43 @@ def test_content_target_image_and_style(dev):
     check_run(out_new, out_ref)
     off = Oracle3P(smoke_cfg(**dict(kw, w_content=0)), oracle.vgg.synthetic_weights()).run(params, style_targets=[sty])
     assert abs(off['l'][0][0] - out_ref['l'][0][0]) > 1e-3 * abs(out_ref['l'][0][0])   # the content term matters
+
+
+def test_edge_all_padding_and_out_of_domain_particles(dev):
+    """Empty input in the reference's sense: every row is padding (p = -1, test_smokegun.py:48) or lies
+    outside the domain -- nothing is splatted, the render is empty, the loss is the style target's own Gram
+    energy and the variables stay zero (the NaN gradients of empty cells are swallowed, styler_3p.py:360)."""
+    res = 10
+    kw = dict(res=res, iter=2, rotate=False, conv_math='fp32', style_layer=['conv1_2'], w_style_layer=[1.0],
+              render_liquid=True)          # liquid render: no division by an all-zero image maximum
+    p = [np.concatenate([-np.ones((40, 3), np.float32), np.full((10, 3), 1.5, np.float32)])]
+    r = [np.random.RandomState(3).rand(50, 2).astype(np.float32)]
+    sty = synth.style_image(res, res)
+    new = Styler(smoke_cfg(**kw), weights=synth.vgg_weights())
+    new.style_img = sty
+    out_new = new.run({'p': p, 'r': r})
+    ref = Oracle3P(smoke_cfg(**kw), oracle.vgg.synthetic_weights()).run({'p': p, 'r': r}, style_targets=[sty])
+    np.testing.assert_allclose(out_new['l'][0], ref['l'][0], rtol=2e-4)
+    assert np.abs(out_new['d']).max() == 0.0 and np.abs(ref['d']).max() == 0.0
+    assert np.abs(out_new['g_opt'][0]).max() == 0.0 and np.abs(ref['g_opt'][0].numpy()).max() == 0.0
+
+
+def test_edge_ragged_frames_padded_like_the_drivers(dev):
+    """Frames with different particle counts, padded to the longest with p = -1 rows as the drivers do
+    (test_smokegun.py:60-65): the padding must not contribute and must not move."""
+    res = 10
+    kw = dict(res=res, iter=2, conv_math='fp32', num_frames=3, window_sigma=1.0, frames_per_opt=1,
+              style_layer=['conv1_2'], w_style_layer=[1.0])
+    p, r = synth.smoke_particles(300, 2, pad=0, num_frames=3)
+    for t, keep in enumerate((300, 220, 150)):                   # ragged: frame t really has `keep` particles
+        p[t] = p[t].copy()
+        p[t][keep:] = -1.0
+    sty = synth.style_image(res, res)
+    new = Styler(smoke_cfg(**kw), weights=synth.vgg_weights())
+    new.style_img = sty
+    out_new = new.run({'p': p, 'r': r})
+    ref = Oracle3P(smoke_cfg(**kw), oracle.vgg.synthetic_weights()).run({'p': p, 'r': r}, style_targets=[sty])
+    check_run(out_new, ref)
+    # padding rows never get a gradient; only the temporal filter can leak neighbours' updates into them
+    assert np.abs(out_new['g_opt'][0][300:]).max(initial=0.0) == 0.0
+    assert np.allclose(out_new['p'][2][150:], -1.0)
