@@ -6,7 +6,8 @@
 
 // m += (g-m)(1-b1); v += (g^2-v)(1-b2); var -= lr_t m/(sqrt(v)+eps)   (eps outside the bias
 // correction, lr_t = lr sqrt(1-b2^t)/(1-b1^t) computed by the caller).  A NaN gradient keeps
-// m and v NaN for good; the variable itself goes through nan_to_num.
+// m and v NaN for good and the variable NaN until it is re-assigned from the host-side iterate, as in
+// TF; every consumer applies the reference's rule for it (clip -> +1, nan_to_num on the iterate).
 __global__ void adam_step_k(float* __restrict__ var, const float* __restrict__ grad, float* __restrict__ m,
                             float* __restrict__ v, int64_t n, float lr_t, float b1, float b2, float eps,
                             float gscale) {
@@ -17,7 +18,7 @@ __global__ void adam_step_k(float* __restrict__ var, const float* __restrict__ g
   const float vi = v[i] + (g * g - v[i]) * (1.f - b2);
   m[i] = mi;
   v[i] = vi;
-  var[i] = lnst_nan_to_num(var[i] - lr_t * mi / (sqrtf(vi) + eps));
+  var[i] = var[i] - lr_t * mi / (sqrtf(vi) + eps);
 }
 
 // Device-resident step counter of one AdamOptimizer (state = {beta1^t, beta2^t, lr_t}): computes
@@ -43,7 +44,7 @@ __global__ void adam_step_dev_k(float* __restrict__ var, const float* __restrict
   const float vi = v[i] + (g * g - v[i]) * (1.f - b2);
   m[i] = mi;
   v[i] = vi;
-  var[i] = lnst_nan_to_num(var[i] - lr_t * mi / (sqrtf(vi) + eps));
+  var[i] = var[i] - lr_t * mi / (sqrtf(vi) + eps);
 }
 
 __global__ void iterate_accumulate_k(float* __restrict__ acc, const float* __restrict__ var, int64_t n, int first) {
@@ -71,7 +72,7 @@ __global__ void axpy_k(float* __restrict__ y, const float* __restrict__ x, float
 // tf.clip_by_value and its gradient (zero strictly outside [lo,hi]); styler_2p.py:68,88,94
 __global__ void clip_fwd_k(const float* __restrict__ x, float lo, float hi, float* __restrict__ y, int64_t n) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) y[i] = fminf(fmaxf(x[i], lo), hi);
+  if (i < n) y[i] = fmaxf(fminf(x[i], hi), lo);   // TF builds max(min(x,hi),lo): NaN reads as hi
 }
 __global__ void clip_bwd_k(const float* __restrict__ g, const float* __restrict__ x, float lo, float hi, float scale,
                            float* __restrict__ gx, int64_t n) {

@@ -206,7 +206,7 @@ __global__ void splat_wavg_num_k(const float* __restrict__ p, const float* __res
   float x[LNST_MAX_NK];
   for (int k = 0; k < nk; ++k) {
     float v = var ? var[i * nk + k] : 0.f;
-    v = fminf(fmaxf(v, -1.f), 1.f);               // styler_3p.py:74
+    v = fmaxf(fminf(v, 1.f), -1.f);               // styler_3p.py:74; TF order max(min(x,1),-1): NaN reads as +1
     x[k] = r[i * nk + k] + v;                     // :76
   }
   for_each_target<DIM>(pt, g, [&](int64_t cell, const float*, float len) {
@@ -273,7 +273,7 @@ __global__ void __launch_bounds__(256) splat_wavg_num3_k(const float* __restrict
 #pragma unroll
   for (int k = 0; k < NK; ++k) {
     float v = var ? var[i * NK + k] : 0.f;
-    v = fminf(fmaxf(v, -1.f), 1.f);               // styler_3p.py:74
+    v = fmaxf(fminf(v, 1.f), -1.f);               // styler_3p.py:74; TF order max(min(x,1),-1): NaN reads as +1
     x[k] = r[i * NK + k] + v;                     // :76
   }
   if (stencil_inside(pt, g)) {

@@ -7,11 +7,19 @@ CHECK the CUDA path; it is never imported by the product package (``lnst``).  On
 ``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` / ``--impl reference`` legs
 of ``bench.py`` may import it.
 
-PARITY STATUS: **parity unpinned** except for the one known-answer the reference holds
-(the 5x5 bilinear-warp tables in ``transform.py:1865-1884``, checked in
-``tests/test_oracle_warp_kat.py``).  The reference has no tests, no golden vectors, and
-cannot be executed here (TensorFlow 1.15 has no wheel for this interpreter), so every other
-function is pinned only by line-by-line restatement plus brute-force definitions on tiny
-grids (``tests/test_oracle_*.py``).
+PARITY STATUS: **pinned against the reference's own code executed in this container**, to the
+extent that is possible without TensorFlow:
+  * ``tests/golden/ref_*.npz`` are outputs of the UNMODIFIED reference modules
+    (``styler_3p.Styler.run``, ``styler_2p.Styler.run``, ``transform.py`` operators, ``vgg.py``,
+    ``styler_base.py``) run by ``tests/golden/make_reference_golden.py`` on top of ``oracle/tfshim`` --
+    a stand-in for the absent third-party TensorFlow 1.15 that restates the published semantics of
+    each op the path calls.  ``tests/test_reference_golden.py`` holds this oracle to them (loss
+    2e-5, field 1e-4, operators 2e-6 with identical NaN patterns, view matrices bit-equal) on 10
+    loop-level cases (density / position / colour modes, views, octaves, sequences, resize, TV,
+    content, style mask) and 20 operator-level vectors;
+  * the one known-answer the reference itself holds (the 5x5 bilinear-warp tables in
+    ``transform.py:1865-1884``) is checked in ``tests/test_golden.py``.
+Not pinned (no TensorFlow binary): the floating-point summation order inside TF's kernels and
+TF's platform-dependent NaN handling on CPU (the GPU rule is the one restated).
 """
 from . import transform, render, vgg, loss, adam, styler  # noqa: F401

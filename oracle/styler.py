@@ -16,16 +16,15 @@ Two view modes for the multi-view 3-D loop:
   ``allreduce``  -- mean gradient over views, ONE Adam step (the data-parallel variant
                     BASELINE.json's north_star asks for; a documented semantic change).
 
-NaN handling (deviation D2).  ``p2g_wavg``'s ``where(wmap>eps, num/wmap, num)`` gives
-a NaN gradient to every variable element that has an empty (wmap == 0) cell among its splat
-targets (``transform.py:1703``).  The reference lets the TF variable go NaN and maps NaN->0
-only on the host copy (``styler_3p.py:337-340,360``), so the END-OF-ITERATION value of such an
-element is always 0 -- reproduced here exactly (Adam m/v stay NaN for good).  Inside a
-multi-view iteration the reference would feed the NaN variable into the next view's forward
-pass, where ``tf.clip_by_value(NaN)`` is platform dependent (fmaxf on GPU gives -1, Eigen
-SIMD on CPU differs) and un-pinnable; here the variable is passed through nan_to_num right
-after every Adam step, i.e. such elements stay frozen at 0.  Identical to the reference
-whenever there is one view per iteration (every demo driver at HEAD has rotate=False).
+NaN handling.  ``p2g_wavg``'s ``where(wmap>eps, num/wmap, num)`` gives a NaN
+gradient to every variable element that has an empty (wmap == 0) cell among its splat targets
+(``transform.py:1703``).  The reference lets the TF variable (and Adam's m, v) go NaN and maps
+NaN->0 only on the host copies (``styler_3p.py:337-340,360``), so the END-OF-ITERATION value of such
+an element is always 0.  Inside a multi-view iteration the NaN variable is fed to the next view's
+forward pass, where ``tf.clip_by_value`` = ``maximum(minimum(x, 1), -1)`` runs through the GPU
+functors (``fminf/fmaxf``: the non-NaN operand wins) and reads it as +1 -- reproduced here (``_clip``)
+and pinned by ``tests/golden/ref_density_sequential.npz``, the reference's own loop executed on the
+TF stand-in.  (On TF's CPU kernels the NaN would propagate instead; the reference targets the GPU.)
 """
 import numpy as np
 import torch
@@ -50,6 +49,16 @@ def octave_sizes(resolution, octave_n, octave_scale):
 
 def _nan_to_num(x):
     return torch.nan_to_num(x)  # NaN->0, +-inf->+-finfo.max, like np.nan_to_num
+
+
+def _clip(x, lo, hi):
+    """``tf.clip_by_value`` as TF-1.15 builds it: ``maximum(minimum(x, hi), lo)`` (``clip_ops.py``) with
+    the GPU functors' NaN rule (Eigen ``numext::mini/maxi`` -> CUDA ``fminf/fmaxf``, IEEE minNum/maxNum:
+    the non-NaN operand wins), so a NaN variable element reads as ``hi``.  Gradient: passes where
+    ``lo <= x <= hi`` (``_MaximumMinimumGrad``), zero for NaN."""
+    lo = torch.as_tensor(lo, dtype=x.dtype)
+    hi = torch.as_tensor(hi, dtype=x.dtype)
+    return torch.fmax(torch.fmin(x, hi), lo)
 
 
 class _Base:
@@ -133,7 +142,7 @@ class Oracle3P(_Base):
                 p_ = p_ + var_list[i].unsqueeze(0)
             p_out.append(p_[0])
             if 'd' in c.target_field:
-                r_opt = torch.clamp(var_list[i], -1, 1)          # :74
+                r_opt = _clip(var_list[i], -1, 1)                # :74
                 d_vars.append(r_opt)
                 r_ = (r_list[i] + r_opt).unsqueeze(0)            # :76
                 d_ = 0
@@ -221,7 +230,7 @@ class Oracle3P(_Base):
                                 lv, gr = self.loss_and_grad(pl, rl, var, res, rot_mats[i:i + c.v_batch],
                                                             style_feats, content_feat)
                                 l_.append(lv)
-                                var = [_nan_to_num(adam[j].step(var[j], gr[j], lr)) for j in range(B)]
+                                var = [adam[j].step(var[j], gr[j], lr) for j in range(B)]
                                 if acc is None:
                                     acc = [_nan_to_num(v) for v in var]
                                 else:
@@ -235,7 +244,7 @@ class Oracle3P(_Base):
                                 l_.append(lv)
                                 gsum = gr if gsum is None else [a + b for a, b in zip(gsum, gr)]
                             nb = n_views // c.v_batch
-                            var = [_nan_to_num(adam[j].step(var[j], gsum[j] / nb, lr)) for j in range(B)]
+                            var = [adam[j].step(var[j], gsum[j] / nb, lr) for j in range(B)]
                             g_new = var
                         loss_o.append(float(np.mean(l_)))                  # :342
                         if 'uniform' not in c.sample_type:                # :344-349
@@ -243,7 +252,7 @@ class Oracle3P(_Base):
                     else:
                         lv, gr = self.loss_and_grad(pl, rl, var, res, None, style_feats, content_feat)
                         loss_o.append(lv)                                  # :354-357
-                        var = [_nan_to_num(adam[j].step(var[j], gr[j], lr)) for j in range(B)]
+                        var = [adam[j].step(var[j], gr[j], lr) for j in range(B)]
                         g_new = var
                     for i, f in enumerate(fr):                            # :359-363
                         g_tmp[f] = _nan_to_num(g_new[i]) - g_opt[f]
@@ -304,7 +313,7 @@ class Oracle2P(_Base):
             dg = T.p2g(p_, c.domain, res, c.radius, c.rest_density, c.nsize, support=c.support,
                        clip=c.clip) / c.rest_density                       # :55-57
             d_gray.append(dg)
-            c_ = torch.clamp(var_list[i].unsqueeze(0), 0, 1)               # :68
+            c_ = _clip(var_list[i].unsqueeze(0), 0, 1)                     # :68
             col.append(c_[0] * torch.clamp(r_[0] / c.rest_density, 0, 1))  # :71
             d.append(T.p2g(p_, c.domain, res, c.radius, c.rest_density, c.nsize, support=c.support,
                            clip=c.clip, pc=c_, pd=r_))                     # :74-75
@@ -359,7 +368,7 @@ class Oracle2P(_Base):
                     loss = self.total_loss(g, style_feats, content_feat)
                     grads = torch.autograd.grad(loss, vs)
                     loss_o.append(float(loss.detach()))
-                    var = [_nan_to_num(adam[j].step(var[j], grads[j].detach(), lr)) for j in range(B)]
+                    var = [adam[j].step(var[j], grads[j].detach(), lr) for j in range(B)]
                     for i, f in enumerate(fr):
                         g_tmp[f] = _nan_to_num(var[i]) - g_opt[f]          # :260-262
                     if step == c.iter - 1 and octave < c.octave_n - 1:

@@ -42,3 +42,14 @@ def liquid_cfg(res=16, **over):
                 render_liquid=True, rest_density=1000, window_sigma=0, frames_per_opt=1)
     base.update(over)
     return make_cfg(**base)
+
+
+def dam_cfg(**over):
+    """'c' mode (2-D colour) like the dambreak2d driver (test_dambreak2d.py:128-190), scaled down."""
+    res = [24, 32]
+    cell = 0.1
+    base = dict(target_field='c', resolution=res, domain=[r * cell for r in res], radius=0.025, nsize=2,
+                support=4, rest_density=1000, lr=0.01, iter=3, octave_n=1, window_sigma=0, frames_per_opt=1,
+                style_layer=['conv1_1'], w_style_layer=[1.0], w_style=1, w_tv=0, conv_math='fp32')
+    base.update(over)
+    return make_cfg(**base)

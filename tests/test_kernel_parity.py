@@ -439,9 +439,10 @@ def test_adam_matches_tf_formula_with_nan(dev):
         g[3, 1] = float('nan')
         lr_t = 0.1 * np.sqrt(1 - np.float32(0.999) ** t) / (1 - np.float32(0.9) ** t)
         ops.adam_step(var, g.to(dev), m, v, lr_t)
-        want = torch.nan_to_num(ref.step(want, g, 0.1))
+        want = ref.step(want, g, 0.1)
     close(var, want, what='adam')
-    assert var[3, 1].item() == 0.0 and torch.isnan(m[3, 1]).item()
+    # like the TF variable, the element stays NaN (with m, v) until the loop re-assigns it from the host iterate
+    assert torch.isnan(var[3, 1]).item() and torch.isnan(m[3, 1]).item()
 
 
 def test_adam_device_step_counter(dev):
@@ -456,7 +457,7 @@ def test_adam_device_step_counter(dev):
     for t in range(1, 6):
         g = torch.tensor(rng.randn(33, 3).astype(np.float32))
         ops.adam_step_dev(var, g.to(dev), m, v, state, 0.05, gscale=0.5)
-        want = torch.nan_to_num(ref.step(want, g * 0.5, 0.05))
+        want = ref.step(want, g * 0.5, 0.05)
     close(var, want, what='adam dev')
     np.testing.assert_allclose(state.cpu().numpy()[:2], [np.float32(0.9) ** 6, np.float32(0.999) ** 6], rtol=1e-6)
 
