@@ -65,6 +65,26 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
+// One lane of the (fully active) warp; the same lane every time for the same mask.  The producer and MMA
+// warps run their loops with ALL lanes so that stage indices, phases, coordinates and descriptors stay
+// warp-uniform (uniform registers), and only the TMA / MMA / commit instructions are guarded by the
+// elected lane.  Running the loops inside `if (lane == 0)` made the compiler wrap every UTCHMMA / UTMALDG
+// in an R2UR + ELECT + BRA.U.ANY "uniformise" loop: ~100 / ~70 issue slots per k-step in a single warp,
+// i.e. 400-600 cycles against the 256 cycles its four MMAs need (ncu source view, profiles/).
+__device__ __forceinline__ bool elect_one() {
+#ifdef LNST_CPU_EMU
+  return (threadIdx.x & 31) == 0;
+#else
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}" : "=r"(pred));
+  return pred != 0;
+#endif
+}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
@@ -371,52 +391,55 @@ conv3x3_tc_persist_k(const __grid_constant__ CUtensorMap map_x, const __grid_con
   const uint32_t tmem_d = *tmem_slot_ptr;
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ===== TMA producer =====
-      uint32_t it = 0;
-      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        const int nb = t % n_blocks_n, sp = t / n_blocks_n;
-        const int img = sp / tiles_sp, rem = sp - img * tiles_sp;
-        const int th = rem / s.tiles_w, tw = rem - th * s.tiles_w;
-        const int h0 = th * s.TH, w0 = tw * s.TW, n0 = nb * BLOCK_N;
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
-          const int st = it % PSTAGES;
-          const uint32_t ph = (it / PSTAGES) & 1;
+    // ===== TMA producer (whole warp in the loop, one elected lane issues) =====
+    const bool leader = elect_one();
+    uint32_t st = 0, ph = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      const int nb = t % n_blocks_n, sp = t / n_blocks_n;
+      const int img = sp / tiles_sp, rem = sp - img * tiles_sp;
+      const int th = rem / s.tiles_w, tw = rem - th * s.tiles_w;
+      const int h0 = th * s.TH, w0 = tw * s.TW, n0 = nb * BLOCK_N;
+      for (int tap = 0; tap < s.taps; ++tap) {
+        int ky = 1, kx = 1;
+        if (s.taps == 9) { ky = tap / 3; kx = tap - 3 * ky; }
+        const int wsel = s.w_img ? img : tap;
+        for (int c0 = 0; c0 < s.Cin; c0 += BLOCK_K) {
           mbar_wait(bars + 8 * (PSTAGES + st), ph ^ 1);
-          const uint32_t full = bars + 8 * st;
-          mbar_expect_tx(full, A_BYTES + B_BYTES);
-          const int tap = kb / kchunks, c0 = (kb - tap * kchunks) * BLOCK_K;
-          int ky = 1, kx = 1;
-          if (s.taps == 9) { ky = tap / 3; kx = tap - 3 * ky; }
-          tma_load_4d(smem_a + st * A_BYTES, &map_x, full, c0, w0 + kx - 1, h0 + ky - 1, img);
-          tma_load_3d(smem_b + st * B_BYTES, &map_w, full, c0, n0, s.w_img ? img : tap);
+          if (leader) {
+            const uint32_t full = bars + 8 * st;
+            mbar_expect_tx(full, A_BYTES + B_BYTES);
+            tma_load_4d(smem_a + st * A_BYTES, &map_x, full, c0, w0 + kx - 1, h0 + ky - 1, img);
+            tma_load_3d(smem_b + st * B_BYTES, &map_w, full, c0, n0, wsel);
+          }
+          if (++st == PSTAGES) { st = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===== MMA issuer =====
-      const uint32_t idesc = umma_idesc_bf16(BLOCK_M, BLOCK_N);
-      uint32_t it = 0, lt = 0;
-      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++lt) {
-        const uint32_t buf = lt & 1, bph = (lt >> 1) & 1;
-        mbar_wait(bar_tempty + 8 * buf, bph ^ 1);                      // epilogue has drained this buffer
+    // ===== MMA issuer (whole warp in the loop, one elected lane issues) =====
+    const bool leader = elect_one();
+    const uint32_t idesc = umma_idesc_bf16(BLOCK_M, BLOCK_N);
+    const uint32_t alo_base = desc_lo(smem_a, 16), blo_base = desc_lo(smem_b, 16);
+    const uint32_t hi = desc_hi_sw128(1024);
+    uint32_t st = 0, ph = 0, lt = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++lt) {
+      const uint32_t buf = lt & 1, bph = (lt >> 1) & 1;
+      mbar_wait(bar_tempty + 8 * buf, bph ^ 1);                      // epilogue has drained this buffer
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t acc = tmem_d + buf * BLOCK_N;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(bars + 8 * st, ph);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t acc = tmem_d + buf * BLOCK_N;
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
-          const int st = it % PSTAGES;
-          const uint32_t ph = (it / PSTAGES) & 1;
-          mbar_wait(bars + 8 * st, ph);
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t alo = desc_lo(smem_a + st * A_BYTES, 16), blo = desc_lo(smem_b + st * B_BYTES, 16);
-          const uint32_t hi = desc_hi_sw128(1024);
+        const uint32_t alo = alo_base + st * (A_BYTES >> 4), blo = blo_base + st * (B_BYTES >> 4);
+        if (leader) {
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
             umma_bf16_lh(acc, alo + k * 2, hi, blo + k * 2, hi, idesc, (kb | k) != 0 ? 1u : 0u);
           umma_commit(bars + 8 * (PSTAGES + st));
         }
-        umma_commit(bar_tfull + 8 * buf);
+        if (++st == PSTAGES) { st = 0; ph ^= 1; }
       }
+      if (leader) umma_commit(bar_tfull + 8 * buf);
     }
   } else {
     // ===== epilogue: warps 2..5, TMEM sub-partition = warp % 4 =====
@@ -607,81 +630,87 @@ conv3x3_halo_k(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
   const uint32_t tmem_d = *tmem_slot_ptr;
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ===== TMA producer =====
-      if (resident) {                                   // all 9 x kchunks weight tiles, once (n0 = 0)
-        mbar_expect_tx(bar_bfull, 9 * kchunks * B_BYTES);
-        for (int tap = 0; tap < 9; ++tap)
-          for (int c = 0; c < kchunks; ++c)
-            tma_load_3d(smem_b + (tap * kchunks + c) * B_BYTES, &map_w, bar_bfull, c * BLOCK_K, 0, tap);
-      }
-      uint32_t ita = 0, itb = 0;
-      for (int t = blockIdx.x; t < cfg.n_tiles; t += gridDim.x) {
-        const int nb = t % cfg.n_blocks_n, sp = t / cfg.n_blocks_n;
-        const int img = sp / tiles_sp, rem = sp - img * tiles_sp;
-        const int th = rem / s.tiles_w, tw = rem - th * s.tiles_w;
-        const int h0 = th * HTH, w0 = tw * HTW, n0 = nb * BLOCK_N;
-        for (int c = 0; c < kchunks; ++c, ++ita) {
-          const int st = ita % cfg.sa;
-          mbar_wait(bar_aempty + 8 * st, ((ita / cfg.sa) & 1) ^ 1);
-          mbar_expect_tx(bar_afull + 8 * st, PATCH_BYTES);
-          tma_load_4d(smem_a + st * PATCH_STRIDE, &map_x, bar_afull + 8 * st, c * BLOCK_K, w0 - 1, h0 - 1, img);
-          if (!resident) {
-            for (int tap = 0; tap < 9; ++tap, ++itb) {
-              const int sb = itb % cfg.sb;
-              mbar_wait(bar_bempty + 8 * sb, ((itb / cfg.sb) & 1) ^ 1);
-              mbar_expect_tx(bar_bfull + 8 * sb, B_BYTES);
-              tma_load_3d(smem_b + sb * B_BYTES, &map_w, bar_bfull + 8 * sb, c * BLOCK_K, n0, tap);
+    // ===== TMA producer (whole warp in the loop, one elected lane issues) =====
+    const bool leader = elect_one();
+    if (resident && leader) {                           // all 9 x kchunks weight tiles, once (n0 = 0)
+      mbar_expect_tx(bar_bfull, 9 * kchunks * B_BYTES);
+      for (int tap = 0; tap < 9; ++tap)
+        for (int c = 0; c < kchunks; ++c)
+          tma_load_3d(smem_b + (tap * kchunks + c) * B_BYTES, &map_w, bar_bfull, c * BLOCK_K, 0, tap);
+    }
+    uint32_t sta = 0, pha = 0, stb = 0, phb = 0;
+    for (int t = blockIdx.x; t < cfg.n_tiles; t += gridDim.x) {
+      const int nb = t % cfg.n_blocks_n, sp = t / cfg.n_blocks_n;
+      const int img = sp / tiles_sp, rem = sp - img * tiles_sp;
+      const int th = rem / s.tiles_w, tw = rem - th * s.tiles_w;
+      const int h0 = th * HTH, w0 = tw * HTW, n0 = nb * BLOCK_N;
+      for (int c = 0; c < kchunks; ++c) {
+        mbar_wait(bar_aempty + 8 * sta, pha ^ 1);
+        if (leader) {
+          mbar_expect_tx(bar_afull + 8 * sta, PATCH_BYTES);
+          tma_load_4d(smem_a + sta * PATCH_STRIDE, &map_x, bar_afull + 8 * sta, c * BLOCK_K, w0 - 1, h0 - 1, img);
+        }
+        if (++sta == (uint32_t)cfg.sa) { sta = 0; pha ^= 1; }
+        if (!resident) {
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(bar_bempty + 8 * stb, phb ^ 1);
+            if (leader) {
+              mbar_expect_tx(bar_bfull + 8 * stb, B_BYTES);
+              tma_load_3d(smem_b + stb * B_BYTES, &map_w, bar_bfull + 8 * stb, c * BLOCK_K, n0, tap);
             }
+            if (++stb == (uint32_t)cfg.sb) { stb = 0; phb ^= 1; }
           }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===== MMA issuer =====
-      const uint32_t idesc = umma_idesc_bf16(BLOCK_M, BLOCK_N);
-      uint32_t ita = 0, itb = 0, lt = 0;
-      if (resident) {
-        mbar_wait(bar_bfull, 0);
+    // ===== MMA issuer (whole warp in the loop, one elected lane issues) =====
+    const bool leader = elect_one();
+    const uint32_t idesc = umma_idesc_bf16(BLOCK_M, BLOCK_N);
+    const uint32_t ahi = desc_hi_sw128((HTW + 2) * 128), bhi = desc_hi_sw128(1024);
+    const uint32_t alo_base = desc_lo(smem_a, 16), blo_base = desc_lo(smem_b, 16);
+    uint32_t sta = 0, pha = 0, stb = 0, phb = 0, lt = 0;
+    if (resident) {
+      mbar_wait(bar_bfull, 0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+    for (int t = blockIdx.x; t < cfg.n_tiles; t += gridDim.x, ++lt) {
+      const uint32_t buf = lt & 1, bph = (lt >> 1) & 1;
+      mbar_wait(bar_tempty + 8 * buf, bph ^ 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t acc = tmem_d + buf * BLOCK_N;
+      for (int c = 0; c < kchunks; ++c) {
+        mbar_wait(bar_afull + 8 * sta, pha);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      }
-      for (int t = blockIdx.x; t < cfg.n_tiles; t += gridDim.x, ++lt) {
-        const uint32_t buf = lt & 1, bph = (lt >> 1) & 1;
-        mbar_wait(bar_tempty + 8 * buf, bph ^ 1);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t acc = tmem_d + buf * BLOCK_N;
-        for (int c = 0; c < kchunks; ++c, ++ita) {
-          const int st = ita % cfg.sa;
-          mbar_wait(bar_afull + 8 * st, (ita / cfg.sa) & 1);
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t alo0 = desc_lo(smem_a + st * PATCH_STRIDE, 16);
-          const uint32_t ahi = desc_hi_sw128((HTW + 2) * 128), bhi = desc_hi_sw128(1024);
+        const uint32_t alo0 = alo_base + sta * (PATCH_STRIDE >> 4);
+        uint32_t blo_res = blo_base + c * (B_BYTES >> 4);               // resident: slot tap * kchunks + c
 #pragma unroll
-          for (int tap = 0; tap < 9; ++tap) {
-            const int ky = tap / 3, kx = tap - 3 * ky;                 // compile-time after unrolling
-            uint32_t blo;
-            if (resident) {
-              blo = desc_lo(smem_b + (tap * kchunks + c) * B_BYTES, 16);
-            } else {
-              const int sb = itb % cfg.sb;
-              mbar_wait(bar_bfull + 8 * sb, (itb / cfg.sb) & 1);
-              asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-              blo = desc_lo(smem_b + sb * B_BYTES, 16);
-            }
-            const uint32_t alo = alo0 + ((ky * (HTW + 2) + kx) * 128 >> 4);
+        for (int tap = 0; tap < 9; ++tap) {
+          const int ky = tap / 3, kx = tap - 3 * ky;                 // compile-time after unrolling
+          uint32_t blo;
+          if (resident) {
+            blo = blo_res;
+            blo_res += kchunks * (B_BYTES >> 4);
+          } else {
+            mbar_wait(bar_bfull + 8 * stb, phb);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            blo = blo_base + stb * (B_BYTES >> 4);
+          }
+          const uint32_t alo = alo0 + ((ky * (HTW + 2) + kx) * 128 >> 4);
+          if (leader) {
 #pragma unroll
             for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
               umma_bf16_lh(acc, alo + k * 2, ahi, blo + k * 2, bhi, idesc, (c | tap | k) != 0 ? 1u : 0u);
-            if (!resident) {
-              umma_commit(bar_bempty + 8 * (itb % cfg.sb));
-              ++itb;
-            }
           }
-          umma_commit(bar_aempty + 8 * st);
+          if (!resident) {
+            if (leader) umma_commit(bar_bempty + 8 * stb);
+            if (++stb == (uint32_t)cfg.sb) { stb = 0; phb ^= 1; }
+          }
         }
-        umma_commit(bar_tfull + 8 * buf);
+        if (leader) umma_commit(bar_aempty + 8 * sta);
+        if (++sta == (uint32_t)cfg.sa) { sta = 0; pha ^= 1; }
       }
+      if (leader) umma_commit(bar_tfull + 8 * buf);
     }
   } else {
     // ===== epilogue: warps 2..5, TMEM sub-partition = warp % 4 =====

@@ -324,6 +324,25 @@ __device__ __forceinline__ float sample_cell(const float* __restrict__ vol, cons
   return fmaf(c.fz, b1 - b0, b0);
 }
 
+// The four voxels of one z-plane of a cell: [y0x0, y0x1, y1x0, y1x1].  A ray whose anchor advances by exactly
+// one voxel in depth between two consecutive samples (the usual case for the reference's small view angles,
+// |R[0]| ~ 1) sees the far plane of one sample as the near plane of the next: the values (forward) and the
+// gradient contributions (backward) of that plane are carried in registers instead of being re-read /
+// scattered twice.  Same arithmetic per sample as sample_cell, so images stay bit-identical.
+struct Plane4 { float a, b, c, d; };
+__device__ __forceinline__ Plane4 load_plane(const float* __restrict__ p, int W) {
+  Plane4 v;
+  v.a = p[0]; v.b = p[1]; v.c = p[W]; v.d = p[W + 1];
+  return v;
+}
+__device__ __forceinline__ float lerp_planes(const Plane4& lo, const Plane4& hi, const Cell& c) {
+  const float a00 = fmaf(c.fx, lo.b - lo.a, lo.a), a01 = fmaf(c.fx, lo.d - lo.c, lo.c);
+  const float a10 = fmaf(c.fx, hi.b - hi.a, hi.a), a11 = fmaf(c.fx, hi.d - hi.c, hi.c);
+  const float b0 = fmaf(c.fy, a01 - a00, a00), b1 = fmaf(c.fy, a11 - a10, a10);
+  return fmaf(c.fz, b1 - b0, b0);
+}
+#define LNST_NO_CELL (-0x40000000)
+
 __device__ __forceinline__ float fast_exp2(float x) {
 #ifdef LNST_CPU_EMU
   return exp2f(x);
@@ -366,20 +385,44 @@ __global__ void __launch_bounds__(128) raymarch_rot_fwd_k(const float* __restric
   } else {
     ray_interval(l, g, bf, i_lo, i0);                  // the density is zero outside [i_lo, i0]
   }
+  // marching towards the eye (descending i): sample i's near plane is sample i-1's far plane when the
+  // anchor steps back by exactly one voxel in depth
+  Plane4 near_prev;
+  near_prev.a = near_prev.b = near_prev.c = near_prev.d = 0.f;
+  int idx_prev = LNST_NO_CELL;
   for (; i0 >= i_lo + RM_UNROLL - 1; i0 -= RM_UNROLL) {   // full groups: no per-sample bounds checks
-    float d[RM_UNROLL];
+    Cell c[RM_UNROLL];
+    Plane4 lo[RM_UNROLL], hi[RM_UNROLL];
+    bool cont[RM_UNROLL];
 #pragma unroll
-    for (int u = 0; u < RM_UNROLL; ++u) d[u] = sample_cell(vol, locate(l, (float)(i0 - u), g), g);
+    for (int u = 0; u < RM_UNROLL; ++u) c[u] = locate(l, (float)(i0 - u), g);
 #pragma unroll
     for (int u = 0; u < RM_UNROLL; ++u) {
-      S += d[u];                                        // inclusive reverse cumsum, styler_3p.py:155
-      I = fmaf(d[u], fast_exp2(S * ntl2), I);
+      const float* p = vol + c[u].idx;
+      lo[u] = load_plane(p, g.W);
+      cont[u] = c[u].idx + g.HW == (u == 0 ? idx_prev : c[u - 1].idx);
+      if (!cont[u]) hi[u] = load_plane(p + g.HW, g.W);
     }
+#pragma unroll
+    for (int u = 0; u < RM_UNROLL; ++u) {
+      if (cont[u]) hi[u] = (u == 0) ? near_prev : lo[u - 1];
+      const float d = lerp_planes(lo[u], hi[u], c[u]);
+      S += d;                                           // inclusive reverse cumsum, styler_3p.py:155
+      I = fmaf(d, fast_exp2(S * ntl2), I);
+    }
+    near_prev = lo[RM_UNROLL - 1];
+    idx_prev = c[RM_UNROLL - 1].idx;
   }
   for (; i0 >= i_lo; --i0) {
-    const float d = sample_cell(vol, locate(l, (float)i0, g), g);
+    const Cell c = locate(l, (float)i0, g);
+    const float* p = vol + c.idx;
+    const Plane4 lo = load_plane(p, g.W);
+    const Plane4 hi = (c.idx + g.HW == idx_prev) ? near_prev : load_plane(p + g.HW, g.W);
+    const float d = lerp_planes(lo, hi, c);
     S += d;
     I = fmaf(d, fast_exp2(S * ntl2), I);
+    near_prev = lo;
+    idx_prev = c.idx;
   }
   if (liquid) I = 1.f - fast_exp2(S * ntl2);            // styler_3p.py:150-152
   img[(int64_t)view * g.HW + pix] = I;
@@ -428,18 +471,53 @@ __global__ void __launch_bounds__(128) raymarch_rot_bwd_k(const float* __restric
       w_hi = max(w_hi, __shfl_xor_sync(0xffffffffu, w_hi, o));
     }
   }
+  // marching away from the eye (ascending i).  carry: the ray advances in +z by about one voxel per sample,
+  // so a sample's far plane is usually the next sample's near plane -- its 4 voxel values are reused and its
+  // 4 gradient contributions wait in registers (pend) to be merged into the next sample's near plane: one
+  // red.global per voxel and sample pair instead of two.  Rays running the other way scatter directly.
+  const bool carry = rot[9 * view] > 0.5f;             // warp-uniform (one view per blockIdx.y)
+  Plane4 far_prev, pend;
+  far_prev.a = far_prev.b = far_prev.c = far_prev.d = 0.f;
+  pend = far_prev;
+  int idx_prev = LNST_NO_CELL;                         // anchor of the previous live, sampled cell
+  int pend_idx = -1;                                   // voxel index of the plane waiting in pend
   for (int i0 = w_lo; i0 <= w_hi; i0 += RM_UNROLL) {
     Cell c[RM_UNROLL];
     float d[RM_UNROLL];
+    Plane4 lo[RM_UNROLL], hi[RM_UNROLL];
+    bool cont[RM_UNROLL], lv[RM_UNROLL];
 #pragma unroll
     for (int u = 0; u < RM_UNROLL; ++u) {
       const int i = min(i0 + u, g.D - 1);              // tail: a repeated sample, masked below
       c[u] = locate(l, (float)i, g);
-      d[u] = (liquid || i0 + u < i_lo || i0 + u > i_hi) ? 0.f : sample_cell(vol, c[u], g);
+      lv[u] = i0 + u >= i_lo && i0 + u <= i_hi;
     }
 #pragma unroll
     for (int u = 0; u < RM_UNROLL; ++u) {
-      const bool live = i0 + u >= i_lo && i0 + u <= i_hi;
+      cont[u] = false;
+      if (!liquid && lv[u]) {
+        const float* p = vol + c[u].idx;
+        const int ip = (u == 0) ? idx_prev : (lv[u - 1] ? c[u - 1].idx : LNST_NO_CELL);
+        cont[u] = c[u].idx == ip + g.HW;
+        hi[u] = load_plane(p + g.HW, g.W);
+        if (!cont[u]) lo[u] = load_plane(p, g.W);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < RM_UNROLL; ++u) {
+      d[u] = 0.f;
+      if (!liquid && lv[u]) {
+        if (cont[u]) lo[u] = (u == 0) ? far_prev : hi[u - 1];
+        d[u] = lerp_planes(lo[u], hi[u], c[u]);
+      }
+    }
+    if (!liquid) {
+      far_prev = hi[RM_UNROLL - 1];
+      idx_prev = lv[RM_UNROLL - 1] ? c[RM_UNROLL - 1].idx : LNST_NO_CELL;
+    }
+#pragma unroll
+    for (int u = 0; u < RM_UNROLL; ++u) {
+      const bool live = lv[u];
       float gk;
       if (liquid) {
         gk = gl;
@@ -457,7 +535,33 @@ __global__ void __launch_bounds__(128) raymarch_rot_bwd_k(const float* __restric
       float c000 = g00 - c001, c010 = g01 - c011, c100 = g10 - c101, c110 = g11 - c111;
       float* p = g_vol + c[u].idx;
       float* q = p + g.HW;
-      if (MERGE) {
+      if (carry) {
+        // the plane waiting in pend: merge it into this sample's near plane, or write it out
+        if (pend_idx >= 0) {
+          if (live && pend_idx == c[u].idx) {
+            c000 += pend.a; c001 += pend.b; c010 += pend.c; c011 += pend.d;
+          } else {
+            float* f = g_vol + pend_idx;
+            atomicAdd(f, pend.a); atomicAdd(f + 1, pend.b); atomicAdd(f + g.W, pend.c); atomicAdd(f + g.W + 1, pend.d);
+          }
+          pend_idx = -1;
+        }
+        bool give = false;
+        if (MERGE) {                                   // near plane only: the far plane is merged when it is written
+          const int my = live ? c[u].idx : -2;
+          const int nb = __shfl_down_sync(0xffffffffu, my, 1);
+          give = lane < 31 && my >= 0 && nb == my + 1;
+          const float r00 = __shfl_up_sync(0xffffffffu, give ? c001 : 0.f, 1);
+          const float r01 = __shfl_up_sync(0xffffffffu, give ? c011 : 0.f, 1);
+          if (lane > 0) { c000 += r00; c010 += r01; }
+        }
+        if (live) {
+          atomicAdd(p, c000); atomicAdd(p + g.W, c010);
+          if (!give) { atomicAdd(p + 1, c001); atomicAdd(p + g.W + 1, c011); }
+          pend.a = c100; pend.b = c101; pend.c = c110; pend.d = c111;
+          pend_idx = c[u].idx + g.HW;
+        }
+      } else if (MERGE) {
         const int my = live ? c[u].idx : -2;
         const int nb = __shfl_down_sync(0xffffffffu, my, 1);
         const bool give = lane < 31 && my >= 0 && nb == my + 1;
@@ -477,6 +581,10 @@ __global__ void __launch_bounds__(128) raymarch_rot_bwd_k(const float* __restric
         atomicAdd(q, c100); atomicAdd(q + 1, c101); atomicAdd(q + g.W, c110); atomicAdd(q + g.W + 1, c111);
       }
     }
+  }
+  if (pend_idx >= 0) {
+    float* f = g_vol + pend_idx;
+    atomicAdd(f, pend.a); atomicAdd(f + 1, pend.b); atomicAdd(f + g.W, pend.c); atomicAdd(f + g.W + 1, pend.d);
   }
 }
 
