@@ -47,7 +47,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "{\n\t"
       ".reg .pred P1;\n\t"
       "LAB_WAIT:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, 0x989680;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
       "@P1 bra DONE;\n\t"
       "bra LAB_WAIT;\n\t"
       "DONE:\n\t"
@@ -172,6 +172,7 @@ struct ConvShape {
   int taps;      // 9: 3x3 convolution; 1: per-pixel GEMM (Gram gradient F x G)
   int w_img;     // 1: third coordinate of the weight map is the image index (per-image B matrix)
   float scale;   // multiplies the accumulator before addend / bias
+  int dbg;       // EXPERIMENT flags
 };
 
 // y = mask( relu?( scale * (X (*) W) + addend + bias ) )
@@ -345,6 +346,40 @@ conv3x3_tc_k(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ 
 // complete.
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+// Coalesced write-out of a warp's 32 accumulator rows (NV x 16 B each).  A thread owns one pixel row, so a plain
+// per-thread store makes every warp-wide instruction touch 32 different lines with 16 B each: the LSU
+// serialises them and the N = 128 epilogues took longer than their tile's MMAs (tools/convdbg.py: conv2_1
+// 41 us without the stores, 80 us with them).  Rows go through a swizzled per-warp staging buffer instead and
+// come back out so that NV consecutive lanes write one row: every instruction covers whole 64/128-byte runs.
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+// position of 16-byte piece j inside row `row`: every 8 lanes of a warp-wide access hit 8 different bank groups
+template <int NV>
+__device__ __forceinline__ uint32_t rows_swz(int j, int row) {
+  return NV == 8 ? (uint32_t)((j ^ row) & 7) : (uint32_t)((j + (row >> 1)) & 3);
+}
+template <int NV, class RowPtr>
+__device__ __forceinline__ void warp_rows_store(uint32_t stage, int lane, const uint4 (&ov)[NV], RowPtr rowptr) {
+  constexpr int RPI = 32 / NV;                         // rows per store instruction
+#pragma unroll
+  for (int j = 0; j < NV; ++j) st_shared_v4(stage + lane * (NV * 16) + (rows_swz<NV>(j, lane) << 4), ov[j]);
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int row = i * RPI + lane / NV, cj = lane % NV;
+    const uint4 v = ld_shared_v4(stage + row * (NV * 16) + (rows_swz<NV>(cj, row) << 4));
+    __nv_bfloat16* dst = rowptr(row);
+    if (dst) *reinterpret_cast<uint4*>(dst + cj * 8) = v;
+  }
+  __syncwarp();
 }
 
 template <int BLOCK_N>
@@ -584,19 +619,27 @@ struct HaloCfg {
   int n_blocks_n, n_tiles;
 };
 
-template <int BLOCK_N, bool OUT3>
+template <int BLOCK_N> struct HaloAcc { static constexpr int value = (BLOCK_N >= 128) ? 4 : 8; };
+// store staging: 128-byte row chunks (8 x 16 B) for the wide tiles, 64-byte ones where shared memory is tight
+template <int BLOCK_N> struct HaloStage { static constexpr int nv = 4; static constexpr int bytes = (BLOCK_N >= 128) ? 4 * nv * 512 : 0; };
+
+template <int BLOCK_N, bool OUT3, bool RES>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv3x3_halo_k(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                const float* __restrict__ bias, const __nv_bfloat16* __restrict__ mask,
                __nv_bfloat16* __restrict__ y, float* __restrict__ y3, ConvShape s, HaloCfg cfg) {
   constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
-  constexpr int TCOLS = (2 * BLOCK_N < 32) ? 32 : 2 * BLOCK_N;
+  // accumulator ring in TMEM: the round trip MMA-complete -> tfull -> epilogue -> tempty -> next MMA costs about
+  // 4000 cycles (measured: with two buffers every tile took >= 2000 cycles even with 1/9 of the MMAs and no
+  // epilogue work), longer than a whole tile's MMAs at BLOCK_N <= 128, so all 512 columns are used as a ring
+  constexpr int NACC = HaloAcc<BLOCK_N>::value;
+  constexpr int TCOLS = NACC * BLOCK_N;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(16) float sbias[512];              // the layer's bias, read as broadcast float4s
   if (bias)
     for (int i = threadIdx.x; i < s.Cout && i < 512; i += blockDim.x) sbias[i] = bias[i];
   const int kchunks = s.Cin / BLOCK_K;
-  const bool resident = cfg.sb == 0;
+  constexpr bool resident = RES;                        // weights resident in smem (cfg.sb == 0) or streamed
   const int n_wslots = resident ? 9 * kchunks : cfg.sb;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t smem_a = base;
@@ -604,8 +647,9 @@ conv3x3_halo_k(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
   const uint32_t bars = smem_b + n_wslots * B_BYTES;
   const uint32_t bar_afull = bars, bar_aempty = bars + 8 * cfg.sa;
   const uint32_t bar_bfull = bar_aempty + 8 * cfg.sa, bar_bempty = bar_bfull + 8 * (resident ? 1 : cfg.sb);
-  const uint32_t bar_tfull = bar_bempty + 8 * (resident ? 1 : cfg.sb), bar_tempty = bar_tfull + 16;
-  const uint32_t tmem_slot = bar_tempty + 16;
+  const uint32_t bar_tfull = bar_bempty + 8 * (resident ? 1 : cfg.sb), bar_tempty = bar_tfull + 8 * NACC;
+  const uint32_t tmem_slot = bar_tempty + 8 * NACC;
+  const uint32_t stage_base = (tmem_slot + 16 + 127u) & ~127u;   // 4 epilogue warps x 4 KiB (warp_rows_store)
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -616,8 +660,7 @@ conv3x3_halo_k(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     prefetch_tmap(&map_w);
     for (int i = 0; i < cfg.sa; ++i) { mbar_init(bar_afull + 8 * i, 1); mbar_init(bar_aempty + 8 * i, 1); }
     for (int i = 0; i < (resident ? 1 : cfg.sb); ++i) { mbar_init(bar_bfull + 8 * i, 1); mbar_init(bar_bempty + 8 * i, 1); }
-    mbar_init(bar_tfull, 1); mbar_init(bar_tfull + 8, 1);
-    mbar_init(bar_tempty, 4); mbar_init(bar_tempty + 8, 4);
+    for (int i = 0; i < NACC; ++i) { mbar_init(bar_tfull + 8 * i, 1); mbar_init(bar_tempty + 8 * i, 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -647,8 +690,13 @@ conv3x3_halo_k(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
       for (int c = 0; c < kchunks; ++c) {
         mbar_wait(bar_aempty + 8 * sta, pha ^ 1);
         if (leader) {
+          if (s.dbg & 16) {
+            mbar_arrive(bar_afull + 8 * sta);
+          } else {
           mbar_expect_tx(bar_afull + 8 * sta, PATCH_BYTES);
-          tma_load_4d(smem_a + sta * PATCH_STRIDE, &map_x, bar_afull + 8 * sta, c * BLOCK_K, w0 - 1, h0 - 1, img);
+          tma_load_4d(smem_a + sta * PATCH_STRIDE, &map_x, bar_afull + 8 * sta, c * BLOCK_K, (s.dbg & 2) ? 0 : w0 - 1,
+                      (s.dbg & 2) ? 0 : h0 - 1, (s.dbg & 2) ? 0 : img);
+          }
         }
         if (++sta == (uint32_t)cfg.sa) { sta = 0; pha ^= 1; }
         if (!resident) {
@@ -669,13 +717,12 @@ conv3x3_halo_k(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     const uint32_t idesc = umma_idesc_bf16(BLOCK_M, BLOCK_N);
     const uint32_t ahi = desc_hi_sw128((HTW + 2) * 128), bhi = desc_hi_sw128(1024);
     const uint32_t alo_base = desc_lo(smem_a, 16), blo_base = desc_lo(smem_b, 16);
-    uint32_t sta = 0, pha = 0, stb = 0, phb = 0, lt = 0;
+    uint32_t sta = 0, pha = 0, stb = 0, phb = 0, buf = 0, bph = 0;
     if (resident) {
       mbar_wait(bar_bfull, 0);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     }
-    for (int t = blockIdx.x; t < cfg.n_tiles; t += gridDim.x, ++lt) {
-      const uint32_t buf = lt & 1, bph = (lt >> 1) & 1;
+    for (int t = blockIdx.x; t < cfg.n_tiles; t += gridDim.x) {
       mbar_wait(bar_tempty + 8 * buf, bph ^ 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t acc = tmem_d + buf * BLOCK_N;
@@ -683,27 +730,38 @@ conv3x3_halo_k(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         mbar_wait(bar_afull + 8 * sta, pha);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t alo0 = alo_base + sta * (PATCH_STRIDE >> 4);
-        uint32_t blo_res = blo_base + c * (B_BYTES >> 4);               // resident: slot tap * kchunks + c
+        if (resident) {
+          // one straight-line block of 36 MMAs per chunk: the issuing warp is alone on its scheduler, every
+          // instruction costs it ~4-5 cycles, and a tile's MMAs only take 32-64 cycles each -- the per-tap
+          // branches and barrier bookkeeping of the streamed path (~50 instructions per tap) capped the
+          // kernel at ~2000 cycles per chunk whatever the MMA count (tools/convdbg.py)
+          if (leader && !(s.dbg & 4)) {
+            const uint32_t bstep = (uint32_t)kchunks * (B_BYTES >> 4);
+            uint32_t blo = blo_base + c * (B_BYTES >> 4);             // slot tap * kchunks + c
 #pragma unroll
-        for (int tap = 0; tap < 9; ++tap) {
-          const int ky = tap / 3, kx = tap - 3 * ky;                 // compile-time after unrolling
-          uint32_t blo;
-          if (resident) {
-            blo = blo_res;
-            blo_res += kchunks * (B_BYTES >> 4);
-          } else {
+            for (int tap = 0; tap < 9; ++tap) {
+              const int ky = tap / 3, kx = tap - 3 * ky;               // compile-time after unrolling
+              const uint32_t alo = alo0 + ((ky * (HTW + 2) + kx) * 128 >> 4);
+#pragma unroll
+              for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+                umma_bf16_lh(acc, alo + k * 2, ahi, blo + k * 2, bhi, idesc, (tap | k) != 0 ? 1u : (c != 0 ? 1u : 0u));
+              blo += bstep;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap) {
+            const int ky = tap / 3, kx = tap - 3 * ky;
             mbar_wait(bar_bfull + 8 * stb, phb);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            blo = blo_base + stb * (B_BYTES >> 4);
-          }
-          const uint32_t alo = alo0 + ((ky * (HTW + 2) + kx) * 128 >> 4);
-          if (leader) {
+            const uint32_t blo = blo_base + stb * (B_BYTES >> 4);
+            const uint32_t alo = alo0 + ((ky * (HTW + 2) + kx) * 128 >> 4);
+            if (leader) {
 #pragma unroll
-            for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-              umma_bf16_lh(acc, alo + k * 2, ahi, blo + k * 2, bhi, idesc, (c | tap | k) != 0 ? 1u : 0u);
-          }
-          if (!resident) {
-            if (leader) umma_commit(bar_bempty + 8 * stb);
+              for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+                umma_bf16_lh(acc, alo + k * 2, ahi, blo + k * 2, bhi, idesc, (c | tap | k) != 0 ? 1u : 0u);
+              umma_commit(bar_bempty + 8 * stb);
+            }
             if (++stb == (uint32_t)cfg.sb) { stb = 0; phb ^= 1; }
           }
         }
@@ -711,13 +769,14 @@ conv3x3_halo_k(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         if (++sta == (uint32_t)cfg.sa) { sta = 0; pha ^= 1; }
       }
       if (leader) umma_commit(bar_tfull + 8 * buf);
+      if (++buf == NACC) { buf = 0; bph ^= 1; }
     }
   } else {
     // ===== epilogue: warps 2..5, TMEM sub-partition = warp % 4 =====
     const int q = warp & 3;
     const int r = q * 32 + lane;
-    uint32_t lt = 0;
-    for (int t = blockIdx.x; t < cfg.n_tiles; t += gridDim.x, ++lt) {
+    uint32_t buf = 0, bph = 0;
+    for (int t = blockIdx.x; t < cfg.n_tiles; t += gridDim.x) {
       const int nb = t % cfg.n_blocks_n, sp = t / cfg.n_blocks_n;
       const int img = sp / tiles_sp, rem = sp - img * tiles_sp;
       const int th = rem / s.tiles_w, tw = rem - th * s.tiles_w;
@@ -725,7 +784,6 @@ conv3x3_halo_k(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
       const int ph_ = th * HTH + (r >> 3), pw_ = tw * HTW + (r & 7);
       const bool valid = ph_ < s.H && pw_ < s.W;
       const int64_t pix = ((int64_t)img * s.H + ph_) * s.W + pw_;
-      const uint32_t buf = lt & 1, bph = (lt >> 1) & 1;
       const uint32_t acc = tmem_d + buf * BLOCK_N + ((uint32_t)(q * 32) << 16);
       if (OUT3) {
         mbar_wait(bar_tfull + 8 * buf, bph);
@@ -766,38 +824,55 @@ conv3x3_halo_k(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         // whole accumulator row into registers (1 CTA/SM: registers are plentiful), then hand the TMEM
         // buffer straight back: the MMAs of the tile after next never wait for this tile's stores
         uint32_t v[NCH * 32];
+        if (!(s.dbg & 8)) {
 #pragma unroll
         for (int c = 0; c < NCH; ++c) tmem_ld32_nowait(acc + (uint32_t)(c * 32), v + c * 32);
         tmem_ld_wait();
+        }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
-        if (valid) {
-          __nv_bfloat16* dst = y + pix * s.Cout + n0;
+        if (!(s.dbg & 8)) {
+          constexpr int NV = HaloStage<BLOCK_N>::nv;                 // 16-byte pieces per staged row chunk
+          constexpr int NCK = (BLOCK_N >= NV * 8) ? BLOCK_N / (NV * 8) : 1;
 #pragma unroll
-          for (int c = 0; c < NCH; ++c) {
-            uint4 ov[4];
+          for (int ck = 0; ck < NCK; ++ck) {
+            uint4 ov[NV];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&ov[j]);
-              const float4 b0 = bias ? *reinterpret_cast<const float4*>(sbias + n0 + c * 32 + j * 8) : make_float4(0, 0, 0, 0);
-              const float4 b1 = bias ? *reinterpret_cast<const float4*>(sbias + n0 + c * 32 + j * 8 + 4) : make_float4(0, 0, 0, 0);
+            for (int jj = 0; jj < NV; ++jj) {
+              const int col = ck * NV * 8 + jj * 8;                  // first of 8 accumulator columns
+              const int c = col >> 5, j = (col >> 3) & 3;            // TMEM chunk of 32 columns, 8-column group
+              __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&ov[jj]);
+              const float4 b0 = bias ? *reinterpret_cast<const float4*>(sbias + n0 + col) : make_float4(0, 0, 0, 0);
+              const float4 b1 = bias ? *reinterpret_cast<const float4*>(sbias + n0 + col + 4) : make_float4(0, 0, 0, 0);
               const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
               for (int e = 0; e < 8; e += 2) {
-                float f0 = fmaf(__uint_as_float(v[c * 32 + j * 8 + e]), s.scale, bb[e]);
-                float f1 = fmaf(__uint_as_float(v[c * 32 + j * 8 + e + 1]), s.scale, bb[e + 1]);
+                float f0 = fmaf(__uint_as_float(v[col + e]), s.scale, bb[e]);
+                float f1 = fmaf(__uint_as_float(v[col + e + 1]), s.scale, bb[e + 1]);
                 if (s.relu) { f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); }
                 if (!((mbits[c] >> (j * 8 + e)) & 1u)) f0 = 0.f;
                 if (!((mbits[c] >> (j * 8 + e + 1)) & 1u)) f1 = 0.f;
                 oh[e >> 1] = __floats2bfloat162_rn(f0, f1);
               }
             }
+            if (BLOCK_N < 128) {                                     // narrow tiles: the direct stores keep up with the MMAs
+              if (valid && !(s.dbg & 1)) {
+                __nv_bfloat16* dst = y + pix * s.Cout + n0 + ck * NV * 8;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(dst + c * 32 + j * 8) = ov[j];
+                for (int jj = 0; jj < NV; ++jj) *reinterpret_cast<uint4*>(dst + jj * 8) = ov[jj];
+              }
+            } else if (!(s.dbg & 1))
+              warp_rows_store<NV>(stage_base + (uint32_t)q * (NV * 512u), lane, ov, [&](int row) -> __nv_bfloat16* {
+                const int rr = q * 32 + row;
+                const int ph2 = th * HTH + (rr >> 3), pw2 = tw * HTW + (rr & 7);
+                if (ph2 >= s.H || pw2 >= s.W) return nullptr;
+                return y + (((int64_t)img * s.H + ph2) * s.W + pw2) * s.Cout + n0 + ck * NV * 8;
+              });
           }
         }
       }
+      if (++buf == NACC) { buf = 0; bph ^= 1; }
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -1100,9 +1175,9 @@ static int launch_halo(const void* x, const void* wmat, const float* bias, const
                        cudaStream_t stream) {
   constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
   constexpr int MAX_SMEM = 232448;                        // 227 KiB opt-in limit per CTA
-  const int budget = MAX_SMEM - 2048 - 1024 - 512;          // static bias table, alignment slack, barriers
+  const int budget = MAX_SMEM - 2048 - 1024 - 512 - HaloStage<BLOCK_N>::bytes - 128;   // static bias table, alignment slack, barriers, store staging
   ConvShape s;
-  s.H = H; s.W = W; s.Cin = Cin; s.Cout = Cout; s.relu = relu; s.taps = 9; s.w_img = 0; s.scale = scale;
+  s.H = H; s.W = W; s.Cin = Cin; s.Cout = Cout; s.relu = relu; s.taps = 9; s.w_img = 0; s.scale = scale; s.dbg = conv_halo >> 8;
   s.TH = HTH; s.TW = HTW;
   s.tiles_w = (W + HTW - 1) / HTW;
   s.tiles_h = (H + HTH - 1) / HTH;
@@ -1121,7 +1196,7 @@ static int launch_halo(const void* x, const void* wmat, const float* bias, const
   if (cfg.sa > 6) cfg.sa = 6;
   if (cfg.sa < 2) return LNST_EARG;
   const int n_wslots = cfg.sb == 0 ? 9 * kchunks : cfg.sb;
-  const int smem = cfg.sa * PATCH_STRIDE + n_wslots * B_BYTES + 8 * (2 * cfg.sa + 2 * (cfg.sb ? cfg.sb : 1) + 4) + 16 + 1024;
+  const int smem = cfg.sa * PATCH_STRIDE + n_wslots * B_BYTES + 8 * (2 * cfg.sa + 2 * (cfg.sb ? cfg.sb : 1) + 16) + 16 + 1024 + HaloStage<BLOCK_N>::bytes + 128;
   CUtensorMap mx, mw;
   {
     const cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n};
@@ -1139,8 +1214,11 @@ static int launch_halo(const void* x, const void* wmat, const float* bias, const
   static bool configured = false;
   static int sms = 148;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv3x3_halo_k<BLOCK_N, OUT3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(conv3x3_halo_k<BLOCK_N, OUT3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          MAX_SMEM - 2048);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(conv3x3_halo_k<BLOCK_N, OUT3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             MAX_SMEM - 2048);
     if (e != cudaSuccess) return (int)e;
     int dev = 0;
     cudaGetDevice(&dev);
@@ -1148,7 +1226,10 @@ static int launch_halo(const void* x, const void* wmat, const float* bias, const
     configured = true;
   }
   const int grid = cfg.n_tiles < sms ? cfg.n_tiles : sms;
-  conv3x3_halo_k<BLOCK_N, OUT3><<<grid, NUM_THREADS, smem, stream>>>(mx, mw, bias, mask, y, y3, s, cfg);
+  if (cfg.sb == 0)
+    conv3x3_halo_k<BLOCK_N, OUT3, true><<<grid, NUM_THREADS, smem, stream>>>(mx, mw, bias, mask, y, y3, s, cfg);
+  else
+    conv3x3_halo_k<BLOCK_N, OUT3, false><<<grid, NUM_THREADS, smem, stream>>>(mx, mw, bias, mask, y, y3, s, cfg);
   return (int)cudaGetLastError();
 }
 
@@ -1434,8 +1515,8 @@ static int run_tc_gemm(const void* x, const void* wmat, const float* bias, const
   // beside >= 3 patch stages: conv1_2, conv2_1 and their data gradients); with streamed weights the
   // per-tap kernels are faster (measured, tools/convbench.py), so those layers keep them.
   const int bn_ = (Cout % 128 == 0) ? 128 : 64;
-  const bool resident = (Cout == bn_) && (9 * (Cin / 64) * bn_ * 128 + 3 * PATCH_STRIDE <= 232448 - 2048 - 1024 - 512);
-  if (taps == 9 && !w_img && !addend && conv_halo && (resident || conv_halo == 2)) {
+  const bool resident = (Cout == bn_) && (9 * (Cin / 64) * bn_ * 128 + 3 * PATCH_STRIDE <= 232448 - 2048 - 1024 - 512 - (bn_ >= 128 ? 8192 : 0) - 128);
+  if (taps == 9 && !w_img && !addend && (conv_halo & 0xff) && (resident || (conv_halo & 0xff) == 2)) {
     if (Cout % 128 == 0)
       return launch_halo<128, false>(x, wmat, bias, (const __nv_bfloat16*)mask, (__nv_bfloat16*)y, nullptr, n, H, W,
                                      Cin, Cout, relu, scale, lnst_stream(stream));
@@ -1444,7 +1525,7 @@ static int run_tc_gemm(const void* x, const void* wmat, const float* bias, const
   }
   ConvShape s;
   s.H = H; s.W = W; s.Cin = Cin; s.Cout = Cout; s.relu = relu;
-  s.taps = taps; s.w_img = w_img; s.scale = scale;
+  s.taps = taps; s.w_img = w_img; s.scale = scale; s.dbg = 0;
   pick_tile(H, W, s.TH, s.TW);
   s.tiles_w = (W + s.TW - 1) / s.TW;
   s.tiles_h = (H + s.TH - 1) / s.TH;
