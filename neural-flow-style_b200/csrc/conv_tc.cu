@@ -172,7 +172,6 @@ struct ConvShape {
   int taps;      // 9: 3x3 convolution; 1: per-pixel GEMM (Gram gradient F x G)
   int w_img;     // 1: third coordinate of the weight map is the image index (per-image B matrix)
   float scale;   // multiplies the accumulator before addend / bias
-  int dbg;       // EXPERIMENT flags
 };
 
 // y = mask( relu?( scale * (X (*) W) + addend + bias ) )
@@ -350,7 +349,7 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 
 // Coalesced write-out of a warp's 32 accumulator rows (NV x 16 B each).  A thread owns one pixel row, so a plain
 // per-thread store makes every warp-wide instruction touch 32 different lines with 16 B each: the LSU
-// serialises them and the N = 128 epilogues took longer than their tile's MMAs (tools/convdbg.py: conv2_1
+// serialises them and the N = 128 epilogues took longer than their tile's MMAs (knock-out experiments, DESIGN.md section 4: conv2_1
 // 41 us without the stores, 80 us with them).  Rows go through a swizzled per-warp staging buffer instead and
 // come back out so that NV consecutive lanes write one row: every instruction covers whole 64/128-byte runs.
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, const uint4& v) {
@@ -690,13 +689,8 @@ conv3x3_halo_k(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
       for (int c = 0; c < kchunks; ++c) {
         mbar_wait(bar_aempty + 8 * sta, pha ^ 1);
         if (leader) {
-          if (s.dbg & 16) {
-            mbar_arrive(bar_afull + 8 * sta);
-          } else {
           mbar_expect_tx(bar_afull + 8 * sta, PATCH_BYTES);
-          tma_load_4d(smem_a + sta * PATCH_STRIDE, &map_x, bar_afull + 8 * sta, c * BLOCK_K, (s.dbg & 2) ? 0 : w0 - 1,
-                      (s.dbg & 2) ? 0 : h0 - 1, (s.dbg & 2) ? 0 : img);
-          }
+          tma_load_4d(smem_a + sta * PATCH_STRIDE, &map_x, bar_afull + 8 * sta, c * BLOCK_K, w0 - 1, h0 - 1, img);
         }
         if (++sta == (uint32_t)cfg.sa) { sta = 0; pha ^= 1; }
         if (!resident) {
@@ -734,8 +728,8 @@ conv3x3_halo_k(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
           // one straight-line block of 36 MMAs per chunk: the issuing warp is alone on its scheduler, every
           // instruction costs it ~4-5 cycles, and a tile's MMAs only take 32-64 cycles each -- the per-tap
           // branches and barrier bookkeeping of the streamed path (~50 instructions per tap) capped the
-          // kernel at ~2000 cycles per chunk whatever the MMA count (tools/convdbg.py)
-          if (leader && !(s.dbg & 4)) {
+          // kernel at ~2000 cycles per chunk whatever the MMA count (knock-out experiments)
+          if (leader) {
             const uint32_t bstep = (uint32_t)kchunks * (B_BYTES >> 4);
             uint32_t blo = blo_base + c * (B_BYTES >> 4);             // slot tap * kchunks + c
 #pragma unroll
@@ -824,15 +818,13 @@ conv3x3_halo_k(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         // whole accumulator row into registers (1 CTA/SM: registers are plentiful), then hand the TMEM
         // buffer straight back: the MMAs of the tile after next never wait for this tile's stores
         uint32_t v[NCH * 32];
-        if (!(s.dbg & 8)) {
 #pragma unroll
         for (int c = 0; c < NCH; ++c) tmem_ld32_nowait(acc + (uint32_t)(c * 32), v + c * 32);
         tmem_ld_wait();
-        }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
-        if (!(s.dbg & 8)) {
+        {
           constexpr int NV = HaloStage<BLOCK_N>::nv;                 // 16-byte pieces per staged row chunk
           constexpr int NCK = (BLOCK_N >= NV * 8) ? BLOCK_N / (NV * 8) : 1;
 #pragma unroll
@@ -857,12 +849,12 @@ conv3x3_halo_k(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
               }
             }
             if (BLOCK_N < 128) {                                     // narrow tiles: the direct stores keep up with the MMAs
-              if (valid && !(s.dbg & 1)) {
+              if (valid) {
                 __nv_bfloat16* dst = y + pix * s.Cout + n0 + ck * NV * 8;
 #pragma unroll
                 for (int jj = 0; jj < NV; ++jj) *reinterpret_cast<uint4*>(dst + jj * 8) = ov[jj];
               }
-            } else if (!(s.dbg & 1))
+            } else
               warp_rows_store<NV>(stage_base + (uint32_t)q * (NV * 512u), lane, ov, [&](int row) -> __nv_bfloat16* {
                 const int rr = q * 32 + row;
                 const int ph2 = th * HTH + (rr >> 3), pw2 = tw * HTW + (rr & 7);
@@ -1177,7 +1169,7 @@ static int launch_halo(const void* x, const void* wmat, const float* bias, const
   constexpr int MAX_SMEM = 232448;                        // 227 KiB opt-in limit per CTA
   const int budget = MAX_SMEM - 2048 - 1024 - 512 - HaloStage<BLOCK_N>::bytes - 128;   // static bias table, alignment slack, barriers, store staging
   ConvShape s;
-  s.H = H; s.W = W; s.Cin = Cin; s.Cout = Cout; s.relu = relu; s.taps = 9; s.w_img = 0; s.scale = scale; s.dbg = conv_halo >> 8;
+  s.H = H; s.W = W; s.Cin = Cin; s.Cout = Cout; s.relu = relu; s.taps = 9; s.w_img = 0; s.scale = scale;
   s.TH = HTH; s.TW = HTW;
   s.tiles_w = (W + HTW - 1) / HTW;
   s.tiles_h = (H + HTH - 1) / HTH;
@@ -1516,7 +1508,7 @@ static int run_tc_gemm(const void* x, const void* wmat, const float* bias, const
   // per-tap kernels are faster (measured, tools/convbench.py), so those layers keep them.
   const int bn_ = (Cout % 128 == 0) ? 128 : 64;
   const bool resident = (Cout == bn_) && (9 * (Cin / 64) * bn_ * 128 + 3 * PATCH_STRIDE <= 232448 - 2048 - 1024 - 512 - (bn_ >= 128 ? 8192 : 0) - 128);
-  if (taps == 9 && !w_img && !addend && (conv_halo & 0xff) && (resident || (conv_halo & 0xff) == 2)) {
+  if (taps == 9 && !w_img && !addend && conv_halo && (resident || conv_halo == 2)) {
     if (Cout % 128 == 0)
       return launch_halo<128, false>(x, wmat, bias, (const __nv_bfloat16*)mask, (__nv_bfloat16*)y, nullptr, n, H, W,
                                      Cin, Cout, relu, scale, lnst_stream(stream));
@@ -1525,7 +1517,7 @@ static int run_tc_gemm(const void* x, const void* wmat, const float* bias, const
   }
   ConvShape s;
   s.H = H; s.W = W; s.Cin = Cin; s.Cout = Cout; s.relu = relu;
-  s.taps = taps; s.w_img = w_img; s.scale = scale; s.dbg = 0;
+  s.taps = taps; s.w_img = w_img; s.scale = scale;
   pick_tile(H, W, s.TH, s.TW);
   s.tiles_w = (W + s.TW - 1) / s.TW;
   s.tiles_h = (H + s.TH - 1) / s.TH;
