@@ -233,11 +233,15 @@ def run_engine(args):
     adam = _Adam()
     lr = cfg.lr
 
+    view_sequential = cfg.rotate and cfg.view_mode == 'sequential'
     runner = styler.step_runner(fr, g_opt, adam, ws, grams, lr)   # eager once, then one CUDA graph per step
+
+    styler.fuse_apply = True                             # g_opt += delta inside the fused Adam/iterate kernel
 
     def step():
         var, loss, delta = runner()
-        ops.axpy(g_opt, delta, 1.0)
+        if view_sequential:
+            ops.axpy(g_opt, delta, 1.0)
         return loss
 
     def barrier():

@@ -257,6 +257,12 @@ int lnst_adam_step(float* var, const float* grad, float* m, float* v, int64_t n,
  * lr*sqrt(1-beta2^t)/(1-beta1^t) in fp32, applies the update, then advances the powers. */
 int lnst_adam_step_dev(float* var, const float* grad, float* m, float* v, int64_t n, float* state, float lr,
                        float beta1, float beta2, float eps, float gscale, void* stream);
+/* A whole single-Adam-step iteration of one frame (styler_3p.py:312,331,359-363,385-386) in one pass:
+ * var = g_opt; ApplyAdam(var, grad*gscale) with the device-resident step counter `state`; var_out = var;
+ * delta = (nan_to_num(var) - g_opt) * (mask ? mask[(i/width)*mask_stride] : 1); apply != 0: g_opt += delta. */
+int lnst_adam_iterate_dev(float* g_opt, const float* grad, float* m, float* v, int64_t n, float* state, float lr,
+                          float beta1, float beta2, float eps, float gscale, const float* mask, int32_t width,
+                          int32_t mask_stride, float* var_out, float* delta, int32_t apply, void* stream);
 /* acc = (first ? 0 : acc) + nan_to_num(var) */
 int lnst_iterate_accumulate(float* acc, const float* var, int64_t n, int32_t first, void* stream);
 /* delta[i] = (nan_to_num(g_new[i]*scale) - g_opt[i]) * (mask ? mask[(i/width)*mask_stride] : 1) */

@@ -47,6 +47,31 @@ __global__ void adam_step_dev_k(float* __restrict__ var, const float* __restrict
   var[i] = var[i] - lr_t * mi / (sqrtf(vi) + eps);
 }
 
+// One iteration of a frame with a single Adam step (no views, or the mean-gradient view mode), fused:
+// var <- g_opt (styler_3p.py:312), ApplyAdam, delta = (nan_to_num(var) - g_opt) [* mask] (:359-363) and, when
+// no temporal filter runs between them, g_opt += delta (:385-386).  One pass over N*c elements instead of four.
+__global__ void adam_iterate_dev_k(float* __restrict__ g_opt, const float* __restrict__ grad, float* __restrict__ m,
+                                   float* __restrict__ v, int64_t n, const float* __restrict__ state, float b1,
+                                   float b2, float eps, float gscale, const float* __restrict__ mask, int width,
+                                   int mask_stride, float* __restrict__ var_out, float* __restrict__ delta,
+                                   int apply) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float lr_t = state[2];
+  const float x = g_opt[i];
+  const float g = grad[i] * gscale;
+  const float mi = m[i] + (g - m[i]) * (1.f - b1);
+  const float vi = v[i] + (g * g - v[i]) * (1.f - b2);
+  m[i] = mi;
+  v[i] = vi;
+  const float var = x - lr_t * mi / (sqrtf(vi) + eps);
+  var_out[i] = var;
+  float d = lnst_nan_to_num(var) - x;
+  if (mask) d *= mask[(i / width) * mask_stride];
+  delta[i] = d;
+  if (apply) g_opt[i] = x + d;
+}
+
 __global__ void iterate_accumulate_k(float* __restrict__ acc, const float* __restrict__ var, int64_t n, int first) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -169,6 +194,19 @@ extern "C" int lnst_adam_step_dev(float* var, const float* grad, float* m, float
   if (n > 0)
     LNST_LAUNCH(adam_step_dev_k, dim3(lnst_blocks(n, 256)), dim3(256), 0, lnst_stream(stream), var, grad, m, v, n,
                 (const float*)state, beta1, beta2, eps, gscale);
+  return lnst_status();
+}
+
+extern "C" int lnst_adam_iterate_dev(float* g_opt, const float* grad, float* m, float* v, int64_t n, float* state,
+                                     float lr, float beta1, float beta2, float eps, float gscale, const float* mask,
+                                     int32_t width, int32_t mask_stride, float* var_out, float* delta, int32_t apply,
+                                     void* stream) {
+  if (!g_opt || !grad || !m || !v || !state || !var_out || !delta || n < 0 || width < 1) return LNST_EARG;
+  LNST_LAUNCH(adam_tick_k, dim3(1), dim3(32), 0, lnst_stream(stream), state, lr, beta1, beta2);
+  if (n > 0)
+    LNST_LAUNCH(adam_iterate_dev_k, dim3(lnst_blocks(n, 256)), dim3(256), 0, lnst_stream(stream), g_opt, grad, m, v,
+                n, (const float*)state, beta1, beta2, eps, gscale, mask, (int)width, (int)mask_stride, var_out, delta,
+                (int)apply);
   return lnst_status();
 }
 

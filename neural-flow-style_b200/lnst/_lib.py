@@ -72,6 +72,7 @@ SIGNATURES = {
     'lnst_tv_loss': [vp, i32, i32, i32, f32, vp, vp, vp],
     'lnst_adam_step': [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, vp],
     'lnst_adam_step_dev': [vp, vp, vp, vp, i64, vp, f32, f32, f32, f32, f32, vp],
+    'lnst_adam_iterate_dev': [vp, vp, vp, vp, i64, vp, f32, f32, f32, f32, f32, vp, i32, i32, vp, vp, i32, vp],
     'lnst_iterate_accumulate': [vp, vp, i64, i32, vp],
     'lnst_iterate_delta': [vp, f32, vp, vp, i32, i32, i64, vp, vp],
     'lnst_masked_accumulate': [vp, vp, vp, i32, i32, f32, vp, i64, vp],

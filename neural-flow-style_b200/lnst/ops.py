@@ -268,6 +268,16 @@ def adam_step_dev(var, grad, m, v, state, lr, gscale=1.0, beta1=0.9, beta2=0.999
     return var
 
 
+def adam_iterate_dev(g_opt, grad, m, v, state, lr, gscale, mask, mask_stride, var_out, delta, apply,
+                     beta1=0.9, beta2=0.999, eps=1e-8):
+    """var = g_opt; Adam step; delta = (nan_to_num(var) - g_opt) [* mask]; optionally g_opt += delta -- one kernel."""
+    width = g_opt.shape[-1]
+    _lib.get().call('lnst_adam_iterate_dev', ptr(g_opt), ptr(grad), ptr(m), ptr(v), g_opt.numel(), ptr(state),
+                    float(lr), beta1, beta2, eps, float(gscale), ptr(mask), width, int(mask_stride), ptr(var_out),
+                    ptr(delta), int(bool(apply)), _s(g_opt))
+    return var_out, delta
+
+
 def adam_step(var, grad, m, v, lr_t, gscale=1.0, beta1=0.9, beta2=0.999, eps=1e-8):
     _lib.get().call('lnst_adam_step', ptr(var), ptr(grad), ptr(m), ptr(v), var.numel(), float(lr_t), beta1, beta2,
                     eps, float(gscale), _s(var))

@@ -34,6 +34,14 @@ class _Adam:
             self.state = torch.tensor([0.9, 0.999, 0.0], dtype=f32).to(var.device)
         ops.adam_step_dev(var, grad, self.m, self.v, self.state, lr, gscale)
 
+    def iterate(self, g_opt, grad, lr, gscale, mask, mask_stride, apply):
+        """The fused single-step iteration (``lnst_adam_iterate_dev``): returns (var, delta)."""
+        if self.m is None:
+            self.m, self.v = torch.zeros_like(g_opt), torch.zeros_like(g_opt)
+            self.state = torch.tensor([0.9, 0.999, 0.0], dtype=f32).to(g_opt.device)
+        return ops.adam_iterate_dev(g_opt, grad, self.m, self.v, self.state, lr, gscale, mask, mask_stride,
+                                    torch.empty_like(g_opt), torch.empty_like(g_opt), apply)
+
 
 class StepRunner:
     """One frame's loop body (``Styler.frame_step``) as a callable.  The first call runs eagerly
@@ -359,40 +367,41 @@ class Styler(StylerBase):
         launch sequence is fixed, so ``StepRunner`` can capture it into a CUDA graph (the view set is
         re-drawn by ``_advance_views`` after the call, outside the graph)."""
         dev = self.device
-        var = g_opt_t.clone()                                      # :312 (device copy, no H2D)
-        if self.rotate:
-            n_step_views = self.n_views // self.v_batch
-            if self.view_mode == 'sequential':                     # :329-340
-                acc = torch.empty_like(var)
-                losses = []
-                for i in range(0, self.n_views, self.v_batch):
-                    l, grad = self.loss_and_grad(fr, var, ws, self._rot_all[i:i + 1], style_grams)
-                    adam.step(var, grad, lr)
-                    ops.iterate_accumulate(acc, var, i == 0)
-                    losses.append(l)
-                loss_t = torch.cat(losses).mean()                  # :342
-                g_new, scale = acc, 1.0 / n_step_views             # :351-352
-            else:                                                  # mean view gradient, views sharded over ranks
-                if self._rot_mine is not None:
-                    l, grad = self.loss_and_grad(fr, var, ws, self._rot_mine, style_grams)
-                    lsum = l.sum().reshape(1)
-                else:
-                    grad, lsum = torch.zeros_like(var), torch.zeros(1, dtype=f32, device=dev)
-                if self.view_world > 1:                            # ONE all-reduce: gradient + loss scalar
-                    buf = torch.cat([grad.reshape(-1), lsum])
-                    torch.distributed.all_reduce(buf)
-                    grad, lsum = buf[:-1].view_as(var), buf[-1:]
-                adam.step(var, grad, lr, gscale=1.0 / self.n_views)
-                loss_t = lsum[0] / self.n_views
-                g_new, scale = var, 1.0
-        else:                                                      # :354-357
-            l, grad = self.loss_and_grad(fr, var, ws, None, style_grams)
-            adam.step(var, grad, lr)
-            loss_t = l[0]
-            g_new, scale = var, 1.0
         mask = fr['r'] if 'd' in self.target_field else None       # :359-363
-        delta = ops.iterate_delta(g_new, scale, g_opt_t, mask, self.num_kernels if mask is not None else 0,
-                                  torch.empty_like(var))
+        mstride = self.num_kernels if mask is not None else 0
+        if self.rotate and self.view_mode == 'sequential':         # :329-340: one Adam step per view
+            var = g_opt_t.clone()                                  # :312 (device copy, no H2D)
+            n_step_views = self.n_views // self.v_batch
+            acc = torch.empty_like(var)
+            losses = []
+            for i in range(0, self.n_views, self.v_batch):
+                l, grad = self.loss_and_grad(fr, var, ws, self._rot_all[i:i + 1], style_grams)
+                adam.step(var, grad, lr)
+                ops.iterate_accumulate(acc, var, i == 0)
+                losses.append(l)
+            loss_t = torch.cat(losses).mean()                      # :342
+            delta = ops.iterate_delta(acc, 1.0 / n_step_views, g_opt_t, mask, mstride, torch.empty_like(var))  # :351-352
+            return var, loss_t, delta
+        # one Adam step per iteration: the forward/backward pass reads g_opt[t] itself (the reference's variable
+        # holds exactly that value, :312), then ONE kernel does Adam + the iterate bookkeeping (+ g_opt += delta
+        # when no temporal filter runs in between, ``self.fuse_apply``)
+        gscale = 1.0
+        if self.rotate:                                            # mean view gradient, views sharded over ranks
+            if self._rot_mine is not None:
+                l, grad = self.loss_and_grad(fr, g_opt_t, ws, self._rot_mine, style_grams)
+                lsum = l.sum().reshape(1)
+            else:
+                grad, lsum = torch.zeros_like(g_opt_t), torch.zeros(1, dtype=f32, device=dev)
+            if self.view_world > 1:                                # ONE all-reduce: gradient + loss scalar
+                buf = torch.cat([grad.reshape(-1), lsum])
+                torch.distributed.all_reduce(buf)
+                grad, lsum = buf[:-1].view_as(g_opt_t), buf[-1:]
+            gscale = 1.0 / self.n_views
+            loss_t = lsum[0] / self.n_views
+        else:                                                      # :354-357
+            l, grad = self.loss_and_grad(fr, g_opt_t, ws, None, style_grams)
+            loss_t = l[0]
+        var, delta = adam.iterate(g_opt_t, grad, lr, gscale, mask, mstride, getattr(self, 'fuse_apply', False))
         return var, loss_t, delta
 
     # ---- device residency -----------------------------------------------------------------------
@@ -445,6 +454,8 @@ class Styler(StylerBase):
         owners = self._frame_owners(key_frames) if shard == 'frames' else {t: self.rank for t in key_frames}
         mine = [t for t in key_frames if owners[t] == self.rank]
 
+        # g_opt += delta happens inside the fused iteration kernel unless the temporal filter sits in between
+        self.fuse_apply = not (self.window_sigma > 0 and nf > 1)
         loss_history, d_intm, opt_ = [], [], {}
         for octave in range(self.octave_n):
             res = oct_size[octave]
@@ -477,8 +488,9 @@ class Styler(StylerBase):
                     sm = ops.temporal_gauss(torch.stack([deltas[t] for t in key_frames], 0), self.window_sigma)
                     for j, t in enumerate(key_frames):
                         deltas[t] = sm[j]
-                for t in mine:                                     # :385-386
-                    ops.axpy(g_opt[t], deltas[t].contiguous(), 1.0)
+                if not self.fuse_apply or (self.rotate and self.view_mode == 'sequential'):
+                    for t in mine:                                 # :385-386
+                        ops.axpy(g_opt[t], deltas[t].contiguous(), 1.0)
             hist = {t: torch.stack(v) for t, v in loss_o.items() if v}
             if shard == 'frames':
                 hist = self._gather_frames(hist, owners, key_frames, (self.iter,)) if self.iter else {}

@@ -462,6 +462,41 @@ def test_adam_device_step_counter(dev):
     np.testing.assert_allclose(state.cpu().numpy()[:2], [np.float32(0.9) ** 6, np.float32(0.999) ** 6], rtol=1e-6)
 
 
+@pytest.mark.parametrize('apply', [False, True])
+def test_fused_adam_iterate_equals_the_separate_kernels(dev, apply):
+    """lnst_adam_iterate_dev = clone + lnst_adam_step_dev + lnst_iterate_delta (+ lnst_axpy), NaN rule included."""
+    rng = np.random.RandomState(23)
+    n, c = 37, 2
+    g0 = torch.tensor(rng.randn(n, c).astype(np.float32))
+    mask = torch.tensor(rng.rand(n, c).astype(np.float32))
+    ref_var, ref_m, ref_v = g0.clone().to(dev), torch.zeros(n, c).to(dev), torch.zeros(n, c).to(dev)
+    ref_state = torch.tensor([0.9, 0.999, 0.0]).to(dev)
+    ref_g = g0.clone().to(dev)
+    g_opt, m, v = g0.clone().to(dev), torch.zeros(n, c).to(dev), torch.zeros(n, c).to(dev)
+    state = torch.tensor([0.9, 0.999, 0.0]).to(dev)
+    for t in range(3):
+        grad = torch.tensor(rng.randn(n, c).astype(np.float32))
+        grad[5, 1] = float('nan')
+        # separate kernels
+        ref_var = ref_g.clone()
+        ops.adam_step_dev(ref_var, grad.to(dev), ref_m, ref_v, ref_state, 0.05, gscale=0.25)
+        ref_delta = ops.iterate_delta(ref_var, 1.0, ref_g, mask.to(dev), c, torch.empty_like(ref_var))
+        # fused
+        before = g_opt.clone()
+        var, delta = ops.adam_iterate_dev(g_opt, grad.to(dev), m, v, state, 0.05, 0.25, mask.to(dev), c,
+                                          torch.empty_like(g_opt), torch.empty_like(g_opt), apply)
+        assert torch.equal(torch.isnan(var), torch.isnan(ref_var)) and torch.isnan(var[5, 1])
+        assert torch.equal(torch.nan_to_num(var), torch.nan_to_num(ref_var))
+        assert torch.equal(delta, ref_delta)
+        assert delta[5, 1].item() == (-before[5, 1].cpu() * mask[5, 0]).item()      # NaN iterate counts as 0
+        ops.axpy(ref_g, ref_delta, 1.0)
+        if not apply:
+            assert torch.equal(g_opt, before)
+            ops.axpy(g_opt, delta, 1.0)
+        assert torch.equal(g_opt, ref_g)
+    assert torch.equal(torch.nan_to_num(m), torch.nan_to_num(ref_m)) and torch.equal(state, ref_state)
+
+
 def test_iterate_glue_and_temporal_gauss(dev):
     from scipy.ndimage import gaussian_filter
     rng = np.random.RandomState(16)
