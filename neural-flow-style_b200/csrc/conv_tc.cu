@@ -32,6 +32,7 @@ constexpr int UMMA_K = 16;
 constexpr int STAGES = 3;
 constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;   // 16 KiB
 constexpr int NUM_THREADS = 192;     // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-5: epilogue
+constexpr int PERSIST_THREADS = 320; // per-tap persistent kernel: 8 epilogue warps (two per TMEM sub-partition)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -382,7 +383,7 @@ __device__ __forceinline__ void warp_rows_store(uint32_t stage, int lane, const 
 }
 
 template <int BLOCK_N>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(PERSIST_THREADS, 1)
 conv3x3_tc_persist_k(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                      const float* __restrict__ bias, const __nv_bfloat16* __restrict__ mask,
                      const __nv_bfloat16* __restrict__ addend, __nv_bfloat16* __restrict__ y, ConvShape s,
@@ -412,7 +413,7 @@ conv3x3_tc_persist_k(const __grid_constant__ CUtensorMap map_x, const __grid_con
       mbar_init(bars + 8 * (PSTAGES + i), 1);
     }
     mbar_init(bar_tfull, 1); mbar_init(bar_tfull + 8, 1);
-    mbar_init(bar_tempty, 4); mbar_init(bar_tempty + 8, 4);          // one arrival per epilogue warp
+    mbar_init(bar_tempty, 8); mbar_init(bar_tempty + 8, 8);          // one arrival per epilogue warp
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -476,25 +477,30 @@ conv3x3_tc_persist_k(const __grid_constant__ CUtensorMap map_x, const __grid_con
       if (leader) umma_commit(bar_tfull + 8 * buf);
     }
   } else {
-    // ===== epilogue: warps 2..5, TMEM sub-partition = warp % 4 =====
+    // ===== epilogue: warps 2..9.  TMEM sub-partition = warp % 4; warps 2-5 take the lower half of the tile's
+    // columns, warps 6-9 the upper half.  The epilogue's global traffic (addend and mask rows in, output rows
+    // out: 16-byte accesses issued by the row's owner) is latency-bound, and with four warps the data in
+    // flight per SM capped the Gram-gradient GEMM and the masked data gradients at ~2.4 TB/s chip-wide =====
+    constexpr int EN = BLOCK_N / 2;
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int r = q * 32 + lane;
     uint32_t lt = 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++lt) {
       const int nb = t % n_blocks_n, sp = t / n_blocks_n;
       const int img = sp / tiles_sp, rem = sp - img * tiles_sp;
       const int th = rem / s.tiles_w, tw = rem - th * s.tiles_w;
-      const int n0 = nb * BLOCK_N;
+      const int n0 = nb * BLOCK_N + half * EN;
       const int ph_ = th * s.TH + r / s.TW, pw_ = tw * s.TW + r % s.TW;
       const bool valid = ph_ < s.H && pw_ < s.W;
       const int64_t pix = ((int64_t)img * s.H + ph_) * s.W + pw_;
-      uint32_t mbits[BLOCK_N / 32];
+      uint32_t mbits[EN / 32];
 #pragma unroll
-      for (int c = 0; c < BLOCK_N / 32; ++c) mbits[c] = 0xffffffffu;
+      for (int c = 0; c < EN / 32; ++c) mbits[c] = 0xffffffffu;
       if (mask && valid) {
         const uint4* msk = reinterpret_cast<const uint4*>(mask + pix * s.Cout + n0);
 #pragma unroll
-        for (int c = 0; c < BLOCK_N / 32; ++c) {
+        for (int c = 0; c < EN / 32; ++c) {
           uint4 mv[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) mv[j] = msk[c * 4 + j];
@@ -519,12 +525,12 @@ conv3x3_tc_persist_k(const __grid_constant__ CUtensorMap map_x, const __grid_con
       const uint32_t buf = lt & 1, bph = (lt >> 1) & 1;
       mbar_wait(bar_tfull + 8 * buf, bph);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t acc = tmem_d + buf * BLOCK_N + ((uint32_t)(q * 32) << 16);
+      const uint32_t acc = tmem_d + buf * BLOCK_N + half * EN + ((uint32_t)(q * 32) << 16);
 #pragma unroll
-      for (int c = 0; c < BLOCK_N / 32; ++c) {
+      for (int c = 0; c < EN / 32; ++c) {
         uint32_t v[32];
         tmem_ld32(acc + (uint32_t)(c * 32), v);
-        if (c == BLOCK_N / 32 - 1) {
+        if (c == EN / 32 - 1) {
           // every TMEM read of this warp has completed: hand the buffer back to the MMA issuer
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           __syncwarp();
@@ -533,7 +539,7 @@ conv3x3_tc_persist_k(const __grid_constant__ CUtensorMap map_x, const __grid_con
         uint4 an[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) an[j] = make_uint4(0, 0, 0, 0);
-        if (add && c + 1 < BLOCK_N / 32) {
+        if (add && c + 1 < EN / 32) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) an[j] = add[(c + 1) * 4 + j];
         }
@@ -1139,7 +1145,7 @@ static int launch_conv(const CUtensorMap& mx, const CUtensorMap& mw, const float
     const int n_blocks_n = s.Cout / BLOCK_N;
     const int n_tiles = s.tiles_w * s.tiles_h * n_img * n_blocks_n;
     const int grid = n_tiles < sms ? n_tiles : sms;
-    conv3x3_tc_persist_k<BLOCK_N><<<grid, NUM_THREADS, psmem, stream>>>(mx, mw, bias, mask, addend, y, s, n_blocks_n,
+    conv3x3_tc_persist_k<BLOCK_N><<<grid, PERSIST_THREADS, psmem, stream>>>(mx, mw, bias, mask, addend, y, s, n_blocks_n,
                                                                         n_tiles);
     return (int)cudaGetLastError();
   }
