@@ -210,6 +210,14 @@ int lnst_set_conv_halo(int32_t on);
  * flipped/transposed 64->3 weights, rows 3..15 zero) -> gx fp32 [n,H,W,3]. */
 int lnst_conv_first_bwd_tc(const void* g, const void* wd16, float* gx, int32_t n, int32_t H, int32_t W,
                            void* stream);
+/* conv1_1 forward and data gradient for a GRAY render replicated to RGB (styler_base.py:41-43, vgg.py:50-53):
+ * x_c = s*gray - mean_c is never materialised.  ws[9][64] = s*sum_c w[tap,c,:], wm[9][64] = sum_c w[tap,c,:]*mean_c,
+ * bsum[64] = b - sum_tap wm; y bf16 [n,H,W,64] = relu(conv).  Backward: wd16 bf16 [9,16,64] with row 0 =
+ * s*sum_c of the flipped/transposed rows, rows 1..15 zero -> g_gray fp32 [n,H,W]. */
+int lnst_conv_first_fwd_gray(const float* gray, const float* ws, const float* wm, const float* bsum, void* y, int32_t n,
+                             int32_t H, int32_t W, void* stream);
+int lnst_conv_first_bwd_gray_tc(const void* g, const void* wd16, float* g_gray, int32_t n, int32_t H, int32_t W,
+                                void* stream);
 /* Gram matrices on tensor cores, batched over images (styler_base.py:96-102,152-185):
  * G[i] = F[i]^T F[i] / denom - Gs (fp32 [n,C,C]; Gs NULL => no subtraction), Gd = bf16 copy of G,
  * loss[i] += weight * sum(G[i]^2).  F bf16 [n,P,C], C a multiple of 64.  tcgen05 with MN-major

@@ -173,6 +173,7 @@ struct ConvShape {
   int taps;      // 9: 3x3 convolution; 1: per-pixel GEMM (Gram gradient F x G)
   int w_img;     // 1: third coordinate of the weight map is the image index (per-image B matrix)
   float scale;   // multiplies the accumulator before addend / bias
+  int out_ch;    // OUT3 epilogue: fp32 channels written per pixel (3, or 1 for the gray render)
 };
 
 // y = mask( relu?( scale * (X (*) W) + addend + bias ) )
@@ -794,8 +795,12 @@ conv3x3_halo_k(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
         if (valid) {
-          float* o = y3 + pix * 3;
-          o[0] = __uint_as_float(v[0]) * s.scale; o[1] = __uint_as_float(v[1]) * s.scale; o[2] = __uint_as_float(v[2]) * s.scale;
+          if (s.out_ch == 1) {
+            y3[pix] = __uint_as_float(v[0]) * s.scale;
+          } else {
+            float* o = y3 + pix * 3;
+            o[0] = __uint_as_float(v[0]) * s.scale; o[1] = __uint_as_float(v[1]) * s.scale; o[2] = __uint_as_float(v[2]) * s.scale;
+          }
         }
       } else {
         constexpr int NCH = (BLOCK_N >= 32) ? BLOCK_N / 32 : 1;
@@ -1170,12 +1175,12 @@ static int conv_halo = 1;         // tuning switch: 1 = halo'd-patch kernel for 
 template <int BLOCK_N, bool OUT3>
 static int launch_halo(const void* x, const void* wmat, const float* bias, const __nv_bfloat16* mask,
                        __nv_bfloat16* y, float* y3, int n, int H, int W, int Cin, int Cout, int relu, float scale,
-                       cudaStream_t stream) {
+                       cudaStream_t stream, int out_ch = 3) {
   constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
   constexpr int MAX_SMEM = 232448;                        // 227 KiB opt-in limit per CTA
   const int budget = MAX_SMEM - 2048 - 1024 - 512 - HaloStage<BLOCK_N>::bytes - 128;   // static bias table, alignment slack, barriers, store staging
   ConvShape s;
-  s.H = H; s.W = W; s.Cin = Cin; s.Cout = Cout; s.relu = relu; s.taps = 9; s.w_img = 0; s.scale = scale;
+  s.H = H; s.W = W; s.Cin = Cin; s.Cout = Cout; s.relu = relu; s.taps = 9; s.w_img = 0; s.scale = scale; s.out_ch = out_ch;
   s.TH = HTH; s.TW = HTW;
   s.tiles_w = (W + HTW - 1) / HTW;
   s.tiles_h = (H + HTH - 1) / HTH;
@@ -1381,6 +1386,82 @@ __global__ void __launch_bounds__(256) conv_first_fwd_k(const float* __restrict_
   }
 }
 
+// conv1_1 on a GRAY render (every 3-D driver: the image is one channel replicated to RGB, styler_base.py:41-43):
+// x_c = s*g - mean_c, so sum_c w[tap,c,co]*x_c = g*(s*sum_c w) - sum_c w*mean_c.  ws[tap][co] = s*sum_c w[tap,c,co],
+// wm[tap][co] = sum_c w[tap,c,co]*mean_c, bsum[co] = b[co] - sum_tap wm[tap][co]: 9 FMAs per output instead of 27
+// and no [n,H,W,3] network input in memory.  SAME padding pads x (not g) with zeros: a tap outside the image
+// contributes neither term, so border pixels add wm[tap] back for their missing taps.
+__global__ void __launch_bounds__(256) conv_first_fwd_gray_k(const float* __restrict__ gimg, const float* __restrict__ ws,
+                                                             const float* __restrict__ wm, const float* __restrict__ bsum,
+                                                             __nv_bfloat16* __restrict__ y, int n, int H, int W) {
+  __shared__ __align__(16) float s_ws[9 * 64];
+  __shared__ __align__(16) float s_wm[9 * 64];
+  __shared__ float s_b[64];
+  for (int i = threadIdx.x; i < 9 * 64; i += blockDim.x) { s_ws[i] = ws[i]; s_wm[i] = wm[i]; }
+  if (threadIdx.x < 64) s_b[threadIdx.x] = bsum[threadIdx.x];
+  __syncthreads();
+  const int WG = (W + FP - 1) / FP;
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t grp = t >> 3;
+  const int cg = (int)(t & 7) * 8;
+  if (grp >= (int64_t)n * H * WG) return;
+  const int px = (int)(grp % WG) * FP, py = (int)((grp / WG) % H);
+  const int64_t img = grp / ((int64_t)WG * H);
+  float acc[FP][8];
+#pragma unroll
+  for (int p = 0; p < FP; ++p)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[p][j] = s_b[cg + j];
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky) {
+    const int yy = py + ky - 1;
+    const bool rowok = yy >= 0 && yy < H;
+    const float* row = gimg + (img * H + (rowok ? yy : 0)) * (int64_t)W;
+    float in[FP + 2];
+#pragma unroll
+    for (int c = 0; c < FP + 2; ++c) {
+      const int xx = px + c - 1;
+      in[c] = (rowok && xx >= 0 && xx < W) ? row[xx] : 0.f;
+    }
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const float4* wr = reinterpret_cast<const float4*>(s_ws + (ky * 3 + kx) * 64 + cg);
+      const float4 w0 = wr[0], w1 = wr[1];
+#pragma unroll
+      for (int p = 0; p < FP; ++p) {
+        const float xv = in[p + kx];
+        acc[p][0] = fmaf(xv, w0.x, acc[p][0]); acc[p][1] = fmaf(xv, w0.y, acc[p][1]);
+        acc[p][2] = fmaf(xv, w0.z, acc[p][2]); acc[p][3] = fmaf(xv, w0.w, acc[p][3]);
+        acc[p][4] = fmaf(xv, w1.x, acc[p][4]); acc[p][5] = fmaf(xv, w1.y, acc[p][5]);
+        acc[p][6] = fmaf(xv, w1.z, acc[p][6]); acc[p][7] = fmaf(xv, w1.w, acc[p][7]);
+      }
+    }
+  }
+  if (py == 0 || py == H - 1 || px == 0 || px + FP >= W) {          // border: give back the mean terms of missing taps
+#pragma unroll
+    for (int p = 0; p < FP; ++p) {
+      const int xc = px + p;
+      for (int ky = 0; ky < 3; ++ky)
+        for (int kx = 0; kx < 3; ++kx) {
+          const int yy = py + ky - 1, xx = xc + kx - 1;
+          if (yy < 0 || yy >= H || xx < 0 || xx >= W) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[p][j] += s_wm[(ky * 3 + kx) * 64 + cg + j];
+          }
+        }
+    }
+  }
+#pragma unroll
+  for (int p = 0; p < FP; ++p) {
+    if (px + p >= W) break;
+    uint4 o;
+    __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) oh[j] = __floats2bfloat162_rn(fmaxf(acc[p][2 * j], 0.f), fmaxf(acc[p][2 * j + 1], 0.f));
+    *reinterpret_cast<uint4*>(y + (((img * H + py) * (int64_t)W + px + p) * 64 + cg)) = o;
+  }
+}
+
 // data gradient: a thread computes BP consecutive pixels x 3 outputs, walking the 64 gradient channels
 // in chunks of 8 (one 16-byte load per window column); each chunk's 3 x 8 x 3 weights come from
 // shared memory as broadcast float4s and feed BP x 72 FMAs.  wd fp32 [3,3,64,3].
@@ -1461,6 +1542,15 @@ extern "C" int lnst_conv_first_fwd(const float* x, const float* w, const float* 
   return lnst_status();
 }
 
+extern "C" int lnst_conv_first_fwd_gray(const float* gray, const float* ws, const float* wm, const float* bsum, void* y,
+                                        int32_t n, int32_t H, int32_t W, void* stream) {
+  if (!gray || !ws || !wm || !bsum || !y || n < 1 || H < 1 || W < 1) return LNST_EARG;
+  const int64_t threads = (int64_t)n * H * ((W + tc::FP - 1) / tc::FP) * 8;
+  tc::conv_first_fwd_gray_k<<<lnst_blocks(threads, 256), 256, 0, lnst_stream(stream)>>>(gray, ws, wm, bsum,
+                                                                                       (__nv_bfloat16*)y, n, H, W);
+  return lnst_status();
+}
+
 extern "C" int lnst_conv_first_bwd(const void* g, const float* wd, float* gx, int32_t n, int32_t H, int32_t W,
                                    void* stream) {
   if (!g || !wd || !gx || n < 1 || H < 1 || W < 1) return LNST_EARG;
@@ -1497,6 +1587,14 @@ extern "C" int lnst_conv_first_bwd_tc(const void* g, const void* wd16, float* gx
                                    lnst_stream(stream));
 }
 
+// The same for a gray render: wd16 row 0 = s * sum_c of the three data-gradient rows -> g_gray fp32 [n,H,W].
+extern "C" int lnst_conv_first_bwd_gray_tc(const void* g, const void* wd16, float* g_gray, int32_t n, int32_t H,
+                                           int32_t W, void* stream) {
+  if (!g || !wd16 || !g_gray || n < 1 || H < 1 || W < 1) return LNST_EARG;
+  return tc::launch_halo<16, true>(g, wd16, nullptr, nullptr, nullptr, g_gray, n, H, W, 64, 16, 0, 1.0f,
+                                   lnst_stream(stream), 1);
+}
+
 extern "C" int lnst_set_conv_persistent(int32_t on) { tc::conv_persistent = on ? 1 : 0; return LNST_OK; }
 
 extern "C" int lnst_tc_supported(void) { return tc::encode_fn() != nullptr ? 1 : 0; }
@@ -1523,7 +1621,7 @@ static int run_tc_gemm(const void* x, const void* wmat, const float* bias, const
   }
   ConvShape s;
   s.H = H; s.W = W; s.Cin = Cin; s.Cout = Cout; s.relu = relu;
-  s.taps = taps; s.w_img = w_img; s.scale = scale;
+  s.taps = taps; s.w_img = w_img; s.scale = scale; s.out_ch = 3;
   pick_tile(H, W, s.TH, s.TW);
   s.tiles_w = (W + s.TW - 1) / s.TW;
   s.tiles_h = (H + s.TH - 1) / s.TH;

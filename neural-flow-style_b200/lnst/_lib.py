@@ -89,6 +89,8 @@ CUDA_ONLY = {
     'lnst_set_conv_persistent': [i32],
     'lnst_set_conv_halo': [i32],
     'lnst_conv_first_bwd_tc': [vp, vp, vp, i32, i32, i32, vp],
+    'lnst_conv_first_fwd_gray': [vp, vp, vp, vp, vp, i32, i32, i32, vp],
+    'lnst_conv_first_bwd_gray_tc': [vp, vp, vp, i32, i32, i32, vp],
     'lnst_umma_probe': [vp, vp, vp, i32, i32, i32, i32, vp],
     'lnst_conv3x3_bf16_tc': [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp],
     'lnst_conv3x3_mixed': [vp, i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp],

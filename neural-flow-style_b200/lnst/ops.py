@@ -399,6 +399,22 @@ def conv_first_bwd_tc(g, wd16):
     return gx
 
 
+def conv_first_fwd_gray(gray, ws, wm, bsum):
+    """VGG conv1_1 on a gray render: gray fp32 [n,H,W] -> bf16 [n,H,W,64] (see lnst_conv_first_fwd_gray)."""
+    n, H, W = gray.shape
+    y = torch.empty(n, H, W, 64, dtype=bf16, device=gray.device)
+    _lib.get().call('lnst_conv_first_fwd_gray', ptr(gray), ptr(ws), ptr(wm), ptr(bsum), ptr(y), n, H, W, _s(gray))
+    return y
+
+
+def conv_first_bwd_gray_tc(g, wd16_gray):
+    """data gradient of conv1_1 w.r.t. the gray render: g bf16 [n,H,W,64] -> fp32 [n,H,W]."""
+    n, H, W, _ = g.shape
+    gg = torch.empty(n, H, W, dtype=f32, device=g.device)
+    _lib.get().call('lnst_conv_first_bwd_gray_tc', ptr(g), ptr(wd16_gray), ptr(gg), n, H, W, _s(g))
+    return gg
+
+
 def avgpool2_bf16_fwd(x):
     n, H, W, ch = x.shape
     y = torch.empty(n, H // 2, W // 2, ch, dtype=bf16, device=x.device)

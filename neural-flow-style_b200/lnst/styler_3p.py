@@ -264,8 +264,9 @@ class Styler(StylerBase):
             ws['box_cells'] = (hi[0] - lo[0] + 1) * (hi[1] - lo[1] + 1) * (hi[2] - lo[2] + 1)
         return ws
 
-    def _render(self, ds, rot, box=None, bricks=None):
-        """ds [D,H,W] -> gray [nv,H,W,1] in [0,1] plus what the backward needs."""
+    def _render(self, ds, rot, box=None, bricks=None, net_input=True):
+        """ds [D,H,W] -> gray [nv,H,W,1] in [0,1] plus what the backward needs.  ``net_input=False``: the loss
+        net starts from the gray image itself (``_gray_path``), d_img / x are not produced."""
         D, H, W = ds.shape
         nv = 1 if rot is None else rot.shape[0]
         dev = self.device
@@ -292,18 +293,23 @@ class Styler(StylerBase):
         nh, nw = self._net_hw((H, W))
         if (nh, nw) != (H, W):                                    # styler_base.py:35-38
             gray = ops.resize_bilinear_fwd(gray, nh, nw)
-        d_img = torch.empty(nv, nh, nw, 3, dtype=f32, device=dev)
-        x = torch.empty(nv, nh, nw, 3, dtype=f32, device=dev)
-        ops.to_net_input_fwd(gray, 255.0, d_img, x)               # styler_base.py:41-45, vgg.py:50-53
-        st.update(d_img=d_img, x=x, hw=(H, W))
+        st.update(gray=gray.reshape(nv, nh, nw), hw=(H, W))
+        if net_input:
+            d_img = torch.empty(nv, nh, nw, 3, dtype=f32, device=dev)
+            x = torch.empty(nv, nh, nw, 3, dtype=f32, device=dev)
+            ops.to_net_input_fwd(gray, 255.0, d_img, x)           # styler_base.py:41-45, vgg.py:50-53
+            st.update(d_img=d_img, x=x)
         return st
 
     def _render_bwd(self, st, g_x, ds, g_ds):
         """d loss / d x -> accumulated into g_ds (which the caller zeroed)."""
         nv = g_x.shape[0]
         H, W = st['hw']
-        g_gray = ops.to_net_input_bwd(g_x, 1, 255.0, torch.empty(nv, g_x.shape[1], g_x.shape[2], 1, dtype=f32,
-                                                                  device=self.device))
+        if g_x.dim() == 3:                                        # already d loss / d gray (gray path)
+            g_gray = g_x.reshape(nv, g_x.shape[1], g_x.shape[2], 1)
+        else:
+            g_gray = ops.to_net_input_bwd(g_x, 1, 255.0, torch.empty(nv, g_x.shape[1], g_x.shape[2], 1, dtype=f32,
+                                                                      device=self.device))
         if (g_x.shape[1], g_x.shape[2]) != (H, W):
             g_gray = ops.resize_bilinear_bwd(g_gray, H, W)
         g_gray = g_gray.reshape(nv, H, W)
@@ -314,6 +320,15 @@ class Styler(StylerBase):
                                       torch.empty_like(g_gray))
         ops.raymarch_bwd(ds, st['rot'], self.transmit, self.render_liquid, st['stot'], g_img, g_ds, st['box'], st['iv'])
 
+    def _gray_path(self):
+        """The render is gray and the tensor-core loss net can take it directly: conv1_1 folds the x255, the RGB
+        replication and the mean subtraction into its weights (no TV loss, which reads d_img)."""
+        wanted = self._wanted()
+        if self.w_tv or not self.net.gray_path() or 'input' in wanted or not getattr(self, 'gray_conv', True):
+            return False
+        pre = self.net.prefix(wanted)
+        return bool(pre) and pre[0] == 'conv1_1'
+
     # ---- one loss + gradient evaluation (= one sess.run([train_op, total_loss]) without Adam) ----
     def loss_and_grad(self, fr, var, ws, rot, style_grams):
         """Sum over the given views of total_loss, and d(sum)/d var.  Returns (loss [nv], grad)."""
@@ -321,10 +336,14 @@ class Styler(StylerBase):
         d = self._density(fr, var, res, ws)
         box = ws['box']
         ds = ops.smooth3_relu_fwd(d, ws['ds'], self.k, box)        # styler_3p.py:112-125
-        st = self._render(ds, rot, box, ws['bricks'])
-        nv = st['x'].shape[0]
+        gray_path = self._gray_path()
+        st = self._render(ds, rot, box, ws['bricks'], net_input=not gray_path)
+        nv = st['gray'].shape[0]
         loss = torch.zeros(nv, dtype=f32, device=self.device)
-        g_x = self.image_loss_and_grad(st['x'], st['d_img'], style_grams, loss)
+        if gray_path:
+            g_x = self.image_loss_and_grad(None, None, style_grams, loss, gray=st['gray'])
+        else:
+            g_x = self.image_loss_and_grad(st['x'], st['d_img'], style_grams, loss)
         g_ds = ops.fill_box(ws['g_ds'], box, 0.0)
         self._render_bwd(st, g_x, ds, g_ds)
         g_d = ops.smooth3_relu_bwd(g_ds, ds, ws['g_d'], self.k, box)

@@ -137,14 +137,19 @@ class StylerBase(object):
             out[l] = (m, [float(a) for a in m.sum(dim=(1, 2)).cpu().tolist()])
         return out
 
-    def image_loss_and_grad(self, x, d_img, style_grams, loss, style_masks=None):
+    def image_loss_and_grad(self, x, d_img, style_grams, loss, style_masks=None, gray=None):
         """x [n,H,W,3] net input (one image per view), d_img the same before mean subtraction.
         Adds each image's total feature/TV loss into ``loss[v]`` and returns d loss_v / d x_v
-        stacked [n,H,W,3] (styler_base.py:127-213)."""
-        n = x.shape[0]
+        stacked [n,H,W,3] (styler_base.py:127-213).
+
+        ``gray`` [n,H,W] (0..1): the render is one channel replicated to RGB and the loss net can start from it
+        (``LossNet.gray_path``, no TV loss): x and d_img are not read (may be None) and the result is
+        d loss_v / d gray_v [n,H,W]."""
+        n = x.shape[0] if gray is None else gray.shape[0]
+        hw = (x.shape[1], x.shape[2]) if gray is None else (gray.shape[1], gray.shape[2])
         wanted = self._wanted()
         style_on = bool(self.w_style) and style_grams is not None
-        acts = self.net.forward(x, wanted) if wanted else {}
+        acts = self.net.forward(x, wanted, gray=gray) if wanted else {}
         shapes = {}
         handles = {}
         if style_on:
@@ -159,7 +164,7 @@ class StylerBase(object):
                     if l != name:
                         continue
                     ch = style_grams[li].shape[0]
-                    P = self._feature_pixels(x.shape[1], x.shape[2], name)
+                    P = self._feature_pixels(hw[0], hw[1], name)
                     coef = self.w_style * self.w_style_layer[li] * 4.0 / (2.0 * P * ch)
                     g = self.net.gram_grad(acts, name, handles[l], coef, g, is_conv)
             if self.w_content and self.content_layer == name:
@@ -167,9 +172,9 @@ class StylerBase(object):
                                      target=getattr(self, '_content_feat', None), amp=self.w_content_amp)
             return g
 
-        g_x = self.net.backward(x, acts, wanted, add_loss_grad, set(wanted)) if wanted else None
+        g_x = self.net.backward(x, acts, wanted, add_loss_grad, set(wanted), gray=gray is not None) if wanted else None
         if g_x is None:
-            g_x = torch.zeros_like(x)
+            g_x = torch.zeros_like(x if gray is None else gray)
         if self.w_tv:
             g_tv = torch.empty_like(d_img[0])
             for v in range(n):

@@ -63,6 +63,10 @@ def load_weights(path, model='vgg_19'):
 
 
 class LossNet:
+    def gray_path(self):
+        """True when conv1_1 can run straight from a gray render (tensor-core back end, ``vgg_tc``)."""
+        return getattr(self, 'tc', None) is not None and self.tc.gray_w is not None
+
     """Forward/backward through the prefix of the network that the requested end points need."""
 
     def __init__(self, weights, model, device, math='fp32'):
@@ -90,10 +94,10 @@ class LossNet:
         return self.order[:last + 1]
 
     # ---- forward ---------------------------------------------------------------------------
-    def forward(self, x, wanted):
+    def forward(self, x, wanted, gray=None):
         """x [n,H,W,3] (mean-subtracted).  Returns {end point: activation [n,h,w,C] fp32}."""
         if self.math == 'bf16':
-            return self.tc.forward(x, self.prefix(wanted))
+            return self.tc.forward(x, self.prefix(wanted), gray=gray)
         acts = {}
         cur = x
         for name in self.prefix(wanted):
@@ -105,14 +109,14 @@ class LossNet:
         return acts
 
     # ---- backward --------------------------------------------------------------------------
-    def backward(self, x, acts, wanted, add_loss_grad, loss_layers):
+    def backward(self, x, acts, wanted, add_loss_grad, loss_layers, gray=False):
         """d loss / d x.  For every end point in ``loss_layers``, ``add_loss_grad(name, g)`` adds
         the loss terms that live there into ``g`` (None = nothing accumulated yet) through
         ``gram_grad`` / ``content`` below and returns the buffer.  Gradients held for conv end
         points are w.r.t. the PRE-activation (ReLU mask already applied).  ``g`` is in the back
         end's native type (fp32 or bf16)."""
         if self.math == 'bf16':
-            return self.tc.backward(x, acts, self.prefix(wanted), add_loss_grad, loss_layers)
+            return self.tc.backward(x, acts, self.prefix(wanted), add_loss_grad, loss_layers, gray=gray)
         layers = self.prefix(wanted)
         g = None
         for i in range(len(layers) - 1, -1, -1):

@@ -19,6 +19,7 @@ class TensorCoreConvs:
         self.net = net
         self.wp, self.wdp = {}, {}
         self.first_bwd_tc = True
+        self.gray_w = None
         for name, w in net.w.items():
             if w.shape[2] % 64 == 0 and w.shape[3] % 64 == 0:
                 self.wp[name] = _pack(w)
@@ -28,16 +29,30 @@ class TensorCoreConvs:
                 wd16 = torch.zeros(9, 16, 64, dtype=torch.bfloat16, device=w.device)
                 wd16[:, :3] = _pack(net.wd[name])
                 self.wd16 = wd16.contiguous()
+                # gray render replicated to RGB (styler_base.py:41-43): x_c = 255*g - mean_c is folded into the weights
+                from .vgg import _R_MEAN, _G_MEAN, _B_MEAN
+                mean = torch.tensor([_R_MEAN, _G_MEAN, _B_MEAN], dtype=torch.float32, device=w.device)
+                w32 = w.to(torch.float32)
+                wm = (w32 * mean.view(1, 1, 3, 1)).sum(2).reshape(9, 64).contiguous()
+                self.gray_w = ((255.0 * w32.sum(2)).reshape(9, 64).contiguous(), wm,
+                               (net.b[name].to(torch.float32) - wm.sum(0)).contiguous())
+                wdg = torch.zeros(9, 16, 64, dtype=torch.bfloat16, device=w.device)
+                wdg[:, 0] = (255.0 * net.wd[name].to(torch.float32).permute(0, 1, 3, 2).reshape(9, 3, 64).sum(1)
+                             ).to(torch.bfloat16)
+                self.wd16_gray = wdg.contiguous()
 
     # ---- network ----------------------------------------------------------------------------------
-    def forward(self, x, layers):
-        """x fp32 [n,H,W,3].  Returns the activation store (bf16 tensors, fp32 copies on demand)."""
+    def forward(self, x, layers, gray=None):
+        """x fp32 [n,H,W,3], or ``gray`` fp32 [n,H,W] in 0..1 for a gray render (x is then not read).
+        Returns the activation store (bf16 tensors, fp32 copies on demand)."""
         acts = {}
         cur = x
         for name in layers:
             if name.startswith('conv'):
                 if name in self.wp and cur.dtype == torch.bfloat16:
                     cur = ops.conv3x3_bf16_tc(cur, self.wp[name], self.net.b[name], relu=True)
+                elif gray is not None and name == layers[0] and tuple(self.net.w[name].shape[2:]) == (3, 64):
+                    cur = ops.conv_first_fwd_gray(gray, *self.gray_w)
                 elif cur.dtype == torch.float32 and tuple(self.net.w[name].shape[2:]) == (3, 64):
                     cur = ops.conv_first_fwd(cur, self.net.w[name], self.net.b[name])
                 else:
@@ -47,7 +62,7 @@ class TensorCoreConvs:
             acts[name] = cur
         return _Acts(acts)
 
-    def backward(self, x, acts, layers, add_loss_grad, loss_layers):
+    def backward(self, x, acts, layers, add_loss_grad, loss_layers, gray=False):
         g = None                                   # bf16 gradient of the current end point
         for i in range(len(layers) - 1, -1, -1):
             name = layers[i]
@@ -61,6 +76,8 @@ class TensorCoreConvs:
             if name.startswith('conv'):
                 if name in self.wdp and prev is not None:
                     g = ops.conv3x3_bf16_tc(g, self.wdp[name], None, relu=False, mask=mask)
+                elif prev is None and gray and tuple(self.net.w[name].shape[2:]) == (3, 64):
+                    g = ops.conv_first_bwd_gray_tc(g, self.wd16_gray)        # d loss / d gray [n,H,W]
                 elif prev is None and tuple(self.net.w[name].shape[2:]) == (3, 64):
                     g = ops.conv_first_bwd_tc(g, self.wd16) if self.first_bwd_tc else ops.conv_first_bwd(g, self.net.wd[name])
                 else:

@@ -209,3 +209,47 @@ def test_styler_bf16_vs_oracle(view_mode):
     g_new, g_ref = out['g_opt'][0], ref['g_opt'][0].numpy()
     assert np.linalg.norm(g_new - g_ref) / np.linalg.norm(g_ref) < 0.15
     assert np.abs(out['d'] - ref['d']).max() <= 0.1 * np.abs(ref['d']).max()
+
+
+@pytest.mark.parametrize('n,H,W', [(2, 13, 9), (3, 50, 64), (1, 200, 200)])
+def test_gray_conv1_1_equals_the_rgb_form(n, H, W):
+    """conv1_1 taken straight from a gray render (x255, RGB replication and mean subtraction folded into the
+    weights, lnst_conv_first_fwd_gray / lnst_conv_first_bwd_gray_tc) against the explicit form: net input
+    x = 255*g - mean built by lnst_to_net_input_fwd, fp32 convolution, and the gradient summed over channels."""
+    from lnst import vgg
+    dev = torch.device('cuda:0')
+    gen = torch.Generator().manual_seed(H * 7 + W)
+    gray = torch.rand(n, H, W, generator=gen)
+    net = vgg.LossNet(synth.vgg_weights(), 'vgg_19', dev, math='bf16')
+    assert net.gray_path()
+    w, b = net.w['conv1_1'].float().cpu(), net.b['conv1_1'].float().cpu()
+    mean = torch.tensor([vgg._R_MEAN, vgg._G_MEAN, vgg._B_MEAN])
+    x = 255.0 * gray[..., None] - mean                                    # [n,H,W,3]
+    want = ref_conv(x, w, b, True)
+    y = ops.conv_first_fwd_gray(gray.to(dev), *net.tc.gray_w)
+    err = (y.float().cpu() - want).abs().max().item()
+    assert err <= 2 ** -7 * want.abs().max().item(), (err, want.abs().max().item())
+    # data gradient w.r.t. the gray image: 255 * sum_c conv_transpose(g, w)_c
+    g = torch.randn(n, H, W, 64, generator=gen).to(torch.bfloat16)
+    gx = torch.nn.functional.conv_transpose2d(g.float().permute(0, 3, 1, 2), w.permute(3, 2, 0, 1), padding=1)
+    want_g = 255.0 * gx.sum(1)
+    got_g = ops.conv_first_bwd_gray_tc(g.to(dev), net.tc.wd16_gray)
+    err = (got_g.cpu() - want_g).abs().max().item()
+    assert err <= 2e-2 * want_g.abs().max().item(), (err, want_g.abs().max().item())     # bf16 weights
+
+
+def test_gray_path_runs_the_loop_like_the_rgb_path():
+    """Styler.run with the gray fast path on and off (conv_math='bf16'): same optimisation within bf16 noise."""
+    from lnst.styler_3p import Styler
+    outs = []
+    for gray in (True, False):
+        cfg = smoke_cfg(res=20, iter=3, rotate=True, n_views=3, view_mode='allreduce', conv_math='bf16',
+                        style_layer=['conv2_1'], w_style_layer=[1.0])
+        p, r = synth.smoke_particles(3000, 2, pad=4)
+        st = Styler(cfg, weights=synth.vgg_weights())
+        st.gray_conv = gray
+        st.style_img = synth.style_image(20, 20)
+        assert st._gray_path() == gray
+        outs.append(st.run({'p': p, 'r': r}))
+    np.testing.assert_allclose(outs[0]['l'][0], outs[1]['l'][0], rtol=2e-2)
+    assert np.abs(outs[0]['d'] - outs[1]['d']).max() <= 5e-2 * np.abs(outs[1]['d']).max()
