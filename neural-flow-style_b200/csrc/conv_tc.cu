@@ -1291,33 +1291,47 @@ __global__ void avgpool2_bf16_fwd_k(const __nv_bfloat16* __restrict__ x, __nv_bf
   }
   *reinterpret_cast<uint4*>(y + (((int64_t)img * OH + oy) * OW + ox) * C + c) = o;
 }
+// One thread per 2x2 input quad and 8 channels: the pooled gradient is read once, the four mask vectors are
+// independent loads in flight together, four 16-byte stores.  Quads hanging over an odd edge (VALID pooling
+// never read those pixels) get zero gradient.
 __global__ void avgpool2_bf16_bwd_k(const __nv_bfloat16* __restrict__ gy, const __nv_bfloat16* __restrict__ mask,
                                     __nv_bfloat16* __restrict__ gx, int n, int H, int W, int C) {
   const int OH = H / 2, OW = W / 2, C8 = C / 8;
-  const int64_t total = (int64_t)n * H * W * C8;
+  const int QH = (H + 1) / 2, QW = (W + 1) / 2;
+  const int64_t total = (int64_t)n * QH * QW * C8;
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= total) return;
   const int c = (int)(t % C8) * 8;
-  const int xx = (int)((t / C8) % W);
-  const int yy = (int)((t / ((int64_t)C8 * W)) % H);
-  const int img = (int)(t / ((int64_t)C8 * W * H));
-  const int64_t o = (((int64_t)img * H + yy) * W + xx) * C + c;
+  const int ox = (int)((t / C8) % QW);
+  const int oy = (int)((t / ((int64_t)C8 * QW)) % QH);
+  const int img = (int)(t / ((int64_t)C8 * QW * QH));
   uint4 g = make_uint4(0, 0, 0, 0);
-  const int oy = yy >> 1, ox = xx >> 1;
   if (oy < OH && ox < OW) g = *reinterpret_cast<const uint4*>(gy + (((int64_t)img * OH + oy) * OW + ox) * C + c);
-  uint4 mv = make_uint4(0, 0, 0, 0);
-  if (mask) mv = *reinterpret_cast<const uint4*>(mask + o);
-  const __nv_bfloat16* gh = reinterpret_cast<const __nv_bfloat16*>(&g);
-  const __nv_bfloat16* mh = reinterpret_cast<const __nv_bfloat16*>(&mv);
-  uint4 ov;
-  __nv_bfloat16* oh = reinterpret_cast<__nv_bfloat16*>(&ov);
+  const int y0 = 2 * oy, x0 = 2 * ox;
+  const int64_t o00 = (((int64_t)img * H + y0) * W + x0) * C + c;
+  const bool hx = x0 + 1 < W, hy = y0 + 1 < H;
+  const int64_t off[4] = {o00, o00 + C, o00 + (int64_t)W * C, o00 + (int64_t)W * C + C};
+  const bool ok[4] = {true, hx, hy, hx && hy};
+  uint4 mv[4];
 #pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    float f = 0.25f * __bfloat162float(gh[e]);
-    if (mask && !(__bfloat162float(mh[e]) > 0.f)) f = 0.f;
-    oh[e] = __float2bfloat16_rn(f);
+  for (int q = 0; q < 4; ++q) {
+    mv[q] = make_uint4(0, 0, 0, 0);
+    if (mask && ok[q]) mv[q] = *reinterpret_cast<const uint4*>(mask + off[q]);
   }
-  *reinterpret_cast<uint4*>(gx + o) = ov;
+  const __nv_bfloat16* gh = reinterpret_cast<const __nv_bfloat16*>(&g);
+  float f[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) f[e] = 0.25f * __bfloat162float(gh[e]);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    if (!ok[q]) continue;
+    const __nv_bfloat16* mh = reinterpret_cast<const __nv_bfloat16*>(&mv[q]);
+    uint4 ov;
+    __nv_bfloat16* oh = reinterpret_cast<__nv_bfloat16*>(&ov);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) oh[e] = __float2bfloat16_rn((mask && !(__bfloat162float(mh[e]) > 0.f)) ? 0.f : f[e]);
+    *reinterpret_cast<uint4*>(gx + off[q]) = ov;
+  }
 }
 
 // ---- conv1_1 (3 -> 64) and its data gradient (64 -> 3): K = 27, far too thin for an MMA tile ----
@@ -1677,7 +1691,7 @@ extern "C" int lnst_gram_diff_bf16_tc(const void* F, int32_t n, int64_t P, int32
   }
   const int tiles_n = (C + 127) / 128;
   const int tiles = tiles_n * tiles_n;
-  int splits = (2 * 148 + tiles * n - 1) / (tiles * n);
+  int splits = (148 + tiles * n - 1) / (tiles * n);            // one wave of CTAs: fewer split-K atomics per element
   const int max_splits = (int)((P + 255) / 256);              // at least 4 K-blocks per CTA
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
@@ -1740,7 +1754,7 @@ extern "C" int lnst_avgpool2_bf16_fwd(const void* x, void* y, int32_t n, int32_t
 extern "C" int lnst_avgpool2_bf16_bwd(const void* g_y, const void* mask, void* g_x, int32_t n, int32_t H, int32_t W,
                                       int32_t C, void* stream) {
   if (!g_y || !g_x || n < 1 || H < 2 || W < 2 || C < 8 || C % 8) return LNST_EARG;
-  const int64_t total = (int64_t)n * H * W * (C / 8);
+  const int64_t total = (int64_t)n * ((H + 1) / 2) * ((W + 1) / 2) * (C / 8);   // one thread per 2x2 quad, 8 channels
   tc::avgpool2_bf16_bwd_k<<<lnst_blocks(total, 256), 256, 0, lnst_stream(stream)>>>(
       (const __nv_bfloat16*)g_y, (const __nv_bfloat16*)mask, (__nv_bfloat16*)g_x, n, H, W, C);
   return lnst_status();
