@@ -1266,13 +1266,14 @@ __global__ void bf16_to_f32_k(const __nv_bfloat16* __restrict__ x, float* __rest
 __global__ void avgpool2_bf16_fwd_k(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int n, int H,
                                     int W, int C) {
   const int OH = H / 2, OW = W / 2, C8 = C / 8;
-  const int64_t total = (int64_t)n * OH * OW * C8;
-  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned total = (unsigned)n * OH * OW * C8;               // 32-bit index arithmetic (host checks the range)
+  const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= total) return;
-  const int c = (int)(t % C8) * 8;
-  const int ox = (int)((t / C8) % OW);
-  const int oy = (int)((t / ((int64_t)C8 * OW)) % OH);
-  const int img = (int)(t / ((int64_t)C8 * OW * OH));
+  const unsigned t1 = t / (unsigned)C8, t2 = t1 / (unsigned)OW, t3 = t2 / (unsigned)OH;
+  const int c = (int)(t - t1 * C8) * 8;
+  const int ox = (int)(t1 - t2 * OW);
+  const int oy = (int)(t2 - t3 * OH);
+  const int img = (int)t3;
   const __nv_bfloat16* b = x + (((int64_t)img * H + 2 * oy) * W + 2 * ox) * C + c;
   const uint4 v00 = *reinterpret_cast<const uint4*>(b), v01 = *reinterpret_cast<const uint4*>(b + C);
   const uint4 v10 = *reinterpret_cast<const uint4*>(b + (int64_t)W * C);
@@ -1298,13 +1299,14 @@ __global__ void avgpool2_bf16_bwd_k(const __nv_bfloat16* __restrict__ gy, const 
                                     __nv_bfloat16* __restrict__ gx, int n, int H, int W, int C) {
   const int OH = H / 2, OW = W / 2, C8 = C / 8;
   const int QH = (H + 1) / 2, QW = (W + 1) / 2;
-  const int64_t total = (int64_t)n * QH * QW * C8;
-  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned total = (unsigned)n * QH * QW * C8;               // 32-bit index arithmetic (host checks the range)
+  const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= total) return;
-  const int c = (int)(t % C8) * 8;
-  const int ox = (int)((t / C8) % QW);
-  const int oy = (int)((t / ((int64_t)C8 * QW)) % QH);
-  const int img = (int)(t / ((int64_t)C8 * QW * QH));
+  const unsigned t1 = t / (unsigned)C8, t2 = t1 / (unsigned)QW, t3 = t2 / (unsigned)QH;
+  const int c = (int)(t - t1 * C8) * 8;
+  const int ox = (int)(t1 - t2 * QW);
+  const int oy = (int)(t2 - t3 * QH);
+  const int img = (int)t3;
   uint4 g = make_uint4(0, 0, 0, 0);
   if (oy < OH && ox < OW) g = *reinterpret_cast<const uint4*>(gy + (((int64_t)img * OH + oy) * OW + ox) * C + c);
   const int y0 = 2 * oy, x0 = 2 * ox;
@@ -1746,6 +1748,7 @@ extern "C" int lnst_avgpool2_bf16_fwd(const void* x, void* y, int32_t n, int32_t
                                       void* stream) {
   if (!x || !y || n < 1 || H < 2 || W < 2 || C < 8 || C % 8) return LNST_EARG;
   const int64_t total = (int64_t)n * (H / 2) * (W / 2) * (C / 8);
+  if (total >= 0x7fffffff) return LNST_EARG;
   tc::avgpool2_bf16_fwd_k<<<lnst_blocks(total, 256), 256, 0, lnst_stream(stream)>>>(
       (const __nv_bfloat16*)x, (__nv_bfloat16*)y, n, H, W, C);
   return lnst_status();
@@ -1755,6 +1758,7 @@ extern "C" int lnst_avgpool2_bf16_bwd(const void* g_y, const void* mask, void* g
                                       int32_t C, void* stream) {
   if (!g_y || !g_x || n < 1 || H < 2 || W < 2 || C < 8 || C % 8) return LNST_EARG;
   const int64_t total = (int64_t)n * ((H + 1) / 2) * ((W + 1) / 2) * (C / 8);   // one thread per 2x2 quad, 8 channels
+  if (total >= 0x7fffffff) return LNST_EARG;
   tc::avgpool2_bf16_bwd_k<<<lnst_blocks(total, 256), 256, 0, lnst_stream(stream)>>>(
       (const __nv_bfloat16*)g_y, (const __nv_bfloat16*)mask, (__nv_bfloat16*)g_x, n, H, W, C);
   return lnst_status();

@@ -110,11 +110,12 @@ __global__ void smooth3_col_k(const float* __restrict__ in, const float* __restr
                               int D, int H, int W, SubVol sv, float w_side, float w_mid, int ZT) {
   const int xw = (sv.ex + SM_VEC - 1) / SM_VEC;
   const int zc = (sv.ez + ZT - 1) / ZT;
-  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= (int64_t)zc * sv.ey * xw) return;
-  const int x0 = sv.ox + (int)(t % xw) * SM_VEC;
-  const int y = sv.oy + (int)((t / xw) % sv.ey);
-  const int z0 = sv.oz + (int)(t / ((int64_t)xw * sv.ey)) * ZT;
+  const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;       // 32-bit index arithmetic: < 2^31 cells
+  if (t >= (unsigned)(zc * sv.ey * xw)) return;
+  const unsigned q = t / (unsigned)xw, zq = q / (unsigned)sv.ey;
+  const int x0 = sv.ox + (int)(t - q * (unsigned)xw) * SM_VEC;
+  const int y = sv.oy + (int)(q - zq * (unsigned)sv.ey);
+  const int z0 = sv.oz + (int)zq * ZT;
   const int z1 = min(z0 + ZT, sv.oz + sv.ez), x_end = sv.ox + sv.ex;
   float a[SM_VEC], b[SM_VEC], c[SM_VEC];
   smooth_slice<MODE>(in, aux, z0 - 1, y, x0, D, H, W, w_side, w_mid, a);
@@ -146,10 +147,11 @@ static inline void smooth_weights(int k, float& side, float& mid) {
 }
 
 __global__ void fill_box_k(float* __restrict__ vol, int H, int W, SubVol sv, float value) {
-  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= (int64_t)sv.ez * sv.ey * sv.ex) return;
-  const int x = sv.ox + (int)(t % sv.ex), y = sv.oy + (int)((t / sv.ex) % sv.ey);
-  const int z = sv.oz + (int)(t / ((int64_t)sv.ex * sv.ey));
+  const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;       // 32-bit index arithmetic: < 2^31 cells
+  if (t >= (unsigned)(sv.ez * sv.ey * sv.ex)) return;
+  const unsigned q = t / (unsigned)sv.ex, zq = q / (unsigned)sv.ey;
+  const int x = sv.ox + (int)(t - q * (unsigned)sv.ex), y = sv.oy + (int)(q - zq * (unsigned)sv.ey);
+  const int z = sv.oz + (int)zq;
   vol[((int64_t)z * H + y) * W + x] = value;
 }
 

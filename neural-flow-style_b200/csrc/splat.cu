@@ -343,10 +343,14 @@ __global__ void __launch_bounds__(256) splat_wavg_bwd3_k(const float* __restrict
 // box variant: combines only the cells of the sub-volume and clears the num it consumed
 __global__ void splat_wavg_combine_box_k(const float* __restrict__ wmap, float* __restrict__ num, int nk,
                                          int64_t cells, int H, int W, SubVol sv, float* __restrict__ out) {
-  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= (int64_t)sv.ez * sv.ey * sv.ex) return;
-  const int x = sv.ox + (int)(t % sv.ex), y = sv.oy + (int)((t / sv.ex) % sv.ey);
-  const int z = sv.oz + (int)(t / ((int64_t)sv.ex * sv.ey));
+  // 32-bit index arithmetic (a volume has fewer than 2^31 cells): the 64-bit divisions cost more than the
+  // five memory accesses of a cell
+  const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (unsigned)(sv.ez * sv.ey * sv.ex)) return;
+  const unsigned q = t / (unsigned)sv.ex;
+  const int x = sv.ox + (int)(t - q * (unsigned)sv.ex);
+  const unsigned zq = q / (unsigned)sv.ey;
+  const int y = sv.oy + (int)(q - zq * (unsigned)sv.ey), z = sv.oz + (int)zq;
   const int64_t c = ((int64_t)z * H + y) * W + x;
   float s = 0.f;
   for (int k = 0; k < nk; ++k) {
