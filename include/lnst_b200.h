@@ -202,7 +202,7 @@ int lnst_set_conv_persistent(int32_t on);
  * fp32 [128,16]. */
 int lnst_umma_probe(const void* x, const void* b, float* out, int32_t pitched, int32_t ky, int32_t kx,
                     int32_t base_mode, void* stream);
-/* Tuning switch (default 1): 1 = layers whose weights fit in shared memory load one halo'd patch per tile
+/* Tuning switch (default 2): 1 = layers whose weights fit in shared memory load one halo'd patch per tile
  * and read the 9 taps through descriptor offsets; 2 = every layer does (weights streamed when they do not
  * fit); 0 = one TMA tile per tap everywhere. */
 int lnst_set_conv_halo(int32_t on);

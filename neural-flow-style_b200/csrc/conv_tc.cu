@@ -1169,7 +1169,8 @@ static void pick_tile(int H, int W, int& TH, int& TW) {
   }
 }
 
-static int conv_halo = 1;         // tuning switch: 1 = halo'd-patch kernel for the 3x3 convolutions
+static int conv_halo = 2;         // tuning switch: 0 = per-tap kernel, 1 = halo'd-patch kernel where the weights stay
+                                  // resident, 2 = halo'd-patch kernel for every 3x3 convolution (weights streamed otherwise)
 
 // smem plan of the halo kernel: weights resident when they fit beside >= 3 patch stages
 template <int BLOCK_N, bool OUT3>
@@ -1623,9 +1624,11 @@ static int run_tc_gemm(const void* x, const void* wmat, const float* bias, const
   using namespace tc;
   if (!x || !wmat || !y || n < 1 || H < 1 || W < 1 || Cin < 64 || Cout < 64 || Cin % 64 || Cout % 64)
     return LNST_EARG;
-  // The halo'd-patch kernel wins when the layer's weights stay resident in shared memory (9*Cin*Cout*2 B
-  // beside >= 3 patch stages: conv1_2, conv2_1 and their data gradients); with streamed weights the
-  // per-tap kernels are faster (measured, tools/convbench.py), so those layers keep them.
+  // The halo'd-patch kernel reads every input byte once per tile instead of once per tap; the weights stay
+  // resident in shared memory when 9*Cin*Cout*2 B fit beside >= 3 patch stages (conv1_2, conv2_1 and their data
+  // gradients) and stream through their own ring otherwise.  Since the issue loops run warp-uniform it beats the
+  // per-tap kernel on every layer (tools/convbench.py, 18 images: conv2_2 45.5 vs 59.0 us, conv3_1 28.0 vs 35.5),
+  // whose 32 KiB of TMA writes per k-step compete with the MMAs' own operand reads for shared-memory bandwidth.
   const int bn_ = (Cout % 128 == 0) ? 128 : 64;
   const bool resident = (Cout == bn_) && (9 * (Cin / 64) * bn_ * 128 + 3 * PATCH_STRIDE <= 232448 - 2048 - 1024 - 512 - (bn_ >= 128 ? 8192 : 0) - 128);
   if (taps == 9 && !w_img && !addend && conv_halo && (resident || conv_halo == 2)) {

@@ -28,6 +28,8 @@ def timeit(fn, reps=20):
 n = 9
 layers = [('conv1_2', 200, 64, 64), ('conv2_1', 100, 64, 128), ('conv2_2', 100, 128, 128), ('conv3_1', 50, 128, 256),
           ('d conv3_1', 50, 256, 128), ('d conv2_1', 100, 128, 64)]
+if len(sys.argv) > 1:
+    n = int(sys.argv[1])
 for name, hw, cin, cout in layers:
     x = torch.randn(n, hw, hw, cin, device=dev).to(torch.bfloat16)
     w = (torch.randn(9, cout, cin, device=dev) / (3 * cin ** 0.5)).to(torch.bfloat16)
@@ -36,13 +38,13 @@ for name, hw, cin, cout in layers:
     mask = torch.randn(n, hw, hw, cout, device=dev).to(torch.bfloat16)
     flops = 2.0 * n * hw * hw * 9 * cin * cout
     row = []
-    for halo in (0, 1):
+    for halo in (0, 1, 2):
         lib.call('lnst_set_conv_halo', halo)
         us = timeit(lambda: ops.conv3x3_bf16_tc(x, w, b, relu=True, y=y))
         usm = timeit(lambda: ops.conv3x3_bf16_tc(x, w, None, relu=False, mask=mask, y=y))
         row.append('halo=%d %7.1f us (%6.1f TF/s)  masked %7.1f us' % (halo, us, flops / us / 1e6, usm))
     print('%-10s %s' % (name, ' | '.join(row)), flush=True)
-lib.call('lnst_set_conv_halo', 1)
+lib.call('lnst_set_conv_halo', 2)
 g = torch.randn(n, 200, 200, 64, device=dev).to(torch.bfloat16)
 wd = torch.randn(3, 3, 64, 3, device=dev)
 wd16 = torch.zeros(9, 16, 64, dtype=torch.bfloat16, device=dev)

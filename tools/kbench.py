@@ -116,7 +116,7 @@ def main():
     lib.call('lnst_set_conv_halo', 0)
     st.net.tc.first_bwd_tc = False
     add('lossnet fwd+bwd (per-tap convs)', lossnet, 0)
-    lib.call('lnst_set_conv_halo', 1)
+    lib.call('lnst_set_conv_halo', 2)
     st.net.tc.first_bwd_tc = True
     add('lossnet fwd+bwd (all views)', lossnet, 0)
     add('zero g_ds', lambda: ops.fill_box(g_ds, box, 0.0), 4 * Vb)
