@@ -117,12 +117,15 @@ def algorithmic_units(name, a, nk=2):
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures
 # (profiles/), keyed by (workload, entry point); None where no capture exists.
-TRAFFIC = {   # bytes per launch, profiles/r1_ncu_full_final.csv (mean over the entry point's launches of one C3 step)
-    ('C3', 'lnst_conv3x3_bf16_tc'): 34.7e6,
+TRAFFIC = {   # bytes per launch, profiles/r1_ncu_full_final2.csv (mean over the entry point's launches of one C3 step)
+    ('C3', 'lnst_conv3x3_bf16_tc'): 34.6e6,        # 3 x halo<64> (58.4 MB) + halo<128> resident (11.7) + 4 x halo<128> streamed (22.5)
     ('C3', 'lnst_raymarch_bwd_box'): 25.4e6,
     ('C3', 'lnst_raymarch_fwd_box'): 13.1e6,
-    ('C3', 'lnst_splat_wavg_fwd_box'): 86.4e6,
-    ('C3', 'lnst_splat_wavg_bwd_coef'): 39.9e6,
+    ('C3', 'lnst_splat_wavg_fwd_box'): 86.7e6,     # num kernel 40.4 + combine 46.3
+    ('C3', 'lnst_splat_wavg_bwd_coef'): 40.0e6,
+    ('C3', 'lnst_smooth3_relu_bwd_box'): 21.8e6,
+    ('C3', 'lnst_smooth3_relu_fwd_box'): 11.8e6,
+    ('C3', 'lnst_adam_iterate_dev'): 42.1e6,
 }
 
 
