@@ -219,9 +219,14 @@ def run_engine(args):
     rank = int(os.environ.get('RANK', '0'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
     torch.cuda.set_device(local)
+    real_stdout = None
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')    # keep NCCL's banner off stdout (one JSON line)
+        # stdout carries exactly ONE JSON line: NCCL prints its version banner with a plain printf when the
+        # communicator comes up (NCCL_DEBUG=VERSION/INFO on the box), so fd 1 points at stderr until the line is due
+        sys.stdout.flush()
+        real_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     dev = torch.device('cuda', local)
     lib = _lib.get()
@@ -409,6 +414,9 @@ def run_engine(args):
     }
     if world == 1 and not args.no_cpu_baseline:
         out['cpu_baseline'] = cpu_baseline(wl, budget_s=args.cpu_budget)
+    if real_stdout is not None:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
     print(json.dumps(out), flush=True)
     _finish(world, dist)
 
