@@ -39,7 +39,8 @@ def _setup_paths():
     for p in (os.path.join(ROOT, 'tests'), os.path.join(ROOT, 'neural-flow-style_b200'), ROOT):
         if p not in sys.path:
             sys.path.append(p)
-    for p in (REF, SHIM):                      # the reference's modules and the TF stand-in win
+    real_tf = bool(os.environ.get('LNST_REAL_TF'))  # a real TensorFlow 1.15 installation: leave the stand-in out
+    for p in ((REF,) if real_tf else (REF, SHIM)):  # the reference's modules and the TF stand-in win
         if p in sys.path:
             sys.path.remove(p)
         sys.path.insert(0, p)
@@ -136,13 +137,15 @@ def case_inputs(name):
 def run_reference(name):
     _setup_paths()
     import tensorflow as tf
-    assert 'shim' in tf.__version__
+    real_tf = bool(os.environ.get('LNST_REAL_TF'))
+    assert real_tf or 'shim' in tf.__version__
     from lnst import synth
     kind = CASES[name][0]
     hcfg, params = case_inputs(name)
     cfg = _cfg_from_helper(hcfg)
     cfg.rng = np.random.RandomState(cfg.seed)
-    register_weights(cfg, synth.vgg_weights('vgg_16' if '16' in cfg.network else 'vgg_19'))
+    if not real_tf:                            # real TF: <data_dir>/<model_dir>/vgg_19.ckpt must hold the seeded weights
+        register_weights(cfg, synth.vgg_weights('vgg_16' if '16' in cfg.network else 'vgg_19'))
     if kind == '2c':
         import styler_2p as mod
     else:
