@@ -103,6 +103,15 @@ CASES = {
                                                     w_content=1.0, content_layer='conv2_1', content_channel=5), 1000),
     'density_sequence': ('3d', 'smoke', dict(res=12, iter=3, rotate=False, num_frames=4, window_sigma=1.0,
                                              frames_per_opt=2, style_layer=['conv1_2'], w_style_layer=[1.0]), 600),
+    # key frames 0,2,4 optimised, frames 1,3 interpolated (styler_3p.py:392-397); 'both' view sampling re-drawn per iteration
+    'density_interp_both': ('3d', 'smoke', dict(res=12, iter=2, rotate=True, n_views=3, sample_type='both', num_frames=5,
+                                                interp=2, window_sigma=0.8, style_layer=['conv1_2'], w_style_layer=[1.0]), 500),
+    # density regulariser (styler_base.py:217-223) and a content TARGET image (:135-141, :233-247)
+    'density_reg_content_image': ('3d', 'smoke', dict(res=12, iter=3, rotate=False, w_density=1e-6, w_content=0.5,
+                                                      w_content_amp=2.0, content_layer='conv1_2', content_image=True, top_k=0,
+                                                      style_layer=['conv2_1'], w_style_layer=[1.0]), 700),
+    'position_clip_vgg16': ('3p', 'liquid', dict(res=12, iter=3, clip=True, network='vgg_16.ckpt',
+                                                 style_layer=['conv1_2', 'conv2_2'], w_style_layer=[0.7, 0.3]), 600),
     'position_liquid': ('3p', 'liquid', dict(res=12, iter=3, w_pressure=0.5, style_layer=['conv1_2'],
                                              w_style_layer=[1.0]), 700),
     'position_smoke_views': ('3p', 'liquid', dict(res=12, iter=2, rotate=True, n_views=3, render_liquid=False,
@@ -160,6 +169,8 @@ def run_reference(name):
     if cfg.w_style:
         assert cfg.octave_n == 1
         styler.style_img = synth.style_image(hw[0], hw[1])
+    if getattr(cfg, 'content_image', False):   # load_img would read config.content_target; same-size seeded image instead
+        styler.content_img = synth.style_image(hw[0], hw[1], seed=11)
     out = styler.run(params)
     res_d = {'l': np.asarray(out['l'], np.float64)}
     if kind == '2c':                           # styler_2p.py:289-314: 'd' is the uint8 colour image, 'c' the masked colours

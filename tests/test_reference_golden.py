@@ -24,7 +24,8 @@ sys.path.insert(0, GOLD)
 import make_reference_golden as M  # noqa: E402
 
 CASES_3D = ['density_noview', 'density_sequential', 'density_resize_tv_content', 'density_octaves_poisson',
-            'density_sequence', 'position_liquid', 'position_smoke_views']
+            'density_sequence', 'density_interp_both', 'density_reg_content_image', 'position_clip_vgg16',
+            'position_liquid', 'position_smoke_views']
 CASES_2D = ['colour_2d', 'colour_2d_mask', 'colour_2d_frames']
 
 
@@ -39,6 +40,13 @@ def _style_targets(cfg):
     res = cfg.resolution
     hw = [int(int(s) * cfg.resize_scale) for s in res[-2:]] if not np.isclose(cfg.resize_scale, 1) else list(res[-2:])
     return [synth.style_image(hw[0], hw[1])] * cfg.octave_n
+
+
+def _content_targets(cfg):
+    from lnst import synth
+    if not getattr(cfg, 'content_image', False):
+        return None
+    return [synth.style_image(int(cfg.resolution[-2]), int(cfg.resolution[-1]), seed=11)] * cfg.octave_n
 
 
 def _check(out, want, kind, ltol=2e-4, ftol=2e-4):
@@ -71,8 +79,10 @@ def test_oracle_matches_reference_run_3d(name):
     import oracle.vgg
     from oracle.styler import Oracle3P
     cfg, params = M.case_inputs(name)
-    out = Oracle3P(cfg, oracle.vgg.synthetic_weights()).run(params, style_targets=_style_targets(cfg),
-                                                           view_mode='sequential')
+    model = 'vgg_16' if '16' in cfg.network else 'vgg_19'
+    out = Oracle3P(cfg, oracle.vgg.synthetic_weights(model)).run(params, style_targets=_style_targets(cfg),
+                                                                content_targets=_content_targets(cfg),
+                                                                view_mode='sequential')
     _check(out, _ref(name), M.CASES[name][0], ltol=2e-5, ftol=1e-4)
 
 
@@ -93,10 +103,13 @@ def test_engine_matches_reference_run_3d(name, dev):
     cfg, params = M.case_inputs(name)
     cfg.conv_math = 'fp32'
     cfg.view_mode = 'sequential'
-    st = Styler(cfg, weights=synth.vgg_weights())
+    st = Styler(cfg, weights=synth.vgg_weights('vgg_16' if '16' in cfg.network else 'vgg_19'))
     tg = _style_targets(cfg)
     if tg is not None:
         st.style_img = tg[0]
+    ct = _content_targets(cfg)
+    if ct is not None:
+        st.content_img = ct[0]
     out = st.run(params)
     _check(out, _ref(name), M.CASES[name][0])
 
