@@ -8,6 +8,7 @@
 #include "common.cuh"
 
 #define RM_UNROLL 4
+#define RMB_UNROLL 2   // backward: two samples in flight keep the kernel at 64 registers (4 needed 96: 20 % occupancy)
 
 struct VolDims {
   int D, H, W;
@@ -481,19 +482,19 @@ __global__ void __launch_bounds__(128) raymarch_rot_bwd_k(const float* __restric
   pend = far_prev;
   int idx_prev = LNST_NO_CELL;                         // anchor of the previous live, sampled cell
   int pend_idx = -1;                                   // voxel index of the plane waiting in pend
-  for (int i0 = w_lo; i0 <= w_hi; i0 += RM_UNROLL) {
-    Cell c[RM_UNROLL];
-    float d[RM_UNROLL];
-    Plane4 lo[RM_UNROLL], hi[RM_UNROLL];
-    bool cont[RM_UNROLL], lv[RM_UNROLL];
+  for (int i0 = w_lo; i0 <= w_hi; i0 += RMB_UNROLL) {
+    Cell c[RMB_UNROLL];
+    float d[RMB_UNROLL];
+    Plane4 lo[RMB_UNROLL], hi[RMB_UNROLL];
+    bool cont[RMB_UNROLL], lv[RMB_UNROLL];
 #pragma unroll
-    for (int u = 0; u < RM_UNROLL; ++u) {
+    for (int u = 0; u < RMB_UNROLL; ++u) {
       const int i = min(i0 + u, g.D - 1);              // tail: a repeated sample, masked below
       c[u] = locate(l, (float)i, g);
       lv[u] = i0 + u >= i_lo && i0 + u <= i_hi;
     }
 #pragma unroll
-    for (int u = 0; u < RM_UNROLL; ++u) {
+    for (int u = 0; u < RMB_UNROLL; ++u) {
       cont[u] = false;
       if (!liquid && lv[u]) {
         const float* p = vol + c[u].idx;
@@ -504,7 +505,7 @@ __global__ void __launch_bounds__(128) raymarch_rot_bwd_k(const float* __restric
       }
     }
 #pragma unroll
-    for (int u = 0; u < RM_UNROLL; ++u) {
+    for (int u = 0; u < RMB_UNROLL; ++u) {
       d[u] = 0.f;
       if (!liquid && lv[u]) {
         if (cont[u]) lo[u] = (u == 0) ? far_prev : hi[u - 1];
@@ -512,11 +513,11 @@ __global__ void __launch_bounds__(128) raymarch_rot_bwd_k(const float* __restric
       }
     }
     if (!liquid) {
-      far_prev = hi[RM_UNROLL - 1];
-      idx_prev = lv[RM_UNROLL - 1] ? c[RM_UNROLL - 1].idx : LNST_NO_CELL;
+      far_prev = hi[RMB_UNROLL - 1];
+      idx_prev = lv[RMB_UNROLL - 1] ? c[RMB_UNROLL - 1].idx : LNST_NO_CELL;
     }
 #pragma unroll
-    for (int u = 0; u < RM_UNROLL; ++u) {
+    for (int u = 0; u < RMB_UNROLL; ++u) {
       const bool live = lv[u];
       float gk;
       if (liquid) {
