@@ -296,6 +296,27 @@ int lnst_mul_bcast(const float* a, const float* b, int32_t C, float* out, int64_
 int lnst_advect(const float* d, const float* vel, int32_t dim, const int32_t* dims, int32_t C, float* out,
                 void* stream);
 
+/* ---- grid -> particle gathers and the resimulation step (transform.py:771-1231, -------------
+ *      test_smokegun_resim.py:17-112: the data-prep stage that produces the stylisation inputs) --- */
+/* g2p: sample all C channels of a grid g [n0,n1,(n2),C] at normalised particle positions p (+ disp, may be
+ * NULL) [n,dim] in the grid's axis order.  linear = 0: Catmull-Rom (g2p_cubic, :778-1108, 4^dim clamped
+ * taps, offsets measured from the clamped anchor as the reference does); 1: g2p_linear (:1110-1231).
+ * out [n,C] is overwritten. */
+int lnst_g2p(const float* g, int32_t dim, const int32_t* dims, int32_t C, const float* p, const float* disp,
+             int64_t n, int32_t linear, float* out, void* stream);
+/* RK4 particle advection through a velocity grid u [n0,n1,(n2),dim] (normalised units, channel k <-> axis k):
+ * v, v1 = u(x + v/2), v2 = u(x + v1/2), v3 = u(x + v2); x_adv = x + time_step*(v + 2 v1 + 2 v2 + v3)/6
+ * (test_smokegun_resim.py:36-55).  One kernel; v_out (may be NULL) receives the blended velocity. */
+int lnst_rk4_advect(const float* u, int32_t dim, const int32_t* dims, const float* x, int64_t n, float time_step,
+                    int32_t linear, float* x_adv, float* v_out, void* stream);
+/* loss += weight * mean(where(d_rec > 0, d_rec - rest_density, 0)^2) and, if g_d != NULL, its gradient w.r.t.
+ * d_rec (test_smokegun_resim.py:69-74; styler_3p.py:96-98).  The caller zeroes `loss` (one device float). */
+int lnst_pressure_loss(const float* d_rec, int64_t cells, float rest_density, float weight, float* loss,
+                       float* g_d, void* stream);
+/* out[z,y,x] = a[z,y,x] - b[z,H-1-y,x]: residual between a density grid and a splatted field (whose H axis is
+ * stored flipped): `d - d_hi[:,:,::-1]` and d_diff of test_smokegun_resim.py:92,106. */
+int lnst_sub_fliph(const float* a, const float* b, float* out, int32_t D, int32_t H, int32_t W, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -82,6 +82,10 @@ SIGNATURES = {
     'lnst_clip_bwd': [vp, vp, f32, f32, f32, vp, i64, vp],
     'lnst_mul_bcast': [vp, vp, i32, vp, i64, vp],
     'lnst_advect': [vp, vp, i32, IP, i32, vp, vp],
+    'lnst_g2p': [vp, i32, IP, i32, vp, vp, i64, i32, vp, vp],
+    'lnst_rk4_advect': [vp, i32, IP, vp, i64, f32, i32, vp, vp, vp],
+    'lnst_pressure_loss': [vp, i64, f32, f32, vp, vp, vp],
+    'lnst_sub_fliph': [vp, vp, vp, i32, i32, i32, vp],
 }
 # entry points that only exist in the CUDA build (tcgen05 / TMA); filled in by conv_tc.cu
 CUDA_ONLY = {

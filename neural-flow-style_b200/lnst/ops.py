@@ -333,6 +333,47 @@ def advect(d, vel):
     return out
 
 
+# ---- grid -> particle, resimulation step (csrc/gather.cu) ---------------------------------------
+def _dims3(shape, dim):
+    return (C.c_int32 * 3)(*([int(s) for s in shape[:dim]] + [1] * (3 - dim)))
+
+
+def g2p(g, p, disp=None, linear=False):
+    """g [n0,n1,(n2),C] sampled at p (+disp) [N,dim] (normalised, grid axis order) -> [N,C]
+    (transform.py:771-1231)"""
+    dim = p.shape[-1]
+    out = torch.empty(p.shape[0], g.shape[-1], dtype=f32, device=g.device)
+    _lib.get().call('lnst_g2p', ptr(g), dim, _dims3(g.shape, dim), g.shape[-1], ptr(p), ptr(disp), p.shape[0],
+                    int(bool(linear)), ptr(out), _s(g))
+    return out
+
+
+def rk4_advect(u, x, time_step, linear=False, want_v=False):
+    """x_adv = x + time_step * RK4-blended velocity sampled from u [n0,n1,(n2),dim] (test_smokegun_resim.py:36-55)"""
+    dim = x.shape[-1]
+    assert u.shape[-1] == dim
+    x_adv = torch.empty_like(x)
+    v = torch.empty_like(x) if want_v else None
+    _lib.get().call('lnst_rk4_advect', ptr(u), dim, _dims3(u.shape, dim), ptr(x), x.shape[0], float(time_step),
+                    int(bool(linear)), ptr(x_adv), ptr(v), _s(u))
+    return (x_adv, v) if want_v else x_adv
+
+
+def pressure_loss(d_rec, rest_density, weight, loss, g_d=None):
+    """loss += weight*mean(where(d>0, d-rho0, 0)^2); g_d (optional, like d_rec) <- its gradient"""
+    _lib.get().call('lnst_pressure_loss', ptr(d_rec), d_rec.numel(), float(rest_density), float(weight), ptr(loss),
+                    ptr(g_d), _s(d_rec))
+
+
+def sub_fliph(a, b, out=None):
+    """a - flip_H(b) for [D,H,W] volumes"""
+    D, H, W = a.shape
+    if out is None:
+        out = torch.empty_like(a)
+    _lib.get().call('lnst_sub_fliph', ptr(a), ptr(b), ptr(out), D, H, W, _s(a))
+    return out
+
+
 # ---- loss net (tensor-core path, bf16 NHWC) ---------------------------------------------------
 bf16 = torch.bfloat16
 

@@ -361,3 +361,79 @@ def rot_mat(phi0, phi1, phi_unit, theta0, theta1, theta_unit, sample_type='unifo
                 views += extra[:nv - len(views)]
     mats = [np.matmul(rot_y_3d(v['theta']), rot_z_3d(v['phi'])) for v in views]
     return mats, views
+
+
+# --------------------------------------------------------------------------------------
+# grid -> particle gathers (resimulation / data-prep stage)
+# --------------------------------------------------------------------------------------
+def _g2p_axis(pos, length, taps):
+    """Clamped tap indices + fractional offset along one axis (``transform.py:796-838`` cubic,
+    ``:1128-1162`` linear).  The reference re-assigns x1 (x0 for linear) by ``clip_by_value``
+    BEFORE computing ``dx = x - (x1 + 0.5)`` (``:999``, ``:1200``): the offset is measured from the
+    clamped anchor, so particles outside the grid extrapolate.  Restated as is."""
+    x = pos * float(length)
+    f = torch.floor(x - 0.5).to(torch.int64)
+    first = f - 1 if taps == 4 else f
+    idx = [torch.clamp(first + i, 0, length - 1) for i in range(taps)]
+    anchor = idx[1] if taps == 4 else idx[0]
+    return idx, x - (anchor.to(pos.dtype) + 0.5)
+
+
+def _hermite(A, B, C, D, t):
+    """``transform.py:972-978``."""
+    a = A * (-0.5) + B * 1.5 + C * (-1.5) + D * 0.5
+    b = A + B * (-2.5) + C * 2.0 + D * (-0.5)
+    c = A * (-0.5) + C * 0.5
+    return a * t * t * t + b * t * t + c * t + B
+
+
+def g2p_cubic(g, p, is_2d=True):
+    """Catmull-Rom grid->particle sampling at cell centres, ``transform.py:778-1108``.
+    g [1,n0,n1,(n2),C], p [1,N,dim] normalised in the grid's axis order -> [1,N,C]."""
+    dims = list(g.shape[1:-1])
+    C = g.shape[-1]
+    flat = g.reshape(-1, C)
+    ix, tx = _g2p_axis(p[0, :, 0], dims[0], 4)
+    iy, ty = _g2p_axis(p[0, :, 1], dims[1], 4)
+    tx, ty = tx[:, None], ty[:, None]
+    if is_2d:
+        rows = [_hermite(*[flat[ix[a] * dims[1] + iy[b]] for a in range(4)], tx) for b in range(4)]
+        out = _hermite(*rows, ty)
+    else:
+        iz, tz = _g2p_axis(p[0, :, 2], dims[2], 4)
+        tz = tz[:, None]
+        planes = []
+        for e in range(4):
+            rows = [_hermite(*[flat[(ix[a] * dims[1] + iy[b]) * dims[2] + iz[e]] for a in range(4)], tx)
+                    for b in range(4)]
+            planes.append(_hermite(*rows, ty))
+        out = _hermite(*planes, tz)
+    return out[None]
+
+
+def g2p_linear(g, p, is_2d=True):
+    """Bi/tri-linear grid->particle sampling at cell centres, ``transform.py:1110-1231``."""
+    dims = list(g.shape[1:-1])
+    C = g.shape[-1]
+    flat = g.reshape(-1, C)
+    ix, tx = _g2p_axis(p[0, :, 0], dims[0], 2)
+    iy, ty = _g2p_axis(p[0, :, 1], dims[1], 2)
+    out = 0
+    if is_2d:
+        for a in range(2):
+            for b in range(2):
+                w = (tx if a else 1.0 - tx) * (ty if b else 1.0 - ty)
+                out = out + w[:, None] * flat[ix[a] * dims[1] + iy[b]]
+    else:
+        iz, tz = _g2p_axis(p[0, :, 2], dims[2], 2)
+        for a in range(2):
+            for b in range(2):
+                for e in range(2):
+                    w = (tx if a else 1.0 - tx) * (ty if b else 1.0 - ty) * (tz if e else 1.0 - tz)
+                    out = out + w[:, None] * flat[(ix[a] * dims[1] + iy[b]) * dims[2] + iz[e]]
+    return out[None]
+
+
+def g2p(g, p, is_2d=True, is_linear=False):
+    """``transform.py:771-776``."""
+    return g2p_linear(g, p, is_2d) if is_linear else g2p_cubic(g, p, is_2d)

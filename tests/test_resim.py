@@ -1,0 +1,148 @@
+"""Resimulation (data-prep) path, ``test_smokegun_resim.py:17-217`` + ``transform.py:771-1231``:
+oracle and engine against vectors produced by the reference's own ``g2p`` / ``SimG2P`` code
+(``tests/golden/make_resim_golden.py`` -> ``ref_resim.npz``), and kernel-level parity against the oracle.
+
+Kernel tests run twice: on the CPU interpreter of the kernel sources here (``dev=emu``) and on the B200
+through the C-ABI (``dev=cuda``, ``-m gpu``).
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, 'golden'))
+import make_resim_golden as G  # noqa: E402  (inputs only; the reference is not needed to run the tests)
+
+from lnst import ops  # noqa: E402
+from lnst.resim import SimG2P  # noqa: E402
+from oracle import transform as T  # noqa: E402
+from oracle.resim import OracleSimG2P  # noqa: E402
+from test_kernel_parity import close  # noqa: E402
+
+REF = np.load(os.path.join(HERE, 'golden', 'ref_resim.npz'))
+
+
+# ---- oracle vs the reference's vectors (CPU) ----------------------------------------------------
+@pytest.mark.parametrize('dim', [2, 3])
+@pytest.mark.parametrize('linear', [False, True])
+def test_oracle_g2p_matches_reference(dim, linear):
+    I = G.g2p_inputs()
+    g, p = torch.tensor(I['g%d' % dim]), torch.tensor(I['p%d' % dim])
+    got = T.g2p(g[None], p[None], is_2d=dim == 2, is_linear=linear)
+    want = REF['g2p%d_%s' % (dim, 'linear' if linear else 'cubic')]
+    np.testing.assert_allclose(got.numpy(), want, rtol=0, atol=2e-6 * np.abs(want).max())
+
+
+def _check_frames(run_frame, p0, tol_l, tol_p, tol_r):
+    c, ds, us = G.resim_inputs()
+    p, p_id = p0, np.arange(p0.shape[0])
+    for t in range(ds.shape[0]):
+        res = run_frame(p, p_id, ds[t], us[t])
+        p, p_id = res['p'], res['p_id']
+        np.testing.assert_allclose(res['l'], REF['f%d_l' % t], rtol=tol_l)
+        assert res['p'].shape == REF['f%d_p' % t].shape           # same particles seeded (d_diff > threshold)
+        np.testing.assert_array_equal(res['p_id'], REF['f%d_p_id' % t])
+        np.testing.assert_allclose(res['p'], REF['f%d_p' % t], rtol=0, atol=tol_p)
+        np.testing.assert_allclose(res['p_den'], REF['f%d_p_den' % t], rtol=0, atol=tol_r)
+        np.testing.assert_allclose(res['d_smp'], REF['f%d_d_smp' % t], rtol=0, atol=tol_r)
+        np.testing.assert_allclose(res['d_diff'], REF['f%d_d_diff' % t], rtol=0, atol=tol_r)
+
+
+def test_oracle_simg2p_matches_reference_run():
+    c, ds, us = G.resim_inputs()
+    sim = OracleSimG2P(c, src_region=G.SRC_REGION)
+    from oracle.resim import sample
+    p0, _ = sample(ds[0], disc=c.disc, threshold=0, src_region=G.SRC_REGION)
+    np.testing.assert_array_equal(p0, REF['p0'])
+    _check_frames(sim.optimize, p0, 1e-5, 2e-6, 2e-5)
+    p_adv, d_rec = sim.naive_adv(REF['p0'], us[0], np.ones([REF['p0'].shape[0], 1]))
+    np.testing.assert_allclose(p_adv, REF['naive_p'], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(d_rec, REF['naive_d'], rtol=0, atol=1e-5)
+
+
+# ---- kernels vs the oracle / the reference's vectors (emu here, cuda on the B200) -----------------
+@pytest.mark.parametrize('dim', [2, 3])
+@pytest.mark.parametrize('linear', [False, True])
+def test_g2p_kernel(dev, dim, linear):
+    I = G.g2p_inputs()
+    g, p = torch.tensor(I['g%d' % dim]), torch.tensor(I['p%d' % dim])
+    got = ops.g2p(g.to(dev), p.to(dev), linear=linear)
+    close(got, torch.tensor(REF['g2p%d_%s' % (dim, 'linear' if linear else 'cubic')][0]), tol=3e-6, what='g2p ref')
+    # displacement argument + a wider channel count than one register window
+    rng = np.random.RandomState(3)
+    shape = [5, 6, 7][:dim] + [6]
+    g6 = torch.tensor(rng.randn(*shape).astype(np.float32))
+    disp = torch.tensor(rng.uniform(-0.05, 0.05, p.shape).astype(np.float32))
+    got = ops.g2p(g6.to(dev), p.to(dev), disp.to(dev), linear=linear)
+    want = T.g2p(g6[None], (p + disp)[None], is_2d=dim == 2, is_linear=linear)[0]
+    close(got, want, tol=3e-6, what='g2p disp C=6')
+
+
+def test_g2p_empty_and_bad_args(dev):
+    g = torch.zeros(3, 3, 3, 1).to(dev)
+    out = ops.g2p(g, torch.zeros(0, 3).to(dev))
+    assert out.shape == (0, 1)
+    from lnst._lib import LnstError
+    with pytest.raises(LnstError):
+        ops.g2p(g, torch.zeros(4, 1).to(dev))            # dim must be 2 or 3
+
+
+@pytest.mark.parametrize('dim', [2, 3])
+@pytest.mark.parametrize('linear', [False, True])
+def test_rk4_advect_kernel(dev, dim, linear):
+    rng = np.random.RandomState(11)
+    shape = [7, 8, 6][:dim]
+    u = torch.tensor(rng.uniform(-0.08, 0.08, shape + [dim]).astype(np.float32))
+    x = torch.tensor(rng.uniform(-0.02, 1.02, (200, dim)).astype(np.float32))
+    got, v = ops.rk4_advect(u.to(dev), x.to(dev), 0.5, linear=linear, want_v=True)
+    xb, ub = x[None], u[None]
+    f = lambda q: T.g2p(ub, q, is_2d=dim == 2, is_linear=linear)      # test_smokegun_resim.py:36-55
+    v0 = f(xb)
+    v1 = f(xb + v0 * 0.5)
+    v2 = f(xb + v1 * 0.5)
+    v3 = f(xb + v2)
+    vm = (v0 + v1 * 2 + v2 * 2 + v3) / 6
+    close(v, vm[0], tol=5e-6, what='rk4 v')
+    close(got, (xb + vm * 0.5)[0], tol=1e-6, what='rk4 x_adv')
+
+
+def test_pressure_loss_kernel(dev):
+    rng = np.random.RandomState(4)
+    d = rng.uniform(500, 1500, (9, 11, 13)).astype(np.float32)
+    d[rng.rand(*d.shape) < 0.4] = 0.0                     # empty cells carry no pressure
+    d[0, 0, 0] = -3.0
+    dt = torch.tensor(d, requires_grad=True)
+    pr = torch.where(dt > 0, dt - 1000.0, torch.zeros_like(dt))
+    want = 0.7 * (pr ** 2).mean()
+    want.backward()
+    loss = torch.zeros(1).to(dev)
+    g = torch.empty(d.shape).to(dev)
+    ops.pressure_loss(torch.tensor(d).to(dev), 1000.0, 0.7, loss, g)
+    np.testing.assert_allclose(float(loss.cpu()), float(want.detach()), rtol=2e-6)
+    close(g, dt.grad, tol=1e-6, what='pressure grad')
+    loss2 = torch.zeros(1).to(dev)
+    ops.pressure_loss(torch.tensor(d).to(dev), 1000.0, 0.7, loss2)       # loss only
+    np.testing.assert_allclose(float(loss2.cpu()), float(want.detach()), rtol=2e-6)
+
+
+def test_sub_fliph_kernel(dev):
+    rng = np.random.RandomState(6)
+    a, b = rng.randn(4, 5, 6).astype(np.float32), rng.randn(4, 5, 6).astype(np.float32)
+    got = ops.sub_fliph(torch.tensor(a).to(dev), torch.tensor(b).to(dev))
+    np.testing.assert_array_equal(got.cpu().numpy(), a - b[:, ::-1])
+
+
+def test_simg2p_matches_reference_run(dev):
+    """The drop-in ``SimG2P`` (engine through the C-ABI) against the reference's own run, three frames with
+    re-seeding; then the naive-advection branch."""
+    c, ds, us = G.resim_inputs()
+    sim = SimG2P(c, device=dev, src_region=G.SRC_REGION)
+    p0, p_id = sim.sample(ds[0], disc=c.disc, threshold=0)
+    np.testing.assert_array_equal(p0, REF['p0'])
+    _check_frames(sim.optimize, p0, 2e-5, 3e-6, 5e-5)
+    p_adv, d_rec = sim.naive_adv(REF['p0'], us[0], np.ones([REF['p0'].shape[0], 1]))
+    np.testing.assert_allclose(p_adv, REF['naive_p'], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(d_rec, REF['naive_d'], rtol=0, atol=1e-5)
