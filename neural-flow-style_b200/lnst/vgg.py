@@ -37,15 +37,53 @@ def model_name(network):
     return 'vgg_16' if '16' in os.path.basename(str(network)) else 'vgg_19'
 
 
+# torchvision's ImageNet normalisation (its VGG weights expect (x/255 - mean)/std; the reference feeds
+# x - 255*mean with no std, vgg.py:18-20,50-53)
+_TV_STD = (0.229, 0.224, 0.225)
+
+
+def from_torchvision(state_dict, model='vgg_19'):
+    """Slim-layout weights from a torchvision ``vgg16`` / ``vgg19`` state dict
+    (``features.<i>.weight`` [Cout,Cin,3,3], ``features.<i>.bias``; batch-norm variants are not
+    supported).  OIHW -> HWIO; the 1/(255*std_c) input scaling torchvision expects is folded into
+    conv1_1 so that the engine's mean-only preprocessing (``vgg.py:50-53``) produces the same
+    activations as torchvision's own pipeline (with the reference's average pooling)."""
+    convs = sorted({int(k.split('.')[1]) for k in state_dict if k.startswith('features.') and k.endswith('.weight')})
+    names = [n for n in layer_order(model) if n.startswith('conv')]
+    if len(convs) != len(names):
+        raise ValueError('state dict has %d conv layers, %s needs %d' % (len(convs), model, len(names)))
+    out = {}
+    for name, idx in zip(names, convs):
+        w = torch.as_tensor(state_dict['features.%d.weight' % idx]).detach().to(torch.float32)
+        b = torch.as_tensor(state_dict['features.%d.bias' % idx]).detach().to(torch.float32)
+        if w.ndim != 4 or tuple(w.shape[2:]) != (3, 3):
+            raise ValueError('%s: unexpected weight shape %s' % (name, tuple(w.shape)))
+        w = w.permute(2, 3, 1, 0).contiguous()                # [3,3,Cin,Cout]
+        if name == 'conv1_1':
+            w = w / (255.0 * torch.tensor(_TV_STD).reshape(1, 1, 3, 1))
+        out[name] = (w, b.contiguous())
+    return out
+
+
 def load_weights(path, model='vgg_19'):
-    """Slim-layout weights from an .npz export of the slim checkpoint."""
-    if not os.path.exists(path):
-        alt = os.path.splitext(path)[0] + '.npz'
-        if not os.path.exists(alt):
+    """Slim-layout weights from ``<model_path>``: an ``.npz`` export of the slim checkpoint (keys
+    ``vgg_19/conv1/conv1_1/weights`` or ``conv1_1/weights``) or a torchvision state dict
+    (``.pth`` / ``.pt``, see ``from_torchvision``).  The path itself (``vgg_19.ckpt``, a TF V1 checkpoint that
+    cannot be parsed offline) is tried first, then the same stem with ``.npz``, ``.pth``, ``.pt``."""
+    if not os.path.exists(path) or path.endswith('.ckpt'):
+        stem = os.path.splitext(path)[0]
+        for ext in ('.npz', '.pth', '.pt'):
+            if os.path.exists(stem + ext):
+                path = stem + ext
+                break
+        else:
             raise FileNotFoundError(
-                'loss-network weights not found: %s (or %s).  Export vgg_19.ckpt to .npz with keys '
-                '"vgg_19/conv1/conv1_1/weights" or pass weights= to Styler.' % (path, alt))
-        path = alt
+                'loss-network weights not found: %s(.npz|.pth|.pt).  Export vgg_19.ckpt to .npz with keys '
+                '"vgg_19/conv1/conv1_1/weights", save a torchvision state dict, or pass weights= to Styler.'
+                % stem)
+    if path.endswith(('.pth', '.pt')):
+        sd = torch.load(path, map_location='cpu', weights_only=True)
+        return from_torchvision(sd.get('state_dict', sd) if isinstance(sd, dict) else sd, model)
     blob = np.load(path)
     out = {}
     for name in layer_order(model):
