@@ -12,7 +12,7 @@ reference hard-codes ``d[76:124,231:279,16:64]`` for its 200x300x200 demo grid
 (``test_smokegun_resim.py:117-119``); the scaled-down case needs a window that fits its 12x16x10 grid, so
 the subclass below repeats ``sample`` with that one line parameterised.
 
-Output: ``tests/golden/ref_resim.npz``; ``tests/test_resim.py`` holds the oracle (CPU) and the CUDA path
+Output: ``tests/golden/ref_resim.npz``; ``tests/test_widen_resim.py`` holds the oracle (CPU) and the CUDA path
 (``-m gpu``) to it.
 """
 import os

@@ -138,7 +138,7 @@ def test_smokegun_driver(dev, tmp_path):
     direct = Styler(cfg2, weights=synth.vgg_weights())
     direct.style_img = np.float32(Image.open(cfg.style_target))
     ref = direct.run({'p': p_l, 'r': r_l})
-    np.testing.assert_allclose(out['l'], ref['l'], rtol=1e-6)
+    np.testing.assert_allclose(out['l'], ref['l'], rtol=1e-4)      # atomics reorder sums between two runs
 
 
 def test_chocolate_driver_writes_particles(dev, tmp_path):
