@@ -317,6 +317,39 @@ int lnst_pressure_loss(const float* d_rec, int64_t cells, float rest_density, fl
  * stored flipped): `d - d_hi[:,:,::-1]` and d_diff of test_smokegun_resim.py:92,106. */
 int lnst_sub_fliph(const float* a, const float* b, float* out, int32_t D, int32_t H, int32_t W, void* stream);
 
+/* ---- GraphDef loss networks (inception5h; styler_base.py:19-31,53-57,91-94) -- fp32 NHWC ------------
+ * The reference imports tensorflow_inception_graph.pb with tf.import_graph_def and reads layers by tensor
+ * name; these replace the TF ops of that graph (Conv2D + BiasAdd, Relu, MaxPool, LRN, Concat) and their
+ * gradients w.r.t. the data.  `accumulate` != 0: the result is ADDED to g_x (a tensor feeding several
+ * branches sums their cotangents). */
+/* y[pix, 0:Cout] = [relu](conv(x, w HWIO) + bias), stride/padding explicit (TF SAME: pad_top = pad_total/2);
+ * ldy >= Cout = row stride of y in floats (write into a channel slice of a concat buffer). bias may be NULL. */
+int lnst_conv2d_f32(const float* x, const float* w, const float* bias, float* y, int32_t n, int32_t H, int32_t W,
+                    int32_t Cin, int32_t Cout, int32_t kh, int32_t kw, int32_t stride, int32_t pad_top,
+                    int32_t pad_left, int32_t OH, int32_t OW, int32_t ldy, int32_t relu, void* stream);
+/* g_x [n,H,W,Cin] (+)= conv2d data gradient of g_y (row stride ldg >= Cout). */
+int lnst_conv2d_bwd_data_f32(const float* g_y, int32_t ldg, const float* w, float* g_x, int32_t n, int32_t H,
+                             int32_t W, int32_t Cin, int32_t Cout, int32_t kh, int32_t kw, int32_t stride,
+                             int32_t pad_top, int32_t pad_left, int32_t OH, int32_t OW, int32_t accumulate,
+                             void* stream);
+int lnst_relu_fwd(const float* x, float* y, int64_t n, void* stream);
+/* g_x (+)= g_y * (y > 0) */
+int lnst_relu_bwd(const float* g_y, const float* y, float* g_x, int64_t n, int32_t accumulate, void* stream);
+/* tf.nn.max_pool k x k (padding cells never win) and MaxPoolGrad (first maximum in scan order takes the cotangent). */
+int lnst_maxpool_fwd(const float* x, float* y, int32_t n, int32_t H, int32_t W, int32_t C, int32_t k, int32_t stride,
+                     int32_t pad_top, int32_t pad_left, int32_t OH, int32_t OW, void* stream);
+int lnst_maxpool_bwd(const float* g_y, const float* x, float* g_x, int32_t n, int32_t H, int32_t W, int32_t C,
+                     int32_t k, int32_t stride, int32_t pad_top, int32_t pad_left, int32_t OH, int32_t OW,
+                     int32_t accumulate, void* stream);
+/* tf.nn.lrn: y_c = x_c (bias + alpha sum_{|j-c|<=depth_radius} x_j^2)^-beta, and LRNGrad. */
+int lnst_lrn_fwd(const float* x, float* y, int64_t pixels, int32_t C, int32_t depth_radius, float bias, float alpha,
+                 float beta, void* stream);
+int lnst_lrn_bwd(const float* g_y, const float* x, float* g_x, int64_t pixels, int32_t C, int32_t depth_radius,
+                 float bias, float alpha, float beta, int32_t accumulate, void* stream);
+/* dst[p, 0:C] (+)= src[p, 0:C] with row strides ld_src / ld_dst: tf.concat along channels and its gradient slices. */
+int lnst_copy_channels(const float* src, int32_t ld_src, float* dst, int32_t ld_dst, int32_t C, int64_t pixels,
+                       int32_t accumulate, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -374,6 +374,95 @@ def sub_fliph(a, b, out=None):
     return out
 
 
+# ---- GraphDef loss networks (csrc/graphnet.cu), fp32 NHWC -----------------------------------------------
+def same_pad(size, k, stride):
+    """TF 'SAME': (output size, pad before) -- the odd cell goes after."""
+    out = -(-size // stride)
+    total = max((out - 1) * stride + k - size, 0)
+    return out, total // 2
+
+
+def conv_out(x_shape, w_shape, stride, padding):
+    n, H, W, _ = x_shape
+    kh, kw = int(w_shape[0]), int(w_shape[1])
+    if padding == 'SAME':
+        (OH, pt), (OW, pl) = same_pad(H, kh, stride), same_pad(W, kw, stride)
+    else:
+        OH, OW, pt, pl = (H - kh) // stride + 1, (W - kw) // stride + 1, 0, 0
+    return OH, OW, pt, pl
+
+
+def conv2d_f32(x, w, bias, stride=1, padding='SAME', relu=False, out=None, ch_off=0):
+    """x [n,H,W,Cin], w [kh,kw,Cin,Cout] -> [n,OH,OW,Cout]; with ``out`` [n,OH,OW,Ctot] the result is written into
+    channels [ch_off, ch_off+Cout)."""
+    n, H, W, cin = x.shape
+    kh, kw, _, cout = w.shape
+    OH, OW, pt, pl = conv_out(x.shape, w.shape, stride, padding)
+    if out is None:
+        out = torch.empty(n, OH, OW, cout, dtype=f32, device=x.device)
+    ld = out.shape[-1]
+    _lib.get().call('lnst_conv2d_f32', ptr(x), ptr(w), ptr(bias), C.c_void_p(out.data_ptr() + 4 * ch_off), n, H, W, cin,
+                    cout, kh, kw, stride, pt, pl, OH, OW, ld, int(bool(relu)), _s(x))
+    return out
+
+
+def conv2d_bwd_data_f32(g_y, w, x_shape, stride, padding, g_x, accumulate, ch_off=0):
+    n, H, W, cin = x_shape
+    kh, kw, _, cout = w.shape
+    OH, OW, pt, pl = conv_out(x_shape, w.shape, stride, padding)
+    _lib.get().call('lnst_conv2d_bwd_data_f32', C.c_void_p(g_y.data_ptr() + 4 * ch_off), g_y.shape[-1], ptr(w), ptr(g_x),
+                    n, H, W, cin, cout, kh, kw, stride, pt, pl, OH, OW, int(bool(accumulate)), _s(g_y))
+    return g_x
+
+
+def relu_fwd(x):
+    y = torch.empty_like(x)
+    _lib.get().call('lnst_relu_fwd', ptr(x), ptr(y), x.numel(), _s(x))
+    return y
+
+
+def relu_bwd(g_y, y, g_x, accumulate):
+    _lib.get().call('lnst_relu_bwd', ptr(g_y), ptr(y), ptr(g_x), y.numel(), int(bool(accumulate)), _s(y))
+    return g_x
+
+
+def maxpool_fwd(x, k, stride, padding='SAME'):
+    n, H, W, ch = x.shape
+    OH, OW, pt, pl = conv_out(x.shape, (k, k), stride, padding)
+    y = torch.empty(n, OH, OW, ch, dtype=f32, device=x.device)
+    _lib.get().call('lnst_maxpool_fwd', ptr(x), ptr(y), n, H, W, ch, k, stride, pt, pl, OH, OW, _s(x))
+    return y
+
+
+def maxpool_bwd(g_y, x, k, stride, padding, g_x, accumulate):
+    n, H, W, ch = x.shape
+    OH, OW, pt, pl = conv_out(x.shape, (k, k), stride, padding)
+    _lib.get().call('lnst_maxpool_bwd', ptr(g_y), ptr(x), ptr(g_x), n, H, W, ch, k, stride, pt, pl, OH, OW,
+                    int(bool(accumulate)), _s(x))
+    return g_x
+
+
+def lrn_fwd(x, depth_radius, bias, alpha, beta):
+    y = torch.empty_like(x)
+    _lib.get().call('lnst_lrn_fwd', ptr(x), ptr(y), x.numel() // x.shape[-1], x.shape[-1], int(depth_radius), float(bias),
+                    float(alpha), float(beta), _s(x))
+    return y
+
+
+def lrn_bwd(g_y, x, depth_radius, bias, alpha, beta, g_x, accumulate):
+    _lib.get().call('lnst_lrn_bwd', ptr(g_y), ptr(x), ptr(g_x), x.numel() // x.shape[-1], x.shape[-1], int(depth_radius),
+                    float(bias), float(alpha), float(beta), int(bool(accumulate)), _s(x))
+    return g_x
+
+
+def copy_channels(src, src_off, dst, dst_off, ch, accumulate=False):
+    """dst[..., dst_off:dst_off+ch] (+)= src[..., src_off:src_off+ch] for NHWC tensors with the same pixel count"""
+    pixels = src.numel() // src.shape[-1]
+    _lib.get().call('lnst_copy_channels', C.c_void_p(src.data_ptr() + 4 * src_off), src.shape[-1],
+                    C.c_void_p(dst.data_ptr() + 4 * dst_off), dst.shape[-1], ch, pixels, int(bool(accumulate)), _s(src))
+    return dst
+
+
 # ---- loss net (tensor-core path, bf16 NHWC) ---------------------------------------------------
 bf16 = torch.bfloat16
 
