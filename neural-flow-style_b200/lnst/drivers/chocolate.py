@@ -82,10 +82,9 @@ def main(config, weights=None):
     config.clip = False
     config.num_kernels = 1
     config.k = 3
-    if 'inception' in config.network:
-        config.network = 'vgg_19.ckpt'
-        config.style_layer = ['conv2_1', 'conv3_1']
-        config.w_style_layer = [0.5, 0.5]
+    config.network = 'tensorflow_inception_graph.pb'
+    config.style_layer = ['conv2d2', 'mixed3b', 'mixed4b']
+    config.w_style_layer = [1, 1, 1]
     config.octave_n = 2
     config.octave_scale = 1.8
     config.render_liquid = True

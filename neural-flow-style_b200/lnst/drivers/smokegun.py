@@ -54,8 +54,7 @@ def run(config, weights=None):
 
 
 def main(config, weights=None):
-    """scene constants of test_smokegun.py:110-160 (the loss network defaults to VGG-19: the inception graph
-    the reference script names is not built)"""
+    """scene constants of test_smokegun.py:110-160"""
     config.dataset = 'smokegun'
     config.d_path = 'pt_low_o2/%03d.bgeo'
     config.num_kernels = 2
@@ -77,10 +76,9 @@ def main(config, weights=None):
     config.frames_per_opt = 1
     config.target_field = 'd'
     config.lr = 0.1
-    if 'inception' in config.network:
-        config.network = 'vgg_19.ckpt'
-        config.style_layer = ['conv2_1', 'conv3_1']
-        config.w_style_layer = [0.5, 0.5]
+    config.network = 'tensorflow_inception_graph.pb'
+    config.style_layer = ['conv2d2', 'mixed3b', 'mixed4b']
+    config.w_style_layer = [1, 1, 1]
     config.octave_n = 1
     config.octave_scale = 1.8
     config.transmit = 0.01

@@ -32,15 +32,19 @@ class StylerBase(object):
             device = torch.device('cuda', torch.cuda.current_device()) if lib.kind == 'cuda' else torch.device('cpu')
         self.device = torch.device(device)
         self.model_path = os.path.join(self.data_dir, self.model_dir, self.network)   # :18
-        if 'vgg' not in self.model_path:
-            raise NotImplementedError(
-                'only the VGG loss networks are built (vgg.py); the inception5h GraphDef '
-                '(styler_base.py:19-31) is not in the reference repository')
         if self.batch_size != 1:
             raise NotImplementedError('batch_size > 1 is not built yet (every reference driver uses 1)')
-        if weights is None:
-            weights = load_weights(self.model_path, model_name(self.network))
-        self.net = LossNet(weights, model_name(self.network), self.device, math=self.conv_math)
+        if 'vgg' in self.model_path:
+            if weights is None:
+                weights = load_weights(self.model_path, model_name(self.network))
+            self.net = LossNet(weights, model_name(self.network), self.device, math=self.conv_math)
+        else:
+            # inception5h: a frozen GraphDef read by tensor name (styler_base.py:17-31,53-57); ``weights`` may be
+            # the parsed node list (lnst.graphdef.Node), else the .pb at model_path is read
+            from . import graphdef
+            from .graphnet import GraphNet
+            nodes = weights if weights is not None else graphdef.load(self.model_path)
+            self.net = GraphNet(nodes, self.device, pool1=bool(getattr(self, 'pool1', False)))
         self.content_img = None
         self.style_img = None
         self._content_feat = None              # set per octave by run() when a content target image is given
@@ -158,13 +162,14 @@ class StylerBase(object):
                                            mask=style_masks[l] if style_masks else None)
 
         def add_loss_grad(name, g):
-            is_conv = 1 if name.startswith('conv') else 0
+            is_conv = 1 if (name.startswith('conv') and not hasattr(self.net, 'relu_masked')) else 0
             if style_on:
                 for li, l in enumerate(self.style_layer):
                     if l != name:
                         continue
                     ch = style_grams[li].shape[0]
-                    P = self._feature_pixels(hw[0], hw[1], name)
+                    P = self.net.feature_pixels(acts, name) if hasattr(self.net, 'feature_pixels') else \
+                        self._feature_pixels(hw[0], hw[1], name)
                     coef = self.w_style * self.w_style_layer[li] * 4.0 / (2.0 * P * ch)
                     g = self.net.gram_grad(acts, name, handles[l], coef, g, is_conv)
             if self.w_content and self.content_layer == name:

@@ -106,3 +106,72 @@ def vgg_weights(model='vgg_19', seed=19):
             w['conv%d_%d' % (b, i)] = (wt, bs)
             cin = cout
     return w
+
+
+# ---- synthetic inception5h GraphDef (the real tensorflow_inception_graph.pb is not available offline) -------
+_INCEPTION_MODULES = [       # name, 1x1, 3x3 bottleneck, 3x3, 5x5 bottleneck, 5x5, pool_reduce  (GoogLeNet / inception5h)
+    ('mixed3a', 64, 96, 128, 16, 32, 32), ('mixed3b', 128, 128, 192, 32, 96, 64), 'maxpool4',
+    ('mixed4a', 192, 96, 204, 16, 48, 64), ('mixed4b', 160, 112, 224, 24, 64, 64),
+    ('mixed4c', 128, 128, 256, 24, 64, 64), ('mixed4d', 112, 144, 288, 32, 64, 64),
+    ('mixed4e', 256, 160, 320, 32, 128, 128), 'maxpool10',
+    ('mixed5a', 256, 160, 320, 48, 128, 128), ('mixed5b', 384, 192, 384, 48, 128, 128),
+]
+
+
+def inception5h_nodes(seed=5, width_div=1, upto=None):
+    """The inception5h topology with the file's node names (``conv2d0_pre_relu/conv`` -> ``conv2d0_pre_relu`` ->
+    ``conv2d0``, ``mixed3a_3x3_bottleneck_pre_relu``, ``mixed3a`` ...; run.bat:15-20 and test_smokegun.py:141 name
+    such tensors) as a list of ``lnst.graphdef.Node`` with seeded He-normal weights.  ``width_div`` divides every
+    channel count (tests); ``upto`` stops after that module.  LRN attributes are those of the Caffe GoogLeNet
+    conversion (radius 2, bias 1, alpha 2e-5, beta .75) -- the real file's own attributes are used when it is
+    loaded.  Serialise with ``lnst.graphdef.serialize`` to get a ``.pb``."""
+    from .graphdef import Node
+    rng = np.random.RandomState(seed)
+    nodes = [Node('input', 'Placeholder', [], {})]
+
+    def ch(c):
+        return max(int(c) // width_div, 2)
+
+    def conv(name, src, k, cin, cout, stride=1):
+        w = (rng.randn(k, k, cin, cout) * np.sqrt(2.0 / (k * k * cin))).astype(np.float32)
+        b = (0.05 * rng.randn(cout)).astype(np.float32)
+        nodes.append(Node(name + '_w', 'Const', [], {'value': w}))
+        nodes.append(Node(name + '_b', 'Const', [], {'value': b}))
+        nodes.append(Node(name + '_pre_relu/conv', 'Conv2D', [src, name + '_w'],
+                          {'strides': [1, stride, stride, 1], 'padding': b'SAME'}))
+        nodes.append(Node(name + '_pre_relu', 'BiasAdd', [name + '_pre_relu/conv', name + '_b'], {}))
+        nodes.append(Node(name, 'Relu', [name + '_pre_relu'], {}))
+        return name, cout
+
+    def pool(name, src, stride):
+        nodes.append(Node(name, 'MaxPool', [src], {'ksize': [1, 3, 3, 1], 'strides': [1, stride, stride, 1],
+                                                    'padding': b'SAME'}))
+        return name
+
+    def lrn(name, src):
+        nodes.append(Node(name, 'LRN', [src], {'depth_radius': 2, 'bias': 1.0, 'alpha': 2e-5, 'beta': 0.75}))
+        return name
+
+    cur, c = conv('conv2d0', 'input', 7, 3, ch(64), stride=2)
+    cur = lrn('localresponsenorm0', pool('maxpool0', cur, 2))
+    cur, c = conv('conv2d1', cur, 1, c, ch(64))
+    cur, c = conv('conv2d2', cur, 3, c, ch(192))
+    cur = pool('maxpool1', lrn('localresponsenorm1', cur), 2)
+    for m in _INCEPTION_MODULES:
+        if isinstance(m, str):
+            cur = pool(m, cur, 2)
+            continue
+        name, c1, c3b, c3, c5b, c5, cp = m
+        a, ca = conv(name + '_1x1', cur, 1, c, ch(c1))
+        b, cb = conv(name + '_3x3_bottleneck', cur, 1, c, ch(c3b))
+        b, cb = conv(name + '_3x3', b, 3, cb, ch(c3))
+        d, cd = conv(name + '_5x5_bottleneck', cur, 1, c, ch(c5b))
+        d, cd = conv(name + '_5x5', d, 5, cd, ch(c5))
+        e = pool(name + '_pool', cur, 1)
+        e, ce = conv(name + '_pool_reduce', e, 1, c, ch(cp))
+        nodes.append(Node(name + '/concat_dim', 'Const', [], {'value': np.asarray(3, np.int32)}))
+        nodes.append(Node(name, 'Concat', [name + '/concat_dim', a, b, d, e], {'N': 4}))
+        cur, c = name, ca + cb + cd + ce
+        if upto == name:
+            break
+    return nodes

@@ -65,7 +65,11 @@ class _Base:
     def __init__(self, cfg, weights, dtype=torch.float32):
         self.cfg = cfg
         self.dtype = dtype
-        self.weights = {k: (w.to(dtype), b.to(dtype)) for k, (w, b) in weights.items()}
+        self.nodes = None
+        if isinstance(weights, (list, tuple)):         # a GraphDef loss network (inception5h): styler_base.py:17-31
+            self.nodes = list(weights)
+        else:
+            self.weights = {k: (w.to(dtype), b.to(dtype)) for k, (w, b) in weights.items()}
         self.model = 'vgg_16' if '16' in cfg.network else 'vgg_19'
 
     # styler_base.py:91-94
@@ -82,6 +86,9 @@ class _Base:
         if c.w_content:
             want.add(c.content_layer)
         want.discard('input')
+        if self.nodes is not None:
+            from . import graphnet
+            return graphnet.forward(d_img, self.nodes, sorted(want), pool1=bool(getattr(c, 'pool1', False)))
         order = [n for n, _, _ in V.layer_specs(self.model)]
         order_all = []
         for b in range(1, 6):

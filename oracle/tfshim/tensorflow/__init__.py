@@ -552,20 +552,170 @@ class Session:
 InteractiveSession = Session
 
 
+# ----------------------------------------------------------------------------------------------
+# GraphDef import (inception5h, styler_base.py:17-31,53-57,91-94).  The protobuf messages are REAL protobuf
+# messages (google.protobuf, declared on the fly with TensorFlow's field numbers), so ParseFromString and the
+# reference's in-place attribute edit ``n.attr['strides'].list.i[1:3] = [1,1]`` run on the genuine library; the
+# engine's own wire-format reader (lnst/graphdef.py) is not involved on this side.
+_IMPORTED = {}          # 'import/<node>:0' -> Tensor   (one default graph, like the reference uses it)
+_IMPORTED_OPS = []
+
+
+def _graph_messages():
+    from google.protobuf import descriptor_pb2, descriptor_pool, message_factory
+    Fd = descriptor_pb2.FieldDescriptorProto
+    fd = descriptor_pb2.FileDescriptorProto(name='tfshim_graph.proto', package='tfshim', syntax='proto3')
+    O, R = Fd.LABEL_OPTIONAL, Fd.LABEL_REPEATED
+
+    def fields(m, spec):
+        for fname, num, typ, label, tname in spec:
+            f = m.field.add(name=fname, number=num, type=typ, label=label)
+            if tname:
+                f.type_name = '.tfshim.' + tname
+
+    m = fd.message_type.add(name='TensorShapeProto')
+    d = m.nested_type.add(name='Dim')
+    fields(d, [('size', 1, Fd.TYPE_INT64, O, None), ('name', 2, Fd.TYPE_STRING, O, None)])
+    fields(m, [('dim', 2, Fd.TYPE_MESSAGE, R, 'TensorShapeProto.Dim'), ('unknown_rank', 3, Fd.TYPE_BOOL, O, None)])
+    m = fd.message_type.add(name='TensorProto')
+    fields(m, [('dtype', 1, Fd.TYPE_INT32, O, None), ('tensor_shape', 2, Fd.TYPE_MESSAGE, O, 'TensorShapeProto'),
+               ('version_number', 3, Fd.TYPE_INT32, O, None), ('tensor_content', 4, Fd.TYPE_BYTES, O, None),
+               ('float_val', 5, Fd.TYPE_FLOAT, R, None), ('double_val', 6, Fd.TYPE_DOUBLE, R, None),
+               ('int_val', 7, Fd.TYPE_INT32, R, None), ('string_val', 8, Fd.TYPE_BYTES, R, None)])
+    m = fd.message_type.add(name='AttrValue')
+    lv = m.nested_type.add(name='ListValue')
+    fields(lv, [('s', 2, Fd.TYPE_BYTES, R, None), ('i', 3, Fd.TYPE_INT64, R, None), ('f', 4, Fd.TYPE_FLOAT, R, None),
+                ('b', 5, Fd.TYPE_BOOL, R, None), ('type', 6, Fd.TYPE_INT32, R, None)])
+    fields(m, [('list', 1, Fd.TYPE_MESSAGE, O, 'AttrValue.ListValue'), ('s', 2, Fd.TYPE_BYTES, O, None),
+               ('i', 3, Fd.TYPE_INT64, O, None), ('f', 4, Fd.TYPE_FLOAT, O, None), ('b', 5, Fd.TYPE_BOOL, O, None),
+               ('type', 6, Fd.TYPE_INT32, O, None), ('shape', 7, Fd.TYPE_MESSAGE, O, 'TensorShapeProto'),
+               ('tensor', 8, Fd.TYPE_MESSAGE, O, 'TensorProto')])
+    m = fd.message_type.add(name='NodeDef')
+    e = m.nested_type.add(name='AttrEntry')
+    e.options.map_entry = True
+    fields(e, [('key', 1, Fd.TYPE_STRING, O, None), ('value', 2, Fd.TYPE_MESSAGE, O, 'AttrValue')])
+    fields(m, [('name', 1, Fd.TYPE_STRING, O, None), ('op', 2, Fd.TYPE_STRING, O, None),
+               ('input', 3, Fd.TYPE_STRING, R, None), ('device', 4, Fd.TYPE_STRING, O, None),
+               ('attr', 5, Fd.TYPE_MESSAGE, R, 'NodeDef.AttrEntry')])
+    m = fd.message_type.add(name='GraphDef')
+    fields(m, [('node', 1, Fd.TYPE_MESSAGE, R, 'NodeDef')])
+    pool = descriptor_pool.DescriptorPool()
+    pool.Add(fd)
+    get = getattr(message_factory, 'GetMessageClass', None)
+    if get is None:                                            # protobuf < 4.21
+        get = message_factory.MessageFactory(pool).GetPrototype
+    return get(pool.FindMessageTypeByName('tfshim.GraphDef'))
+
+
+_GRAPHDEF_CLS = None
+
+
+def GraphDef():
+    global _GRAPHDEF_CLS
+    if _GRAPHDEF_CLS is None:
+        _GRAPHDEF_CLS = _graph_messages()
+    return _GRAPHDEF_CLS()
+
+
+def _tensor_proto_to_np(t):
+    shape = [int(d.size) for d in t.tensor_shape.dim]
+    if t.dtype == 1:
+        dt, vals = np.float32, list(t.float_val)
+    elif t.dtype == 3:
+        dt, vals = np.int32, list(t.int_val)
+    else:
+        raise NotImplementedError('tfshim: Const dtype %d' % t.dtype)
+    if t.tensor_content:
+        arr = np.frombuffer(t.tensor_content, dt)
+    else:
+        n = int(np.prod(shape)) if shape else 1
+        arr = np.asarray(vals, dt)
+        if arr.size == 1 and n > 1:
+            arr = np.full(n, arr[0], dt)
+    return arr.reshape(shape).copy()
+
+
+def _lrn(x, depth_radius=5, bias=1.0, alpha=1.0, beta=0.5, name=None):
+    """tf.nn.local_response_normalization (core/kernels/lrn_op.cc): sqr_sum over [c-r, c+r], alpha NOT divided by n."""
+    r = int(depth_radius)
+
+    def f(a):
+        sq = F.pad(a * a, (r, r))
+        s = sq[..., 0:a.shape[-1]]
+        for i in _py_range(1, 2 * r + 1):
+            s = s + sq[..., i:i + a.shape[-1]]
+        return a * torch.pow(bias + alpha * s, -beta)
+    return _unary('LRN', f, x)
+
+
+class _ImportedOp:
+    def __init__(self, name, type_):
+        self.name, self.type = name, type_
+
+
+def import_graph_def(graph_def, input_map=None, return_elements=None, name=None):
+    """tf.import_graph_def for frozen inference graphs: every node becomes a lazy Tensor named
+    '<prefix>/<node>:0' (prefix 'import'), placeholders are replaced through ``input_map``."""
+    prefix = 'import' if name is None else name
+    input_map = {k.split(':')[0]: v for k, v in (input_map or {}).items()}
+    local = {}
+
+    def ref(n):
+        n = n.split(':')[0]
+        return local[n]
+
+    for nd in graph_def.node:
+        a = nd.attr
+        ins = [i for i in nd.input if not i.startswith('^')]
+        if nd.name in input_map:
+            t = input_map[nd.name]
+        elif nd.op == 'Placeholder':
+            t = placeholder(float32, name=nd.name)
+        elif nd.op == 'Const':
+            t = constant(_tensor_proto_to_np(a['value'].tensor))
+        elif nd.op == 'Conv2D':
+            t = nn.conv2d(ref(ins[0]), ref(ins[1]), list(a['strides'].list.i), a['padding'].s.decode())
+        elif nd.op == 'BiasAdd':
+            t = add(ref(ins[0]), ref(ins[1]))
+        elif nd.op == 'Relu':
+            t = nn.relu(ref(ins[0]))
+        elif nd.op == 'MaxPool':
+            t = nn.max_pool(ref(ins[0]), list(a['ksize'].list.i), list(a['strides'].list.i), a['padding'].s.decode())
+        elif nd.op == 'LRN':
+            kw = {}
+            for k in ('depth_radius', 'bias', 'alpha', 'beta'):
+                if k in a:
+                    kw[k] = a[k].i if k == 'depth_radius' else a[k].f
+            t = _lrn(ref(ins[0]), **kw)
+        elif nd.op == 'Concat':
+            t = concat([ref(i) for i in ins[1:]], int(_tensor_value(ref(ins[0]))))
+        elif nd.op == 'ConcatV2':
+            t = concat([ref(i) for i in ins[:-1]], int(_tensor_value(ref(ins[-1]))))
+        elif nd.op == 'Identity':
+            t = identity(ref(ins[0]))
+        else:
+            raise NotImplementedError('tfshim.import_graph_def: op %s (%s)' % (nd.op, nd.name))
+        local[nd.name] = t
+        _IMPORTED['%s/%s:0' % (prefix, nd.name)] = t
+        _IMPORTED_OPS.append(_ImportedOp('%s/%s' % (prefix, nd.name), nd.op))
+    if return_elements:
+        return [ref(e) for e in return_elements]
+
+
+def _tensor_value(t):
+    return _to_t(_ev(t, {})).item() if isinstance(t, Tensor) else t
+
+
 class Graph:
+    def __init__(self):                      # a fresh graph per Styler (styler_base.py:20): forget earlier imports
+        _IMPORTED.clear()
+        del _IMPORTED_OPS[:]
+
     def get_operations(self):
-        return []
+        return list(_IMPORTED_OPS)
 
-
-class GraphDef:
-    node = []
-
-    def ParseFromString(self, s):
-        raise NotImplementedError('tfshim: GraphDef import (inception5h) is not available')
-
-
-def import_graph_def(*a, **k):
-    raise NotImplementedError('tfshim: GraphDef import (inception5h) is not available')
+    def get_tensor_by_name(self, name):
+        return _IMPORTED[name]
 
 
 @contextlib.contextmanager
@@ -1058,6 +1208,8 @@ nn = types.SimpleNamespace(
     max_pool=_pool('max', 2), max_pool3d=_pool('max', 3), avg_pool=_pool('avg', 2), avg_pool3d=_pool('avg', 3),
     top_k=_top_k,
     conv2d_transpose=None, conv3d_transpose=None,
+    lrn=lambda *a, **k: _lrn(*a, **k), local_response_normalization=lambda *a, **k: _lrn(*a, **k),
+    bias_add=lambda v, b, name=None: add(v, b),
 )
 
 
@@ -1332,6 +1484,7 @@ math = types.SimpleNamespace(squared_difference=squared_difference, ceil=ceil, f
                              sqrt=sqrt, abs=abs, maximum=maximum, minimum=minimum, reduce_sum=reduce_sum,
                              reduce_mean=reduce_mean, reduce_max=reduce_max)
 io = types.SimpleNamespace(gfile=types.SimpleNamespace(GFile=open))
+gfile = io.gfile
 _v1 = types.SimpleNamespace(
     placeholder=placeholder, where=where, variable_scope=variable_scope, variables_initializer=variables_initializer,
     train=train, initializers=initializers, InteractiveSession=InteractiveSession, Session=Session,

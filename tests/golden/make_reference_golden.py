@@ -116,11 +116,28 @@ CASES = {
                                              w_style_layer=[1.0]), 700),
     'position_smoke_views': ('3p', 'liquid', dict(res=12, iter=2, rotate=True, n_views=3, render_liquid=False,
                                                   transmit=0.05, style_layer=['conv1_2'], w_style_layer=[1.0]), 500),
+    # inception5h path (styler_base.py:17-31,53-57,91-94): the reference parses the GraphDef file (here: the seeded
+    # synthetic graph with the inception5h topology, written by lnst.graphdef.serialize and read back by the
+    # protobuf library inside oracle/tfshim), imports it and reads layers by tensor name -- semantic transfer on a
+    # pre-ReLU bottleneck channel (run.bat:15-20) plus the style layers of test_smokegun.py:141, 3 views
+    'density_inception': ('3d', 'smoke', dict(res=20, iter=3, network='tensorflow_inception_graph.pb', rotate=True,
+                                              n_views=3, w_content=0.7, content_layer='mixed3b_3x3_bottleneck_pre_relu',
+                                              content_channel=5, style_layer=['conv2d2', 'mixed3a', 'mixed3b'],
+                                              w_style_layer=[1, 1, 1]), 900),
+    'density_inception_pool1': ('3d', 'smoke', dict(res=14, iter=2, network='tensorflow_inception_graph.pb', pool1=True,
+                                                    w_style=0, w_content=1.0, content_layer='mixed3a_pool_reduce_pre_relu',
+                                                    content_channel=0), 600),
     'colour_2d': ('2c', 'dam', dict(iter=4, w_tv=0.01, style_layer=['conv1_1', 'conv2_1'], w_style_layer=[0.5, 0.5]), 0),
     'colour_2d_mask': ('2c', 'dam', dict(iter=3, style_mask=True, style_layer=['conv1_1', 'conv2_1'],
                                          w_style_layer=[0.5, 0.5]), 0),
     'colour_2d_frames': ('2c', 'dam', dict(iter=2, num_frames=3, window_sigma=1.0), 0),
 }
+
+
+def inception_nodes():
+    """The synthetic inception5h graph of the 'density_inception*' cases (shared with the tests)."""
+    from lnst import synth
+    return synth.inception5h_nodes(width_div=8, upto='mixed3b')
 
 
 def case_inputs(name):
@@ -153,7 +170,14 @@ def run_reference(name):
     hcfg, params = case_inputs(name)
     cfg = _cfg_from_helper(hcfg)
     cfg.rng = np.random.RandomState(cfg.seed)
-    if not real_tf:                            # real TF: <data_dir>/<model_dir>/vgg_19.ckpt must hold the seeded weights
+    if 'inception' in cfg.network:             # the GraphDef file the reference opens (styler_base.py:18-23)
+        import tempfile
+        from lnst import graphdef
+        cfg.data_dir = tempfile.mkdtemp(prefix='lnst_ref_')
+        os.makedirs(os.path.join(cfg.data_dir, cfg.model_dir))
+        with open(os.path.join(cfg.data_dir, cfg.model_dir, cfg.network), 'wb') as f:
+            f.write(graphdef.serialize(inception_nodes()))
+    elif not real_tf:                          # real TF: <data_dir>/<model_dir>/vgg_19.ckpt must hold the seeded weights
         register_weights(cfg, synth.vgg_weights('vgg_16' if '16' in cfg.network else 'vgg_19'))
     if kind == '2c':
         import styler_2p as mod
