@@ -16,8 +16,8 @@ from .vgg import _R_MEAN, _G_MEAN, _B_MEAN
 
 
 class Styler(StylerBase):
-    def __init__(self, self_dict, weights=None, device=None):
-        StylerBase.__init__(self, self_dict, weights=weights, device=device)
+    def __init__(self, self_dict, weights=None, device=None, content_weights=None):
+        StylerBase.__init__(self, self_dict, weights=weights, device=device, content_weights=content_weights)
         if self.style_mask and self.style_mask_on_ref:
             raise NotImplementedError('style_mask_on_ref (styler_base.py:171-173) is not built')
         if self.style_mask and self.conv_math != 'fp32':

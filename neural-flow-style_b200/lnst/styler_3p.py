@@ -77,8 +77,8 @@ class StepRunner:
 
 
 class Styler(StylerBase):
-    def __init__(self, self_dict, weights=None, device=None):
-        StylerBase.__init__(self, self_dict, weights=weights, device=device)
+    def __init__(self, self_dict, weights=None, device=None, content_weights=None):
+        StylerBase.__init__(self, self_dict, weights=weights, device=device, content_weights=content_weights)
         if self.target_field not in ('d', 'p'):
             raise ValueError("styler_3p handles target_field 'd' or 'p'")
         if 'd' in self.target_field and self.num_kernels > 4:
@@ -324,7 +324,8 @@ class Styler(StylerBase):
         """The render is gray and the tensor-core loss net can take it directly: conv1_1 folds the x255, the RGB
         replication and the mean subtraction into its weights (no TV loss, which reads d_img)."""
         wanted = self._wanted()
-        if self.w_tv or not self.net.gray_path() or 'input' in wanted or not getattr(self, 'gray_conv', True):
+        if self.w_tv or not self.net.gray_path() or 'input' in wanted or not getattr(self, 'gray_conv', True) or \
+                (self.net2 is not None and self.w_content):       # the second network reads the RGB net input
             return False
         pre = self.net.prefix(wanted)
         return bool(pre) and pre[0] == 'conv1_1'

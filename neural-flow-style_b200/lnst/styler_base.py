@@ -19,7 +19,7 @@ f32 = torch.float32
 
 
 class StylerBase(object):
-    def __init__(self, self_dict, weights=None, device=None):
+    def __init__(self, self_dict, weights=None, device=None, content_weights=None):
         # styler_base.py:14-15 -- every config attribute becomes an attribute of the styler
         for arg in vars(self_dict):
             setattr(self, arg, getattr(self_dict, arg))
@@ -45,6 +45,18 @@ class StylerBase(object):
             from .graphnet import GraphNet
             nodes = weights if weights is not None else graphdef.load(self.model_path)
             self.net = GraphNet(nodes, self.device, pool1=bool(getattr(self, 'pool1', False)))
+        # multi-net loss (engine extension, BASELINE.json configs[4]): the content loss lives on a second network
+        self.net2 = None
+        if getattr(self, 'content_network', ''):
+            path2 = os.path.join(self.data_dir, self.model_dir, self.content_network)
+            if 'vgg' in path2:
+                w2 = content_weights if content_weights is not None else load_weights(path2, model_name(self.content_network))
+                self.net2 = LossNet(w2, model_name(self.content_network), self.device, math='fp32')
+            else:
+                from . import graphdef
+                from .graphnet import GraphNet
+                nodes2 = content_weights if content_weights is not None else graphdef.load(path2)
+                self.net2 = GraphNet(nodes2, self.device, pool1=bool(getattr(self, 'pool1', False)))
         self.content_img = None
         self.style_img = None
         self._content_feat = None              # set per octave by run() when a content target image is given
@@ -76,7 +88,7 @@ class StylerBase(object):
         w = []
         if self.w_style and self.style_img is not None:
             w += list(self.style_layer)
-        if self.w_content:
+        if self.w_content and self.net2 is None:
             w.append(self.content_layer)
         return w
 
@@ -122,8 +134,9 @@ class StylerBase(object):
         """Feature of the content target at ``content_layer`` (styler_base.py:233-247): fp32 [h,w,C] on the
         device; ``image_loss_and_grad`` compares every view's feature with it."""
         x = self._target_tensor(content_target, content_shp)
-        acts = self.net.forward(x, [self.content_layer])
-        return self.net.features_f32(acts, self.content_layer)[0].contiguous()
+        net = self.net2 if self.net2 is not None else self.net
+        acts = net.forward(x, [self.content_layer])
+        return net.features_f32(acts, self.content_layer)[0].contiguous()
 
     # ---- feature-space losses + their gradient w.r.t. the net input ---------------------------------
     def style_masks_for(self, d_gray, net_hw):
@@ -172,7 +185,7 @@ class StylerBase(object):
                         self._feature_pixels(hw[0], hw[1], name)
                     coef = self.w_style * self.w_style_layer[li] * 4.0 / (2.0 * P * ch)
                     g = self.net.gram_grad(acts, name, handles[l], coef, g, is_conv)
-            if self.w_content and self.content_layer == name:
+            if self.w_content and self.net2 is None and self.content_layer == name:
                 g = self.net.content(acts, name, self.content_channel, self.w_content, loss, g, is_conv,
                                      target=getattr(self, '_content_feat', None), amp=self.w_content_amp)
             return g
@@ -180,6 +193,17 @@ class StylerBase(object):
         g_x = self.net.backward(x, acts, wanted, add_loss_grad, set(wanted), gray=gray is not None) if wanted else None
         if g_x is None:
             g_x = torch.zeros_like(x if gray is None else gray)
+        if self.w_content and self.net2 is not None:               # multi-net loss: content term on the second network
+            net2, cl = self.net2, self.content_layer
+            relu2 = 1 if (cl.startswith('conv') and not hasattr(net2, 'relu_masked')) else 0
+            acts2 = net2.forward(x, [cl])
+
+            def add2(name, g):
+                return net2.content(acts2, name, self.content_channel, self.w_content, loss, g, relu2,
+                                    target=getattr(self, '_content_feat', None), amp=self.w_content_amp)
+
+            g2 = net2.backward(x, acts2, [cl], add2, {cl})
+            ops.axpy(g_x, g2, 1.0)
         if self.w_tv:
             g_tv = torch.empty_like(d_img[0])
             for v in range(n):

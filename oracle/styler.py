@@ -62,8 +62,10 @@ def _clip(x, lo, hi):
 
 
 class _Base:
-    def __init__(self, cfg, weights, dtype=torch.float32):
+    def __init__(self, cfg, weights, dtype=torch.float32, content_weights=None):
         self.cfg = cfg
+        # multi-net loss (engine extension, BASELINE.json configs[4]): content loss on a second GraphDef network
+        self.nodes2 = list(content_weights) if content_weights is not None else None
         self.dtype = dtype
         self.nodes = None
         if isinstance(weights, (list, tuple)):         # a GraphDef loss network (inception5h): styler_base.py:17-31
@@ -86,6 +88,17 @@ class _Base:
         if c.w_content:
             want.add(c.content_layer)
         want.discard('input')
+        if self.nodes2 is not None and c.w_content:
+            from . import graphnet
+            want.discard(c.content_layer)
+            ep2 = graphnet.forward(d_img, self.nodes2, [c.content_layer], pool1=bool(getattr(c, 'pool1', False)))
+            ep = dict(self._net_first(d_img, want)) if want else {'input': d_img}
+            ep[c.content_layer] = ep2[c.content_layer]
+            return ep
+        return self._net_first(d_img, want)
+
+    def _net_first(self, d_img, want):
+        c = self.cfg
         if self.nodes is not None:
             from . import graphnet
             return graphnet.forward(d_img, self.nodes, sorted(want), pool1=bool(getattr(c, 'pool1', False)))

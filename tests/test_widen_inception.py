@@ -240,3 +240,4 @@ def test_engine_matches_reference_inception_run(name, dev):
     if tg is not None:
         st.style_img = tg[0]
     TR._check(st.run(params), want, '3d')
+
