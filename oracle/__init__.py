@@ -19,7 +19,12 @@ extent that is possible without TensorFlow:
     content, style mask) and 20 operator-level vectors;
   * the one known-answer the reference itself holds (the 5x5 bilinear-warp tables in
     ``transform.py:1865-1884``) is checked in ``tests/test_golden.py``.
+  * the resimulation path (``oracle/resim.py``, ``transform.g2p*``) is pinned the same way by
+    ``tests/golden/ref_resim.npz`` (the reference's ``test_smokegun_resim.SimG2P`` run here), the inception path
+    (``oracle/graphnet.py``) by ``ref_density_inception*.npz`` (the reference's own GraphDef parsing / import /
+    tensor naming / losses on a seeded synthetic graph; the network's op numerics themselves are UNPINNED --
+    see that module's header).
 Not pinned (no TensorFlow binary): the floating-point summation order inside TF's kernels and
 TF's platform-dependent NaN handling on CPU (the GPU rule is the one restated).
 """
-from . import transform, render, vgg, loss, adam, styler  # noqa: F401
+from . import transform, render, vgg, loss, adam, styler, resim, graphnet  # noqa: F401
