@@ -155,6 +155,14 @@ int lnst_resize_bilinear_bwd(const float* g_out, int32_t n_img, int32_t H, int32
  * mask of styler_base.py:165-169.  in [n,H,W,C] -> out [n,OH,OW,C]. */
 int lnst_resize_bicubic_fwd(const float* in, int32_t n_img, int32_t H, int32_t W, int32_t C, int32_t OH,
                             int32_t OW, float* out, void* stream);
+/* Gradient of lnst_resize_bicubic_fwd w.r.t. its input (the 3-D style mask is the render itself, so the mask
+ * carries a gradient: styler_base.py:165-169); g_in [n,H,W,C] is overwritten. */
+int lnst_resize_bicubic_bwd(const float* g_out, int32_t n_img, int32_t H, int32_t W, int32_t C, int32_t OH,
+                            int32_t OW, float* g_in, void* stream);
+/* out[p] (+)= sum_c a[p,c] b[p,c] + scale * scalar[0]  (scalar: device float, may be NULL): cotangent of the style
+ * mask, <d loss/d (F m), F> per pixel plus the term through the masked area in the Gram denominator. */
+int lnst_rowdot(const float* a, const float* b, int32_t C, int64_t P, const float* scalar, float scale,
+                int32_t accumulate, float* out, void* stream);
 /* d_img[v,p,c] = s*gray[v,p,(c)] (gray has Cg = 1 or 3 channels), x = d_img - mean_rgb. */
 int lnst_to_net_input_fwd(const float* gray, int32_t n_img, int64_t n_pix, int32_t Cg, float s,
                           float* d_img, float* x, void* stream);

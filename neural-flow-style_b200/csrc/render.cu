@@ -716,6 +716,47 @@ __global__ void resize_bicubic_fwd_k(const float* __restrict__ in, int H, int W,
   out[(int64_t)img * total + t] = acc;
 }
 
+// Transpose of resize_bicubic_fwd_k: every output pixel's cotangent goes to its 16 (clamped) taps with the same
+// weights; taps clamped onto the border accumulate there.  g_in is zeroed by the entry point.
+__global__ void resize_bicubic_bwd_k(const float* __restrict__ g_out, int H, int W, int C, int OH, int OW, float sy,
+                                     float sx, float* __restrict__ g_in) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = (int64_t)OH * OW * C;
+  if (t >= total) return;
+  const int img = blockIdx.y;
+  const int c = (int)(t % C), ox = (int)((t / C) % OW), oy = (int)(t / ((int64_t)C * OW));
+  const float fy = (float)oy * sy, fx = (float)ox * sx;
+  const float by = floorf(fy), bx = floorf(fx);
+  const float g = g_out[(int64_t)img * total + t];
+  float* b = g_in + (int64_t)img * H * W * C;
+#pragma unroll
+  for (int kx = 0; kx < 4; ++kx) {
+    const int xx = min(max((int)bx + kx - 1, 0), W - 1);
+    const float wx = keys_w(fx - (bx + (float)(kx - 1)));
+#pragma unroll
+    for (int ky = 0; ky < 4; ++ky) {
+      const int yy = min(max((int)by + ky - 1, 0), H - 1);
+      atomicAdd(b + ((int64_t)yy * W + xx) * C + c, g * wx * keys_w(fy - (by + (float)(ky - 1))));
+    }
+  }
+}
+
+// out[p] (+)= sum_c a[p,c] * b[p,c] + scale * (*scalar): the style-mask cotangent (styler_base.py:165-169):
+// d loss / d mask = <d loss / d (F*m), F> per pixel plus the pixel-independent term through the masked area.
+__global__ void rowdot_k(const float* __restrict__ a, const float* __restrict__ b, int C, int64_t P,
+                         const float* __restrict__ scalar, float scale, int accumulate, float* __restrict__ out) {
+  const int64_t p = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);     // one warp per pixel row
+  if (p >= P) return;
+  const int lane = threadIdx.x & 31;
+  float acc = 0.f;
+  for (int c = lane; c < C; c += 32) acc = fmaf(a[p * C + c], b[p * C + c], acc);
+  acc = lnst_warp_sum(acc);
+  if (lane == 0) {
+    const float v = acc + (scalar ? scale * scalar[0] : 0.f);
+    out[p] = accumulate ? out[p] + v : v;
+  }
+}
+
 __constant__ float kMeanRGB[3] = {(float)(0.485 * 255), (float)(0.456 * 255), (float)(0.406 * 255)};   // vgg.py:16-18
 
 __global__ void to_net_input_fwd_k(const float* __restrict__ gray, int64_t total_pix, int Cg, float s,
@@ -885,6 +926,24 @@ extern "C" int lnst_resize_bicubic_fwd(const float* in, int32_t n_img, int32_t H
   const float sy = (float)H / (float)OH, sx = (float)W / (float)OW;
   LNST_LAUNCH(resize_bicubic_fwd_k, dim3(lnst_blocks((int64_t)OH * OW * C, 256), n_img), dim3(256), 0,
               lnst_stream(stream), in, (int)H, (int)W, (int)C, (int)OH, (int)OW, sy, sx, out);
+  return lnst_status();
+}
+
+extern "C" int lnst_resize_bicubic_bwd(const float* g_out, int32_t n_img, int32_t H, int32_t W, int32_t C, int32_t OH,
+                                       int32_t OW, float* g_in, void* stream) {
+  if (!g_out || !g_in || n_img < 1 || H < 1 || W < 1 || C < 1 || OH < 1 || OW < 1) return LNST_EARG;
+  const float sy = (float)H / (float)OH, sx = (float)W / (float)OW;
+  cudaMemsetAsync(g_in, 0, sizeof(float) * (int64_t)n_img * H * W * C, lnst_stream(stream));
+  LNST_LAUNCH(resize_bicubic_bwd_k, dim3(lnst_blocks((int64_t)OH * OW * C, 256), n_img), dim3(256), 0,
+              lnst_stream(stream), g_out, (int)H, (int)W, (int)C, (int)OH, (int)OW, sy, sx, g_in);
+  return lnst_status();
+}
+
+extern "C" int lnst_rowdot(const float* a, const float* b, int32_t C, int64_t P, const float* scalar, float scale,
+                           int32_t accumulate, float* out, void* stream) {
+  if (!a || !b || !out || C < 1 || P < 1) return LNST_EARG;
+  LNST_LAUNCH(rowdot_k, dim3(lnst_blocks(P, 8)), dim3(256), 0, lnst_stream(stream), a, b, (int)C, P, scalar, scale,
+              (int)accumulate, out);
   return lnst_status();
 }
 

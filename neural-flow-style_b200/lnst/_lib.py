@@ -60,6 +60,8 @@ SIGNATURES = {
     'lnst_resize_bilinear_fwd': [vp, i32, i32, i32, i32, i32, i32, vp, vp],
     'lnst_resize_bilinear_bwd': [vp, i32, i32, i32, i32, i32, i32, vp, vp],
     'lnst_resize_bicubic_fwd': [vp, i32, i32, i32, i32, i32, i32, vp, vp],
+    'lnst_resize_bicubic_bwd': [vp, i32, i32, i32, i32, i32, i32, vp, vp],
+    'lnst_rowdot': [vp, vp, i32, i64, vp, f32, i32, vp, vp],
     'lnst_to_net_input_fwd': [vp, i32, i64, i32, f32, vp, vp, vp],
     'lnst_to_net_input_bwd': [vp, i32, i64, i32, f32, vp, vp],
     'lnst_conv3x3_f32': [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp],

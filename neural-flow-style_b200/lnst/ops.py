@@ -181,6 +181,22 @@ def resize_bicubic_fwd(x, oh, ow):
     return out
 
 
+def resize_bicubic_bwd(g_out, H, W):
+    """gradient of resize_bicubic_fwd: g_out [n,OH,OW,C] -> [n,H,W,C]"""
+    n, OH, OW, ch = g_out.shape
+    g_in = torch.empty(n, H, W, ch, dtype=f32, device=g_out.device)
+    _lib.get().call('lnst_resize_bicubic_bwd', ptr(g_out), n, H, W, ch, OH, OW, ptr(g_in), _s(g_out))
+    return g_in
+
+
+def rowdot(a, b, out, scalar=None, scale=0.0, accumulate=False):
+    """out[p] (+)= sum_c a[p,c] b[p,c] + scale*scalar[0]"""
+    P, ch = a.shape
+    _lib.get().call('lnst_rowdot', ptr(a), ptr(b), ch, P, ptr(scalar), float(scale), int(bool(accumulate)), ptr(out),
+                    _s(a))
+    return out
+
+
 def masked_accumulate(t, m, f, relu, g, beta):
     """g = beta*g + t * m[..., None] [* (f > 0)]"""
     _lib.get().call('lnst_masked_accumulate', ptr(t), ptr(m), ptr(f), int(relu), t.shape[-1], float(beta), ptr(g),
@@ -303,6 +319,7 @@ def temporal_gauss(x, sigma):
 
 def axpy(y, x, a):
     _lib.get().call('lnst_axpy', ptr(y), ptr(x), float(a), y.numel(), _s(y))
+    return y
 
 
 def clip_fwd(x, lo, hi):

@@ -83,9 +83,14 @@ class Styler(StylerBase):
             raise ValueError("styler_3p handles target_field 'd' or 'p'")
         if 'd' in self.target_field and self.num_kernels > 4:
             raise NotImplementedError('num_kernels > 4')
-        if self.style_mask:
-            raise NotImplementedError('style_mask in the 3-D styler (the mask depends on the optimised density: '
-                                      'styler_base.py:165-169) is not built; the 2-D colour styler has it')
+        if self.style_mask:                                        # styler_base.py:165-169 with d_gray = the render
+            if self.style_mask_on_ref:
+                raise NotImplementedError('style_mask_on_ref (styler_base.py:171-173) is not built')
+            if self.conv_math != 'fp32' and 'vgg' in self.model_path:
+                raise NotImplementedError("style_mask needs conv_math='fp32' (the masked Gram runs on the fp32 path)")
+            if 'vgg' not in self.model_path:
+                raise NotImplementedError('style_mask with a GraphDef loss network')
+            self.cuda_graphs = False        # the masked areas (Gram denominators) are read back every step
         self.rot_mat_, self.views = None, None
         if self.rotate:                                            # styler_3p.py:137-145
             self.rot_mat_, self.views = rot_mat(self.phi0, self.phi1, self.phi_unit, self.theta0, self.theta1,
@@ -290,6 +295,7 @@ class Styler(StylerBase):
             st['stats'] = ops.image_max(img, torch.empty(2 * nv, dtype=f32, device=dev))
             gray = ops.normalize_fwd(img, st['stats'], torch.empty_like(img))
         gray = gray.reshape(nv, H, W, 1)
+        st['gray0'] = gray.reshape(nv, H, W)                      # self.d_gray (styler_3p.py:161): before any resize
         nh, nw = self._net_hw((H, W))
         if (nh, nw) != (H, W):                                    # styler_base.py:35-38
             gray = ops.resize_bilinear_fwd(gray, nh, nw)
@@ -301,8 +307,9 @@ class Styler(StylerBase):
             st.update(d_img=d_img, x=x)
         return st
 
-    def _render_bwd(self, st, g_x, ds, g_ds):
-        """d loss / d x -> accumulated into g_ds (which the caller zeroed)."""
+    def _render_bwd(self, st, g_x, ds, g_ds, g_gray0=None):
+        """d loss / d x -> accumulated into g_ds (which the caller zeroed).  ``g_gray0`` [nv,H,W]: extra cotangent
+        of the un-resized gray render (style mask)."""
         nv = g_x.shape[0]
         H, W = st['hw']
         if g_x.dim() == 3:                                        # already d loss / d gray (gray path)
@@ -313,6 +320,8 @@ class Styler(StylerBase):
         if (g_x.shape[1], g_x.shape[2]) != (H, W):
             g_gray = ops.resize_bilinear_bwd(g_gray, H, W)
         g_gray = g_gray.reshape(nv, H, W)
+        if g_gray0 is not None:
+            g_gray = ops.axpy(g_gray.contiguous(), g_gray0, 1.0)
         if self.render_liquid:
             g_img = g_gray
         else:
@@ -341,12 +350,22 @@ class Styler(StylerBase):
         st = self._render(ds, rot, box, ws['bricks'], net_input=not gray_path)
         nv = st['gray'].shape[0]
         loss = torch.zeros(nv, dtype=f32, device=self.device)
+        g_gray0 = None
         if gray_path:
             g_x = self.image_loss_and_grad(None, None, style_grams, loss, gray=st['gray'])
+        elif self.style_mask and self.w_style and style_grams is not None:
+            # mask per style layer = TF-legacy bicubic resize of the render to the feature size; its cotangent comes
+            # back through the same resize and joins the render's gradient
+            masks, mg = self.style_masks_for(st['gray0'], (st['x'].shape[1], st['x'].shape[2])), {}
+            g_x = self.image_loss_and_grad(st['x'], st['d_img'], style_grams, loss, style_masks=masks, mask_grads=mg)
+            H, W = st['hw']
+            for l, dm in mg.items():
+                gm = ops.resize_bicubic_bwd(dm.reshape(nv, dm.shape[1], dm.shape[2], 1), H, W).reshape(nv, H, W)
+                g_gray0 = gm if g_gray0 is None else ops.axpy(g_gray0, gm, 1.0)
         else:
             g_x = self.image_loss_and_grad(st['x'], st['d_img'], style_grams, loss)
         g_ds = ops.fill_box(ws['g_ds'], box, 0.0)
-        self._render_bwd(st, g_x, ds, g_ds)
+        self._render_bwd(st, g_x, ds, g_ds, g_gray0)
         g_d = ops.smooth3_relu_bwd(g_ds, ds, ws['g_d'], self.k, box)
         if self.w_pressure > 0 and 'p' in self.target_field:       # styler_3p.py:96-98, styler_base.py:228-230
             pos = d > 0

@@ -154,14 +154,17 @@ class StylerBase(object):
             out[l] = (m, [float(a) for a in m.sum(dim=(1, 2)).cpu().tolist()])
         return out
 
-    def image_loss_and_grad(self, x, d_img, style_grams, loss, style_masks=None, gray=None):
+    def image_loss_and_grad(self, x, d_img, style_grams, loss, style_masks=None, gray=None, mask_grads=None):
         """x [n,H,W,3] net input (one image per view), d_img the same before mean subtraction.
         Adds each image's total feature/TV loss into ``loss[v]`` and returns d loss_v / d x_v
         stacked [n,H,W,3] (styler_base.py:127-213).
 
         ``gray`` [n,H,W] (0..1): the render is one channel replicated to RGB and the loss net can start from it
         (``LossNet.gray_path``, no TV loss): x and d_img are not read (may be None) and the result is
-        d loss_v / d gray_v [n,H,W]."""
+        d loss_v / d gray_v [n,H,W].
+
+        ``mask_grads`` (a dict, 3-D style mask): filled with {style layer: d loss / d mask [n,h,w]} -- there the mask
+        is the render itself and carries a gradient (styler_base.py:165-169)."""
         n = x.shape[0] if gray is None else gray.shape[0]
         hw = (x.shape[1], x.shape[2]) if gray is None else (gray.shape[1], gray.shape[2])
         wanted = self._wanted()
@@ -193,6 +196,9 @@ class StylerBase(object):
         g_x = self.net.backward(x, acts, wanted, add_loss_grad, set(wanted), gray=gray is not None) if wanted else None
         if g_x is None:
             g_x = torch.zeros_like(x if gray is None else gray)
+        if mask_grads is not None and style_on and style_masks:
+            for l in self.style_layer:
+                mask_grads[l] = self.net.gram_mask_grad(acts, l, handles[l])
         if self.w_content and self.net2 is not None:               # multi-net loss: content term on the second network
             net2, cl = self.net2, self.content_layer
             relu2 = 1 if (cl.startswith('conv') and not hasattr(net2, 'relu_masked')) else 0

@@ -188,7 +188,7 @@ class LossNet:
             return self.tc.gram(acts, name, Gs, weight, loss)
         f = acts[name]
         n, P, ch = f.shape[0], f.shape[1] * f.shape[2], f.shape[3]
-        out = {'G': [], 'den': [], 'Fm': [], 'mask': mask, 'weight': weight}
+        out = {'G': [], 'den': [], 'Fm': [], 'mask': mask, 'weight': weight, 'Gs': Gs, 'tmp': {}}
         for v in range(n):
             G = torch.empty(ch, ch, dtype=torch.float32, device=self.device)
             Fv, den = f[v].reshape(P, ch), 2.0 * P * ch
@@ -222,8 +222,23 @@ class LossNet:
             else:
                 tmp = torch.empty(P, ch, dtype=torch.float32, device=self.device)
                 ops.gram_bwd(handle['Fm'][v], handle['G'][v], cv, 0.0, 0, tmp)
+                handle['tmp'][v] = tmp                             # d loss / d (F m), reused by gram_mask_grad
                 ops.masked_accumulate(tmp.reshape(f[v].shape), handle['mask'][0][v], f[v], relu_mask, g[v], beta)
         return g
+
+    def gram_mask_grad(self, acts, name, handle):
+        """d loss / d mask [n,h,w] of a masked ``gram`` handle, after ``gram_grad`` ran on it (the 3-D style mask is
+        the render, styler_base.py:165-169): per pixel <d loss/d(F m), F>, plus the pixel-independent term through
+        den = 2 area C: -4 w C sum(D o (D + Gs)) / den with D = G/den - Gs."""
+        f = acts[name]
+        n, P, ch = f.shape[0], f.shape[1] * f.shape[2], f.shape[3]
+        dm = torch.empty(n, f.shape[1], f.shape[2], dtype=torch.float32, device=self.device)
+        for v in range(n):
+            D = handle['G'][v]
+            s = (D * (D + handle['Gs'])).sum().reshape(1) if handle['Gs'] is not None else (D * D).sum().reshape(1)
+            ops.rowdot(handle['tmp'][v], f[v].reshape(P, ch), dm[v].reshape(P), scalar=s,
+                       scale=-4.0 * handle['weight'] * ch / handle['den'][v])
+        return dm
 
     def content(self, acts, name, channel, weight, loss, g, relu_mask, target=None, amp=1.0):
         """Content loss on end point ``name``: channel activation (styler_base.py:143-148), or, with

@@ -127,6 +127,10 @@ CASES = {
     'density_inception_pool1': ('3d', 'smoke', dict(res=14, iter=2, network='tensorflow_inception_graph.pb', pool1=True,
                                                     w_style=0, w_content=1.0, content_layer='mixed3a_pool_reduce_pre_relu',
                                                     content_channel=0), 600),
+    # style mask in 3-D (styler_base.py:165-169): the mask is the normalised render itself, so the gradient also
+    # flows through the mask and through the masked area in the Gram denominator
+    'density_style_mask': ('3d', 'smoke', dict(res=12, iter=3, rotate=True, n_views=3, style_mask=True,
+                                               style_layer=['conv1_2', 'conv2_1'], w_style_layer=[0.5, 0.5]), 800),
     'colour_2d': ('2c', 'dam', dict(iter=4, w_tv=0.01, style_layer=['conv1_1', 'conv2_1'], w_style_layer=[0.5, 0.5]), 0),
     'colour_2d_mask': ('2c', 'dam', dict(iter=3, style_mask=True, style_layer=['conv1_1', 'conv2_1'],
                                          w_style_layer=[0.5, 0.5]), 0),

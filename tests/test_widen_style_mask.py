@@ -1,0 +1,82 @@
+"""Style mask in the 3-D styler (reference styler_base.py:165-169 with d_gray = the normalised render): the mask
+depends on the optimised density, so the loss gradient also flows through the mask (bicubic resize backward) and
+through the masked area in the Gram denominator.  Kernel parity + the reference's own run (ref_density_style_mask)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from lnst import ops
+from oracle import loss as L
+from test_kernel_parity import close
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+sys.path.insert(0, GOLD)
+
+
+@pytest.mark.parametrize('H,W,oh,ow', [(12, 12, 6, 6), (9, 14, 4, 7), (5, 6, 10, 9)])
+def test_resize_bicubic_bwd(dev, H, W, oh, ow):
+    rng = np.random.RandomState(H + ow)
+    x = torch.tensor(rng.rand(2, H, W, 1).astype(np.float32), requires_grad=True)
+    y = L.bicubic_legacy(x, oh, ow)
+    close(ops.resize_bicubic_fwd(x.detach().to(dev), oh, ow), y, tol=2e-6, what='bicubic fwd')
+    g = torch.tensor(rng.randn(*y.shape).astype(np.float32))
+    (y * g).sum().backward()
+    close(ops.resize_bicubic_bwd(g.to(dev), H, W), x.grad, tol=3e-6, what='bicubic bwd')
+
+
+def test_rowdot(dev):
+    rng = np.random.RandomState(0)
+    a, b = rng.randn(37, 70).astype(np.float32), rng.randn(37, 70).astype(np.float32)
+    s = torch.tensor([2.5])
+    out = torch.ones(37).to(dev)
+    ops.rowdot(torch.tensor(a).to(dev), torch.tensor(b).to(dev), out, scalar=s.to(dev), scale=-0.5, accumulate=True)
+    np.testing.assert_allclose(out.cpu().numpy(), 1 + (a * b).sum(1) - 1.25, rtol=2e-5, atol=2e-5)
+    ops.rowdot(torch.tensor(a).to(dev), torch.tensor(b).to(dev), out)
+    np.testing.assert_allclose(out.cpu().numpy(), (a * b).sum(1), rtol=2e-5, atol=2e-5)
+
+
+def test_engine_matches_reference_style_mask_run(dev):
+    import make_reference_golden as M
+    import test_reference_golden as TR
+    from lnst import synth
+    from lnst.styler_3p import Styler
+    name = 'density_style_mask'
+    cfg, params = M.case_inputs(name)
+    cfg.conv_math, cfg.view_mode = 'fp32', 'sequential'
+    st = Styler(cfg, weights=synth.vgg_weights(), device=dev)
+    st.style_img = TR._style_targets(cfg)[0]
+    TR._check(st.run(params), dict(np.load(os.path.join(GOLD, 'ref_%s.npz' % name))), '3d')
+
+
+def test_oracle_matches_reference_style_mask_run():
+    import make_reference_golden as M
+    import test_reference_golden as TR
+    import oracle.vgg
+    from oracle.styler import Oracle3P
+    name = 'density_style_mask'
+    cfg, params = M.case_inputs(name)
+    out = Oracle3P(cfg, oracle.vgg.synthetic_weights()).run(params, style_targets=TR._style_targets(cfg),
+                                                          view_mode='sequential')
+    TR._check(out, dict(np.load(os.path.join(GOLD, 'ref_%s.npz' % name))), '3d', ltol=2e-5, ftol=1e-4)
+
+
+def test_style_mask_with_resize_scale_matches_oracle(dev):
+    """mask from the un-resized render, net input resized (styler_base.py:35-38 after styler_3p.py:161)"""
+    from helpers import smoke_cfg
+    from lnst import synth
+    from lnst.styler_3p import Styler
+    from oracle.styler import Oracle3P
+    import oracle.vgg
+    kw = dict(res=12, iter=2, rotate=False, style_mask=True, resize_scale=1.5, conv_math='fp32',
+              style_layer=['conv1_2', 'conv2_1'], w_style_layer=[0.5, 0.5])
+    p, r = synth.smoke_particles(700, 2)
+    sty = synth.style_image(18, 18)
+    new = Styler(smoke_cfg(**kw), weights=synth.vgg_weights(), device=dev)
+    new.style_img = sty
+    out = new.run({'p': p, 'r': r})
+    ref = Oracle3P(smoke_cfg(**kw), oracle.vgg.synthetic_weights()).run({'p': p, 'r': r}, style_targets=[sty])
+    np.testing.assert_allclose(out['l'][0], ref['l'][0], rtol=3e-4)
+    assert np.abs(out['d'] - ref['d']).max() <= 3e-4 * np.abs(ref['d']).max()
