@@ -93,6 +93,12 @@ def main(config, weights=None):
     config.batch_size = 1
     config.window_sigma = 9
     config.target_field = 'p'
+    if config.w_content == 1:                                   # test_chocolate.py:237-245
+        config.tag = 'test_%s_%s_%d' % (config.target_field, config.content_layer, config.content_channel)
+    else:
+        style = os.path.splitext(os.path.basename(config.style_target))[0]
+        config.tag = 'test_%s_%s' % (config.target_field, style)
+    config.tag += '_%d_intp%d' % (config.num_frames, config.interp)
     return run(config, weights)
 
 

@@ -77,7 +77,7 @@ def main(config, weights=None):
     cell_size = 2 * config.radius * config.disc
     config.domain = [float(_ * cell_size) for _ in base]
     config.nsize = max(3 - config.disc, 1)
-    config.scale = getattr(config, 'scale', None) or 4         # upscaling for rendering
+    config.scale = 4                                           # upscaling for rendering
     config.nsize *= config.scale
     config.resolution = [base[0] * config.scale, base[1] * config.scale]
     config.frames_per_opt = 200
@@ -98,6 +98,12 @@ def main(config, weights=None):
     config.style_mask_on_ref = False
     config.style_tiling = 2
     config.w_tv = 0.01
+    if config.w_content == 1:                                   # test_dambreak2d.py:192-200
+        config.tag = 'test_%s_%s_%d' % (config.target_field, config.content_layer, config.content_channel)
+    else:
+        style = os.path.splitext(os.path.basename(config.style_target))[0]
+        config.tag = 'test_%s_%s' % (config.target_field, style)
+    config.tag += '_%d' % config.num_frames
     return run(config, weights)
 
 

@@ -215,3 +215,35 @@ def test_mac_velocity_conversion():
     u = normalised_velocity(c, 2.0)
     np.testing.assert_allclose(u[..., 0], c[..., 2] / 3 * 2.0)
     np.testing.assert_allclose(u[..., 1], -c[..., 1] / 4 * 2.0)
+
+
+# ---- scene constants: lnst.drivers.*.main against the reference scripts' own main() (captured by
+# tests/golden/make_driver_config_golden.py from the unmodified scripts) --------------------------------------
+ENGINE_ONLY = {'view_mode', 'conv_math', 'content_network', 'command', 'log_dir'}
+
+
+@pytest.mark.parametrize('ref_name,mod_name', [('test_smokegun', 'smokegun'), ('test_chocolate', 'chocolate'),
+                                               ('test_dambreak2d', 'dambreak2d'), ('test_smokegun_resim', 'smokegun_resim')])
+def test_driver_main_sets_the_reference_scene_constants(ref_name, mod_name, monkeypatch):
+    import importlib
+    import json
+    from lnst.config import get_config
+    want = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'ref_driver_configs.json')))[ref_name]
+    mod = importlib.import_module('lnst.drivers.' + mod_name)
+    got = {}
+    monkeypatch.setattr(mod, 'run', lambda cfg, *a, **k: got.update(vars(cfg)))
+    cfg, _ = get_config([])
+    mod.main(cfg)
+    diffs = []
+    for k, v in want.items():
+        if k in ENGINE_ONLY:
+            continue
+        g = got.get(k, '<missing>')
+        g = list(g) if isinstance(g, tuple) else g
+        same = (g == v) or (isinstance(v, float) and isinstance(g, (int, float)) and abs(g - v) <= 1e-12 * max(1, abs(v))) \
+            or (isinstance(v, list) and isinstance(g, list) and len(g) == len(v) and
+                all(a == b or (isinstance(a, (int, float)) and isinstance(b, (int, float)) and abs(a - b) < 1e-9)
+                    for a, b in zip(g, v)))
+        if not same:
+            diffs.append((k, g, v))
+    assert not diffs, diffs
