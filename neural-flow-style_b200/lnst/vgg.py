@@ -66,25 +66,30 @@ def from_torchvision(state_dict, model='vgg_19'):
 
 
 def load_weights(path, model='vgg_19'):
-    """Slim-layout weights from ``<model_path>``: an ``.npz`` export of the slim checkpoint (keys
-    ``vgg_19/conv1/conv1_1/weights`` or ``conv1_1/weights``) or a torchvision state dict
-    (``.pth`` / ``.pt``, see ``from_torchvision``).  The path itself (``vgg_19.ckpt``, a TF V1 checkpoint that
-    cannot be parsed offline) is tried first, then the same stem with ``.npz``, ``.pth``, ``.pt``."""
-    if not os.path.exists(path) or path.endswith('.ckpt'):
-        stem = os.path.splitext(path)[0]
-        for ext in ('.npz', '.pth', '.pt'):
-            if os.path.exists(stem + ext):
-                path = stem + ext
-                break
-        else:
-            raise FileNotFoundError(
-                'loss-network weights not found: %s(.npz|.pth|.pt).  Export vgg_19.ckpt to .npz with keys '
-                '"vgg_19/conv1/conv1_1/weights", save a torchvision state dict, or pass weights= to Styler.'
-                % stem)
-    if path.endswith(('.pth', '.pt')):
-        sd = torch.load(path, map_location='cpu', weights_only=True)
+    """Slim-layout weights for ``<model_path>`` (``config.network``, e.g. ``data/model/vgg_19.ckpt``), from
+      * the TensorFlow V1 checkpoint itself (``lnst.tfckpt``: the slim model-zoo file the reference loads,
+        ``vgg.py:115-120``), or -- same stem --
+      * ``.npz``: an export of it (keys ``vgg_19/conv1/conv1_1/weights`` or ``conv1_1/weights``),
+      * ``.pth`` / ``.pt``: a torchvision state dict (see ``from_torchvision``)."""
+    stem = os.path.splitext(path)[0]
+    found = None
+    for cand in ([path] if os.path.isfile(path) else []) + [stem + e for e in ('.npz', '.pth', '.pt')]:
+        if os.path.isfile(cand):
+            found = cand
+            break
+    if found is None:
+        raise FileNotFoundError(
+            'loss-network weights not found: %s (TF V1 checkpoint) or %s(.npz|.pth|.pt).  Download the slim vgg_19 '
+            'checkpoint, export it to .npz with keys "vgg_19/conv1/conv1_1/weights", save a torchvision state dict, '
+            'or pass weights= to Styler.' % (path, stem))
+    if found.endswith(('.pth', '.pt')):
+        sd = torch.load(found, map_location='cpu', weights_only=True)
         return from_torchvision(sd.get('state_dict', sd) if isinstance(sd, dict) else sd, model)
-    blob = np.load(path)
+    if found.endswith('.npz'):
+        blob = np.load(found)
+    else:
+        from . import tfckpt
+        blob = tfckpt.read(found, names=lambda n: '/conv' in n and n.endswith(('/weights', '/biases')))
     out = {}
     for name in layer_order(model):
         if not name.startswith('conv'):
@@ -92,11 +97,11 @@ def load_weights(path, model='vgg_19'):
         cands = ['%s/%s/%s' % (model, name.split('_')[0], name), name]
         for c in cands:
             if c + '/weights' in blob:
-                out[name] = (torch.tensor(blob[c + '/weights'], dtype=torch.float32),
-                             torch.tensor(blob[c + '/biases'], dtype=torch.float32))
+                out[name] = (torch.tensor(np.asarray(blob[c + '/weights']), dtype=torch.float32),
+                             torch.tensor(np.asarray(blob[c + '/biases']), dtype=torch.float32))
                 break
         else:
-            raise KeyError('no weights for %s in %s' % (name, path))
+            raise KeyError('no weights for %s in %s' % (name, found))
     return out
 
 

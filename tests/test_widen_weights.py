@@ -1,4 +1,6 @@
 """Loss-network weight loaders (``lnst/vgg.py``): slim ``.npz`` export and torchvision state dicts."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -74,3 +76,108 @@ def test_missing_weights_message(tmp_path):
     feats = _torchvision_features('vgg_16')
     with pytest.raises(ValueError, match='conv layers'):
         vgg.from_torchvision({'features.' + k: v for k, v in feats.state_dict().items()}, 'vgg_19')
+
+
+# ---- TensorFlow V1 checkpoint files (lnst/tfckpt.py) ------------------------------------------------------
+def _slim_tensors(model='vgg_16', with_extra=True):
+    w = OV.synthetic_weights(model)
+    t = {}
+    for name, (wt, b) in w.items():
+        t['%s/%s/%s/weights' % (model, name.split('_')[0], name)] = wt.numpy()
+        t['%s/%s/%s/biases' % (model, name.split('_')[0], name)] = b.numpy()
+    if with_extra:                                             # the zoo file also holds the classifier and a step
+        t['%s/fc8/biases' % model] = np.arange(7, dtype=np.float32)
+        t['global_step'] = np.asarray(123, np.int32)
+    return w, t
+
+
+def test_v1_checkpoint_round_trip_and_loader(tmp_path):
+    from lnst import tfckpt
+    w, t = _slim_tensors()
+    path = str(tmp_path / 'vgg_16.ckpt')
+    tfckpt.write(path, t)
+    back = tfckpt.read(path)
+    assert sorted(back) == sorted(t)
+    for k in t:
+        np.testing.assert_array_equal(back[k], t[k])
+        assert back[k].shape == np.asarray(t[k]).shape
+    got = vgg.load_weights(path, 'vgg_16')                      # config.network points at the .ckpt itself
+    for name in w:
+        torch.testing.assert_close(got[name][0], w[name][0], rtol=0, atol=0)
+        torch.testing.assert_close(got[name][1], w[name][1], rtol=0, atol=0)
+    only = tfckpt.read(path, names={'global_step'})
+    assert list(only) == ['global_step'] and int(only['global_step']) == 123
+
+
+def test_v1_checkpoint_table_layout(tmp_path):
+    """footer magic, block trailers with valid masked crc32c, prefix-compressed keys and snappy blocks are read"""
+    import struct
+    from lnst import tfckpt
+    assert tfckpt.crc32c(b'123456789') == 0xE3069283            # the CRC-32C check value
+    _, t = _slim_tensors(with_extra=False)
+    path = str(tmp_path / 'a.ckpt')
+    tfckpt.write(path, {k: t[k] for k in list(t)[:4]})
+    blob = open(path, 'rb').read()
+    assert struct.unpack('<Q', blob[-8:])[0] == 0xdb4775248b80fb57
+    foot = memoryview(blob[-48:])
+    mo, ms, pos = tfckpt._handle(foot, 0)
+    io, isz, _ = tfckpt._handle(foot, pos)
+    for off, size in ((mo, ms), (io, isz)):
+        assert blob[off + size] == 0
+        crc, = struct.unpack_from('<I', blob, off + size + 1)
+        assert crc == tfckpt._mask(tfckpt.crc32c(b'\x00', tfckpt.crc32c(blob[off:off + size])))
+    # a block with shared key prefixes and restart points, as TF's TableBuilder writes them
+    ents = [(b'abc', b'1'), (b'abd', b'22'), (b'abdz', b''), (b'b', b'4444')]
+    body = bytearray()
+    prev = b''
+    for i, (k, v) in enumerate(ents):
+        shared = 0 if i % 2 == 0 else len(os.path.commonprefix([prev, k]))
+        body += bytes([shared, len(k) - shared, len(v)]) + k[shared:] + v
+        prev = k
+    # restart offsets of entries 0 and 2
+    o2 = len(bytes([0, 3, 1]) + b'abc' + b'1') + len(bytes([2, 1, 2]) + b'd' + b'22')
+    body += struct.pack('<III', 0, o2, 2)
+    raw = bytes(body) + b'\x00'
+    assert [(k, bytes(v)) for k, v in tfckpt._block(memoryview(raw), 0, len(body))] == ents
+    # the same block snappy-compressed by hand: one literal, then a back-reference copy
+    data = b'abcdabcdabcdXY'
+    comp = bytes([len(data)]) + bytes([(4 - 1) << 2]) + b'abcd' + bytes([((8 - 4) << 2) | 1 | (0 << 5), 4]) + \
+        bytes([(2 - 1) << 2]) + b'XY'
+    assert bytes(tfckpt._snappy(memoryview(comp))) == data
+
+
+def test_v1_checkpoint_partitioned_tensor_is_reassembled(tmp_path):
+    """two slices of one tensor (a partitioned variable) land in the right rows"""
+    from lnst import tfckpt
+    from lnst.graphdef import _enc_varint, _ld, _enc_shape
+    full = np.arange(12, dtype=np.float32).reshape(4, 3)
+
+    def slice_entry(rows):
+        a = full[rows[0]:rows[0] + rows[1]]
+        ext = _ld(1, _enc_varint(1 << 3) + _enc_varint(rows[0]) + _enc_varint(2 << 3) + _enc_varint(rows[1])) + _ld(1, b'')
+        tp = _enc_varint(1 << 3) + _enc_varint(1) + _ld(2, _enc_shape(a.shape)) + _ld(5, a.tobytes())
+        return _ld(2, _ld(1, b'v') + _ld(2, ext) + _ld(3, tp))
+
+    meta = _ld(1, _ld(1, _ld(1, b'v') + _ld(2, _enc_shape(full.shape)) + _enc_varint(3 << 3) + _enc_varint(1)))
+    entries = [(b'', meta), (b'\x00v\x00\x01a', slice_entry((0, 1))), (b'\x00v\x00\x01b', slice_entry((1, 3)))]
+    out, index = bytearray(), []
+    for k, v in entries:
+        blk = tfckpt._enc_block([(k, v)])
+        index.append((k + b'\x00', _enc_varint(len(out)) + _enc_varint(len(blk))))
+        out += blk + b'\x00' + b'\x00' * 4
+    mo = len(out)
+    mblk = tfckpt._enc_block([])
+    out += mblk + b'\x00' * 5
+    io = len(out)
+    iblk = tfckpt._enc_block(index)
+    out += iblk + b'\x00' * 5
+    import struct
+    foot = _enc_varint(mo) + _enc_varint(len(mblk)) + _enc_varint(io) + _enc_varint(len(iblk))
+    out += foot + b'\x00' * (40 - len(foot)) + struct.pack('<Q', tfckpt.MAGIC)
+    p = tmp_path / 'part.ckpt'
+    p.write_bytes(bytes(out))
+    np.testing.assert_array_equal(tfckpt.read(str(p))['v'], full)
+    with pytest.raises(ValueError):
+        bad = tmp_path / 'bad.ckpt'
+        bad.write_bytes(b'x' * 100)
+        tfckpt.read(str(bad))
