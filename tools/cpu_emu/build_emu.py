@@ -13,6 +13,8 @@ SOURCES = ['splat.cu', 'field.cu', 'render.cu', 'lossnet.cu', 'optim.cu', 'gathe
 
 
 def build(force=False):
+    if os.environ.get('LNST_EMU_LIB'):          # e.g. an AddressSanitizer build of the same sources (tools/cpu_emu/README)
+        return os.environ['LNST_EMU_LIB']
     srcs = [os.path.join(CSRC, s) for s in SOURCES]
     deps = srcs + [os.path.join(HERE, 'cpu_emu.h'), os.path.join(CSRC, 'common.cuh'),
                    os.path.join(ROOT, 'include', 'lnst_b200.h')]
