@@ -335,8 +335,10 @@ int lnst_sub_fliph(const float* a, const float* b, float* out, int32_t D, int32_
 int lnst_conv2d_f32(const float* x, const float* w, const float* bias, float* y, int32_t n, int32_t H, int32_t W,
                     int32_t Cin, int32_t Cout, int32_t kh, int32_t kw, int32_t stride, int32_t pad_top,
                     int32_t pad_left, int32_t OH, int32_t OW, int32_t ldy, int32_t relu, void* stream);
-/* g_x [n,H,W,Cin] (+)= conv2d data gradient of g_y (row stride ldg >= Cout). */
-int lnst_conv2d_bwd_data_f32(const float* g_y, int32_t ldg, const float* w, float* g_x, int32_t n, int32_t H,
+/* g_x [n,H,W,Cin] (+)= conv2d data gradient of g_y (row stride ldg >= Cout).  relu_y (may be NULL): the post-ReLU
+ * output of a convolution that ran with relu = 1, indexed like g_y -- the cotangent is masked by (relu_y > 0) while
+ * it is loaded (tf.nn.relu's gradient without a pass of its own). */
+int lnst_conv2d_bwd_data_f32(const float* g_y, const float* relu_y, int32_t ldg, const float* w, float* g_x, int32_t n, int32_t H,
                              int32_t W, int32_t Cin, int32_t Cout, int32_t kh, int32_t kw, int32_t stride,
                              int32_t pad_top, int32_t pad_left, int32_t OH, int32_t OW, int32_t accumulate,
                              void* stream);

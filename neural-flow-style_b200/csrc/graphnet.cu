@@ -27,7 +27,8 @@ struct Conv2dA {          // im2col view of x [n,H,W,Cin]: row = output pixel, k
 
 struct Conv2dGradA {      // rows = INPUT pixels, k = (ky*kw+kx)*Cout + co: the output pixel that tap (ky,kx) maps here
   const float* gy;
-  int ldg;
+  const float* mask;      // post-ReLU output of the convolution (same indexing as gy) or NULL: gy * (mask > 0), the
+  int ldg;                // tf.nn.relu gradient folded into the operand load
   Conv2dGeom g;
   static constexpr bool kContigM = false;
   __device__ __forceinline__ float operator()(int m, int k) const {
@@ -39,7 +40,9 @@ struct Conv2dGradA {      // rows = INPUT pixels, k = (ky*kw+kx)*Cout + co: the 
     if (ty < 0 || tx < 0) return 0.f;
     const int oy = ty / g.stride, ox = tx / g.stride;
     if (oy * g.stride != ty || ox * g.stride != tx || oy >= g.OH || ox >= g.OW) return 0.f;
-    return gy[(((int64_t)img * g.OH + oy) * g.OW + ox) * ldg + co];
+    const int64_t o = (((int64_t)img * g.OH + oy) * g.OW + ox) * ldg + co;
+    if (mask && !(mask[o] > 0.f)) return 0.f;
+    return gy[o];
   }
 };
 
@@ -205,13 +208,13 @@ extern "C" int lnst_conv2d_f32(const float* x, const float* w, const float* bias
   return run_sgemm(A, B, ep, n * OH * OW, Cout, kh * kw * Cin, 1, lnst_stream(stream));
 }
 
-extern "C" int lnst_conv2d_bwd_data_f32(const float* g_y, int32_t ldg, const float* w, float* g_x, int32_t n,
+extern "C" int lnst_conv2d_bwd_data_f32(const float* g_y, const float* relu_y, int32_t ldg, const float* w, float* g_x, int32_t n,
                                         int32_t H, int32_t W, int32_t Cin, int32_t Cout, int32_t kh, int32_t kw,
                                         int32_t stride, int32_t pad_top, int32_t pad_left, int32_t OH, int32_t OW,
                                         int32_t accumulate, void* stream) {
   Conv2dGeom g{H, W, Cin, Cout, kh, kw, stride, pad_top, pad_left, OH, OW};
   if (!g_y || !w || !g_x || !conv_geom_ok(g, n) || ldg < Cout) return LNST_EARG;
-  Conv2dGradA A{g_y, (int)ldg, g};
+  Conv2dGradA A{g_y, relu_y, (int)ldg, g};
   Conv2dGradB B{w, (int)Cin, (int)Cout};
   AccEpilogue ep{g_x, (int)Cin, (int)accumulate};
   return run_sgemm(A, B, ep, n * H * W, Cin, kh * kw * Cout, 1, lnst_stream(stream));

@@ -89,7 +89,7 @@ SIGNATURES = {
     'lnst_pressure_loss': [vp, i64, f32, f32, vp, vp, vp],
     'lnst_sub_fliph': [vp, vp, vp, i32, i32, i32, vp],
     'lnst_conv2d_f32': [vp, vp, vp, vp] + [i32] * 14 + [vp],
-    'lnst_conv2d_bwd_data_f32': [vp, i32, vp, vp] + [i32] * 13 + [vp],
+    'lnst_conv2d_bwd_data_f32': [vp, vp, i32, vp, vp] + [i32] * 13 + [vp],
     'lnst_relu_fwd': [vp, vp, i64, vp],
     'lnst_relu_bwd': [vp, vp, vp, i64, i32, vp],
     'lnst_maxpool_fwd': [vp, vp] + [i32] * 10 + [vp],

@@ -12,6 +12,11 @@ entry point of ``csrc/graphnet.cu`` (fp32 NHWC):
     Concat / ConcatV2 (channel axis)          lnst_copy_channels
     Identity, Placeholder, Const              --
 
+Fusions decided per call from the requested layers (``_fusion``): Conv2D + BiasAdd always; + Relu when the pre-ReLU
+tensor is not itself a requested layer (the ReLU gradient is then folded into the operand load of the data-gradient
+GEMM); branch convolutions of an inception module write straight into their channel slice of the module's concat buffer
+and read their cotangent slice in place (no concat / slice copies).
+
 Only the sub-graph between ``input`` and the requested layers runs.  Weights are frozen: the backward pass
 computes data gradients only, accumulating where a tensor feeds several consumers.  ``GraphNet`` offers the same
 methods as ``lnst.vgg.LossNet`` (``forward / backward / gram / gram_grad / content ...``) so ``StylerBase`` drives
@@ -61,6 +66,7 @@ class GraphNet(object):
         for n in nodes:
             for i in n.inputs:
                 consumers.setdefault(_clean(i), []).append(n.name)
+        self.consumers = consumers
         self.fused_bias = {}
         for n in nodes:
             if n.op == 'BiasAdd':
@@ -132,9 +138,45 @@ class GraphNet(object):
             raise NotImplementedError('%s: data_format %s' % (node.name, fmt))
         return int(strides[1]), (node.attr.get('padding') or b'SAME').decode()
 
+    def _fusion(self, wanted):
+        """Per call: which Relu nodes run inside their convolution, and which of those write straight into a concat.
+
+        relu_of[R] = B      Relu R whose input is a Conv2D+BiasAdd B that nobody else reads and that is not itself a
+                            requested layer (a content layer such as ``mixed4d_3x3_bottleneck_pre_relu`` is, and keeps
+                            the separate Relu pass): one kernel, relu = 1.
+        slot[R] = (C, off)  such an R whose only consumer is the channel-axis Concat C, every input of C qualifying
+                            and none of them requested: R's convolution writes channels [off, off+ch) of C's buffer,
+                            the concat copies disappear, the backward pass reads the cotangent slice in place.
+        """
+        want = {_clean(w) for w in wanted}
+        relu_of = {}
+        for name, node in self.nodes.items():
+            if node.op != 'Relu':
+                continue
+            b = _clean(node.inputs[0])
+            if b in self.fused_bias and b not in want and self.consumers.get(b) == [name]:
+                relu_of[name] = b
+        slot, width = {}, {}
+        for name, node in self.nodes.items():
+            if node.op not in ('Concat', 'ConcatV2'):
+                continue
+            ins = self._data_inputs(node)
+            if not ins or any(i not in relu_of or i in want or self.consumers.get(i) != [name] for i in ins):
+                continue
+            off = 0
+            for i in ins:
+                conv = self.nodes[self.fused_bias[relu_of[i]]]
+                slot[i] = (name, off)
+                off += int(self.const[_clean(conv.inputs[1])].shape[-1])
+            width[name] = off
+        return relu_of, slot, width
+
     def forward(self, x, wanted, gray=None):
-        """x [n,H,W,3] mean-subtracted net input.  Returns {tensor name: fp32 [n,h,w,C]} for every executed node."""
-        acts = {self.input_name: x}
+        """x [n,H,W,3] mean-subtracted net input.  Returns {tensor name: fp32 [n,h,w,C]} for every materialised node
+        (plus ``'__fusion__'``, the plan the backward pass must follow)."""
+        relu_of, slot, width = self._fusion(wanted)
+        fused_pre = set(relu_of.values())
+        acts = {self.input_name: x, '__fusion__': (relu_of, slot)}
         for name in self._plan(wanted):
             node = self.nodes[name]
             ins = self._data_inputs(node)
@@ -144,6 +186,8 @@ class GraphNet(object):
                 stride, padding = self._conv_attrs(node)
                 acts[name] = ops.conv2d_f32(acts[ins[0]], self._w(_clean(node.inputs[1])), None, stride, padding)
             elif node.op == 'BiasAdd':
+                if name in fused_pre:
+                    continue                                   # produced by its Relu (conv + bias + relu in one kernel)
                 if name in self.fused_bias:
                     conv = self.nodes[self.fused_bias[name]]
                     stride, padding = self._conv_attrs(conv)
@@ -152,7 +196,23 @@ class GraphNet(object):
                 else:
                     acts[name] = acts[ins[0]] + self._w(_clean(node.inputs[1]))
             elif node.op == 'Relu':
-                acts[name] = ops.relu_fwd(acts[ins[0]])
+                if name in relu_of:
+                    bias_node = self.nodes[relu_of[name]]
+                    conv = self.nodes[self.fused_bias[relu_of[name]]]
+                    stride, padding = self._conv_attrs(conv)
+                    src, w = acts[_clean(conv.inputs[0])], self._w(_clean(conv.inputs[1]))
+                    if name in slot:                           # straight into the concat buffer
+                        cat, off = slot[name]
+                        if cat not in acts:
+                            OH, OW, _, _ = ops.conv_out(src.shape, w.shape, stride, padding)
+                            acts[cat] = torch.empty(src.shape[0], OH, OW, width[cat], dtype=f32, device=self.device)
+                        ops.conv2d_f32(src, w, self._w(_clean(bias_node.inputs[1])), stride, padding, relu=True,
+                                       out=acts[cat], ch_off=off)
+                    else:
+                        acts[name] = ops.conv2d_f32(src, w, self._w(_clean(bias_node.inputs[1])), stride, padding,
+                                                    relu=True)
+                else:
+                    acts[name] = ops.relu_fwd(acts[ins[0]])
             elif node.op == 'MaxPool':
                 k, stride, padding = self._pool_attrs(node)
                 acts[name] = ops.maxpool_fwd(acts[ins[0]], k, stride, padding)
@@ -161,6 +221,8 @@ class GraphNet(object):
                 acts[name] = ops.lrn_fwd(acts[ins[0]], r, bias, alpha, beta)
             elif node.op in ('Concat', 'ConcatV2'):
                 self._concat_axis(node)
+                if name in width:
+                    continue                                   # its inputs wrote acts[name] directly
                 parts = [acts[i] for i in ins]
                 out = torch.empty(parts[0].shape[:3] + (sum(p.shape[-1] for p in parts),), dtype=f32, device=self.device)
                 off = 0
@@ -190,8 +252,11 @@ class GraphNet(object):
         """d loss / d x [n,H,W,3].  ``add_loss_grad(name, g)`` adds the loss terms living on tensor ``name`` into g
         (None = nothing accumulated yet) and returns the buffer."""
         plan = self._plan(wanted)
+        relu_of, slot = acts['__fusion__']
+        fused_pre = set(relu_of.values())
         loss_names = {_clean(l): l for l in loss_layers}
         grads = {}
+        sliced = {}                                            # R -> (cotangent of its concat, channel offset)
 
         def acc(name, shape_like):
             """(buffer, accumulate flag) for the gradient of tensor ``name``"""
@@ -202,12 +267,28 @@ class GraphNet(object):
 
         for name in reversed(plan):
             node = self.nodes[name]
+            if name in fused_pre or (node.op == 'Conv2D' and name in self.fused_bias.values()):
+                continue                                       # handled at the node that produced the tensor
             if name in loss_names:
                 grads[name] = add_loss_grad(loss_names[name], grads.get(name))
             g = grads.pop(name, None)
+            ins = self._data_inputs(node)
+            if node.op == 'Relu' and name in relu_of:          # conv + bias + relu: mask folded into the dgrad load
+                conv = self.nodes[self.fused_bias[relu_of[name]]]
+                src = _clean(conv.inputs[0])
+                stride, padding = self._conv_attrs(conv)
+                if name in sliced:
+                    gcat, off = sliced.pop(name)
+                    gx, a = acc(src, acts[src])
+                    ops.conv2d_bwd_data_f32(gcat, self._w(_clean(conv.inputs[1])), acts[src].shape, stride, padding, gx,
+                                            a, ch_off=off, relu_y=acts[slot[name][0]])
+                elif g is not None:
+                    gx, a = acc(src, acts[src])
+                    ops.conv2d_bwd_data_f32(g, self._w(_clean(conv.inputs[1])), acts[src].shape, stride, padding, gx, a,
+                                            relu_y=acts[name])
+                continue
             if g is None:
                 continue
-            ins = self._data_inputs(node)
             if node.op == 'Conv2D' or name in self.fused_bias:
                 conv = self.nodes[self.fused_bias[name]] if name in self.fused_bias else node
                 src = _clean(conv.inputs[0])
@@ -229,6 +310,10 @@ class GraphNet(object):
                 gx, a = acc(ins[0], acts[ins[0]])
                 ops.lrn_bwd(g, acts[ins[0]], r, bias, alpha, beta, gx, a)
             elif node.op in ('Concat', 'ConcatV2'):
+                if all(i in slot and slot[i][0] == name for i in ins):
+                    for i in ins:                              # the branches read their slice of g in place
+                        sliced[i] = (g, slot[i][1])
+                    continue
                 off = 0
                 for i in ins:
                     ch = acts[i].shape[-1]

@@ -423,11 +423,14 @@ def conv2d_f32(x, w, bias, stride=1, padding='SAME', relu=False, out=None, ch_of
     return out
 
 
-def conv2d_bwd_data_f32(g_y, w, x_shape, stride, padding, g_x, accumulate, ch_off=0):
+def conv2d_bwd_data_f32(g_y, w, x_shape, stride, padding, g_x, accumulate, ch_off=0, relu_y=None):
+    """``relu_y``: post-ReLU output of the convolution, same layout (and channel offset) as g_y -> g_y * (relu_y > 0)"""
     n, H, W, cin = x_shape
     kh, kw, _, cout = w.shape
     OH, OW, pt, pl = conv_out(x_shape, w.shape, stride, padding)
-    _lib.get().call('lnst_conv2d_bwd_data_f32', C.c_void_p(g_y.data_ptr() + 4 * ch_off), g_y.shape[-1], ptr(w), ptr(g_x),
+    mask = None if relu_y is None else C.c_void_p(relu_y.data_ptr() + 4 * ch_off)
+    assert relu_y is None or relu_y.shape == g_y.shape
+    _lib.get().call('lnst_conv2d_bwd_data_f32', C.c_void_p(g_y.data_ptr() + 4 * ch_off), mask, g_y.shape[-1], ptr(w), ptr(g_x),
                     n, H, W, cin, cout, kh, kw, stride, pt, pl, OH, OW, int(bool(accumulate)), _s(g_y))
     return g_x
 

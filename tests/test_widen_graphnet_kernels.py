@@ -63,6 +63,20 @@ def test_conv2d_fwd_bwd(dev, n, H, W, cin, cout, k, stride, padding):
     close(gx, 2 * x.grad, tol=3e-6, what='conv2d dgrad accumulate')
 
 
+def test_conv2d_dgrad_with_relu_mask(dev):
+    rng = np.random.RandomState(3)
+    x = torch.tensor(rng.randn(2, 7, 6, 5).astype(np.float32), requires_grad=True)
+    w = torch.tensor(rng.randn(3, 3, 5, 4).astype(np.float32))
+    b = torch.tensor(rng.randn(4).astype(np.float32))
+    y = ref_conv(x, w, b, 1, 'SAME', relu=True)
+    g = torch.tensor(rng.randn(*y.shape).astype(np.float32))
+    (y * g).sum().backward()
+    yk = ops.conv2d_f32(x.detach().to(dev), w.to(dev), b.to(dev), 1, 'SAME', relu=True)
+    gx = torch.empty(x.shape).to(dev)
+    ops.conv2d_bwd_data_f32(g.to(dev), w.to(dev), x.shape, 1, 'SAME', gx, accumulate=False, relu_y=yk)
+    close(gx, x.grad, tol=3e-6, what='dgrad through conv+relu')
+
+
 def test_conv2d_into_concat_slice(dev):
     rng = np.random.RandomState(0)
     x = torch.tensor(rng.randn(1, 6, 5, 4).astype(np.float32))

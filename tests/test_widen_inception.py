@@ -129,17 +129,22 @@ def test_graphnet_forward_backward(dev, pool1):
     nodes = synth.inception5h_nodes(width_div=8, upto='mixed4a')
     hw = (40, 36) if not pool1 else (22, 20)
     img = torch.tensor(np.random.RandomState(0).uniform(0, 255, (2,) + hw + (3,)).astype(np.float32), requires_grad=True)
-    layers = ['conv2d2', 'mixed3a_3x3_bottleneck_pre_relu', 'mixed3b', 'mixed4a_pool_reduce_pre_relu', 'mixed4a']
+    # a post-ReLU tensor, a pre-ReLU one (keeps the separate Relu pass), a branch output (its module then concatenates
+    # by copy), concats whose branches write in place
+    layers = ['conv2d2', 'mixed3a_3x3_bottleneck_pre_relu', 'mixed3a_5x5', 'mixed3b', 'mixed4a_pool_reduce_pre_relu', 'mixed4a']
     want = OG.forward(img, nodes, layers, pool1=pool1)
     net = GraphNet(nodes, dev, pool1=pool1)
     x = OV.preprocess(img.detach()).contiguous().to(dev)
     acts = net.forward(x, layers)
-    for l in layers + ['localresponsenorm0', 'maxpool1', 'mixed3a_pool']:
+    relu_of, slot = acts['__fusion__']
+    assert 'mixed3b_1x1' in slot and 'mixed3a_1x1' not in slot and 'mixed3a_3x3_bottleneck' not in relu_of
+    assert 'mixed3b_1x1' not in acts and 'mixed3b_1x1_pre_relu' not in acts          # never materialised on their own
+    for l in layers + ['localresponsenorm0', 'maxpool1', 'mixed3a_pool', 'mixed3a']:
         close(acts[l], want[l], tol=2e-5, what=l)
     # cotangents on three tensors at different depths, one of them pre-ReLU, one a concat
     rng = np.random.RandomState(1)
     cot = {l: torch.tensor(rng.randn(*want[l].shape).astype(np.float32)) for l in
-           ('conv2d2', 'mixed3a_3x3_bottleneck_pre_relu', 'mixed4a')}
+           ('conv2d2', 'mixed3a_3x3_bottleneck_pre_relu', 'mixed3a_5x5', 'mixed3b', 'mixed4a')}
     sum((want[l] * c).sum() for l, c in cot.items()).backward()
 
     def add(name, g):
