@@ -83,6 +83,29 @@ class StylerBase(object):
                 img = crop_ratio(img, hw[1] / hw[0])
             self.style_img = img
 
+    # ---- semi-Lagrangian transport between frames (styler_base.py:59-74) ----------------------------------------
+    def _transport(self, g, v, a, b, recursive=True):
+        """Carry a per-cell field g [H,W,C] (or [D,H,W,C]) from frame a to frame b along the velocity fields
+        v [N,H,W,dim] (normalised units per frame) by repeated order-1 advection -- the reference's temporal-coherence
+        helper (its graph nodes ``self.adv / self.g / self.u`` are not built at HEAD, so nothing calls it there; kept
+        with the reference's signature and semantics over ``lnst_advect``).  Returns a NumPy array like the reference."""
+        dev = self.device
+        gt = torch.as_tensor(np.ascontiguousarray(g, dtype=np.float32)).to(dev)
+        vt = torch.as_tensor(np.ascontiguousarray(v, dtype=np.float32)).to(dev)
+        if a < b:
+            if recursive:
+                for i in range(a, b):
+                    gt = ops.advect(gt, vt[i].contiguous())
+            else:                                                  # forward once
+                gt = ops.advect(gt, (vt[a] * (b - a)).contiguous())
+        elif a > b:
+            if recursive:
+                for i in reversed(range(b, a)):
+                    gt = ops.advect(gt, (-vt[i]).contiguous())
+            else:
+                gt = ops.advect(gt, (-vt[a - 1] * (a - b)).contiguous())
+        return gt.cpu().numpy()
+
     # ---- end points needed -----------------------------------------------------------------------
     def _wanted(self):
         w = []

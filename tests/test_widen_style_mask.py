@@ -80,3 +80,39 @@ def test_style_mask_with_resize_scale_matches_oracle(dev):
     ref = Oracle3P(smoke_cfg(**kw), oracle.vgg.synthetic_weights()).run({'p': p, 'r': r}, style_targets=[sty])
     np.testing.assert_allclose(out['l'][0], ref['l'][0], rtol=3e-4)
     assert np.abs(out['d'] - ref['d']).max() <= 3e-4 * np.abs(ref['d']).max()
+
+
+def test_transport_between_frames(dev):
+    """StylerBase._transport (reference styler_base.py:59-74): repeated order-1 advection forward / backward in time,
+    recursive and single-step, 2-D and 3-D, against the oracle's advect."""
+    from helpers import smoke_cfg
+    from lnst import synth
+    from lnst.styler_3p import Styler
+    from oracle import transform as T
+    st = Styler(smoke_cfg(res=8, conv_math='fp32'), weights=synth.vgg_weights(), device=dev)
+    rng = np.random.RandomState(2)
+    for shape in ([9, 11], [6, 7, 5]):
+        dim = len(shape)
+        g = rng.rand(*shape, 2).astype(np.float32)
+        v = rng.uniform(-0.2, 0.2, [4] + shape + [dim]).astype(np.float32)
+
+        def ref(a, b, recursive):
+            x = torch.tensor(g)[None]
+            adv = lambda f, u: T.advect(f, torch.tensor(u)[None], is_3d=dim == 3)
+            if a < b:
+                if recursive:
+                    for i in range(a, b):
+                        x = adv(x, v[i])
+                else:
+                    x = adv(x, v[a] * (b - a))
+            elif a > b:
+                if recursive:
+                    for i in reversed(range(b, a)):
+                        x = adv(x, -v[i])
+                else:
+                    x = adv(x, -v[a - 1] * (a - b))
+            return x[0].numpy()
+
+        for a, b in ((0, 3), (3, 1), (2, 2)):
+            for rec in (True, False):
+                np.testing.assert_allclose(st._transport(g, v, a, b, recursive=rec), ref(a, b, rec), rtol=0, atol=3e-6)
