@@ -14,14 +14,22 @@ struct Conv2dA {          // im2col view of x [n,H,W,Cin]: row = output pixel, k
   const float* x;
   Conv2dGeom g;
   static constexpr bool kContigM = false;
-  __device__ __forceinline__ float operator()(int m, int k) const {
-    const int ci = k % g.Cin, tap = k / g.Cin;
-    const int ky = tap / g.kw, kx = tap - g.kw * ky;
+  struct Row { int base, y0, x0; };                // img*H*W, top-left input coordinate of the window
+  struct Col { int ci, ky, kx; };
+  __device__ __forceinline__ Row row(int m) const {
     const int ox = m % g.OW, t = m / g.OW;
     const int oy = t % g.OH, img = t / g.OH;
-    const int yy = oy * g.stride + ky - g.pt, xx = ox * g.stride + kx - g.pl;
+    return Row{img * g.H * g.W, oy * g.stride - g.pt, ox * g.stride - g.pl};
+  }
+  __device__ __forceinline__ Col col(int k) const {
+    const int ci = k % g.Cin, tap = k / g.Cin;
+    const int ky = tap / g.kw;
+    return Col{ci, ky, tap - g.kw * ky};
+  }
+  __device__ __forceinline__ float load(const Row& r, const Col& c) const {
+    const int yy = r.y0 + c.ky, xx = r.x0 + c.kx;
     if (yy < 0 || yy >= g.H || xx < 0 || xx >= g.W) return 0.f;
-    return x[(((int64_t)img * g.H + yy) * g.W + xx) * g.Cin + ci];
+    return x[(int64_t)(r.base + yy * g.W + xx) * g.Cin + c.ci];
   }
 };
 
@@ -31,28 +39,42 @@ struct Conv2dGradA {      // rows = INPUT pixels, k = (ky*kw+kx)*Cout + co: the 
   int ldg;                // tf.nn.relu gradient folded into the operand load
   Conv2dGeom g;
   static constexpr bool kContigM = false;
-  __device__ __forceinline__ float operator()(int m, int k) const {
-    const int co = k % g.Cout, tap = k / g.Cout;
-    const int ky = tap / g.kw, kx = tap - g.kw * ky;
+  struct Row { int base, ty0, tx0; };              // img*OH*OW, input coordinate + padding
+  struct Col { int co, ky, kx; };
+  __device__ __forceinline__ Row row(int m) const {
     const int ix = m % g.W, t = m / g.W;
     const int iy = t % g.H, img = t / g.H;
-    const int ty = iy + g.pt - ky, tx = ix + g.pl - kx;
+    return Row{img * g.OH * g.OW, iy + g.pt, ix + g.pl};
+  }
+  __device__ __forceinline__ Col col(int k) const {
+    const int co = k % g.Cout, tap = k / g.Cout;
+    const int ky = tap / g.kw;
+    return Col{co, ky, tap - g.kw * ky};
+  }
+  __device__ __forceinline__ float load(const Row& r, const Col& c) const {
+    const int ty = r.ty0 - c.ky, tx = r.tx0 - c.kx;
     if (ty < 0 || tx < 0) return 0.f;
-    const int oy = ty / g.stride, ox = tx / g.stride;
-    if (oy * g.stride != ty || ox * g.stride != tx || oy >= g.OH || ox >= g.OW) return 0.f;
-    const int64_t o = (((int64_t)img * g.OH + oy) * g.OW + ox) * ldg + co;
+    int oy = ty, ox = tx;
+    if (g.stride != 1) {
+      oy = ty / g.stride; ox = tx / g.stride;
+      if (oy * g.stride != ty || ox * g.stride != tx) return 0.f;
+    }
+    if (oy >= g.OH || ox >= g.OW) return 0.f;
+    const int64_t o = (int64_t)(r.base + oy * g.OW + ox) * ldg + c.co;
     if (mask && !(mask[o] > 0.f)) return 0.f;
     return gy[o];
   }
 };
 
-struct Conv2dGradB {      // (k = tap*Cout + co, n = ci) -> w[tap][ci][co]   (HWIO)
+struct Conv2dGradB {      // (k = tap*Cout + co, n = ci) -> w[tap][ci][co]   (HWIO): contiguous along k
   const float* w;
   int Cin, Cout;
-  __device__ __forceinline__ float operator()(int k, int n) const {
+  static constexpr bool kContigK = true;
+  __device__ __forceinline__ int64_t kcol(int k) const {
     const int co = k % Cout, tap = k / Cout;
-    return w[((int64_t)tap * Cin + n) * Cout + co];
+    return (int64_t)tap * Cin * Cout + co;
   }
+  __device__ __forceinline__ float load(int64_t kc, int n) const { return w[kc + (int64_t)n * Cout]; }
 };
 
 struct AccEpilogue {      // g = acc (+ g)

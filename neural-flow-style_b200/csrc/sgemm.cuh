@@ -9,6 +9,10 @@
 #define GBK 16
 
 // ---- operand loaders: element (row, k) of A [M,K] and (k, col) of B [K,N] ---------------
+// An A loader is used in two stages: ``row(m)`` once per thread and tile row (the rows a thread stages do not change
+// over the K loop), ``col(k)`` once per K step, ``load(row, col)`` per element.  For the implicit-im2col views this
+// keeps every runtime integer division (pixel -> image/y/x, k -> tap/channel) out of the per-element path: the direct
+// ``A(m, k)`` form spent ~6 divisions per staged element, several times the FMA work of the tile.
 __device__ __forceinline__ float lnst_to_f32(float v) { return v; }
 __device__ __forceinline__ void lnst_from_f32(float* p, float v) { *p = v; }
 #ifndef LNST_CPU_EMU
@@ -22,14 +26,21 @@ struct ConvAT {           // im2col view of x [n,H,W,Cin]: row = pixel, k = (ky*
   const TIn* x;
   int H, W, Cin;
   static constexpr bool kContigM = false;
-  __device__ __forceinline__ float operator()(int m, int k) const {
-    const int ci = k % Cin, tap = k / Cin;
-    const int ky = tap / 3, kx = tap - 3 * ky;
+  struct Row { int pix, py, px; };                 // linear pixel index (img*H + py)*W + px
+  struct Col { int ci, dy, dx; };                  // channel, tap offset in [-1,1]
+  __device__ __forceinline__ Row row(int m) const {
     const int px = m % W, t = m / W;
-    const int py = t % H, img = t / H;
-    const int yy = py + ky - 1, xx = px + kx - 1;
+    return Row{m, t % H, px};
+  }
+  __device__ __forceinline__ Col col(int k) const {
+    const int ci = k % Cin, tap = k / Cin;
+    const int ky = tap / 3;
+    return Col{ci, ky - 1, tap - 3 * ky - 1};
+  }
+  __device__ __forceinline__ float load(const Row& r, const Col& c) const {
+    const int yy = r.py + c.dy, xx = r.px + c.dx;
     if (yy < 0 || yy >= H || xx < 0 || xx >= W) return 0.f;
-    return lnst_to_f32(x[(((int64_t)img * H + yy) * W + xx) * Cin + ci]);
+    return lnst_to_f32(x[(int64_t)(r.pix + c.dy * W + c.dx) * Cin + c.ci]);
   }
 };
 typedef ConvAT<float> ConvA;
@@ -37,17 +48,26 @@ struct RowMajorA {        // A [M,K] row-major with leading dimension ld
   const float* a;
   int ld;
   static constexpr bool kContigM = false;
-  __device__ __forceinline__ float operator()(int m, int k) const { return a[(int64_t)m * ld + k]; }
+  typedef int Row;
+  typedef int Col;
+  __device__ __forceinline__ Row row(int m) const { return m; }
+  __device__ __forceinline__ Col col(int k) const { return k; }
+  __device__ __forceinline__ float load(Row m, Col k) const { return a[(int64_t)m * ld + k]; }
 };
 struct TransposedA {      // A = X^T where X [K,M] row-major (Gram: F^T)
   const float* a;
   int ld;
   static constexpr bool kContigM = true;
-  __device__ __forceinline__ float operator()(int m, int k) const { return a[(int64_t)k * ld + m]; }
+  typedef int Row;
+  typedef int Col;
+  __device__ __forceinline__ Row row(int m) const { return m; }
+  __device__ __forceinline__ Col col(int k) const { return k; }
+  __device__ __forceinline__ float load(Row m, Col k) const { return a[(int64_t)k * ld + m]; }
 };
-struct RowMajorB {
-  const float* b;
+struct RowMajorB {        // B loaders: kContigK = false -> staged 64 columns wide (coalesced along n), B(k, n) per element;
+  const float* b;         // kContigK = true -> 16 k wide (operands contiguous along k), kcol(k) once per K step + load(kcol, n)
   int ld;
+  static constexpr bool kContigK = false;
   __device__ __forceinline__ float operator()(int k, int n) const { return b[(int64_t)k * ld + n]; }
 };
 
@@ -103,19 +123,49 @@ __global__ void __launch_bounds__(256) sgemm_k(AL A, BL B, EP ep, int M, int N, 
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
+  // A elements this thread stages per 64x16 tile (same shared-memory layout as a flat e = tid + 256 j sweep):
+  //   !kContigM: k column tid & 15, rows (tid >> 4) + 16 j;   kContigM: row tid & 63, k columns (tid >> 6) + 4 j
+  constexpr int AR = AL::kContigM ? 1 : 4;
+  typename AL::Row arow[AR];
+  bool arow_ok[AR];
+#pragma unroll
+  for (int j = 0; j < AR; ++j) {
+    const int m = m0 + (AL::kContigM ? (tid & 63) : (tid >> 4) + 16 * j);
+    arow_ok[j] = m < M;
+    arow[j] = A.row(arow_ok[j] ? m : 0);
+  }
+
   for (int k0 = kbeg; k0 < kend; k0 += GBK) {
+    if (AL::kContigM) {
 #pragma unroll
-    for (int e = tid; e < GBM * GBK; e += 256) {
-      int mm, kk;
-      if (AL::kContigM) { mm = e % GBM; kk = e / GBM; } else { kk = e % GBK; mm = e / GBK; }
-      const int m = m0 + mm, k = k0 + kk;
-      As[kk][mm] = (m < M && k < kend) ? A(m, k) : 0.f;
+      for (int j = 0; j < 4; ++j) {
+        const int kk = (tid >> 6) + 4 * j, k = k0 + kk;
+        As[kk][tid & 63] = (arow_ok[0] && k < kend) ? A.load(arow[0], A.col(k)) : 0.f;
+      }
+    } else {
+      const int kk = tid & 15, k = k0 + kk;
+      const bool kok = k < kend;
+      const typename AL::Col acol = A.col(kok ? k : kbeg);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        As[kk][(tid >> 4) + 16 * j] = (kok && arow_ok[j < AR ? j : 0]) ? A.load(arow[j < AR ? j : 0], acol) : 0.f;
     }
+    if constexpr (BL::kContigK) {
+      const int kk = tid & 15, k = k0 + kk;
+      const bool kok = k < kend;
+      const auto bcol = B.kcol(kok ? k : kbeg);
 #pragma unroll
-    for (int e = tid; e < GBN * GBK; e += 256) {
-      const int nn = e % GBN, kk = e / GBN;
-      const int n = n0 + nn, k = k0 + kk;
-      Bs[kk][nn] = (n < N && k < kend) ? B(k, n) : 0.f;
+      for (int j = 0; j < 4; ++j) {
+        const int nn = (tid >> 4) + 16 * j, n = n0 + nn;
+        Bs[kk][nn] = (kok && n < N) ? B.load(bcol, n) : 0.f;
+      }
+    } else {
+#pragma unroll
+      for (int e = tid; e < GBN * GBK; e += 256) {
+        const int nn = e % GBN, kk = e / GBN;
+        const int n = n0 + nn, k = k0 + kk;
+        Bs[kk][nn] = (n < N && k < kend) ? B(k, n) : 0.f;
+      }
     }
     __syncthreads();
 #pragma unroll
