@@ -100,8 +100,14 @@ class Styler(StylerBase):
                 self.n_views = len(self.views)
             assert self.n_views % self.v_batch == 0
             if self.v_batch != 1:
-                raise NotImplementedError('v_batch > 1 is not built (its loss ignores all but the first view, '
-                                          'styler_base.py:98)')
+                # a group of v_batch views per Adam step: joint normalisation, Gram loss on the group's first image
+                # only (styler_base.py:98 loops over range(batch_size)), content / TV averaged over the group
+                if self.view_mode != 'sequential':
+                    raise NotImplementedError("v_batch > 1 is the reference's per-group Adam loop: view_mode='sequential'")
+                if self.conv_math != 'fp32' and 'vgg' in self.model_path:
+                    raise NotImplementedError("v_batch > 1 needs conv_math='fp32'")
+                if self.style_mask:
+                    raise NotImplementedError('v_batch > 1 with style_mask')
         self._frame_cache = {}
         self._iv_cache = {}
         self._pool = None
@@ -269,7 +275,7 @@ class Styler(StylerBase):
             ws['box_cells'] = (hi[0] - lo[0] + 1) * (hi[1] - lo[1] + 1) * (hi[2] - lo[2] + 1)
         return ws
 
-    def _render(self, ds, rot, box=None, bricks=None, net_input=True):
+    def _render(self, ds, rot, box=None, bricks=None, net_input=True, joint=False):
         """ds [D,H,W] -> gray [nv,H,W,1] in [0,1] plus what the backward needs.  ``net_input=False``: the loss
         net starts from the gray image itself (``_gray_path``), d_img / x are not produced."""
         D, H, W = ds.shape
@@ -292,8 +298,12 @@ class Styler(StylerBase):
         if self.render_liquid:
             gray = img
         else:                                                     # styler_3p.py:158
-            st['stats'] = ops.image_max(img, torch.empty(2 * nv, dtype=f32, device=dev))
-            gray = ops.normalize_fwd(img, st['stats'], torch.empty_like(img))
+            # `d /= tf.reduce_max(d)` is over the whole fed tensor: one maximum per view here, or -- ``joint``, a
+            # v_batch group -- one for all views of the call (the views seen as a single nv*H x W image)
+            imj = img.reshape(1, nv * H, W) if joint else img
+            st['stats'] = ops.image_max(imj, torch.empty(2 * imj.shape[0], dtype=f32, device=dev))
+            gray = ops.normalize_fwd(imj, st['stats'], torch.empty_like(imj))
+            st['joint'] = joint
         gray = gray.reshape(nv, H, W, 1)
         st['gray0'] = gray.reshape(nv, H, W)                      # self.d_gray (styler_3p.py:161): before any resize
         nh, nw = self._net_hw((H, W))
@@ -325,8 +335,11 @@ class Styler(StylerBase):
         if self.render_liquid:
             g_img = g_gray
         else:
-            g_img = ops.normalize_bwd(st['img'], st['stats'], g_gray, torch.empty(nv, dtype=f32, device=self.device),
-                                      torch.empty_like(g_gray))
+            imj, ggj = st['img'], g_gray.contiguous()
+            if st.get('joint'):
+                imj, ggj = imj.reshape(1, nv * H, W), ggj.reshape(1, nv * H, W)
+            g_img = ops.normalize_bwd(imj, st['stats'], ggj, torch.empty(imj.shape[0], dtype=f32, device=self.device),
+                                      torch.empty_like(ggj)).reshape(nv, H, W)
         ops.raymarch_bwd(ds, st['rot'], self.transmit, self.render_liquid, st['stot'], g_img, g_ds, st['box'], st['iv'])
 
     def _gray_path(self):
@@ -340,14 +353,15 @@ class Styler(StylerBase):
         return bool(pre) and pre[0] == 'conv1_1'
 
     # ---- one loss + gradient evaluation (= one sess.run([train_op, total_loss]) without Adam) ----
-    def loss_and_grad(self, fr, var, ws, rot, style_grams):
-        """Sum over the given views of total_loss, and d(sum)/d var.  Returns (loss [nv], grad)."""
+    def loss_and_grad(self, fr, var, ws, rot, style_grams, group=False):
+        """Sum over the given views of total_loss, and d(sum)/d var.  Returns (loss [nv], grad).  ``group``: the views
+        are ONE fed batch of the reference graph (v_batch > 1): joint normalisation and the group loss weights."""
         res = ws['res']
         d = self._density(fr, var, res, ws)
         box = ws['box']
         ds = ops.smooth3_relu_fwd(d, ws['ds'], self.k, box)        # styler_3p.py:112-125
         gray_path = self._gray_path()
-        st = self._render(ds, rot, box, ws['bricks'], net_input=not gray_path)
+        st = self._render(ds, rot, box, ws['bricks'], net_input=not gray_path, joint=group)
         nv = st['gray'].shape[0]
         loss = torch.zeros(nv, dtype=f32, device=self.device)
         g_gray0 = None
@@ -363,15 +377,16 @@ class Styler(StylerBase):
                 gm = ops.resize_bicubic_bwd(dm.reshape(nv, dm.shape[1], dm.shape[2], 1), H, W).reshape(nv, H, W)
                 g_gray0 = gm if g_gray0 is None else ops.axpy(g_gray0, gm, 1.0)
         else:
-            g_x = self.image_loss_and_grad(st['x'], st['d_img'], style_grams, loss)
+            g_x = self.image_loss_and_grad(st['x'], st['d_img'], style_grams, loss, group=group)
         g_ds = ops.fill_box(ws['g_ds'], box, 0.0)
         self._render_bwd(st, g_x, ds, g_ds, g_gray0)
         g_d = ops.smooth3_relu_bwd(g_ds, ds, ws['g_d'], self.k, box)
+        n_terms = 1 if group else nv                               # field / variable terms: once per fed batch
         if self.w_pressure > 0 and 'p' in self.target_field:       # styler_3p.py:96-98, styler_base.py:228-230
             pos = d > 0
             pr = torch.where(pos, d - 1, torch.zeros_like(d))
-            loss += self.w_pressure * (pr * pr).mean()
-            g_d += (nv * self.w_pressure * 2.0 / d.numel()) * pr
+            loss[:n_terms] += self.w_pressure * (pr * pr).mean()
+            g_d += (n_terms * self.w_pressure * 2.0 / d.numel()) * pr
         if 'd' in self.target_field:
             grad = torch.empty_like(var)
             if self.nsize == 1:
@@ -383,8 +398,8 @@ class Styler(StylerBase):
             if self.w_density > 0:                                 # styler_base.py:217-223
                 dv = torch.clamp(var, -1, 1)
                 inside = ((var >= -1) & (var <= 1)).to(f32)
-                loss += self.w_density * (dv.sum() ** 2 + 1e3 * (-torch.log(dv.abs() + 1e-6)).sum())
-                grad += nv * self.w_density * inside * (2 * dv.sum() - 1e3 * torch.sign(dv) / (dv.abs() + 1e-6))
+                loss[:n_terms] += self.w_density * (dv.sum() ** 2 + 1e3 * (-torch.log(dv.abs() + 1e-6)).sum())
+                grad += n_terms * self.w_density * inside * (2 * dv.sum() - 1e3 * torch.sign(dv) / (dv.abs() + 1e-6))
         else:
             scale = 0.8 * (2 * self.radius) ** 3 * self.rest_density / self.rest_density
             grad = ops.splat_sph_bwd_pos(fr['p'], var, ws['grid'], self._supports()[0], scale, g_d)
@@ -414,10 +429,11 @@ class Styler(StylerBase):
             acc = torch.empty_like(var)
             losses = []
             for i in range(0, self.n_views, self.v_batch):
-                l, grad = self.loss_and_grad(fr, var, ws, self._rot_all[i:i + 1], style_grams)
+                l, grad = self.loss_and_grad(fr, var, ws, self._rot_all[i:i + self.v_batch], style_grams,
+                                             group=self.v_batch > 1)
                 adam.step(var, grad, lr)
                 ops.iterate_accumulate(acc, var, i == 0)
-                losses.append(l)
+                losses.append(l.sum().reshape(1))                  # one total_loss per fed group
             loss_t = torch.cat(losses).mean()                      # :342
             delta = ops.iterate_delta(acc, 1.0 / n_step_views, g_opt_t, mask, mstride, torch.empty_like(var))  # :351-352
             return var, loss_t, delta

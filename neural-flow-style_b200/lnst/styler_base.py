@@ -177,7 +177,7 @@ class StylerBase(object):
             out[l] = (m, [float(a) for a in m.sum(dim=(1, 2)).cpu().tolist()])
         return out
 
-    def image_loss_and_grad(self, x, d_img, style_grams, loss, style_masks=None, gray=None, mask_grads=None):
+    def image_loss_and_grad(self, x, d_img, style_grams, loss, style_masks=None, gray=None, mask_grads=None, group=False):
         """x [n,H,W,3] net input (one image per view), d_img the same before mean subtraction.
         Adds each image's total feature/TV loss into ``loss[v]`` and returns d loss_v / d x_v
         stacked [n,H,W,3] (styler_base.py:127-213).
@@ -185,6 +185,10 @@ class StylerBase(object):
         ``gray`` [n,H,W] (0..1): the render is one channel replicated to RGB and the loss net can start from it
         (``LossNet.gray_path``, no TV loss): x and d_img are not read (may be None) and the result is
         d loss_v / d gray_v [n,H,W].
+
+        ``group``: the n images are one fed batch of the reference graph with batch_size = 1 (v_batch > 1): the Gram
+        loss reads image 0 only (``_gram_matrix`` loops over range(batch_size), styler_base.py:98), the content and TV
+        terms are means over the batch (:137-148, :212), i.e. weighted 1/n per image.
 
         ``mask_grads`` (a dict, 3-D style mask): filled with {style layer: d loss / d mask [n,h,w]} -- there the mask
         is the render itself and carries a gradient (styler_base.py:165-169)."""
@@ -195,9 +199,13 @@ class StylerBase(object):
         acts = self.net.forward(x, wanted, gray=gray) if wanted else {}
         shapes = {}
         handles = {}
+        share = 1.0 / n if group else 1.0                          # per-image weight of the batch-mean terms
+        acts_style = acts
+        if group and style_on:                                     # image 0 only
+            acts_style = {l: self.net.features_f32(acts, l)[:1] for l in self.style_layer}
         if style_on:
             for li, l in enumerate(self.style_layer):
-                handles[l] = self.net.gram(acts, l, style_grams[li], self.w_style * self.w_style_layer[li], loss,
+                handles[l] = self.net.gram(acts_style, l, style_grams[li], self.w_style * self.w_style_layer[li], loss,
                                            mask=style_masks[l] if style_masks else None)
 
         def add_loss_grad(name, g):
@@ -210,9 +218,14 @@ class StylerBase(object):
                     P = self.net.feature_pixels(acts, name) if hasattr(self.net, 'feature_pixels') else \
                         self._feature_pixels(hw[0], hw[1], name)
                     coef = self.w_style * self.w_style_layer[li] * 4.0 / (2.0 * P * ch)
-                    g = self.net.gram_grad(acts, name, handles[l], coef, g, is_conv)
+                    if group:                                      # cotangent on image 0, zeros on the others
+                        if g is None:
+                            g = torch.zeros_like(self.net.features_f32(acts, name))
+                        self.net.gram_grad(acts_style, name, handles[l], coef, g[:1], is_conv)
+                    else:
+                        g = self.net.gram_grad(acts, name, handles[l], coef, g, is_conv)
             if self.w_content and self.net2 is None and self.content_layer == name:
-                g = self.net.content(acts, name, self.content_channel, self.w_content, loss, g, is_conv,
+                g = self.net.content(acts, name, self.content_channel, self.w_content * share, loss, g, is_conv,
                                      target=getattr(self, '_content_feat', None), amp=self.w_content_amp)
             return g
 
@@ -228,7 +241,7 @@ class StylerBase(object):
             acts2 = net2.forward(x, [cl])
 
             def add2(name, g):
-                return net2.content(acts2, name, self.content_channel, self.w_content, loss, g, relu2,
+                return net2.content(acts2, name, self.content_channel, self.w_content * share, loss, g, relu2,
                                     target=getattr(self, '_content_feat', None), amp=self.w_content_amp)
 
             g2 = net2.backward(x, acts2, [cl], add2, {cl})
@@ -236,6 +249,6 @@ class StylerBase(object):
         if self.w_tv:
             g_tv = torch.empty_like(d_img[0])
             for v in range(n):
-                ops.tv_loss(d_img[v], self.w_tv, loss[v:v + 1], g_tv)
+                ops.tv_loss(d_img[v], self.w_tv * share, loss[v:v + 1], g_tv)
                 ops.axpy(g_x[v], g_tv, 1.0)
         return g_x

@@ -131,6 +131,11 @@ CASES = {
     # flows through the mask and through the masked area in the Gram denominator
     'density_style_mask': ('3d', 'smoke', dict(res=12, iter=3, rotate=True, n_views=3, style_mask=True,
                                                style_layer=['conv1_2', 'conv2_1'], w_style_layer=[0.5, 0.5]), 800),
+    # v_batch > 1 (config.py:69, styler_3p.py:329-352): a group of views is rendered and normalised by ONE maximum,
+    # the Gram loss reads only the group's first image (styler_base.py:98), content / TV average over the group
+    'density_vbatch': ('3d', 'smoke', dict(res=12, iter=2, rotate=True, n_views=6, v_batch=3, w_tv=1e-3, w_content=0.4,
+                                           content_layer='conv2_1', content_channel=5, style_layer=['conv1_2'],
+                                           w_style_layer=[1.0]), 800),
     'colour_2d': ('2c', 'dam', dict(iter=4, w_tv=0.01, style_layer=['conv1_1', 'conv2_1'], w_style_layer=[0.5, 0.5]), 0),
     'colour_2d_mask': ('2c', 'dam', dict(iter=3, style_mask=True, style_layer=['conv1_1', 'conv2_1'],
                                          w_style_layer=[0.5, 0.5]), 0),

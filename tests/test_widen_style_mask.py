@@ -116,3 +116,29 @@ def test_transport_between_frames(dev):
         for a, b in ((0, 3), (3, 1), (2, 2)):
             for rec in (True, False):
                 np.testing.assert_allclose(st._transport(g, v, a, b, recursive=rec), ref(a, b, rec), rtol=0, atol=3e-6)
+
+
+# ---- v_batch > 1 (config.py:69; styler_3p.py:329-352): groups of views per Adam step -----------------------------
+def test_engine_matches_reference_vbatch_run(dev):
+    import make_reference_golden as M
+    import test_reference_golden as TR
+    from lnst import synth
+    from lnst.styler_3p import Styler
+    name = 'density_vbatch'
+    cfg, params = M.case_inputs(name)
+    cfg.conv_math, cfg.view_mode = 'fp32', 'sequential'
+    st = Styler(cfg, weights=synth.vgg_weights(), device=dev)
+    st.style_img = TR._style_targets(cfg)[0]
+    TR._check(st.run(params), dict(np.load(os.path.join(GOLD, 'ref_%s.npz' % name))), '3d')
+
+
+def test_oracle_matches_reference_vbatch_run():
+    import make_reference_golden as M
+    import test_reference_golden as TR
+    import oracle.vgg
+    from oracle.styler import Oracle3P
+    name = 'density_vbatch'
+    cfg, params = M.case_inputs(name)
+    out = Oracle3P(cfg, oracle.vgg.synthetic_weights()).run(params, style_targets=TR._style_targets(cfg),
+                                                          view_mode='sequential')
+    TR._check(out, dict(np.load(os.path.join(GOLD, 'ref_%s.npz' % name))), '3d', ltol=2e-5, ftol=1e-4)
