@@ -55,7 +55,8 @@ class Styler(StylerBase):
         ops.to_net_input_fwd(gray3, 255.0, d_img, x)                  # styler_base.py:41-45
         return {'grid': grid, 'd_raw': d_raw, 'd': d, 'd_img': d_img, 'x': x, 'hw': (H, W)}
 
-    def loss_and_grad(self, fr, var, res, style_grams):
+    def loss_and_grad(self, fr, var, res, style_grams, share=1.0):
+        """``share``: 1/batch_size -- this frame's weight in the batch-mean terms of a joint loss (content, TV)"""
         st = self._forward(fr, var, res)
         loss = torch.zeros(1, dtype=f32, device=self.device)
         masks = None
@@ -66,7 +67,7 @@ class Styler(StylerBase):
                 self._cache[key] = self.style_masks_for(self._gray(fr, res).reshape(1, H_, W_),
                                                         (st['x'].shape[1], st['x'].shape[2]))
             masks = self._cache[key]
-        g_x = self.image_loss_and_grad(st['x'], st['d_img'], style_grams, loss, style_masks=masks)
+        g_x = self.image_loss_and_grad(st['x'], st['d_img'], style_grams, loss, style_masks=masks, share=share)
         H, W = st['hw']
         g_d3 = ops.to_net_input_bwd(g_x, 3, 255.0, torch.empty(1, g_x.shape[1], g_x.shape[2], 3, dtype=f32,
                                                                 device=self.device))
@@ -89,6 +90,8 @@ class Styler(StylerBase):
     def run(self, params, c_init=None):
         dev = self.device
         nf = self.num_frames
+        if nf % self.batch_size:
+            raise ValueError('num_frames must be a multiple of batch_size (the reference feeds p[t+i], styler_2p.py:237-240)')
         oct_size = octave_sizes(self.resolution, self.octave_n, self.octave_scale)
         frames = []
         for i in range(nf):
@@ -113,16 +116,23 @@ class Styler(StylerBase):
             loss_o, intm_o = [], []
             for step in range(self.iter):
                 deltas = []
-                for t in range(0, nf, self.batch_size):
-                    fr = frames[t]
-                    var = g_opt[t].clone()
-                    adam = opt_.setdefault(t // self.frames_per_opt, _Adam())
-                    l, grad = self.loss_and_grad(fr, var, res, style_grams)
-                    adam.step(var, grad, lr)
-                    loss_o.append(l[0])
-                    deltas.append(ops.iterate_delta(var, 1.0, g_opt[t], None, 0, torch.empty_like(var)))   # :260-262
-                    if step == self.iter - 1 and octave < self.octave_n - 1:
-                        intm_o.append(self._out_image(fr, var, res))
+                # batch_size frames per sess.run (:236-262): ONE joint loss -- Gram terms summed over the batch, content
+                # and TV means over it -- and one Adam op over the batch's variables: slot i of the group's optimizer is
+                # shared by every frame fed into position i; no term couples the frames, so they run one after another
+                B = self.batch_size
+                for t in range(0, nf, B):
+                    joint = None
+                    for i in range(B):
+                        fr = frames[t + i]
+                        var = g_opt[t + i].clone()
+                        adam = opt_.setdefault((t // self.frames_per_opt, i), _Adam())
+                        l, grad = self.loss_and_grad(fr, var, res, style_grams, share=1.0 / B)
+                        adam.step(var, grad, lr)
+                        joint = l[0] if joint is None else joint + l[0]
+                        deltas.append(ops.iterate_delta(var, 1.0, g_opt[t + i], None, 0, torch.empty_like(var)))   # :260-262
+                        if step == self.iter - 1 and octave < self.octave_n - 1:
+                            intm_o.append(self._out_image(fr, var, res))
+                    loss_o.append(joint)
                 if self.window_sigma > 0 and nf > 1:                                 # :276-277
                     sm = ops.temporal_gauss(torch.stack(deltas, 0), self.window_sigma)
                     deltas = [sm[j] for j in range(nf)]

@@ -79,6 +79,11 @@ class StepRunner:
 class Styler(StylerBase):
     def __init__(self, self_dict, weights=None, device=None, content_weights=None):
         StylerBase.__init__(self, self_dict, weights=weights, device=device, content_weights=content_weights)
+        if self.batch_size != 1:
+            raise NotImplementedError('batch_size > 1 in the 3-D styler: the smoke render is normalised by ONE maximum over the '
+                                      'batch (styler_3p.py:158) and the reference itself breaks with rotate '
+                                      '(:417 feeds batch_size matrices, rotate() tiles the batch by them); the 2-D '
+                                      'colour styler has it')
         if self.target_field not in ('d', 'p'):
             raise ValueError("styler_3p handles target_field 'd' or 'p'")
         if 'd' in self.target_field and self.num_kernels > 4:

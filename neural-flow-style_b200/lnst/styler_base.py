@@ -32,8 +32,6 @@ class StylerBase(object):
             device = torch.device('cuda', torch.cuda.current_device()) if lib.kind == 'cuda' else torch.device('cpu')
         self.device = torch.device(device)
         self.model_path = os.path.join(self.data_dir, self.model_dir, self.network)   # :18
-        if self.batch_size != 1:
-            raise NotImplementedError('batch_size > 1 is not built yet (every reference driver uses 1)')
         if 'vgg' in self.model_path:
             if weights is None:
                 weights = load_weights(self.model_path, model_name(self.network))
@@ -177,7 +175,8 @@ class StylerBase(object):
             out[l] = (m, [float(a) for a in m.sum(dim=(1, 2)).cpu().tolist()])
         return out
 
-    def image_loss_and_grad(self, x, d_img, style_grams, loss, style_masks=None, gray=None, mask_grads=None, group=False):
+    def image_loss_and_grad(self, x, d_img, style_grams, loss, style_masks=None, gray=None, mask_grads=None, group=False,
+                            share=None):
         """x [n,H,W,3] net input (one image per view), d_img the same before mean subtraction.
         Adds each image's total feature/TV loss into ``loss[v]`` and returns d loss_v / d x_v
         stacked [n,H,W,3] (styler_base.py:127-213).
@@ -190,6 +189,9 @@ class StylerBase(object):
         loss reads image 0 only (``_gram_matrix`` loops over range(batch_size), styler_base.py:98), the content and TV
         terms are means over the batch (:137-148, :212), i.e. weighted 1/n per image.
 
+        ``share``: weight of the batch-mean terms (content, TV) when the images of one fed batch are evaluated in
+        separate calls (batch_size > 1 in the 2-D styler: 1/batch_size); the Gram terms are sums over the batch.
+
         ``mask_grads`` (a dict, 3-D style mask): filled with {style layer: d loss / d mask [n,h,w]} -- there the mask
         is the render itself and carries a gradient (styler_base.py:165-169)."""
         n = x.shape[0] if gray is None else gray.shape[0]
@@ -199,7 +201,8 @@ class StylerBase(object):
         acts = self.net.forward(x, wanted, gray=gray) if wanted else {}
         shapes = {}
         handles = {}
-        share = 1.0 / n if group else 1.0                          # per-image weight of the batch-mean terms
+        if share is None:
+            share = 1.0 / n if group else 1.0                      # per-image weight of the batch-mean terms
         acts_style = acts
         if group and style_on:                                     # image 0 only
             acts_style = {l: self.net.features_f32(acts, l)[:1] for l in self.style_layer}
