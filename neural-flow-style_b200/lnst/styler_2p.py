@@ -18,8 +18,6 @@ from .vgg import _R_MEAN, _G_MEAN, _B_MEAN
 class Styler(StylerBase):
     def __init__(self, self_dict, weights=None, device=None, content_weights=None):
         StylerBase.__init__(self, self_dict, weights=weights, device=device, content_weights=content_weights)
-        if self.style_mask and self.style_mask_on_ref:
-            raise NotImplementedError('style_mask_on_ref (styler_base.py:171-173) is not built')
         if self.style_mask and self.conv_math != 'fp32':
             raise NotImplementedError("style_mask needs conv_math='fp32' (the masked Gram runs on the fp32 path)")
 
@@ -67,6 +65,11 @@ class Styler(StylerBase):
                 self._cache[key] = self.style_masks_for(self._gray(fr, res).reshape(1, H_, W_),
                                                         (st['x'].shape[1], st['x'].shape[2]))
             masks = self._cache[key]
+            if self.style_mask_on_ref:                             # the mask is constant per (frame, octave): so is the target
+                gkey = (fr['id'], tuple(res), 'grams_on_ref')
+                if gkey not in self._cache:
+                    self._cache[gkey] = self.masked_style_grams(masks)
+                style_grams = self._cache[gkey]
         g_x = self.image_loss_and_grad(st['x'], st['d_img'], style_grams, loss, style_masks=masks, share=share)
         H, W = st['hw']
         g_d3 = ops.to_net_input_bwd(g_x, 3, 255.0, torch.empty(1, g_x.shape[1], g_x.shape[2], 3, dtype=f32,

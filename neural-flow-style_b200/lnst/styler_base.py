@@ -135,6 +135,9 @@ class StylerBase(object):
         2*h*w*C (styler_base.py:157-162,178-179, 249-278).  Returned as device tensors."""
         x = self._target_tensor(style_target, style_shp)
         acts = self.net.forward(x, list(self.style_layer))
+        # kept for style_mask_on_ref (styler_base.py:171-173: the style feature itself is masked per frame)
+        self._style_acts = {l: self.net.features_f32(acts, l) for l in self.style_layer} if getattr(
+            self, 'style_mask_on_ref', False) and self.style_mask else None
         grams = []
         for l in self.style_layer:
             if 'input' in l:
@@ -150,6 +153,19 @@ class StylerBase(object):
         for _ in range(block - 1):
             h, w = h // 2, w // 2
         return h * w
+
+    def masked_style_grams(self, masks):
+        """Style Gram targets under ``style_mask_on_ref`` (styler_base.py:171-173): (Fs m)^T (Fs m) / (2 area C) with the
+        render's own mask and area; ``masks`` as returned by ``style_masks_for`` (one image)."""
+        grams = []
+        for l in self.style_layer:
+            fs, (m, area) = self._style_acts[l], masks[l]
+            if tuple(fs.shape[1:3]) != tuple(m.shape[1:3]):
+                raise ValueError('style_mask_on_ref: style feature %s and render feature %s differ in size (the reference '
+                                 'multiplies them elementwise)' % (tuple(fs.shape[1:3]), tuple(m.shape[1:3])))
+            handle = self.net.gram({l: fs}, l, None, 0.0, None, mask=(m[:1], area[:1]))
+            grams.append(self.net.gram_values(handle)[0].contiguous())
+        return grams
 
     def _content_feature(self, content_target, content_shp):
         """Feature of the content target at ``content_layer`` (styler_base.py:233-247): fp32 [h,w,C] on the

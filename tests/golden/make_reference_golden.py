@@ -140,6 +140,9 @@ CASES = {
     'colour_2d_mask': ('2c', 'dam', dict(iter=3, style_mask=True, style_layer=['conv1_1', 'conv2_1'],
                                          w_style_layer=[0.5, 0.5]), 0),
     'colour_2d_frames': ('2c', 'dam', dict(iter=2, num_frames=3, window_sigma=1.0), 0),
+    # style_mask_on_ref (styler_base.py:171-173): the style feature is masked and area-normalised like the render's
+    'colour_2d_mask_on_ref': ('2c', 'dam', dict(iter=3, style_mask=True, style_mask_on_ref=True,
+                                                style_layer=['conv1_1', 'conv2_1'], w_style_layer=[0.5, 0.5]), 0),
     # batch_size > 1 (styler_2p.py:42,236-262): two frames per sess.run -- one joint loss (Gram terms summed over the
     # batch, TV / content averaged), one Adam op over both frames' variables, slots shared by the frames of a group
     'colour_2d_batch': ('2c', 'dam', dict(iter=3, num_frames=4, batch_size=2, frames_per_opt=4, window_sigma=1.0, w_tv=0.01,

@@ -26,7 +26,7 @@ import make_reference_golden as M  # noqa: E402
 CASES_3D = ['density_noview', 'density_sequential', 'density_resize_tv_content', 'density_octaves_poisson',
             'density_sequence', 'density_interp_both', 'density_reg_content_image', 'position_clip_vgg16',
             'position_liquid', 'position_smoke_views']
-CASES_2D = ['colour_2d', 'colour_2d_mask', 'colour_2d_frames', 'colour_2d_batch']
+CASES_2D = ['colour_2d', 'colour_2d_mask', 'colour_2d_frames', 'colour_2d_batch', 'colour_2d_mask_on_ref']
 
 
 def _ref(name):
