@@ -181,3 +181,100 @@ def test_v1_checkpoint_partitioned_tensor_is_reassembled(tmp_path):
         bad = tmp_path / 'bad.ckpt'
         bad.write_bytes(b'x' * 100)
         tfckpt.read(str(bad))
+
+
+def _slice_messages():
+    """SavedTensorSlices & co. declared on the fly with TensorFlow's field numbers (saved_tensor_slice.proto,
+    tensor_slice.proto, tensor.proto, tensor_shape.proto) -- the protobuf library as an independent codec."""
+    from google.protobuf import descriptor_pb2, descriptor_pool, message_factory
+    Fd = descriptor_pb2.FieldDescriptorProto
+    fd = descriptor_pb2.FileDescriptorProto(name='lnst_ckpt_subset.proto', package='lnstck', syntax='proto3')
+    O, R = Fd.LABEL_OPTIONAL, Fd.LABEL_REPEATED
+
+    def msg(name, spec):
+        m = fd.message_type.add(name=name)
+        for fname, num, typ, label, tname in spec:
+            f = m.field.add(name=fname, number=num, type=typ, label=label)
+            if tname:
+                f.type_name = '.lnstck.' + tname
+
+    msg('Dim', [('size', 1, Fd.TYPE_INT64, O, None)])
+    msg('TensorShapeProto', [('dim', 2, Fd.TYPE_MESSAGE, R, 'Dim')])
+    msg('TensorProto', [('dtype', 1, Fd.TYPE_INT32, O, None), ('tensor_shape', 2, Fd.TYPE_MESSAGE, O, 'TensorShapeProto'),
+                        ('tensor_content', 4, Fd.TYPE_BYTES, O, None), ('float_val', 5, Fd.TYPE_FLOAT, R, None),
+                        ('int_val', 7, Fd.TYPE_INT32, R, None)])
+    msg('Extent', [('start', 1, Fd.TYPE_INT64, O, None), ('length', 2, Fd.TYPE_INT64, O, None)])
+    msg('TensorSliceProto', [('extent', 1, Fd.TYPE_MESSAGE, R, 'Extent')])
+    msg('SavedSliceMeta', [('name', 1, Fd.TYPE_STRING, O, None), ('shape', 2, Fd.TYPE_MESSAGE, O, 'TensorShapeProto'),
+                           ('type', 3, Fd.TYPE_INT32, O, None), ('slice', 4, Fd.TYPE_MESSAGE, R, 'TensorSliceProto')])
+    msg('SavedTensorSliceMeta', [('tensor', 1, Fd.TYPE_MESSAGE, R, 'SavedSliceMeta')])
+    msg('SavedSlice', [('name', 1, Fd.TYPE_STRING, O, None), ('slice', 2, Fd.TYPE_MESSAGE, O, 'TensorSliceProto'),
+                       ('data', 3, Fd.TYPE_MESSAGE, O, 'TensorProto')])
+    msg('SavedTensorSlices', [('meta', 1, Fd.TYPE_MESSAGE, O, 'SavedTensorSliceMeta'), ('data', 2, Fd.TYPE_MESSAGE, O, 'SavedSlice')])
+    pool = descriptor_pool.DescriptorPool()
+    pool.Add(fd)
+    get = getattr(message_factory, 'GetMessageClass', None)
+    if get is None:
+        get = message_factory.MessageFactory(pool).GetPrototype
+    return get(pool.FindMessageTypeByName('lnstck.SavedTensorSlices'))
+
+
+def test_v1_checkpoint_protos_against_the_protobuf_library(tmp_path):
+    import struct
+    from lnst import tfckpt
+    from lnst.graphdef import _enc_varint
+    STS = _slice_messages()
+    # 1. what lnst.tfckpt.write emits parses with the protobuf library to the same content
+    t = {'a/weights': np.arange(24, dtype=np.float32).reshape(2, 3, 4) - 3.5, 'step': np.asarray([7, -2], np.int32)}
+    path = str(tmp_path / 'w.ckpt')
+    tfckpt.write(path, t)
+    seen = {}
+    blob = memoryview(open(path, 'rb').read())
+    for key, val in tfckpt._entries(blob):
+        m = STS()
+        m.ParseFromString(bytes(val))
+        if key == b'':
+            meta = {s.name: ([d.size for d in s.shape.dim], s.type, len(s.slice)) for s in m.meta.tensor}
+        else:
+            d = m.data
+            seen[d.name] = (list(d.data.float_val) or list(d.data.int_val), [d_.size for d_ in d.data.tensor_shape.dim],
+                            [(e.start, e.length) for e in d.slice.extent])
+    assert meta == {'a/weights': ([2, 3, 4], 1, 1), 'step': ([2], 3, 1)}
+    assert seen['a/weights'][0] == list(t['a/weights'].reshape(-1)) and seen['a/weights'][2] == [(0, 0)] * 3
+    assert seen['step'][0] == [7, -2]
+    # 2. protos written by the protobuf library (packed float_val, one full slice and one two-part tensor) are read back
+    m0 = STS()
+    for name, shape, dt in (('x', [2, 2], 1), ('y', [4], 1)):
+        s = m0.meta.tensor.add(name=name, type=dt)
+        for d in shape:
+            s.shape.dim.add(size=d)
+    ents = [(b'', m0.SerializeToString())]
+    mx = STS()
+    mx.data.name = 'x'
+    mx.data.slice.extent.add()
+    mx.data.slice.extent.add()
+    mx.data.data.dtype = 1
+    mx.data.data.float_val.extend([1.5, 2.5, 3.5, 4.5])
+    ents.append((b'\x00x\x00\x01', mx.SerializeToString()))
+    for start, vals in ((0, [10.0]), (1, [11.0, 12.0, 13.0])):
+        my = STS()
+        my.data.name = 'y'
+        e = my.data.slice.extent.add(start=start, length=len(vals))
+        my.data.data.dtype = 1
+        my.data.data.float_val.extend(vals)
+        ents.append((b'\x00y\x00\x01' + bytes([start]), my.SerializeToString()))
+    out, index = bytearray(), []
+    blk = tfckpt._enc_block(ents)                               # all entries in ONE data block this time
+    index.append((ents[-1][0] + b'\x00', _enc_varint(0) + _enc_varint(len(blk))))
+    out += blk + b'\x00' * 5
+    mo, mblk = len(out), tfckpt._enc_block([])
+    out += mblk + b'\x00' * 5
+    io, iblk = len(out), tfckpt._enc_block(index)
+    out += iblk + b'\x00' * 5
+    foot = _enc_varint(mo) + _enc_varint(len(mblk)) + _enc_varint(io) + _enc_varint(len(iblk))
+    out += foot + b'\x00' * (40 - len(foot)) + struct.pack('<Q', tfckpt.MAGIC)
+    p2 = tmp_path / 'pb.ckpt'
+    p2.write_bytes(bytes(out))
+    got = tfckpt.read(str(p2))
+    np.testing.assert_array_equal(got['x'], np.array([[1.5, 2.5], [3.5, 4.5]], np.float32))
+    np.testing.assert_array_equal(got['y'], np.array([10, 11, 12, 13], np.float32))
