@@ -80,10 +80,13 @@ class Styler(StylerBase):
     def __init__(self, self_dict, weights=None, device=None, content_weights=None):
         StylerBase.__init__(self, self_dict, weights=weights, device=device, content_weights=content_weights)
         if self.batch_size != 1:
-            raise NotImplementedError('batch_size > 1 in the 3-D styler: the smoke render is normalised by ONE maximum over the '
-                                      'batch (styler_3p.py:158) and the reference itself breaks with rotate '
-                                      '(:417 feeds batch_size matrices, rotate() tiles the batch by them); the 2-D '
-                                      'colour styler has it')
+            if self.rotate:
+                raise NotImplementedError('batch_size > 1 with rotate: the reference itself breaks there (styler_3p.py:417 '
+                                          'feeds batch_size matrices and rotate() tiles the batch by them)')
+            if self.conv_math != 'fp32' and 'vgg' in self.model_path:
+                raise NotImplementedError("batch_size > 1 needs conv_math='fp32'")
+            if self.style_mask:
+                raise NotImplementedError('batch_size > 1 with style_mask')
         if self.target_field not in ('d', 'p'):
             raise ValueError("styler_3p handles target_field 'd' or 'p'")
         if 'd' in self.target_field and self.num_kernels > 4:
@@ -419,6 +422,184 @@ class Styler(StylerBase):
         p_out = fr['p'] + var if 'p' in self.target_field else fr['p']
         return p_out, ds + 0.0, st['d_img'][0]                     # "+0.0" folds the -0.0 markers
 
+    # ---- batch_size > 1 (styler_3p.py:42, 304-363, 409-431), rotate off ----------------------------------------
+    def _render_batch(self, ds_list, ws):
+        """B smoothed fields -> net input of the fed batch.  `d /= tf.reduce_max(d)` (:158) is ONE maximum over all B
+        renders: the frames of a batch are coupled through it (forward value and, via the ties rule, gradient)."""
+        B = len(ds_list)
+        D, H, W = ds_list[0].shape
+        dev = self.device
+        img = torch.empty(B, H, W, dtype=f32, device=dev)
+        stot = torch.empty(B, H, W, dtype=f32, device=dev)
+        for i, ds in enumerate(ds_list):
+            ops.raymarch_fwd(ds, None, self.transmit, self.render_liquid, img[i:i + 1], stot[i:i + 1], ws['box'])
+        st = {'img': img, 'stot': stot, 'hw': (H, W)}
+        if self.render_liquid:
+            gray = img
+        else:
+            imj = img.reshape(1, B * H, W)
+            st['stats'] = ops.image_max(imj, torch.empty(2, dtype=f32, device=dev))
+            gray = ops.normalize_fwd(imj, st['stats'], torch.empty_like(imj))
+        gray = gray.reshape(B, H, W, 1)
+        nh, nw = self._net_hw((H, W))
+        if (nh, nw) != (H, W):
+            gray = ops.resize_bilinear_fwd(gray, nh, nw)
+        d_img = torch.empty(B, nh, nw, 3, dtype=f32, device=dev)
+        x = torch.empty(B, nh, nw, 3, dtype=f32, device=dev)
+        ops.to_net_input_fwd(gray, 255.0, d_img, x)
+        st.update(d_img=d_img, x=x)
+        return st
+
+    def _fields_batch(self, frs, var_list, ws):
+        """(d_i, smoothed d_i) per frame, each in its own buffer (the workspace volumes are per-call scratch)."""
+        d_list, ds_list = [], []
+        for fr, var in zip(frs, var_list):
+            d = self._density(fr, var, ws['res'], ws).clone()
+            ds_list.append(ops.smooth3_relu_fwd(d, torch.zeros_like(d), self.k, ws['box']))
+            d_list.append(d)
+        return d_list, ds_list
+
+    def loss_and_grad_batch(self, frs, var_list, ws, style_grams):
+        """One `sess.run([train_op, total_loss])` of a fed batch: joint loss (scalar tensor) and d loss / d var_i.
+        Gram terms are sums over the batch, content / TV / pressure are means over it (styler_base.py:127-230)."""
+        B = len(frs)
+        d_list, ds_list = self._fields_batch(frs, var_list, ws)
+        st = self._render_batch(ds_list, ws)
+        loss = torch.zeros(B, dtype=f32, device=self.device)
+        g_x = self.image_loss_and_grad(st['x'], st['d_img'], style_grams, loss, share=1.0 / B)
+        H, W = st['hw']
+        g_gray = ops.to_net_input_bwd(g_x, 1, 255.0, torch.empty(B, g_x.shape[1], g_x.shape[2], 1, dtype=f32,
+                                                                 device=self.device))
+        if (g_x.shape[1], g_x.shape[2]) != (H, W):
+            g_gray = ops.resize_bilinear_bwd(g_gray, H, W)
+        g_gray = g_gray.reshape(B, H, W).contiguous()
+        if self.render_liquid:
+            g_img = g_gray
+        else:
+            g_img = ops.normalize_bwd(st['img'].reshape(1, B * H, W), st['stats'], g_gray.reshape(1, B * H, W),
+                                      torch.empty(1, dtype=f32, device=self.device),
+                                      torch.empty(1, B * H, W, dtype=f32, device=self.device)).reshape(B, H, W)
+        total = loss.sum()
+        grads = []
+        for i, (fr, var) in enumerate(zip(frs, var_list)):
+            d, ds = d_list[i], ds_list[i]
+            g_ds = ops.fill_box(ws['g_ds'], ws['box'], 0.0)
+            ops.raymarch_bwd(ds, None, self.transmit, self.render_liquid, st['stot'][i:i + 1], g_img[i:i + 1].contiguous(),
+                             g_ds, ws['box'])
+            g_d = ops.smooth3_relu_bwd(g_ds, ds, ws['g_d'], self.k, ws['box'])
+            if self.w_pressure > 0 and 'p' in self.target_field:   # reduce_mean over the [B,D,H,W,1] pressure tensor
+                pr = torch.where(d > 0, d - 1, torch.zeros_like(d))
+                total = total + self.w_pressure * (pr * pr).mean() / B
+                g_d += (self.w_pressure * 2.0 / (B * d.numel())) * pr
+            if 'd' in self.target_field:
+                grad = torch.empty_like(var)
+                if self.nsize == 1:
+                    ops.splat_wavg_bwd_coef(fr['p'], var, ws['grid'], self._supports(),
+                                            self._coef(fr, ws['res'], ws['grid']), g_d, grad)
+                else:
+                    ops.splat_wavg_bwd(fr['p'], var, ws['grid'], self._supports(), self._wmap(fr, ws['res'], ws['grid']),
+                                       g_d, grad)
+                if self.w_density > 0:                             # summed over the batch (styler_base.py:217-223)
+                    dv = torch.clamp(var, -1, 1)
+                    inside = ((var >= -1) & (var <= 1)).to(f32)
+                    total = total + self.w_density * (dv.sum() ** 2 + 1e3 * (-torch.log(dv.abs() + 1e-6)).sum())
+                    grad += self.w_density * inside * (2 * dv.sum() - 1e3 * torch.sign(dv) / (dv.abs() + 1e-6))
+            else:
+                scale = 0.8 * (2 * self.radius) ** 3 * self.rest_density / self.rest_density
+                grad = ops.splat_sph_bwd_pos(fr['p'], var, ws['grid'], self._supports()[0], scale, g_d)
+            grads.append(grad)
+        return total, grads
+
+    def _infer_batch(self, frs, var_list, ws):
+        """forward only for a fed batch: (p_out_i, d_out_i, d_img_i) with the batch's joint normalisation"""
+        _, ds_list = self._fields_batch(frs, var_list, ws)
+        st = self._render_batch(ds_list, ws)
+        return [((fr['p'] + var) if 'p' in self.target_field else fr['p'], ds + 0.0, st['d_img'][i])
+                for i, (fr, var, ds) in enumerate(zip(frs, var_list, ds_list))]
+
+    def _run_batched(self, params):
+        """`run` for batch_size > 1: the reference's loop with B frames per `sess.run` (one process, eager launches --
+        the single-frame path keeps the CUDA-graph / sharded loop)."""
+        dev = self.device
+        nf, B, itp = self.num_frames, self.batch_size, self.interp
+        if any(t + (B - 1) * itp >= nf for t in range(0, nf, B * itp)) or nf % B:
+            raise ValueError('the key frames must fill whole batches (the reference feeds p[t+i*interp], styler_3p.py:304-308, '
+                             'and p[t+i] in the final pass, :409-412)')
+        lr_list = None
+        if abs(self.lr_scale - 1) > 1e-7:
+            lr_list = [self.lr / self.lr_scale ** i for i in range(self.octave_n)]
+        oct_size = octave_sizes(self.resolution, self.octave_n, self.octave_scale)
+        frames, inv = self.upload(params)
+        width = 3 if 'p' in self.target_field else self.num_kernels
+        g_opt = [torch.zeros(fr['p'].shape[0], width, dtype=f32, device=dev) for fr in frames]
+        key = list(range(0, nf, itp))
+        mask_of = (lambda fr: fr['r']) if 'd' in self.target_field else (lambda fr: None)
+        mstride = self.num_kernels if 'd' in self.target_field else 0
+        loss_history, d_intm, opt_ = [], [], {}
+        for octave in range(self.octave_n):
+            res = oct_size[octave]
+            self._frame_cache = {}
+            ws = self._workspace(res, frames)
+            style_grams = None
+            if self.w_style and self.style_img is not None:
+                style_grams = self._style_feature(self.style_img, res[1:])
+            self._content_feat = None
+            if self.w_content and self.content_img is not None:
+                self._content_feat = self._content_feature(self.content_img, res[1:])
+            lr = lr_list[octave] if lr_list is not None else (self.lr[octave] if isinstance(self.lr, list) else self.lr)
+            loss_o, intm_o = [], []
+            for step in range(self.iter):
+                deltas = {}
+                for t in range(0, nf, B * itp):
+                    idx = [t + i * itp for i in range(B)]
+                    frs = [frames[f] for f in idx]
+                    var = [g_opt[f].clone() for f in idx]                            # :312
+                    total, grads = self.loss_and_grad_batch(frs, var, ws, style_grams)
+                    for i in range(B):                                               # one Adam op, a slot per position
+                        opt_.setdefault((t // self.frames_per_opt, i), _Adam()).step(var[i], grads[i], lr)
+                    loss_o.append(total)
+                    for i, f in enumerate(idx):                                      # :359-363
+                        deltas[f] = ops.iterate_delta(var[i], 1.0, g_opt[f], mask_of(frames[f]), mstride,
+                                                      torch.empty_like(var[i]))
+                    if step == self.iter - 1 and octave < self.octave_n - 1:         # :365-370
+                        intm_o += [o[2] for o in self._infer_batch(frs, var, ws)]
+                if self.window_sigma > 0 and nf > 1:                                 # :382-383
+                    sm = ops.temporal_gauss(torch.stack([deltas[f] for f in key], 0), self.window_sigma)
+                    for j, f in enumerate(key):
+                        deltas[f] = sm[j]
+                for f in key:                                                        # :385-386
+                    ops.axpy(g_opt[f], deltas[f].contiguous(), 1.0)
+            loss_history.append([float(v) for v in torch.stack(loss_o).cpu().tolist()] if loss_o else [])
+            if octave < self.octave_n - 1:
+                d_intm.append(torch.stack(intm_o, 0).cpu().numpy().astype(np.uint8))
+        if itp > 1:                                                                  # :392-397
+            w = np.linspace(0, 1, itp + 1)
+            for t in range(0, nf - 1, itp):
+                for i in range(1, itp):
+                    g_opt[t + i] = g_opt[t] * float(1 - w[i]) + g_opt[t + itp] * float(w[i])
+        result = {'l': loss_history, 'd_intm': d_intm, 'v': None, 'c': None}
+        res = oct_size[-1]
+        self._frame_cache = {}
+        ws = self._workspace(res, frames)
+        p_sty, v_sty, d_sty, r_sty = [], [], [], []
+        for t in range(0, nf, B):                                                    # :409-431
+            idx = list(range(t, min(t + B, nf)))
+            outs = self._infer_batch([frames[f] for f in idx], [g_opt[f] for f in idx], ws)
+            for f, (p_out, d_out, d_img) in zip(idx, outs):
+                if inv is not None:
+                    p_out, g_opt[f] = p_out[inv], g_opt[f][inv]
+                p_sty.append(p_out.cpu().numpy())
+                v_sty.append(g_opt[f].cpu().numpy())
+                d_sty.append(d_out.cpu().numpy()[..., None])
+                r_sty.append(d_img.cpu().numpy().astype(np.uint8))
+        result['p'] = p_sty
+        if 'p' in self.target_field:
+            result['v'] = v_sty
+        result['d'] = np.array(d_sty)
+        result['r'] = np.array(r_sty)
+        result['g_opt'] = [g.cpu().numpy() for g in g_opt]
+        return result
+
     # ---- one pass of the loop body for one frame (styler_3p.py:304-363) --------------------------
     def frame_step(self, fr, g_opt_t, adam, ws, style_grams, lr):
         """var <- g_opt[t]; Adam step(s) over the views; returns (var, loss, delta) with
@@ -497,6 +678,8 @@ class Styler(StylerBase):
 
     # ---- the optimisation loop (styler_3p.py:229-438) ----------------------------------------------
     def run(self, params):
+        if self.batch_size > 1:
+            return self._run_batched(params)
         dev = self.device
         nf = self.num_frames
         lr_list = None

@@ -136,6 +136,14 @@ CASES = {
     'density_vbatch': ('3d', 'smoke', dict(res=12, iter=2, rotate=True, n_views=6, v_batch=3, w_tv=1e-3, w_content=0.4,
                                            content_layer='conv2_1', content_channel=5, style_layer=['conv1_2'],
                                            w_style_layer=[1.0]), 800),
+    # batch_size > 1 in 3-D without rotate (styler_3p.py:42,304-363,409-431): two frames per sess.run -- ONE maximum
+    # normalises both renders (:158, also in the final renders), Gram terms summed over the batch, content / TV /
+    # pressure means over it, one Adam op over both frames' variables
+    'density_batch': ('3d', 'smoke', dict(res=12, iter=3, rotate=False, num_frames=4, batch_size=2, frames_per_opt=4,
+                                          window_sigma=1.0, w_tv=1e-3, w_content=0.4, content_layer='conv2_1',
+                                          content_channel=5, style_layer=['conv1_2'], w_style_layer=[1.0]), 600),
+    'position_batch_pressure': ('3p', 'liquid', dict(res=12, iter=3, num_frames=2, batch_size=2, frames_per_opt=2,
+                                                     w_pressure=0.5, style_layer=['conv1_2'], w_style_layer=[1.0]), 600),
     'colour_2d': ('2c', 'dam', dict(iter=4, w_tv=0.01, style_layer=['conv1_1', 'conv2_1'], w_style_layer=[0.5, 0.5]), 0),
     'colour_2d_mask': ('2c', 'dam', dict(iter=3, style_mask=True, style_layer=['conv1_1', 'conv2_1'],
                                          w_style_layer=[0.5, 0.5]), 0),

@@ -142,3 +142,29 @@ def test_oracle_matches_reference_vbatch_run():
     out = Oracle3P(cfg, oracle.vgg.synthetic_weights()).run(params, style_targets=TR._style_targets(cfg),
                                                           view_mode='sequential')
     TR._check(out, dict(np.load(os.path.join(GOLD, 'ref_%s.npz' % name))), '3d', ltol=2e-5, ftol=1e-4)
+
+
+# ---- batch_size > 1 in the 3-D styler, rotate off (styler_3p.py:42,304-363,409-431) ----------------------------------
+@pytest.mark.parametrize('name', ['density_batch', 'position_batch_pressure'])
+def test_engine_matches_reference_batch_run_3d(dev, name):
+    import make_reference_golden as M
+    import test_reference_golden as TR
+    from lnst import synth
+    from lnst.styler_3p import Styler
+    cfg, params = M.case_inputs(name)
+    cfg.conv_math, cfg.view_mode = 'fp32', 'sequential'
+    st = Styler(cfg, weights=synth.vgg_weights(), device=dev)
+    st.style_img = TR._style_targets(cfg)[0]
+    TR._check(st.run(params), dict(np.load(os.path.join(GOLD, 'ref_%s.npz' % name))), M.CASES[name][0])
+
+
+@pytest.mark.parametrize('name', ['density_batch', 'position_batch_pressure'])
+def test_oracle_matches_reference_batch_run_3d(name):
+    import make_reference_golden as M
+    import test_reference_golden as TR
+    import oracle.vgg
+    from oracle.styler import Oracle3P
+    cfg, params = M.case_inputs(name)
+    out = Oracle3P(cfg, oracle.vgg.synthetic_weights()).run(params, style_targets=TR._style_targets(cfg),
+                                                          view_mode='sequential')
+    TR._check(out, dict(np.load(os.path.join(GOLD, 'ref_%s.npz' % name))), M.CASES[name][0], ltol=2e-5, ftol=1e-4)
