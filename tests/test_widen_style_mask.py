@@ -168,3 +168,28 @@ def test_oracle_matches_reference_batch_run_3d(name):
     out = Oracle3P(cfg, oracle.vgg.synthetic_weights()).run(params, style_targets=TR._style_targets(cfg),
                                                           view_mode='sequential')
     TR._check(out, dict(np.load(os.path.join(GOLD, 'ref_%s.npz' % name))), M.CASES[name][0], ltol=2e-5, ftol=1e-4)
+
+
+def test_batch_run_3d_octaves_matches_oracle(dev):
+    """batches over two octaves: intermediate octave renders with the batch's joint normalisation (interp > 1 cannot be
+    combined with batch_size > 1 in the reference: one needs an odd, the other an even frame count)"""
+    from helpers import smoke_cfg
+    from lnst import synth
+    from lnst.styler_3p import Styler
+    from oracle.styler import Oracle3P
+    import oracle.vgg
+    kw = dict(res=12, iter=2, rotate=False, num_frames=4, batch_size=2, frames_per_opt=4, window_sigma=0.7,
+              octave_n=2, octave_scale=1.5, w_style=0, w_content=1.0, content_layer='conv1_2', content_channel=3,
+              conv_math='fp32')
+    p, r = synth.smoke_particles(500, 2, num_frames=4)
+    new = Styler(smoke_cfg(**kw), weights=synth.vgg_weights(), device=dev)
+    out = new.run({'p': p, 'r': r})
+    ref = Oracle3P(smoke_cfg(**kw), oracle.vgg.synthetic_weights()).run({'p': p, 'r': r})
+    np.testing.assert_allclose(out['l'][0], ref['l'][0], rtol=3e-4)
+    np.testing.assert_allclose(out['l'][1], ref['l'][1], rtol=3e-4)
+    rd = np.asarray(ref['d'])
+    rd = rd.reshape(out['d'].shape)
+    assert np.abs(out['d'] - rd).max() <= 3e-4 * np.abs(rd).max()
+    assert out['d_intm'][0].shape == ref['d_intm'][0].shape
+    assert np.abs(out['d_intm'][0].astype(int) - ref['d_intm'][0].astype(int)).max() <= 1
+    assert np.abs(out['r'].astype(int) - ref['r'].astype(int)).max() <= 1
