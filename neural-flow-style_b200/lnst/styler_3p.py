@@ -92,8 +92,6 @@ class Styler(StylerBase):
         if 'd' in self.target_field and self.num_kernels > 4:
             raise NotImplementedError('num_kernels > 4')
         if self.style_mask:                                        # styler_base.py:165-169 with d_gray = the render
-            if self.style_mask_on_ref:
-                raise NotImplementedError('style_mask_on_ref (styler_base.py:171-173) is not built')
             if self.conv_math != 'fp32' and 'vgg' in self.model_path:
                 raise NotImplementedError("style_mask needs conv_math='fp32' (the masked Gram runs on the fp32 path)")
             if 'vgg' not in self.model_path:
@@ -378,8 +376,12 @@ class Styler(StylerBase):
         elif self.style_mask and self.w_style and style_grams is not None:
             # mask per style layer = TF-legacy bicubic resize of the render to the feature size; its cotangent comes
             # back through the same resize and joins the render's gradient
-            masks, mg = self.style_masks_for(st['gray0'], (st['x'].shape[1], st['x'].shape[2])), {}
-            g_x = self.image_loss_and_grad(st['x'], st['d_img'], style_grams, loss, style_masks=masks, mask_grads=mg)
+            masks, mg, side = self.style_masks_for(st['gray0'], (st['x'].shape[1], st['x'].shape[2])), {}, None
+            if self.style_mask_on_ref:                             # :171-173: the target is masked by the same render
+                by_layer, side = self.masked_style_grams(masks, per_image=True)
+                style_grams = [by_layer[l] for l in self.style_layer]
+            g_x = self.image_loss_and_grad(st['x'], st['d_img'], style_grams, loss, style_masks=masks, mask_grads=mg,
+                                           style_side=side)
             H, W = st['hw']
             for l, dm in mg.items():
                 gm = ops.resize_bicubic_bwd(dm.reshape(nv, dm.shape[1], dm.shape[2], 1), H, W).reshape(nv, H, W)

@@ -154,18 +154,23 @@ class StylerBase(object):
             h, w = h // 2, w // 2
         return h * w
 
-    def masked_style_grams(self, masks):
+    def masked_style_grams(self, masks, per_image=False):
         """Style Gram targets under ``style_mask_on_ref`` (styler_base.py:171-173): (Fs m)^T (Fs m) / (2 area C) with the
-        render's own mask and area; ``masks`` as returned by ``style_masks_for`` (one image)."""
-        grams = []
+        render's own mask and area; ``masks`` as returned by ``style_masks_for``.  One image: a list of Gram matrices
+        (per style layer).  ``per_image``: ({layer: [Gram per image]}, {layer: [handle per image]}) -- the 3-D styler,
+        where every view has its own mask and the mask carries a gradient."""
+        grams, by_layer, handles = [], {}, {}
         for l in self.style_layer:
             fs, (m, area) = self._style_acts[l], masks[l]
             if tuple(fs.shape[1:3]) != tuple(m.shape[1:3]):
                 raise ValueError('style_mask_on_ref: style feature %s and render feature %s differ in size (the reference '
                                  'multiplies them elementwise)' % (tuple(fs.shape[1:3]), tuple(m.shape[1:3])))
-            handle = self.net.gram({l: fs}, l, None, 0.0, None, mask=(m[:1], area[:1]))
-            grams.append(self.net.gram_values(handle)[0].contiguous())
-        return grams
+            hs = [self.net.gram({l: fs}, l, None, 0.0, None, mask=(m[v:v + 1], area[v:v + 1]))
+                  for v in range(m.shape[0] if per_image else 1)]
+            by_layer[l] = [self.net.gram_values(h)[0].contiguous() for h in hs]
+            handles[l] = hs
+            grams.append(by_layer[l][0])
+        return (by_layer, handles) if per_image else grams
 
     def _content_feature(self, content_target, content_shp):
         """Feature of the content target at ``content_layer`` (styler_base.py:233-247): fp32 [h,w,C] on the
@@ -192,7 +197,7 @@ class StylerBase(object):
         return out
 
     def image_loss_and_grad(self, x, d_img, style_grams, loss, style_masks=None, gray=None, mask_grads=None, group=False,
-                            share=None):
+                            share=None, style_side=None):
         """x [n,H,W,3] net input (one image per view), d_img the same before mean subtraction.
         Adds each image's total feature/TV loss into ``loss[v]`` and returns d loss_v / d x_v
         stacked [n,H,W,3] (styler_base.py:127-213).
@@ -233,7 +238,7 @@ class StylerBase(object):
                 for li, l in enumerate(self.style_layer):
                     if l != name:
                         continue
-                    ch = style_grams[li].shape[0]
+                    ch = (style_grams[li][0] if isinstance(style_grams[li], (list, tuple)) else style_grams[li]).shape[0]
                     P = self.net.feature_pixels(acts, name) if hasattr(self.net, 'feature_pixels') else \
                         self._feature_pixels(hw[0], hw[1], name)
                     coef = self.w_style * self.w_style_layer[li] * 4.0 / (2.0 * P * ch)
@@ -252,8 +257,9 @@ class StylerBase(object):
         if g_x is None:
             g_x = torch.zeros_like(x if gray is None else gray)
         if mask_grads is not None and style_on and style_masks:
-            for l in self.style_layer:
-                mask_grads[l] = self.net.gram_mask_grad(acts, l, handles[l])
+            for l in self.style_layer:                             # style_side: {layer: handles} under style_mask_on_ref
+                side = (self._style_acts[l], style_side[l]) if style_side is not None else None
+                mask_grads[l] = self.net.gram_mask_grad(acts, l, handles[l], style_side=side)
         if self.w_content and self.net2 is not None:               # multi-net loss: content term on the second network
             net2, cl = self.net2, self.content_layer
             relu2 = 1 if (cl.startswith('conv') and not hasattr(net2, 'relu_masked')) else 0

@@ -200,7 +200,8 @@ class LossNet:
             if mask is not None:
                 Fv = ops.mul_bcast(f[v], mask[0][v]).reshape(P, ch)
                 den = 2.0 * float(mask[1][v]) * ch
-            ops.gram_diff(Fv, den, Gs, weight, G, loss[v:v + 1] if loss is not None else None)
+            Gs_v = Gs[v] if isinstance(Gs, (list, tuple)) else Gs     # per-image target (style_mask_on_ref)
+            ops.gram_diff(Fv, den, Gs_v, weight, G, loss[v:v + 1] if loss is not None else None)
             out['G'].append(G)
             out['den'].append(den)
             out['Fm'].append(Fv)
@@ -231,18 +232,31 @@ class LossNet:
                 ops.masked_accumulate(tmp.reshape(f[v].shape), handle['mask'][0][v], f[v], relu_mask, g[v], beta)
         return g
 
-    def gram_mask_grad(self, acts, name, handle):
+    def gram_mask_grad(self, acts, name, handle, style_side=None):
         """d loss / d mask [n,h,w] of a masked ``gram`` handle, after ``gram_grad`` ran on it (the 3-D style mask is
         the render, styler_base.py:165-169): per pixel <d loss/d(F m), F>, plus the pixel-independent term through
-        den = 2 area C: -4 w C sum(D o (D + Gs)) / den with D = G/den - Gs."""
+        den = 2 area C: -4 w C sum(D o (D + Gs)) / den with D = G/den - Gs.
+
+        ``style_side`` = (style feature [1,h,w,C], per-image handles of its masked Gram): ``style_mask_on_ref`` -- the
+        target Gs = (Fs m)^T (Fs m)/den depends on the mask too: minus <4 w/den (Fs m) D, Fs> per pixel, and the two
+        denominator terms combine to -4 w C sum(D o D) / den."""
         f = acts[name]
         n, P, ch = f.shape[0], f.shape[1] * f.shape[2], f.shape[3]
         dm = torch.empty(n, f.shape[1], f.shape[2], dtype=torch.float32, device=self.device)
         for v in range(n):
             D = handle['G'][v]
-            s = (D * (D + handle['Gs'])).sum().reshape(1) if handle['Gs'] is not None else (D * D).sum().reshape(1)
+            Gs = handle['Gs'][v] if isinstance(handle['Gs'], (list, tuple)) else handle['Gs']
+            if style_side is not None:
+                s = (D * D).sum().reshape(1)
+            else:
+                s = (D * (D + Gs)).sum().reshape(1) if Gs is not None else (D * D).sum().reshape(1)
             ops.rowdot(handle['tmp'][v], f[v].reshape(P, ch), dm[v].reshape(P), scalar=s,
                        scale=-4.0 * handle['weight'] * ch / handle['den'][v])
+            if style_side is not None:
+                fs, hs = style_side
+                tmp_s = torch.empty(P, ch, dtype=torch.float32, device=self.device)
+                ops.gram_bwd(hs[v]['Fm'][0], D, -4.0 * handle['weight'] / handle['den'][v], 0.0, 0, tmp_s)
+                ops.rowdot(tmp_s, fs[0].reshape(P, ch), dm[v].reshape(P), accumulate=True)
         return dm
 
     def content(self, acts, name, channel, weight, loss, g, relu_mask, target=None, amp=1.0):

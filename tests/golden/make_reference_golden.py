@@ -144,6 +144,9 @@ CASES = {
                                           content_channel=5, style_layer=['conv1_2'], w_style_layer=[1.0]), 600),
     'position_batch_pressure': ('3p', 'liquid', dict(res=12, iter=3, num_frames=2, batch_size=2, frames_per_opt=2,
                                                      w_pressure=0.5, style_layer=['conv1_2'], w_style_layer=[1.0]), 600),
+    'density_style_mask_on_ref': ('3d', 'smoke', dict(res=12, iter=3, rotate=True, n_views=3, style_mask=True,
+                                                      style_mask_on_ref=True, style_layer=['conv1_2', 'conv2_1'],
+                                                      w_style_layer=[0.5, 0.5]), 800),
     'colour_2d': ('2c', 'dam', dict(iter=4, w_tv=0.01, style_layer=['conv1_1', 'conv2_1'], w_style_layer=[0.5, 0.5]), 0),
     'colour_2d_mask': ('2c', 'dam', dict(iter=3, style_mask=True, style_layer=['conv1_1', 'conv2_1'],
                                          w_style_layer=[0.5, 0.5]), 0),

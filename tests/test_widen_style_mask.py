@@ -193,3 +193,18 @@ def test_batch_run_3d_octaves_matches_oracle(dev):
     assert out['d_intm'][0].shape == ref['d_intm'][0].shape
     assert np.abs(out['d_intm'][0].astype(int) - ref['d_intm'][0].astype(int)).max() <= 1
     assert np.abs(out['r'].astype(int) - ref['r'].astype(int)).max() <= 1
+
+
+def test_engine_matches_reference_style_mask_on_ref_run(dev):
+    """styler_base.py:171-173 in 3-D: the style feature is masked by the render as well, so the target Gram moves with
+    the optimised density and the mask's gradient has a style-side term."""
+    import make_reference_golden as M
+    import test_reference_golden as TR
+    from lnst import synth
+    from lnst.styler_3p import Styler
+    name = 'density_style_mask_on_ref'
+    cfg, params = M.case_inputs(name)
+    cfg.conv_math, cfg.view_mode = 'fp32', 'sequential'
+    st = Styler(cfg, weights=synth.vgg_weights(), device=dev)
+    st.style_img = TR._style_targets(cfg)[0]
+    TR._check(st.run(params), dict(np.load(os.path.join(GOLD, 'ref_%s.npz' % name))), '3d')
