@@ -351,6 +351,11 @@ int lnst_maxpool_fwd(const float* x, float* y, int32_t n, int32_t H, int32_t W, 
 int lnst_maxpool_bwd(const float* g_y, const float* x, float* g_x, int32_t n, int32_t H, int32_t W, int32_t C,
                      int32_t k, int32_t stride, int32_t pad_top, int32_t pad_left, int32_t OH, int32_t OW,
                      int32_t accumulate, void* stream);
+/* tf.nn.avg_pool k x k (SAME padding cells are not counted) and AvgPoolGrad -- the inception head's avgpool0. */
+int lnst_avgpool_fwd(const float* x, float* y, int32_t n, int32_t H, int32_t W, int32_t C, int32_t k, int32_t stride,
+                     int32_t pad_top, int32_t pad_left, int32_t OH, int32_t OW, void* stream);
+int lnst_avgpool_bwd(const float* g_y, float* g_x, int32_t n, int32_t H, int32_t W, int32_t C, int32_t k, int32_t stride,
+                     int32_t pad_top, int32_t pad_left, int32_t OH, int32_t OW, int32_t accumulate, void* stream);
 /* tf.nn.lrn: y_c = x_c (bias + alpha sum_{|j-c|<=depth_radius} x_j^2)^-beta, and LRNGrad. */
 int lnst_lrn_fwd(const float* x, float* y, int64_t pixels, int32_t C, int32_t depth_radius, float bias, float alpha,
                  float beta, void* stream);

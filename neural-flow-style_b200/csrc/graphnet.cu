@@ -155,6 +155,62 @@ __global__ void maxpool_bwd_k(const float* __restrict__ gy, const float* __restr
   if (arg >= 0 && g != 0.f) atomicAdd(gx + arg, g);
 }
 
+// tf.nn.avg_pool: mean over the window's cells that lie inside the image (SAME padding does not count)
+__global__ void avgpool_fwd_k(const float* __restrict__ x, float* __restrict__ y, PoolGeom p) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = (int64_t)p.n * p.OH * p.OW * p.C;
+  if (t >= total) return;
+  const int c = (int)(t % p.C);
+  int64_t r = t / p.C;
+  const int ox = (int)(r % p.OW); r /= p.OW;
+  const int oy = (int)(r % p.OH);
+  const int img = (int)(r / p.OH);
+  float acc = 0.f;
+  int cnt = 0;
+  for (int ky = 0; ky < p.k; ++ky) {
+    const int yy = oy * p.stride + ky - p.pt;
+    if (yy < 0 || yy >= p.H) continue;
+    for (int kx = 0; kx < p.k; ++kx) {
+      const int xx = ox * p.stride + kx - p.pl;
+      if (xx < 0 || xx >= p.W) continue;
+      acc += x[(((int64_t)img * p.H + yy) * p.W + xx) * p.C + c];
+      ++cnt;
+    }
+  }
+  y[t] = acc / (float)cnt;
+}
+
+// AvgPoolGrad in gather form: an input cell collects g_y / count from every window that contains it
+__global__ void avgpool_bwd_k(const float* __restrict__ gy, float* __restrict__ gx, PoolGeom p, int accumulate) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = (int64_t)p.n * p.H * p.W * p.C;
+  if (t >= total) return;
+  const int c = (int)(t % p.C);
+  int64_t r = t / p.C;
+  const int ix = (int)(r % p.W); r /= p.W;
+  const int iy = (int)(r % p.H);
+  const int img = (int)(r / p.H);
+  float acc = 0.f;
+  for (int ky = 0; ky < p.k; ++ky) {
+    const int ty = iy + p.pt - ky;
+    if (ty < 0 || ty % p.stride) continue;
+    const int oy = ty / p.stride;
+    if (oy >= p.OH) continue;
+    const int y0 = oy * p.stride - p.pt;
+    const int ny = min(y0 + p.k, p.H) - max(y0, 0);
+    for (int kx = 0; kx < p.k; ++kx) {
+      const int tx = ix + p.pl - kx;
+      if (tx < 0 || tx % p.stride) continue;
+      const int ox = tx / p.stride;
+      if (ox >= p.OW) continue;
+      const int x0 = ox * p.stride - p.pl;
+      const int nx = min(x0 + p.k, p.W) - max(x0, 0);
+      acc += gy[(((int64_t)img * p.OH + oy) * p.OW + ox) * p.C + c] / (float)(ny * nx);
+    }
+  }
+  gx[t] = accumulate ? gx[t] + acc : acc;
+}
+
 // tf.nn.local_response_normalization: y_c = x_c * (bias + alpha * sum_{|j-c|<=r} x_j^2)^-beta  (alpha is NOT divided
 // by the window size, unlike Caffe / torch)
 __device__ __forceinline__ float lrn_norm(const float* __restrict__ row, int C, int c, int radius, float bias,
@@ -282,6 +338,27 @@ extern "C" int lnst_maxpool_bwd(const float* g_y, const float* x, float* g_x, in
   if (!accumulate) cudaMemsetAsync(g_x, 0, sizeof(float) * (int64_t)n * H * W * C, lnst_stream(stream));
   const int64_t total = (int64_t)n * OH * OW * C;
   LNST_LAUNCH(maxpool_bwd_k, dim3(lnst_blocks(total, 256)), dim3(256), 0, lnst_stream(stream), g_y, x, g_x, p);
+  return lnst_status();
+}
+
+extern "C" int lnst_avgpool_fwd(const float* x, float* y, int32_t n, int32_t H, int32_t W, int32_t C, int32_t k,
+                                int32_t stride, int32_t pad_top, int32_t pad_left, int32_t OH, int32_t OW,
+                                void* stream) {
+  PoolGeom p{n, H, W, C, k, stride, pad_top, pad_left, OH, OW};
+  if (!x || !y || !pool_geom_ok(p)) return LNST_EARG;
+  const int64_t total = (int64_t)n * OH * OW * C;
+  LNST_LAUNCH(avgpool_fwd_k, dim3(lnst_blocks(total, 256)), dim3(256), 0, lnst_stream(stream), x, y, p);
+  return lnst_status();
+}
+
+extern "C" int lnst_avgpool_bwd(const float* g_y, float* g_x, int32_t n, int32_t H, int32_t W, int32_t C, int32_t k,
+                                int32_t stride, int32_t pad_top, int32_t pad_left, int32_t OH, int32_t OW,
+                                int32_t accumulate, void* stream) {
+  PoolGeom p{n, H, W, C, k, stride, pad_top, pad_left, OH, OW};
+  if (!g_y || !g_x || !pool_geom_ok(p)) return LNST_EARG;
+  const int64_t total = (int64_t)n * H * W * C;
+  LNST_LAUNCH(avgpool_bwd_k, dim3(lnst_blocks(total, 256)), dim3(256), 0, lnst_stream(stream), g_y, g_x, p,
+              (int)accumulate);
   return lnst_status();
 }
 

@@ -94,6 +94,8 @@ SIGNATURES = {
     'lnst_relu_bwd': [vp, vp, vp, i64, i32, vp],
     'lnst_maxpool_fwd': [vp, vp] + [i32] * 10 + [vp],
     'lnst_maxpool_bwd': [vp, vp, vp] + [i32] * 11 + [vp],
+    'lnst_avgpool_fwd': [vp, vp] + [i32] * 10 + [vp],
+    'lnst_avgpool_bwd': [vp, vp] + [i32] * 11 + [vp],
     'lnst_lrn_fwd': [vp, vp, i64, i32, i32, f32, f32, f32, vp],
     'lnst_lrn_bwd': [vp, vp, vp, i64, i32, i32, f32, f32, f32, i32, vp],
     'lnst_copy_channels': [vp, i32, vp, i32, i32, i64, i32, vp],

@@ -10,6 +10,10 @@ entry point of ``csrc/graphnet.cu`` (fp32 NHWC):
     MaxPool                                   lnst_maxpool_fwd / lnst_maxpool_bwd
     LRN                                       lnst_lrn_fwd / lnst_lrn_bwd
     Concat / ConcatV2 (channel axis)          lnst_copy_channels
+    AvgPool                                   lnst_avgpool_fwd / lnst_avgpool_bwd     (the head's avgpool0)
+    Reshape to [-1, C], MatMul                a view / lnst_conv2d_f32 as a 1x1 convolution (softmax2_pre_activation:
+                                              the class logits the reference's top_k content target reads,
+                                              styler_base.py:240-246); 2-D tensors are carried as [n, rows, 1, C]
     Identity, Placeholder, Const              --
 
 Fusions decided per call from the requested layers (``_fusion``): Conv2D + BiasAdd always; + Relu when the pre-ReLU
@@ -29,7 +33,8 @@ import torch
 from . import graphdef, ops
 
 f32 = torch.float32
-_SUPPORTED = ('Placeholder', 'Const', 'Conv2D', 'BiasAdd', 'Relu', 'MaxPool', 'LRN', 'Concat', 'ConcatV2', 'Identity')
+_SUPPORTED = ('Placeholder', 'Const', 'Conv2D', 'BiasAdd', 'Relu', 'MaxPool', 'AvgPool', 'LRN', 'Concat', 'ConcatV2',
+              'Identity', 'Reshape', 'MatMul')
 
 
 def _clean(name):
@@ -119,7 +124,7 @@ class GraphNet(object):
             return ins[1:]                                     # concat_dim first
         if node.op == 'ConcatV2':
             return ins[:-1]                                    # axis last
-        if node.op in ('Conv2D', 'BiasAdd'):
+        if node.op in ('Conv2D', 'BiasAdd', 'Reshape', 'MatMul'):
             return ins[:1]
         return ins
 
@@ -219,6 +224,20 @@ class GraphNet(object):
             elif node.op == 'LRN':
                 r, bias, alpha, beta = self._lrn_attrs(node)
                 acts[name] = ops.lrn_fwd(acts[ins[0]], r, bias, alpha, beta)
+            elif node.op == 'AvgPool':
+                k, stride, padding = self._pool_attrs(node)
+                acts[name] = ops.avgpool_fwd(acts[ins[0]], k, stride, padding)
+            elif node.op == 'Reshape':                         # [n,h,w,C] -> [-1, C], carried as [n, h*w, 1, C]
+                src = acts[ins[0]]
+                shp = [int(v) for v in np.asarray(self.const[_clean(node.inputs[1])]).reshape(-1)]
+                if len(shp) != 2 or shp[0] != -1 or shp[1] != src.shape[-1]:
+                    raise NotImplementedError('%s: only Reshape to [-1, channels] is built (got %s)' % (name, shp))
+                acts[name] = src.reshape(src.shape[0], -1, 1, src.shape[-1])
+            elif node.op == 'MatMul':                          # rows x [K, N]: a 1x1 convolution
+                if node.attr.get('transpose_a') or node.attr.get('transpose_b'):
+                    raise NotImplementedError('%s: transposed MatMul' % name)
+                w = self._w(_clean(node.inputs[1]))
+                acts[name] = ops.conv2d_f32(acts[ins[0]], w.reshape(1, 1, w.shape[0], w.shape[1]), None, 1, 'SAME')
             elif node.op in ('Concat', 'ConcatV2'):
                 self._concat_axis(node)
                 if name in width:
@@ -309,6 +328,17 @@ class GraphNet(object):
                 r, bias, alpha, beta = self._lrn_attrs(node)
                 gx, a = acc(ins[0], acts[ins[0]])
                 ops.lrn_bwd(g, acts[ins[0]], r, bias, alpha, beta, gx, a)
+            elif node.op == 'AvgPool':
+                k, stride, padding = self._pool_attrs(node)
+                gx, a = acc(ins[0], acts[ins[0]])
+                ops.avgpool_bwd(g, acts[ins[0]].shape, k, stride, padding, gx, a)
+            elif node.op == 'Reshape':
+                gx, a = acc(ins[0], acts[ins[0]])
+                ops.copy_channels(g, 0, gx, 0, g.shape[-1], accumulate=a)      # same memory order, other shape
+            elif node.op == 'MatMul':
+                w = self._w(_clean(node.inputs[1]))
+                gx, a = acc(ins[0], acts[ins[0]])
+                ops.conv2d_bwd_data_f32(g, w.reshape(1, 1, w.shape[0], w.shape[1]), acts[ins[0]].shape, 1, 'SAME', gx, a)
             elif node.op in ('Concat', 'ConcatV2'):
                 if all(i in slot and slot[i][0] == name for i in ins):
                     for i in ins:                              # the branches read their slice of g in place

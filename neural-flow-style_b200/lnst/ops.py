@@ -462,6 +462,22 @@ def maxpool_bwd(g_y, x, k, stride, padding, g_x, accumulate):
     return g_x
 
 
+def avgpool_fwd(x, k, stride, padding='VALID'):
+    n, H, W, ch = x.shape
+    OH, OW, pt, pl = conv_out(x.shape, (k, k), stride, padding)
+    y = torch.empty(n, OH, OW, ch, dtype=f32, device=x.device)
+    _lib.get().call('lnst_avgpool_fwd', ptr(x), ptr(y), n, H, W, ch, k, stride, pt, pl, OH, OW, _s(x))
+    return y
+
+
+def avgpool_bwd(g_y, x_shape, k, stride, padding, g_x, accumulate):
+    n, H, W, ch = x_shape
+    OH, OW, pt, pl = conv_out(x_shape, (k, k), stride, padding)
+    _lib.get().call('lnst_avgpool_bwd', ptr(g_y), ptr(g_x), n, H, W, ch, k, stride, pt, pl, OH, OW,
+                    int(bool(accumulate)), _s(g_y))
+    return g_x
+
+
 def lrn_fwd(x, depth_radius, bias, alpha, beta):
     y = torch.empty_like(x)
     _lib.get().call('lnst_lrn_fwd', ptr(x), ptr(y), x.numel() // x.shape[-1], x.shape[-1], int(depth_radius), float(bias),

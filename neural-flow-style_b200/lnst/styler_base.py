@@ -178,7 +178,14 @@ class StylerBase(object):
         x = self._target_tensor(content_target, content_shp)
         net = self.net2 if self.net2 is not None else self.net
         acts = net.forward(x, [self.content_layer])
-        return net.features_f32(acts, self.content_layer)[0].contiguous()
+        feat = net.features_f32(acts, self.content_layer)[0].contiguous()
+        if self.top_k > 0:                                         # :240-246: keep the k strongest logits of every row
+            assert 'softmax2_pre_activation' in self.content_layer
+            rows = feat.reshape(-1, feat.shape[-1])
+            keep = torch.zeros_like(rows, dtype=torch.bool)
+            keep.scatter_(1, torch.topk(rows.abs(), int(self.top_k), dim=1).indices, True)
+            feat = torch.where(keep, rows, torch.zeros_like(rows)).reshape(feat.shape).contiguous()
+        return feat
 
     # ---- feature-space losses + their gradient w.r.t. the net input ---------------------------------
     def style_masks_for(self, d_gray, net_hw):

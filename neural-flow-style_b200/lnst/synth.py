@@ -118,13 +118,18 @@ _INCEPTION_MODULES = [       # name, 1x1, 3x3 bottleneck, 3x3, 5x5 bottleneck, 5
 ]
 
 
-def inception5h_nodes(seed=5, width_div=1, upto=None):
+def inception5h_nodes(seed=5, width_div=1, upto=None, head_pool=0, n_classes=1008):
     """The inception5h topology with the file's node names (``conv2d0_pre_relu/conv`` -> ``conv2d0_pre_relu`` ->
     ``conv2d0``, ``mixed3a_3x3_bottleneck_pre_relu``, ``mixed3a`` ...; run.bat:15-20 and test_smokegun.py:141 name
     such tensors) as a list of ``lnst.graphdef.Node`` with seeded He-normal weights.  ``width_div`` divides every
     channel count (tests); ``upto`` stops after that module.  LRN attributes are those of the Caffe GoogLeNet
     conversion (radius 2, bias 1, alpha 2e-5, beta .75) -- the real file's own attributes are used when it is
-    loaded.  Serialise with ``lnst.graphdef.serialize`` to get a ``.pb``."""
+    loaded.  Serialise with ``lnst.graphdef.serialize`` to get a ``.pb``.
+
+    ``head_pool`` > 0 appends the classifier head after the last module built: ``avgpool0`` (AvgPool head_pool x head_pool,
+    stride 1, VALID; 7 in the real file, for 224 x 224 inputs) -> ``avgpool0/reshape`` [-1, C] ->
+    ``softmax2_pre_activation/matmul`` -> ``softmax2_pre_activation`` (BiasAdd): the class logits the reference's
+    content-target mode with ``top_k`` reads (styler_base.py:240-246)."""
     from .graphdef import Node
     rng = np.random.RandomState(seed)
     nodes = [Node('input', 'Placeholder', [], {})]
@@ -174,4 +179,15 @@ def inception5h_nodes(seed=5, width_div=1, upto=None):
         cur, c = name, ca + cb + cd + ce
         if upto == name:
             break
+    if head_pool:
+        nc = max(int(n_classes) // width_div, 4)
+        nodes.append(Node('avgpool0', 'AvgPool', [cur], {'ksize': [1, head_pool, head_pool, 1], 'strides': [1, 1, 1, 1],
+                                                          'padding': b'VALID'}))
+        nodes.append(Node('avgpool0/reshape/shape', 'Const', [], {'value': np.asarray([-1, c], np.int32)}))
+        nodes.append(Node('avgpool0/reshape', 'Reshape', ['avgpool0', 'avgpool0/reshape/shape'], {}))
+        nodes.append(Node('softmax2_w', 'Const', [], {'value': (rng.randn(c, nc) * np.sqrt(1.0 / c)).astype(np.float32)}))
+        nodes.append(Node('softmax2_b', 'Const', [], {'value': (0.05 * rng.randn(nc)).astype(np.float32)}))
+        nodes.append(Node('softmax2_pre_activation/matmul', 'MatMul', ['avgpool0/reshape', 'softmax2_w'],
+                          {'transpose_a': False, 'transpose_b': False}))
+        nodes.append(Node('softmax2_pre_activation', 'BiasAdd', ['softmax2_pre_activation/matmul', 'softmax2_b'], {}))
     return nodes

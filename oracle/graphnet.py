@@ -78,6 +78,19 @@ def forward(d_img, nodes, wanted, pool1=False):
             y = torch.cat([get(p) for p in parts], dim=axis)
         elif n.op == 'Identity':
             y = get(n.inputs[0])
+        elif n.op == 'AvgPool':                                # SAME padding cells are not counted
+            k, s = list(a['ksize'])[1], list(a['strides'])[1]
+            x = get(n.inputs[0]).permute(0, 3, 1, 2)
+            if (a.get('padding') or b'VALID') == b'SAME':
+                ones = _same_pad(torch.ones(1, 1, x.shape[2], x.shape[3], dtype=x.dtype), k, s)
+                y = F.avg_pool2d(_same_pad(x, k, s), k, s, divisor_override=1) / F.avg_pool2d(ones, k, s, divisor_override=1)
+            else:
+                y = F.avg_pool2d(x, k, s)
+            y = y.permute(0, 2, 3, 1)
+        elif n.op == 'Reshape':
+            y = get(n.inputs[0]).reshape([int(v) for v in np.asarray(const[_clean(n.inputs[1])]).reshape(-1)])
+        elif n.op == 'MatMul':
+            y = get(n.inputs[0]) @ get(n.inputs[1])
         else:
             raise NotImplementedError(n.op)
         vals[name] = y

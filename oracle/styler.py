@@ -124,7 +124,14 @@ class _Base:
         c = self.cfg
         img = torch.as_tensor(np.asarray(content_img)[..., :3], dtype=self.dtype)
         ep = self._net(torch.stack([img] * c.batch_size, 0))
-        return self._layer(ep, c.content_layer).detach()
+        feat = self._layer(ep, c.content_layer).detach()
+        if getattr(c, 'top_k', 0) > 0:                         # styler_base.py:240-246
+            assert 'softmax2_pre_activation' in c.content_layer
+            feat = feat.clone()
+            idx = torch.topk(feat.abs(), c.top_k, dim=1).indices
+            keep = torch.zeros_like(feat, dtype=torch.bool).scatter_(1, idx, True)
+            feat[~keep] = 0
+        return feat
 
     # styler_base.py:127-231
     def total_loss(self, g, style_feats=None, content_feat=None):

@@ -693,6 +693,13 @@ def import_graph_def(graph_def, input_map=None, return_elements=None, name=None)
             t = concat([ref(i) for i in ins[:-1]], int(_tensor_value(ref(ins[-1]))))
         elif nd.op == 'Identity':
             t = identity(ref(ins[0]))
+        elif nd.op == 'AvgPool':
+            t = nn.avg_pool(ref(ins[0]), list(a['ksize'].list.i), list(a['strides'].list.i), a['padding'].s.decode())
+        elif nd.op == 'Reshape':
+            t = reshape(ref(ins[0]), [int(v) for v in np.asarray(_tensor_value_np(ref(ins[1]))).reshape(-1)])
+        elif nd.op == 'MatMul':
+            t = matmul(ref(ins[0]), ref(ins[1]), transpose_a=a['transpose_a'].b if 'transpose_a' in a else False,
+                       transpose_b=a['transpose_b'].b if 'transpose_b' in a else False)
         else:
             raise NotImplementedError('tfshim.import_graph_def: op %s (%s)' % (nd.op, nd.name))
         local[nd.name] = t
@@ -704,6 +711,10 @@ def import_graph_def(graph_def, input_map=None, return_elements=None, name=None)
 
 def _tensor_value(t):
     return _to_t(_ev(t, {})).item() if isinstance(t, Tensor) else t
+
+
+def _tensor_value_np(t):
+    return _to_t(_ev(t, {})).numpy() if isinstance(t, Tensor) else np.asarray(t)
 
 
 class Graph:

@@ -147,6 +147,11 @@ CASES = {
     'density_style_mask_on_ref': ('3d', 'smoke', dict(res=12, iter=3, rotate=True, n_views=3, style_mask=True,
                                                       style_mask_on_ref=True, style_layer=['conv1_2', 'conv2_1'],
                                                       w_style_layer=[0.5, 0.5]), 800),
+    # content TARGET IMAGE on the inception class logits with top_k (styler_base.py:135-141, 233-247): the head of the
+    # graph (AvgPool -> Reshape -> MatMul -> BiasAdd = softmax2_pre_activation), the k strongest logits of the target kept
+    'density_inception_logits': ('3d', 'smoke', dict(res=20, iter=3, network='tensorflow_inception_graph.pb', rotate=False,
+                                                     w_style=0, w_content=1.0, w_content_amp=3.0, content_image=True, top_k=3,
+                                                     content_layer='softmax2_pre_activation'), 900),
     'colour_2d': ('2c', 'dam', dict(iter=4, w_tv=0.01, style_layer=['conv1_1', 'conv2_1'], w_style_layer=[0.5, 0.5]), 0),
     'colour_2d_mask': ('2c', 'dam', dict(iter=3, style_mask=True, style_layer=['conv1_1', 'conv2_1'],
                                          w_style_layer=[0.5, 0.5]), 0),
@@ -161,10 +166,11 @@ CASES = {
 }
 
 
-def inception_nodes():
-    """The synthetic inception5h graph of the 'density_inception*' cases (shared with the tests)."""
+def inception_nodes(head=False):
+    """The synthetic inception5h graph of the 'density_inception*' cases (shared with the tests); ``head``: with the
+    classifier head (a 2x2 avgpool0: the 20x20 test renders leave a 3x3 mixed3b map)."""
     from lnst import synth
-    return synth.inception5h_nodes(width_div=8, upto='mixed3b')
+    return synth.inception5h_nodes(width_div=8, upto='mixed3b', head_pool=2 if head else 0)
 
 
 def case_inputs(name):
@@ -203,7 +209,7 @@ def run_reference(name):
         cfg.data_dir = tempfile.mkdtemp(prefix='lnst_ref_')
         os.makedirs(os.path.join(cfg.data_dir, cfg.model_dir))
         with open(os.path.join(cfg.data_dir, cfg.model_dir, cfg.network), 'wb') as f:
-            f.write(graphdef.serialize(inception_nodes()))
+            f.write(graphdef.serialize(inception_nodes(head='logits' in name)))
     elif not real_tf:                          # real TF: <data_dir>/<model_dir>/vgg_19.ckpt must hold the seeded weights
         register_weights(cfg, synth.vgg_weights('vgg_16' if '16' in cfg.network else 'vgg_19'))
     if kind == '2c':

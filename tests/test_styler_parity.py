@@ -112,8 +112,8 @@ def test_content_target_image_and_style(dev):
     """Content loss against a target IMAGE's feature (styler_base.py:137-141, 233-247) together with the
     style loss, single view, density mode."""
     res = 12
-    kw = dict(res=res, iter=3, rotate=False, conv_math='fp32', w_content=0.7, w_content_amp=1.5,
-              content_layer='conv2_1', style_layer=['conv1_2'], w_style_layer=[1.0])
+    kw = dict(res=res, iter=3, rotate=False, conv_math='fp32', w_content=0.7, w_content_amp=1.5, top_k=0,
+              content_layer='conv2_1', style_layer=['conv1_2'], w_style_layer=[1.0])   # top_k > 0 is for class logits only
     params = scene(res, 900)
     sty = synth.style_image(res, res)
     con = synth.style_image(res, res, seed=11)

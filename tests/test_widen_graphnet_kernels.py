@@ -147,3 +147,27 @@ def test_relu_and_copy_channels(dev):
     back = torch.ones(3, 4, 5, 4).to(dev)
     ops.copy_channels(cat, 4, back, 0, 4, accumulate=True)       # slice gradient, accumulated
     np.testing.assert_array_equal(back.cpu().numpy(), 1 + x.numpy()[..., 1:5])
+
+
+@pytest.mark.parametrize('H,W,k,stride,padding', [(7, 7, 7, 1, 'VALID'), (10, 15, 7, 1, 'VALID'), (6, 5, 3, 2, 'SAME'),
+                                                   (5, 5, 2, 2, 'VALID'), (4, 7, 3, 1, 'SAME')])
+def test_avgpool_fwd_bwd(dev, H, W, k, stride, padding):
+    rng = np.random.RandomState(H * W)
+    x = torch.tensor(rng.randn(2, H, W, 3).astype(np.float32), requires_grad=True)
+    xp = x.permute(0, 3, 1, 2)
+    if padding == 'SAME':                                        # TF counts only the cells inside the image
+        ones = tf_pad(torch.ones(1, 1, H, W), k, stride)
+        want = F.avg_pool2d(tf_pad(xp, k, stride), k, stride, divisor_override=1) / \
+            F.avg_pool2d(ones, k, stride, divisor_override=1)
+    else:
+        want = F.avg_pool2d(xp, k, stride)
+    want = want.permute(0, 2, 3, 1)
+    got = ops.avgpool_fwd(x.detach().to(dev), k, stride, padding)
+    close(got, want, tol=2e-6, what='avgpool')
+    g = torch.tensor(rng.randn(*want.shape).astype(np.float32))
+    (want * g).sum().backward()
+    gx = torch.full(x.shape, 3.0).to(dev)
+    ops.avgpool_bwd(g.to(dev), x.shape, k, stride, padding, gx, accumulate=False)
+    close(gx, x.grad, tol=3e-6, what='avgpool grad')
+    ops.avgpool_bwd(g.to(dev), x.shape, k, stride, padding, gx, accumulate=True)
+    close(gx, 2 * x.grad, tol=3e-6, what='avgpool grad accumulate')

@@ -213,7 +213,7 @@ def test_styler_reads_the_pb_file(dev, tmp_path):
 
 # ---- the reference's own inception path, run here (tests/golden/make_reference_golden.py: the unmodified
 # styler_base / styler_3p parse the GraphDef file, import it and read layers by tensor name on oracle/tfshim) --------
-REF_CASES = ['density_inception', 'density_inception_pool1']
+REF_CASES = ['density_inception', 'density_inception_pool1', 'density_inception_logits']
 
 
 def _ref_setup(name):
@@ -231,7 +231,8 @@ def _ref_setup(name):
 def test_oracle_matches_reference_inception_run(name):
     from oracle.styler import Oracle3P
     M, TR, cfg, params, want = _ref_setup(name)
-    out = Oracle3P(cfg, M.inception_nodes()).run(params, style_targets=TR._style_targets(cfg), view_mode='sequential')
+    out = Oracle3P(cfg, M.inception_nodes(head='logits' in name)).run(
+        params, style_targets=TR._style_targets(cfg), content_targets=TR._content_targets(cfg), view_mode='sequential')
     TR._check(out, want, '3d', ltol=2e-5, ftol=1e-4)
 
 
@@ -240,9 +241,30 @@ def test_engine_matches_reference_inception_run(name, dev):
     from lnst.styler_3p import Styler
     M, TR, cfg, params, want = _ref_setup(name)
     cfg.view_mode = 'sequential'
-    st = Styler(cfg, weights=M.inception_nodes(), device=dev)
-    tg = TR._style_targets(cfg)
+    st = Styler(cfg, weights=M.inception_nodes(head='logits' in name), device=dev)
+    tg, ct = TR._style_targets(cfg), TR._content_targets(cfg)
     if tg is not None:
         st.style_img = tg[0]
+    if ct is not None:
+        st.content_img = ct[0]
     TR._check(st.run(params), want, '3d')
 
+
+
+def test_graphnet_classifier_head(dev):
+    """avgpool0 -> reshape [-1, C] -> MatMul -> BiasAdd (softmax2_pre_activation): forward and data gradient vs the oracle"""
+    nodes = synth.inception5h_nodes(width_div=8, upto='mixed3b', head_pool=2)
+    img = torch.tensor(np.random.RandomState(4).uniform(0, 255, (2, 36, 30, 3)).astype(np.float32), requires_grad=True)
+    want = OG.forward(img, nodes, ['softmax2_pre_activation'])
+    net = GraphNet(nodes, dev)
+    x = OV.preprocess(img.detach()).contiguous().to(dev)
+    acts = net.forward(x, ['softmax2_pre_activation'])
+    logits = acts['softmax2_pre_activation']                       # [n, rows per image, 1, classes]
+    assert logits.shape[0] == 2 and logits.shape[2] == 1
+    close(logits.reshape(-1, logits.shape[-1]), want['softmax2_pre_activation'], tol=2e-5, what='logits')
+    close(acts['avgpool0'], want['avgpool0'], tol=2e-5, what='avgpool0')
+    cot = torch.tensor(np.random.RandomState(5).randn(*want['softmax2_pre_activation'].shape).astype(np.float32))
+    (want['softmax2_pre_activation'] * cot).sum().backward()
+    g = cot.reshape(logits.shape).to(dev)
+    g_x = net.backward(x, acts, ['softmax2_pre_activation'], lambda n, gg: g.clone(), {'softmax2_pre_activation'})
+    close(g_x, img.grad, tol=5e-5, what='d logits / d input')

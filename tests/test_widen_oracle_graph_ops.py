@@ -92,6 +92,34 @@ def test_graph_ops_match_brute_force(H, W, k, stride):
     assert got['input'] is not None and got['input'].shape == (2, H, W, 3)      # layer 'input' is d_img (styler_base.py:92)
 
 
+def test_head_ops_match_brute_force():
+    """AvgPool (VALID and SAME: padding cells are not counted), Reshape, MatMul"""
+    rng = np.random.RandomState(3)
+    img = rng.uniform(0, 255, (2, 5, 6, 3))
+    w = rng.randn(3, 4).astype(np.float32)
+    nodes = [Node('input', 'Placeholder'),
+             Node('ap', 'AvgPool', ['input'], {'ksize': [1, 2, 2, 1], 'strides': [1, 1, 1, 1], 'padding': b'VALID'}),
+             Node('aps', 'AvgPool', ['input'], {'ksize': [1, 3, 3, 1], 'strides': [1, 2, 2, 1], 'padding': b'SAME'}),
+             Node('shape', 'Const', [], {'value': np.asarray([-1, 3], np.int32)}),
+             Node('flat', 'Reshape', ['ap', 'shape']), Node('w', 'Const', [], {'value': w}),
+             Node('mm', 'MatMul', ['flat', 'w'], {'transpose_a': False, 'transpose_b': False})]
+    got = OG.forward(torch.tensor(img), nodes, ['mm', 'aps'])
+    x = img - np.asarray(torch.tensor(OV.MEAN_RGB, dtype=torch.float64))
+    ap = np.zeros((2, 4, 5, 3))
+    for oy in range(4):
+        for ox in range(5):
+            ap[:, oy, ox] = x[:, oy:oy + 2, ox:ox + 2].mean(axis=(1, 2))
+    np.testing.assert_allclose(got['ap'].numpy(), ap, rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(got['mm'].numpy(), ap.reshape(-1, 3) @ w.astype(np.float64), rtol=1e-9, atol=1e-9)
+    (OH, pt), (OW, pl) = _same(5, 3, 2), _same(6, 3, 2)
+    aps = np.zeros((2, OH, OW, 3))
+    for oy in range(OH):
+        for ox in range(OW):
+            y0, x0 = oy * 2 - pt, ox * 2 - pl
+            aps[:, oy, ox] = x[:, max(y0, 0):min(y0 + 3, 5), max(x0, 0):min(x0 + 3, 6)].mean(axis=(1, 2))
+    np.testing.assert_allclose(got['aps'].numpy(), aps, rtol=1e-9, atol=1e-9)
+
+
 def test_pool1_only_touches_the_first_convolution():
     rng = np.random.RandomState(0)
     img = torch.tensor(rng.uniform(0, 255, (1, 9, 9, 3)))
