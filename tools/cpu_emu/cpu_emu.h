@@ -110,9 +110,14 @@ inline void launch(dim3 grid, dim3 block, size_t smem, const std::function<void(
   blk.body = &body;
   for (auto& f : blk.fibers) if (f.stack.empty()) f.stack.resize(128 * 1024);
   B() = &blk;
-  for (unsigned bz = 0; bz < grid.z; ++bz)
-  for (unsigned by = 0; by < grid.y; ++by)
-  for (unsigned bx = 0; bx < grid.x; ++bx) {
+  // LNST_EMU_ORDER=reverse runs blocks and the fibers of a block in descending order: a kernel whose result depends
+  // on the (unspecified) execution order of threads between barriers, or of blocks, then fails its parity test --
+  // a poor man's racecheck for missing __syncthreads / inter-block assumptions.
+  static const bool rev = [] { const char* e = getenv("LNST_EMU_ORDER"); return e && e[0] == 'r'; }();
+  const unsigned long nblk = (unsigned long)grid.x * grid.y * grid.z;
+  for (unsigned long bl = 0; bl < nblk; ++bl) {
+    const unsigned long bi = rev ? nblk - 1 - bl : bl;
+    const unsigned bx = (unsigned)(bi % grid.x), by = (unsigned)((bi / grid.x) % grid.y), bz = (unsigned)(bi / ((unsigned long)grid.x * grid.y));
     blk.bid = {bx, by, bz};
     blk.arrived.assign(1 + nwarp, 0);
     blk.phase.assign(1 + nwarp, 0);
@@ -132,7 +137,8 @@ inline void launch(dim3 grid, dim3 block, size_t smem, const std::function<void(
     int remaining = nt;
     while (remaining > 0) {
       int progressed = 0;
-      for (int k = 0; k < nt; ++k) {
+      for (int kk = 0; kk < nt; ++kk) {
+        const int k = rev ? nt - 1 - kk : kk;
         if (blk.fibers[k].done) continue;
         blk.cur = k;
         swapcontext(&blk.sched, &blk.fibers[k].ctx);
