@@ -33,6 +33,16 @@ WORKLOADS = {
     'C2': dict(res=128, n=1 << 18, rotate=False, n_views=1,
                desc='smokegun-like 128^3, N=2^18 particles x 2 kernels, 1 view, VGG-19 conv2_1+conv3_1'),
     'tiny': dict(res=32, n=1 << 13, rotate=True, n_views=9, desc='debug 32^3'),
+    # BASELINE.json configs[4] on one GPU's share: multi-net loss -- semantic term on an inception5h GraphDef (seeded
+    # synthetic weights, full channel widths), style term on VGG-19.  Not a default bench line (a parity-test config);
+    # `--workload C5` measures it, tools/wbench.py times its pieces.
+    'C5': dict(res=256, n=1 << 21, rotate=True, n_views=9,
+               content=dict(layer='mixed4d_3x3_bottleneck_pre_relu', channel=139, upto='mixed4d', width_div=1),
+               desc='smokegun-like 256^3, N=2^21 particles x 2 kernels, 9 rotated views, inception5h '
+                    'mixed4d_3x3_bottleneck_pre_relu ch 139 semantic + VGG-19 conv2_1+conv3_1 style (multi-net loss)'),
+    'C5tiny': dict(res=24, n=1 << 12, rotate=True, n_views=3,
+                   content=dict(layer='mixed3b_3x3_bottleneck_pre_relu', channel=5, upto='mixed3b', width_div=8),
+                   desc='debug 24^3 multi-net'),
 }
 ACTIVE_CELLS = 0   # cells of the workload's active box (set by run_engine)
 KERNELS_PER_CALL = {'lnst_splat_wavg_fwd_box': 2, 'lnst_adam_step_dev': 2, 'lnst_image_max': 2, 'lnst_normalize_bwd': 2, 'lnst_gram_diff': 2,
@@ -44,8 +54,20 @@ TENSOR_BOUND = ('lnst_conv3x3_f32', 'lnst_conv3x3_bf16_tc', 'lnst_gram_diff', 'l
 def make_cfg(wl, view_mode, conv_math):
     from helpers import smoke_cfg
     w = WORKLOADS[wl]
+    extra = {}
+    if w.get('content'):
+        extra = dict(content_network='tensorflow_inception_graph.pb', w_content=1.0, content_layer=w['content']['layer'],
+                     content_channel=w['content']['channel'])
     return smoke_cfg(res=w['res'], iter=1, rotate=w['rotate'], n_views=w['n_views'], view_mode=view_mode,
-                     conv_math=conv_math, transmit=0.01, style_layer=['conv2_1', 'conv3_1'], w_style_layer=[0.5, 0.5])
+                     conv_math=conv_math, transmit=0.01, style_layer=['conv2_1', 'conv3_1'], w_style_layer=[0.5, 0.5],
+                     **extra)
+
+
+def content_nodes(wl):
+    """The second (GraphDef) loss network of a multi-net workload, else None."""
+    from lnst import synth
+    c = WORKLOADS[wl].get('content')
+    return synth.inception5h_nodes(width_div=c['width_div'], upto=c['upto']) if c else None
 
 
 def make_scene(wl):
@@ -234,7 +256,7 @@ def run_engine(args):
     wl = args.workload
     cfg = make_cfg(wl, args.view_mode, conv_math)
     p, r, sty = make_scene(wl)
-    styler = Styler(cfg, weights=synth.vgg_weights(), device=dev)
+    styler = Styler(cfg, weights=synth.vgg_weights(), device=dev, content_weights=content_nodes(wl))
     styler.style_img = sty
     res = [WORKLOADS[wl]['res']] * 3
     grams = styler._style_feature(sty, res[1:])
@@ -435,7 +457,7 @@ def cpu_baseline(wl, budget_s=25.0, steps=None, warmup=0):
         steps = w['n_views']                      # one whole iteration, unless the time budget ends it earlier
     cfg = make_cfg(wl, 'sequential', 'fp32')
     p, r, sty = make_scene(wl)
-    o = Oracle3P(cfg, oracle.vgg.synthetic_weights())
+    o = Oracle3P(cfg, oracle.vgg.synthetic_weights(), content_weights=content_nodes(wl))
     res = [w['res']] * 3
     sf = o.style_features(sty)
     pt, rt = torch.tensor(p[0]), torch.tensor(r[0])
