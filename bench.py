@@ -47,7 +47,7 @@ WORKLOADS = {
 ACTIVE_CELLS = 0   # cells of the workload's active box (set by run_engine)
 KERNELS_PER_CALL = {'lnst_splat_wavg_fwd_box': 2, 'lnst_adam_step_dev': 2, 'lnst_image_max': 2, 'lnst_normalize_bwd': 2, 'lnst_gram_diff': 2,
                     'lnst_gram_diff_bf16_tc': 2}
-TENSOR_BOUND = ('lnst_conv3x3_f32', 'lnst_conv3x3_bf16_tc', 'lnst_gram_diff', 'lnst_gram_bwd', 'lnst_gram_diff_bf16_tc',
+TENSOR_BOUND = ('lnst_conv3x3_f32', 'lnst_conv2d_f32', 'lnst_conv2d_bwd_data_f32', 'lnst_conv3x3_bf16_tc', 'lnst_gram_diff', 'lnst_gram_bwd', 'lnst_gram_diff_bf16_tc',
                 'lnst_gram_bwd_bf16_tc')
 
 
@@ -128,6 +128,11 @@ def algorithmic_units(name, a, nk=2):
     if name == 'lnst_gram_bwd_bf16_tc':
         n, H, W, ch = [v(x) for x in a[6:10]]
         return (n * (6 * H * W * ch + 2 * ch * ch), 2 * n * H * W * ch * ch)
+    if name in ('lnst_conv2d_f32', 'lnst_conv2d_bwd_data_f32'):      # GraphDef network (multi-net workloads)
+        o = 4 if name == 'lnst_conv2d_f32' else 5
+        n, H, W, ci, co, kh, kw = [v(x) for x in a[o:o + 7]]
+        OH, OW = v(a[o + 10]), v(a[o + 11])
+        return (4 * (n * H * W * ci + n * OH * OW * co + kh * kw * ci * co), 2 * n * OH * OW * kh * kw * ci * co)
     if name == 'lnst_gram_diff':
         P, ch = v(a[1]), v(a[2])
         return (4 * P * ch + 4 * ch * ch, 2 * P * ch * ch)
