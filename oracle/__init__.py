@@ -14,7 +14,7 @@ extent that is possible without TensorFlow:
     ``styler_base.py``) run by ``tests/golden/make_reference_golden.py`` on top of ``oracle/tfshim`` --
     a stand-in for the absent third-party TensorFlow 1.15 that restates the published semantics of
     each op the path calls.  ``tests/test_reference_golden.py`` holds this oracle to them (loss
-    2e-5, field 1e-4, operators 2e-6 with identical NaN patterns, view matrices bit-equal) on 13
+    2e-5, field 1e-4, operators 2e-6 with identical NaN patterns, view matrices bit-equal) on 23
     loop-level cases (density / position / colour modes, views, octaves, sequences, resize, TV,
     content, style mask) and 20 operator-level vectors;
   * the one known-answer the reference itself holds (the 5x5 bilinear-warp tables in
