@@ -66,6 +66,7 @@ class GraphNet(object):
                     s[1:3] = [1, 1]
                     n.attr['strides'] = s
         self._dev_w = {}
+        self._plan_cache, self._fusion_cache = {}, {}            # per requested-layer set (host-side graph walks)
         # Conv2D whose only consumer is a BiasAdd: run as one kernel (the un-biased tensor is not materialised)
         consumers = {}
         for n in nodes:
@@ -104,6 +105,12 @@ class GraphNet(object):
 
     def _plan(self, wanted):
         """Nodes (file order) on a path from the input to a wanted tensor; Const inputs are not activations."""
+        key = tuple(sorted(_clean(w) for w in wanted))
+        if key not in self._plan_cache:
+            self._plan_cache[key] = self._plan_walk(wanted)
+        return self._plan_cache[key]
+
+    def _plan_walk(self, wanted):
         need, stack = set(), [_clean(w) for w in wanted if 'input' != _clean(w)]
         while stack:
             name = stack.pop()
@@ -153,6 +160,9 @@ class GraphNet(object):
                             and none of them requested: R's convolution writes channels [off, off+ch) of C's buffer,
                             the concat copies disappear, the backward pass reads the cotangent slice in place.
         """
+        key = tuple(sorted(_clean(w) for w in wanted))
+        if key in self._fusion_cache:
+            return self._fusion_cache[key]
         want = {_clean(w) for w in wanted}
         relu_of = {}
         for name, node in self.nodes.items():
@@ -174,6 +184,7 @@ class GraphNet(object):
                 slot[i] = (name, off)
                 off += int(self.const[_clean(conv.inputs[1])].shape[-1])
             width[name] = off
+        self._fusion_cache[key] = (relu_of, slot, width)
         return relu_of, slot, width
 
     def forward(self, x, wanted, gray=None):
