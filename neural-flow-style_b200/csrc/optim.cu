@@ -180,8 +180,9 @@ extern "C" int lnst_abi_version(void) { return LNST_ABI_VERSION; }
 
 extern "C" int lnst_adam_step(float* var, const float* grad, float* m, float* v, int64_t n, float lr_t,
                               float beta1, float beta2, float eps, float gscale, void* stream) {
-  if (!var || !grad || !m || !v || n < 0) return LNST_EARG;
+  if (n < 0) return LNST_EARG;
   if (n == 0) return LNST_OK;
+  if (!var || !grad || !m || !v) return LNST_EARG;
   LNST_LAUNCH(adam_step_k, dim3(lnst_blocks(n, 256)), dim3(256), 0, lnst_stream(stream), var, grad, m, v, n, lr_t,
               beta1, beta2, eps, gscale);
   return lnst_status();
@@ -189,7 +190,7 @@ extern "C" int lnst_adam_step(float* var, const float* grad, float* m, float* v,
 
 extern "C" int lnst_adam_step_dev(float* var, const float* grad, float* m, float* v, int64_t n, float* state,
                                   float lr, float beta1, float beta2, float eps, float gscale, void* stream) {
-  if (!var || !grad || !m || !v || !state || n < 0) return LNST_EARG;
+  if (!state || n < 0 || (n > 0 && (!var || !grad || !m || !v))) return LNST_EARG;   // an empty variable has no storage
   LNST_LAUNCH(adam_tick_k, dim3(1), dim3(32), 0, lnst_stream(stream), state, lr, beta1, beta2);
   if (n > 0)
     LNST_LAUNCH(adam_step_dev_k, dim3(lnst_blocks(n, 256)), dim3(256), 0, lnst_stream(stream), var, grad, m, v, n,
@@ -201,7 +202,7 @@ extern "C" int lnst_adam_iterate_dev(float* g_opt, const float* grad, float* m, 
                                      float lr, float beta1, float beta2, float eps, float gscale, const float* mask,
                                      int32_t width, int32_t mask_stride, float* var_out, float* delta, int32_t apply,
                                      void* stream) {
-  if (!g_opt || !grad || !m || !v || !state || !var_out || !delta || n < 0 || width < 1) return LNST_EARG;
+  if (!state || n < 0 || width < 1 || (n > 0 && (!g_opt || !grad || !m || !v || !var_out || !delta))) return LNST_EARG;
   LNST_LAUNCH(adam_tick_k, dim3(1), dim3(32), 0, lnst_stream(stream), state, lr, beta1, beta2);
   if (n > 0)
     LNST_LAUNCH(adam_iterate_dev_k, dim3(lnst_blocks(n, 256)), dim3(256), 0, lnst_stream(stream), g_opt, grad, m, v,
@@ -211,8 +212,9 @@ extern "C" int lnst_adam_iterate_dev(float* g_opt, const float* grad, float* m, 
 }
 
 extern "C" int lnst_iterate_accumulate(float* acc, const float* var, int64_t n, int32_t first, void* stream) {
-  if (!acc || !var || n < 0) return LNST_EARG;
+  if (n < 0) return LNST_EARG;
   if (n == 0) return LNST_OK;
+  if (!acc || !var) return LNST_EARG;
   LNST_LAUNCH(iterate_accumulate_k, dim3(lnst_blocks(n, 256)), dim3(256), 0, lnst_stream(stream), acc, var, n,
               (int)first);
   return lnst_status();
@@ -220,46 +222,52 @@ extern "C" int lnst_iterate_accumulate(float* acc, const float* var, int64_t n, 
 
 extern "C" int lnst_iterate_delta(const float* g_new, float scale, const float* g_opt, const float* mask,
                                   int32_t width, int32_t mask_stride, int64_t n, float* delta, void* stream) {
-  if (!g_new || !g_opt || !delta || n < 0 || width < 1) return LNST_EARG;
+  if (n < 0 || width < 1) return LNST_EARG;
   if (n == 0) return LNST_OK;
+  if (!g_new || !g_opt || !delta) return LNST_EARG;
   LNST_LAUNCH(iterate_delta_k, dim3(lnst_blocks(n, 256)), dim3(256), 0, lnst_stream(stream), g_new, scale, g_opt,
               mask, (int)width, (int)mask_stride, n, delta);
   return lnst_status();
 }
 
 extern "C" int lnst_axpy(float* y, const float* x, float a, int64_t n, void* stream) {
-  if (!y || !x || n < 0) return LNST_EARG;
+  if (n < 0) return LNST_EARG;
   if (n == 0) return LNST_OK;
+  if (!y || !x) return LNST_EARG;
   LNST_LAUNCH(axpy_k, dim3(lnst_blocks(n, 256)), dim3(256), 0, lnst_stream(stream), y, x, a, n);
   return lnst_status();
 }
 
 extern "C" int lnst_clip_fwd(const float* x, float lo, float hi, float* y, int64_t n, void* stream) {
-  if (!x || !y || n < 0) return LNST_EARG;
+  if (n < 0) return LNST_EARG;
   if (n == 0) return LNST_OK;
+  if (!x || !y) return LNST_EARG;
   LNST_LAUNCH(clip_fwd_k, dim3(lnst_blocks(n, 256)), dim3(256), 0, lnst_stream(stream), x, lo, hi, y, n);
   return lnst_status();
 }
 
 extern "C" int lnst_clip_bwd(const float* g, const float* x, float lo, float hi, float scale, float* gx, int64_t n,
                              void* stream) {
-  if (!g || !x || !gx || n < 0) return LNST_EARG;
+  if (n < 0) return LNST_EARG;
   if (n == 0) return LNST_OK;
+  if (!g || !x || !gx) return LNST_EARG;
   LNST_LAUNCH(clip_bwd_k, dim3(lnst_blocks(n, 256)), dim3(256), 0, lnst_stream(stream), g, x, lo, hi, scale, gx, n);
   return lnst_status();
 }
 
 extern "C" int lnst_mul_bcast(const float* a, const float* b, int32_t C, float* out, int64_t n, void* stream) {
-  if (!a || !b || !out || n < 0 || C < 1) return LNST_EARG;
+  if (n < 0 || C < 1) return LNST_EARG;
   if (n == 0) return LNST_OK;
+  if (!a || !b || !out) return LNST_EARG;
   LNST_LAUNCH(mul_bcast_k, dim3(lnst_blocks(n, 256)), dim3(256), 0, lnst_stream(stream), a, b, (int)C, out, n);
   return lnst_status();
 }
 
 extern "C" int lnst_masked_accumulate(const float* t, const float* m, const float* f, int32_t relu, int32_t C,
                                       float beta, float* g, int64_t n, void* stream) {
-  if (!t || !m || !g || (relu && !f) || n < 0 || C < 1) return LNST_EARG;
+  if (n < 0 || C < 1) return LNST_EARG;
   if (n == 0) return LNST_OK;
+  if ((relu && !f) || !t || !m || !g) return LNST_EARG;
   LNST_LAUNCH(masked_accumulate_k, dim3(lnst_blocks(n, 256)), dim3(256), 0, lnst_stream(stream), t, m, f, (int)relu,
               (int)C, beta, g, n);
   return lnst_status();

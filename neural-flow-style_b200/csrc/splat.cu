@@ -419,7 +419,7 @@ static inline bool fill_kernels(SplatKernels& ks, int dim, const float* h, int n
 extern "C" int lnst_splat_sph_fwd(const float* p, const float* disp, int64_t n, const LnstGrid* g,
                                   float h, float scale, const float* pc, const float* pd, int32_t C,
                                   float rest_density, float* out, void* stream) {
-  if (!grid_ok(g) || !p || !out || n < 0 || !(h > 0.f) || (pc && (C < 1 || C > 4))) return LNST_EARG;
+  if (!grid_ok(g) || (n > 0 && !p) || !out || n < 0 || !(h > 0.f) || (pc && (C < 1 || C > 4))) return LNST_EARG;   // an empty set has no storage
   if (n == 0) return LNST_OK;
   const float sigma = sigma_for(g->dim, h);
   const int T = 256;
@@ -438,7 +438,7 @@ extern "C" int lnst_splat_sph_fwd(const float* p, const float* disp, int64_t n, 
 extern "C" int lnst_splat_sph_bwd_pos(const float* p, const float* disp, int64_t n, const LnstGrid* g,
                                       float h, float scale, const float* g_out, float* g_p,
                                       void* stream) {
-  if (!grid_ok(g) || !p || !g_out || !g_p || n < 0 || !(h > 0.f)) return LNST_EARG;
+  if (!grid_ok(g) || (n > 0 && (!p || !g_p)) || !g_out || n < 0 || !(h > 0.f)) return LNST_EARG;
   if (n == 0) return LNST_OK;
   const float sigma = sigma_for(g->dim, h);
   const int T = 256;
@@ -457,7 +457,7 @@ extern "C" int lnst_splat_sph_bwd_pos(const float* p, const float* disp, int64_t
 extern "C" int lnst_splat_sph_bwd_color(const float* p, int64_t n, const LnstGrid* g, float h,
                                         float scale, const float* pd, int32_t C, float rest_density,
                                         const float* g_out, float* g_pc, void* stream) {
-  if (!grid_ok(g) || !p || !g_out || !g_pc || n < 0 || !(h > 0.f) || C < 1 || C > 4) return LNST_EARG;
+  if (!grid_ok(g) || (n > 0 && (!p || !g_pc)) || !g_out || n < 0 || !(h > 0.f) || C < 1 || C > 4) return LNST_EARG;
   if (n == 0) return LNST_OK;
   const float sigma = sigma_for(g->dim, h);
   const int T = 256;
@@ -476,7 +476,7 @@ extern "C" int lnst_splat_sph_bwd_color(const float* p, int64_t n, const LnstGri
 extern "C" int lnst_splat_wavg_wmap(const float* p, int64_t n, const LnstGrid* g, const float* h,
                                     int32_t nk, float* wmap, void* stream) {
   SplatKernels ks;
-  if (!grid_ok(g) || !p || !wmap || n < 0 || !fill_kernels(ks, g ? g->dim : 3, h, nk)) return LNST_EARG;
+  if (!grid_ok(g) || (n > 0 && !p) || !wmap || n < 0 || !fill_kernels(ks, g ? g->dim : 3, h, nk)) return LNST_EARG;
   const int64_t cells = grid_cells(g);
   cudaMemsetAsync(wmap, 0, sizeof(float) * cells * nk, lnst_stream(stream));
   if (n == 0) return lnst_status();
@@ -503,7 +503,7 @@ extern "C" int lnst_splat_wavg_fwd_box(const float* p, const float* r, const flo
                                        const LnstGrid* g, const float* h, int32_t nk, const float* wmap,
                                        float* num, float* out, const LnstBox* box, void* stream) {
   SplatKernels ks;
-  if (!grid_ok(g) || !p || !r || !wmap || !num || !out || n < 0 ||
+  if (!grid_ok(g) || (n > 0 && (!p || !r)) || !wmap || !num || !out || n < 0 ||
       !fill_kernels(ks, g ? g->dim : 3, h, nk))
     return LNST_EARG;
   const int Dz = g->dim == 3 ? g->res[0] : 1;
@@ -552,7 +552,7 @@ extern "C" int lnst_splat_wavg_bwd_coef(const float* p, const float* var, int64_
                                         const float* h, int32_t nk, const float* coef, const float* g_out,
                                         float* g_var, void* stream) {
   SplatKernels ks;
-  if (!grid_ok(g) || !p || !coef || !g_out || !g_var || n < 0 || !fill_kernels(ks, g ? g->dim : 3, h, nk))
+  if (!grid_ok(g) || (n > 0 && (!p || !g_var)) || !coef || !g_out || n < 0 || !fill_kernels(ks, g ? g->dim : 3, h, nk))
     return LNST_EARG;
   if (g->dim != 3 || g->nsize != 1) return LNST_EARG;
   if (n == 0) return LNST_OK;
@@ -571,7 +571,7 @@ extern "C" int lnst_splat_wavg_bwd(const float* p, const float* var, int64_t n, 
                                    const float* h, int32_t nk, const float* wmap, const float* g_out,
                                    float* g_var, void* stream) {
   SplatKernels ks;
-  if (!grid_ok(g) || !p || !wmap || !g_out || !g_var || n < 0 || !fill_kernels(ks, g ? g->dim : 3, h, nk))
+  if (!grid_ok(g) || (n > 0 && (!p || !g_var)) || !wmap || !g_out || n < 0 || !fill_kernels(ks, g ? g->dim : 3, h, nk))
     return LNST_EARG;
   if (n == 0) return LNST_OK;
   const int64_t cells = grid_cells(g);

@@ -90,3 +90,86 @@ def test_g2p_any_shape(emu_lib, dims, C, n, linear, seed):
             assert x_adv.shape == p.shape and bool(torch.isfinite(x_adv).all())
     finally:
         _lib.set_for_testing(prev)
+
+
+# ---- the hot-path operators under random shapes (odd sizes, N = 0, particles on faces / outside, nsize 1..4) ----------
+from oracle import render as R  # noqa: E402
+
+
+@settings(**CFG)
+@given(res=st.lists(st.integers(1, 7), min_size=3, max_size=3), n=st.integers(0, 60), nsize=st.sampled_from([1, 2, 4]),
+       clip=st.booleans(), seed=st.integers(0, 1000))
+def test_splat_sph_any_shape(emu_lib, res, n, nsize, clip, seed):
+    prev = _use_emu(emu_lib)
+    try:
+        rng = np.random.RandomState(seed)
+        cell = 0.1
+        domain = [r * cell for r in res]
+        p = rng.uniform(-0.1, 1.1, (n, 3)).astype(np.float32)
+        if n > 3:
+            p[0], p[1], p[2] = 0.0, 1.0, -1.0                     # faces and the drivers' padding row
+        p = torch.tensor(p)
+        grid = _lib.make_grid(3, res, domain, nsize, clip)
+        radius, support, rho = 0.025, 4, 1000.0
+        scale = 0.8 * (2 * radius) ** 3
+        out = ops.splat_sph_fwd(p, None, grid, radius * support, scale)
+        pv = p.clone().requires_grad_(True)
+        want = T.p2g(pv[None], domain, res, radius, rho, nsize, is_2d=False, clip=clip, support=support)[0, ..., 0] / rho
+        _close(out, want, 2e-5)
+        if n:
+            g = torch.tensor(rng.randn(*res).astype(np.float32))
+            (want * g).sum().backward()
+            gp = ops.splat_sph_bwd_pos(p, None, grid, radius * support, scale, g)
+            _close(gp, pv.grad, 5e-5)
+    finally:
+        _lib.set_for_testing(prev)
+
+
+@settings(**CFG)
+@given(res=st.lists(st.integers(1, 8), min_size=3, max_size=3), k=st.sampled_from([1, 3, 5]), seed=st.integers(0, 1000))
+def test_smooth_and_raymarch_any_shape(emu_lib, res, k, seed):
+    prev = _use_emu(emu_lib)
+    try:
+        rng = np.random.RandomState(seed)
+        D, H, W = res
+        d = torch.tensor((rng.rand(D, H, W) - 0.3).astype(np.float32), requires_grad=True)
+        want = R.field_post(d[None, ..., None], k)[0, ..., 0]
+        out = ops.smooth3_relu_fwd(d.detach(), torch.empty(D, H, W), k)
+        _close(out, want, 2e-5)
+        vol = torch.relu(d.detach())
+        mats = [np.identity(3), np.matmul(T.rot_y_3d(17.0), T.rot_z_3d(-9.0))]
+        rot = torch.tensor(np.asarray(mats), dtype=torch.float32).reshape(-1, 9)
+        img, stot = torch.empty(2, H, W), torch.empty(2, H, W)
+        ops.raymarch_fwd(vol, rot, 0.3, False, img, stot)
+        dr = T.rotate(vol[None, ..., None], mats)
+        cs = torch.flip(torch.cumsum(torch.flip(dr, [1]), 1), [1])
+        _close(img, (dr * torch.exp(-cs * 0.3)).sum(1)[..., 0], 3e-5)
+    finally:
+        _lib.set_for_testing(prev)
+
+
+def test_empty_particle_set_runs_like_the_oracle(emu_lib):
+    """N = 0 (a frame before the first particles are seeded): every particle-sized buffer is empty, the C-ABI takes
+    NULL for them, and the loop still renders / evaluates the (constant) loss like the oracle (liquid render: the
+    smoke render's 0/0 normalisation is NaN in the reference as well)."""
+    import warnings
+    from helpers import liquid_cfg
+    from lnst import synth
+    from lnst.styler_3p import Styler
+    from oracle.styler import Oracle3P
+    import oracle.vgg
+    prev = _use_emu(emu_lib)
+    try:
+        kw = dict(res=8, iter=2, conv_math='fp32', style_layer=['conv1_2'], w_style_layer=[1.0])
+        params = {'p': [np.zeros((0, 3), np.float32)]}
+        sty = synth.style_image(8, 8)
+        st = Styler(liquid_cfg(**kw), weights=synth.vgg_weights(), device=torch.device('cpu'))
+        st.style_img = sty
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            out = st.run(params)
+            ref = Oracle3P(liquid_cfg(**kw), oracle.vgg.synthetic_weights()).run(params, style_targets=[sty])
+        np.testing.assert_allclose(out['l'][0], ref['l'][0], rtol=2e-4)
+        assert out['p'][0].shape == (0, 3) and float(np.abs(out['d']).max()) == 0.0
+    finally:
+        _lib.set_for_testing(prev)
