@@ -27,8 +27,15 @@ class TFAdam:
             self.v = torch.zeros_like(var)
         lr_t = np.float32(lr) * np.sqrt(np.float32(1) - self.b2p) / (np.float32(1) - self.b1p)
         lr_t = float(lr_t)
-        self.m = self.m + (grad - self.m) * (1 - self.b1)
-        self.v = self.v + (grad * grad - self.v) * (1 - self.b2)
+        # TF's kernel forms T(1) - beta in the variable's dtype (training_ops.cc): in fp32 1 - 0.999f = 0.00099998713,
+        # 1.3e-5 off the decimal value -- the CUDA kernel does the same; a Python-float (1 - beta) would not
+        if grad.dtype == torch.float32:
+            omb1 = float(np.float32(1) - np.float32(self.b1))
+            omb2 = float(np.float32(1) - np.float32(self.b2))
+        else:
+            omb1, omb2 = 1 - self.b1, 1 - self.b2
+        self.m = self.m + (grad - self.m) * omb1
+        self.v = self.v + (grad * grad - self.v) * omb2
         var = var - lr_t * self.m / (torch.sqrt(self.v) + self.eps)
         self.b1p = np.float32(self.b1p * np.float32(self.b1))
         self.b2p = np.float32(self.b2p * np.float32(self.b2))

@@ -173,3 +173,85 @@ def test_empty_particle_set_runs_like_the_oracle(emu_lib):
         assert out['p'][0].shape == (0, 3) and float(np.abs(out['d']).max()) == 0.0
     finally:
         _lib.set_for_testing(prev)
+
+
+@settings(**CFG)
+@given(res=st.lists(st.integers(1, 6), min_size=3, max_size=3), n=st.integers(0, 50), nk=st.integers(1, 3),
+       nsize=st.sampled_from([1, 2]), seed=st.integers(0, 1000))
+def test_splat_wavg_any_shape(emu_lib, res, n, nk, nsize, seed):
+    prev = _use_emu(emu_lib)
+    try:
+        rng = np.random.RandomState(seed)
+        p = torch.tensor(rng.uniform(-0.05, 1.05, (n, 3)).astype(np.float32))
+        r = torch.tensor(rng.uniform(0.2, 1.0, (n, nk)).astype(np.float32))
+        var = torch.tensor(rng.uniform(-1.3, 1.3, (n, nk)).astype(np.float32))       # some outside the clip range
+        grid = _lib.make_grid(3, res, res, nsize, False)
+        hs = [0.5 * 4 / 2 ** k for k in range(nk)]
+        cells = int(np.prod(res))
+        wmap = ops.splat_wavg_wmap(p, grid, hs)
+        out = ops.splat_wavg_fwd(p, r, var, grid, hs, wmap, torch.empty(nk, cells), torch.empty(*res))
+        vv = var.clone().requires_grad_(True)
+        x = r + torch.clamp(vv, -1, 1)
+        want = sum(T.p2g_wavg(p[None], x[None, :, k:k + 1], res, res, 0.5, nsize, is_2d=False, clip=False,
+                              support=4 / 2 ** k)[0, ..., 0] for k in range(nk)) if n else torch.zeros(*res)
+        _close(out, want, 2e-5)
+        if n:
+            g = torch.tensor(rng.randn(*res).astype(np.float32))
+            (want * g).sum().backward()
+            gv = ops.splat_wavg_bwd(p, var, grid, hs, wmap, g, torch.empty(n, nk))
+            nan_w, nan_g = torch.isnan(vv.grad), torch.isnan(gv)
+            assert torch.equal(nan_w, nan_g)                                         # TF's where/div NaN rule
+            ok = ~nan_w
+            if ok.any():
+                assert float((gv[ok] - vv.grad[ok]).abs().max()) <= 5e-5 * max(float(vv.grad[ok].abs().max()), 1e-30)
+    finally:
+        _lib.set_for_testing(prev)
+
+
+@settings(**CFG)
+@given(n=st.integers(0, 70), width=st.integers(1, 3), T_=st.integers(1, 6), sigma=st.floats(0.3, 3.0), seed=st.integers(0, 1000))
+def test_adam_and_loop_glue_any_shape(emu_lib, n, width, T_, sigma, seed):
+    from scipy.ndimage import gaussian_filter
+    from oracle.adam import TFAdam
+    prev = _use_emu(emu_lib)
+    try:
+        rng = np.random.RandomState(seed)
+        var = torch.tensor(rng.randn(n, width).astype(np.float32))
+        g = torch.tensor(rng.randn(n, width).astype(np.float32))
+        m, v = torch.zeros_like(var), torch.zeros_like(var)
+        state = torch.tensor([0.9, 0.999, 0.0])
+        ref = TFAdam()
+        want = var.clone()
+        v0 = float(var.abs().max()) if n else 0.0
+        for _ in range(2):
+            ops.adam_step_dev(var, g, m, v, state, 0.05)
+            want = ref.step(want, g, 0.05)
+        if n:                                                   # fp32 round-off of the operands (|var0|, 2 lr), not of the result
+            assert float((var - want).abs().max()) <= 1e-6 * (v0 + 0.1)
+        assert abs(float(state[0]) - 0.9 ** 3) < 1e-6                                # the step counter ticks for n = 0 too
+        x = torch.tensor(rng.randn(T_, max(n, 1), width).astype(np.float32))
+        y = ops.temporal_gauss(x, sigma)
+        _close(y, torch.tensor(gaussian_filter(x.numpy(), sigma=(sigma, 0, 0))), 3e-6)
+    finally:
+        _lib.set_for_testing(prev)
+
+
+@settings(**CFG)
+@given(H=st.integers(1, 9), W=st.integers(1, 9), oh=st.integers(1, 12), ow=st.integers(1, 12), nv=st.integers(1, 3),
+       seed=st.integers(0, 1000))
+def test_image_glue_any_shape(emu_lib, H, W, oh, ow, nv, seed):
+    prev = _use_emu(emu_lib)
+    try:
+        rng = np.random.RandomState(seed)
+        img = torch.tensor(rng.rand(nv, H, W).astype(np.float32) + 0.01)
+        stats = ops.image_max(img, torch.empty(2 * nv))
+        gray = ops.normalize_fwd(img, stats, torch.empty_like(img))
+        _close(gray, img / img.reshape(nv, -1).max(1).values.reshape(nv, 1, 1), 2e-6)
+        x = torch.tensor(rng.rand(nv, H, W, 1).astype(np.float32), requires_grad=True)
+        want = R.resize_bilinear_legacy(x, oh, ow)
+        _close(ops.resize_bilinear_fwd(x.detach(), oh, ow), want, 3e-6)
+        g = torch.tensor(rng.randn(*want.shape).astype(np.float32))
+        (want * g).sum().backward()
+        _close(ops.resize_bilinear_bwd(g, H, W), x.grad, 3e-6)
+    finally:
+        _lib.set_for_testing(prev)
