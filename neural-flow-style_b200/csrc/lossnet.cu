@@ -78,6 +78,9 @@ __global__ void content_loss_k(const float* __restrict__ F, int64_t P, int C, in
     if (gF) gF[t] = (beta != 0.f ? beta * gF[t] : 0.f) + ((!relu_mask || f > 0.f) ? weight * g : 0.f);
   }
   s = lnst_warp_sum(s);
+  // the LAST channel leaves `feature[..., c+1:]` empty: tf.reduce_mean of an empty tensor is NaN, so the reference logs
+  // a NaN loss there (its gradient is unaffected: nothing flows into an empty slice) -- reproduced
+  if (channel > 0 && channel == C - 1) s = __int_as_float(0x7fc00000);
   if (loss && (threadIdx.x & 31) == 0) atomicAdd(loss, weight * s);
 }
 

@@ -255,3 +255,109 @@ def test_image_glue_any_shape(emu_lib, H, W, oh, ow, nv, seed):
         _close(ops.resize_bilinear_bwd(g, H, W), x.grad, 3e-6)
     finally:
         _lib.set_for_testing(prev)
+
+
+from oracle import loss as L  # noqa: E402
+
+
+@settings(**CFG)
+@given(H=st.integers(1, 9), W=st.integers(1, 9), cin=st.integers(1, 70), cout=st.integers(1, 70), n=st.integers(1, 2),
+       seed=st.integers(0, 1000))
+def test_fp32_loss_net_layers_any_shape(emu_lib, H, W, cin, cout, n, seed):
+    prev = _use_emu(emu_lib)
+    try:
+        rng = np.random.RandomState(seed)
+        x = torch.tensor(rng.randn(n, H, W, cin).astype(np.float32), requires_grad=True)
+        w = torch.tensor((rng.randn(3, 3, cin, cout) / np.sqrt(9 * cin)).astype(np.float32))
+        b = torch.tensor(rng.randn(cout).astype(np.float32))
+        y = ops.conv3x3_f32(x.detach(), w, b, relu=True)
+        want = torch.relu(torch.nn.functional.conv2d(x.permute(0, 3, 1, 2), w.permute(3, 2, 0, 1), b, padding=1))
+        want = want.permute(0, 2, 3, 1)
+        _close(y, want, 2e-5)
+        g = torch.tensor(rng.randn(*want.shape).astype(np.float32))
+        (want * g).sum().backward()
+        gx = ops.conv3x3_f32((g * (want > 0)).detach().contiguous(), w.flip(0, 1).permute(0, 1, 3, 2).contiguous(), None,
+                             relu=False)
+        _close(gx, x.grad, 3e-5)
+        if H >= 2 and W >= 2:
+            xp = x.detach().clone().requires_grad_(True)
+            pw = torch.nn.functional.avg_pool2d(xp.permute(0, 3, 1, 2), 2, 2).permute(0, 2, 3, 1)
+            _close(ops.avgpool2_fwd(xp.detach()), pw, 2e-6)
+            gp = torch.tensor(rng.randn(*pw.shape).astype(np.float32))
+            (pw * gp).sum().backward()
+            _close(ops.avgpool2_bwd(gp, None, xp.shape), xp.grad, 2e-6)
+    finally:
+        _lib.set_for_testing(prev)
+
+
+@settings(**CFG)
+@given(h=st.integers(1, 8), w=st.integers(1, 8), ch=st.integers(1, 80), hs=st.integers(1, 6), channel=st.integers(0, 79),
+       seed=st.integers(0, 1000))
+def test_losses_any_shape(emu_lib, h, w, ch, hs, channel, seed):
+    prev = _use_emu(emu_lib)
+    try:
+        rng = np.random.RandomState(seed)
+        P = h * w
+        channel = channel % ch
+        F = torch.tensor(np.maximum(rng.randn(P, ch), 0).astype(np.float32), requires_grad=True)
+        Fs = torch.tensor(np.maximum(rng.randn(hs * 3, ch), 0).astype(np.float32))
+        Gs, loss = torch.empty(ch, ch), torch.zeros(1)
+        ops.gram_diff(Fs, 2.0 * hs * 3 * ch, None, 0.0, Gs, None)
+        G = torch.empty_like(Gs)
+        ops.gram_diff(F.detach(), 2.0 * P * ch, Gs, 0.7, G, loss)
+        want, _ = L.style_loss([F.reshape(1, h, w, ch)], [Fs.reshape(1, hs, 3, ch)], [0.7], 1)
+        _close(loss, want.reshape(1), 3e-5)
+        want.backward()
+        gF = torch.empty(P, ch)
+        ops.gram_bwd(F.detach(), G, 0.7 * 4.0 / (2.0 * P * ch), 0.0, 0, gF)
+        _close(gF, F.grad, 3e-5)
+        Fc = F.detach().clone().requires_grad_(True)
+        wc = L.content_loss(Fc.reshape(1, h, w, ch), channel) * 1.5
+        wc.backward()
+        loss.zero_()
+        gC = torch.empty(P, ch)
+        ops.content_loss(Fc.detach(), channel, 1.5, loss, gC, 0.0, 0)
+        if channel and channel == ch - 1:                       # mean over the empty slice f[..., c+1:]: NaN in TF, oracle, kernel
+            assert np.isnan(float(wc.detach())) and np.isnan(float(loss))
+        else:
+            assert abs(float(loss) - float(wc.detach())) <= 3e-6 * max(abs(float(wc.detach())), float(Fc.detach().abs().max()), 1e-30)
+        _close(gC, Fc.grad, 3e-6)
+        img = torch.tensor((rng.rand(1, h, w, 3) * 255).astype(np.float32), requires_grad=True)
+        tv = L.tv_loss(img) * 0.01
+        tv.backward()
+        loss.zero_()
+        gi = torch.empty(h, w, 3)
+        ops.tv_loss(img.detach()[0], 0.01, loss, gi)
+        assert abs(float(loss) - float(tv.detach())) <= 3e-6 * max(abs(float(tv.detach())), 1.0)
+        _close(gi, img.grad[0], 3e-6) if float(img.grad.abs().max()) > 0 else None
+    finally:
+        _lib.set_for_testing(prev)
+
+
+@settings(**CFG)
+@given(res=st.lists(st.integers(1, 7), min_size=3, max_size=3), liquid=st.booleans(), big=st.booleans(), seed=st.integers(0, 1000))
+def test_raymarch_backward_any_shape(emu_lib, res, liquid, big, seed):
+    prev = _use_emu(emu_lib)
+    try:
+        rng = np.random.RandomState(seed)
+        D, H, W = res
+        vol = torch.tensor((rng.rand(D, H, W) * (rng.rand(D, H, W) > 0.3)).astype(np.float32), requires_grad=True)
+        mats = [np.matmul(T.rot_y_3d(70.0 if big else 8.0), T.rot_z_3d(-55.0 if big else 4.0)), np.identity(3)]
+        rot = torch.tensor(np.asarray(mats), dtype=torch.float32).reshape(-1, 9)
+        img, stot = torch.empty(2, H, W), torch.empty(2, H, W)
+        ops.raymarch_fwd(vol.detach(), rot, 0.2, liquid, img, stot)
+        dr = T.rotate(vol[None, ..., None], mats)
+        if liquid:
+            want = (1.0 - torch.exp(-dr.sum(1) * 0.2))[..., 0]
+        else:
+            cs = torch.flip(torch.cumsum(torch.flip(dr, [1]), 1), [1])
+            want = (dr * torch.exp(-cs * 0.2)).sum(1)[..., 0]
+        _close(img, want, 3e-5)
+        g = torch.tensor(rng.randn(2, H, W).astype(np.float32))
+        g[0, 0, 0] = 0.0                                          # a ray without incoming gradient
+        (want * g).sum().backward()
+        gv = torch.zeros(D, H, W)
+        ops.raymarch_bwd(vol.detach(), rot, 0.2, liquid, stot, g, gv)
+        _close(gv, vol.grad, 5e-5)
+    finally:
+        _lib.set_for_testing(prev)
