@@ -361,3 +361,73 @@ def test_raymarch_backward_any_shape(emu_lib, res, liquid, big, seed):
         _close(gv, vol.grad, 5e-5)
     finally:
         _lib.set_for_testing(prev)
+
+
+@settings(**CFG)
+@given(res=st.lists(st.integers(1, 9), min_size=2, max_size=2), n=st.integers(0, 50), nsize=st.sampled_from([1, 2, 4]),
+       seed=st.integers(0, 1000))
+def test_colour_splat_2d_any_shape(emu_lib, res, n, nsize, seed):
+    prev = _use_emu(emu_lib)
+    try:
+        rng = np.random.RandomState(seed)
+        dom = [r * 0.1 for r in res]
+        p = torch.tensor(rng.uniform(-0.05, 1.05, (n, 2)).astype(np.float32))
+        pc = torch.tensor(rng.rand(n, 3).astype(np.float32), requires_grad=True)
+        pd = torch.tensor((1000 * (1 + 0.02 * rng.randn(n, 1))).astype(np.float32))
+        grid = _lib.make_grid(2, res, dom, nsize, False)
+        h, scale = 0.025 * 4, 0.8 * (2 * 0.025) ** 2 * 1000.0
+        out = ops.splat_sph_fwd(p, None, grid, h, scale, pc=pc.detach(), pd=pd)
+        want = T.p2g(p[None], dom, res, 0.025, 1000.0, nsize, pc=pc[None], pd=pd[None], is_2d=True, clip=False)[0]
+        _close(out, want, 2e-5)
+        if n:
+            g = torch.tensor(rng.randn(*res, 3).astype(np.float32))
+            (want * g).sum().backward()
+            _close(ops.splat_sph_bwd_color(p, grid, h, scale, pd, 3, 1000.0, g), pc.grad, 3e-5)
+    finally:
+        _lib.set_for_testing(prev)
+
+
+@settings(**CFG)
+@given(dims=st.lists(st.integers(1, 7), min_size=2, max_size=3), C=st.integers(1, 3), seed=st.integers(0, 1000))
+def test_warps_any_shape(emu_lib, dims, C, seed):
+    prev = _use_emu(emu_lib)
+    try:
+        rng = np.random.RandomState(seed)
+        dim = len(dims)
+        d = torch.tensor(rng.rand(*dims, C).astype(np.float32))
+        vel = torch.tensor(rng.uniform(-0.6, 0.6, dims + [dim]).astype(np.float32))
+        _close(ops.advect(d, vel), T.advect(d[None], vel[None], is_3d=dim == 3)[0], 3e-6)
+        if dim == 3:
+            vol = d[..., 0].contiguous()
+            mats = [np.matmul(T.rot_y_3d(25.0), T.rot_z_3d(-40.0)), np.identity(3)]
+            rot = torch.tensor(np.asarray(mats), dtype=torch.float32).reshape(-1, 9)
+            _close(ops.rotate_fwd(vol, rot), T.rotate(vol[None, ..., None], mats)[..., 0], 3e-6)
+    finally:
+        _lib.set_for_testing(prev)
+
+
+@settings(**CFG)
+@given(nv=st.integers(1, 3), H=st.integers(1, 7), W=st.integers(1, 7), ties=st.integers(1, 4), oh=st.integers(1, 9),
+       ow=st.integers(1, 9), seed=st.integers(0, 1000))
+def test_normalise_ties_and_bicubic_any_shape(emu_lib, nv, H, W, ties, oh, ow, seed):
+    prev = _use_emu(emu_lib)
+    try:
+        rng = np.random.RandomState(seed)
+        img = rng.rand(nv, H, W).astype(np.float32) * 0.9
+        for v in range(nv):                                       # `ties` pixels share the maximum: reduce_max splits its gradient
+            idx = rng.choice(H * W, size=min(ties, H * W), replace=False)
+            img[v].reshape(-1)[idx] = 0.95
+        img = torch.tensor(img, requires_grad=True)
+        stats = ops.image_max(img.detach(), torch.empty(2 * nv))
+        gray = ops.normalize_fwd(img.detach(), stats, torch.empty(nv, H, W))
+        want = torch.stack([img[v] / torch.amax(img[v]) for v in range(nv)])
+        _close(gray, want, 2e-6)
+        g = torch.tensor(rng.randn(nv, H, W).astype(np.float32))
+        (want * g).sum().backward()
+        gi = ops.normalize_bwd(img.detach(), stats, g, torch.empty(nv), torch.empty(nv, H, W))
+        # relative to the cotangent: the gradient itself can cancel to exactly 0 (a one-pixel image is constant 1)
+        assert float((gi - img.grad).abs().max()) <= 3e-5 * max(float(g.abs().max()) / 0.95, 1e-30)
+        x = torch.tensor(rng.rand(1, H, W, 1).astype(np.float32))
+        _close(ops.resize_bicubic_fwd(x, oh, ow), L.bicubic_legacy(x, oh, ow), 3e-6)
+    finally:
+        _lib.set_for_testing(prev)
