@@ -431,3 +431,4 @@ def test_normalise_ties_and_bicubic_any_shape(emu_lib, nv, H, W, ties, oh, ow, s
         _close(ops.resize_bicubic_fwd(x, oh, ow), L.bicubic_legacy(x, oh, ow), 3e-6)
     finally:
         _lib.set_for_testing(prev)
+
