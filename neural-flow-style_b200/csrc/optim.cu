@@ -274,7 +274,9 @@ extern "C" int lnst_masked_accumulate(const float* t, const float* m, const floa
 }
 
 extern "C" int lnst_temporal_gauss(const float* x, float* y, int32_t T, int64_t M, float sigma, void* stream) {
-  if (!x || !y || T < 1 || M < 1 || !(sigma > 0.f)) return LNST_EARG;
+  if (T < 1 || M < 0 || !(sigma > 0.f)) return LNST_EARG;
+  if (M == 0) return LNST_OK;                          // frames without particles: nothing to filter
+  if (!x || !y) return LNST_EARG;
   GaussTaps g;
   g.radius = (int)(4.0 * (double)sigma + 0.5);           // scipy: int(truncate*sd + 0.5)
   if (g.radius > LNST_MAX_GAUSS_RADIUS) return LNST_EARG;
