@@ -513,7 +513,7 @@ def main():
     ap.add_argument('--impl', default='engine', choices=['engine', 'reference'])
     ap.add_argument('--workload', default='C3', choices=list(WORKLOADS))
     ap.add_argument('--view-mode', dest='view_mode', default='allreduce', choices=['allreduce', 'sequential'])
-    ap.add_argument('--conv-math', dest='conv_math', default=None, choices=['bf16', 'fp32'])
+    ap.add_argument('--conv-math', dest='conv_math', default=None, choices=['bf16', 'bf16x3', 'fp32'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--cpu-budget', type=float, default=25.0)
     args = ap.parse_args()

@@ -45,6 +45,14 @@ typedef struct LnstBox {
 } LnstBox;
 
 int lnst_abi_version(void);
+/* Human-readable library version (static storage). */
+const char* lnst_version(void);
+/* Bytes of caller-provided scratch one call of entry point `op` (its name without the lnst_ prefix) needs beyond its
+ * inputs and outputs, for the problem size in `dims` (the library allocates nothing).  dims per op:
+ *   splat_wavg_fwd {V, nk} (the num volume); raymarch_fwd / raymarch_bwd {P, n_views} (ray intervals); image_max {n_img};
+ *   normalize_bwd {n_img}; density_reg {}; adam_step_dev / adam_iterate_dev {} (the 3-float state);
+ *   gram_diff_bf16_tc {n_img, C}.  Ops that need none return 0; an unknown op returns -1. */
+int64_t lnst_workspace_bytes(const char* op, const int64_t* dims, int32_t n_dims);
 
 /* ---- particle -> grid (transform.py:1310-1453 p2g, :1577-1704 p2g_wavg) ------------------ */
 /* SPH splat: out[cell] += scale * W(|x_p - x_cell|/h).  `disp` (may be NULL) is added to p
@@ -105,6 +113,10 @@ int lnst_fill_box(float* vol, int32_t D, int32_t H, int32_t W, const LnstBox* bo
 /* rot: [n_views,9] row-major rotation matrices, or NULL for the unrotated render. */
 int lnst_rotate_fwd(const float* vol, const float* rot, int32_t n_views, int32_t D, int32_t H,
                     int32_t W, float* out, void* stream);
+/* Gradient of lnst_rotate_fwd w.r.t. the volume: g_vol [D,H,W] += 8-corner scatter of g_out [n_views,D,H,W]
+ * (accumulates over the views: zero it first). */
+int lnst_rotate_bwd(const float* g_out, const float* rot, int32_t n_views, int32_t D, int32_t H,
+                    int32_t W, float* g_vol, void* stream);
 /* Fused rotate + emission/absorption ray-march.  img [n_views,H,W] = sum_i d_i T_i (smoke) or
  * 1-exp(-tau sum d) (liquid); stot [n_views,H,W] = sum_i d_i (saved for the backward). */
 int lnst_raymarch_fwd(const float* vol, const float* rot, int32_t n_views, int32_t D, int32_t H,
@@ -243,6 +255,34 @@ int lnst_avgpool2_bf16_bwd(const void* g_y, const void* mask, void* g_x, int32_t
 int lnst_f32_to_bf16(const float* x, void* y, int64_t n, void* stream);
 int lnst_bf16_to_f32(const void* x, float* y, int64_t n, void* stream);
 
+/* ---- bf16x3 ("split") tensor-core loss network: fp32-tolerance results at tensor-core speed (vgg.py:89-113 is fp32) ----
+ * Every fp32 value v travels as two bf16 halves hi = bf16(v), lo = bf16(v - hi): an NHWC row of C logical channels is
+ * 2C bf16 = [hi(0..C-1) | lo(0..C-1)], weights are packed [9, Cout, 2*Cin] = [Whi | Wlo].  A convolution runs three K
+ * passes -- x_hi*W_hi, x_lo*W_hi, x_hi*W_lo -- into one fp32 TMEM accumulator (products carry 16 mantissa bits; the
+ * lo*lo term, 2^-16 relative, is dropped) and its epilogue splits the fp32 result again.  Same kernels and argument
+ * meaning as the bf16 entry points above; `C`, `Cin`, `Cout` are LOGICAL channel counts. */
+int lnst_conv3x3_bf16x3_tc(const void* x, const void* w_packed2, const float* bias, const void* mask, void* y,
+                           int32_t n, int32_t H, int32_t W, int32_t Cin, int32_t Cout, int32_t relu, void* stream);
+/* G2: fp32 scratch [n,2C,2C]; G fp32 [n,C,C] = F^T F/denom - Gs; Gd2 bf16 [n,C,2C] = split copy of G (may be NULL). */
+int lnst_gram_diff_bf16x3_tc(const void* F, int32_t n, int64_t P, int32_t C, float denom, const float* Gs, float weight,
+                             float* G2, float* G, void* Gd2, float* loss, void* stream);
+int lnst_gram_bwd_bf16x3_tc(const void* F, const void* Gd2, float coef, const void* addend, int32_t relu_mask, void* g,
+                            int32_t n, int32_t H, int32_t W, int32_t C, void* stream);
+int lnst_conv_first_fwd_x3(const float* x, const float* w, const float* b, void* y, int32_t n, int32_t H, int32_t W,
+                           void* stream);
+int lnst_conv_first_fwd_gray_x3(const float* gray, const float* ws, const float* wm, const float* bsum, void* y,
+                                int32_t n, int32_t H, int32_t W, void* stream);
+/* wd16 bf16 [9,16,128] = [hi | lo] rows */
+int lnst_conv_first_bwd_x3_tc(const void* g, const void* wd16, float* gx, int32_t n, int32_t H, int32_t W, void* stream);
+int lnst_conv_first_bwd_gray_x3_tc(const void* g, const void* wd16, float* g_gray, int32_t n, int32_t H, int32_t W,
+                                   void* stream);
+int lnst_avgpool2_bf16x3_fwd(const void* x, void* y, int32_t n, int32_t H, int32_t W, int32_t C, void* stream);
+int lnst_avgpool2_bf16x3_bwd(const void* g_y, const void* mask, void* g_x, int32_t n, int32_t H, int32_t W, int32_t C,
+                             void* stream);
+/* fp32 [rows, C] <-> split bf16 [rows, 2C] */
+int lnst_f32_to_bf16x3(const float* x, void* y, int64_t rows, int32_t C, void* stream);
+int lnst_bf16x3_to_f32(const void* x, float* y, int64_t rows, int32_t C, void* stream);
+
 /* ---- losses (styler_base.py:96-102,135-185,211-213) --------------------------------------- */
 /* G [C,C] = F^T F / denom - Gs (the difference is what both the loss and its gradient need);
  * loss[0] += weight * sum(G^2).  F [P,C].  Gs NULL => G = F^T F / denom (style-target pass). */
@@ -321,6 +361,16 @@ int lnst_rk4_advect(const float* u, int32_t dim, const int32_t* dims, const floa
  * d_rec (test_smokegun_resim.py:69-74; styler_3p.py:96-98).  The caller zeroes `loss` (one device float). */
 int lnst_pressure_loss(const float* d_rec, int64_t cells, float rest_density, float weight, float* loss,
                        float* g_d, void* stream);
+/* Loss regularisers of the stylisation step, accumulating into the step's buffers:
+ * pressure (styler_3p.py:96-98, styler_base.py:228-230): loss[0..n_loss) += w_mean * mean(pr^2) and
+ * g_d[i] += g_scale * pr_i with pr = d > 0 ? d - rest_density : 0 (g_d may be NULL). */
+int lnst_pressure_reg(const float* d, int64_t cells, float rest_density, float w_mean, float g_scale, float* loss,
+                      int32_t n_loss, float* g_d, void* stream);
+/* density (styler_base.py:217-223 on dv = clip(var, -1, 1)): loss[0..n_loss) += weight * ((sum dv)^2 + 1e3 * sum
+ * -log(|dv| + 1e-6)); grad[i] += g_weight * [-1 <= var_i <= 1] * (2 sum dv - 1e3 sign(dv_i) / (|dv_i| + 1e-6)).
+ * sums: 2 floats of scratch. */
+int lnst_density_reg(const float* var, int64_t n, float weight, float g_weight, float* sums, float* loss,
+                     int32_t n_loss, float* grad, void* stream);
 /* out[z,y,x] = a[z,y,x] - b[z,H-1-y,x]: residual between a density grid and a splatted field (whose H axis is
  * stored flipped): `d - d_hi[:,:,::-1]` and d_diff of test_smokegun_resim.py:92,106. */
 int lnst_sub_fliph(const float* a, const float* b, float* out, int32_t D, int32_t H, int32_t W, void* stream);

@@ -174,7 +174,28 @@ struct ConvShape {
   int w_img;     // 1: third coordinate of the weight map is the image index (per-image B matrix)
   float scale;   // multiplies the accumulator before addend / bias
   int out_ch;    // OUT3 epilogue: fp32 channels written per pixel (3, or 1 for the gray render)
+  // bf16x3 ("split") operands: a value v travels as hi = bf16(v), lo = bf16(v - hi) in channels [0,C) and [C,2C) of one
+  // NHWC row, weights as [Whi | Wlo] along Cin, and the K loop runs 3 passes -- x_hi*W_hi, x_lo*W_hi, x_hi*W_lo -- into
+  // the same fp32 accumulator: products carry 16 mantissa bits instead of 8 at 3x the MMA count (the lo*lo term, 2^-16
+  // relative, is dropped).  nchunks = K-loop length in 64-channel chunks (Cin/64, or 3*Cin/64), wchunks = weight
+  // chunks per tap (Cin/64 or 2*Cin/64), kc = Cin/64; chunk c reads activation chunk xchunk(c) and weight chunk wchunk(c).
+  int split, kc, nchunks, wchunks;
+  int ldy, ldm;  // row strides (elements) of the output / mask / addend tensors: Cout, or 2*Cout when split
 };
+__device__ __forceinline__ int xchunk(const ConvShape& s, int c) { return (s.split && c >= 2 * s.kc) ? c - 2 * s.kc : c; }
+__device__ __forceinline__ int wchunk(const ConvShape& s, int c) { return (s.split && c >= s.kc) ? c - s.kc : c; }
+static inline void shape_plain(ConvShape& s) {
+  s.split = 0; s.kc = s.Cin / 64; s.nchunks = s.kc; s.wchunks = s.kc; s.ldy = s.Cout; s.ldm = s.Cout;
+}
+static inline void shape_split(ConvShape& s) {
+  s.split = 1; s.kc = s.Cin / 64; s.nchunks = 3 * s.kc; s.wchunks = 2 * s.kc; s.ldy = 2 * s.Cout; s.ldm = 2 * s.Cout;
+}
+// hi/lo split of an fp32 pair
+__device__ __forceinline__ void split2(float f0, float f1, __nv_bfloat162& hi, __nv_bfloat162& lo) {
+  hi = __floats2bfloat162_rn(f0, f1);
+  const float2 h = __bfloat1622float2(hi);
+  lo = __floats2bfloat162_rn(f0 - h.x, f1 - h.y);
+}
 
 // y = mask( relu?( scale * (X (*) W) + addend + bias ) )
 template <int BLOCK_N>
@@ -196,7 +217,7 @@ conv3x3_tc_k(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ 
   const int tile = blockIdx.x;
   const int tw = tile % s.tiles_w, th = (tile / s.tiles_w) % s.tiles_h, img = tile / (s.tiles_w * s.tiles_h);
   const int h0 = th * s.TH, w0 = tw * s.TW, n0 = blockIdx.y * BLOCK_N;
-  const int kchunks = s.Cin / BLOCK_K;
+  const int kchunks = s.nchunks;
   const int num_kb = s.taps * kchunks;
 
   if (warp == 0 && lane == 0) {
@@ -227,11 +248,11 @@ conv3x3_tc_k(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ 
         mbar_wait(bars + 8 * (STAGES + st), ph ^ 1);                 // slot free
         const uint32_t full = bars + 8 * st;
         mbar_expect_tx(full, A_BYTES + B_BYTES);
-        const int tap = kb / kchunks, c0 = (kb - tap * kchunks) * BLOCK_K;
+        const int tap = kb / kchunks, cc = kb - tap * kchunks, c0 = xchunk(s, cc) * BLOCK_K;
         int ky = 1, kx = 1;
         if (s.taps == 9) { ky = tap / 3; kx = tap - 3 * ky; }
         tma_load_4d(smem_a + st * A_BYTES, &map_x, full, c0, w0 + kx - 1, h0 + ky - 1, img);
-        tma_load_3d(smem_b + st * B_BYTES, &map_w, full, c0, n0, s.w_img ? img : tap);
+        tma_load_3d(smem_b + st * B_BYTES, &map_w, full, wchunk(s, cc) * BLOCK_K, n0, s.w_img ? img : tap);
       }
     }
   } else if (warp == 1) {
@@ -402,7 +423,7 @@ conv3x3_tc_persist_k(const __grid_constant__ CUtensorMap map_x, const __grid_con
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int kchunks = s.Cin / BLOCK_K;
+  const int kchunks = s.nchunks;
   const int num_kb = s.taps * kchunks;
   const int tiles_sp = s.tiles_w * s.tiles_h;
 
@@ -439,13 +460,13 @@ conv3x3_tc_persist_k(const __grid_constant__ CUtensorMap map_x, const __grid_con
         int ky = 1, kx = 1;
         if (s.taps == 9) { ky = tap / 3; kx = tap - 3 * ky; }
         const int wsel = s.w_img ? img : tap;
-        for (int c0 = 0; c0 < s.Cin; c0 += BLOCK_K) {
+        for (int c = 0; c < kchunks; ++c) {
           mbar_wait(bars + 8 * (PSTAGES + st), ph ^ 1);
           if (leader) {
             const uint32_t full = bars + 8 * st;
             mbar_expect_tx(full, A_BYTES + B_BYTES);
-            tma_load_4d(smem_a + st * A_BYTES, &map_x, full, c0, w0 + kx - 1, h0 + ky - 1, img);
-            tma_load_3d(smem_b + st * B_BYTES, &map_w, full, c0, n0, wsel);
+            tma_load_4d(smem_a + st * A_BYTES, &map_x, full, xchunk(s, c) * BLOCK_K, w0 + kx - 1, h0 + ky - 1, img);
+            tma_load_3d(smem_b + st * B_BYTES, &map_w, full, wchunk(s, c) * BLOCK_K, n0, wsel);
           }
           if (++st == PSTAGES) { st = 0; ph ^= 1; }
         }
@@ -499,7 +520,7 @@ conv3x3_tc_persist_k(const __grid_constant__ CUtensorMap map_x, const __grid_con
 #pragma unroll
       for (int c = 0; c < EN / 32; ++c) mbits[c] = 0xffffffffu;
       if (mask && valid) {
-        const uint4* msk = reinterpret_cast<const uint4*>(mask + pix * s.Cout + n0);
+        const uint4* msk = reinterpret_cast<const uint4*>(mask + pix * s.ldm + n0);
 #pragma unroll
         for (int c = 0; c < EN / 32; ++c) {
           uint4 mv[4];
@@ -515,13 +536,18 @@ conv3x3_tc_persist_k(const __grid_constant__ CUtensorMap map_x, const __grid_con
           mbits[c] = bits;
         }
       }
-      uint4 av[4];
+      uint4 av[4], al[4];                                             // addend (hi) and its lo half (split)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) av[j] = make_uint4(0, 0, 0, 0);
-      const uint4* add = (addend && valid) ? reinterpret_cast<const uint4*>(addend + pix * s.Cout + n0) : nullptr;
+      for (int j = 0; j < 4; ++j) { av[j] = make_uint4(0, 0, 0, 0); al[j] = make_uint4(0, 0, 0, 0); }
+      const uint4* add = (addend && valid) ? reinterpret_cast<const uint4*>(addend + pix * s.ldy + n0) : nullptr;
+      const uint4* addl = (add && s.split) ? reinterpret_cast<const uint4*>(addend + pix * s.ldy + s.Cout + n0) : nullptr;
       if (add) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) av[j] = add[j];
+      }
+      if (addl) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) al[j] = addl[j];
       }
       const uint32_t buf = lt & 1, bph = (lt >> 1) & 1;
       mbar_wait(bar_tfull + 8 * buf, bph);
@@ -537,37 +563,49 @@ conv3x3_tc_persist_k(const __grid_constant__ CUtensorMap map_x, const __grid_con
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
         }
-        uint4 an[4];
+        uint4 an[4], anl[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) an[j] = make_uint4(0, 0, 0, 0);
+        for (int j = 0; j < 4; ++j) { an[j] = make_uint4(0, 0, 0, 0); anl[j] = make_uint4(0, 0, 0, 0); }
         if (add && c + 1 < EN / 32) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) an[j] = add[(c + 1) * 4 + j];
+          if (addl) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) anl[j] = addl[(c + 1) * 4 + j];
+          }
         }
         if (valid) {
           const int co = n0 + c * 32;
-          __nv_bfloat16* dst = y + pix * s.Cout + co;
-          uint4 ov[4];
+          __nv_bfloat16* dst = y + pix * s.ldy + co;
+          uint4 ov[4], ol[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const __nv_bfloat16* ah = reinterpret_cast<const __nv_bfloat16*>(&av[j]);
+            const __nv_bfloat16* alh = reinterpret_cast<const __nv_bfloat16*>(&al[j]);
             __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&ov[j]);
+            __nv_bfloat162* ohl = reinterpret_cast<__nv_bfloat162*>(&ol[j]);
 #pragma unroll
             for (int e = 0; e < 8; e += 2) {
               float f0 = __uint_as_float(v[j * 8 + e]) * s.scale, f1 = __uint_as_float(v[j * 8 + e + 1]) * s.scale;
               if (addend) { f0 += __bfloat162float(ah[e]); f1 += __bfloat162float(ah[e + 1]); }
+              if (addl) { f0 += __bfloat162float(alh[e]); f1 += __bfloat162float(alh[e + 1]); }
               if (bias) { f0 += bias[co + j * 8 + e]; f1 += bias[co + j * 8 + e + 1]; }
               if (s.relu) { f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); }
               if (!((mbits[c] >> (j * 8 + e)) & 1u)) f0 = 0.f;
               if (!((mbits[c] >> (j * 8 + e + 1)) & 1u)) f1 = 0.f;
-              oh[e >> 1] = __floats2bfloat162_rn(f0, f1);
+              if (s.split) split2(f0, f1, oh[e >> 1], ohl[e >> 1]);
+              else oh[e >> 1] = __floats2bfloat162_rn(f0, f1);
             }
           }
 #pragma unroll
           for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(dst + j * 8) = ov[j];
+          if (s.split) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(dst + s.Cout + j * 8) = ol[j];
+          }
         }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) av[j] = an[j];
+        for (int j = 0; j < 4; ++j) { av[j] = an[j]; al[j] = anl[j]; }
       }
     }
   }
@@ -644,9 +682,9 @@ conv3x3_halo_k(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
   __shared__ __align__(16) float sbias[512];              // the layer's bias, read as broadcast float4s
   if (bias)
     for (int i = threadIdx.x; i < s.Cout && i < 512; i += blockDim.x) sbias[i] = bias[i];
-  const int kchunks = s.Cin / BLOCK_K;
+  const int kchunks = s.nchunks;
   constexpr bool resident = RES;                        // weights resident in smem (cfg.sb == 0) or streamed
-  const int n_wslots = resident ? 9 * kchunks : cfg.sb;
+  const int n_wslots = resident ? 9 * s.wchunks : cfg.sb;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t smem_a = base;
   const uint32_t smem_b = base + cfg.sa * PATCH_STRIDE;
@@ -682,10 +720,10 @@ conv3x3_halo_k(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     // ===== TMA producer (whole warp in the loop, one elected lane issues) =====
     const bool leader = elect_one();
     if (resident && leader) {                           // all 9 x kchunks weight tiles, once (n0 = 0)
-      mbar_expect_tx(bar_bfull, 9 * kchunks * B_BYTES);
+      mbar_expect_tx(bar_bfull, 9 * s.wchunks * B_BYTES);
       for (int tap = 0; tap < 9; ++tap)
-        for (int c = 0; c < kchunks; ++c)
-          tma_load_3d(smem_b + (tap * kchunks + c) * B_BYTES, &map_w, bar_bfull, c * BLOCK_K, 0, tap);
+        for (int c = 0; c < s.wchunks; ++c)
+          tma_load_3d(smem_b + (tap * s.wchunks + c) * B_BYTES, &map_w, bar_bfull, c * BLOCK_K, 0, tap);
     }
     uint32_t sta = 0, pha = 0, stb = 0, phb = 0;
     for (int t = blockIdx.x; t < cfg.n_tiles; t += gridDim.x) {
@@ -697,7 +735,7 @@ conv3x3_halo_k(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         mbar_wait(bar_aempty + 8 * sta, pha ^ 1);
         if (leader) {
           mbar_expect_tx(bar_afull + 8 * sta, PATCH_BYTES);
-          tma_load_4d(smem_a + sta * PATCH_STRIDE, &map_x, bar_afull + 8 * sta, c * BLOCK_K, w0 - 1, h0 - 1, img);
+          tma_load_4d(smem_a + sta * PATCH_STRIDE, &map_x, bar_afull + 8 * sta, xchunk(s, c) * BLOCK_K, w0 - 1, h0 - 1, img);
         }
         if (++sta == (uint32_t)cfg.sa) { sta = 0; pha ^= 1; }
         if (!resident) {
@@ -705,7 +743,7 @@ conv3x3_halo_k(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
             mbar_wait(bar_bempty + 8 * stb, phb ^ 1);
             if (leader) {
               mbar_expect_tx(bar_bfull + 8 * stb, B_BYTES);
-              tma_load_3d(smem_b + stb * B_BYTES, &map_w, bar_bfull + 8 * stb, c * BLOCK_K, n0, tap);
+              tma_load_3d(smem_b + stb * B_BYTES, &map_w, bar_bfull + 8 * stb, wchunk(s, c) * BLOCK_K, n0, tap);
             }
             if (++stb == (uint32_t)cfg.sb) { stb = 0; phb ^= 1; }
           }
@@ -737,8 +775,8 @@ conv3x3_halo_k(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
           // branches and barrier bookkeeping of the streamed path (~50 instructions per tap) capped the
           // kernel at ~2000 cycles per chunk whatever the MMA count (knock-out experiments)
           if (leader) {
-            const uint32_t bstep = (uint32_t)kchunks * (B_BYTES >> 4);
-            uint32_t blo = blo_base + c * (B_BYTES >> 4);             // slot tap * kchunks + c
+            const uint32_t bstep = (uint32_t)s.wchunks * (B_BYTES >> 4);
+            uint32_t blo = blo_base + wchunk(s, c) * (B_BYTES >> 4);  // slot tap * wchunks + wchunk(c)
 #pragma unroll
             for (int tap = 0; tap < 9; ++tap) {
               const int ky = tap / 3, kx = tap - 3 * ky;               // compile-time after unrolling
@@ -808,7 +846,7 @@ conv3x3_halo_k(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
 #pragma unroll
         for (int c = 0; c < NCH; ++c) mbits[c] = 0xffffffffu;
         if (mask && valid) {
-          const uint4* msk = reinterpret_cast<const uint4*>(mask + pix * s.Cout + n0);
+          const uint4* msk = reinterpret_cast<const uint4*>(mask + pix * s.ldm + n0);
 #pragma unroll
           for (int c = 0; c < NCH; ++c) {
             uint4 mv[4];
@@ -840,12 +878,13 @@ conv3x3_halo_k(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
           constexpr int NCK = (BLOCK_N >= NV * 8) ? BLOCK_N / (NV * 8) : 1;
 #pragma unroll
           for (int ck = 0; ck < NCK; ++ck) {
-            uint4 ov[NV];
+            uint4 ov[NV], ol[NV];
 #pragma unroll
             for (int jj = 0; jj < NV; ++jj) {
               const int col = ck * NV * 8 + jj * 8;                  // first of 8 accumulator columns
               const int c = col >> 5, j = (col >> 3) & 3;            // TMEM chunk of 32 columns, 8-column group
               __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&ov[jj]);
+              __nv_bfloat162* ohl = reinterpret_cast<__nv_bfloat162*>(&ol[jj]);
               const float4 b0 = bias ? *reinterpret_cast<const float4*>(sbias + n0 + col) : make_float4(0, 0, 0, 0);
               const float4 b1 = bias ? *reinterpret_cast<const float4*>(sbias + n0 + col + 4) : make_float4(0, 0, 0, 0);
               const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
@@ -856,22 +895,35 @@ conv3x3_halo_k(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                 if (s.relu) { f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); }
                 if (!((mbits[c] >> (j * 8 + e)) & 1u)) f0 = 0.f;
                 if (!((mbits[c] >> (j * 8 + e + 1)) & 1u)) f1 = 0.f;
-                oh[e >> 1] = __floats2bfloat162_rn(f0, f1);
+                if (s.split) split2(f0, f1, oh[e >> 1], ohl[e >> 1]);
+                else oh[e >> 1] = __floats2bfloat162_rn(f0, f1);
               }
             }
             if (BLOCK_N < 128) {                                     // narrow tiles: the direct stores keep up with the MMAs
               if (valid) {
-                __nv_bfloat16* dst = y + pix * s.Cout + n0 + ck * NV * 8;
+                __nv_bfloat16* dst = y + pix * s.ldy + n0 + ck * NV * 8;
 #pragma unroll
                 for (int jj = 0; jj < NV; ++jj) *reinterpret_cast<uint4*>(dst + jj * 8) = ov[jj];
+                if (s.split) {
+#pragma unroll
+                  for (int jj = 0; jj < NV; ++jj) *reinterpret_cast<uint4*>(dst + s.Cout + jj * 8) = ol[jj];
+                }
               }
-            } else
+            } else {
               warp_rows_store<NV>(stage_base + (uint32_t)q * (NV * 512u), lane, ov, [&](int row) -> __nv_bfloat16* {
                 const int rr = q * 32 + row;
                 const int ph2 = th * HTH + (rr >> 3), pw2 = tw * HTW + (rr & 7);
                 if (ph2 >= s.H || pw2 >= s.W) return nullptr;
-                return y + (((int64_t)img * s.H + ph2) * s.W + pw2) * s.Cout + n0 + ck * NV * 8;
+                return y + (((int64_t)img * s.H + ph2) * s.W + pw2) * s.ldy + n0 + ck * NV * 8;
               });
+              if (s.split)
+                warp_rows_store<NV>(stage_base + (uint32_t)q * (NV * 512u), lane, ol, [&](int row) -> __nv_bfloat16* {
+                  const int rr = q * 32 + row;
+                  const int ph2 = th * HTH + (rr >> 3), pw2 = tw * HTW + (rr & 7);
+                  if (ph2 >= s.H || pw2 >= s.W) return nullptr;
+                  return y + (((int64_t)img * s.H + ph2) * s.W + pw2) * s.ldy + s.Cout + n0 + ck * NV * 8;
+                });
+            }
           }
         }
       }
@@ -1092,6 +1144,31 @@ __global__ void gram_finish_bf16_k(float* __restrict__ G, const float* __restric
   if (loss && Gs && (threadIdx.x & 31) == 0 && s != 0.f) atomicAdd(loss + img, weight * s);
 }
 
+// Split features: G2 = F'^T F' with F' = [hi | lo] is [2C, 2C] = [[hh, hl], [lh, ll]]; F^T F = hh + hl + lh + ll.
+// G <- that / denom - Gs (fp32), Gd2 [C, 2C] = [hi | lo] split copy for the gradient GEMM, loss += weight * sum(G^2).
+__global__ void gram_finish_split_k(const float* __restrict__ G2, float* __restrict__ G, const float* __restrict__ Gs,
+                                    __nv_bfloat16* __restrict__ Gd2, int C, float inv_denom, float weight,
+                                    float* __restrict__ loss) {
+  const int img = blockIdx.y;
+  const int n_el = C * C;
+  const float* g2 = G2 + (int64_t)img * 4 * n_el;
+  float s = 0.f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_el; i += gridDim.x * blockDim.x) {
+    const int r = i / C, c = i - r * C;
+    const int64_t a = (int64_t)r * 2 * C + c;
+    float d = ((g2[a] + g2[a + C]) + (g2[a + (int64_t)2 * C * C] + g2[a + (int64_t)2 * C * C + C])) * inv_denom;
+    if (Gs) { d -= Gs[i]; s += d * d; }
+    G[(int64_t)img * n_el + i] = d;
+    if (Gd2) {
+      const __nv_bfloat16 h = __float2bfloat16_rn(d);
+      Gd2[(int64_t)img * 2 * n_el + a] = h;
+      Gd2[(int64_t)img * 2 * n_el + a + C] = __float2bfloat16_rn(d - __bfloat162float(h));
+    }
+  }
+  s = lnst_warp_sum(s);
+  if (loss && Gs && (threadIdx.x & 31) == 0 && s != 0.f) atomicAdd(loss + img, weight * s);
+}
+
 // ---- host side: tensor maps ------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -1176,7 +1253,7 @@ static int conv_halo = 2;         // tuning switch: 0 = per-tap kernel, 1 = halo
 template <int BLOCK_N, bool OUT3>
 static int launch_halo(const void* x, const void* wmat, const float* bias, const __nv_bfloat16* mask,
                        __nv_bfloat16* y, float* y3, int n, int H, int W, int Cin, int Cout, int relu, float scale,
-                       cudaStream_t stream, int out_ch = 3) {
+                       cudaStream_t stream, int out_ch = 3, int split = 0) {
   constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
   constexpr int MAX_SMEM = 232448;                        // 227 KiB opt-in limit per CTA
   const int budget = MAX_SMEM - 2048 - 1024 - 512 - HaloStage<BLOCK_N>::bytes - 128;   // static bias table, alignment slack, barriers, store staging
@@ -1185,7 +1262,9 @@ static int launch_halo(const void* x, const void* wmat, const float* bias, const
   s.TH = HTH; s.TW = HTW;
   s.tiles_w = (W + HTW - 1) / HTW;
   s.tiles_h = (H + HTH - 1) / HTH;
-  const int kchunks = Cin / BLOCK_K;
+  if (split) shape_split(s); else shape_plain(s);
+  const int kchunks = s.wchunks;                          // weight chunks per tap (what residency has to hold)
+  const int xC = split ? 2 * Cin : Cin;                   // channels of a row of x / of the weight rows
   HaloCfg cfg;
   cfg.n_blocks_n = OUT3 ? 1 : Cout / BLOCK_N;
   cfg.n_tiles = s.tiles_w * s.tiles_h * n * cfg.n_blocks_n;
@@ -1203,15 +1282,15 @@ static int launch_halo(const void* x, const void* wmat, const float* bias, const
   const int smem = cfg.sa * PATCH_STRIDE + n_wslots * B_BYTES + 8 * (2 * cfg.sa + 2 * (cfg.sb ? cfg.sb : 1) + 16) + 16 + 1024 + HaloStage<BLOCK_N>::bytes + 128;
   CUtensorMap mx, mw;
   {
-    const cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n};
-    const cuuint64_t strides[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2};
+    const cuuint64_t dims[4] = {(cuuint64_t)xC, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n};
+    const cuuint64_t strides[3] = {(cuuint64_t)xC * 2, (cuuint64_t)W * xC * 2, (cuuint64_t)H * W * xC * 2};
     const cuuint32_t box[4] = {(cuuint32_t)BLOCK_K, (cuuint32_t)(HTW + 2), (cuuint32_t)(HTH + 2), 1};
     if (!make_map(&mx, x, 4, dims, strides, box)) return LNST_EARG;
   }
   {
     const int rows = OUT3 ? BLOCK_N : Cout;
-    const cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)rows, 9};
-    const cuuint64_t strides[2] = {(cuuint64_t)Cin * 2, (cuuint64_t)rows * Cin * 2};
+    const cuuint64_t dims[3] = {(cuuint64_t)xC, (cuuint64_t)rows, 9};
+    const cuuint64_t strides[2] = {(cuuint64_t)xC * 2, (cuuint64_t)rows * xC * 2};
     const cuuint32_t box[3] = {(cuuint32_t)BLOCK_K, (cuuint32_t)BLOCK_N, 1};
     if (!make_map(&mw, wmat, 3, dims, strides, box)) return LNST_EARG;
   }
@@ -1261,6 +1340,106 @@ __global__ void bf16_to_f32_k(const __nv_bfloat16* __restrict__ x, float* __rest
     *reinterpret_cast<float4*>(y + i) = make_float4(fa.x, fa.y, fb.x, fb.y);
   } else {
     for (int64_t j = i; j < n; ++j) y[j] = __bfloat162float(x[j]);
+  }
+}
+// fp32 [rows, C] <-> split bf16 [rows, 2C] = [hi | lo] (bf16x3 operand layout, see ConvShape)
+__global__ void f32_to_split_k(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int64_t rows, int C) {
+  const int C2 = C / 2;
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= rows * C2) return;
+  const int64_t r = t / C2;
+  const int c = (int)(t - r * C2) * 2;
+  const float2 v = *reinterpret_cast<const float2*>(x + r * C + c);
+  __nv_bfloat162 hi, lo;
+  split2(v.x, v.y, hi, lo);
+  *reinterpret_cast<__nv_bfloat162*>(y + r * 2 * C + c) = hi;
+  *reinterpret_cast<__nv_bfloat162*>(y + r * 2 * C + C + c) = lo;
+}
+__global__ void split_to_f32_k(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, int64_t rows, int C) {
+  const int C2 = C / 2;
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= rows * C2) return;
+  const int64_t r = t / C2;
+  const int c = (int)(t - r * C2) * 2;
+  const float2 h = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(x + r * 2 * C + c));
+  const float2 l = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(x + r * 2 * C + C + c));
+  *reinterpret_cast<float2*>(y + r * C + c) = make_float2(h.x + l.x, h.y + l.y);
+}
+__device__ __forceinline__ void load8_split(const __nv_bfloat16* __restrict__ p, int C, float* f) {
+  const uint4 h = *reinterpret_cast<const uint4*>(p), l = *reinterpret_cast<const uint4*>(p + C);
+  const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&h);
+  const __nv_bfloat162* ll = reinterpret_cast<const __nv_bfloat162*>(&l);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float2 a = __bfloat1622float2(hh[e]), b = __bfloat1622float2(ll[e]);
+    f[2 * e] = a.x + b.x; f[2 * e + 1] = a.y + b.y;
+  }
+}
+__device__ __forceinline__ void store8_split(__nv_bfloat16* __restrict__ p, int C, const float* f) {
+  uint4 h, l;
+  __nv_bfloat162* hh = reinterpret_cast<__nv_bfloat162*>(&h);
+  __nv_bfloat162* ll = reinterpret_cast<__nv_bfloat162*>(&l);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) split2(f[2 * e], f[2 * e + 1], hh[e], ll[e]);
+  *reinterpret_cast<uint4*>(p) = h;
+  *reinterpret_cast<uint4*>(p + C) = l;
+}
+// 2x2/2 average pool on split rows: the four (hi + lo) values are summed in fp32 and split again
+__global__ void avgpool2_split_fwd_k(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int n, int H,
+                                     int W, int C) {
+  const int OH = H / 2, OW = W / 2, C8 = C / 8;
+  const unsigned total = (unsigned)n * OH * OW * C8;
+  const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const unsigned t1 = t / (unsigned)C8, t2 = t1 / (unsigned)OW, t3 = t2 / (unsigned)OH;
+  const int c = (int)(t - t1 * C8) * 8;
+  const int ox = (int)(t1 - t2 * OW), oy = (int)(t2 - t3 * OH), img = (int)t3;
+  const int64_t R = 2 * (int64_t)C;                                 // row stride
+  const __nv_bfloat16* b = x + (((int64_t)img * H + 2 * oy) * W + 2 * ox) * R + c;
+  float f0[8], f1[8], f2[8], f3[8], o[8];
+  load8_split(b, C, f0); load8_split(b + R, C, f1); load8_split(b + (int64_t)W * R, C, f2); load8_split(b + (int64_t)W * R + R, C, f3);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) o[e] = (f0[e] + f1[e] + f2[e] + f3[e]) * 0.25f;
+  store8_split(y + (((int64_t)img * OH + oy) * OW + ox) * R + c, C, o);
+}
+__global__ void avgpool2_split_bwd_k(const __nv_bfloat16* __restrict__ gy, const __nv_bfloat16* __restrict__ mask,
+                                     __nv_bfloat16* __restrict__ gx, int n, int H, int W, int C) {
+  const int OH = H / 2, OW = W / 2, C8 = C / 8;
+  const int QH = (H + 1) / 2, QW = (W + 1) / 2;
+  const unsigned total = (unsigned)n * QH * QW * C8;
+  const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const unsigned t1 = t / (unsigned)C8, t2 = t1 / (unsigned)QW, t3 = t2 / (unsigned)QH;
+  const int c = (int)(t - t1 * C8) * 8;
+  const int ox = (int)(t1 - t2 * QW), oy = (int)(t2 - t3 * QH), img = (int)t3;
+  const int64_t R = 2 * (int64_t)C;
+  float f[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) f[e] = 0.f;
+  if (oy < OH && ox < OW) {
+    load8_split(gy + (((int64_t)img * OH + oy) * OW + ox) * R + c, C, f);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) f[e] *= 0.25f;
+  }
+  const int y0 = 2 * oy, x0 = 2 * ox;
+  const int64_t o00 = (((int64_t)img * H + y0) * W + x0) * R + c;
+  const bool hx = x0 + 1 < W, hy = y0 + 1 < H;
+  const int64_t off[4] = {o00, o00 + R, o00 + (int64_t)W * R, o00 + (int64_t)W * R + R};
+  const bool ok[4] = {true, hx, hy, hx && hy};
+  uint4 mv[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    mv[q] = make_uint4(0, 0, 0, 0);
+    if (mask && ok[q]) mv[q] = *reinterpret_cast<const uint4*>(mask + off[q]);     // hi half carries the sign
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    if (!ok[q]) continue;
+    const __nv_bfloat16* mh = reinterpret_cast<const __nv_bfloat16*>(&mv[q]);
+    float o[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o[e] = (mask && !(__bfloat162float(mh[e]) > 0.f)) ? 0.f : f[e];
+    store8_split(gx + off[q], C, o);
   }
 }
 // 2x2/2 average pool on NHWC bf16, 8 channels (16 bytes) per thread
@@ -1342,9 +1521,28 @@ __global__ void avgpool2_bf16_bwd_k(const __nv_bfloat16* __restrict__ gy, const 
 // float4 fetched from shared memory feeds FP FMAs per lane, the (FP+2) x 3 x 3 input window is read
 // once per tap row (the 8 lanes of a pixel group read the same addresses: one broadcast transaction).
 constexpr int FP = 4;
+// relu'd accumulators of one pixel's 8 channels -> bf16 (or hi/lo halves of a 128-channel split row)
+__device__ __forceinline__ void store_first8(__nv_bfloat16* __restrict__ y, int64_t pixel, int cg, const float* acc, int split) {
+  uint4 o, ol;
+  __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+  __nv_bfloat162* ohl = reinterpret_cast<__nv_bfloat162*>(&ol);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float f0 = fmaxf(acc[2 * j], 0.f), f1 = fmaxf(acc[2 * j + 1], 0.f);
+    if (split) split2(f0, f1, oh[j], ohl[j]);
+    else oh[j] = __floats2bfloat162_rn(f0, f1);
+  }
+  if (split) {
+    *reinterpret_cast<uint4*>(y + pixel * 128 + cg) = o;
+    *reinterpret_cast<uint4*>(y + pixel * 128 + 64 + cg) = ol;
+  } else {
+    *reinterpret_cast<uint4*>(y + pixel * 64 + cg) = o;
+  }
+}
+
 __global__ void __launch_bounds__(256) conv_first_fwd_k(const float* __restrict__ x, const float* __restrict__ w,
                                                         const float* __restrict__ b, __nv_bfloat16* __restrict__ y,
-                                                        int n, int H, int W) {
+                                                        int n, int H, int W, int split) {
   __shared__ __align__(16) float ws[27 * 64];
   __shared__ float bs[64];
   for (int i = threadIdx.x; i < 27 * 64; i += blockDim.x) ws[i] = w[i];
@@ -1395,11 +1593,7 @@ __global__ void __launch_bounds__(256) conv_first_fwd_k(const float* __restrict_
 #pragma unroll
   for (int p = 0; p < FP; ++p) {
     if (px + p >= W) break;
-    uint4 o;
-    __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) oh[j] = __floats2bfloat162_rn(fmaxf(acc[p][2 * j], 0.f), fmaxf(acc[p][2 * j + 1], 0.f));
-    *reinterpret_cast<uint4*>(y + (((img * H + py) * (int64_t)W + px + p) * 64 + cg)) = o;
+    store_first8(y, (img * H + py) * (int64_t)W + px + p, cg, acc[p], split);
   }
 }
 
@@ -1410,7 +1604,7 @@ __global__ void __launch_bounds__(256) conv_first_fwd_k(const float* __restrict_
 // contributes neither term, so border pixels add wm[tap] back for their missing taps.
 __global__ void __launch_bounds__(256) conv_first_fwd_gray_k(const float* __restrict__ gimg, const float* __restrict__ ws,
                                                              const float* __restrict__ wm, const float* __restrict__ bsum,
-                                                             __nv_bfloat16* __restrict__ y, int n, int H, int W) {
+                                                             __nv_bfloat16* __restrict__ y, int n, int H, int W, int split) {
   __shared__ __align__(16) float s_ws[9 * 64];
   __shared__ __align__(16) float s_wm[9 * 64];
   __shared__ float s_b[64];
@@ -1471,11 +1665,7 @@ __global__ void __launch_bounds__(256) conv_first_fwd_gray_k(const float* __rest
 #pragma unroll
   for (int p = 0; p < FP; ++p) {
     if (px + p >= W) break;
-    uint4 o;
-    __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) oh[j] = __floats2bfloat162_rn(fmaxf(acc[p][2 * j], 0.f), fmaxf(acc[p][2 * j + 1], 0.f));
-    *reinterpret_cast<uint4*>(y + (((img * H + py) * (int64_t)W + px + p) * 64 + cg)) = o;
+    store_first8(y, (img * H + py) * (int64_t)W + px + p, cg, acc[p], split);
   }
 }
 
@@ -1555,7 +1745,14 @@ extern "C" int lnst_conv_first_fwd(const float* x, const float* w, const float* 
                                    int32_t W, void* stream) {
   if (!x || !w || !y || n < 1 || H < 1 || W < 1) return LNST_EARG;
   const int64_t threads = (int64_t)n * H * ((W + tc::FP - 1) / tc::FP) * 8;
-  tc::conv_first_fwd_k<<<lnst_blocks(threads, 256), 256, 0, lnst_stream(stream)>>>(x, w, b, (__nv_bfloat16*)y, n, H, W);
+  tc::conv_first_fwd_k<<<lnst_blocks(threads, 256), 256, 0, lnst_stream(stream)>>>(x, w, b, (__nv_bfloat16*)y, n, H, W, 0);
+  return lnst_status();
+}
+extern "C" int lnst_conv_first_fwd_x3(const float* x, const float* w, const float* b, void* y, int32_t n, int32_t H,
+                                      int32_t W, void* stream) {
+  if (!x || !w || !y || n < 1 || H < 1 || W < 1) return LNST_EARG;
+  const int64_t threads = (int64_t)n * H * ((W + tc::FP - 1) / tc::FP) * 8;
+  tc::conv_first_fwd_k<<<lnst_blocks(threads, 256), 256, 0, lnst_stream(stream)>>>(x, w, b, (__nv_bfloat16*)y, n, H, W, 1);
   return lnst_status();
 }
 
@@ -1564,7 +1761,15 @@ extern "C" int lnst_conv_first_fwd_gray(const float* gray, const float* ws, cons
   if (!gray || !ws || !wm || !bsum || !y || n < 1 || H < 1 || W < 1) return LNST_EARG;
   const int64_t threads = (int64_t)n * H * ((W + tc::FP - 1) / tc::FP) * 8;
   tc::conv_first_fwd_gray_k<<<lnst_blocks(threads, 256), 256, 0, lnst_stream(stream)>>>(gray, ws, wm, bsum,
-                                                                                       (__nv_bfloat16*)y, n, H, W);
+                                                                                       (__nv_bfloat16*)y, n, H, W, 0);
+  return lnst_status();
+}
+extern "C" int lnst_conv_first_fwd_gray_x3(const float* gray, const float* ws, const float* wm, const float* bsum,
+                                           void* y, int32_t n, int32_t H, int32_t W, void* stream) {
+  if (!gray || !ws || !wm || !bsum || !y || n < 1 || H < 1 || W < 1) return LNST_EARG;
+  const int64_t threads = (int64_t)n * H * ((W + tc::FP - 1) / tc::FP) * 8;
+  tc::conv_first_fwd_gray_k<<<lnst_blocks(threads, 256), 256, 0, lnst_stream(stream)>>>(gray, ws, wm, bsum,
+                                                                                       (__nv_bfloat16*)y, n, H, W, 1);
   return lnst_status();
 }
 
@@ -1612,6 +1817,20 @@ extern "C" int lnst_conv_first_bwd_gray_tc(const void* g, const void* wd16, floa
                                    lnst_stream(stream), 1);
 }
 
+// split (bf16x3) variants: g bf16 [n,H,W,128] = [hi | lo], wd16 bf16 [9,16,128] = [hi | lo] rows
+extern "C" int lnst_conv_first_bwd_x3_tc(const void* g, const void* wd16, float* gx, int32_t n, int32_t H, int32_t W,
+                                         void* stream) {
+  if (!g || !wd16 || !gx || n < 1 || H < 1 || W < 1) return LNST_EARG;
+  return tc::launch_halo<16, true>(g, wd16, nullptr, nullptr, nullptr, gx, n, H, W, 64, 16, 0, 1.0f,
+                                   lnst_stream(stream), 3, 1);
+}
+extern "C" int lnst_conv_first_bwd_gray_x3_tc(const void* g, const void* wd16, float* g_gray, int32_t n, int32_t H,
+                                              int32_t W, void* stream) {
+  if (!g || !wd16 || !g_gray || n < 1 || H < 1 || W < 1) return LNST_EARG;
+  return tc::launch_halo<16, true>(g, wd16, nullptr, nullptr, nullptr, g_gray, n, H, W, 64, 16, 0, 1.0f,
+                                   lnst_stream(stream), 1, 1);
+}
+
 extern "C" int lnst_set_conv_persistent(int32_t on) { tc::conv_persistent = on ? 1 : 0; return LNST_OK; }
 
 extern "C" int lnst_tc_supported(void) { return tc::encode_fn() != nullptr ? 1 : 0; }
@@ -1620,7 +1839,7 @@ extern "C" int lnst_tc_supported(void) { return tc::encode_fn() != nullptr ? 1 :
 // (taps = 1, one B matrix per image)
 static int run_tc_gemm(const void* x, const void* wmat, const float* bias, const void* mask, const void* addend,
                        void* y, int n, int H, int W, int Cin, int Cout, int relu, int taps, int w_img, float scale,
-                       void* stream) {
+                       void* stream, int split = 0) {
   using namespace tc;
   if (!x || !wmat || !y || n < 1 || H < 1 || W < 1 || Cin < 64 || Cout < 64 || Cin % 64 || Cout % 64)
     return LNST_EARG;
@@ -1630,31 +1849,35 @@ static int run_tc_gemm(const void* x, const void* wmat, const float* bias, const
   // per-tap kernel on every layer (tools/convbench.py, 18 images: conv2_2 45.5 vs 59.0 us, conv3_1 28.0 vs 35.5),
   // whose 32 KiB of TMA writes per k-step compete with the MMAs' own operand reads for shared-memory bandwidth.
   const int bn_ = (Cout % 128 == 0) ? 128 : 64;
-  const bool resident = (Cout == bn_) && (9 * (Cin / 64) * bn_ * 128 + 3 * PATCH_STRIDE <= 232448 - 2048 - 1024 - 512 - (bn_ >= 128 ? 8192 : 0) - 128);
-  if (taps == 9 && !w_img && !addend && conv_halo && (resident || conv_halo == 2)) {
+  const int wch = (split ? 2 : 1) * (Cin / 64);
+  const bool resident = (Cout == bn_) && (9 * wch * bn_ * 128 + 3 * PATCH_STRIDE <= 232448 - 2048 - 1024 - 512 - (bn_ >= 128 ? 8192 : 0) - 128);
+  if (taps == 9 && !w_img && !addend && (split || (conv_halo && (resident || conv_halo == 2)))) {
     if (Cout % 128 == 0)
       return launch_halo<128, false>(x, wmat, bias, (const __nv_bfloat16*)mask, (__nv_bfloat16*)y, nullptr, n, H, W,
-                                     Cin, Cout, relu, scale, lnst_stream(stream));
+                                     Cin, Cout, relu, scale, lnst_stream(stream), 3, split);
     return launch_halo<64, false>(x, wmat, bias, (const __nv_bfloat16*)mask, (__nv_bfloat16*)y, nullptr, n, H, W, Cin,
-                                  Cout, relu, scale, lnst_stream(stream));
+                                  Cout, relu, scale, lnst_stream(stream), 3, split);
   }
+  if (split && (!conv_persistent || taps != 1)) return LNST_EARG;    // split operands: halo kernel, or the persistent per-pixel GEMM
   ConvShape s;
   s.H = H; s.W = W; s.Cin = Cin; s.Cout = Cout; s.relu = relu;
   s.taps = taps; s.w_img = w_img; s.scale = scale; s.out_ch = 3;
+  if (split) shape_split(s); else shape_plain(s);
+  const int xC = split ? 2 * Cin : Cin;
   pick_tile(H, W, s.TH, s.TW);
   s.tiles_w = (W + s.TW - 1) / s.TW;
   s.tiles_h = (H + s.TH - 1) / s.TH;
   const int BN = (Cout % 128 == 0) ? 128 : 64;
   CUtensorMap mx, mw;
   {
-    const cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n};
-    const cuuint64_t strides[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2};
+    const cuuint64_t dims[4] = {(cuuint64_t)xC, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n};
+    const cuuint64_t strides[3] = {(cuuint64_t)xC * 2, (cuuint64_t)W * xC * 2, (cuuint64_t)H * W * xC * 2};
     const cuuint32_t box[4] = {(cuuint32_t)BLOCK_K, (cuuint32_t)s.TW, (cuuint32_t)s.TH, 1};
     if (!make_map(&mx, x, 4, dims, strides, box)) return LNST_EARG;
   }
   {
-    const cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)Cout, (cuuint64_t)(w_img ? n : taps)};
-    const cuuint64_t strides[2] = {(cuuint64_t)Cin * 2, (cuuint64_t)Cout * Cin * 2};
+    const cuuint64_t dims[3] = {(cuuint64_t)xC, (cuuint64_t)Cout, (cuuint64_t)(w_img ? n : taps)};
+    const cuuint64_t strides[2] = {(cuuint64_t)xC * 2, (cuuint64_t)Cout * xC * 2};
     const cuuint32_t box[3] = {(cuuint32_t)BLOCK_K, (cuuint32_t)BN, 1};
     if (!make_map(&mw, wmat, 3, dims, strides, box)) return LNST_EARG;
   }
@@ -1669,6 +1892,20 @@ extern "C" int lnst_conv3x3_bf16_tc(const void* x, const void* w_packed, const f
                                     void* y, int32_t n, int32_t H, int32_t W, int32_t Cin, int32_t Cout,
                                     int32_t relu, void* stream) {
   return run_tc_gemm(x, w_packed, bias, mask, nullptr, y, n, H, W, Cin, Cout, relu, 9, 0, 1.0f, stream);
+}
+
+// bf16x3: x [n,H,W,2*Cin] = [hi | lo], w_packed [9, Cout, 2*Cin] = [Whi | Wlo], mask (ReLU mask of the layer below) and
+// y [n,H,W,2*Cout] split rows.  Three K passes (hi*hi, lo*hi, hi*lo) into one fp32 accumulator (ConvShape).
+extern "C" int lnst_conv3x3_bf16x3_tc(const void* x, const void* w_packed, const float* bias, const void* mask,
+                                      void* y, int32_t n, int32_t H, int32_t W, int32_t Cin, int32_t Cout,
+                                      int32_t relu, void* stream) {
+  return run_tc_gemm(x, w_packed, bias, mask, nullptr, y, n, H, W, Cin, Cout, relu, 9, 0, 1.0f, stream, 1);
+}
+// F split [n,H,W,2C], Gd2 bf16 [n,C,2C] = [hi | lo] of the (symmetric) Gram difference, addend / g split rows
+extern "C" int lnst_gram_bwd_bf16x3_tc(const void* F, const void* Gd2, float coef, const void* addend,
+                                       int32_t relu_mask, void* g, int32_t n, int32_t H, int32_t W, int32_t C,
+                                       void* stream) {
+  return run_tc_gemm(F, Gd2, nullptr, relu_mask ? F : nullptr, addend, g, n, H, W, C, C, 0, 1, 1, coef, stream, 1);
 }
 
 // Gram-loss gradient on tensor cores: g[img] = (addend + coef * F[img] x Gd[img]) * (F > 0 if relu_mask).
@@ -1715,6 +1952,52 @@ extern "C" int lnst_gram_diff_bf16_tc(const void* F, int32_t n, int64_t P, int32
   const int n_el = C * C;
   const unsigned nb = lnst_blocks(n_el, 256) > 32 ? 32 : lnst_blocks(n_el, 256);
   gram_finish_bf16_k<<<dim3(nb, n), 256, 0, st>>>(G, Gs, (__nv_bfloat16*)Gd, n_el, 1.f / denom, weight, loss);
+  return lnst_status();
+}
+
+// Split features F bf16 [n,P,2C]: the 2C x 2C Gram of the split rows (same tensor-core kernel) lands in the scratch G2
+// [n,2C,2C] fp32 and its four blocks are folded into F^T F (hi*hi + hi*lo + lo*hi + lo*lo); G [n,C,C] fp32 = that / denom
+// - Gs, Gd2 [n,C,2C] its split copy, loss[i] += weight * sum(G[i]^2).
+extern "C" int lnst_gram_diff_bf16x3_tc(const void* F, int32_t n, int64_t P, int32_t C, float denom, const float* Gs,
+                                        float weight, float* G2, float* G, void* Gd2, float* loss, void* stream) {
+  if (!G2 || !G) return LNST_EARG;
+  const int rc = lnst_gram_diff_bf16_tc(F, n, P, 2 * C, 1.0f, nullptr, 0.f, G2, nullptr, nullptr, stream);
+  if (rc != 0) return rc;
+  const int n_el = C * C;
+  const unsigned nb = lnst_blocks(n_el, 256) > 32 ? 32 : lnst_blocks(n_el, 256);
+  tc::gram_finish_split_k<<<dim3(nb, n), 256, 0, lnst_stream(stream)>>>(G2, G, Gs, (__nv_bfloat16*)Gd2, (int)C,
+                                                                        1.f / denom, weight, loss);
+  return lnst_status();
+}
+
+extern "C" int lnst_avgpool2_bf16x3_fwd(const void* x, void* y, int32_t n, int32_t H, int32_t W, int32_t C,
+                                        void* stream) {
+  if (!x || !y || n < 1 || H < 2 || W < 2 || C < 8 || C % 8) return LNST_EARG;
+  const int64_t total = (int64_t)n * (H / 2) * (W / 2) * (C / 8);
+  if (total >= 0x7fffffff) return LNST_EARG;
+  tc::avgpool2_split_fwd_k<<<lnst_blocks(total, 256), 256, 0, lnst_stream(stream)>>>(
+      (const __nv_bfloat16*)x, (__nv_bfloat16*)y, n, H, W, C);
+  return lnst_status();
+}
+extern "C" int lnst_avgpool2_bf16x3_bwd(const void* g_y, const void* mask, void* g_x, int32_t n, int32_t H, int32_t W,
+                                        int32_t C, void* stream) {
+  if (!g_y || !g_x || n < 1 || H < 2 || W < 2 || C < 8 || C % 8) return LNST_EARG;
+  const int64_t total = (int64_t)n * ((H + 1) / 2) * ((W + 1) / 2) * (C / 8);
+  if (total >= 0x7fffffff) return LNST_EARG;
+  tc::avgpool2_split_bwd_k<<<lnst_blocks(total, 256), 256, 0, lnst_stream(stream)>>>(
+      (const __nv_bfloat16*)g_y, (const __nv_bfloat16*)mask, (__nv_bfloat16*)g_x, n, H, W, C);
+  return lnst_status();
+}
+extern "C" int lnst_f32_to_bf16x3(const float* x, void* y, int64_t rows, int32_t C, void* stream) {
+  if (!x || !y || rows < 0 || C < 2 || C % 2) return LNST_EARG;
+  if (rows == 0) return LNST_OK;
+  tc::f32_to_split_k<<<lnst_blocks(rows * (C / 2), 256), 256, 0, lnst_stream(stream)>>>(x, (__nv_bfloat16*)y, rows, C);
+  return lnst_status();
+}
+extern "C" int lnst_bf16x3_to_f32(const void* x, float* y, int64_t rows, int32_t C, void* stream) {
+  if (!x || !y || rows < 0 || C < 2 || C % 2) return LNST_EARG;
+  if (rows == 0) return LNST_OK;
+  tc::split_to_f32_k<<<lnst_blocks(rows * (C / 2), 256), 256, 0, lnst_stream(stream)>>>((const __nv_bfloat16*)x, y, rows, C);
   return lnst_status();
 }
 

@@ -13,13 +13,18 @@
 
 struct G2PDims { int n[3]; int dim; };
 
-// transform.py:972-978 (_hermite): Catmull-Rom through B..C with tangents from A and D; same
-// operation order as the reference so that fp32 round-off matches to the last bits.
+// transform.py:972-978 (_hermite): Catmull-Rom through B..C with tangents from A and D.  TensorFlow evaluates the
+// expression one op at a time (every product and sum rounded to fp32), so the arithmetic is written with
+// __fmul_rn/__fadd_rn: nvcc's default FMA contraction skips the rounding of the products and moved the 3-D cubic
+// gather 3.4e-6 (relative) away from the reference vectors on the B200 while the CPU interpreter matched them.
 __device__ __forceinline__ float g2p_hermite(float A, float B, float C, float D, float t) {
-  const float a = A * (-0.5f) + B * 1.5f + C * (-1.5f) + D * 0.5f;
-  const float b = A + B * (-2.5f) + C * 2.0f + D * (-0.5f);
-  const float c = A * (-0.5f) + C * 0.5f;
-  return a * t * t * t + b * t * t + c * t + B;
+  const float a = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(A, -0.5f), __fmul_rn(B, 1.5f)), __fmul_rn(C, -1.5f)),
+                            __fmul_rn(D, 0.5f));
+  const float b = __fadd_rn(__fadd_rn(__fadd_rn(A, __fmul_rn(B, -2.5f)), __fmul_rn(C, 2.0f)), __fmul_rn(D, -0.5f));
+  const float c = __fadd_rn(__fmul_rn(A, -0.5f), __fmul_rn(C, 0.5f));
+  const float at3 = __fmul_rn(__fmul_rn(__fmul_rn(a, t), t), t);
+  const float bt2 = __fmul_rn(__fmul_rn(b, t), t);
+  return __fadd_rn(__fadd_rn(__fadd_rn(at3, bt2), __fmul_rn(c, t)), B);
 }
 
 // Clamped tap indices and the fractional offset of one axis (transform.py:812-838 cubic, :1144-1162 linear).
@@ -27,7 +32,7 @@ __device__ __forceinline__ float g2p_hermite(float A, float B, float C, float D,
 // `dx = x - (x1 + 0.5)`, :999 / :1200), so particles outside the grid extrapolate; restated as is.
 template <int TAPS>
 __device__ __forceinline__ float g2p_axis(float pos01, int len, int* idx) {
-  const float x = pos01 * (float)len;
+  const float x = __fmul_rn(pos01, (float)len);   // rounded product: floorf(x - 0.5f) must not see an FMA
   const int f = (int)floorf(x - 0.5f);
   const int first = TAPS == 4 ? f - 1 : f;
 #pragma unroll
@@ -60,13 +65,13 @@ __device__ __forceinline__ void g2p_sample(const float* __restrict__ g, const G2
       for (int a = 0; a < 2; ++a)
 #pragma unroll
         for (int b = 0; b < 2; ++b) {
-          const float wab = (a ? tx : 1.f - tx) * (b ? ty : 1.f - ty);
+          const float wab = __fmul_rn(a ? tx : 1.f - tx, b ? ty : 1.f - ty);
           if (DIM == 3) {
 #pragma unroll
             for (int e = 0; e < 2; ++e)
-              o += wab * (e ? tz : 1.f - tz) * g[(ix[a] * s0 + iy[b] * s1 + iz[e]) * C + c];
+              o = __fadd_rn(o, __fmul_rn(__fmul_rn(wab, e ? tz : 1.f - tz), g[(ix[a] * s0 + iy[b] * s1 + iz[e]) * C + c]));
           } else {
-            o += wab * g[(ix[a] * s0 + iy[b] * s1) * C + c];
+            o = __fadd_rn(o, __fmul_rn(wab, g[(ix[a] * s0 + iy[b] * s1) * C + c]));
           }
         }
       out[c] = o;
@@ -75,7 +80,7 @@ __device__ __forceinline__ void g2p_sample(const float* __restrict__ g, const G2
       // planes are walked one at a time (16 loads in flight, a rotating 4-entry window of plane results):
       // fully unrolled, the 64 taps x 64-bit addresses need > 255 registers.
       float Iz0 = 0.f, Iz1 = 0.f, Iz2 = 0.f, Iz3 = 0.f;
-      const int zfirst = (int)floorf(pos[2] * (float)d.n[2] - 0.5f) - 1;
+      const int zfirst = (int)floorf(__fmul_rn(pos[2], (float)d.n[2]) - 0.5f) - 1;
 #pragma unroll 1
       for (int e = 0; e < 4; ++e) {
         const int ze = min(max(zfirst + e, 0), d.n[2] - 1);
@@ -131,18 +136,18 @@ __global__ void __launch_bounds__(128) rk4_advect_k(const float* __restrict__ u,
   for (int k = 0; k < DIM; ++k) x0[k] = x[i * DIM + k];
   g2p_sample<DIM, LINEAR>(u, d, DIM, DIM, x0, v);
 #pragma unroll
-  for (int k = 0; k < DIM; ++k) xs[k] = x0[k] + v[k] * 0.5f;
+  for (int k = 0; k < DIM; ++k) xs[k] = __fadd_rn(x0[k], __fmul_rn(v[k], 0.5f));
   g2p_sample<DIM, LINEAR>(u, d, DIM, DIM, xs, v1);
 #pragma unroll
-  for (int k = 0; k < DIM; ++k) xs[k] = x0[k] + v1[k] * 0.5f;
+  for (int k = 0; k < DIM; ++k) xs[k] = __fadd_rn(x0[k], __fmul_rn(v1[k], 0.5f));
   g2p_sample<DIM, LINEAR>(u, d, DIM, DIM, xs, v2);
 #pragma unroll
   for (int k = 0; k < DIM; ++k) xs[k] = x0[k] + v2[k];
   g2p_sample<DIM, LINEAR>(u, d, DIM, DIM, xs, v3);
 #pragma unroll
   for (int k = 0; k < DIM; ++k) {
-    const float vm = (v[k] + v1[k] * 2.f + v2[k] * 2.f + v3[k]) / 6.f;
-    x_adv[i * DIM + k] = x0[k] + vm * time_step;
+    const float vm = __fdiv_rn(__fadd_rn(__fadd_rn(__fadd_rn(v[k], __fmul_rn(v1[k], 2.f)), __fmul_rn(v2[k], 2.f)), v3[k]), 6.f);
+    x_adv[i * DIM + k] = __fadd_rn(x0[k], __fmul_rn(vm, time_step));
     if (v_out) v_out[i * DIM + k] = vm;
   }
 }

@@ -92,6 +92,21 @@ __global__ void rotate_fwd_k(const float* __restrict__ vol, const float* __restr
   out[view * V + t] = sample8(vol, c, v);
 }
 
+// gradient of rotate() w.r.t. the volume: the 8-corner scatter-add of every rotated sample's cotangent
+// (TF: gather gradient = unsorted_segment_sum, transform.py:385-428); g_vol accumulates over all views
+__global__ void rotate_bwd_k(const float* __restrict__ g_out, const float* __restrict__ rot, VolDims v,
+                             float* __restrict__ g_vol) {
+  const int64_t V = (int64_t)v.D * v.H * v.W;
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= V) return;
+  const int view = blockIdx.y;
+  const float g = g_out[view * V + t];
+  if (g == 0.f) return;
+  const int w = (int)(t % v.W), h = (int)((t / v.W) % v.H), i = (int)(t / ((int64_t)v.W * v.H));
+  const Corner8 c = rotate_sample(rot + 9 * view, lin_coord(i, v.sD), lin_coord(h, v.sH), lin_coord(w, v.sW), v);
+  scatter8(g_vol, c, v, g);
+}
+
 // one thread per pixel column (view, h, w); marches from the camera side (high D) down
 __global__ void raymarch_fwd_k(const float* __restrict__ vol, const float* __restrict__ rot, VolDims v,
                                SubVol sv, float tau, int liquid, float* __restrict__ img,
@@ -792,6 +807,16 @@ extern "C" int lnst_rotate_fwd(const float* vol, const float* rot, int32_t n_vie
   const int64_t V = (int64_t)D * H * W;
   LNST_LAUNCH(rotate_fwd_k, dim3(lnst_blocks(V, 256), n_views), dim3(256), 0, lnst_stream(stream), vol, rot,
               v, out);
+  return lnst_status();
+}
+
+extern "C" int lnst_rotate_bwd(const float* g_out, const float* rot, int32_t n_views, int32_t D, int32_t H,
+                               int32_t W, float* g_vol, void* stream) {
+  if (!g_out || !rot || !g_vol || n_views < 1 || D < 1 || H < 1 || W < 1) return LNST_EARG;
+  const VolDims v = make_dims(D, H, W);
+  const int64_t V = (int64_t)D * H * W;
+  LNST_LAUNCH(rotate_bwd_k, dim3(lnst_blocks(V, 256), n_views), dim3(256), 0, lnst_stream(stream), g_out, rot,
+              v, g_vol);
   return lnst_status();
 }
 

@@ -88,6 +88,9 @@ SIGNATURES = {
     'lnst_rk4_advect': [vp, i32, IP, vp, i64, f32, i32, vp, vp, vp],
     'lnst_pressure_loss': [vp, i64, f32, f32, vp, vp, vp],
     'lnst_sub_fliph': [vp, vp, vp, i32, i32, i32, vp],
+    'lnst_pressure_reg': [vp, i64, f32, f32, f32, vp, i32, vp, vp],
+    'lnst_density_reg': [vp, i64, f32, f32, vp, vp, i32, vp, vp],
+    'lnst_rotate_bwd': [vp, vp, i32, i32, i32, i32, vp, vp],
     'lnst_conv2d_f32': [vp, vp, vp, vp] + [i32] * 14 + [vp],
     'lnst_conv2d_bwd_data_f32': [vp, vp, i32, vp, vp] + [i32] * 13 + [vp],
     'lnst_relu_fwd': [vp, vp, i64, vp],
@@ -117,6 +120,17 @@ CUDA_ONLY = {
     'lnst_conv_first_bwd': [vp, vp, vp, i32, i32, i32, vp],
     'lnst_avgpool2_bf16_fwd': [vp, vp, i32, i32, i32, i32, vp],
     'lnst_avgpool2_bf16_bwd': [vp, vp, vp, i32, i32, i32, i32, vp],
+    'lnst_conv3x3_bf16x3_tc': [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp],
+    'lnst_gram_diff_bf16x3_tc': [vp, i32, i64, i32, f32, vp, f32, vp, vp, vp, vp, vp],
+    'lnst_gram_bwd_bf16x3_tc': [vp, vp, f32, vp, i32, vp, i32, i32, i32, i32, vp],
+    'lnst_conv_first_fwd_x3': [vp, vp, vp, vp, i32, i32, i32, vp],
+    'lnst_conv_first_fwd_gray_x3': [vp, vp, vp, vp, vp, i32, i32, i32, vp],
+    'lnst_conv_first_bwd_x3_tc': [vp, vp, vp, i32, i32, i32, vp],
+    'lnst_conv_first_bwd_gray_x3_tc': [vp, vp, vp, i32, i32, i32, vp],
+    'lnst_avgpool2_bf16x3_fwd': [vp, vp, i32, i32, i32, i32, vp],
+    'lnst_avgpool2_bf16x3_bwd': [vp, vp, vp, i32, i32, i32, i32, vp],
+    'lnst_f32_to_bf16x3': [vp, vp, i64, i32, vp],
+    'lnst_bf16x3_to_f32': [vp, vp, i64, i32, vp],
     'lnst_f32_to_bf16': [vp, vp, i64, vp],
     'lnst_bf16_to_f32': [vp, vp, i64, vp],
 }
@@ -139,6 +153,10 @@ class Lib:
             fn = getattr(self.dll, name)
             fn.argtypes = args
             fn.restype = C.c_int
+        self.dll.lnst_version.restype = C.c_char_p
+        self.dll.lnst_version.argtypes = []
+        self.dll.lnst_workspace_bytes.restype = C.c_int64
+        self.dll.lnst_workspace_bytes.argtypes = [C.c_char_p, C.POINTER(C.c_int64), i32]
         self.has_tc = False
         if kind == 'cuda' and hasattr(self.dll, 'lnst_tc_supported'):
             for name, args in CUDA_ONLY.items():
@@ -148,6 +166,13 @@ class Lib:
             self.has_tc = True
         if self.dll.lnst_abi_version() != 1:
             raise LnstError('ABI version mismatch in %s' % path)
+
+    def version(self):
+        return self.dll.lnst_version().decode()
+
+    def workspace_bytes(self, op, dims=()):
+        arr = (C.c_int64 * max(len(dims), 1))(*[int(d) for d in dims])
+        return int(self.dll.lnst_workspace_bytes(op.encode(), arr, len(dims)))
 
     def call(self, name, *args):
         rc = getattr(self.dll, name)(*args)
@@ -223,3 +248,30 @@ def make_grid(dim, res, domain, nsize, clip):
     g.nsize = int(nsize)
     g.clip = 1 if clip else 0
     return g
+
+
+class _Range:
+    """NVTX range around one stage of the step (tracing).  Off unless LNST_NVTX=1 or
+    ``enable_nvtx(True)``: under CUDA-graph replay the ranges would only mark the capture."""
+    enabled = os.environ.get('LNST_NVTX', '') not in ('', '0')
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if _Range.enabled and torch.cuda.is_available():
+            torch.cuda.nvtx.range_push(self.name)
+        return self
+
+    def __exit__(self, *exc):
+        if _Range.enabled and torch.cuda.is_available():
+            torch.cuda.nvtx.range_pop()
+        return False
+
+
+def nvtx(name):
+    return _Range(name)
+
+
+def enable_nvtx(on=True):
+    _Range.enabled = bool(on)

@@ -113,6 +113,15 @@ def rotate_fwd(vol, rot):
     return out
 
 
+def rotate_bwd(g_out, rot, g_vol=None):
+    """d loss / d vol of ``rotate_fwd``: 8-corner scatter of g_out [nv,D,H,W], summed over the views"""
+    nv, D, H, W = g_out.shape
+    if g_vol is None:
+        g_vol = torch.zeros(D, H, W, dtype=f32, device=g_out.device)
+    _lib.get().call('lnst_rotate_bwd', ptr(g_out), ptr(rot), nv, D, H, W, ptr(g_vol), _s(g_out))
+    return g_vol
+
+
 def _u8(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 
@@ -382,6 +391,19 @@ def pressure_loss(d_rec, rest_density, weight, loss, g_d=None):
                     ptr(g_d), _s(d_rec))
 
 
+def pressure_reg(d, rest_density, w_mean, g_scale, loss, n_loss, g_d):
+    """loss[:n_loss] += w_mean * mean(pr^2); g_d += g_scale * pr, pr = where(d > 0, d - rho0, 0) (styler_3p.py:96-98)"""
+    _lib.get().call('lnst_pressure_reg', ptr(d), d.numel(), float(rest_density), float(w_mean), float(g_scale), ptr(loss),
+                    int(n_loss), ptr(g_d), _s(d))
+
+
+def density_reg(var, weight, g_weight, loss, n_loss, grad):
+    """styler_base.py:217-223 on clip(var, -1, 1): loss[:n_loss] += weight * (...); grad += g_weight * d(...)/d var"""
+    sums = torch.empty(2, dtype=f32, device=var.device)
+    _lib.get().call('lnst_density_reg', ptr(var), var.numel(), float(weight), float(g_weight), ptr(sums), ptr(loss),
+                    int(n_loss), ptr(grad), _s(var))
+
+
 def sub_fliph(a, b, out=None):
     """a - flip_H(b) for [D,H,W] volumes"""
     D, H, W = a.shape
@@ -604,4 +626,94 @@ def to_bf16(x):
 def to_f32(x):
     y = torch.empty(x.shape, dtype=f32, device=x.device)
     _lib.get().call('lnst_bf16_to_f32', ptr(x), ptr(y), x.numel(), _s(x))
+    return y
+
+
+# ---- bf16x3 ("split") tensor-core path: rows carry [hi | lo] bf16 halves of every fp32 value (csrc/conv_tc.cu ConvShape)
+def conv3x3_bf16x3_tc(x, w_packed2, bias, relu, mask=None):
+    """x bf16 [n,H,W,2*Cin] split, w_packed2 bf16 [9,Cout,2*Cin] = [Whi | Wlo] -> y bf16 [n,H,W,2*Cout] split"""
+    n, H, W, c2 = x.shape
+    cout = w_packed2.shape[1]
+    y = torch.empty(n, H, W, 2 * cout, dtype=bf16, device=x.device)
+    _lib.get().call('lnst_conv3x3_bf16x3_tc', ptr(x), ptr(w_packed2), ptr(bias), ptr(mask), ptr(y), n, H, W, c2 // 2,
+                    cout, int(relu), _s(x))
+    return y
+
+
+def gram_diff_bf16x3_tc(F, denom, Gs, weight, loss):
+    """F split bf16 [n,h,w,2C] -> (G fp32 [n,C,C] = F^T F/denom - Gs, Gd2 bf16 [n,C,2C] split); loss[n] += weight*sum(G^2)"""
+    n, h, w, c2 = F.shape
+    ch = c2 // 2
+    G2 = torch.empty(n, c2, c2, dtype=f32, device=F.device)
+    G = torch.empty(n, ch, ch, dtype=f32, device=F.device)
+    Gd2 = torch.empty(n, ch, c2, dtype=bf16, device=F.device)
+    _lib.get().call('lnst_gram_diff_bf16x3_tc', ptr(F), n, h * w, ch, float(denom), ptr(Gs), float(weight), ptr(G2),
+                    ptr(G), ptr(Gd2), ptr(loss), _s(F))
+    return G, Gd2
+
+
+def gram_bwd_bf16x3_tc(F, Gd2, coef, addend, relu_mask, g=None):
+    n, h, w, c2 = F.shape
+    if g is None:
+        g = torch.empty_like(F)
+    _lib.get().call('lnst_gram_bwd_bf16x3_tc', ptr(F), ptr(Gd2), float(coef), ptr(addend), int(relu_mask), ptr(g), n, h,
+                    w, c2 // 2, _s(F))
+    return g
+
+
+def conv_first_fwd_x3(x, w, b):
+    n, H, W, _ = x.shape
+    y = torch.empty(n, H, W, 128, dtype=bf16, device=x.device)
+    _lib.get().call('lnst_conv_first_fwd_x3', ptr(x), ptr(w), ptr(b), ptr(y), n, H, W, _s(x))
+    return y
+
+
+def conv_first_fwd_gray_x3(gray, ws, wm, bsum):
+    n, H, W = gray.shape
+    y = torch.empty(n, H, W, 128, dtype=bf16, device=gray.device)
+    _lib.get().call('lnst_conv_first_fwd_gray_x3', ptr(gray), ptr(ws), ptr(wm), ptr(bsum), ptr(y), n, H, W, _s(gray))
+    return y
+
+
+def conv_first_bwd_x3_tc(g, wd16_2):
+    n, H, W, _ = g.shape
+    gx = torch.empty(n, H, W, 3, dtype=f32, device=g.device)
+    _lib.get().call('lnst_conv_first_bwd_x3_tc', ptr(g), ptr(wd16_2), ptr(gx), n, H, W, _s(g))
+    return gx
+
+
+def conv_first_bwd_gray_x3_tc(g, wd16_gray2):
+    n, H, W, _ = g.shape
+    gg = torch.empty(n, H, W, dtype=f32, device=g.device)
+    _lib.get().call('lnst_conv_first_bwd_gray_x3_tc', ptr(g), ptr(wd16_gray2), ptr(gg), n, H, W, _s(g))
+    return gg
+
+
+def avgpool2_bf16x3_fwd(x):
+    n, H, W, c2 = x.shape
+    y = torch.empty(n, H // 2, W // 2, c2, dtype=bf16, device=x.device)
+    _lib.get().call('lnst_avgpool2_bf16x3_fwd', ptr(x), ptr(y), n, H, W, c2 // 2, _s(x))
+    return y
+
+
+def avgpool2_bf16x3_bwd(g_y, mask, shape):
+    n, H, W, c2 = shape
+    g_x = torch.empty(n, H, W, c2, dtype=bf16, device=g_y.device)
+    _lib.get().call('lnst_avgpool2_bf16x3_bwd', ptr(g_y), ptr(mask), ptr(g_x), n, H, W, c2 // 2, _s(g_y))
+    return g_x
+
+
+def to_split(x):
+    """fp32 [..., C] -> bf16 [..., 2C] = [hi | lo]"""
+    C_ = x.shape[-1]
+    y = torch.empty(tuple(x.shape[:-1]) + (2 * C_,), dtype=bf16, device=x.device)
+    _lib.get().call('lnst_f32_to_bf16x3', ptr(x), ptr(y), x.numel() // C_, C_, _s(x))
+    return y
+
+
+def from_split(x):
+    """bf16 [..., 2C] split -> fp32 [..., C] = hi + lo"""
+    C_ = x.shape[-1] // 2
+    y = torch.empty(tuple(x.shape[:-1]) + (C_,), dtype=f32, device=x.device)
+    _lib.get().call('lnst_bf16x3_to_f32', ptr(x), ptr(y), x.numel() // (2 * C_), C_, _s(x))
     return y

@@ -18,8 +18,8 @@ from .vgg import _R_MEAN, _G_MEAN, _B_MEAN
 class Styler(StylerBase):
     def __init__(self, self_dict, weights=None, device=None, content_weights=None):
         StylerBase.__init__(self, self_dict, weights=weights, device=device, content_weights=content_weights)
-        if self.style_mask and self.conv_math != 'fp32':
-            raise NotImplementedError("style_mask needs conv_math='fp32' (the masked Gram runs on the fp32 path)")
+        if self.style_mask and 'vgg' not in self.model_path:    # style_masks_for reads the VGG block number of a layer
+            raise NotImplementedError('style_mask with a GraphDef loss network')
 
     # ---- graph pieces ----------------------------------------------------------------------------
     def _grid(self, res):

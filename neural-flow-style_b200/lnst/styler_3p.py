@@ -83,8 +83,6 @@ class Styler(StylerBase):
             if self.rotate:
                 raise NotImplementedError('batch_size > 1 with rotate: the reference itself breaks there (styler_3p.py:417 '
                                           'feeds batch_size matrices and rotate() tiles the batch by them)')
-            if self.conv_math != 'fp32' and 'vgg' in self.model_path:
-                raise NotImplementedError("batch_size > 1 needs conv_math='fp32'")
             if self.style_mask:
                 raise NotImplementedError('batch_size > 1 with style_mask')
         if self.target_field not in ('d', 'p'):
@@ -92,8 +90,6 @@ class Styler(StylerBase):
         if 'd' in self.target_field and self.num_kernels > 4:
             raise NotImplementedError('num_kernels > 4')
         if self.style_mask:                                        # styler_base.py:165-169 with d_gray = the render
-            if self.conv_math != 'fp32' and 'vgg' in self.model_path:
-                raise NotImplementedError("style_mask needs conv_math='fp32' (the masked Gram runs on the fp32 path)")
             if 'vgg' not in self.model_path:
                 raise NotImplementedError('style_mask with a GraphDef loss network')
             self.cuda_graphs = False        # the masked areas (Gram denominators) are read back every step
@@ -110,8 +106,6 @@ class Styler(StylerBase):
                 # only (styler_base.py:98 loops over range(batch_size)), content / TV averaged over the group
                 if self.view_mode != 'sequential':
                     raise NotImplementedError("v_batch > 1 is the reference's per-group Adam loop: view_mode='sequential'")
-                if self.conv_math != 'fp32' and 'vgg' in self.model_path:
-                    raise NotImplementedError("v_batch > 1 needs conv_math='fp32'")
                 if self.style_mask:
                     raise NotImplementedError('v_batch > 1 with style_mask')
         self._frame_cache = {}
@@ -250,6 +244,7 @@ class Styler(StylerBase):
         D, H, W = res
         dev = self.device
         nk = self.num_kernels if 'd' in self.target_field else 1
+        self._iv_cache = {}                                        # ray intervals belong to the old workspace's bricks
         ws = {'grid': self._grid(res), 'res': res, 'box': None, 'bricks': None,
               'num': torch.zeros(nk, D * H * W, dtype=f32, device=dev),
               'd': torch.zeros(D, H, W, dtype=f32, device=dev),
@@ -363,11 +358,15 @@ class Styler(StylerBase):
         """Sum over the given views of total_loss, and d(sum)/d var.  Returns (loss [nv], grad).  ``group``: the views
         are ONE fed batch of the reference graph (v_batch > 1): joint normalisation and the group loss weights."""
         res = ws['res']
-        d = self._density(fr, var, res, ws)
+        nvtx = _lib.nvtx
+        with nvtx('lnst.splat_fwd'):
+            d = self._density(fr, var, res, ws)
         box = ws['box']
-        ds = ops.smooth3_relu_fwd(d, ws['ds'], self.k, box)        # styler_3p.py:112-125
+        with nvtx('lnst.smooth_fwd'):
+            ds = ops.smooth3_relu_fwd(d, ws['ds'], self.k, box)    # styler_3p.py:112-125
         gray_path = self._gray_path()
-        st = self._render(ds, rot, box, ws['bricks'], net_input=not gray_path, joint=group)
+        with nvtx('lnst.render_fwd'):
+            st = self._render(ds, rot, box, ws['bricks'], net_input=not gray_path, joint=group)
         nv = st['gray'].shape[0]
         loss = torch.zeros(nv, dtype=f32, device=self.device)
         g_gray0 = None
@@ -388,15 +387,14 @@ class Styler(StylerBase):
                 g_gray0 = gm if g_gray0 is None else ops.axpy(g_gray0, gm, 1.0)
         else:
             g_x = self.image_loss_and_grad(st['x'], st['d_img'], style_grams, loss, group=group)
-        g_ds = ops.fill_box(ws['g_ds'], box, 0.0)
-        self._render_bwd(st, g_x, ds, g_ds, g_gray0)
-        g_d = ops.smooth3_relu_bwd(g_ds, ds, ws['g_d'], self.k, box)
+        with nvtx('lnst.render_bwd'):
+            g_ds = ops.fill_box(ws['g_ds'], box, 0.0)
+            self._render_bwd(st, g_x, ds, g_ds, g_gray0)
+        with nvtx('lnst.smooth_bwd'):
+            g_d = ops.smooth3_relu_bwd(g_ds, ds, ws['g_d'], self.k, box)
         n_terms = 1 if group else nv                               # field / variable terms: once per fed batch
         if self.w_pressure > 0 and 'p' in self.target_field:       # styler_3p.py:96-98, styler_base.py:228-230
-            pos = d > 0
-            pr = torch.where(pos, d - 1, torch.zeros_like(d))
-            loss[:n_terms] += self.w_pressure * (pr * pr).mean()
-            g_d += (n_terms * self.w_pressure * 2.0 / d.numel()) * pr
+            ops.pressure_reg(d, 1.0, self.w_pressure, n_terms * self.w_pressure * 2.0 / d.numel(), loss, n_terms, g_d)
         if 'd' in self.target_field:
             grad = torch.empty_like(var)
             if self.nsize == 1:
@@ -406,10 +404,7 @@ class Styler(StylerBase):
                 ops.splat_wavg_bwd(fr['p'], var, ws['grid'], self._supports(), self._wmap(fr, res, ws['grid']), g_d,
                                    grad)
             if self.w_density > 0:                                 # styler_base.py:217-223
-                dv = torch.clamp(var, -1, 1)
-                inside = ((var >= -1) & (var <= 1)).to(f32)
-                loss[:n_terms] += self.w_density * (dv.sum() ** 2 + 1e3 * (-torch.log(dv.abs() + 1e-6)).sum())
-                grad += n_terms * self.w_density * inside * (2 * dv.sum() - 1e3 * torch.sign(dv) / (dv.abs() + 1e-6))
+                ops.density_reg(var, self.w_density, n_terms * self.w_density, loss, n_terms, grad)
         else:
             scale = 0.8 * (2 * self.radius) ** 3 * self.rest_density / self.rest_density
             grad = ops.splat_sph_bwd_pos(fr['p'], var, ws['grid'], self._supports()[0], scale, g_d)
@@ -482,6 +477,7 @@ class Styler(StylerBase):
                                       torch.empty(1, dtype=f32, device=self.device),
                                       torch.empty(1, B * H, W, dtype=f32, device=self.device)).reshape(B, H, W)
         total = loss.sum()
+        extra = torch.zeros(1, dtype=f32, device=self.device)     # regulariser terms, accumulated by their kernels
         grads = []
         for i, (fr, var) in enumerate(zip(frs, var_list)):
             d, ds = d_list[i], ds_list[i]
@@ -490,9 +486,7 @@ class Styler(StylerBase):
                              g_ds, ws['box'])
             g_d = ops.smooth3_relu_bwd(g_ds, ds, ws['g_d'], self.k, ws['box'])
             if self.w_pressure > 0 and 'p' in self.target_field:   # reduce_mean over the [B,D,H,W,1] pressure tensor
-                pr = torch.where(d > 0, d - 1, torch.zeros_like(d))
-                total = total + self.w_pressure * (pr * pr).mean() / B
-                g_d += (self.w_pressure * 2.0 / (B * d.numel())) * pr
+                ops.pressure_reg(d, 1.0, self.w_pressure / B, self.w_pressure * 2.0 / (B * d.numel()), extra, 1, g_d)
             if 'd' in self.target_field:
                 grad = torch.empty_like(var)
                 if self.nsize == 1:
@@ -502,15 +496,12 @@ class Styler(StylerBase):
                     ops.splat_wavg_bwd(fr['p'], var, ws['grid'], self._supports(), self._wmap(fr, ws['res'], ws['grid']),
                                        g_d, grad)
                 if self.w_density > 0:                             # summed over the batch (styler_base.py:217-223)
-                    dv = torch.clamp(var, -1, 1)
-                    inside = ((var >= -1) & (var <= 1)).to(f32)
-                    total = total + self.w_density * (dv.sum() ** 2 + 1e3 * (-torch.log(dv.abs() + 1e-6)).sum())
-                    grad += self.w_density * inside * (2 * dv.sum() - 1e3 * torch.sign(dv) / (dv.abs() + 1e-6))
+                    ops.density_reg(var, self.w_density, self.w_density, extra, 1, grad)
             else:
                 scale = 0.8 * (2 * self.radius) ** 3 * self.rest_density / self.rest_density
                 grad = ops.splat_sph_bwd_pos(fr['p'], var, ws['grid'], self._supports()[0], scale, g_d)
             grads.append(grad)
-        return total, grads
+        return total + extra[0], grads
 
     def _infer_batch(self, frs, var_list, ws):
         """forward only for a fed batch: (p_out_i, d_out_i, d_img_i) with the batch's joint normalisation"""

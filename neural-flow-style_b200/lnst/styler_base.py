@@ -27,6 +27,17 @@ class StylerBase(object):
             self.view_mode = 'sequential'
         if not hasattr(self, 'conv_math'):
             self.conv_math = 'bf16'
+        if getattr(self, 'w_hist', 0) > 0:
+            raise NotImplementedError('histogram loss (w_hist > 0) is not built: DESIGN.md section 5 (out of scope, '
+                                      'broken at the reference HEAD, styler_base.py:203-207)')
+        # the masked Gram, v_batch groups and fed batches run on the exact fp32 loss-net path only: a reference
+        # config that asks for them (test_dambreak2d.py:190 sets style_mask) gets that path instead of an error
+        if self.conv_math != 'fp32' and 'vgg' in getattr(self, 'network', '') and (
+                getattr(self, 'style_mask', False) or getattr(self, 'batch_size', 1) > 1 or getattr(self, 'v_batch', 1) > 1):
+            import warnings
+            warnings.warn("conv_math=%r -> 'fp32': style_mask / batch_size > 1 / v_batch > 1 run on the fp32 loss-network "
+                          'path' % self.conv_math)
+            self.conv_math = 'fp32'
         lib = _lib.get()                          # raises without the CUDA library / a GPU
         if device is None:
             device = torch.device('cuda', torch.cuda.current_device()) if lib.kind == 'cuda' else torch.device('cpu')

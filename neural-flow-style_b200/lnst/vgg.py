@@ -122,11 +122,11 @@ class LossNet:
             self.b[name] = b.to(device=device, dtype=torch.float32).contiguous()
             # data-gradient weights: flip taps, swap in/out channels (HWIO with I=Cout, O=Cin)
             self.wd[name] = w.flip(0, 1).permute(0, 1, 3, 2).contiguous()
-        if math == 'bf16':
+        if math in ('bf16', 'bf16x3'):
             from . import vgg_tc
-            self.tc = vgg_tc.TensorCoreConvs(self)
+            self.tc = vgg_tc.TensorCoreConvs(self, split=(math == 'bf16x3'))
         elif math != 'fp32':
-            raise ValueError('conv_math must be fp32 or bf16')
+            raise ValueError('conv_math must be fp32, bf16 or bf16x3')
 
     def prefix(self, wanted):
         wanted = [w for w in wanted if w != 'input']
@@ -139,7 +139,7 @@ class LossNet:
     # ---- forward ---------------------------------------------------------------------------
     def forward(self, x, wanted, gray=None):
         """x [n,H,W,3] (mean-subtracted).  Returns {end point: activation [n,h,w,C] fp32}."""
-        if self.math == 'bf16':
+        if self.math != 'fp32':
             return self.tc.forward(x, self.prefix(wanted), gray=gray)
         acts = {}
         cur = x
@@ -158,7 +158,7 @@ class LossNet:
         ``gram_grad`` / ``content`` below and returns the buffer.  Gradients held for conv end
         points are w.r.t. the PRE-activation (ReLU mask already applied).  ``g`` is in the back
         end's native type (fp32 or bf16)."""
-        if self.math == 'bf16':
+        if self.math != 'fp32':
             return self.tc.backward(x, acts, self.prefix(wanted), add_loss_grad, loss_layers, gray=gray)
         layers = self.prefix(wanted)
         g = None
@@ -187,7 +187,7 @@ class LossNet:
         variant of styler_base.py:165-169 -- F_v is the feature times m, den_v = 2 area_v C; m is a constant
         here (2-D colour mode: the density mask does not depend on the colours).  Returns a handle for
         ``gram_grad`` / ``gram_values``."""
-        if self.math == 'bf16':
+        if self.math != 'fp32':
             if mask is not None:
                 raise NotImplementedError("style_mask needs conv_math='fp32'")
             return self.tc.gram(acts, name, Gs, weight, loss)
@@ -209,12 +209,12 @@ class LossNet:
 
     def gram_values(self, handle):
         """fp32 [n,C,C] view of a ``gram`` handle."""
-        return handle[0] if self.math == 'bf16' else torch.stack(handle['G'], 0)
+        return handle[0] if self.math != 'fp32' else torch.stack(handle['G'], 0)
 
     def gram_grad(self, acts, name, handle, coef, g, relu_mask):
         """g <- (g + coef_v * F G) [* (F > 0)] with coef_v = 4 weight / den_v (``coef`` is that value for the
         unmasked denominator; the fp32 handle carries its own); allocates g when None."""
-        if self.math == 'bf16':
+        if self.math != 'fp32':
             return self.tc.gram_grad(acts, name, handle, coef, g, relu_mask)
         f = acts[name]
         n, P, ch = f.shape[0], f.shape[1] * f.shape[2], f.shape[3]
@@ -262,7 +262,7 @@ class LossNet:
     def content(self, acts, name, channel, weight, loss, g, relu_mask, target=None, amp=1.0):
         """Content loss on end point ``name``: channel activation (styler_base.py:143-148), or, with
         ``target`` (the content image's feature, fp32 [h,w,C]), mean((f - target*amp)^2) (:137-141)."""
-        if self.math == 'bf16':
+        if self.math != 'fp32':
             return self.tc.content(acts, name, channel, weight, loss, g, relu_mask, target, amp)
         f = acts[name]
         n, P, ch = f.shape[0], f.shape[1] * f.shape[2], f.shape[3]

@@ -3,7 +3,11 @@ implicit-GEMM convolutions for every layer with >= 64 input and output channels,
 CUDA-core kernels for conv1_1 (K = 27) and its data gradient, tcgen05 Gram matrices (F^T F,
 MN-major operands, split-K) and Gram gradients (F x G, same kernel as the convolution with one
 tap and a per-image B matrix).  Activations and gradients stay bf16 end to end; Gram matrices
-and losses are fp32."""
+and losses are fp32.
+
+``split=True`` (``conv_math='bf16x3'``): the same kernels on [hi | lo] bf16 halves of every value -- three K passes per
+convolution, fp32-tolerance results (csrc/conv_tc.cu ConvShape; include/lnst_b200.h "bf16x3").  Activation tensors
+then have 2C physical channels."""
 import torch
 
 from . import ops
@@ -14,21 +18,36 @@ def _pack(w):
     return w.permute(0, 1, 3, 2).reshape(9, w.shape[3], w.shape[2]).to(torch.bfloat16).contiguous()
 
 
+def _hilo(t):
+    """fp32 [..., K] -> bf16 [..., 2K] = [hi | lo] along the last axis"""
+    t = t.to(torch.float32)
+    hi = t.to(torch.bfloat16)
+    lo = (t - hi.to(torch.float32)).to(torch.bfloat16)
+    return torch.cat([hi, lo], -1).contiguous()
+
+
+def _pack2(w):
+    """HWIO fp32 -> [9, Cout, 2*Cin] bf16 = [Whi | Wlo]"""
+    return _hilo(w.permute(0, 1, 3, 2).reshape(9, w.shape[3], w.shape[2]))
+
+
 class TensorCoreConvs:
-    def __init__(self, net):
+    def __init__(self, net, split=False):
         self.net = net
+        self.split = bool(split)
+        pack = _pack2 if self.split else _pack
         self.wp, self.wdp = {}, {}
         self.first_bwd_tc = True
         self.gray_w = None
         for name, w in net.w.items():
             if w.shape[2] % 64 == 0 and w.shape[3] % 64 == 0:
-                self.wp[name] = _pack(w)
-                self.wdp[name] = _pack(net.wd[name])
+                self.wp[name] = pack(w)
+                self.wdp[name] = pack(net.wd[name])
             elif tuple(w.shape[2:]) == (3, 64):
                 # conv1_1's data gradient (64 -> 3) as a 64 -> 16 tensor-core convolution: rows 3..15 zero
-                wd16 = torch.zeros(9, 16, 64, dtype=torch.bfloat16, device=w.device)
-                wd16[:, :3] = _pack(net.wd[name])
-                self.wd16 = wd16.contiguous()
+                wd16f = torch.zeros(9, 16, 64, dtype=torch.float32, device=w.device)
+                wd16f[:, :3] = net.wd[name].to(torch.float32).permute(0, 1, 3, 2).reshape(9, 3, 64)
+                self.wd16 = _hilo(wd16f) if self.split else wd16f.to(torch.bfloat16).contiguous()
                 # gray render replicated to RGB (styler_base.py:41-43): x_c = 255*g - mean_c is folded into the weights
                 from .vgg import _R_MEAN, _G_MEAN, _B_MEAN
                 mean = torch.tensor([_R_MEAN, _G_MEAN, _B_MEAN], dtype=torch.float32, device=w.device)
@@ -36,10 +55,9 @@ class TensorCoreConvs:
                 wm = (w32 * mean.view(1, 1, 3, 1)).sum(2).reshape(9, 64).contiguous()
                 self.gray_w = ((255.0 * w32.sum(2)).reshape(9, 64).contiguous(), wm,
                                (net.b[name].to(torch.float32) - wm.sum(0)).contiguous())
-                wdg = torch.zeros(9, 16, 64, dtype=torch.bfloat16, device=w.device)
-                wdg[:, 0] = (255.0 * net.wd[name].to(torch.float32).permute(0, 1, 3, 2).reshape(9, 3, 64).sum(1)
-                             ).to(torch.bfloat16)
-                self.wd16_gray = wdg.contiguous()
+                wdg = torch.zeros(9, 16, 64, dtype=torch.float32, device=w.device)
+                wdg[:, 0] = 255.0 * net.wd[name].to(torch.float32).permute(0, 1, 3, 2).reshape(9, 3, 64).sum(1)
+                self.wd16_gray = _hilo(wdg) if self.split else wdg.to(torch.bfloat16).contiguous()
 
     # ---- network ----------------------------------------------------------------------------------
     def forward(self, x, layers, gray=None):
@@ -47,20 +65,24 @@ class TensorCoreConvs:
         Returns the activation store (bf16 tensors, fp32 copies on demand)."""
         acts = {}
         cur = x
+        sp = self.split
         for name in layers:
             if name.startswith('conv'):
                 if name in self.wp and cur.dtype == torch.bfloat16:
-                    cur = ops.conv3x3_bf16_tc(cur, self.wp[name], self.net.b[name], relu=True)
+                    cur = (ops.conv3x3_bf16x3_tc if sp else ops.conv3x3_bf16_tc)(cur, self.wp[name], self.net.b[name],
+                                                                               relu=True)
                 elif gray is not None and name == layers[0] and tuple(self.net.w[name].shape[2:]) == (3, 64):
-                    cur = ops.conv_first_fwd_gray(gray, *self.gray_w)
+                    cur = (ops.conv_first_fwd_gray_x3 if sp else ops.conv_first_fwd_gray)(gray, *self.gray_w)
                 elif cur.dtype == torch.float32 and tuple(self.net.w[name].shape[2:]) == (3, 64):
-                    cur = ops.conv_first_fwd(cur, self.net.w[name], self.net.b[name])
+                    cur = (ops.conv_first_fwd_x3 if sp else ops.conv_first_fwd)(cur, self.net.w[name], self.net.b[name])
+                elif sp:
+                    raise NotImplementedError("conv_math='bf16x3' needs channel counts that are multiples of 64")
                 else:
                     cur = ops.conv3x3_mixed(cur, self.net.w[name], self.net.b[name], relu=True, out_bf16=True)
             else:
-                cur = ops.avgpool2_bf16_fwd(cur)
+                cur = (ops.avgpool2_bf16x3_fwd if sp else ops.avgpool2_bf16_fwd)(cur)
             acts[name] = cur
-        return _Acts(acts)
+        return _Acts(acts, split=sp)
 
     def backward(self, x, acts, layers, add_loss_grad, loss_layers, gray=False):
         g = None                                   # bf16 gradient of the current end point
@@ -73,34 +95,45 @@ class TensorCoreConvs:
             prev = layers[i - 1] if i > 0 else None
             prev_act = acts.raw[prev] if prev is not None else None
             mask = prev_act if (prev is not None and prev.startswith('conv')) else None
+            sp = self.split
             if name.startswith('conv'):
                 if name in self.wdp and prev is not None:
-                    g = ops.conv3x3_bf16_tc(g, self.wdp[name], None, relu=False, mask=mask)
+                    g = (ops.conv3x3_bf16x3_tc if sp else ops.conv3x3_bf16_tc)(g, self.wdp[name], None, relu=False, mask=mask)
                 elif prev is None and gray and tuple(self.net.w[name].shape[2:]) == (3, 64):
-                    g = ops.conv_first_bwd_gray_tc(g, self.wd16_gray)        # d loss / d gray [n,H,W]
+                    g = (ops.conv_first_bwd_gray_x3_tc if sp else ops.conv_first_bwd_gray_tc)(g, self.wd16_gray)  # d loss / d gray
                 elif prev is None and tuple(self.net.w[name].shape[2:]) == (3, 64):
-                    g = ops.conv_first_bwd_tc(g, self.wd16) if self.first_bwd_tc else ops.conv_first_bwd(g, self.net.wd[name])
+                    if sp:
+                        g = ops.conv_first_bwd_x3_tc(g, self.wd16)
+                    else:
+                        g = ops.conv_first_bwd_tc(g, self.wd16) if self.first_bwd_tc else ops.conv_first_bwd(g, self.net.wd[name])
+                elif sp:
+                    raise NotImplementedError("conv_math='bf16x3' needs channel counts that are multiples of 64")
                 else:
                     g = ops.conv3x3_mixed(g, self.net.wd[name], None, relu=False, out_bf16=(prev is not None), mask=mask)
             else:
-                g = ops.avgpool2_bf16_bwd(g, mask, prev_act.shape)
+                g = (ops.avgpool2_bf16x3_bwd if sp else ops.avgpool2_bf16_bwd)(g, mask, prev_act.shape)
         return g
 
     # ---- losses -------------------------------------------------------------------------------------
     def gram(self, acts, name, Gs, weight, loss):
         F = acts.raw[name]
-        P, ch = F.shape[1] * F.shape[2], F.shape[3]
+        P, ch = F.shape[1] * F.shape[2], F.shape[3] // (2 if self.split else 1)
         if ch % 64:
             raise NotImplementedError('tensor-core Gram needs a channel count that is a multiple of 64')
+        if self.split:
+            return ops.gram_diff_bf16x3_tc(F, 2.0 * P * ch, Gs, weight, loss)
         return ops.gram_diff_bf16_tc(F, 2.0 * P * ch, Gs, weight, loss)
 
     def gram_grad(self, acts, name, handle, coef, g, relu_mask):
+        if self.split:
+            return ops.gram_bwd_bf16x3_tc(acts.raw[name], handle[1], coef, g, relu_mask, g)
         return ops.gram_bwd_bf16_tc(acts.raw[name], handle[1], coef, g, relu_mask, g)
 
     def content(self, acts, name, channel, weight, loss, g, relu_mask, target=None, amp=1.0):
         f = acts[name]                                          # fp32 copy
         n, P, ch = f.shape[0], f.shape[1] * f.shape[2], f.shape[3]
-        g32 = ops.to_f32(g) if g is not None else torch.empty_like(f)
+        to_f32, to_bf = (ops.from_split, ops.to_split) if self.split else (ops.to_f32, ops.to_bf16)
+        g32 = to_f32(g) if g is not None else torch.empty_like(f)
         beta = 1.0 if g is not None else 0.0
         for v in range(n):
             if target is not None:
@@ -108,17 +141,17 @@ class TensorCoreConvs:
             else:
                 ops.content_loss(f[v].reshape(P, ch), channel, weight, loss[v:v + 1], g32[v].reshape(P, ch), beta,
                                  relu_mask)
-        return ops.to_bf16(g32)
+        return to_bf(g32)
 
 
 class _Acts:
     """Activation store: ``raw`` holds the bf16 tensors; ``acts[name]`` hands out an fp32 copy
     (made on first use, cached)."""
 
-    def __init__(self, raw):
-        self.raw, self._f32 = raw, {}
+    def __init__(self, raw, split=False):
+        self.raw, self._f32, self.split = raw, {}, split
 
     def __getitem__(self, name):
         if name not in self._f32:
-            self._f32[name] = ops.to_f32(self.raw[name])
+            self._f32[name] = (ops.from_split if self.split else ops.to_f32)(self.raw[name])
         return self._f32[name]

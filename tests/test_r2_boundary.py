@@ -1,0 +1,85 @@
+"""Round-2 additions to the boundary: library queries, the standalone rotate gradient, and the
+pressure / density regularisers as kernels -- against torch autograd on the same inputs (emu here, cuda on the B200)."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from lnst import _lib, ops
+from oracle import transform as T
+from test_kernel_parity import close
+
+
+def test_version_and_workspace_queries():
+    import os
+    if not os.path.exists(_lib.LIB_PATH):
+        import __graft_entry__
+        __graft_entry__.build()
+    dll = ctypes.CDLL(_lib.LIB_PATH)
+    dll.lnst_version.restype = ctypes.c_char_p
+    assert dll.lnst_version().decode().startswith('lnst-b200')
+    dll.lnst_workspace_bytes.restype = ctypes.c_int64
+    dll.lnst_workspace_bytes.argtypes = [ctypes.c_char_p, ctypes.POINTER(ctypes.c_int64), ctypes.c_int32]
+    dims = (ctypes.c_int64 * 2)(200 ** 3, 2)
+    assert dll.lnst_workspace_bytes(b'splat_wavg_fwd', dims, 2) == 4 * 2 * 200 ** 3
+    dims = (ctypes.c_int64 * 2)(200 * 200, 9)
+    assert dll.lnst_workspace_bytes(b'raymarch_bwd', dims, 2) == 8 * 9 * 200 * 200
+    assert dll.lnst_workspace_bytes(b'smooth3_relu_fwd', None, 0) == 0
+    assert dll.lnst_workspace_bytes(b'no_such_op', None, 0) == -1
+    assert dll.lnst_workspace_bytes(None, None, 0) == -1
+
+
+def test_rotate_bwd_is_the_transpose_of_rotate_fwd(dev):
+    rng = np.random.RandomState(5)
+    D, H, W = 7, 9, 8
+    vol = torch.tensor(rng.rand(D, H, W).astype(np.float32))
+    from lnst.transform import rot_mat
+    mats, _ = rot_mat(-20, 20, 20, -30, 30, 30, sample_type='uniform', rng=rng, nv=None)
+    rot = torch.tensor(np.asarray(mats, np.float64).reshape(-1, 9), dtype=torch.float32)
+    g_out = torch.tensor(rng.randn(rot.shape[0], D, H, W).astype(np.float32))
+    got = ops.rotate_bwd(g_out.to(dev), rot.to(dev))
+    v = vol.double().clone().requires_grad_(True)
+    out = T.rotate(v[None, ..., None], [m for m in np.asarray(mats)])          # [nv, D, H, W, 1]
+    (out[..., 0] * g_out.double()).sum().backward()
+    close(got, v.grad.float(), tol=2e-6, what='rotate bwd')
+    # adjoint identity <rotate(vol), g> = <vol, rotate_bwd(g)>
+    fwd = ops.rotate_fwd(vol.to(dev), rot.to(dev))
+    lhs = float((fwd.double() * g_out.to(dev).double()).sum())
+    rhs = float((vol.to(dev).double() * got.double()).sum())
+    assert abs(lhs - rhs) <= 1e-5 * max(abs(lhs), 1.0)
+
+
+def test_pressure_reg_accumulates(dev):
+    rng = np.random.RandomState(2)
+    d = rng.rand(6, 5, 7).astype(np.float32) * 2
+    d[rng.rand(*d.shape) < 0.3] = 0.0
+    g0 = rng.randn(*d.shape).astype(np.float32)
+    loss = torch.tensor([0.25, 0.5, 7.0]).to(dev)
+    g = torch.tensor(g0).to(dev)
+    w, n_terms = 0.5, 2
+    ops.pressure_reg(torch.tensor(d).to(dev), 1.0, w, n_terms * w * 2.0 / d.size, loss, n_terms, g)
+    dt = torch.tensor(d, dtype=torch.float64, requires_grad=True)
+    pr = torch.where(dt > 0, dt - 1, torch.zeros_like(dt))
+    val = w * (pr * pr).mean()
+    (n_terms * val).backward()
+    close(loss, torch.tensor([0.25 + float(val), 0.5 + float(val), 7.0]), tol=2e-6, what='pressure loss')
+    close(g, torch.tensor(g0).double() + dt.grad, tol=2e-6, what='pressure grad')
+
+
+@pytest.mark.parametrize('n', [0, 1, 3000])
+def test_density_reg(dev, n):
+    rng = np.random.RandomState(4)
+    var = (rng.randn(n, 2) * 0.8).astype(np.float32)              # some elements outside [-1, 1]
+    g0 = rng.randn(n, 2).astype(np.float32)
+    loss = torch.tensor([1.0, 2.0]).to(dev)
+    grad = torch.tensor(g0).to(dev)
+    w, n_terms = 1e-3, 1
+    ops.density_reg(torch.tensor(var).to(dev), w, n_terms * w, loss, n_terms, grad)
+    vt = torch.tensor(var, dtype=torch.float64, requires_grad=True)
+    dv = torch.clamp(vt, -1, 1)
+    val = w * (dv.sum() ** 2 + 1e3 * (-torch.log(dv.abs() + 1e-6)).sum())
+    val.backward()
+    close(loss, torch.tensor([1.0 + float(val), 2.0]), tol=3e-6, what='density loss')
+    if n:
+        close(grad, torch.tensor(g0).double() + vt.grad, tol=3e-6, what='density grad')

@@ -1,0 +1,159 @@
+"""bf16x3 ("split") tensor-core loss network -- GPU only.  Every value travels as [hi | lo] bf16 halves and every
+contraction runs three passes (hi*hi, lo*hi, hi*lo) into one fp32 accumulator: results are compared with fp32 / fp64
+references at fp32-level tolerances (products carry 16 mantissa bits: 2^-16 = 1.5e-5 relative per term, averaging
+down over K).  Loop level: conv_math='bf16x3' holds the SAME tolerances as the exact fp32 CUDA-core path
+(tests/test_styler_parity.py): loss rel 2e-4, field 2e-4 of its maximum, variables rel-L2 2e-3."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import smoke_cfg
+from lnst import _lib, ops, synth
+from lnst.vgg_tc import _hilo, _pack2
+
+pytestmark = pytest.mark.gpu
+TOL = 3e-5
+
+
+@pytest.fixture(autouse=True)
+def cuda_lib():
+    prev = _lib._lib
+    _lib.set_for_testing(None)
+    lib = _lib.get()
+    assert lib.has_tc
+    yield
+    torch.cuda.synchronize()
+    _lib.set_for_testing(prev)
+
+
+def ref_conv(x, w, b, relu):
+    y = torch.nn.functional.conv2d(x.permute(0, 3, 1, 2), w.permute(3, 2, 0, 1), b, padding=1)
+    y = torch.relu(y) if relu else y
+    return y.permute(0, 2, 3, 1)
+
+
+def test_split_round_trip_and_pool():
+    dev = torch.device('cuda:0')
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(3, 9, 12, 64, generator=g) * 37
+    s = ops.to_split(x.to(dev))
+    assert s.shape == (3, 9, 12, 128) and torch.equal(s.cpu(), _hilo(x))
+    back = ops.from_split(s).cpu()
+    assert (back - x).abs().max() <= 2 ** -16 * x.abs().max()
+    p = ops.from_split(ops.avgpool2_bf16x3_fwd(s)).cpu()
+    want = torch.nn.functional.avg_pool2d(x.permute(0, 3, 1, 2), 2, 2).permute(0, 2, 3, 1)
+    assert (p - want).abs().max() <= TOL * want.abs().max()
+    gp = torch.randn(3, 4, 6, 64, generator=g)
+    got = ops.from_split(ops.avgpool2_bf16x3_bwd(ops.to_split(gp.to(dev)), s, s.shape)).cpu()
+    wantb = torch.zeros(3, 9, 12, 64)
+    wantb[:, :8, :12] = gp.repeat_interleave(2, 1).repeat_interleave(2, 2) * 0.25
+    wantb = wantb * (x > 0)
+    assert (got - wantb).abs().max() <= TOL * wantb.abs().max()
+
+
+@pytest.mark.parametrize('n,H,W,cin,cout', [
+    (1, 8, 16, 64, 64), (2, 13, 9, 64, 128), (1, 50, 50, 128, 256), (3, 100, 100, 64, 128), (1, 25, 25, 256, 512),
+    (1, 200, 200, 64, 64), (2, 50, 50, 256, 128)])
+def test_conv3x3_x3_matches_fp64_reference(n, H, W, cin, cout):
+    dev = torch.device('cuda:0')
+    g = torch.Generator().manual_seed(n * 1000 + H + cin)
+    x = torch.randn(n, H, W, cin, generator=g)
+    w = torch.randn(3, 3, cin, cout, generator=g) / np.sqrt(9 * cin)
+    b = torch.randn(cout, generator=g)
+    want = ref_conv(x.double(), w.double(), b.double(), True)
+    xs = ops.to_split(x.to(dev))
+    y = ops.from_split(ops.conv3x3_bf16x3_tc(xs, _pack2(w).to(dev), b.to(dev), relu=True)).cpu()
+    err = (y.double() - want).abs().max().item()
+    assert err <= TOL * want.abs().max().item(), (err, want.abs().max().item())
+    mask = torch.randn(n, H, W, cout, generator=g)
+    want2 = ref_conv(x.double(), w.double(), None, False) * (mask.double() > 0)
+    y2 = ops.from_split(ops.conv3x3_bf16x3_tc(xs, _pack2(w).to(dev), None, relu=False, mask=ops.to_split(mask.to(dev)))).cpu()
+    err2 = (y2.double() - want2).abs().max().item()
+    assert err2 <= TOL * want2.abs().max().item(), err2
+
+
+@pytest.mark.parametrize('n,h,w,ch', [(1, 8, 8, 64), (2, 50, 50, 256), (3, 100, 100, 128), (1, 13, 7, 512)])
+def test_gram_x3_forward_and_gradient(n, h, w, ch):
+    dev = torch.device('cuda:0')
+    g = torch.Generator().manual_seed(h * 7 + ch)
+    F = torch.relu(torch.randn(n, h, w, ch, generator=g))
+    Fs = torch.relu(torch.randn(1, h, w, ch, generator=g))
+    P = h * w
+    den = 2.0 * P * ch
+    Gs, _ = ops.gram_diff_bf16x3_tc(ops.to_split(Fs.to(dev)), den, None, 0.0, None)
+    Fsd = Fs.double().reshape(P, ch)
+    want_s = Fsd.t() @ Fsd / den
+    assert (Gs[0].cpu().double() - want_s).abs().max() <= TOL * want_s.abs().max()
+    loss = torch.zeros(n, device=dev)
+    Fsp = ops.to_split(F.to(dev))
+    G, Gd2 = ops.gram_diff_bf16x3_tc(Fsp, den, Gs[0].contiguous(), 0.7, loss)
+    Fd = F.double().reshape(n, P, ch)
+    want = torch.einsum('npc,npd->ncd', Fd, Fd) / den - Gs[0].cpu().double()
+    assert (G.cpu().double() - want).abs().max() <= TOL * (want.abs().max() + want_s.abs().max())
+    np.testing.assert_allclose(loss.cpu().numpy(), (0.7 * (want ** 2).sum(dim=(1, 2))).numpy(), rtol=2e-4)
+    assert torch.equal(Gd2.cpu(), _hilo(G.cpu()))
+    add = torch.randn(n, h, w, ch, generator=g)
+    coef = 0.37
+    out = ops.from_split(ops.gram_bwd_bf16x3_tc(Fsp, Gd2, coef, ops.to_split(add.to(dev)), 1)).cpu()
+    ref = (add.double().reshape(n, P, ch) + coef * torch.einsum('npc,ncd->npd', Fd, G.cpu().double())) * (Fd > 0)
+    err = (out.double().reshape(n, P, ch) - ref).abs().max().item()
+    assert err <= TOL * ref.abs().max().item(), err
+
+
+def test_lossnet_x3_against_fp32_features_and_gradient():
+    """Whole prefix to conv3_1 in bf16x3 against the exact fp32 CUDA-core path: features and data gradient."""
+    from lnst.vgg import LossNet
+    dev = torch.device('cuda:0')
+    W = synth.vgg_weights()
+    wanted = ['conv2_1', 'conv3_1']
+    n32, n3 = LossNet(W, 'vgg_19', dev, 'fp32'), LossNet(W, 'vgg_19', dev, 'bf16x3')
+    for gray in (False, True):
+        if gray:
+            gimg = torch.rand(2, 40, 56, generator=torch.Generator().manual_seed(3)).to(dev)
+            mean = torch.tensor([0.485 * 255, 0.456 * 255, 0.406 * 255], device=dev)
+            x = (255.0 * gimg[..., None] - mean).contiguous()
+            a3 = n3.forward(None, wanted, gray=gimg)
+        else:
+            x = (torch.tensor(synth.style_image(40, 56, seed=3)).reshape(1, 40, 56, 3) - 110.0).to(dev).contiguous()
+            a3 = n3.forward(x, wanted)
+        a32 = n32.forward(x, wanted)
+        for l in wanted:
+            rel = (a3[l] - a32[l]).norm() / a32[l].norm()
+            assert rel < 2e-5, (l, rel.item())
+
+        def top(acts, split):
+            def fn(name, g):
+                if name != 'conv3_1':
+                    return g
+                act = acts[name]
+                t = (act > 0).float() * torch.sin(torch.arange(act.numel(), device=dev).reshape(act.shape) * 0.37)
+                return ops.to_split(t) if split else t
+            return fn
+        g32 = n32.backward(x, a32, wanted, top(a32, False), {'conv3_1'})
+        g3 = n3.backward(x, a3, wanted, top(a3, True), {'conv3_1'}, gray=gray)
+        if gray:
+            g32 = 255.0 * g32.sum(-1)
+        # a unit whose pre-activation is within 1e-5 (relative) of zero can still flip its ReLU mask
+        rel = (g3 - g32).norm() / g32.norm()
+        assert rel < 2e-3, rel.item()
+
+
+@pytest.mark.parametrize('view_mode', ['allreduce', 'sequential'])
+def test_styler_x3_holds_the_fp32_tolerance(view_mode):
+    from lnst.styler_3p import Styler
+    from oracle.styler import Oracle3P
+    import oracle.vgg
+    res = 20
+    kw = dict(res=res, iter=3, rotate=True, n_views=9, view_mode=view_mode, style_layer=['conv2_1', 'conv3_1'],
+              w_style_layer=[0.5, 0.5])
+    p, r = synth.smoke_particles(4000, 2, pad=4)
+    sty = synth.style_image(res, res)
+    new = Styler(smoke_cfg(conv_math='bf16x3', **kw), weights=synth.vgg_weights())
+    new.style_img = sty
+    out = new.run({'p': p, 'r': r})
+    ref = Oracle3P(smoke_cfg(conv_math='fp32', **kw), oracle.vgg.synthetic_weights()).run(
+        {'p': p, 'r': r}, style_targets=[sty], view_mode=view_mode)
+    np.testing.assert_allclose(out['l'][0], ref['l'][0], rtol=2e-4)
+    g_new, g_ref = out['g_opt'][0], ref['g_opt'][0].numpy()
+    assert np.linalg.norm(g_new - g_ref) / np.linalg.norm(g_ref) < 2e-3
+    assert np.abs(out['d'] - ref['d']).max() <= 2e-4 * np.abs(ref['d']).max()

@@ -3,13 +3,13 @@ one-pixel images, more taps than pixels, empty particle sets, channel counts aro
 (SURVEY.md section 4, item 3).  CPU only -- the GPU runs the fixed-shape versions of these tests."""
 import numpy as np
 import torch
-from hypothesis import HealthCheck, given, settings, strategies as st
+from hypothesis import HealthCheck, example, given, settings, strategies as st
 
 from lnst import _lib, ops
 from oracle import transform as T
 from test_widen_graphnet_kernels import ref_conv, ref_maxpool, ref_lrn
 
-CFG = dict(max_examples=25, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow])
+CFG = dict(max_examples=25, deadline=None, derandomize=True, suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow])
 
 
 def _use_emu(emu_lib):
@@ -291,6 +291,7 @@ def test_fp32_loss_net_layers_any_shape(emu_lib, H, W, cin, cout, n, seed):
 
 
 @settings(**CFG)
+@example(h=1, w=3, ch=1, hs=6, channel=0, seed=107)
 @given(h=st.integers(1, 8), w=st.integers(1, 8), ch=st.integers(1, 80), hs=st.integers(1, 6), channel=st.integers(0, 79),
        seed=st.integers(0, 1000))
 def test_losses_any_shape(emu_lib, h, w, ch, hs, channel, seed):
@@ -306,7 +307,10 @@ def test_losses_any_shape(emu_lib, h, w, ch, hs, channel, seed):
         G = torch.empty_like(Gs)
         ops.gram_diff(F.detach(), 2.0 * P * ch, Gs, 0.7, G, loss)
         want, _ = L.style_loss([F.reshape(1, h, w, ch)], [Fs.reshape(1, hs, 3, ch)], [0.7], 1)
-        _close(loss, want.reshape(1), 3e-5)
+        # the loss is the square of a (possibly almost cancelled) difference G - Gs: its round-off scales with |G|^2,
+        # not with the loss itself (h=1, w=3, ch=1, hs=6, seed=107 gives a loss of 1e-8 from G ~ 0.1)
+        floor = 0.7 * 32 * np.finfo(np.float32).eps * float(max(G.abs().max(), Gs.abs().max())) ** 2 * ch * ch
+        assert abs(float(loss) - float(want)) <= 3e-5 * abs(float(want)) + floor, (float(loss), float(want), floor)
         want.backward()
         gF = torch.empty(P, ch)
         ops.gram_bwd(F.detach(), G, 0.7 * 4.0 / (2.0 * P * ch), 0.0, 0, gF)

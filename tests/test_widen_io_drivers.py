@@ -247,3 +247,32 @@ def test_driver_main_sets_the_reference_scene_constants(ref_name, mod_name, monk
         if not same:
             diffs.append((k, g, v))
     assert not diffs, diffs
+
+
+def test_dambreak2d_main_runs_with_default_flags(dev, tmp_path, monkeypatch):
+    """main() sets style_mask=True on vgg_19 and leaves conv_math at the engine default; the Styler must
+    pick the fp32 loss-net path (with a warning) instead of raising, and the whole driver must run end to end."""
+    import warnings
+    from lnst.config import get_config
+    from lnst.drivers import dambreak2d
+    cfg, _ = get_config([])
+    cfg.keep_resolution, cfg.resolution = True, [6, 8]             # base grid; main() scales it by 4
+    cfg.data_dir, cfg.log_dir = str(tmp_path / 'data'), str(tmp_path / 'log')
+    cfg.num_frames, cfg.target_frame = 1, 0
+    from PIL import Image
+    os.makedirs(os.path.join(cfg.data_dir, 'image'), exist_ok=True)
+    cfg.style_target = os.path.join(cfg.data_dir, 'image', 'style.png')
+    Image.fromarray(np.uint8(synth.style_image(32, 32))).save(cfg.style_target)
+    real_run = dambreak2d.run
+
+    def short_run(c, weights=None):
+        c.iter, c.octave_n = 2, 1                                  # scene constants stay main()'s, the budget shrinks
+        p, r = synth.dam_particles_2d(c.domain)
+        _write_frames(c.data_dir, c.dataset, c.d_path, p, c.domain, dens=r, dim=2)
+        return real_run(c, weights=synth.vgg_weights())
+    monkeypatch.setattr(dambreak2d, 'run', short_run)
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter('always')
+        out = dambreak2d.main(cfg)
+    assert any("'fp32'" in str(x.message) for x in w)
+    assert cfg.style_mask and len(out['l'][0]) == 2 and np.isfinite(out['l'][0]).all()

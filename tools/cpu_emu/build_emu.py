@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, 'neural-flow-style_b200', 'csrc')
 OUT = os.path.join(HERE, 'liblnst_emu.so')
-SOURCES = ['splat.cu', 'field.cu', 'render.cu', 'lossnet.cu', 'optim.cu', 'gather.cu', 'graphnet.cu']
+SOURCES = ['splat.cu', 'field.cu', 'render.cu', 'lossnet.cu', 'optim.cu', 'gather.cu', 'reg.cu', 'graphnet.cu']
 
 
 def build(force=False):
