@@ -255,6 +255,20 @@ int lnst_avgpool2_bf16_bwd(const void* g_y, const void* mask, void* g_x, int32_t
 int lnst_f32_to_bf16(const float* x, void* y, int64_t n, void* stream);
 int lnst_bf16_to_f32(const void* x, float* y, int64_t n, void* stream);
 
+/* ---- TMA-tiled volume kernels (csrc/tiles_tma.cu) ---------------------------------------------------------------
+ * Same results as the entry points they shadow, with the 3-D tiles of the volume staged in shared memory by TMA bulk
+ * tensor copies.  They need rows of a multiple of 4 floats and 16-byte aligned volume pointers (LNST_EARG otherwise: the
+ * caller then uses the SIMT entry point).  lnst_tma_supported(): 1 when the driver exposes cuTensorMapEncodeTiled. */
+int lnst_tma_supported(void);
+int lnst_smooth3_relu_fwd_tma(const float* in, float* out, int32_t D, int32_t H, int32_t W, int32_t k, const LnstBox* box,
+                              void* stream);
+int lnst_smooth3_relu_bwd_tma(const float* g_out, const float* out, float* g_in, int32_t D, int32_t H, int32_t W,
+                              int32_t k, const LnstBox* box, void* stream);
+/* images bit-identical to lnst_raymarch_fwd_box (same per-sample arithmetic, same order along the ray) */
+int lnst_raymarch_fwd_tma(const float* vol, const float* rot, int32_t n_views, int32_t D, int32_t H, int32_t W, float tau,
+                          int32_t liquid, const LnstBox* box, const int32_t* intervals, float* img, float* stot,
+                          void* stream);
+
 /* ---- bf16x3 ("split") tensor-core loss network: fp32-tolerance results at tensor-core speed (vgg.py:89-113 is fp32) ----
  * Every fp32 value v travels as two bf16 halves hi = bf16(v), lo = bf16(v - hi): an NHWC row of C logical channels is
  * 2C bf16 = [hi(0..C-1) | lo(0..C-1)], weights are packed [9, Cout, 2*Cin] = [Whi | Wlo].  A convolution runs three K

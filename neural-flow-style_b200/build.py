@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, 'csrc')
 OUT = os.path.join(HERE, 'lnst', 'liblnst_b200.so')
 STAMP = OUT + '.stamp'
 
-SOURCES = ['splat.cu', 'field.cu', 'render.cu', 'lossnet.cu', 'optim.cu', 'gather.cu', 'reg.cu', 'graphnet.cu', 'conv_tc.cu']
+SOURCES = ['splat.cu', 'field.cu', 'render.cu', 'lossnet.cu', 'optim.cu', 'gather.cu', 'reg.cu', 'graphnet.cu', 'conv_tc.cu', 'tiles_tma.cu']
 
 
 def _sources():

@@ -1,0 +1,309 @@
+// Volume kernels of the stylisation step with their 3-D tiles staged in shared memory by TMA (BASELINE north_star:
+// "the splat, ray-march and advect kernels stage 3D tiles in shared memory via TMA").  CUDA only -- the SIMT versions in
+// field.cu / render.cu / splat.cu / optim.cu stay as the path of the CPU interpreter, of volumes TMA cannot address
+// (W % 4 != 0) and of views too oblique for a fixed slab box.
+//   reference: styler_3p.py:112-125 (3x3x3 smoothing + ReLU), :148-158 (render), transform.py:611-628,343-433 (rotate),
+//              transform.py:1577-1704 (p2g_wavg), :557-609 (advect).
+#include "tma_tiles.cuh"
+#include "render_common.cuh"
+
+// =====================================================================================================================
+// 3x3x3 smoothing (+ ReLU / ReLU-mask): one TMA box {SX+4, SY+2, SZ+2} per tile of SZ x SY x SX outputs.  The zero
+// fill of out-of-volume coordinates IS the SAME padding of tf.nn.conv3d (styler_3p.py:112-121).  A thread owns one (y,x)
+// column of the tile and walks its SZ outputs with a rolling window of three plane values; a plane value is the 3x3
+// in-plane filter read from shared memory (9 LDS, conflict-free: a warp is 32 consecutive x of one row).
+// =====================================================================================================================
+namespace sm3 {
+constexpr int SZ = 8, SY = 16, SX = 32;
+constexpr int BZ = SZ + 2, BY = SY + 2, BX = SX + 8;        // box: the innermost start coordinate must be a multiple of 4
+                                                            // floats (TMA: 16-byte aligned global address of the box start;
+                                                            // measured: x = -1 or 1 raises an illegal-instruction fault),
+                                                            // so the halo column x0-1 sits 0..3 floats into the box
+constexpr int BOX = BZ * BY * BX;                           // 7200 floats
+constexpr int BOX_PAD = (BOX * 4 + 127) / 128 * 32;         // floats to the next 128-byte boundary (second TMA destination)
+constexpr int THREADS = SY * SX;                            // 512
+}
+
+// MODE 0: out = relu(conv(in)), negative pre-activations stored as -0.0f (field.cu);  MODE 1: g_in = conv(g_out * pass(out))
+template <int MODE>
+__global__ void __launch_bounds__(sm3::THREADS) smooth3_tma_k(const __grid_constant__ CUtensorMap map_in,
+                                                              const __grid_constant__ CUtensorMap map_aux,
+                                                              float* __restrict__ out, int H, int W, SubVol sv,
+                                                              float w_side, float w_mid, int tiles_y, int tiles_x) {
+  using namespace sm3;
+  extern __shared__ unsigned char smem_raw[];                 // TMA destinations need 128-byte alignment: aligned by hand
+  float* tin = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  float* taux = tin + BOX_PAD;                                  // MODE 1 only
+  __shared__ __align__(8) uint64_t bar_store;
+  const uint32_t bar = tma::smem_u32(&bar_store);
+  const int t = blockIdx.x;
+  const int tx_ = t % tiles_x, ty_ = (t / tiles_x) % tiles_y, tz_ = t / (tiles_x * tiles_y);
+  const int z0 = sv.oz + tz_ * SZ, y0 = sv.oy + ty_ * SY, x0 = sv.ox + tx_ * SX;
+  const int xs = (x0 - 1) & ~3;                             // box start: x0-1 rounded down to a multiple of 4 (also below 0)
+  const int xo = x0 - 1 - xs;                               // 0..3
+  if (threadIdx.x == 0) {
+    tma::mbar_init(bar, 1);
+    tma::fence_mbar_init();
+    tma::mbar_expect_tx(bar, (MODE == 1 ? 2 : 1) * BOX * 4);
+    tma::load_3d(tma::smem_u32(tin), &map_in, bar, xs, y0 - 1, z0 - 1);
+    if (MODE == 1) tma::load_3d(tma::smem_u32(taux), &map_aux, bar, xs, y0 - 1, z0 - 1);
+  }
+  __syncthreads();
+  tma::mbar_wait(bar, 0);
+  if (MODE == 1) {                                          // mask the incoming gradient by the forward pre-activation sign
+    for (int i = threadIdx.x; i < BOX; i += THREADS)
+      if (__float_as_uint(taux[i]) >> 31) tin[i] = 0.f;
+    __syncthreads();
+  }
+  const int ly = threadIdx.x >> 5, lx = threadIdx.x & 31;
+  const int y = y0 + ly, x = x0 + lx;
+  const bool col_ok = y < sv.oy + sv.ey && x < sv.ox + sv.ex;
+  const int z_end = min(z0 + SZ, sv.oz + sv.ez);
+  auto plane = [&](int zp) -> float {                       // same expression as field.cu smooth_slice
+    const float* r = tin + (zp * BY + ly) * BX + lx + xo;
+    float p = 0.f;
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy) {
+      const float wy = dy == 1 ? w_mid : w_side;
+      p += wy * (w_side * r[dy * BX] + w_mid * r[dy * BX + 1] + w_side * r[dy * BX + 2]);
+    }
+    return p;
+  };
+  float a = plane(0), b = plane(1);
+  float* o = out + ((int64_t)z0 * H + y) * W + x;
+  for (int z = z0; z < z_end; ++z) {
+    const float c = plane(z - z0 + 2);
+    float v = w_side * a + w_mid * b + w_side * c;
+    if (MODE == 0) v = (v < 0.f) ? -0.0f : v;
+    if (col_ok) *o = v;
+    o += (int64_t)H * W;
+    a = b; b = c;
+  }
+}
+
+static inline void smooth_weights_tma(int k, float& side, float& mid) {
+  const float s = (float)(k + 2);                           // k1 = [1,k,1] / (k+2) per axis (styler_3p.py:115-120)
+  side = 1.f / s;
+  mid = (float)k / s;
+}
+
+template <int MODE>
+static int launch_smooth_tma(const float* in, const float* aux, float* out, int D, int H, int W, int k,
+                             const LnstBox* box, cudaStream_t st) {
+  using namespace sm3;
+  CUtensorMap m_in, m_aux;
+  if (!tma::make_volume_map(&m_in, in, D, H, W, BZ, BY, BX)) return LNST_EARG;
+  if (MODE == 1) { if (!tma::make_volume_map(&m_aux, aux, D, H, W, BZ, BY, BX)) return LNST_EARG; }
+  else m_aux = m_in;
+  float side, mid;
+  smooth_weights_tma(k, side, mid);
+  const SubVol sv = make_subvol(box, D, H, W);
+  const int tz = (sv.ez + SZ - 1) / SZ, ty = (sv.ey + SY - 1) / SY, tx = (sv.ex + SX - 1) / SX;
+  const int smem = (MODE == 1 ? 2 : 1) * BOX_PAD * 4 + 128;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(smooth3_tma_k<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * BOX_PAD * 4 + 128);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  smooth3_tma_k<MODE><<<(unsigned)(tz * ty * tx), THREADS, smem, st>>>(m_in, m_aux, out, H, W, sv, side, mid, ty, tx);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int lnst_tma_supported(void) { return tma::encode_fn() != nullptr ? 1 : 0; }
+
+extern "C" int lnst_smooth3_relu_fwd_tma(const float* in, float* out, int32_t D, int32_t H, int32_t W, int32_t k,
+                                         const LnstBox* box, void* stream) {
+  if (!in || !out || D < 1 || H < 1 || W < 1 || k < 1 || !box_ok(box, D, H, W)) return LNST_EARG;
+  return launch_smooth_tma<0>(in, nullptr, out, D, H, W, k, box, lnst_stream(stream));
+}
+extern "C" int lnst_smooth3_relu_bwd_tma(const float* g_out, const float* out, float* g_in, int32_t D, int32_t H,
+                                         int32_t W, int32_t k, const LnstBox* box, void* stream) {
+  if (!g_out || !out || !g_in || D < 1 || H < 1 || W < 1 || k < 1 || !box_ok(box, D, H, W)) return LNST_EARG;
+  return launch_smooth_tma<1>(g_out, out, g_in, D, H, W, k, box, lnst_stream(stream));
+}
+
+// =====================================================================================================================
+// Rotated ray-march, forward.  A CTA owns a TH x TW tile of pixels of one view and walks the volume in slabs of BZ
+// planes, front (high z) to back: every slab is ONE TMA box {BX, BY, BZ} -- the bounding box of the tile's sample
+// footprints inside those planes -- double buffered, so the samples of a slab come out of shared memory while the next
+// slab is in flight.  A thread is one ray, as in render.cu, and evaluates each sample with the same functions
+// (render_common.cuh) in the same order: the image is bit-identical to raymarch_rot_fwd_k's.
+// Views whose footprint does not fit the fixed box (|angle| beyond ~15 degrees) or that do not run towards +z take the
+// gather path inside the same kernel -- the decision is per CTA and on the device, because the view matrices live in a
+// device buffer that is refreshed between CUDA-graph replays (Poisson view sampling).
+// =====================================================================================================================
+namespace rm {
+constexpr int TH = 8, TW = 32;
+constexpr int BZ = 16, BY = 16, BX = 44;                    // x origin rounded down to a multiple of 4 (TMA alignment): +3 columns
+constexpr int SLAB = BZ * BY * BX;                          // 11264 floats = 44 KiB
+constexpr int THREADS = TH * TW;
+}
+
+struct Anchor { int z0, y0, x0; float fz, fy, fx; };
+// same arithmetic as locate() (render_common.cuh), with the anchor kept as three indices
+__device__ __forceinline__ Anchor locate3(const RayLine& l, float fi, const RayGeo& g) {
+  const float z = fminf(fmaxf(fmaf(l.kz, fi, l.cz), 0.f), g.mD);
+  const float y = fminf(fmaxf(fmaf(l.ky, fi, l.cy), 0.f), g.mH);
+  const float x = fminf(fmaxf(fmaf(l.kx, fi, l.cx), 0.f), g.mW);
+  Anchor a;
+  a.z0 = min((int)z, g.D2); a.y0 = min((int)y, g.H2); a.x0 = min((int)x, g.W2);
+  a.fz = z - (float)a.z0; a.fy = y - (float)a.y0; a.fx = x - (float)a.x0;
+  return a;
+}
+
+// Bounding rows / columns of the tile's sample positions over the planes [za, zb + 1]: along a ray y = Y0 + r z with
+// Y0 = cy - r cz affine in the pixel, so the extremes sit at the tile's corner pixels and the slab's end planes.
+struct TileSpan { float lo, hi, r; };                       // Y0 range over the tile's 4 corners, slope dy/dz
+__device__ __forceinline__ TileSpan tile_span(const float* __restrict__ R, const RayGeo& g, int h0, int h1, int w0, int w1,
+                                              int axis) {
+  float lo = 3.0e38f, hi = -3.0e38f, r = 0.f;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const RayLine l = ray_line(R, lin_coord((c & 1) ? h1 : h0, g.sH), lin_coord((c & 2) ? w1 : w0, g.sW), g);
+    const float k = axis == 1 ? l.ky : l.kx, cc = axis == 1 ? l.cy : l.cx;
+    r = k / l.kz;
+    const float v = cc - r * l.cz;
+    lo = fminf(lo, v); hi = fmaxf(hi, v);
+  }
+  TileSpan s = {lo, hi, r};
+  return s;
+}
+__device__ __forceinline__ int span_origin(const TileSpan& s, int za, int zb, float m, bool align4) {
+  const float a = s.r * (float)za, b = s.r * (float)(zb + 1);
+  const float lo = fminf(fmaxf(s.lo + fminf(a, b), 0.f), m);  // positions are clamped to the volume, so is their range
+  const int o = (int)floorf(lo) - 1;                          // one voxel of slack against round-off
+  return align4 ? (o & ~3) : o;                               // innermost TMA coordinate: a multiple of 4 floats
+}
+
+__global__ void __launch_bounds__(rm::THREADS) raymarch_fwd_tma_k(const __grid_constant__ CUtensorMap map_vol,
+                                                                  const float* __restrict__ vol,
+                                                                  const float* __restrict__ rot, RayGeo g, BoxF bf,
+                                                                  const int2* __restrict__ iv, float ntl2, int liquid,
+                                                                  float* __restrict__ img, float* __restrict__ stot,
+                                                                  int tiles_w) {
+  using namespace rm;
+  extern __shared__ unsigned char smem_raw[];
+  float* slab = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));   // 2 x SLAB
+  __shared__ __align__(8) uint64_t bar_store[2];
+  __shared__ int s_ztop, s_zbot;
+  const int view = blockIdx.y;
+  const float* R = rot + 9 * view;
+  const int th = blockIdx.x / tiles_w, tw = blockIdx.x - th * tiles_w;
+  const int h0 = th * TH, w0 = tw * TW;
+  const int ly = threadIdx.x >> 5, lx = threadIdx.x & 31;
+  const int h = h0 + ly, w = w0 + lx;
+  const bool valid = h < g.H && w < g.W;
+  const int hc = min(h, g.H - 1), wc = min(w, g.W - 1);
+  const RayLine l = ray_line(R, lin_coord(hc, g.sH), lin_coord(wc, g.sW), g);
+  int i_lo = 1, i = 0;                                       // [i_lo, i]: the ray's live samples, marched downwards
+  if (valid) {
+    if (iv) { const int2 r = iv[(int64_t)view * g.HW + h * g.W + w]; i_lo = r.x; i = r.y; }
+    else ray_interval(l, g, bf, i_lo, i);
+  }
+  const bool live = valid && i_lo <= i;
+  if (threadIdx.x == 0) {
+    s_ztop = -1; s_zbot = 0x7fffffff;
+    tma::mbar_init(tma::smem_u32(&bar_store[0]), 1);
+    tma::mbar_init(tma::smem_u32(&bar_store[1]), 1);
+    tma::fence_mbar_init();
+  }
+  __syncthreads();
+  // tile-uniform: does the slab box hold this view's footprint?  (kz, ky, kx do not depend on the pixel)
+  const int h1 = min(h0 + TH, g.H) - 1, w1 = min(w0 + TW, g.W) - 1;
+  const TileSpan sy = tile_span(R, g, h0, h1, w0, w1, 1), sx = tile_span(R, g, h0, h1, w0, w1, 2);
+  const bool fits = l.kz > 0.5f && (sy.hi - sy.lo) + fabsf(sy.r) * (float)BZ + 4.f <= (float)BY &&
+                    (sx.hi - sx.lo) + fabsf(sx.r) * (float)BZ + 7.f <= (float)BX;
+  float S = 0.f, I = 0.f;
+  if (!fits) {                                               // gather path (render.cu arithmetic, no plane carry)
+    for (; i >= i_lo; --i) {
+      const Cell c = locate(l, (float)i, g);
+      const float* p = vol + c.idx;
+      const Plane4 lo = load_plane(p, g.W), hi = load_plane(p + g.HW, g.W);
+      const float d = lerp_planes(lo, hi, c);
+      S += d;
+      I = fmaf(d, fast_exp2(S * ntl2), I);
+    }
+  } else {
+    if (live) {
+      atomicMax(&s_ztop, locate3(l, (float)i, g).z0);
+      atomicMin(&s_zbot, locate3(l, (float)i_lo, g).z0);
+    }
+    __syncthreads();
+    const int ztop = s_ztop, zbot = s_zbot;
+    const int nslab = ztop >= zbot ? (ztop - zbot) / (BZ - 1) + 1 : 0;
+    // slab s holds the anchors [za, za + BZ - 2] with za = ztop - (BZ - 2) - s (BZ - 1)
+    if (threadIdx.x == 0) {
+      for (int s = 0; s < 2 && s < nslab; ++s) {
+        const int za = ztop - (BZ - 2) - s * (BZ - 1);
+        const uint32_t bar = tma::smem_u32(&bar_store[s]);
+        tma::mbar_expect_tx(bar, SLAB * 4);
+        tma::load_3d(tma::smem_u32(slab + s * SLAB), &map_vol, bar, span_origin(sx, za, za + BZ - 2, g.mW, true),
+                     span_origin(sy, za, za + BZ - 2, g.mH, false), za);
+      }
+    }
+    for (int s = 0; s < nslab; ++s) {
+      const int buf = s & 1;
+      const int za = ztop - (BZ - 2) - s * (BZ - 1);
+      const int oy = span_origin(sy, za, za + BZ - 2, g.mH, false), ox = span_origin(sx, za, za + BZ - 2, g.mW, true);
+      tma::mbar_wait(tma::smem_u32(&bar_store[buf]), (uint32_t)((s >> 1) & 1));
+      const float* sb = slab + buf * SLAB;
+      while (i >= i_lo) {
+        const Anchor a = locate3(l, (float)i, g);
+        if (a.z0 < za) break;                                // belongs to a slab further back
+        const int ry = a.y0 - oy, rx = a.x0 - ox;
+        Plane4 lo, hi;
+        if ((unsigned)ry < (unsigned)(BY - 1) && (unsigned)rx < (unsigned)(BX - 1)) {
+          const float* p = sb + ((a.z0 - za) * BY + ry) * BX + rx;
+          lo.a = p[0]; lo.b = p[1]; lo.c = p[BX]; lo.d = p[BX + 1];
+          const float* q = p + BY * BX;
+          hi.a = q[0]; hi.b = q[1]; hi.c = q[BX]; hi.d = q[BX + 1];
+        } else {                                             // outside the staged box (round-off at its rim): gather
+          const float* p = vol + ((int64_t)a.z0 * g.H + a.y0) * g.W + a.x0;
+          lo = load_plane(p, g.W); hi = load_plane(p + g.HW, g.W);
+        }
+        Cell c; c.idx = 0; c.fz = a.fz; c.fy = a.fy; c.fx = a.fx;
+        const float d = lerp_planes(lo, hi, c);
+        S += d;                                              // inclusive reverse cumsum, styler_3p.py:155
+        I = fmaf(d, fast_exp2(S * ntl2), I);
+        --i;
+      }
+      __syncthreads();                                       // every ray is done with this buffer
+      if (threadIdx.x == 0 && s + 2 < nslab) {
+        const int zn = ztop - (BZ - 2) - (s + 2) * (BZ - 1);
+        const uint32_t bar = tma::smem_u32(&bar_store[buf]);
+        tma::mbar_expect_tx(bar, SLAB * 4);
+        tma::load_3d(tma::smem_u32(slab + buf * SLAB), &map_vol, bar, span_origin(sx, zn, zn + BZ - 2, g.mW, true),
+                     span_origin(sy, zn, zn + BZ - 2, g.mH, false), zn);
+      }
+    }
+  }
+  if (liquid) I = 1.f - fast_exp2(S * ntl2);                 // styler_3p.py:150-152
+  if (valid) {
+    img[(int64_t)view * g.HW + h * g.W + w] = I;
+    stot[(int64_t)view * g.HW + h * g.W + w] = S;
+  }
+}
+
+extern "C" int lnst_raymarch_fwd_tma(const float* vol, const float* rot, int32_t n_views, int32_t D, int32_t H,
+                                     int32_t W, float tau, int32_t liquid, const LnstBox* box, const int32_t* intervals,
+                                     float* img, float* stot, void* stream) {
+  using namespace rm;
+  if (!vol || !rot || !img || !stot || n_views < 1 || D < 2 || H < 2 || W < 2 || !box_ok(box, D, H, W)) return LNST_EARG;
+  if ((int64_t)D * H * W >= 0x7fffffff) return LNST_EARG;
+  CUtensorMap mv;
+  if (!tma::make_volume_map(&mv, vol, D, H, W, BZ, BY, BX)) return LNST_EARG;
+  const RayGeo g = make_geo(D, H, W);
+  const int tiles_h = (H + TH - 1) / TH, tiles_w = (W + TW - 1) / TW;
+  const int smem = 2 * SLAB * 4 + 128;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(raymarch_fwd_tma_k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  raymarch_fwd_tma_k<<<dim3((unsigned)(tiles_h * tiles_w), (unsigned)n_views), THREADS, smem, lnst_stream(stream)>>>(
+      mv, vol, rot, g, make_boxf(box, D, H, W), reinterpret_cast<const int2*>(intervals), -tau * 1.4426950408889634f,
+      (int)liquid, img, stot, tiles_w);
+  return (int)cudaGetLastError();
+}

@@ -132,6 +132,11 @@ CUDA_ONLY = {
     'lnst_f32_to_bf16x3': [vp, vp, i64, i32, vp],
     'lnst_bf16x3_to_f32': [vp, vp, i64, i32, vp],
     'lnst_f32_to_bf16': [vp, vp, i64, vp],
+    # TMA-tiled volume kernels (csrc/tiles_tma.cu)
+    'lnst_tma_supported': [],
+    'lnst_smooth3_relu_fwd_tma': [vp, vp, i32, i32, i32, i32, BP, vp],
+    'lnst_smooth3_relu_bwd_tma': [vp, vp, vp, i32, i32, i32, i32, BP, vp],
+    'lnst_raymarch_fwd_tma': [vp, vp, i32, i32, i32, i32, f32, i32, BP, vp, vp, vp, vp],
     'lnst_bf16_to_f32': [vp, vp, i64, vp],
 }
 
@@ -157,13 +162,14 @@ class Lib:
         self.dll.lnst_version.argtypes = []
         self.dll.lnst_workspace_bytes.restype = C.c_int64
         self.dll.lnst_workspace_bytes.argtypes = [C.c_char_p, C.POINTER(C.c_int64), i32]
-        self.has_tc = False
+        self.has_tc = self.has_tma = False
         if kind == 'cuda' and hasattr(self.dll, 'lnst_tc_supported'):
             for name, args in CUDA_ONLY.items():
                 fn = getattr(self.dll, name)
                 fn.argtypes = args
                 fn.restype = C.c_int
             self.has_tc = True
+            self.has_tma = bool(self.dll.lnst_tma_supported())
         if self.dll.lnst_abi_version() != 1:
             raise LnstError('ABI version mismatch in %s' % path)
 

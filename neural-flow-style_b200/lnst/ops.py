@@ -1,6 +1,7 @@
 """Tensor-level wrappers over the C-ABI (``_lib``): allocate outputs with torch, pass raw
 pointers + the current CUDA stream.  No arithmetic happens here."""
 import ctypes as C
+import os
 
 import torch
 
@@ -86,14 +87,33 @@ def splat_wavg_bwd_coef(p, var, grid, hs, coef, g_out, g_var):
 
 
 # ---- field ---------------------------------------------------------------------------------
+# TMA-tiled volume kernels (csrc/tiles_tma.cu) replace the SIMT ones on the GPU whenever TMA can address the volume:
+# rows of a multiple of 4 floats and a 16-byte aligned base.  LNST_TMA=0 (or ``ops.USE_TMA = False``) keeps the SIMT
+# kernels -- the A/B switch of the parity tests and microbenchmarks.
+USE_TMA = os.environ.get('LNST_TMA', '1') not in ('0', '')
+
+
+def _tma_ok(*vols):
+    lib = _lib.get()
+    if not (USE_TMA and lib.kind == 'cuda' and lib.has_tma):
+        return False
+    return all(v is None or (v.shape[-1] % 4 == 0 and v.data_ptr() % 16 == 0) for v in vols)
+
+
 def smooth3_relu_fwd(d, out, k, box=None):
     D, H, W = d.shape
+    if int(k) > 0 and _tma_ok(d):
+        _lib.get().call('lnst_smooth3_relu_fwd_tma', ptr(d), ptr(out), D, H, W, int(k), _b(box), _s(d))
+        return out
     _lib.get().call('lnst_smooth3_relu_fwd_box', ptr(d), ptr(out), D, H, W, int(k), _b(box), _s(d))
     return out
 
 
 def smooth3_relu_bwd(g_out, out, g_in, k, box=None):
     D, H, W = out.shape
+    if int(k) > 0 and _tma_ok(g_out, out):
+        _lib.get().call('lnst_smooth3_relu_bwd_tma', ptr(g_out), ptr(out), ptr(g_in), D, H, W, int(k), _b(box), _s(out))
+        return g_in
     _lib.get().call('lnst_smooth3_relu_bwd_box', ptr(g_out), ptr(out), ptr(g_in), D, H, W, int(k), _b(box), _s(out))
     return g_in
 
@@ -139,6 +159,10 @@ def ray_intervals(rot, shape, box, bricks, out=None):
 def raymarch_fwd(vol, rot, tau, liquid, img, stot, box=None, intervals=None):
     D, H, W = vol.shape
     nv = 1 if rot is None else rot.shape[0]
+    if rot is not None and min(D, H, W) >= 2 and D * H * W < 2 ** 31 - 1 and _tma_ok(vol):
+        _lib.get().call('lnst_raymarch_fwd_tma', ptr(vol), ptr(rot), nv, D, H, W, float(tau), int(bool(liquid)), _b(box),
+                        _u8(intervals), ptr(img), ptr(stot), _s(vol))
+        return img, stot
     _lib.get().call('lnst_raymarch_fwd_box', ptr(vol), ptr(rot), nv, D, H, W, float(tau), int(bool(liquid)), _b(box),
                     _u8(intervals), ptr(img), ptr(stot), _s(vol))
     return img, stot

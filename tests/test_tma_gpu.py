@@ -1,0 +1,93 @@
+"""TMA-tiled volume kernels (csrc/tiles_tma.cu) against the SIMT kernels they shadow -- GPU only.  The SIMT kernels are
+the ones pinned against the oracle / the reference's vectors (test_kernel_parity.py, test_reference_golden.py, here and on
+the CPU interpreter); these tests pin the TMA versions to them: ray-march images bit for bit, the rest to round-off."""
+import numpy as np
+import pytest
+import torch
+
+from lnst import _lib, ops
+from lnst.transform import rot_mat
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device('cuda:0')
+
+
+@pytest.fixture(autouse=True)
+def cuda_lib():
+    prev = _lib._lib
+    _lib.set_for_testing(None)
+    lib = _lib.get()
+    assert lib.has_tma, 'TMA entry points missing from the CUDA library'
+    yield
+    torch.cuda.synchronize()
+    ops.USE_TMA = True
+    _lib.set_for_testing(prev)
+
+
+def both(fn):
+    """run fn() with the SIMT and with the TMA kernels"""
+    outs = []
+    for tma in (False, True):
+        ops.USE_TMA = tma
+        n0 = _lib.get().launches
+        outs.append(fn())
+    ops.USE_TMA = True
+    return outs
+
+
+def blob(D, H, W, seed=0, frac=0.6):
+    """smooth non-negative density that is exactly zero outside a centred ellipsoid, and that ellipsoid's box"""
+    rng = np.random.RandomState(seed)
+    z, y, x = np.meshgrid(np.linspace(-1, 1, D), np.linspace(-1, 1, H), np.linspace(-1, 1, W), indexing='ij')
+    rr = (z / frac) ** 2 + (y / (frac * 1.1)) ** 2 + (x / frac) ** 2
+    v = np.where(rr < 1, rng.rand(D, H, W) * (1 - rr), 0).astype(np.float32)
+    nz = np.nonzero(v)
+    lo = [max(int(a.min()) - 1, 0) for a in nz]
+    hi = [min(int(a.max()) + 1, s - 1) for a, s in zip(nz, (D, H, W))]
+    return torch.tensor(v).to(DEV), _lib.make_box(lo, hi)
+
+
+def views(phi, theta, n=None):
+    rng = np.random.RandomState(1)
+    mats, _ = rot_mat(-phi, phi, phi, -theta, theta, theta, sample_type='uniform', rng=rng, nv=n)
+    return torch.tensor(np.asarray(mats, np.float64).reshape(-1, 9), dtype=torch.float32).to(DEV)
+
+
+@pytest.mark.parametrize('shape', [(24, 24, 24), (20, 28, 36), (200, 200, 200), (9, 5, 8), (64, 64, 132)])
+@pytest.mark.parametrize('use_box', [False, True])
+def test_smooth3_tma_equals_simt(shape, use_box):
+    D, H, W = shape
+    d, box = blob(D, H, W, seed=D)
+    d = d - 0.05 * (d > 0)                                   # some negative pre-activations for the ReLU marker
+    box = box if use_box else None
+    g = torch.tensor(np.random.RandomState(3).randn(D, H, W).astype(np.float32)).to(DEV)
+
+    def run():
+        ds = ops.smooth3_relu_fwd(d, torch.zeros_like(d), 3, box)
+        gd = ops.smooth3_relu_bwd(g, ds, torch.zeros_like(d), 3, box)
+        return ds, gd
+    (ds0, gd0), (ds1, gd1) = both(run)
+    assert torch.equal(torch.signbit(ds0), torch.signbit(ds1))        # the -0.0 markers
+    assert (ds0 - ds1).abs().max() <= 1e-6 * ds0.abs().max()
+    assert (gd0 - gd1).abs().max() <= 2e-6 * gd0.abs().max()
+
+
+@pytest.mark.parametrize('shape,phi,theta', [((24, 24, 24), 5, 10), ((200, 200, 200), 5, 10), ((20, 28, 36), 5, 10),
+                                             ((40, 40, 40), 40, 60),      # too oblique for the slab box: gather path
+                                             ((64, 64, 64), 12, 15), ((33, 30, 32), 0, 0)])
+@pytest.mark.parametrize('liquid', [False, True])
+def test_raymarch_fwd_tma_is_bit_identical(shape, phi, theta, liquid):
+    D, H, W = shape
+    vol, box = blob(D, H, W, seed=H)
+    rot = views(phi, theta) if phi or theta else torch.eye(3).reshape(1, 9).to(DEV)
+    nv = rot.shape[0]
+    for bx in (None, box):
+        def run():
+            img = torch.empty(nv, H, W, device=DEV)
+            stot = torch.empty(nv, H, W, device=DEV)
+            iv = ops.ray_intervals(rot, (D, H, W), bx, None) if bx is not None else None
+            ops.raymarch_fwd(vol, rot, 0.01 if not liquid else 0.2, liquid, img, stot, bx, iv)
+            return img, stot
+        (i0, s0), (i1, s1) = both(run)
+        assert torch.equal(i0, i1) and torch.equal(s0, s1)
+        assert float(i0.max()) > 0
