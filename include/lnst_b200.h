@@ -144,6 +144,10 @@ int lnst_raymarch_bwd_box(const float* vol, const float* rot, int32_t n_views, i
  * skipped, so images stay bit-identical and every ACTIVE voxel still receives its exact gradient. */
 int lnst_ray_intervals(const float* rot, int32_t n_views, int32_t D, int32_t H, int32_t W, const LnstBox* box,
                        const unsigned char* bricks, int32_t* intervals, void* stream);
+/* Exact variant for view sets that stay fixed: touch [D,H,W] bytes, non-zero for an anchor voxel v when any voxel of
+ * {v, v+1}^3 can hold smoothed density.  Same output layout; about the cost of one forward march. */
+int lnst_ray_intervals_exact(const float* rot, int32_t n_views, int32_t D, int32_t H, int32_t W, const LnstBox* box,
+                             const unsigned char* touch, int32_t* intervals, void* stream);
 /* Tuning switch for lnst_raymarch_bwd (process-wide, default 1): 1 = neighbouring lanes merge their
  * shared x-corner contributions by warp shuffle before the atomics; 0 = eight atomics per sample. */
 int lnst_set_raymarch_merge(int32_t on);
@@ -260,6 +264,8 @@ int lnst_bf16_to_f32(const void* x, float* y, int64_t n, void* stream);
  * tensor copies.  They need rows of a multiple of 4 floats and 16-byte aligned volume pointers (LNST_EARG otherwise: the
  * caller then uses the SIMT entry point).  lnst_tma_supported(): 1 when the driver exposes cuTensorMapEncodeTiled. */
 int lnst_tma_supported(void);
+/* tuning switch for microbenchmarks: planes per TMA slab of the ray-march kernels (8, 12 or 16; default 12) */
+int lnst_set_raymarch_slab(int32_t planes);
 int lnst_smooth3_relu_fwd_tma(const float* in, float* out, int32_t D, int32_t H, int32_t W, int32_t k, const LnstBox* box,
                               void* stream);
 int lnst_smooth3_relu_bwd_tma(const float* g_out, const float* out, float* g_in, int32_t D, int32_t H, int32_t W,
@@ -268,6 +274,11 @@ int lnst_smooth3_relu_bwd_tma(const float* g_out, const float* out, float* g_in,
 int lnst_raymarch_fwd_tma(const float* vol, const float* rot, int32_t n_views, int32_t D, int32_t H, int32_t W, float tau,
                           int32_t liquid, const LnstBox* box, const int32_t* intervals, float* img, float* stot,
                           void* stream);
+
+/* smoke render (liquid = 0) only; g_vol accumulates like lnst_raymarch_bwd_box */
+int lnst_raymarch_bwd_tma(const float* vol, const float* rot, int32_t n_views, int32_t D, int32_t H, int32_t W, float tau,
+                          const LnstBox* box, const int32_t* intervals, const float* stot, const float* g_img,
+                          float* g_vol, void* stream);
 
 /* ---- bf16x3 ("split") tensor-core loss network: fp32-tolerance results at tensor-core speed (vgg.py:89-113 is fp32) ----
  * Every fp32 value v travels as two bf16 halves hi = bf16(v), lo = bf16(v - hi): an NHWC row of C logical channels is

@@ -237,6 +237,26 @@ __global__ void __launch_bounds__(128) ray_intervals_k(const float* __restrict__
   iv[(int64_t)view * g.HW + pix] = make_int2(lo, hi);
 }
 
+// Exact live interval of every ray: first and last sample whose trilinear footprint touches a voxel where the smoothed
+// density can be non-zero.  `touch` [D,H,W] (one byte per voxel) is set for an ANCHOR voxel v when any of the 8 voxels
+// {v, v+1}^3 is active, so one byte per sample decides.  Costs about one forward march, so it is meant for view sets
+// that stay fixed over the iterations (sample_type 'uniform'); the brick test above is the cheap conservative version.
+__global__ void __launch_bounds__(128) ray_intervals_exact_k(const float* __restrict__ rot, RayGeo g, BoxF bf,
+                                                              const unsigned char* __restrict__ touch,
+                                                              int2* __restrict__ iv) {
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= g.HW) return;
+  const int view = blockIdx.y;
+  const int h = pix / g.W, w = pix - h * g.W;
+  const RayLine l = ray_line(rot + 9 * view, lin_coord(h, g.sH), lin_coord(w, g.sW), g);
+  int lo, hi;
+  ray_interval(l, g, bf, lo, hi);
+  while (lo <= hi && touch[locate(l, (float)lo, g).idx] == 0) ++lo;
+  while (hi > lo && touch[locate(l, (float)hi, g).idx] == 0) --hi;
+  if (lo > hi) { lo = 1; hi = 0; }
+  iv[(int64_t)view * g.HW + pix] = make_int2(lo, hi);
+}
+
 __global__ void __launch_bounds__(128) raymarch_rot_fwd_k(const float* __restrict__ vol, const float* __restrict__ rot,
                                                            RayGeo g, BoxF bf, const int2* __restrict__ iv,
                                                            float ntl2, int liquid, float* __restrict__ img,
@@ -692,6 +712,16 @@ extern "C" int lnst_ray_intervals(const float* rot, int32_t n_views, int32_t D, 
   const RayGeo g = make_geo(D, H, W);
   LNST_LAUNCH(ray_intervals_k, dim3(lnst_blocks((int64_t)H * W, 128), n_views), dim3(128), 0, lnst_stream(stream), rot,
               g, make_boxf(box, D, H, W), make_bricks(bricks, H, W), reinterpret_cast<int2*>(intervals));
+  return lnst_status();
+}
+
+extern "C" int lnst_ray_intervals_exact(const float* rot, int32_t n_views, int32_t D, int32_t H, int32_t W,
+                                        const LnstBox* box, const unsigned char* touch, int32_t* intervals, void* stream) {
+  if (!rot || !intervals || !touch || n_views < 1 || D < 2 || H < 2 || W < 2 || !box_ok(box, D, H, W)) return LNST_EARG;
+  if ((int64_t)D * H * W >= 0x7fffffff) return LNST_EARG;
+  const RayGeo g = make_geo(D, H, W);
+  LNST_LAUNCH(ray_intervals_exact_k, dim3(lnst_blocks((int64_t)H * W, 128), n_views), dim3(128), 0, lnst_stream(stream),
+              rot, g, make_boxf(box, D, H, W), touch, reinterpret_cast<int2*>(intervals));
   return lnst_status();
 }
 

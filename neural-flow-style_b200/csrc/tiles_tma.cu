@@ -135,9 +135,8 @@ extern "C" int lnst_smooth3_relu_bwd_tma(const float* g_out, const float* out, f
 // =====================================================================================================================
 namespace rm {
 constexpr int TH = 8, TW = 32;
-constexpr int BZ = 16, BY = 16, BX = 44;                    // x origin rounded down to a multiple of 4 (TMA alignment): +3 columns
-constexpr int SLAB = BZ * BY * BX;                          // 11264 floats = 44 KiB
-constexpr int THREADS = TH * TW;
+constexpr int BY = 16, BX = 44;                             // x origin rounded down to a multiple of 4 (TMA alignment): +3 columns
+constexpr int THREADS = TH * TW;                            // planes per slab (BZ): template parameter, 8 / 12 / 16
 }
 
 struct Anchor { int z0, y0, x0; float fz, fy, fx; };
@@ -176,6 +175,7 @@ __device__ __forceinline__ int span_origin(const TileSpan& s, int za, int zb, fl
   return align4 ? (o & ~3) : o;                               // innermost TMA coordinate: a multiple of 4 floats
 }
 
+template <int BZ>
 __global__ void __launch_bounds__(rm::THREADS) raymarch_fwd_tma_k(const __grid_constant__ CUtensorMap map_vol,
                                                                   const float* __restrict__ vol,
                                                                   const float* __restrict__ rot, RayGeo g, BoxF bf,
@@ -183,6 +183,7 @@ __global__ void __launch_bounds__(rm::THREADS) raymarch_fwd_tma_k(const __grid_c
                                                                   float* __restrict__ img, float* __restrict__ stot,
                                                                   int tiles_w) {
   using namespace rm;
+  constexpr int SLAB = BZ * BY * BX;                         // floats per slab (a multiple of 32: 128-byte aligned buffers)
   extern __shared__ unsigned char smem_raw[];
   float* slab = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));   // 2 x SLAB
   __shared__ __align__(8) uint64_t bar_store[2];
@@ -248,25 +249,67 @@ __global__ void __launch_bounds__(rm::THREADS) raymarch_fwd_tma_k(const __grid_c
       const int oy = span_origin(sy, za, za + BZ - 2, g.mH, false), ox = span_origin(sx, za, za + BZ - 2, g.mW, true);
       tma::mbar_wait(tma::smem_u32(&bar_store[buf]), (uint32_t)((s >> 1) & 1));
       const float* sb = slab + buf * SLAB;
-      while (i >= i_lo) {
-        const Anchor a = locate3(l, (float)i, g);
-        if (a.z0 < za) break;                                // belongs to a slab further back
-        const int ry = a.y0 - oy, rx = a.x0 - ox;
-        Plane4 lo, hi;
-        if ((unsigned)ry < (unsigned)(BY - 1) && (unsigned)rx < (unsigned)(BX - 1)) {
-          const float* p = sb + ((a.z0 - za) * BY + ry) * BX + rx;
+      // interior slab: the staged box lies inside the volume and no sample of it is clamped -- positions need no
+      // clamping and every footprint is inside the box by construction (tile-uniform test)
+      const bool interior = za >= 1 && za + BZ <= g.D - 1 && oy >= 0 && oy + BY <= g.H && ox >= 0 && ox + BX <= g.W;
+      if (interior) {
+        const float czl = l.cz - (float)za, cyl = l.cy - (float)oy, cxl = l.cx - (float)ox;   // (unused: see below)
+        (void)czl; (void)cyl; (void)cxl;
+        const int base = -((za * BY + oy) * BX + ox);
+        auto sample_in = [&](float fi, int& z0) -> float {   // same values as locate3 + lerp_planes, clamps are no-ops here
+          const float z = fmaf(l.kz, fi, l.cz), y = fmaf(l.ky, fi, l.cy), x = fmaf(l.kx, fi, l.cx);
+          z0 = (int)z;
+          const int y0 = (int)y, x0 = (int)x;
+          const float* p = sb + ((z0 * BY + y0) * BX + x0 + base);
+          Plane4 lo, hi;
           lo.a = p[0]; lo.b = p[1]; lo.c = p[BX]; lo.d = p[BX + 1];
-          const float* q = p + BY * BX;
-          hi.a = q[0]; hi.b = q[1]; hi.c = q[BX]; hi.d = q[BX + 1];
-        } else {                                             // outside the staged box (round-off at its rim): gather
-          const float* p = vol + ((int64_t)a.z0 * g.H + a.y0) * g.W + a.x0;
-          lo = load_plane(p, g.W); hi = load_plane(p + g.HW, g.W);
+          hi.a = p[BY * BX]; hi.b = p[BY * BX + 1]; hi.c = p[BY * BX + BX]; hi.d = p[BY * BX + BX + 1];
+          Cell c; c.idx = 0; c.fz = z - (float)z0; c.fy = y - (float)y0; c.fx = x - (float)x0;
+          return lerp_planes(lo, hi, c);
+        };
+        while (i - 3 >= i_lo) {
+          if ((int)fmaf(l.kz, (float)(i - 3), l.cz) < za) break;     // the group's lowest sample is in a later slab
+          int zz;
+          const float d0 = sample_in((float)i, zz), d1 = sample_in((float)(i - 1), zz), d2 = sample_in((float)(i - 2), zz),
+                      d3 = sample_in((float)(i - 3), zz);
+          S += d0; I = fmaf(d0, fast_exp2(S * ntl2), I);     // inclusive reverse cumsum, styler_3p.py:155
+          S += d1; I = fmaf(d1, fast_exp2(S * ntl2), I);
+          S += d2; I = fmaf(d2, fast_exp2(S * ntl2), I);
+          S += d3; I = fmaf(d3, fast_exp2(S * ntl2), I);
+          i -= 4;
         }
-        Cell c; c.idx = 0; c.fz = a.fz; c.fy = a.fy; c.fx = a.fx;
-        const float d = lerp_planes(lo, hi, c);
-        S += d;                                              // inclusive reverse cumsum, styler_3p.py:155
-        I = fmaf(d, fast_exp2(S * ntl2), I);
-        --i;
+        while (i >= i_lo) {
+          if ((int)fmaf(l.kz, (float)i, l.cz) < za) break;
+          int zz;
+          const float d = sample_in((float)i, zz);
+          S += d;
+          I = fmaf(d, fast_exp2(S * ntl2), I);
+          --i;
+        }
+      } else {
+        auto sample = [&](const Anchor& a) -> float {        // one trilinear sample out of the staged slab
+          const int ry = a.y0 - oy, rx = a.x0 - ox;
+          Plane4 lo, hi;
+          if ((unsigned)ry < (unsigned)(BY - 1) && (unsigned)rx < (unsigned)(BX - 1)) {
+            const float* p = sb + ((a.z0 - za) * BY + ry) * BX + rx;
+            lo.a = p[0]; lo.b = p[1]; lo.c = p[BX]; lo.d = p[BX + 1];
+            const float* q = p + BY * BX;
+            hi.a = q[0]; hi.b = q[1]; hi.c = q[BX]; hi.d = q[BX + 1];
+          } else {                                           // clamped onto a face, outside the staged box: gather
+            const float* p = vol + ((int64_t)a.z0 * g.H + a.y0) * g.W + a.x0;
+            lo = load_plane(p, g.W); hi = load_plane(p + g.HW, g.W);
+          }
+          Cell c; c.idx = 0; c.fz = a.fz; c.fy = a.fy; c.fx = a.fx;
+          return lerp_planes(lo, hi, c);
+        };
+        while (i >= i_lo) {
+          const Anchor a = locate3(l, (float)i, g);
+          if (a.z0 < za) break;                              // belongs to a slab further back
+          const float d = sample(a);
+          S += d;
+          I = fmaf(d, fast_exp2(S * ntl2), I);
+          --i;
+        }
       }
       __syncthreads();                                       // every ray is done with this buffer
       if (threadIdx.x == 0 && s + 2 < nslab) {
@@ -285,25 +328,298 @@ __global__ void __launch_bounds__(rm::THREADS) raymarch_fwd_tma_k(const __grid_c
   }
 }
 
+
+// =====================================================================================================================
+// Rotated ray-march, backward.  Same CTA tile and TMA slabs as the forward kernel (the density is re-sampled from shared
+// memory to rebuild T_k and the running sums), ascending in z.  What bounds this kernel is the scatter of the 8 corner
+// contributions of every sample (red.global.add.f32: LSU-bound, ~1.3 cycles per lane and instruction), so the thread
+// layout is chosen for MERGING them before they leave the SM:
+//   * a warp is a 4 x 8 pixel patch; its lanes walk the depth index in lockstep (warp-uniform i range per slab);
+//   * depth: a sample's far plane waits in registers and is merged into the next sample's near plane (anchor + 1 in z);
+//   * x: lane (r,c) hands its x1 column to lane (r,c+1) when that lane's anchor is one voxel to the right;
+//   * y: lane (r,c) hands its (y1,x0) value to lane (r+1,c) when that lane's anchor is one voxel down.
+// With the reference's small view angles nearly every voxel then receives ONE atomic per view instead of eight.
+// Slabs overlap by two planes so that a warp-uniform i range exists whose samples all sit inside one slab (the z shear
+// across a 4 x 8 patch is below two voxels for every view the slab box admits).
+// =====================================================================================================================
+template <int BZ>
+__global__ void __launch_bounds__(rm::THREADS) raymarch_bwd_tma_k(const __grid_constant__ CUtensorMap map_vol,
+                                                                  const float* __restrict__ vol,
+                                                                  const float* __restrict__ rot, RayGeo g, BoxF bf,
+                                                                  const int2* __restrict__ iv, float tau, float ntl2,
+                                                                  const float* __restrict__ stot,
+                                                                  const float* __restrict__ g_img,
+                                                                  float* __restrict__ g_vol, int tiles_w) {
+  using namespace rm;
+  constexpr int SLAB = BZ * BY * BX;
+  constexpr int ADV = BZ - 3;                                 // slab advance: BZ - 1 anchors per slab, two of them overlap
+  extern __shared__ unsigned char smem_raw[];
+  float* slab = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  __shared__ __align__(8) uint64_t bar_store[2];
+  __shared__ int s_ztop, s_zbot;
+  const int view = blockIdx.y;
+  const float* R = rot + 9 * view;
+  const int th = blockIdx.x / tiles_w, tw = blockIdx.x - th * tiles_w;
+  const int h0 = th * TH, w0 = tw * TW;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ly = (warp >> 2) * 4 + (lane >> 3), lx = (warp & 3) * 8 + (lane & 7);   // 4 x 8 pixel patch per warp
+  const int h = h0 + ly, w = w0 + lx;
+  const bool valid = h < g.H && w < g.W;
+  const int hc = min(h, g.H - 1), wc = min(w, g.W - 1);
+  const RayLine l = ray_line(R, lin_coord(hc, g.sH), lin_coord(wc, g.sW), g);
+  float gI = 0.f, St = 0.f;
+  int i_lo = 0x7fffffff, i_hi = -1;
+  if (valid) {
+    gI = g_img[(int64_t)view * g.HW + h * g.W + w];
+    St = stot[(int64_t)view * g.HW + h * g.W + w];
+    if (gI != 0.f) {
+      if (iv) { const int2 r = iv[(int64_t)view * g.HW + h * g.W + w]; i_lo = r.x; i_hi = r.y; }
+      else ray_interval(l, g, bf, i_lo, i_hi);
+      if (i_lo > i_hi) { i_lo = 0x7fffffff; i_hi = -1; }
+    }
+  }
+  const bool has = i_lo <= i_hi;
+  if (threadIdx.x == 0) {
+    s_ztop = -1; s_zbot = 0x7fffffff;
+    tma::mbar_init(tma::smem_u32(&bar_store[0]), 1);
+    tma::mbar_init(tma::smem_u32(&bar_store[1]), 1);
+    tma::fence_mbar_init();
+  }
+  __syncthreads();
+  const int h1 = min(h0 + TH, g.H) - 1, w1 = min(w0 + TW, g.W) - 1;
+  const TileSpan sy = tile_span(R, g, h0, h1, w0, w1, 1), sx = tile_span(R, g, h0, h1, w0, w1, 2);
+  // z shear across a warp's 4 x 8 patch must stay below the two overlapping planes
+  const float shear = 3.f * fabsf(R[1] * g.sH * g.hD) + 7.f * fabsf(R[2] * g.sW * g.hD);
+  const bool fits = l.kz > 0.5f && shear < 1.9f && (sy.hi - sy.lo) + fabsf(sy.r) * (float)BZ + 4.f <= (float)BY &&
+                    (sx.hi - sx.lo) + fabsf(sx.r) * (float)BZ + 7.f <= (float)BX;
+  if (!fits) {                                               // oblique view: plain 8-corner scatter, no staging
+    float below = 0.f, Pk = 0.f;
+    for (int i = i_lo; i <= i_hi; ++i) {
+      const Cell c = locate(l, (float)i, g);
+      const float* p = vol + c.idx;
+      const Plane4 lo = load_plane(p, g.W), hi = load_plane(p + g.HW, g.W);
+      const float d = lerp_planes(lo, hi, c);
+      const float T = fast_exp2((St - below) * ntl2);
+      Pk = fmaf(d, T, Pk);
+      below += d;
+      const float gk = gI * fmaf(-tau, Pk, T);
+      const float g1 = gk * c.fz, g0 = gk - g1;
+      const float g01 = g0 * c.fy, g00 = g0 - g01, g11 = g1 * c.fy, g10 = g1 - g11;
+      const float c001 = g00 * c.fx, c011 = g01 * c.fx, c101 = g10 * c.fx, c111 = g11 * c.fx;
+      float* q = g_vol + c.idx;
+      atomicAdd(q, g00 - c001); atomicAdd(q + 1, c001); atomicAdd(q + g.W, g01 - c011); atomicAdd(q + g.W + 1, c011);
+      q += g.HW;
+      atomicAdd(q, g10 - c101); atomicAdd(q + 1, c101); atomicAdd(q + g.W, g11 - c111); atomicAdd(q + g.W + 1, c111);
+    }
+    return;
+  }
+  if (has) {
+    atomicMax(&s_ztop, locate3(l, (float)i_hi, g).z0);
+    atomicMin(&s_zbot, locate3(l, (float)i_lo, g).z0);
+  }
+  __syncthreads();
+  const int ztop = s_ztop, zbot = s_zbot;
+  if (ztop < zbot) return;                                   // nothing live in this tile
+  const int nslab = (ztop - zbot) / ADV + 1;                 // slab s: anchors [za, za + BZ - 2], za = zbot + s ADV
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 2 && s < nslab; ++s) {
+      const int za = zbot + s * ADV;
+      const uint32_t bar = tma::smem_u32(&bar_store[s]);
+      tma::mbar_expect_tx(bar, SLAB * 4);
+      tma::load_3d(tma::smem_u32(slab + s * SLAB), &map_vol, bar, span_origin(sx, za, za + BZ - 2, g.mW, true),
+                   span_origin(sy, za, za + BZ - 2, g.mH, false), za);
+    }
+  }
+  // warp-uniform depth range
+  int w_lo = i_lo, w_hi = i_hi;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    w_lo = min(w_lo, __shfl_xor_sync(0xffffffffu, w_lo, o));
+    w_hi = max(w_hi, __shfl_xor_sync(0xffffffffu, w_hi, o));
+  }
+  // first depth index of this lane whose anchor plane is >= z (anchors do not decrease with i: kz > 0.5)
+  auto first_i = [&](int z) -> int {
+    int i = (int)ceilf(((float)z - l.cz) / l.kz);
+    i = min(max(i, 0), g.D - 1);
+    while (i > 0 && locate3(l, (float)(i - 1), g).z0 >= z) --i;
+    while (i < g.D - 1 && locate3(l, (float)i, g).z0 < z) ++i;
+    if (locate3(l, (float)i, g).z0 < z) i = g.D;             // never reaches plane z
+    return i;
+  };
+  float below = 0.f, Pk = 0.f;
+  Plane4 pend;                                               // far-plane contributions waiting for the next sample
+  pend.a = pend.b = pend.c = pend.d = 0.f;
+  int pend_idx = -1;
+  int i_beg = w_lo;
+  const bool xr = (lane & 7) != 7, yr = lane < 24;           // has a right / lower neighbour inside the warp's patch
+  for (int s = 0; s < nslab; ++s) {
+    const int buf = s & 1;
+    const int za = zbot + s * ADV;
+    const int oy = span_origin(sy, za, za + BZ - 2, g.mH, false), ox = span_origin(sx, za, za + BZ - 2, g.mW, true);
+    int i_end = w_hi + 1;
+    if (s + 1 < nslab) {
+      int f = has ? first_i(za + ADV) : 0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) f = max(f, __shfl_xor_sync(0xffffffffu, f, o));
+      i_end = min(i_end, f);
+    }
+    tma::mbar_wait(tma::smem_u32(&bar_store[buf]), (uint32_t)((s >> 1) & 1));
+    const float* sb = slab + buf * SLAB;
+    const int base = -((za * BY + oy) * BX + ox);
+    for (int i = i_beg; i < i_end; ++i) {
+      const bool live = i >= i_lo && i <= i_hi;
+      const Anchor a = locate3(l, (float)min(i, g.D - 1), g);
+      const int gidx = (a.z0 * g.H + a.y0) * g.W + a.x0;
+      float gk = 0.f;
+      if (live) {
+        const int ry = a.y0 - oy, rx = a.x0 - ox, rz = a.z0 - za;
+        Plane4 lo, hi;
+        if ((unsigned)ry < (unsigned)(BY - 1) && (unsigned)rx < (unsigned)(BX - 1) && (unsigned)rz < (unsigned)(BZ - 1)) {
+          const float* p = sb + ((a.z0 * BY + a.y0) * BX + a.x0 + base);
+          lo.a = p[0]; lo.b = p[1]; lo.c = p[BX]; lo.d = p[BX + 1];
+          hi.a = p[BY * BX]; hi.b = p[BY * BX + 1]; hi.c = p[BY * BX + BX]; hi.d = p[BY * BX + BX + 1];
+        } else {                                             // clamped onto a face / rim of the box: gather
+          const float* p = vol + gidx;
+          lo = load_plane(p, g.W); hi = load_plane(p + g.HW, g.W);
+        }
+        Cell c; c.idx = 0; c.fz = a.fz; c.fy = a.fy; c.fx = a.fx;
+        const float d = lerp_planes(lo, hi, c);
+        const float T = fast_exp2((St - below) * ntl2);
+        Pk = fmaf(d, T, Pk);
+        below += d;
+        gk = gI * fmaf(-tau, Pk, T);
+      }
+      const float g1 = gk * a.fz, g0 = gk - g1;
+      const float g01 = g0 * a.fy, g00 = g0 - g01, g11 = g1 * a.fy, g10 = g1 - g11;
+      float n01 = g00 * a.fx, n11 = g01 * a.fx;              // near plane: (y0,x1), (y1,x1)
+      float n00 = g00 - n01, n10 = g01 - n11;                //             (y0,x0), (y1,x0)
+      const float f01 = g10 * a.fx, f11 = g11 * a.fx;        // far plane
+      const float f00 = g10 - f01, f10 = g11 - f11;
+      // depth: merge the waiting plane into this sample's near plane, or write it out
+      if (pend_idx >= 0) {
+        if (live && pend_idx == gidx) {
+          n00 += pend.a; n01 += pend.b; n10 += pend.c; n11 += pend.d;
+        } else {
+          float* f = g_vol + pend_idx;
+          atomicAdd(f, pend.a); atomicAdd(f + 1, pend.b); atomicAdd(f + g.W, pend.c); atomicAdd(f + g.W + 1, pend.d);
+        }
+        pend_idx = -1;
+      }
+      // x: hand the x1 column to the right neighbour when its anchor is one voxel to the right
+      const int my = live ? gidx : -0x40000000;
+      const int nbx = __shfl_down_sync(0xffffffffu, my, 1);
+      const bool give_x = xr && live && nbx == my + 1;
+      const float rx0 = __shfl_up_sync(0xffffffffu, give_x ? n01 : 0.f, 1);
+      const float rx1 = __shfl_up_sync(0xffffffffu, give_x ? n11 : 0.f, 1);
+      if ((lane & 7) != 0) { n00 += rx0; n10 += rx1; }
+      // y: hand the (y1,x0) value to the lane one row down when its anchor is one voxel down
+      const int nby = __shfl_down_sync(0xffffffffu, my, 8);
+      const bool give_y = yr && live && nby == my + g.W;
+      const float ry0 = __shfl_up_sync(0xffffffffu, give_y ? n10 : 0.f, 8);
+      if (lane >= 8) n00 += ry0;
+      if (live) {
+        float* p = g_vol + gidx;
+        atomicAdd(p, n00);
+        if (!give_y) atomicAdd(p + g.W, n10);
+        if (!give_x) { atomicAdd(p + 1, n01); atomicAdd(p + g.W + 1, n11); }
+        pend.a = f00; pend.b = f01; pend.c = f10; pend.d = f11;
+        pend_idx = gidx + g.HW;
+      }
+    }
+    i_beg = max(i_beg, i_end);
+    __syncthreads();                                         // every warp is done with this buffer
+    if (threadIdx.x == 0 && s + 2 < nslab) {
+      const int zn = zbot + (s + 2) * ADV;
+      const uint32_t bar = tma::smem_u32(&bar_store[buf]);
+      tma::mbar_expect_tx(bar, SLAB * 4);
+      tma::load_3d(tma::smem_u32(slab + buf * SLAB), &map_vol, bar, span_origin(sx, zn, zn + BZ - 2, g.mW, true),
+                   span_origin(sy, zn, zn + BZ - 2, g.mH, false), zn);
+    }
+  }
+  if (pend_idx >= 0) {
+    float* f = g_vol + pend_idx;
+    atomicAdd(f, pend.a); atomicAdd(f + 1, pend.b); atomicAdd(f + g.W, pend.c); atomicAdd(f + g.W + 1, pend.d);
+  }
+}
+
+static int rm_slab_planes = 12;   // tuning switch (microbenchmarks): planes per TMA slab of the ray-march kernels, 8 / 12 / 16
+                                  // (C3 on the B200, exact intervals: forward 78 / 68 / 70 us; the gather kernel 81 us)
+extern "C" int lnst_set_raymarch_slab(int32_t planes) {
+  if (planes != 8 && planes != 12 && planes != 16) return LNST_EARG;
+  rm_slab_planes = planes;
+  return LNST_OK;
+}
+
+template <int BZ>
+static int launch_rm_fwd(const CUtensorMap& mv, const float* vol, const float* rot, int n_views, const RayGeo& g,
+                         const BoxF& bf, const int2* iv, float ntl2, int liquid, float* img, float* stot, cudaStream_t st) {
+  using namespace rm;
+  const int tiles_h = (g.H + TH - 1) / TH, tiles_w = (g.W + TW - 1) / TW;
+  const int smem = 2 * BZ * BY * BX * 4 + 128;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(raymarch_fwd_tma_k<BZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  raymarch_fwd_tma_k<BZ><<<dim3((unsigned)(tiles_h * tiles_w), (unsigned)n_views), THREADS, smem, st>>>(
+      mv, vol, rot, g, bf, iv, ntl2, liquid, img, stot, tiles_w);
+  return (int)cudaGetLastError();
+}
+
 extern "C" int lnst_raymarch_fwd_tma(const float* vol, const float* rot, int32_t n_views, int32_t D, int32_t H,
                                      int32_t W, float tau, int32_t liquid, const LnstBox* box, const int32_t* intervals,
                                      float* img, float* stot, void* stream) {
   using namespace rm;
   if (!vol || !rot || !img || !stot || n_views < 1 || D < 2 || H < 2 || W < 2 || !box_ok(box, D, H, W)) return LNST_EARG;
   if ((int64_t)D * H * W >= 0x7fffffff) return LNST_EARG;
+  const int bz = rm_slab_planes;
   CUtensorMap mv;
-  if (!tma::make_volume_map(&mv, vol, D, H, W, BZ, BY, BX)) return LNST_EARG;
+  if (!tma::make_volume_map(&mv, vol, D, H, W, bz, BY, BX)) return LNST_EARG;
   const RayGeo g = make_geo(D, H, W);
-  const int tiles_h = (H + TH - 1) / TH, tiles_w = (W + TW - 1) / TW;
-  const int smem = 2 * SLAB * 4 + 128;
+  const BoxF bf = make_boxf(box, D, H, W);
+  const int2* iv = reinterpret_cast<const int2*>(intervals);
+  const float ntl2 = -tau * 1.4426950408889634f;
+  cudaStream_t st = lnst_stream(stream);
+  if (bz == 8) return launch_rm_fwd<8>(mv, vol, rot, n_views, g, bf, iv, ntl2, (int)liquid, img, stot, st);
+  if (bz == 12) return launch_rm_fwd<12>(mv, vol, rot, n_views, g, bf, iv, ntl2, (int)liquid, img, stot, st);
+  return launch_rm_fwd<16>(mv, vol, rot, n_views, g, bf, iv, ntl2, (int)liquid, img, stot, st);
+}
+
+template <int BZ>
+static int launch_rm_bwd(const CUtensorMap& mv, const float* vol, const float* rot, int n_views, const RayGeo& g,
+                         const BoxF& bf, const int2* iv, float tau, const float* stot, const float* g_img, float* g_vol,
+                         cudaStream_t st) {
+  using namespace rm;
+  const int tiles_h = (g.H + TH - 1) / TH, tiles_w = (g.W + TW - 1) / TW;
+  const int smem = 2 * BZ * BY * BX * 4 + 128;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(raymarch_fwd_tma_k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(raymarch_bwd_tma_k<BZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }
-  raymarch_fwd_tma_k<<<dim3((unsigned)(tiles_h * tiles_w), (unsigned)n_views), THREADS, smem, lnst_stream(stream)>>>(
-      mv, vol, rot, g, make_boxf(box, D, H, W), reinterpret_cast<const int2*>(intervals), -tau * 1.4426950408889634f,
-      (int)liquid, img, stot, tiles_w);
+  raymarch_bwd_tma_k<BZ><<<dim3((unsigned)(tiles_h * tiles_w), (unsigned)n_views), THREADS, smem, st>>>(
+      mv, vol, rot, g, bf, iv, tau, -tau * 1.4426950408889634f, stot, g_img, g_vol, tiles_w);
   return (int)cudaGetLastError();
+}
+
+// smoke render only (the liquid render's gradient does not depend on the samples: lnst_raymarch_bwd_box handles it)
+extern "C" int lnst_raymarch_bwd_tma(const float* vol, const float* rot, int32_t n_views, int32_t D, int32_t H,
+                                     int32_t W, float tau, const LnstBox* box, const int32_t* intervals,
+                                     const float* stot, const float* g_img, float* g_vol, void* stream) {
+  using namespace rm;
+  if (!vol || !rot || !stot || !g_img || !g_vol || n_views < 1 || D < 2 || H < 2 || W < 2 || !box_ok(box, D, H, W))
+    return LNST_EARG;
+  if ((int64_t)D * H * W >= 0x3fffffff) return LNST_EARG;
+  const int bz = rm_slab_planes;
+  CUtensorMap mv;
+  if (!tma::make_volume_map(&mv, vol, D, H, W, bz, BY, BX)) return LNST_EARG;
+  const RayGeo g = make_geo(D, H, W);
+  const BoxF bf = make_boxf(box, D, H, W);
+  const int2* iv = reinterpret_cast<const int2*>(intervals);
+  cudaStream_t st = lnst_stream(stream);
+  if (bz == 8) return launch_rm_bwd<8>(mv, vol, rot, n_views, g, bf, iv, tau, stot, g_img, g_vol, st);
+  if (bz == 12) return launch_rm_bwd<12>(mv, vol, rot, n_views, g, bf, iv, tau, stot, g_img, g_vol, st);
+  return launch_rm_bwd<16>(mv, vol, rot, n_views, g, bf, iv, tau, stot, g_img, g_vol, st);
 }

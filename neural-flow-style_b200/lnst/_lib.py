@@ -53,6 +53,7 @@ SIGNATURES = {
     'lnst_raymarch_fwd_box': [vp, vp, i32, i32, i32, i32, f32, i32, BP, vp, vp, vp, vp],
     'lnst_raymarch_bwd_box': [vp, vp, i32, i32, i32, i32, f32, i32, BP, vp, vp, vp, vp, vp],
     'lnst_ray_intervals': [vp, i32, i32, i32, i32, BP, vp, vp, vp],
+    'lnst_ray_intervals_exact': [vp, i32, i32, i32, i32, BP, vp, vp, vp],
     'lnst_set_raymarch_merge': [i32],
     'lnst_image_max': [vp, i32, i64, vp, vp],
     'lnst_normalize_fwd': [vp, vp, i32, i64, vp, vp],
@@ -134,9 +135,11 @@ CUDA_ONLY = {
     'lnst_f32_to_bf16': [vp, vp, i64, vp],
     # TMA-tiled volume kernels (csrc/tiles_tma.cu)
     'lnst_tma_supported': [],
+    'lnst_set_raymarch_slab': [i32],
     'lnst_smooth3_relu_fwd_tma': [vp, vp, i32, i32, i32, i32, BP, vp],
     'lnst_smooth3_relu_bwd_tma': [vp, vp, vp, i32, i32, i32, i32, BP, vp],
     'lnst_raymarch_fwd_tma': [vp, vp, i32, i32, i32, i32, f32, i32, BP, vp, vp, vp, vp],
+    'lnst_raymarch_bwd_tma': [vp, vp, i32, i32, i32, i32, f32, BP, vp, vp, vp, vp, vp],
     'lnst_bf16_to_f32': [vp, vp, i64, vp],
 }
 

@@ -91,6 +91,10 @@ def splat_wavg_bwd_coef(p, var, grid, hs, coef, g_out, g_var):
 # rows of a multiple of 4 floats and a 16-byte aligned base.  LNST_TMA=0 (or ``ops.USE_TMA = False``) keeps the SIMT
 # kernels -- the A/B switch of the parity tests and microbenchmarks.
 USE_TMA = os.environ.get('LNST_TMA', '1') not in ('0', '')
+# The TMA-slab ray-march BACKWARD is correct but slower than the gather kernel on the B200 (C3, exact intervals: 170 us
+# against 151 us -- its per-slab CTA barriers and 25 % occupancy cost more than the merged atomics save; DESIGN.md
+# section 3), so it is opt-in: LNST_TMA_BWD=1 or ``ops.USE_TMA_BWD = True``.
+USE_TMA_BWD = os.environ.get('LNST_TMA_BWD', '0') not in ('0', '')
 
 
 def _tma_ok(*vols):
@@ -156,6 +160,16 @@ def ray_intervals(rot, shape, box, bricks, out=None):
     return out
 
 
+def ray_intervals_exact(rot, shape, box, touch, out=None):
+    """int32 [n_views,H,W,2] like ``ray_intervals``, from the per-voxel footprint mask ``touch`` (uint8 [D,H,W])"""
+    D, H, W = shape
+    nv = rot.shape[0]
+    if out is None:
+        out = torch.empty(nv, H, W, 2, dtype=torch.int32, device=rot.device)
+    _lib.get().call('lnst_ray_intervals_exact', ptr(rot), nv, D, H, W, _b(box), _u8(touch), _u8(out), _s(rot))
+    return out
+
+
 def raymarch_fwd(vol, rot, tau, liquid, img, stot, box=None, intervals=None):
     D, H, W = vol.shape
     nv = 1 if rot is None else rot.shape[0]
@@ -171,6 +185,10 @@ def raymarch_fwd(vol, rot, tau, liquid, img, stot, box=None, intervals=None):
 def raymarch_bwd(vol, rot, tau, liquid, stot, g_img, g_vol, box=None, intervals=None):
     D, H, W = vol.shape
     nv = 1 if rot is None else rot.shape[0]
+    if USE_TMA_BWD and rot is not None and not liquid and min(D, H, W) >= 2 and D * H * W < 2 ** 30 - 1 and _tma_ok(vol):
+        _lib.get().call('lnst_raymarch_bwd_tma', ptr(vol), ptr(rot), nv, D, H, W, float(tau), _b(box), _u8(intervals),
+                        ptr(stot), ptr(g_img), ptr(g_vol), _s(vol))
+        return g_vol
     _lib.get().call('lnst_raymarch_bwd_box', ptr(vol), ptr(rot), nv, D, H, W, float(tau), int(bool(liquid)), _b(box),
                     _u8(intervals), ptr(stot), ptr(g_img), ptr(g_vol), _s(vol))
     return g_vol

@@ -245,7 +245,7 @@ class Styler(StylerBase):
         dev = self.device
         nk = self.num_kernels if 'd' in self.target_field else 1
         self._iv_cache = {}                                        # ray intervals belong to the old workspace's bricks
-        ws = {'grid': self._grid(res), 'res': res, 'box': None, 'bricks': None,
+        ws = {'grid': self._grid(res), 'res': res, 'box': None, 'bricks': None, 'touch': None,
               'num': torch.zeros(nk, D * H * W, dtype=f32, device=dev),
               'd': torch.zeros(D, H, W, dtype=f32, device=dev),
               'ds': torch.zeros(D, H, W, dtype=f32, device=dev),
@@ -273,10 +273,15 @@ class Styler(StylerBase):
                 o = mp(o, 4, 4, 0, ceil_mode=True)                        # bricks
                 o = mp(o, 3, 1, 1)                                        # + one brick
                 ws['bricks'] = (o[0, 0] > 0).to(torch.uint8).contiguous()
+                # exact footprint mask for fixed view sets: anchor voxel v is marked when any voxel of {v, v+1}^3 lies
+                # within one voxel (the blur) of a reachable cell
+                a = mp(occ.to(f32)[None, None], 3, 1, 1)
+                a = mp(torch.nn.functional.pad(a, (0, 1, 0, 1, 0, 1)), 2, 1, 0)
+                ws['touch'] = (a[0, 0] > 0).to(torch.uint8).contiguous()
             ws['box_cells'] = (hi[0] - lo[0] + 1) * (hi[1] - lo[1] + 1) * (hi[2] - lo[2] + 1)
         return ws
 
-    def _render(self, ds, rot, box=None, bricks=None, net_input=True, joint=False):
+    def _render(self, ds, rot, box=None, bricks=None, net_input=True, joint=False, touch=None):
         """ds [D,H,W] -> gray [nv,H,W,1] in [0,1] plus what the backward needs.  ``net_input=False``: the loss
         net starts from the gray image itself (``_gray_path``), d_img / x are not produced."""
         D, H, W = ds.shape
@@ -291,7 +296,10 @@ class Styler(StylerBase):
             if 'uniform' in self.sample_type and key in self._iv_cache:
                 iv = self._iv_cache[key]
             else:
-                iv = ops.ray_intervals(rot, ds.shape, box, bricks)
+                if 'uniform' in self.sample_type and touch is not None and getattr(self, 'exact_intervals', True):
+                    iv = ops.ray_intervals_exact(rot, ds.shape, box, touch)   # fixed views: pay one march, once
+                else:
+                    iv = ops.ray_intervals(rot, ds.shape, box, bricks)
                 if 'uniform' in self.sample_type:
                     self._iv_cache[key] = iv
         ops.raymarch_fwd(ds, rot, self.transmit, self.render_liquid, img, stot, box, iv)
@@ -366,7 +374,7 @@ class Styler(StylerBase):
             ds = ops.smooth3_relu_fwd(d, ws['ds'], self.k, box)    # styler_3p.py:112-125
         gray_path = self._gray_path()
         with nvtx('lnst.render_fwd'):
-            st = self._render(ds, rot, box, ws['bricks'], net_input=not gray_path, joint=group)
+            st = self._render(ds, rot, box, ws['bricks'], net_input=not gray_path, joint=group, touch=ws['touch'])
         nv = st['gray'].shape[0]
         loss = torch.zeros(nv, dtype=f32, device=self.device)
         g_gray0 = None
@@ -415,7 +423,7 @@ class Styler(StylerBase):
         d = self._density(fr, var, ws['res'], ws)
         ds = ops.smooth3_relu_fwd(d, ws['ds'], self.k, ws['box'])
         rot = self._eye if identity_view else None
-        st = self._render(ds, rot, ws['box'], ws['bricks'])
+        st = self._render(ds, rot, ws['box'], ws['bricks'], touch=ws['touch'])
         p_out = fr['p'] + var if 'p' in self.target_field else fr['p']
         return p_out, ds + 0.0, st['d_img'][0]                     # "+0.0" folds the -0.0 markers
 

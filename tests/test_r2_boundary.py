@@ -83,3 +83,42 @@ def test_density_reg(dev, n):
     close(loss, torch.tensor([1.0 + float(val), 2.0]), tol=3e-6, what='density loss')
     if n:
         close(grad, torch.tensor(g0).double() + vt.grad, tol=3e-6, what='density grad')
+
+
+def _blob(D, H, W, seed=0, frac=0.55):
+    rng = np.random.RandomState(seed)
+    z, y, x = np.meshgrid(np.linspace(-1, 1, D), np.linspace(-1, 1, H), np.linspace(-1, 1, W), indexing='ij')
+    rr = (z / frac) ** 2 + (y / (frac * 1.1)) ** 2 + (x / frac) ** 2
+    occ = rr < 1
+    v = np.where(occ, rng.rand(D, H, W) * (1.05 - rr), 0).astype(np.float32)
+    return v, occ
+
+
+@pytest.mark.parametrize('shape', [(16, 16, 16), (12, 18, 20)])
+def test_exact_ray_intervals_leave_the_render_and_its_gradient_unchanged(dev, shape):
+    """lnst_ray_intervals_exact: per ray the first / last sample whose footprint touches the support -- images stay bit
+    identical to the full march, the volume gradient is the same wherever the support (the only place it is read) is."""
+    import torch.nn.functional as Fn
+    D, H, W = shape
+    v, occ = _blob(D, H, W, seed=D)
+    vol = torch.tensor(v).to(dev)
+    act = torch.tensor(occ.astype(np.float32))[None, None]            # support of the volume itself (no blur here)
+    touch = (Fn.max_pool3d(Fn.pad(act, (0, 1, 0, 1, 0, 1)), 2, 1, 0)[0, 0] > 0).to(torch.uint8).contiguous().to(dev)
+    from lnst.transform import rot_mat
+    mats, _ = rot_mat(-5, 5, 5, -10, 10, 10, sample_type='uniform', rng=np.random.RandomState(0), nv=None)
+    rot = torch.tensor(np.asarray(mats, np.float64).reshape(-1, 9), dtype=torch.float32).to(dev)
+    nv = rot.shape[0]
+    iv = ops.ray_intervals_exact(rot, shape, None, touch)
+    lo, hi = iv[..., 0].cpu().numpy(), iv[..., 1].cpu().numpy()
+    assert ((hi - lo + 1).clip(0).sum()) < 0.8 * nv * D * H * W     # it does cut
+    outs = []
+    for use in (None, iv):
+        img, stot = torch.empty(nv, H, W).to(dev), torch.empty(nv, H, W).to(dev)
+        ops.raymarch_fwd(vol, rot, 0.05, False, img, stot, None, use)
+        g_img = torch.tensor(np.random.RandomState(1).randn(nv, H, W).astype(np.float32)).to(dev)
+        g_vol = torch.zeros(D, H, W).to(dev)
+        ops.raymarch_bwd(vol, rot, 0.05, False, stot, g_img, g_vol, None, use)
+        outs.append((img.cpu(), stot.cpu(), g_vol.cpu()))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    m = torch.tensor(occ)
+    close(outs[1][2][m], outs[0][2][m], tol=1e-5, what='gradient on the support')

@@ -20,7 +20,7 @@ def cuda_lib():
     assert lib.has_tma, 'TMA entry points missing from the CUDA library'
     yield
     torch.cuda.synchronize()
-    ops.USE_TMA = True
+    ops.USE_TMA, ops.USE_TMA_BWD = True, False
     _lib.set_for_testing(prev)
 
 
@@ -28,10 +28,10 @@ def both(fn):
     """run fn() with the SIMT and with the TMA kernels"""
     outs = []
     for tma in (False, True):
-        ops.USE_TMA = tma
+        ops.USE_TMA = ops.USE_TMA_BWD = tma
         n0 = _lib.get().launches
         outs.append(fn())
-    ops.USE_TMA = True
+    ops.USE_TMA, ops.USE_TMA_BWD = True, False
     return outs
 
 
@@ -91,3 +91,30 @@ def test_raymarch_fwd_tma_is_bit_identical(shape, phi, theta, liquid):
         (i0, s0), (i1, s1) = both(run)
         assert torch.equal(i0, i1) and torch.equal(s0, s1)
         assert float(i0.max()) > 0
+
+
+@pytest.mark.parametrize('shape,phi,theta', [((24, 24, 24), 5, 10), ((200, 200, 200), 5, 10), ((20, 28, 36), 5, 10),
+                                             ((40, 40, 40), 40, 60), ((64, 64, 64), 12, 15), ((33, 30, 32), 0, 0),
+                                             ((48, 48, 48), 2, 25)])
+def test_raymarch_bwd_tma_equals_simt(shape, phi, theta):
+    """gradient of the rotated render w.r.t. the volume: TMA-slab kernel (4 x 8 warp patches, depth / x / y merges of the
+    corner atomics) against the SIMT kernel -- same sums in another order"""
+    D, H, W = shape
+    vol, box = blob(D, H, W, seed=H)
+    rot = views(phi, theta) if phi or theta else torch.eye(3).reshape(1, 9).to(DEV)
+    nv = rot.shape[0]
+    g_img = torch.tensor(np.random.RandomState(2).randn(nv, H, W).astype(np.float32)).to(DEV)
+    g_img[:, ::5, ::3] = 0.0                                  # rays without a cotangent are skipped
+    for bx in (None, box):
+        iv = ops.ray_intervals(rot, (D, H, W), bx, None) if bx is not None else None
+        img = torch.empty(nv, H, W, device=DEV)
+        stot = torch.empty(nv, H, W, device=DEV)
+        ops.raymarch_fwd(vol, rot, 0.03, False, img, stot, bx, iv)
+
+        def run():
+            g_vol = torch.zeros(D, H, W, device=DEV)
+            ops.raymarch_bwd(vol, rot, 0.03, False, stot, g_img, g_vol, bx, iv)
+            return g_vol
+        g0, g1 = both(run)
+        assert float(g0.abs().max()) > 0
+        assert (g0 - g1).abs().max() <= 2e-5 * g0.abs().max(), float((g0 - g1).abs().max() / g0.abs().max())

@@ -41,11 +41,14 @@ def main():
     ap.add_argument('--workload', default='C3')
     ap.add_argument('--reps', type=int, default=10)
     ap.add_argument('--only', default='')
+    ap.add_argument('--rm-slab', dest='rm_slab', type=int, default=0)
     args = ap.parse_args()
     from lnst import _lib, ops, synth
     from lnst.styler_3p import Styler
     dev = torch.device('cuda:0')
     lib = _lib.get()
+    if args.rm_slab:
+        lib.call('lnst_set_raymarch_slab', args.rm_slab)
     wl = bench.WORKLOADS[args.workload]
     cfg = bench.make_cfg(args.workload, 'allreduce', 'bf16')
     p, r, sty = bench.make_scene(args.workload)
@@ -93,6 +96,13 @@ def main():
     bricks = ops.ray_intervals(rot, ds.shape, box, ws['bricks']) if rot is not None else None
     add('ray_intervals', lambda: ops.ray_intervals(rot, ds.shape, box, ws['bricks']), nv * 8 * P)
     add('raymarch_fwd', lambda: ops.raymarch_fwd(ds, rot, st.transmit, False, img, stot, box, bricks), nv * (4 * Vb + 8 * P))
+    exact = ops.ray_intervals_exact(rot, ds.shape, box, ws['touch']) if rot is not None and ws.get('touch') is not None else None
+    if exact is not None:
+        live = lambda t: int((t[..., 1] - t[..., 0] + 1).clamp(min=0).sum())
+        print('live samples: bricks %d, exact %d' % (live(bricks), live(exact)))
+        add('ray_intervals_exact', lambda: ops.ray_intervals_exact(rot, ds.shape, box, ws['touch']), nv * 8 * P)
+        add('raymarch_fwd(exact iv)', lambda: ops.raymarch_fwd(ds, rot, st.transmit, False, img, stot, box, exact), nv * (4 * Vb + 8 * P))
+        add('raymarch_bwd(exact iv)', lambda: ops.raymarch_bwd(ds, rot, st.transmit, False, stot, g_img, g_ds, box, exact), nv * (8 * Vb + 8 * P))
     if rot is not None:
         lib.call('lnst_set_raymarch_merge', 0)
         add('raymarch_bwd(merge=0)', lambda: ops.raymarch_bwd(ds, rot, st.transmit, False, stot, g_img, g_ds, box),
