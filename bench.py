@@ -52,7 +52,7 @@ WORKLOADS = {
 }
 ACTIVE_CELLS = 0   # cells of the workload's active box (set by run_engine)
 KERNELS_PER_CALL = {'lnst_splat_wavg_fwd_box': 2, 'lnst_adam_step_dev': 2, 'lnst_image_max': 2, 'lnst_normalize_bwd': 2, 'lnst_gram_diff': 2,
-                    'lnst_gram_diff_bf16_tc': 2, 'lnst_gram_diff_bf16x3_tc': 3, 'lnst_density_reg': 2}
+                    'lnst_gram_diff_bf16_tc': 2, 'lnst_gram_diff_bf16x3_tc': 2, 'lnst_density_reg': 2}
 TENSOR_BOUND = ('lnst_conv3x3_f32', 'lnst_conv2d_f32', 'lnst_conv2d_bwd_data_f32', 'lnst_conv3x3_bf16_tc', 'lnst_gram_diff', 'lnst_gram_bwd', 'lnst_gram_diff_bf16_tc',
                 'lnst_gram_bwd_bf16_tc', 'lnst_conv3x3_bf16x3_tc', 'lnst_gram_diff_bf16x3_tc', 'lnst_gram_bwd_bf16x3_tc')
 # bf16x3 entry points execute three bf16 MMA passes per algorithmic (fp32) multiply-add
@@ -359,42 +359,60 @@ def measure_step(ctx, wl, view_mode, conv_math, steps, warmup, full=True):
     # back, styler_3p.py:312,331,334).  p and r do not depend on the previous step, so their upload for
     # step i+1 runs on a copy stream under step i (into staging buffers, then one device copy into the
     # buffers the step's graph reads); the variable's round trip is sequential by construction.
-    hp = fr['p'].cpu().pin_memory()                      # host copies in the engine's (cell-sorted) order
-    hr = fr['r'].cpu().pin_memory()
-    hg = g_opt.cpu().pin_memory()
+    # With several ranks every rank feeds only ITS 1/W slice of p, r and the variable over PCIe and the slices are
+    # all-gathered over NVLink (one collective per tensor), and reads back its slice of the variable (+ the loss).
+    n_rows = fr['p'].shape[0]
+    chunk = (n_rows + world - 1) // world
+    lo_r, hi_r = min(rank * chunk, n_rows), min((rank + 1) * chunk, n_rows)
+    hp = fr['p'][lo_r:hi_r].cpu().pin_memory()           # host copies in the engine's (cell-sorted) order
+    hr = fr['r'][lo_r:hi_r].cpu().pin_memory()
+    hg = g_opt[lo_r:hi_r].cpu().pin_memory()
     hl = torch.zeros(1).pin_memory()
-    sp, sr = torch.empty_like(fr['p']), torch.empty_like(fr['r'])
+    sp = torch.zeros(world * chunk, fr['p'].shape[1], device=dev)      # staging, padded to W equal chunks
+    sr = torch.zeros(world * chunk, fr['r'].shape[1], device=dev)
+    sg = torch.zeros(world * chunk, g_opt.shape[1], device=dev)
     cs = torch.cuda.Stream(device=dev)
     main = torch.cuda.current_stream(dev)
     e2e_steps = max(3, min(steps, 10))
+
+    def gather(full):
+        if world > 1:
+            ctx.dist.all_gather_into_tensor(full, full[rank * chunk:(rank + 1) * chunk])
+
     ctx.barrier()
     w0 = time.perf_counter()
     uploaded, consumed = torch.cuda.Event(), torch.cuda.Event()
     with torch.cuda.stream(cs):
-        sp.copy_(hp, non_blocking=True)
-        sr.copy_(hr, non_blocking=True)
+        sp[lo_r:hi_r].copy_(hp, non_blocking=True)
+        sr[lo_r:hi_r].copy_(hr, non_blocking=True)
         uploaded.record(cs)
     for i in range(e2e_steps):
         main.wait_event(uploaded)
-        fr['p'].copy_(sp, non_blocking=True)
-        fr['r'].copy_(sr, non_blocking=True)
+        gather(sp)
+        gather(sr)
+        fr['p'].copy_(sp[:n_rows], non_blocking=True)
+        fr['r'].copy_(sr[:n_rows], non_blocking=True)
         consumed.record(main)
         if i + 1 < e2e_steps:                            # next step's particle upload, under this step
             with torch.cuda.stream(cs):
                 cs.wait_event(consumed)
-                sp.copy_(hp, non_blocking=True)
-                sr.copy_(hr, non_blocking=True)
+                sp[lo_r:hi_r].copy_(hp, non_blocking=True)
+                sr[lo_r:hi_r].copy_(hr, non_blocking=True)
                 uploaded.record(cs)
-        g_opt.copy_(hg, non_blocking=True)
+        sg[lo_r:hi_r].copy_(hg, non_blocking=True)
+        gather(sg)
+        g_opt.copy_(sg[:n_rows], non_blocking=True)
         l = step()
-        hg.copy_(g_opt, non_blocking=True)
+        hg.copy_(g_opt[lo_r:hi_r], non_blocking=True)
         hl.copy_(l.reshape(1), non_blocking=True)
         main.synchronize()
     torch.cuda.synchronize()
     ctx.barrier()
     e2e_s = ctx.max_over_ranks(time.perf_counter() - w0)
-    out['e2e'] = {'value': e2e_steps / e2e_s, 'unit': 'iters/s', 'h2d_bytes_per_step': hp.numel() * 4 + hr.numel() * 4 + hg.numel() * 4,
-                  'd2h_bytes_per_step': hg.numel() * 4 + 4, 'steps': e2e_steps,
+    out['e2e'] = {'value': e2e_steps / e2e_s, 'unit': 'iters/s',
+                  'h2d_bytes_per_step': world * (hp.numel() * 4 + hr.numel() * 4 + hg.numel() * 4),
+                  'd2h_bytes_per_step': world * (hg.numel() * 4 + 4), 'steps': e2e_steps,
+                  'per_rank': 'each rank moves 1/%d of the rows over PCIe; slices all-gathered over NVLink' % world if world > 1 else 'single rank',
                   'boundary': "the reference's sess.run boundary per step (styler_3p.py:312,331,334): p, r and the variable "
                               'uploaded from pinned host memory, variable + loss read back'}
 
@@ -466,7 +484,7 @@ def time_run(make_styler, params, iters_a, iters_b, **run_kw):
     of their wall clocks over the difference in iterations (set-up, capture and the final inference cancel); also the
     whole wall clock of the longer run"""
     walls = []
-    for it in (iters_a, iters_b):
+    for it in (iters_a, iters_a, iters_b):               # the first run is an untimed warm-up (allocator, lazy initialisation)
         st = make_styler(it)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
@@ -474,6 +492,7 @@ def time_run(make_styler, params, iters_a, iters_b, **run_kw):
         torch.cuda.synchronize()
         walls.append(time.perf_counter() - t0)
         del st
+    walls = walls[1:]
     per_iter = max((walls[1] - walls[0]) / (iters_b - iters_a), 1e-9)
     return {'value': 1.0 / per_iter, 'unit': 'iters/s', 'ms_per_iter': 1e3 * per_iter, 'run_wall_s': walls[1],
             'run_iters': iters_b, 'final_loss': float(np.asarray(out['l'][-1]).reshape(-1)[-1])}

@@ -91,6 +91,10 @@ int lnst_splat_wavg_bwd(const float* p, const float* var, int64_t n, const LnstG
  * wmap == 0 -- TF's where/div rule), computed once per (frame, octave) like wmap; the gradient kernel
  * then needs no division.  Same result as lnst_splat_wavg_bwd. */
 int lnst_splat_wavg_coef(const float* wmap, int32_t nk, int64_t cells, float* coef, void* stream);
+/* Home cell of every particle (linear index over the unflipped [D,H,W] grid; -1: outside the domain / padding row; -2:
+ * valid but rounded onto the far face) and its offset from that cell's centre [n,3]: input of the per-cell particle
+ * lists the gather splat (lnst_splat_wavg_fwd_gather) walks.  3-D grids. */
+int lnst_splat_cells(const float* p, int64_t n, const LnstGrid* g, int32_t* cell, float* rel, void* stream);
 int lnst_splat_wavg_bwd_coef(const float* p, const float* var, int64_t n, const LnstGrid* g, const float* h,
                              int32_t nk, const float* coef, const float* g_out, float* g_var, void* stream);
 
@@ -270,6 +274,13 @@ int lnst_smooth3_relu_fwd_tma(const float* in, float* out, int32_t D, int32_t H,
                               void* stream);
 int lnst_smooth3_relu_bwd_tma(const float* g_out, const float* out, float* g_in, int32_t D, int32_t H, int32_t W,
                               int32_t k, const LnstBox* box, void* stream);
+/* p2g_wavg forward as a gather over per-cell particle lists: cstart [V+1] (first entry of every cell, cells in unflipped
+ * (z,y,x) order), order [Nv] (particle index per entry), rel [Nv,3] (lnst_splat_cells offsets in list order).  Writes
+ * out = sum_k where(wmap_k > 1e-6, num_k / wmap_k, num_k) for the cells of `box` (output coordinates, NULL = all) with
+ * one TMA store per 4 x 8 x 32 tile; wmap is accumulated on the fly.  nsize = 1, clip = 0. */
+int lnst_splat_wavg_fwd_gather(const int32_t* cstart, const int32_t* order, const float* rel, const float* r,
+                               const float* var, const LnstGrid* g, const float* h, int32_t nk, float* out,
+                               const LnstBox* box, void* stream);
 /* images bit-identical to lnst_raymarch_fwd_box (same per-sample arithmetic, same order along the ray) */
 int lnst_raymarch_fwd_tma(const float* vol, const float* rot, int32_t n_views, int32_t D, int32_t H, int32_t W, float tau,
                           int32_t liquid, const LnstBox* box, const int32_t* intervals, float* img, float* stot,

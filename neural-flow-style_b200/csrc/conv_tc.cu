@@ -1028,7 +1028,7 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t saddr) {
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gram_tc_k(const __grid_constant__ CUtensorMap map_f, float* __restrict__ G, int P, int C, int tiles_n,
-          int k_per_split) {
+          int k_per_split, int sym) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t smem_a = base;
@@ -1038,7 +1038,12 @@ gram_tc_k(const __grid_constant__ CUtensorMap map_f, float* __restrict__ G, int 
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = (blockIdx.x / tiles_n) * 128, n0 = (blockIdx.x % tiles_n) * 128;
+  int m0 = (blockIdx.x / tiles_n) * 128, n0 = (blockIdx.x % tiles_n) * 128;
+  if (sym) {                                             // F^T F is symmetric: only the tiles with m0 <= n0 are launched
+    int i = 0, rem = blockIdx.x;                         // (the epilogue stores them transposed: row block >= column block)
+    while (rem >= tiles_n - i) { rem -= tiles_n - i; ++i; }
+    m0 = i * 128; n0 = (i + rem) * 128;
+  }
   const int img = blockIdx.z;
   const int p_beg = blockIdx.y * k_per_split;
   const int p_end = min(P, p_beg + k_per_split);
@@ -1156,7 +1161,11 @@ __global__ void gram_finish_split_k(const float* __restrict__ G2, float* __restr
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_el; i += gridDim.x * blockDim.x) {
     const int r = i / C, c = i - r * C;
     const int64_t a = (int64_t)r * 2 * C + c;
-    float d = ((g2[a] + g2[a + C]) + (g2[a + (int64_t)2 * C * C] + g2[a + (int64_t)2 * C * C + C])) * inv_denom;
+    // G2 holds the 128 x 128 blocks with row block >= column block (gram_tc_k, sym): the others are read mirrored
+    auto at = [&](int R, int Cc) -> float {
+      return (R >> 7) >= (Cc >> 7) ? g2[(int64_t)R * 2 * C + Cc] : g2[(int64_t)Cc * 2 * C + R];
+    };
+    float d = ((at(r, c) + at(r, C + c)) + (at(C + r, c) + at(C + r, C + c))) * inv_denom;
     if (Gs) { d -= Gs[i]; s += d * d; }
     G[(int64_t)img * n_el + i] = d;
     if (Gd2) {
@@ -1919,11 +1928,9 @@ extern "C" int lnst_gram_bwd_bf16_tc(const void* F, const void* Gd, float coef, 
 // Gram difference on tensor cores, batched over images: G[i] = F[i]^T F[i] / denom - Gs (fp32, [n,C,C]),
 // Gd = bf16 copy of G (operand of lnst_gram_bwd_bf16_tc), loss[i] += weight * sum(G[i]^2).
 // F bf16 [n,P,C]; Gs fp32 [C,C] or NULL (then G = F^T F / denom: the style-target pass).
-extern "C" int lnst_gram_diff_bf16_tc(const void* F, int32_t n, int64_t P, int32_t C, float denom, const float* Gs,
-                                      float weight, float* G, void* Gd, float* loss, void* stream) {
+// raw F^T F of a bf16 feature map into G (fp32 [n,C,C], zeroed here); sym: only the blocks with row block >= column block
+static int gram_raw(const void* F, int n, int64_t P, int C, float* G, cudaStream_t st, int sym) {
   using namespace tc;
-  if (!F || !G || n < 1 || P < 1 || C < 64 || C % 64 || !(denom > 0.f) || P > 0x7fffffff) return LNST_EARG;
-  cudaStream_t st = lnst_stream(stream);
   CUtensorMap mf;
   {
     const cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)P, (cuuint64_t)n};
@@ -1932,7 +1939,7 @@ extern "C" int lnst_gram_diff_bf16_tc(const void* F, int32_t n, int64_t P, int32
     if (!make_map(&mf, F, 3, dims, strides, box)) return LNST_EARG;
   }
   const int tiles_n = (C + 127) / 128;
-  const int tiles = tiles_n * tiles_n;
+  const int tiles = sym ? tiles_n * (tiles_n + 1) / 2 : tiles_n * tiles_n;
   int splits = (148 + tiles * n - 1) / (tiles * n);            // one wave of CTAs: fewer split-K atomics per element
   const int max_splits = (int)((P + 255) / 256);              // at least 4 K-blocks per CTA
   if (splits > max_splits) splits = max_splits;
@@ -1948,7 +1955,17 @@ extern "C" int lnst_gram_diff_bf16_tc(const void* F, int32_t n, int64_t P, int32
     configured = true;
   }
   cudaMemsetAsync(G, 0, sizeof(float) * (size_t)n * C * C, st);
-  gram_tc_k<<<dim3(tiles, splits, n), NUM_THREADS, smem, st>>>(mf, G, (int)P, (int)C, tiles_n, kps);
+  gram_tc_k<<<dim3(tiles, splits, n), NUM_THREADS, smem, st>>>(mf, G, (int)P, (int)C, tiles_n, kps, sym);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int lnst_gram_diff_bf16_tc(const void* F, int32_t n, int64_t P, int32_t C, float denom, const float* Gs,
+                                      float weight, float* G, void* Gd, float* loss, void* stream) {
+  using namespace tc;
+  if (!F || !G || n < 1 || P < 1 || C < 64 || C % 64 || !(denom > 0.f) || P > 0x7fffffff) return LNST_EARG;
+  cudaStream_t st = lnst_stream(stream);
+  const int rc = gram_raw(F, n, P, C, G, st, 0);
+  if (rc != 0) return rc;
   const int n_el = C * C;
   const unsigned nb = lnst_blocks(n_el, 256) > 32 ? 32 : lnst_blocks(n_el, 256);
   gram_finish_bf16_k<<<dim3(nb, n), 256, 0, st>>>(G, Gs, (__nv_bfloat16*)Gd, n_el, 1.f / denom, weight, loss);
@@ -1960,8 +1977,8 @@ extern "C" int lnst_gram_diff_bf16_tc(const void* F, int32_t n, int64_t P, int32
 // - Gs, Gd2 [n,C,2C] its split copy, loss[i] += weight * sum(G[i]^2).
 extern "C" int lnst_gram_diff_bf16x3_tc(const void* F, int32_t n, int64_t P, int32_t C, float denom, const float* Gs,
                                         float weight, float* G2, float* G, void* Gd2, float* loss, void* stream) {
-  if (!G2 || !G) return LNST_EARG;
-  const int rc = lnst_gram_diff_bf16_tc(F, n, P, 2 * C, 1.0f, nullptr, 0.f, G2, nullptr, nullptr, stream);
+  if (!F || !G2 || !G || n < 1 || P < 1 || C < 64 || C % 64 || !(denom > 0.f) || P > 0x7fffffff) return LNST_EARG;
+  const int rc = gram_raw(F, n, P, 2 * C, G2, lnst_stream(stream), 1);     // symmetric: 10 of the 16 tiles at C = 256
   if (rc != 0) return rc;
   const int n_el = C * C;
   const unsigned nb = lnst_blocks(n_el, 256) > 32 ? 32 : lnst_blocks(n_el, 256);

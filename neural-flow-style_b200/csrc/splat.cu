@@ -6,64 +6,7 @@
 // explicitly un-fused multiplies/adds (__fmul_rn/__fadd_rn) because a contracted FMA changes
 // the offset by up to one ulp of the (large) domain coordinate.
 #include "common.cuh"
-
-#define LNST_MAX_NK 4
-struct SplatKernels {
-  float h[LNST_MAX_NK];
-  float inv_h[LNST_MAX_NK];
-  float sigma[LNST_MAX_NK];
-};
-
-template <int DIM>
-struct Particle {
-  bool valid;
-  int idx[DIM];
-  float r[DIM];    // offset from the centre of the particle's own cell (domain units)
-  float dpd[DIM];  // d(domain coordinate)/d(normalised coordinate): domain, or 0 where clamped
-};
-
-template <int DIM>
-__device__ __forceinline__ Particle<DIM> load_particle(const float* __restrict__ p,
-                                                       const float* __restrict__ disp, int64_t i,
-                                                       const LnstGrid& g) {
-  Particle<DIM> o;
-  o.valid = true;
-  const int off = 3 - DIM;
-#pragma unroll
-  for (int a = 0; a < DIM; ++a) {
-    float pn = p[i * DIM + a];
-    if (disp != nullptr) pn = __fadd_rn(pn, disp[i * DIM + a]);
-    const float dom = g.domain[off + a];
-    float pd = __fmul_rn(pn, dom);
-    float gs = dom;
-    if (g.clip) {
-      const float hi = __fadd_rn(dom, -1e-6f);
-      if (pd < 0.f) { pd = 0.f; gs = 0.f; }
-      if (pd > hi) { pd = hi; gs = 0.f; }
-      if (pd != pd) o.valid = false;
-    } else if (!(pd >= 0.f && pd < dom)) {
-      o.valid = false;
-    }
-    const float f = floorf(pd / g.cell);
-    o.idx[a] = (int)f;
-    o.r[a] = __fadd_rn(pd, -__fmul_rn(f + 0.5f, g.cell));
-    o.dpd[a] = gs;
-  }
-  return o;
-}
-
-__device__ __forceinline__ float cubic_w(float q, float sigma) {
-  if (q > 1.f) return 0.f;
-  const float a = 6.f * (q * q * q - q * q) + 1.f;
-  const float omq = 1.f - q;
-  const float b = 2.f * omq * omq * omq;
-  return sigma * (q <= 0.5f ? a : b);
-}
-__device__ __forceinline__ float cubic_dw(float q, float sigma) {
-  if (q > 1.f) return 0.f;
-  const float omq = 1.f - q;
-  return sigma * (q <= 0.5f ? (18.f * q * q - 12.f * q) : (-6.f * omq * omq));
-}
+#include "splat_common.cuh"
 
 // Visit every in-range target cell of a particle: f(cell_linear_index_with_H_flip, d[DIM], |d|)
 template <int DIM, class F>
@@ -394,26 +337,29 @@ __global__ void splat_wavg_bwd_k(const float* __restrict__ p, const float* __res
 // ---------------------------------------------------------------------------------------
 // C-ABI
 // ---------------------------------------------------------------------------------------
-static inline float sigma_for(int dim, float h) {
-  const double pi = 3.14159265358979323846;
-  return dim == 3 ? (float)(8.0 / pi / ((double)h * h * h)) : (float)(40.0 / 7.0 / pi / ((double)h * h));
-}
-static inline bool grid_ok(const LnstGrid* g) {
-  return g && (g->dim == 2 || g->dim == 3) && g->res[1] > 0 && g->res[2] > 0 &&
-         (g->dim == 2 || g->res[0] > 0) && g->cell > 0.f && g->nsize >= 0 && g->nsize <= 8;
-}
-static inline int64_t grid_cells(const LnstGrid* g) {
-  return (int64_t)(g->dim == 3 ? g->res[0] : 1) * g->res[1] * g->res[2];
-}
-static inline bool fill_kernels(SplatKernels& ks, int dim, const float* h, int nk) {
-  if (!h || nk < 1 || nk > LNST_MAX_NK) return false;
-  for (int k = 0; k < LNST_MAX_NK; ++k) {
-    ks.h[k] = k < nk ? h[k] : 1.f;
-    ks.inv_h[k] = 1.f / ks.h[k];
-    ks.sigma[k] = k < nk ? sigma_for(dim, h[k]) : 0.f;
-    if (!(ks.h[k] > 0.f)) return false;
+// home cell (linear index over [D,H,W], y NOT flipped; -1: outside the domain / padding row, -2: valid but its cell index
+// rounded onto the grid's far face) and offset from that cell's centre, for the per-cell particle lists of the gather splat
+__global__ void splat_cells_k(const float* __restrict__ p, int64_t n, LnstGrid g, int* __restrict__ cell,
+                              float* __restrict__ rel) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const Particle<3> pt = load_particle<3>(p, nullptr, i, g);
+  int c = -1;
+  if (pt.valid) {
+    const bool in = pt.idx[0] >= 0 && pt.idx[0] < g.res[0] && pt.idx[1] >= 0 && pt.idx[1] < g.res[1] && pt.idx[2] >= 0 &&
+                    pt.idx[2] < g.res[2];
+    c = in ? (pt.idx[0] * g.res[1] + pt.idx[1]) * g.res[2] + pt.idx[2] : -2;
   }
-  return true;
+  cell[i] = c;
+  rel[i * 3] = pt.r[0]; rel[i * 3 + 1] = pt.r[1]; rel[i * 3 + 2] = pt.r[2];
+}
+
+extern "C" int lnst_splat_cells(const float* p, int64_t n, const LnstGrid* g, int32_t* cell, float* rel, void* stream) {
+  if (!grid_ok(g) || g->dim != 3 || n < 0 || (n > 0 && (!p || !cell || !rel))) return LNST_EARG;
+  if (n == 0) return LNST_OK;
+  if (grid_cells(g) >= 0x7fffffff) return LNST_EARG;
+  LNST_LAUNCH(splat_cells_k, dim3(lnst_blocks(n, 256)), dim3(256), 0, lnst_stream(stream), p, n, *g, (int*)cell, rel);
+  return lnst_status();
 }
 
 extern "C" int lnst_splat_sph_fwd(const float* p, const float* disp, int64_t n, const LnstGrid* g,

@@ -6,6 +6,7 @@
 //              transform.py:1577-1704 (p2g_wavg), :557-609 (advect).
 #include "tma_tiles.cuh"
 #include "render_common.cuh"
+#include "splat_common.cuh"
 
 // =====================================================================================================================
 // 3x3x3 smoothing (+ ReLU / ReLU-mask): one TMA box {SX+4, SY+2, SZ+2} per tile of SZ x SY x SX outputs.  The zero
@@ -121,6 +122,129 @@ extern "C" int lnst_smooth3_relu_bwd_tma(const float* g_out, const float* out, f
                                          int32_t W, int32_t k, const LnstBox* box, void* stream) {
   if (!g_out || !out || !g_in || D < 1 || H < 1 || W < 1 || k < 1 || !box_ok(box, D, H, W)) return LNST_EARG;
   return launch_smooth_tma<1>(g_out, out, g_in, D, H, W, k, box, lnst_stream(stream));
+}
+
+// =====================================================================================================================
+// Weighted-average splat (p2g_wavg, density mode), forward, as a GATHER: one thread per output cell walks the particles
+// of its 27 neighbour cells (per-cell lists built once per (frame, octave) -- positions are constants in density mode)
+// and accumulates num_k = sum w x and wmap_k = sum w in registers, so there are no atomics, no `num` volumes and no
+// separate combine pass (the scatter version: 27 nk atomics per particle + 16 V bytes of combine traffic).  A CTA's
+// 4 x 8 x 32 tile of results is assembled in shared memory -- rows already in the reference's flipped H order
+// (transform.py:1703) -- and leaves with ONE TMA store; the store clips the tile at the volume's faces.
+//   cstart [V+1]: first list entry of every cell (cells in unflipped (z,y,x) order); order [Nv]: particle index of every
+//   list entry; rel [Nv,3]: that particle's offset from its cell centre (lnst_splat_cells), in list order.
+// =====================================================================================================================
+namespace sg {
+constexpr int TZ = 4, TY = 8, TX = 32;
+constexpr int THREADS = TY * TX;
+}
+
+template <int NK>
+__global__ void __launch_bounds__(sg::THREADS) splat_wavg_gather_k(const __grid_constant__ CUtensorMap map_out,
+                                                                   const int* __restrict__ cstart,
+                                                                   const int* __restrict__ order,
+                                                                   const float* __restrict__ rel,
+                                                                   const float* __restrict__ r,
+                                                                   const float* __restrict__ var, LnstGrid g,
+                                                                   SplatKernels ks, int z_base, int y_base, int x_base,
+                                                                   int tiles_y, int tiles_x) {
+  using namespace sg;
+  __shared__ __align__(128) float tile[TZ * TY * TX];
+  const int D = g.res[0], H = g.res[1], W = g.res[2];
+  const int t = blockIdx.x;
+  const int tx_ = t % tiles_x, ty_ = (t / tiles_x) % tiles_y, tz_ = t / (tiles_x * tiles_y);
+  // tiles are laid out over OUTPUT rows (R = H - 1 - y, transform.py:1703) so that the store's coordinates are never
+  // negative (a negative row start faults on the B200 like a misaligned column start; overhang past the far faces is fine)
+  const int z0 = z_base + tz_ * TZ, r0 = y_base + ty_ * TY, x0 = x_base + tx_ * TX;
+  const int ly = threadIdx.x >> 5, lx = threadIdx.x & 31;
+  const int y = H - 1 - (r0 + ly), x = x0 + lx;
+  float off[3];                                              // (target - home) * cell for -1, 0, +1, as stencil27 forms it
+#pragma unroll
+  for (int q = 0; q < 3; ++q) off[q] = __fmul_rn((float)(q - 1), g.cell);
+#pragma unroll 1
+  for (int tz = 0; tz < TZ; ++tz) {
+    const int z = z0 + tz;
+    float num[NK], wm[NK];
+#pragma unroll
+    for (int k = 0; k < NK; ++k) { num[k] = 0.f; wm[k] = 0.f; }
+    if (x < W && y >= 0 && z < D) {
+      const int xa = max(x - 1, 0), xb = min(x + 2, W);
+#pragma unroll 1
+      for (int dz = -1; dz <= 1; ++dz) {
+        const int zz = z + dz;
+        if (zz < 0 || zz >= D) continue;
+#pragma unroll 1
+        for (int dy = -1; dy <= 1; ++dy) {
+          const int yy = y + dy;
+          if (yy < 0 || yy >= H) continue;
+          const int row = (zz * H + yy) * W;
+          const int j0 = cstart[row + xa], j1 = cstart[row + xb];
+          if (j0 == j1) continue;
+          const int b1 = cstart[row + x], b2 = cstart[row + x + 1];    // list of the home cell at x: [b1, b2)
+          for (int j = j0; j < j1; ++j) {
+            const int hx = j < b1 ? 0 : (j < b2 ? 1 : 2);              // home x = x - 1, x, x + 1
+            // offset of the particle from the TARGET cell's centre: r - (target - home) * cell
+            const float ddz = __fadd_rn(rel[3 * j], -off[1 - dz]);
+            const float ddy = __fadd_rn(rel[3 * j + 1], -off[1 - dy]);
+            const float ddx = __fadd_rn(rel[3 * j + 2], -off[2 - hx]);
+            const float len = sqrtf(ddx * ddx + ddy * ddy + ddz * ddz);
+            const int i = order[j];
+#pragma unroll
+            for (int k = 0; k < NK; ++k) {
+              const float w = cubic_w(len * ks.inv_h[k], ks.sigma[k]);
+              if (w != 0.f) {
+                float v = var ? var[(int64_t)i * NK + k] : 0.f;
+                v = fmaxf(fminf(v, 1.f), -1.f);              // styler_3p.py:74; TF order max(min(x,1),-1): NaN reads as +1
+                num[k] = fmaf(w, r[(int64_t)i * NK + k] + v, num[k]);
+                wm[k] += w;
+              }
+            }
+          }
+        }
+      }
+    }
+    float sres = 0.f;
+#pragma unroll
+    for (int k = 0; k < NK; ++k) sres += (wm[k] > 1e-6f) ? num[k] / wm[k] : num[k];   // transform.py:1703
+    tile[(tz * TY + ly) * TX + lx] = sres;
+  }
+  tma::fence_async_smem();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    tma::store_3d(&map_out, tma::smem_u32(tile), x0, r0, z0);
+    tma::store_commit();
+    tma::store_wait_all();
+  }
+}
+
+extern "C" int lnst_splat_wavg_fwd_gather(const int32_t* cstart, const int32_t* order, const float* rel, const float* r,
+                                          const float* var, const LnstGrid* g, const float* h, int32_t nk, float* out,
+                                          const LnstBox* box, void* stream) {
+  using namespace sg;
+  SplatKernels ks;
+  if (!grid_ok(g) || g->dim != 3 || g->nsize != 1 || g->clip || !cstart || !order || !rel || !r || !out ||
+      !fill_kernels(ks, 3, h, nk))
+    return LNST_EARG;
+  const int D = g->res[0], H = g->res[1], W = g->res[2];
+  if (!box_ok(box, D, H, W) || grid_cells(g) >= 0x7fffffff) return LNST_EARG;
+  CUtensorMap mo;
+  if (!tma::make_volume_map(&mo, out, D, H, W, TZ, TY, TX)) return LNST_EARG;
+  const SubVol sv = make_subvol(box, D, H, W);               // box rows are OUTPUT rows (H already flipped)
+  const int y_lo = sv.oy;
+  const int x_base = sv.ox & ~3;                             // TMA: innermost start coordinate a multiple of 4 floats
+  const int ex = sv.ox + sv.ex - x_base;
+  const int tz = (sv.ez + TZ - 1) / TZ, ty = (sv.ey + TY - 1) / TY, tx = (ex + TX - 1) / TX;
+  // tiles hang over the box's far faces: the cells there receive their true value (zero outside the particles' reach,
+  // which the box contains), clipped at the volume's faces by the store
+  const unsigned grid_ = (unsigned)(tz * ty * tx);
+  cudaStream_t st = lnst_stream(stream);
+  switch (nk) {
+    case 1: splat_wavg_gather_k<1><<<grid_, THREADS, 0, st>>>(mo, cstart, order, rel, r, var, *g, ks, sv.oz, y_lo, x_base, ty, tx); break;
+    case 2: splat_wavg_gather_k<2><<<grid_, THREADS, 0, st>>>(mo, cstart, order, rel, r, var, *g, ks, sv.oz, y_lo, x_base, ty, tx); break;
+    case 3: splat_wavg_gather_k<3><<<grid_, THREADS, 0, st>>>(mo, cstart, order, rel, r, var, *g, ks, sv.oz, y_lo, x_base, ty, tx); break;
+    default: splat_wavg_gather_k<4><<<grid_, THREADS, 0, st>>>(mo, cstart, order, rel, r, var, *g, ks, sv.oz, y_lo, x_base, ty, tx); break;
+  }
+  return (int)cudaGetLastError();
 }
 
 // =====================================================================================================================

@@ -38,6 +38,7 @@ __device__ __forceinline__ void load_3d(uint32_t dst, const CUtensorMap* map, ui
 }
 // generic-proxy writes to shared memory -> visible to the async proxy (before a TMA store / reduce reads them)
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// stores: same alignment rule for x; NEGATIVE start coordinates fault (loads accept them), overhang past the far faces is clipped
 __device__ __forceinline__ void store_3d(const CUtensorMap* map, uint32_t src, int x, int y, int z) {
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
                ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(x), "r"(y), "r"(z) : "memory");

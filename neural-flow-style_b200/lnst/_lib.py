@@ -41,6 +41,7 @@ SIGNATURES = {
     'lnst_splat_wavg_fwd_box': [vp, vp, vp, i64, GP, FP, i32, vp, vp, vp, BP, vp],
     'lnst_splat_wavg_bwd': [vp, vp, i64, GP, FP, i32, vp, vp, vp, vp],
     'lnst_splat_wavg_coef': [vp, i32, i64, vp, vp],
+    'lnst_splat_cells': [vp, i64, GP, vp, vp, vp],
     'lnst_splat_wavg_bwd_coef': [vp, vp, i64, GP, FP, i32, vp, vp, vp, vp],
     'lnst_smooth3_relu_fwd': [vp, vp, i32, i32, i32, i32, vp],
     'lnst_smooth3_relu_bwd': [vp, vp, vp, i32, i32, i32, i32, vp],
@@ -135,6 +136,7 @@ CUDA_ONLY = {
     'lnst_f32_to_bf16': [vp, vp, i64, vp],
     # TMA-tiled volume kernels (csrc/tiles_tma.cu)
     'lnst_tma_supported': [],
+    'lnst_splat_wavg_fwd_gather': [vp, vp, vp, vp, vp, GP, FP, i32, vp, BP, vp],
     'lnst_set_raymarch_slab': [i32],
     'lnst_smooth3_relu_fwd_tma': [vp, vp, i32, i32, i32, i32, BP, vp],
     'lnst_smooth3_relu_bwd_tma': [vp, vp, vp, i32, i32, i32, i32, BP, vp],

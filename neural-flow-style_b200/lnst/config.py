@@ -104,7 +104,7 @@ _FLAGS = [
     # over ranks (BASELINE.json north_star).
     ('Engine', 'view_mode', str, 'sequential', {'choices': ['sequential', 'allreduce']}),
     # loss-network arithmetic: 'bf16' = tcgen05 tensor cores, 'fp32' = CUDA-core reference.
-    ('Engine', 'conv_math', str, 'bf16', {'choices': ['bf16', 'bf16x3', 'fp32']}),
+    ('Engine', 'conv_math', str, 'bf16x3', {'choices': ['bf16', 'bf16x3', 'fp32']}),
     # multi-net loss (BASELINE.json configs[4]: inception semantic + VGG style): when set, the content loss
     # (content_layer / content_channel) is evaluated on this second network, the style loss stays on `network`.
     ('Engine', 'content_network', str, '', {'choices': [''] + _NETWORKS}),

@@ -15,6 +15,10 @@ def _s(t):
     return _lib.stream_ptr(t.device)
 
 
+def _u8(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
 def _harr(vals):
     return (C.c_float * len(vals))(*[float(v) for v in vals])
 
@@ -65,6 +69,40 @@ def splat_wavg_fwd(p, r, var, grid, hs, wmap, num, out, box=None):
     """With ``box``: only its cells are combined; ``num`` must be zero on entry and is zero again on exit."""
     _lib.get().call('lnst_splat_wavg_fwd_box', ptr(p), ptr(r), ptr(var), p.shape[0], C.byref(grid), _harr(hs),
                     len(hs), ptr(wmap), ptr(num), ptr(out), _b(box), _s(p))
+    return out
+
+
+def splat_cells(p, grid):
+    """(cell int32 [N] -- linear index over the unflipped [D,H,W] grid, -1 outside / padding, -2 rounded onto the far face;
+    rel fp32 [N,3] -- offset from the cell centre): what the per-cell particle lists of the gather splat are built from"""
+    n = p.shape[0]
+    cell = torch.empty(n, dtype=torch.int32, device=p.device)
+    rel = torch.empty(n, 3, dtype=f32, device=p.device)
+    _lib.get().call('lnst_splat_cells', ptr(p), n, C.byref(grid), _u8(cell), ptr(rel), _s(p))
+    return cell, rel
+
+
+def cell_lists(p, grid):
+    """(cstart int32 [V+1], order int32 [Nv], rel fp32 [Nv,3]) or None when a particle's cell index rounds out of the grid"""
+    cell, rel = splat_cells(p, grid)
+    if bool((cell == -2).any()):
+        return None
+    V = cells(grid)
+    valid = torch.nonzero(cell >= 0).flatten()
+    cv = cell[valid].to(torch.int64)
+    srt = torch.argsort(cv, stable=True)
+    order = valid[srt]
+    counts = torch.bincount(cv, minlength=V)
+    cstart = torch.zeros(V + 1, dtype=torch.int32, device=p.device)
+    cstart[1:] = torch.cumsum(counts, 0).to(torch.int32)
+    return cstart, order.to(torch.int32).contiguous(), rel[order].contiguous()
+
+
+def splat_wavg_fwd_gather(lists, r, var, grid, hs, out, box=None):
+    """gather form of ``splat_wavg_fwd`` (csrc/tiles_tma.cu): no atomics, no num / wmap volumes, TMA store of the tiles"""
+    cstart, order, rel = lists
+    _lib.get().call('lnst_splat_wavg_fwd_gather', _u8(cstart), _u8(order), ptr(rel), ptr(r), ptr(var), C.byref(grid),
+                    _harr(hs), len(hs), ptr(out), _b(box), _s(r))
     return out
 
 

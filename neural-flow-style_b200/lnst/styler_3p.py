@@ -185,6 +185,32 @@ class Styler(StylerBase):
         torch.distributed.all_gather(out, buf)
         return {t: out[r][j] for r in range(self.world) for j, t in enumerate(per_rank[r])}
 
+    def _filter_frames_alltoall(self, deltas, owners, key_frames, sigma):
+        """The one exchange step of a frame-sharded sequence (styler_3p.py:382-383) as two all-to-all transposes
+        (SURVEY.md 8e): frame-sharded updates [T/W, N, c] -> particle-sharded [T, N/W, c], Gaussian along T on the
+        local particle slice, and back.  Each rank moves (W-1)/W of its own share twice -- the all-gather variant makes
+        every rank receive and filter the whole [T, N, c] stack.  Returns {t: filtered update} for this rank's frames,
+        or None when the frames do not split evenly (the caller then all-gathers)."""
+        W, rk = self.world, self.rank
+        per_rank = [[t for t in key_frames if owners[t] == r] for r in range(W)]
+        tm = len(per_rank[0])
+        if tm == 0 or any(len(x) != tm for x in per_rank) or [t for x in per_rank for t in x] != list(key_frames):
+            return None
+        mine = per_rank[rk]
+        n, c = deltas[mine[0]].shape
+        nw = (n + W - 1) // W
+        stack = torch.zeros(tm, W * nw, c, dtype=f32, device=self.device)
+        for j, t in enumerate(mine):
+            stack[j, :n].copy_(deltas[t])
+        send = stack.view(tm, W, nw, c).permute(1, 0, 2, 3).contiguous()          # [W, tm, nw, c]: block w -> rank w
+        recv = torch.empty_like(send)
+        torch.distributed.all_to_all_single(recv, send)                            # block w = rank w's frames, my particles
+        sm = ops.temporal_gauss(recv.view(W * tm, nw, c), sigma).view(W, tm, nw, c)
+        back = torch.empty_like(sm)
+        torch.distributed.all_to_all_single(back, sm.contiguous())                 # block w = my frames, rank w's particles
+        out = back.permute(1, 0, 2, 3).reshape(tm, W * nw, c)
+        return {t: out[j, :n].contiguous() for j, t in enumerate(mine)}
+
     def _advance_views(self):
         """Poisson-disc view sets are re-drawn after every frame pass (styler_3p.py:344-349)."""
         if self.rotate and 'uniform' not in self.sample_type:
@@ -214,6 +240,10 @@ class Styler(StylerBase):
         """var -> density field d [D,H,W] (styler_3p.py:49-91)."""
         grid = ws['grid']
         if 'd' in self.target_field:
+            lists = self._cell_lists(fr, res, grid, ws['d'])
+            if lists is not None:                                   # gather over per-cell lists, TMA-stored tiles
+                ops.splat_wavg_fwd_gather(lists, fr['r'], var, grid, self._supports(), ws['d'], ws['box'])
+                return ws['d']
             wmap = self._wmap(fr, res, grid)
             ops.splat_wavg_fwd(fr['p'], fr['r'], var, grid, self._supports(), wmap, ws['num'], ws['d'], ws['box'])
         else:
@@ -227,6 +257,18 @@ class Styler(StylerBase):
         key = (fr['id'], tuple(res))
         if key not in self._frame_cache:
             self._frame_cache[key] = ops.splat_wavg_wmap(fr['p'], grid, self._supports())
+        return self._frame_cache[key]
+
+    def _cell_lists(self, fr, res, grid, out):
+        """Per-cell particle lists of a frame (positions are constants in density mode): built once per (frame, octave)
+        for the gather splat; None when that kernel does not apply (then the scatter kernel runs).  Opt-in
+        (``gather_splat = True``): the first version walks the lists straight from global memory and is latency-bound --
+        0.33 ms against the scatter kernel's 0.095 ms at C3 on the B200."""
+        if not (getattr(self, 'gather_splat', False) and self.nsize == 1 and not self.clip and ops._tma_ok(out)):
+            return None
+        key = (fr['id'], tuple(res), 'cells')
+        if key not in self._frame_cache:
+            self._frame_cache[key] = ops.cell_lists(fr['p'], grid) if fr['p'].shape[0] else None
         return self._frame_cache[key]
 
     def _coef(self, fr, res, grid):
@@ -362,7 +404,7 @@ class Styler(StylerBase):
         return bool(pre) and pre[0] == 'conv1_1'
 
     # ---- one loss + gradient evaluation (= one sess.run([train_op, total_loss]) without Adam) ----
-    def loss_and_grad(self, fr, var, ws, rot, style_grams, group=False):
+    def loss_and_grad(self, fr, var, ws, rot, style_grams, group=False, grad_out=None):
         """Sum over the given views of total_loss, and d(sum)/d var.  Returns (loss [nv], grad).  ``group``: the views
         are ONE fed batch of the reference graph (v_batch > 1): joint normalisation and the group loss weights."""
         res = ws['res']
@@ -404,7 +446,7 @@ class Styler(StylerBase):
         if self.w_pressure > 0 and 'p' in self.target_field:       # styler_3p.py:96-98, styler_base.py:228-230
             ops.pressure_reg(d, 1.0, self.w_pressure, n_terms * self.w_pressure * 2.0 / d.numel(), loss, n_terms, g_d)
         if 'd' in self.target_field:
-            grad = torch.empty_like(var)
+            grad = grad_out if grad_out is not None else torch.empty_like(var)
             if self.nsize == 1:
                 ops.splat_wavg_bwd_coef(fr['p'], var, ws['grid'], self._supports(), self._coef(fr, res, ws['grid']),
                                         g_d, grad)
@@ -629,13 +671,19 @@ class Styler(StylerBase):
         # when no temporal filter runs in between, ``self.fuse_apply``)
         gscale = 1.0
         if self.rotate:                                            # mean view gradient, views sharded over ranks
+            # the gradient is written straight into the all-reduce buffer, the loss scalar rides in its last element
+            buf = torch.empty(g_opt_t.numel() + 1, dtype=f32, device=dev) if self.view_world > 1 else None
+            gview = buf[:-1].view_as(g_opt_t) if buf is not None and 'd' in self.target_field else None
             if self._rot_mine is not None:
-                l, grad = self.loss_and_grad(fr, g_opt_t, ws, self._rot_mine, style_grams)
+                l, grad = self.loss_and_grad(fr, g_opt_t, ws, self._rot_mine, style_grams, grad_out=gview)
                 lsum = l.sum().reshape(1)
             else:
-                grad, lsum = torch.zeros_like(g_opt_t), torch.zeros(1, dtype=f32, device=dev)
+                grad = gview.zero_() if gview is not None else torch.zeros_like(g_opt_t)
+                lsum = torch.zeros(1, dtype=f32, device=dev)
             if self.view_world > 1:                                # ONE all-reduce: gradient + loss scalar
-                buf = torch.cat([grad.reshape(-1), lsum])
+                if gview is None:
+                    buf[:-1].copy_(grad.reshape(-1))
+                buf[-1:].copy_(lsum)
                 torch.distributed.all_reduce(buf)
                 grad, lsum = buf[:-1].view_as(g_opt_t), buf[-1:]
             gscale = 1.0 / self.n_views
@@ -727,11 +775,17 @@ class Styler(StylerBase):
                         _, _, d_img = self.infer(fr, var, ws, eye)
                         intm_o[t] = d_img
                 if self.window_sigma > 0 and nf > 1:               # :382-383
-                    if shard == 'frames':                          # the one exchange step of a sharded sequence
-                        deltas = self._gather_frames(deltas, owners, key_frames, g_opt[key_frames[0]].shape)
-                    sm = ops.temporal_gauss(torch.stack([deltas[t] for t in key_frames], 0), self.window_sigma)
-                    for j, t in enumerate(key_frames):
-                        deltas[t] = sm[j]
+                    done = None
+                    if shard == 'frames' and getattr(self, 'frame_exchange', 'alltoall') == 'alltoall':
+                        done = self._filter_frames_alltoall(deltas, owners, key_frames, self.window_sigma)
+                    if done is not None:
+                        deltas = done
+                    else:
+                        if shard == 'frames':                      # the one exchange step of a sharded sequence
+                            deltas = self._gather_frames(deltas, owners, key_frames, g_opt[key_frames[0]].shape)
+                        sm = ops.temporal_gauss(torch.stack([deltas[t] for t in key_frames], 0), self.window_sigma)
+                        for j, t in enumerate(key_frames):
+                            deltas[t] = sm[j]
                 if not self.fuse_apply or (self.rotate and self.view_mode == 'sequential'):
                     for t in mine:                                 # :385-386
                         ops.axpy(g_opt[t], deltas[t].contiguous(), 1.0)

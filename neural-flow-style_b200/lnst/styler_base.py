@@ -26,7 +26,7 @@ class StylerBase(object):
         if not hasattr(self, 'view_mode'):
             self.view_mode = 'sequential'
         if not hasattr(self, 'conv_math'):
-            self.conv_math = 'bf16'
+            self.conv_math = 'bf16x3'
         if getattr(self, 'w_hist', 0) > 0:
             raise NotImplementedError('histogram loss (w_hist > 0) is not built: DESIGN.md section 5 (out of scope, '
                                       'broken at the reference HEAD, styler_base.py:203-207)')

@@ -22,7 +22,7 @@ def _worker(rank, world, port, out_path):
     dist.init_process_group('nccl', init_method='tcp://127.0.0.1:%d' % port, rank=rank, world_size=world,
                             device_id=torch.device('cuda', rank))
     res = 24
-    kw = dict(res=res, iter=5, rotate=True, n_views=9, view_mode='allreduce', conv_math='bf16',
+    kw = dict(res=res, iter=5, rotate=True, n_views=9, view_mode='allreduce', conv_math='bf16x3',
               style_layer=['conv2_1', 'conv3_1'], w_style_layer=[0.5, 0.5])
     p, r = synth.smoke_particles(6000, 2, pad=8)
     sty = synth.style_image(res, res)
@@ -91,7 +91,12 @@ def test_two_gpus_match_one(tmp_path):
     port = 29600 + (os.getpid() % 2000)
     mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
     z = np.load(out)
-    # same arithmetic per view; only the order of the fp32 sums over views / atomics differs
-    np.testing.assert_allclose(z['l'], z['l_ref'], rtol=2e-3)
-    assert np.linalg.norm(z['g'] - z['g_ref']) <= 2e-2 * np.linalg.norm(z['g_ref'])
-    assert np.abs(z['d'] - z['d_ref']).max() <= 2e-2 * np.abs(z['d_ref']).max()
+    # same arithmetic per view (fp32-tolerance bf16x3 loss network); only the order of the fp32 sums over views / atomics
+    # differs (~1e-6)
+    # measured on 2 B200s (profiles/r2_pytest_multigpu_n2.log): loss 7e-8, variables 1.5e-7, field 1.7e-7
+    np.testing.assert_allclose(z['l'], z['l_ref'], rtol=1e-5)
+    assert np.linalg.norm(z['g'] - z['g_ref']) <= 1e-5 * np.linalg.norm(z['g_ref'])
+    assert np.abs(z['d'] - z['d_ref']).max() <= 1e-5 * np.abs(z['d_ref']).max()
+    print('2 GPUs vs 1: loss rel %.2e, variables rel-L2 %.2e, field %.2e' % (
+        np.max(np.abs(z['l'] - z['l_ref']) / np.abs(z['l_ref'])), np.linalg.norm(z['g'] - z['g_ref']) / np.linalg.norm(z['g_ref']),
+        np.abs(z['d'] - z['d_ref']).max() / np.abs(z['d_ref']).max()))

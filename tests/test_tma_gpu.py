@@ -118,3 +118,40 @@ def test_raymarch_bwd_tma_equals_simt(shape, phi, theta):
         g0, g1 = both(run)
         assert float(g0.abs().max()) > 0
         assert (g0 - g1).abs().max() <= 2e-5 * g0.abs().max(), float((g0 - g1).abs().max() / g0.abs().max())
+
+
+@pytest.mark.parametrize('res,nk,n', [((24, 24, 24), 2, 5000), ((20, 28, 36), 1, 3000), ((64, 48, 40), 3, 40000),
+                                      ((200, 200, 200), 2, 300000)])
+def test_splat_gather_equals_scatter(res, nk, n):
+    """p2g_wavg forward as a gather over per-cell lists (TMA-stored tiles) against the atomics kernel: same weights,
+    another summation order; particles on the faces, padding rows (p = -1), variables outside [-1, 1] and NaN."""
+    from lnst import synth
+    D, H, W = res
+    rng = np.random.RandomState(n)
+    p = rng.uniform(0.15, 0.85, (n, 3)).astype(np.float32)
+    p[:50] = rng.uniform(0.0, 1.0, (50, 3))                   # some next to / on the faces
+    p[50:60] = -1.0                                           # padding rows
+    p[60:64] = [[0.0, 0.0, 0.0], [0.999999, 0.5, 0.5], [0.5, 0.999999, 0.5], [0.5, 0.5, 0.999999]]
+    r = rng.uniform(0.2, 1.0, (n, nk)).astype(np.float32)
+    var = (rng.randn(n, nk) * 0.7).astype(np.float32)
+    var[100:104] = np.nan
+    grid = _lib.make_grid(3, res, [float(v) for v in res], 1, False)
+    hs = [2.0 / (2 ** k) for k in range(nk)]
+    pt, rt, vt = (torch.tensor(a).to(DEV) for a in (p, r, var))
+    wmap = ops.splat_wavg_wmap(pt, grid, hs)
+    num = torch.zeros(nk, D * H * W, device=DEV)
+    want = ops.splat_wavg_fwd(pt, rt, vt, grid, hs, wmap, num, torch.zeros(D, H, W, device=DEV), None)
+    lists = ops.cell_lists(pt, grid)
+    assert lists is not None
+    got = ops.splat_wavg_fwd_gather(lists, rt, vt, grid, hs, torch.zeros(D, H, W, device=DEV), None)
+    assert torch.equal(torch.isnan(got), torch.isnan(want))
+    ok = ~torch.isnan(want)
+    assert (got[ok] - want[ok]).abs().max() <= 2e-5 * want[ok].abs().max()
+    # box variant: only the box is written, and it holds the same values
+    occ = (wmap > 0).any(0).reshape(D, H, W)
+    idx = torch.nonzero(occ)
+    lo, hi = idx.min(0).values.tolist(), idx.max(0).values.tolist()
+    box = _lib.make_box(lo, hi)
+    got_b = ops.splat_wavg_fwd_gather(lists, rt, vt, grid, hs, torch.zeros(D, H, W, device=DEV), box)
+    assert torch.equal(torch.isnan(got_b), torch.isnan(want))
+    assert (got_b[ok] - want[ok]).abs().max() <= 2e-5 * want[ok].abs().max()
