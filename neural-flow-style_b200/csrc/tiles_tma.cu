@@ -137,8 +137,15 @@ extern "C" int lnst_smooth3_relu_bwd_tma(const float* g_out, const float* out, f
 namespace sg {
 constexpr int TZ = 4, TY = 8, TX = 32;
 constexpr int THREADS = TY * TX;
+constexpr int ROWS = (TZ + 2) * (TY + 2);                    // (z,y) rows of cells a tile's outputs can receive from
+constexpr int RC = TX + 3;                                   // cell boundaries per row: cells x0-1 .. x0+TX, + the end
+constexpr int PMAX = 3072;                                   // particles staged per tile (C3: ~2000); more -> global path
 }
 
+// The tile's neighbourhood particles are staged in shared memory first (their offsets and x = r + clip(var), in list
+// order -- every (z,y) row of cells is one contiguous list range), with the per-cell list boundaries beside them; each
+// thread then walks the 27 neighbour cells of its output cells out of shared memory.  Tiles whose neighbourhood holds
+// more than PMAX particles walk the lists in global memory instead.
 template <int NK>
 __global__ void __launch_bounds__(sg::THREADS) splat_wavg_gather_k(const __grid_constant__ CUtensorMap map_out,
                                                                    const int* __restrict__ cstart,
@@ -149,7 +156,12 @@ __global__ void __launch_bounds__(sg::THREADS) splat_wavg_gather_k(const __grid_
                                                                    SplatKernels ks, int z_base, int y_base, int x_base,
                                                                    int tiles_y, int tiles_x) {
   using namespace sg;
-  __shared__ __align__(128) float tile[TZ * TY * TX];
+  extern __shared__ unsigned char smem_raw[];
+  float* tile = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));   // TMA source
+  float* s_rel = tile + TZ * TY * TX;                        // [PMAX][3]
+  float* s_x = s_rel + 3 * PMAX;                             // [NK][PMAX]
+  int* s_cell = reinterpret_cast<int*>(s_x + NK * PMAX);     // [ROWS][RC] list boundaries, relative to the staged arrays
+  __shared__ int s_row_j0[ROWS], s_row_off[ROWS + 1];
   const int D = g.res[0], H = g.res[1], W = g.res[2];
   const int t = blockIdx.x;
   const int tx_ = t % tiles_x, ty_ = (t / tiles_x) % tiles_y, tz_ = t / (tiles_x * tiles_y);
@@ -158,6 +170,52 @@ __global__ void __launch_bounds__(sg::THREADS) splat_wavg_gather_k(const __grid_
   const int z0 = z_base + tz_ * TZ, r0 = y_base + ty_ * TY, x0 = x_base + tx_ * TX;
   const int ly = threadIdx.x >> 5, lx = threadIdx.x & 31;
   const int y = H - 1 - (r0 + ly), x = x0 + lx;
+  // ---- stage: row q = (rz, ry) holds the cells (z0 - 1 + rz, y_hi + 1 - ry, x0 - 1 .. x0 + TX) ------------------------------
+  const int y_hi = H - 1 - r0;                               // unflipped y of output row r0 (the tile's highest y)
+  auto row_base = [&](int q, bool& ok) -> int {
+    const int zz = z0 - 1 + q / (TY + 2), yy = y_hi + 1 - q % (TY + 2);
+    ok = zz >= 0 && zz < D && yy >= 0 && yy < H;
+    return (zz * H + yy) * W;
+  };
+  auto clampx = [&](int xx) -> int { return min(max(xx, 0), W); };
+  if (threadIdx.x < ROWS) {
+    bool ok;
+    const int rb = row_base(threadIdx.x, ok);
+    const int j0 = ok ? cstart[rb + clampx(x0 - 1)] : 0, j1 = ok ? cstart[rb + clampx(x0 + TX + 1)] : 0;
+    s_row_j0[threadIdx.x] = j0;
+    s_row_off[threadIdx.x + 1] = j1 - j0;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    s_row_off[0] = 0;
+    for (int q = 0; q < ROWS; ++q) { acc += s_row_off[q + 1]; s_row_off[q + 1] = acc; }
+  }
+  __syncthreads();
+  const int total = s_row_off[ROWS];
+  const bool staged = total <= PMAX;
+  if (staged) {
+    for (int e = threadIdx.x; e < ROWS * RC; e += THREADS) {
+      const int q = e / RC, c = e - q * RC;
+      bool ok;
+      const int rb = row_base(q, ok);
+      s_cell[e] = ok ? cstart[rb + clampx(x0 - 1 + c)] - s_row_j0[q] + s_row_off[q] : s_row_off[q];
+    }
+    for (int e = threadIdx.x; e < total; e += THREADS) {      // staged entry e: which row's list does it come from?
+      int lo = 0, hi = ROWS;                                 // largest q with s_row_off[q] <= e
+      while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_row_off[mid] <= e) lo = mid; else hi = mid; }
+      const int j = s_row_j0[lo] + (e - s_row_off[lo]);
+      s_rel[3 * e] = rel[3 * j]; s_rel[3 * e + 1] = rel[3 * j + 1]; s_rel[3 * e + 2] = rel[3 * j + 2];
+      const int i = order[j];
+#pragma unroll
+      for (int k = 0; k < NK; ++k) {
+        float v = var ? var[(int64_t)i * NK + k] : 0.f;
+        v = fmaxf(fminf(v, 1.f), -1.f);                    // styler_3p.py:74; TF order max(min(x,1),-1): NaN reads as +1
+        s_x[k * PMAX + e] = r[(int64_t)i * NK + k] + v;
+      }
+    }
+    __syncthreads();
+  }
   float off[3];                                              // (target - home) * cell for -1, 0, +1, as stencil27 forms it
 #pragma unroll
   for (int q = 0; q < 3; ++q) off[q] = __fmul_rn((float)(q - 1), g.cell);
@@ -168,35 +226,50 @@ __global__ void __launch_bounds__(sg::THREADS) splat_wavg_gather_k(const __grid_
 #pragma unroll
     for (int k = 0; k < NK; ++k) { num[k] = 0.f; wm[k] = 0.f; }
     if (x < W && y >= 0 && z < D) {
-      const int xa = max(x - 1, 0), xb = min(x + 2, W);
 #pragma unroll 1
       for (int dz = -1; dz <= 1; ++dz) {
-        const int zz = z + dz;
-        if (zz < 0 || zz >= D) continue;
+        const float oz = dz < 0 ? off[2] : (dz == 0 ? off[1] : off[0]);   // off[1 - dz]
 #pragma unroll 1
         for (int dy = -1; dy <= 1; ++dy) {
-          const int yy = y + dy;
-          if (yy < 0 || yy >= H) continue;
-          const int row = (zz * H + yy) * W;
-          const int j0 = cstart[row + xa], j1 = cstart[row + xb];
-          if (j0 == j1) continue;
-          const int b1 = cstart[row + x], b2 = cstart[row + x + 1];    // list of the home cell at x: [b1, b2)
-          for (int j = j0; j < j1; ++j) {
-            const int hx = j < b1 ? 0 : (j < b2 ? 1 : 2);              // home x = x - 1, x, x + 1
-            // offset of the particle from the TARGET cell's centre: r - (target - home) * cell
-            const float ddz = __fadd_rn(rel[3 * j], -off[1 - dz]);
-            const float ddy = __fadd_rn(rel[3 * j + 1], -off[1 - dy]);
-            const float ddx = __fadd_rn(rel[3 * j + 2], -off[2 - hx]);
-            const float len = sqrtf(ddx * ddx + ddy * ddy + ddz * ddz);
-            const int i = order[j];
+          const float oy = dy < 0 ? off[2] : (dy == 0 ? off[1] : off[0]);
+          if (staged) {
+            // row of (z + dz, y + dy): rz = tz + 1 + dz, ry = (y_hi + 1) - (y + dy) = ly + 1 - dy
+            const int* cb = s_cell + ((tz + 1 + dz) * (TY + 2) + (ly + 1 - dy)) * RC + lx;   // cell x - 1 is local lx
+            const int j0 = cb[0], b1 = cb[1], b2 = cb[2], j1 = cb[3];
+            for (int j = j0; j < j1; ++j) {
+              const float ox = j < b1 ? off[2] : (j < b2 ? off[1] : off[0]);  // home x - 1, x, x + 1 -> target - home = +1, 0, -1
+              const float ddz = __fadd_rn(s_rel[3 * j], -oz);
+              const float ddy = __fadd_rn(s_rel[3 * j + 1], -oy);
+              const float ddx = __fadd_rn(s_rel[3 * j + 2], -ox);
+              const float len = sqrtf(ddx * ddx + ddy * ddy + ddz * ddz);
 #pragma unroll
-            for (int k = 0; k < NK; ++k) {
-              const float w = cubic_w(len * ks.inv_h[k], ks.sigma[k]);
-              if (w != 0.f) {
-                float v = var ? var[(int64_t)i * NK + k] : 0.f;
-                v = fmaxf(fminf(v, 1.f), -1.f);              // styler_3p.py:74; TF order max(min(x,1),-1): NaN reads as +1
-                num[k] = fmaf(w, r[(int64_t)i * NK + k] + v, num[k]);
-                wm[k] += w;
+              for (int k = 0; k < NK; ++k) {
+                const float w = cubic_w(len * ks.inv_h[k], ks.sigma[k]);
+                if (w != 0.f) { num[k] = fmaf(w, s_x[k * PMAX + j], num[k]); wm[k] += w; }
+              }
+            }
+          } else {
+            const int zz = z + dz, yy = y + dy;
+            if (zz < 0 || zz >= D || yy < 0 || yy >= H) continue;
+            const int row = (zz * H + yy) * W;
+            const int j0 = cstart[row + max(x - 1, 0)], j1 = cstart[row + min(x + 2, W)];
+            const int b1 = cstart[row + x], b2 = cstart[row + x + 1];
+            for (int j = j0; j < j1; ++j) {
+              const float ox = j < b1 ? off[2] : (j < b2 ? off[1] : off[0]);
+              const float ddz = __fadd_rn(rel[3 * j], -oz);
+              const float ddy = __fadd_rn(rel[3 * j + 1], -oy);
+              const float ddx = __fadd_rn(rel[3 * j + 2], -ox);
+              const float len = sqrtf(ddx * ddx + ddy * ddy + ddz * ddz);
+              const int i = order[j];
+#pragma unroll
+              for (int k = 0; k < NK; ++k) {
+                const float w = cubic_w(len * ks.inv_h[k], ks.sigma[k]);
+                if (w != 0.f) {
+                  float v = var ? var[(int64_t)i * NK + k] : 0.f;
+                  v = fmaxf(fminf(v, 1.f), -1.f);
+                  num[k] = fmaf(w, r[(int64_t)i * NK + k] + v, num[k]);
+                  wm[k] += w;
+                }
               }
             }
           }
@@ -215,6 +288,23 @@ __global__ void __launch_bounds__(sg::THREADS) splat_wavg_gather_k(const __grid_
     tma::store_commit();
     tma::store_wait_all();
   }
+}
+
+template <int NK>
+static int launch_gather(const CUtensorMap& mo, const int* cstart, const int* order, const float* rel, const float* r,
+                         const float* var, const LnstGrid& g, const SplatKernels& ks, int oz, int y_lo, int x_base, int tz,
+                         int ty, int tx, cudaStream_t st) {
+  using namespace sg;
+  const int smem = 128 + 4 * (TZ * TY * TX + 3 * PMAX + NK * PMAX + ROWS * RC);
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(splat_wavg_gather_k<NK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  splat_wavg_gather_k<NK><<<(unsigned)(tz * ty * tx), THREADS, smem, st>>>(mo, cstart, order, rel, r, var, g, ks, oz, y_lo,
+                                                                          x_base, ty, tx);
+  return (int)cudaGetLastError();
 }
 
 extern "C" int lnst_splat_wavg_fwd_gather(const int32_t* cstart, const int32_t* order, const float* rel, const float* r,
@@ -236,15 +326,13 @@ extern "C" int lnst_splat_wavg_fwd_gather(const int32_t* cstart, const int32_t* 
   const int tz = (sv.ez + TZ - 1) / TZ, ty = (sv.ey + TY - 1) / TY, tx = (ex + TX - 1) / TX;
   // tiles hang over the box's far faces: the cells there receive their true value (zero outside the particles' reach,
   // which the box contains), clipped at the volume's faces by the store
-  const unsigned grid_ = (unsigned)(tz * ty * tx);
   cudaStream_t st = lnst_stream(stream);
   switch (nk) {
-    case 1: splat_wavg_gather_k<1><<<grid_, THREADS, 0, st>>>(mo, cstart, order, rel, r, var, *g, ks, sv.oz, y_lo, x_base, ty, tx); break;
-    case 2: splat_wavg_gather_k<2><<<grid_, THREADS, 0, st>>>(mo, cstart, order, rel, r, var, *g, ks, sv.oz, y_lo, x_base, ty, tx); break;
-    case 3: splat_wavg_gather_k<3><<<grid_, THREADS, 0, st>>>(mo, cstart, order, rel, r, var, *g, ks, sv.oz, y_lo, x_base, ty, tx); break;
-    default: splat_wavg_gather_k<4><<<grid_, THREADS, 0, st>>>(mo, cstart, order, rel, r, var, *g, ks, sv.oz, y_lo, x_base, ty, tx); break;
+    case 1: return launch_gather<1>(mo, cstart, order, rel, r, var, *g, ks, sv.oz, y_lo, x_base, tz, ty, tx, st);
+    case 2: return launch_gather<2>(mo, cstart, order, rel, r, var, *g, ks, sv.oz, y_lo, x_base, tz, ty, tx, st);
+    case 3: return launch_gather<3>(mo, cstart, order, rel, r, var, *g, ks, sv.oz, y_lo, x_base, tz, ty, tx, st);
+    default: return launch_gather<4>(mo, cstart, order, rel, r, var, *g, ks, sv.oz, y_lo, x_base, tz, ty, tx, st);
   }
-  return (int)cudaGetLastError();
 }
 
 // =====================================================================================================================

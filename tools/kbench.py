@@ -112,6 +112,13 @@ def main():
     add('raymarch_bwd', lambda: ops.raymarch_bwd(ds, rot, st.transmit, False, stot, g_img, g_ds, box, bricks), nv * (8 * Vb + 8 * P))
     add('splat_wavg_fwd', lambda: ops.splat_wavg_fwd(fr['p'], fr['r'], var, ws['grid'], hs, wmap, ws['num'], ws['d'], box),
         N * (12 + 16) + 4 * Vb)
+    lists = ops.cell_lists(fr['p'], ws['grid'])
+    if lists is not None and lib.has_tma:
+        dg = torch.zeros_like(ws['d'])
+        add('splat_wavg_fwd(gather+TMA store)', lambda: ops.splat_wavg_fwd_gather(lists, fr['r'], var, ws['grid'], hs, dg, box),
+            N * (12 + 16) + 4 * Vb)
+        dref = ops.splat_wavg_fwd(fr['p'], fr['r'], var, ws['grid'], hs, wmap, ws['num'], torch.zeros_like(ws['d']), box)
+        print('gather vs scatter max rel diff %.2e' % float((dg - dref).abs().max() / dref.abs().max()))
     add('splat_wavg_bwd(generic)', lambda: ops.splat_wavg_bwd(fr['p'], var, ws['grid'], hs, wmap, g_d, gvar), N * (12 + 16) + 4 * Vb)
     coef = ops.splat_wavg_coef(wmap)
     add('splat_wavg_bwd', lambda: ops.splat_wavg_bwd_coef(fr['p'], var, ws['grid'], hs, coef, g_d, gvar), N * (12 + 16) + 4 * Vb)
