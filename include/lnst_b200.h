@@ -286,6 +286,11 @@ int lnst_raymarch_fwd_tma(const float* vol, const float* rot, int32_t n_views, i
                           int32_t liquid, const LnstBox* box, const int32_t* intervals, float* img, float* stot,
                           void* stream);
 
+/* lnst_advect for a 3-D scalar field (dim = 3, C = 1): d [D,H,W], vel [D,H,W,3], out [D,H,W].  The source box of each
+ * 8 x 8 x 32 output tile, grown by `reach` cells (1..4: the caller's bound on the back-trace length), is one TMA box;
+ * longer back-traces gather from global memory, so the result does not depend on the bound. */
+int lnst_advect3_tma(const float* d, const float* vel, int32_t D, int32_t H, int32_t W, int32_t reach, float* out,
+                     void* stream);
 /* smoke render (liquid = 0) only; g_vol accumulates like lnst_raymarch_bwd_box */
 int lnst_raymarch_bwd_tma(const float* vol, const float* rot, int32_t n_views, int32_t D, int32_t H, int32_t W, float tau,
                           const LnstBox* box, const int32_t* intervals, const float* stot, const float* g_img,

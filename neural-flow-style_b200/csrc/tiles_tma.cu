@@ -835,3 +835,128 @@ extern "C" int lnst_raymarch_bwd_tma(const float* vol, const float* rot, int32_t
   if (bz == 12) return launch_rm_bwd<12>(mv, vol, rot, n_views, g, bf, iv, tau, stot, g_img, g_vol, st);
   return launch_rm_bwd<16>(mv, vol, rot, n_views, g, bf, iv, tau, stot, g_img, g_vol, st);
 }
+
+// =====================================================================================================================
+// Semi-Lagrangian advection, order 1 (transform.py:557-609), 3-D scalar field: out(p) = d(p - v(p)), trilinear, edge
+// clamped.  A CTA owns an 8 x 8 x 32 tile of outputs; the source box of the tile -- the tile grown by `reach` cells,
+// the caller's bound on the back-trace length -- is ONE TMA box, and the 8 corners of every back-traced point come out
+// of shared memory.  Points whose back-trace leaves the staged box (|v| above the bound) gather from global memory, so
+// the result never depends on the bound.  Same arithmetic per output as advect_k (optim.cu): bit-identical fields.
+// =====================================================================================================================
+namespace adv {
+constexpr int TZ = 8, TY = 8, TX = 32;
+constexpr int THREADS = TY * TX;
+}
+
+template <int R>
+__global__ void __launch_bounds__(adv::THREADS) advect3_tma_k(const __grid_constant__ CUtensorMap map_d,
+                                                              const float* __restrict__ d, const float* __restrict__ vel,
+                                                              int D, int H, int W, float sD, float sH, float sW,
+                                                              float* __restrict__ out, int tiles_y, int tiles_x) {
+  using namespace adv;
+  constexpr int BZ = TZ + 2 * R + 1, BY = TY + 2 * R + 1, BX = ((TX + 2 * R + 1 + 3) + 3) & ~3;
+  extern __shared__ unsigned char smem_raw[];
+  float* box = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  __shared__ __align__(8) uint64_t bar_store;
+  const uint32_t bar = tma::smem_u32(&bar_store);
+  const int t = blockIdx.x;
+  const int tx_ = t % tiles_x, ty_ = (t / tiles_x) % tiles_y, tz_ = t / (tiles_x * tiles_y);
+  const int z0 = tz_ * TZ, y0 = ty_ * TY, x0 = tx_ * TX;
+  const int oz = z0 - R, oy = y0 - R, ox = (x0 - R) & ~3;    // x start: a multiple of 4 floats (tma_tiles.cuh)
+  if (threadIdx.x == 0) {
+    tma::mbar_init(bar, 1);
+    tma::fence_mbar_init();
+    tma::mbar_expect_tx(bar, BZ * BY * BX * 4);
+    tma::load_3d(tma::smem_u32(box), &map_d, bar, ox, oy, oz);
+  }
+  __syncthreads();
+  const int ly = threadIdx.x >> 5, lx = threadIdx.x & 31;
+  const int y = y0 + ly, x = x0 + lx;
+  const bool col = y < H && x < W;
+  // velocities of the column first (independent of the staged box): TZ x 3 loads in flight under the TMA copy
+  float vz[TZ], vy[TZ], vx[TZ];
+#pragma unroll
+  for (int k = 0; k < TZ; ++k) {
+    const int z = z0 + k;
+    vz[k] = vy[k] = vx[k] = 0.f;
+    if (col && z < D) {
+      const int64_t c = ((int64_t)z * H + y) * W + x;
+      vz[k] = vel[c * 3]; vy[k] = vel[c * 3 + 1]; vx[k] = vel[c * 3 + 2];
+    }
+  }
+  tma::mbar_wait(bar, 0);
+  const float mD = (float)D - 1.f, mH = (float)H - 1.f, mW = (float)W - 1.f;
+#pragma unroll
+  for (int k = 0; k < TZ; ++k) {
+    const int z = z0 + k;
+    if (!(col && z < D)) continue;
+    // advect_k's arithmetic: g = linspace(-1,1)[idx] - v;  x = (g + 1) (n - 1) / 2;  floor / floor+1 clamped separately
+    const float gz = __fadd_rn(-1.f, __fmul_rn(sD, (float)z)) - vz[k];
+    const float gy = __fadd_rn(-1.f, __fmul_rn(sH, (float)y)) - vy[k];
+    const float gx = __fadd_rn(-1.f, __fmul_rn(sW, (float)x)) - vx[k];
+    const float pz = (gz + 1.f) * mD * 0.5f, py = (gy + 1.f) * mH * 0.5f, px = (gx + 1.f) * mW * 0.5f;
+    const int fz = (int)floorf(pz), fy = (int)floorf(py), fx = (int)floorf(px);
+    const int lz = min(max(fz, 0), D - 1), hz = min(max(fz + 1, 0), D - 1);
+    const int lyy = min(max(fy, 0), H - 1), hy = min(max(fy + 1, 0), H - 1);
+    const int lxx = min(max(fx, 0), W - 1), hx = min(max(fx + 1, 0), W - 1);
+    const float wz = pz - (float)lz, wy = py - (float)lyy, wx = px - (float)lxx;
+    float v[8];
+    const bool inside = lz >= oz && hz < oz + BZ && lyy >= oy && hy < oy + BY && lxx >= ox && hx < ox + BX;
+    if (inside) {
+      const float* b = box - ((oz * BY + oy) * BX + ox);
+      v[0] = b[(lz * BY + lyy) * BX + lxx]; v[1] = b[(lz * BY + lyy) * BX + hx];
+      v[2] = b[(lz * BY + hy) * BX + lxx];  v[3] = b[(lz * BY + hy) * BX + hx];
+      v[4] = b[(hz * BY + lyy) * BX + lxx]; v[5] = b[(hz * BY + lyy) * BX + hx];
+      v[6] = b[(hz * BY + hy) * BX + lxx];  v[7] = b[(hz * BY + hy) * BX + hx];
+    } else {
+      v[0] = d[((int64_t)lz * H + lyy) * W + lxx]; v[1] = d[((int64_t)lz * H + lyy) * W + hx];
+      v[2] = d[((int64_t)lz * H + hy) * W + lxx];  v[3] = d[((int64_t)lz * H + hy) * W + hx];
+      v[4] = d[((int64_t)hz * H + lyy) * W + lxx]; v[5] = d[((int64_t)hz * H + lyy) * W + hx];
+      v[6] = d[((int64_t)hz * H + hy) * W + lxx];  v[7] = d[((int64_t)hz * H + hy) * W + hx];
+    }
+    // corner order and weight products of advect_k: corner bits (z, y, x), w = wz' * wy' * wx', o += w * value
+    float o = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      float w = 1.f;
+      w *= (c & 4) ? wz : (1.f - wz);
+      w *= (c & 2) ? wy : (1.f - wy);
+      w *= (c & 1) ? wx : (1.f - wx);
+      o += w * v[c];
+    }
+    out[((int64_t)z * H + y) * W + x] = o;
+  }
+}
+
+template <int R>
+static int launch_advect(const float* d, const float* vel, int D, int H, int W, float* out, cudaStream_t st) {
+  using namespace adv;
+  constexpr int BZ = TZ + 2 * R + 1, BY = TY + 2 * R + 1, BX = ((TX + 2 * R + 1 + 3) + 3) & ~3;
+  CUtensorMap md;
+  if (!tma::make_volume_map(&md, d, D, H, W, BZ, BY, BX)) return LNST_EARG;
+  const int smem = BZ * BY * BX * 4 + 128;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(advect3_tma_k<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  const int tz = (D + TZ - 1) / TZ, ty = (H + TY - 1) / TY, tx = (W + TX - 1) / TX;
+  advect3_tma_k<R><<<(unsigned)(tz * ty * tx), THREADS, smem, st>>>(
+      md, d, vel, D, H, W, D > 1 ? 2.0f / (float)(D - 1) : 0.f, H > 1 ? 2.0f / (float)(H - 1) : 0.f,
+      W > 1 ? 2.0f / (float)(W - 1) : 0.f, out, ty, tx);
+  return (int)cudaGetLastError();
+}
+
+// d [D,H,W] scalar field, vel [D,H,W,3] in normalised units per step (channel i <-> axis i), out [D,H,W].
+// reach: bound on the back-trace length in cells the staged box is sized for (1..4); longer back-traces still give the
+// exact result (global gathers).
+extern "C" int lnst_advect3_tma(const float* d, const float* vel, int32_t D, int32_t H, int32_t W, int32_t reach,
+                                float* out, void* stream) {
+  if (!d || !vel || !out || D < 1 || H < 1 || W < 1 || (int64_t)D * H * W >= 0x7fffffff) return LNST_EARG;
+  cudaStream_t st = lnst_stream(stream);
+  if (reach <= 1) return launch_advect<1>(d, vel, D, H, W, out, st);
+  if (reach == 2) return launch_advect<2>(d, vel, D, H, W, out, st);
+  if (reach == 3) return launch_advect<3>(d, vel, D, H, W, out, st);
+  return launch_advect<4>(d, vel, D, H, W, out, st);
+}

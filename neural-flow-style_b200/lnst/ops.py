@@ -133,6 +133,7 @@ USE_TMA = os.environ.get('LNST_TMA', '1') not in ('0', '')
 # against 151 us -- its per-slab CTA barriers and 25 % occupancy cost more than the merged atomics save; DESIGN.md
 # section 3), so it is opt-in: LNST_TMA_BWD=1 or ``ops.USE_TMA_BWD = True``.
 USE_TMA_BWD = os.environ.get('LNST_TMA_BWD', '0') not in ('0', '')
+ADVECT_REACH = 2
 
 
 def _tma_ok(*vols):
@@ -435,6 +436,12 @@ def advect(d, vel):
     dim = vel.shape[-1]
     dims = (C.c_int32 * 3)(*([int(s) for s in d.shape[:dim]] + [1] * (3 - dim)))
     out = torch.empty_like(d)
+    if dim == 3 and d.shape[-1] == 1 and d.numel() < 2 ** 31 - 1 and d.shape[2] % 4 == 0 and _tma_ok(d.reshape(d.shape[:3])):
+        # scalar field: the source box of every output tile is staged in shared memory by TMA (csrc/tiles_tma.cu);
+        # ADVECT_REACH = the back-trace length in cells the box is sized for (longer ones gather from global memory)
+        _lib.get().call('lnst_advect3_tma', ptr(d), ptr(vel), d.shape[0], d.shape[1], d.shape[2], int(ADVECT_REACH),
+                        ptr(out), _s(d))
+        return out
     _lib.get().call('lnst_advect', ptr(d), ptr(vel), dim, dims, d.shape[-1], ptr(out), _s(d))
     return out
 

@@ -155,3 +155,22 @@ def test_splat_gather_equals_scatter(res, nk, n):
     got_b = ops.splat_wavg_fwd_gather(lists, rt, vt, grid, hs, torch.zeros(D, H, W, device=DEV), box)
     assert torch.equal(torch.isnan(got_b), torch.isnan(want))
     assert (got_b[ok] - want[ok]).abs().max() <= 2e-5 * want[ok].abs().max()
+
+
+@pytest.mark.parametrize('shape,amp', [((24, 24, 24), 1.5), ((128, 128, 128), 2.0), ((20, 28, 36), 0.5), ((16, 16, 32), 6.0)])
+def test_advect_tma_equals_simt(shape, amp):
+    """order-1 semi-Lagrangian advection of a scalar field with the source tiles staged by TMA against the gather kernel;
+    velocities up to `amp` cells (6 cells: beyond the staged reach, the global-memory branch)"""
+    D, H, W = shape
+    rng = np.random.RandomState(D + W)
+    d = torch.tensor(rng.rand(D, H, W, 1).astype(np.float32)).to(DEV)
+    cells = np.array([D - 1, H - 1, W - 1], np.float32)
+    vel = torch.tensor((rng.uniform(-amp, amp, (D, H, W, 3)) * 2.0 / cells).astype(np.float32)).to(DEV)
+    o0, o1 = both(lambda: ops.advect(d, vel))
+    assert (o0 - o1).abs().max() <= 1e-6 * o0.abs().max()
+    for reach in (1, 4):
+        ops.ADVECT_REACH = reach
+        try:
+            assert (ops.advect(d, vel) - o0).abs().max() <= 1e-6 * o0.abs().max()
+        finally:
+            ops.ADVECT_REACH = 2

@@ -124,6 +124,13 @@ def main():
     add('splat_wavg_bwd', lambda: ops.splat_wavg_bwd_coef(fr['p'], var, ws['grid'], hs, coef, g_d, gvar), N * (12 + 16) + 4 * Vb)
     add('smooth3_relu_fwd', lambda: ops.smooth3_relu_fwd(ws['d'], ws['ds'], st.k, box), 8 * Vb)
     add('smooth3_relu_bwd', lambda: ops.smooth3_relu_bwd(g_ds, ds, ws['g_d'], st.k, box), 12 * Vb)
+    # semi-Lagrangian advect microbenchmark: 128^3 scalar density, 3-channel velocity U(+-2 cells)
+    ad = torch.rand(128, 128, 128, 1, device=dev)
+    av = ((torch.rand(128, 128, 128, 3, device=dev) * 4 - 2) * (2.0 / 127)).contiguous()
+    add('advect 128^3 (TMA-staged tiles)', lambda: ops.advect(ad, av), 4 * 128 ** 3 * 5)
+    ops.USE_TMA = False
+    add('advect 128^3 (gather kernel)', lambda: ops.advect(ad, av), 4 * 128 ** 3 * 5)
+    ops.USE_TMA = True
     x = torch.randn(nv, H, W, 3, device=dev)
     d_img = torch.empty_like(x)
 
