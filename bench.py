@@ -483,16 +483,19 @@ def time_run(make_styler, params, iters_a, iters_b, **run_kw):
     """steady-state iterations/s of a drop-in ``Styler.run``: two runs with different iteration budgets, the difference
     of their wall clocks over the difference in iterations (set-up, capture and the final inference cancel); also the
     whole wall clock of the longer run"""
-    walls = []
-    for it in (iters_a, iters_a, iters_b):               # the first run is an untimed warm-up (allocator, lazy initialisation)
+    walls = {iters_a: [], iters_b: []}
+    for k, it in enumerate((iters_a, iters_b, iters_a, iters_b, iters_a)):   # the first run is an untimed warm-up
         st = make_styler(it)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         out = st.run(params, **run_kw)
         torch.cuda.synchronize()
-        walls.append(time.perf_counter() - t0)
+        if k:
+            walls[it].append(time.perf_counter() - t0)
         del st
-    walls = walls[1:]
+    # set-up, graph capture and the final inference cancel in the difference; the minimum of the repeats of each budget
+    # keeps allocator churn (cudaFree of the previous run's graph pools) out of it
+    walls = [min(walls[iters_a]), min(walls[iters_b])]
     per_iter = max((walls[1] - walls[0]) / (iters_b - iters_a), 1e-9)
     return {'value': 1.0 / per_iter, 'unit': 'iters/s', 'ms_per_iter': 1e3 * per_iter, 'run_wall_s': walls[1],
             'run_iters': iters_b, 'final_loss': float(np.asarray(out['l'][-1]).reshape(-1)[-1])}
@@ -560,6 +563,7 @@ def other_configs(ctx, conv_math, hbm_peak, tf_peak, src):
         m = measure_step(ctx, 'C5', 'allreduce', conv_math, steps=3, warmup=3, full=True)
         res['C5'] = {'workload': WORKLOADS['C5']['desc'], 'value': m['value'], 'unit': 'iters/s', 'ms_per_step': m['ms_step'],
                      'e2e': m['e2e']['value'], 'conv_math': conv_math + ' (VGG), fp32 CUDA cores (GraphDef network)',
+                     'kernel_table_ms_per_step': {k: round(v['ms'], 3) for k, v in sorted(m['table'].items(), key=lambda kv: -kv[1]['ms'])[:8]},
                      'roofline': roofline_entry('C5', m['table'], m['ms_step'], hbm_peak, tf_peak, src, {})}
     except Exception as e:                                 # pragma: no cover
         res['C5'] = {'error': repr(e)}

@@ -86,6 +86,74 @@ struct AccEpilogue {      // g = acc (+ g)
   }
 };
 
+// Data gradient of a convolution with a THIN input (Cin <= 4: the network's first layer, conv2d0 7x7/2 on RGB).  As a GEMM
+// it has N = Cin columns, and the 64-wide tiles of the shared SGEMM engine spend 95 % of their FMAs on padding (C5: 11.9 of
+// the step's 21 ms).  Here a thread owns one input pixel: it walks the taps that map onto it (stride-aligned ones only),
+// reads the Cout cotangents of that output pixel as float4s and keeps its Cin sums in registers; the weights sit in shared
+// memory.  Same k order (tap-major, co inner) as the GEMM form.
+template <int CIN>
+__global__ void __launch_bounds__(128) conv2d_bwd_data_thin_k(const float* __restrict__ gy, const float* __restrict__ mask,
+                                                              int ldg, const float* __restrict__ w, float* __restrict__ gx,
+                                                              int n, Conv2dGeom g, int accumulate) {
+  LNST_DYN_SMEM(float, ws);                                   // [kh*kw][CIN][Cout] (HWIO)
+  const int nw = g.kh * g.kw * CIN * g.Cout;
+  for (int i = threadIdx.x; i < nw; i += blockDim.x) ws[i] = w[i];
+  __syncthreads();
+  const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= (int64_t)n * g.H * g.W) return;
+  const int ix = (int)(m % g.W);
+  const int64_t t = m / g.W;
+  const int iy = (int)(t % g.H), img = (int)(t / g.H);
+  float acc[CIN];
+#pragma unroll
+  for (int ci = 0; ci < CIN; ++ci) acc[ci] = 0.f;
+  const bool vec = (g.Cout % 4 == 0) && (ldg % 4 == 0);
+  for (int ky = 0; ky < g.kh; ++ky) {
+    const int ty = iy + g.pt - ky;
+    if (ty < 0) break;
+    const int oy = ty / g.stride;
+    if (oy * g.stride != ty || oy >= g.OH) continue;
+    for (int kx = 0; kx < g.kw; ++kx) {
+      const int tx = ix + g.pl - kx;
+      if (tx < 0) break;
+      const int ox = tx / g.stride;
+      if (ox * g.stride != tx || ox >= g.OW) continue;
+      const int64_t o = ((int64_t)(img * g.OH + oy) * g.OW + ox) * ldg;
+      const float* wp = ws + (ky * g.kw + kx) * CIN * g.Cout;
+      if (vec) {
+        for (int co = 0; co < g.Cout; co += 4) {
+          float4 gv = *reinterpret_cast<const float4*>(gy + o + co);
+          if (mask) {
+            const float4 mv = *reinterpret_cast<const float4*>(mask + o + co);
+            if (!(mv.x > 0.f)) gv.x = 0.f;
+            if (!(mv.y > 0.f)) gv.y = 0.f;
+            if (!(mv.z > 0.f)) gv.z = 0.f;
+            if (!(mv.w > 0.f)) gv.w = 0.f;
+          }
+#pragma unroll
+          for (int ci = 0; ci < CIN; ++ci) {
+            const float4 wv = *reinterpret_cast<const float4*>(wp + ci * g.Cout + co);
+            acc[ci] = fmaf(gv.x, wv.x, acc[ci]); acc[ci] = fmaf(gv.y, wv.y, acc[ci]);
+            acc[ci] = fmaf(gv.z, wv.z, acc[ci]); acc[ci] = fmaf(gv.w, wv.w, acc[ci]);
+          }
+        }
+      } else {
+        for (int co = 0; co < g.Cout; ++co) {
+          float gv = gy[o + co];
+          if (mask && !(mask[o + co] > 0.f)) gv = 0.f;
+#pragma unroll
+          for (int ci = 0; ci < CIN; ++ci) acc[ci] = fmaf(gv, wp[ci * g.Cout + co], acc[ci]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int ci = 0; ci < CIN; ++ci) {
+    const int64_t q = m * CIN + ci;
+    gx[q] = accumulate ? gx[q] + acc[ci] : acc[ci];
+  }
+}
+
 __global__ void relu_fwd_k(const float* __restrict__ x, float* __restrict__ y, int64_t n) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) y[i] = fmaxf(x[i], 0.f);
@@ -292,6 +360,18 @@ extern "C" int lnst_conv2d_bwd_data_f32(const float* g_y, const float* relu_y, i
                                         int32_t accumulate, void* stream) {
   Conv2dGeom g{H, W, Cin, Cout, kh, kw, stride, pad_top, pad_left, OH, OW};
   if (!g_y || !w || !g_x || !conv_geom_ok(g, n) || ldg < Cout) return LNST_EARG;
+  const size_t wbytes = sizeof(float) * (size_t)kh * kw * Cin * Cout;
+  if (Cin <= 4 && wbytes <= 48 * 1024 && (int64_t)n * OH * OW * ldg < 0x7fffffff) {   // thin input: one thread per input pixel
+    const int64_t pixels = (int64_t)n * H * W;
+    const dim3 grid_(lnst_blocks(pixels, 128)), blk(128);
+    switch (Cin) {
+      case 1: { auto k = conv2d_bwd_data_thin_k<1>; LNST_LAUNCH(k, grid_, blk, wbytes, lnst_stream(stream), g_y, relu_y, (int)ldg, w, g_x, (int)n, g, (int)accumulate); break; }
+      case 2: { auto k = conv2d_bwd_data_thin_k<2>; LNST_LAUNCH(k, grid_, blk, wbytes, lnst_stream(stream), g_y, relu_y, (int)ldg, w, g_x, (int)n, g, (int)accumulate); break; }
+      case 3: { auto k = conv2d_bwd_data_thin_k<3>; LNST_LAUNCH(k, grid_, blk, wbytes, lnst_stream(stream), g_y, relu_y, (int)ldg, w, g_x, (int)n, g, (int)accumulate); break; }
+      default: { auto k = conv2d_bwd_data_thin_k<4>; LNST_LAUNCH(k, grid_, blk, wbytes, lnst_stream(stream), g_y, relu_y, (int)ldg, w, g_x, (int)n, g, (int)accumulate); break; }
+    }
+    return lnst_status();
+  }
   Conv2dGradA A{g_y, relu_y, (int)ldg, g};
   Conv2dGradB B{w, (int)Cin, (int)Cout};
   AccEpilogue ep{g_x, (int)Cin, (int)accumulate};

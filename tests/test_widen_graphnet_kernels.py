@@ -63,10 +63,11 @@ def test_conv2d_fwd_bwd(dev, n, H, W, cin, cout, k, stride, padding):
     close(gx, 2 * x.grad, tol=3e-6, what='conv2d dgrad accumulate')
 
 
-def test_conv2d_dgrad_with_relu_mask(dev):
+@pytest.mark.parametrize('cin', [5, 3])                      # 3: the thin-input kernel (one thread per input pixel)
+def test_conv2d_dgrad_with_relu_mask(dev, cin):
     rng = np.random.RandomState(3)
-    x = torch.tensor(rng.randn(2, 7, 6, 5).astype(np.float32), requires_grad=True)
-    w = torch.tensor(rng.randn(3, 3, 5, 4).astype(np.float32))
+    x = torch.tensor(rng.randn(2, 7, 6, cin).astype(np.float32), requires_grad=True)
+    w = torch.tensor(rng.randn(3, 3, cin, 4).astype(np.float32))
     b = torch.tensor(rng.randn(4).astype(np.float32))
     y = ref_conv(x, w, b, 1, 'SAME', relu=True)
     g = torch.tensor(rng.randn(*y.shape).astype(np.float32))
