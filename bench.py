@@ -121,6 +121,9 @@ def algorithmic_units(name, a, nk=2):
         return (28 * v(a[4]), 0)
     if name == 'lnst_adam_iterate_dev':                  # g_opt, grad, m, v in; m, v, var, delta, g_opt out (+ mask/width)
         return (40 * v(a[4]), 0)
+    if name == 'lnst_conv_first_bwd_gray_direct':
+        n, H, W = [v(x) for x in a[4:7]]
+        return (n * H * W * (4 + (256 if v(a[1]) else 128)), 2 * n * H * W * 9 * 64)
     if name in ('lnst_conv_first_fwd_gray', 'lnst_conv_first_bwd_gray_tc', 'lnst_conv_first_fwd_gray_x3', 'lnst_conv_first_bwd_gray_x3_tc'):
         n, H, W = [v(x) for x in (a[5:8] if 'fwd' in name else a[3:6])]
         return (n * H * W * (4 + 128), 2 * n * H * W * 9 * 64)
@@ -532,7 +535,7 @@ def other_configs(ctx, conv_math, hbm_peak, tf_peak, src):
         r_ = time_run(mk2, {'p': p2, 'r': r2}, 50, 150, c_init=c0)
         r_.update({'workload': 'C1: dambreak2d-like single frame, 2-D 256x256 colour field (81 splat taps), VGG-19 conv1_1, '
                                '50 Adam iterations; N = %d particles' % p2[0].shape[0], 'conv_math': 'fp32 (Cin = 3: CUDA cores)',
-                   'wall_s_50_iters_whole_run': None})
+                   })
         res['C1'] = r_
     except Exception as e:                                 # pragma: no cover
         res['C1'] = {'error': repr(e)}

@@ -291,6 +291,12 @@ int lnst_raymarch_fwd_tma(const float* vol, const float* rot, int32_t n_views, i
  * longer back-traces gather from global memory, so the result does not depend on the bound. */
 int lnst_advect3_tma(const float* d, const float* vel, int32_t D, int32_t H, int32_t W, int32_t reach, float* out,
                      void* stream);
+/* Data gradient of conv1_1 w.r.t. a gray render on the CUDA cores, the 18 x 18 patch of every 16 x 16 pixel tile staged by
+ * one TMA box: g bf16 [n,H,W,64] (split = 0) or [n,H,W,128] = [hi | lo] (split = 1), wg fp32 [9,64] (data-gradient
+ * weights summed over the three input channels times the input scale) -> g_gray fp32 [n,H,W].  Same result as
+ * lnst_conv_first_bwd_gray[_x3]_tc with un-rounded weights. */
+int lnst_conv_first_bwd_gray_direct(const void* g, int32_t split, const float* wg, float* g_gray, int32_t n, int32_t H,
+                                    int32_t W, void* stream);
 /* smoke render (liquid = 0) only; g_vol accumulates like lnst_raymarch_bwd_box */
 int lnst_raymarch_bwd_tma(const float* vol, const float* rot, int32_t n_views, int32_t D, int32_t H, int32_t W, float tau,
                           const LnstBox* box, const int32_t* intervals, const float* stot, const float* g_img,

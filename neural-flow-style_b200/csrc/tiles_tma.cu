@@ -4,6 +4,7 @@
 // (W % 4 != 0) and of views too oblique for a fixed slab box.
 //   reference: styler_3p.py:112-125 (3x3x3 smoothing + ReLU), :148-158 (render), transform.py:611-628,343-433 (rotate),
 //              transform.py:1577-1704 (p2g_wavg), :557-609 (advect).
+#include <cuda_bf16.h>
 #include "tma_tiles.cuh"
 #include "render_common.cuh"
 #include "splat_common.cuh"
@@ -959,4 +960,108 @@ extern "C" int lnst_advect3_tma(const float* d, const float* vel, int32_t D, int
   if (reach == 2) return launch_advect<2>(d, vel, D, H, W, out, st);
   if (reach == 3) return launch_advect<3>(d, vel, D, H, W, out, st);
   return launch_advect<4>(d, vel, D, H, W, out, st);
+}
+
+// =====================================================================================================================
+// Data gradient of conv1_1 w.r.t. a GRAY render (styler_base.py:41-43 folds the RGB replication into the weights):
+// g_gray[p] = sum_tap sum_ch g[p + tap][ch] * wg[tap][ch], zero padded -- 64 (or 2 x 64 split) bf16 channels in, ONE fp32
+// channel out.  On the tensor cores this is an N = 16 MMA whose time is the A operand's shared-memory reads (0.064 ms at
+// C3 in bf16x3); here a CTA stages the 18 x 18 pixel patch of its 16 x 16 tile with ONE TMA box (out-of-image pixels are
+// zero filled = the SAME padding) and a thread sums its pixel's 9 x 64 products on the CUDA cores, fp32 weights.
+// Bank conflicts: a pixel row is 128 / 256 B, so the lanes of a quarter-warp read the 16-byte chunk (j + lane) % NCH of
+// their pixel in step j -- 8 distinct bank groups -- and fetch the matching weights.
+// =====================================================================================================================
+namespace cfb {
+constexpr int T = 16;                                        // tile of T x T pixels, patch (T+2)^2
+constexpr int THREADS = T * T;
+}
+
+template <int SPLIT>
+__global__ void __launch_bounds__(cfb::THREADS) conv_first_bwd_gray_direct_k(const __grid_constant__ CUtensorMap map_g,
+                                                                            const float* __restrict__ wg,
+                                                                            float* __restrict__ g_gray, int H, int W,
+                                                                            int tiles_y, int tiles_x) {
+  using namespace cfb;
+  constexpr int C2 = SPLIT ? 128 : 64;                       // bf16 elements per pixel row
+  constexpr int NCH = C2 / 8;                                // 16-byte chunks per pixel row
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  const uint4* patch = reinterpret_cast<const uint4*>(base);                // [(T+2)*(T+2)][NCH]
+  float* sw = reinterpret_cast<float*>(base + (T + 2) * (T + 2) * C2 * 2);   // [9][64]
+  __shared__ __align__(8) uint64_t bar_store;
+  const uint32_t bar = tma::smem_u32(&bar_store);
+  const int t = blockIdx.x;
+  const int tx_ = t % tiles_x, ty_ = (t / tiles_x) % tiles_y, img = t / (tiles_x * tiles_y);
+  const int y0 = ty_ * T, x0 = tx_ * T;
+  if (threadIdx.x == 0) {
+    tma::mbar_init(bar, 1);
+    tma::fence_mbar_init();
+    tma::mbar_expect_tx(bar, (T + 2) * (T + 2) * C2 * 2);
+    tma::load_4d(tma::smem_u32(base), &map_g, bar, 0, x0 - 1, y0 - 1, img);
+  }
+  for (int i = threadIdx.x; i < 9 * 64; i += THREADS) sw[i] = wg[i];
+  __syncthreads();
+  tma::mbar_wait(bar, 0);
+  const int ly = threadIdx.x / T, lx = threadIdx.x % T;
+  const int rot = threadIdx.x & 7;                           // chunk rotation of this lane within its quarter-warp
+  float acc = 0.f;
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap) {
+    const int dy = tap / 3, dx = tap - 3 * dy;
+    const uint4* row = patch + ((ly + dy) * (T + 2) + lx + dx) * NCH;
+    const float* w = sw + tap * 64;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {                            // 8 chunks of 8 channels
+      const int c = (j + rot) & 7;
+      const float4 w0 = *reinterpret_cast<const float4*>(w + c * 8), w1 = *reinterpret_cast<const float4*>(w + c * 8 + 4);
+      const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+      const uint4 hi = row[c];
+      const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&hi);
+      float v[8];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { const float2 f = __bfloat1622float2(hh[e]); v[2 * e] = f.x; v[2 * e + 1] = f.y; }
+      if (SPLIT) {
+        const uint4 lo = row[8 + c];
+        const __nv_bfloat162* ll = reinterpret_cast<const __nv_bfloat162*>(&lo);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { const float2 f = __bfloat1622float2(ll[e]); v[2 * e] += f.x; v[2 * e + 1] += f.y; }
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc = fmaf(v[e], wv[e], acc);
+    }
+  }
+  const int y = y0 + ly, x = x0 + lx;
+  if (y < H && x < W) g_gray[((int64_t)img * H + y) * W + x] = acc;
+}
+
+// g bf16 [n,H,W,64] (split = 0) or [n,H,W,128] = [hi | lo] (split = 1); wg fp32 [9,64] = the data-gradient weights of
+// conv1_1 summed over the three input channels, times the net-input scale; g_gray fp32 [n,H,W]
+extern "C" int lnst_conv_first_bwd_gray_direct(const void* g, int32_t split, const float* wg, float* g_gray, int32_t n,
+                                               int32_t H, int32_t W, void* stream) {
+  using namespace cfb;
+  if (!g || !wg || !g_gray || n < 1 || H < 1 || W < 1) return LNST_EARG;
+  const int C2 = split ? 128 : 64;
+  CUtensorMap mg;
+  if (!tma::make_nhwc_bf16_map(&mg, g, n, H, W, C2, T + 2, T + 2)) return LNST_EARG;
+  const int ty = (H + T - 1) / T, tx = (W + T - 1) / T;
+  const int smem = (T + 2) * (T + 2) * C2 * 2 + 9 * 64 * 4 + 128;
+  cudaStream_t st = lnst_stream(stream);
+  if (split) {
+    static bool configured = false;
+    if (!configured) {
+      cudaError_t e = cudaFuncSetAttribute(conv_first_bwd_gray_direct_k<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      if (e != cudaSuccess) return (int)e;
+      configured = true;
+    }
+    conv_first_bwd_gray_direct_k<1><<<(unsigned)(n * ty * tx), THREADS, smem, st>>>(mg, wg, g_gray, H, W, ty, tx);
+  } else {
+    static bool configured = false;
+    if (!configured) {
+      cudaError_t e = cudaFuncSetAttribute(conv_first_bwd_gray_direct_k<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      if (e != cudaSuccess) return (int)e;
+      configured = true;
+    }
+    conv_first_bwd_gray_direct_k<0><<<(unsigned)(n * ty * tx), THREADS, smem, st>>>(mg, wg, g_gray, H, W, ty, tx);
+  }
+  return (int)cudaGetLastError();
 }

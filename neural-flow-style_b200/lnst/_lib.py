@@ -136,6 +136,7 @@ CUDA_ONLY = {
     'lnst_f32_to_bf16': [vp, vp, i64, vp],
     # TMA-tiled volume kernels (csrc/tiles_tma.cu)
     'lnst_tma_supported': [],
+    'lnst_conv_first_bwd_gray_direct': [vp, i32, vp, vp, i32, i32, i32, vp],
     'lnst_advect3_tma': [vp, vp, i32, i32, i32, i32, vp, vp],
     'lnst_splat_wavg_fwd_gather': [vp, vp, vp, vp, vp, GP, FP, i32, vp, BP, vp],
     'lnst_set_raymarch_slab': [i32],

@@ -804,3 +804,11 @@ def from_split(x):
     y = torch.empty(tuple(x.shape[:-1]) + (C_,), dtype=f32, device=x.device)
     _lib.get().call('lnst_bf16x3_to_f32', ptr(x), ptr(y), x.numel() // (2 * C_), C_, _s(x))
     return y
+
+
+def conv_first_bwd_gray_direct(g, split, wg):
+    """d loss / d gray render from the conv1_1 gradient: g bf16 [n,H,W,64] (or [n,H,W,128] split), wg fp32 [9,64] -> [n,H,W]"""
+    n, H, W, _ = g.shape
+    gg = torch.empty(n, H, W, dtype=f32, device=g.device)
+    _lib.get().call('lnst_conv_first_bwd_gray_direct', ptr(g), int(bool(split)), ptr(wg), ptr(gg), n, H, W, _s(g))
+    return gg

@@ -58,6 +58,7 @@ class TensorCoreConvs:
                 wdg = torch.zeros(9, 16, 64, dtype=torch.float32, device=w.device)
                 wdg[:, 0] = 255.0 * net.wd[name].to(torch.float32).permute(0, 1, 3, 2).reshape(9, 3, 64).sum(1)
                 self.wd16_gray = _hilo(wdg) if self.split else wdg.to(torch.bfloat16).contiguous()
+                self.wg_gray = wdg[:, 0].contiguous()              # fp32 [9,64]: the CUDA-core kernel's weights
 
     # ---- network ----------------------------------------------------------------------------------
     def forward(self, x, layers, gray=None):
@@ -100,7 +101,12 @@ class TensorCoreConvs:
                 if name in self.wdp and prev is not None:
                     g = (ops.conv3x3_bf16x3_tc if sp else ops.conv3x3_bf16_tc)(g, self.wdp[name], None, relu=False, mask=mask)
                 elif prev is None and gray and tuple(self.net.w[name].shape[2:]) == (3, 64):
-                    g = (ops.conv_first_bwd_gray_x3_tc if sp else ops.conv_first_bwd_gray_tc)(g, self.wd16_gray)  # d loss / d gray
+                    if getattr(self, 'first_bwd_direct', False) and ops._tma_ok():
+                        # TMA-staged patch + CUDA cores with un-rounded fp32 weights: shared-memory-bandwidth bound
+                        # (0.090 ms at C3 against 0.064 for the N = 16 MMA form), so not the default
+                        g = ops.conv_first_bwd_gray_direct(g, sp, self.wg_gray)
+                    else:
+                        g = (ops.conv_first_bwd_gray_x3_tc if sp else ops.conv_first_bwd_gray_tc)(g, self.wd16_gray)  # d loss / d gray
                 elif prev is None and tuple(self.net.w[name].shape[2:]) == (3, 64):
                     if sp:
                         g = ops.conv_first_bwd_x3_tc(g, self.wd16)

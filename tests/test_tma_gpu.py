@@ -174,3 +174,22 @@ def test_advect_tma_equals_simt(shape, amp):
             assert (ops.advect(d, vel) - o0).abs().max() <= 1e-6 * o0.abs().max()
         finally:
             ops.ADVECT_REACH = 2
+
+
+@pytest.mark.parametrize('n,H,W', [(2, 13, 9), (3, 50, 64), (1, 200, 200), (2, 16, 16), (1, 33, 47)])
+@pytest.mark.parametrize('split', [False, True])
+def test_conv_first_bwd_gray_direct(n, H, W, split):
+    """conv1_1's data gradient w.r.t. the gray render on the CUDA cores (TMA-staged patch) against an fp64 transposed
+    convolution of the same bf16 / split-bf16 cotangent"""
+    from lnst import synth, vgg
+    gen = torch.Generator().manual_seed(H * 7 + W)
+    net = vgg.LossNet(synth.vgg_weights(), 'vgg_19', DEV, math='bf16x3' if split else 'bf16')
+    w = net.w['conv1_1'].double().cpu()
+    g32 = torch.randn(n, H, W, 64, generator=gen)
+    g_dev = ops.to_split(g32.to(DEV)) if split else g32.to(torch.bfloat16).to(DEV)
+    g_val = ops.from_split(g_dev).cpu().double() if split else g_dev.float().cpu().double()
+    gx = torch.nn.functional.conv_transpose2d(g_val.permute(0, 3, 1, 2), w.permute(3, 2, 0, 1), padding=1)
+    want = 255.0 * gx.sum(1)
+    got = ops.conv_first_bwd_gray_direct(g_dev, split, net.tc.wg_gray).cpu().double()
+    err = (got - want).abs().max().item()
+    assert err <= 3e-6 * want.abs().max().item(), (err, want.abs().max().item())
