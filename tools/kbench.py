@@ -107,7 +107,7 @@ def main():
         lib.call('lnst_set_raymarch_merge', 0)
         add('raymarch_bwd(merge=0)', lambda: ops.raymarch_bwd(ds, rot, st.transmit, False, stot, g_img, g_ds, box),
             nv * (8 * Vb + 8 * P))
-        lib.call('lnst_set_raymarch_merge', 1)
+        lib.call('lnst_set_raymarch_merge', 2)
     add('raymarch_bwd(box only)', lambda: ops.raymarch_bwd(ds, rot, st.transmit, False, stot, g_img, g_ds, box), nv * (8 * Vb + 8 * P))
     add('raymarch_bwd', lambda: ops.raymarch_bwd(ds, rot, st.transmit, False, stot, g_img, g_ds, box, bricks), nv * (8 * Vb + 8 * P))
     add('splat_wavg_fwd', lambda: ops.splat_wavg_fwd(fr['p'], fr['r'], var, ws['grid'], hs, wmap, ws['num'], ws['d'], box),
