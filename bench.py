@@ -483,9 +483,26 @@ def roofline_entry(wl, table, ms_step, hbm_peak, tf_peak, src, extra):
 
 
 def time_run(make_styler, params, iters_a, iters_b, **run_kw):
-    """steady-state iterations/s of a drop-in ``Styler.run``: two runs with different iteration budgets, the difference
-    of their wall clocks over the difference in iterations (set-up, capture and the final inference cancel); also the
-    whole wall clock of the longer run"""
+    """steady-state iterations/s of a drop-in ``Styler.run``.  3-D styler: CUDA events the run loop records at the start of
+    every iteration (``Styler.iter_events``; iterations 0 and 1 are the eager pass and the graph captures).  Stylers without
+    that hook (2-D): two runs with different iteration budgets, the difference of their wall clocks over the difference in
+    iterations (set-up and the final inference cancel; minimum over repeats)."""
+    st = make_styler(iters_b)
+    hook = hasattr(st, 'frame_step')
+    if hook:
+        st.iter_events = []
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        out = st.run(params, **run_kw)
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        ev = st.iter_events
+        per_iter = ev[2].elapsed_time(ev[-1]) / (len(ev) - 3) * 1e-3
+        del st
+        return {'value': 1.0 / per_iter, 'unit': 'iters/s', 'ms_per_iter': 1e3 * per_iter, 'run_wall_s': wall,
+                'run_iters': iters_b, 'final_loss': float(np.asarray(out['l'][-1]).reshape(-1)[-1]),
+                'timed': 'CUDA events around iterations 2..%d of one Styler.run' % (iters_b - 1)}
+    del st
     walls = {iters_a: [], iters_b: []}
     for k, it in enumerate((iters_a, iters_b, iters_a, iters_b, iters_a)):   # the first run is an untimed warm-up
         st = make_styler(it)
@@ -496,12 +513,11 @@ def time_run(make_styler, params, iters_a, iters_b, **run_kw):
         if k:
             walls[it].append(time.perf_counter() - t0)
         del st
-    # set-up, graph capture and the final inference cancel in the difference; the minimum of the repeats of each budget
-    # keeps allocator churn (cudaFree of the previous run's graph pools) out of it
     walls = [min(walls[iters_a]), min(walls[iters_b])]
     per_iter = max((walls[1] - walls[0]) / (iters_b - iters_a), 1e-9)
     return {'value': 1.0 / per_iter, 'unit': 'iters/s', 'ms_per_iter': 1e3 * per_iter, 'run_wall_s': walls[1],
-            'run_iters': iters_b, 'final_loss': float(np.asarray(out['l'][-1]).reshape(-1)[-1])}
+            'run_iters': iters_b, 'final_loss': float(np.asarray(out['l'][-1]).reshape(-1)[-1]),
+            'timed': 'wall-clock difference of runs with %d and %d iterations' % (iters_a, iters_b)}
 
 
 def other_configs(ctx, conv_math, hbm_peak, tf_peak, src):

@@ -763,6 +763,10 @@ class Styler(StylerBase):
             loss_o, intm_o = {t: [] for t in mine}, {}
             runners = {}
             for step in range(self.iter):
+                if getattr(self, 'iter_events', None) is not None and self.device.type == 'cuda':
+                    ev = torch.cuda.Event(enable_timing=True)    # measurement hook (bench.py, tools/c4_sharded.py):
+                    ev.record()                                  # one event at the start of every iteration
+                    self.iter_events.append(ev)
                 deltas = {}
                 for t in mine:
                     fr = frames[t]

@@ -33,29 +33,31 @@ def main():
     sty = synth.style_image(128, 128)
     out = {'workload': 'C4: 60 frames, 128^3, position mode, N = 200000 per frame, temporal Gaussian sigma 9', 'n_gpus': world}
     for mode in ('alltoall', 'allgather'):
-        walls = {4: [], 24: []}
-        for k, it in enumerate((4, 24, 4, 24, 4)):            # the first run is an untimed warm-up
-            cfg = liquid_cfg(res=128, iter=it, num_frames=nf, window_sigma=9, frames_per_opt=1, lr=0.002, conv_math='bf16x3',
-                             style_layer=['conv2_1', 'conv3_1'], w_style_layer=[0.5, 0.5])
-            st = Styler(cfg, weights=synth.vgg_weights(), device=torch.device('cuda', local))
-            st.style_img = sty
-            st.frame_exchange = mode
-            if world > 1:
-                dist.barrier()
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            res = st.run({'p': p})
-            torch.cuda.synchronize()
-            if world > 1:
-                dist.barrier()
-            if k:
-                walls[it].append(time.perf_counter() - t0)
-            del st
-            torch.cuda.empty_cache()
-        walls = [min(walls[4]), min(walls[24])]               # minimum of the repeats: allocator churn stays out
-        per_iter = (walls[1] - walls[0]) / 20
+        # steady-state rate from CUDA events the run loop records at the start of every iteration (iterations 0 and 1 are
+        # the eager pass and the graph captures): 22 replayed iterations, max over ranks
+        iters = 25
+        cfg = liquid_cfg(res=128, iter=iters, num_frames=nf, window_sigma=9, frames_per_opt=1, lr=0.002, conv_math='bf16x3',
+                         style_layer=['conv2_1', 'conv3_1'], w_style_layer=[0.5, 0.5])
+        st = Styler(cfg, weights=synth.vgg_weights(), device=torch.device('cuda', local))
+        st.style_img = sty
+        st.frame_exchange = mode
+        st.iter_events = []
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        res = st.run({'p': p})
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        ev = st.iter_events
+        ms = torch.tensor([ev[2].elapsed_time(ev[-1]) / (len(ev) - 3)], device=torch.device('cuda', local))
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        per_iter = float(ms.item()) * 1e-3
+        del st
+        torch.cuda.empty_cache()
         out[mode] = {'iters_per_s': 1.0 / per_iter, 'ms_per_iter': 1e3 * per_iter, 'frame_steps_per_s': nf / per_iter,
-                     'run_wall_s_24_iters': walls[1], 'final_loss': float(res['l'][0][-1])}
+                     'run_wall_s_%d_iters' % iters: wall, 'final_loss': float(res['l'][0][-1])}
     if rank == 0:
         print(json.dumps(out), flush=True)
     if world > 1:
