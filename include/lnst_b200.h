@@ -379,6 +379,9 @@ int lnst_masked_accumulate(const float* t, const float* m, const float* f, int32
 int lnst_temporal_gauss(const float* x, float* y, int32_t T, int64_t M, float sigma, void* stream);
 /* y += a*x */
 int lnst_axpy(float* y, const float* x, float a, int64_t n, void* stream);
+/* out[0] = scale * sum(x[0..n)) (the iteration's mean loss over its views, styler_3p.py:342); x[0..n) = 0 on the stream. */
+int lnst_sum_scale(const float* x, int32_t n, float scale, float* out, void* stream);
+int lnst_zero(float* x, int64_t n, void* stream);
 /* tf.clip_by_value (styler_2p.py:68,88,94) and its gradient gx = scale*g inside [lo,hi], 0 outside. */
 int lnst_clip_fwd(const float* x, float lo, float hi, float* y, int64_t n, void* stream);
 int lnst_clip_bwd(const float* g, const float* x, float lo, float hi, float scale, float* gx, int64_t n,

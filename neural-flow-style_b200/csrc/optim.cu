@@ -230,6 +230,26 @@ extern "C" int lnst_iterate_delta(const float* g_new, float scale, const float* 
   return lnst_status();
 }
 
+// out[0] = scale * sum(x[0..n)) for a handful of per-view loss slots (one warp; n <= a few hundred): the per-iteration loss
+// scalar of the loop (styler_3p.py:342 `np.mean(loss)`), so that the replayed step holds no framework reduction kernels
+__global__ void sum_scale_k(const float* __restrict__ x, int n, float scale, float* __restrict__ out) {
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += 32) s += x[i];
+  s = lnst_warp_sum(s);
+  if (threadIdx.x == 0) out[0] = s * scale;
+}
+extern "C" int lnst_sum_scale(const float* x, int32_t n, float scale, float* out, void* stream) {
+  if (!x || !out || n < 1) return LNST_EARG;
+  LNST_LAUNCH(sum_scale_k, dim3(1), dim3(32), 0, lnst_stream(stream), x, (int)n, scale, out);
+  return lnst_status();
+}
+// x[0..n) = 0 on the stream (loss slots the loss kernels accumulate into)
+extern "C" int lnst_zero(float* x, int64_t n, void* stream) {
+  if (n < 0 || (n > 0 && !x)) return LNST_EARG;
+  if (n > 0) cudaMemsetAsync(x, 0, sizeof(float) * n, lnst_stream(stream));
+  return lnst_status();
+}
+
 extern "C" int lnst_axpy(float* y, const float* x, float a, int64_t n, void* stream) {
   if (n < 0) return LNST_EARG;
   if (n == 0) return LNST_OK;

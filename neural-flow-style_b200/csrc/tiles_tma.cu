@@ -466,8 +466,6 @@ __global__ void __launch_bounds__(rm::THREADS) raymarch_fwd_tma_k(const __grid_c
       // clamping and every footprint is inside the box by construction (tile-uniform test)
       const bool interior = za >= 1 && za + BZ <= g.D - 1 && oy >= 0 && oy + BY <= g.H && ox >= 0 && ox + BX <= g.W;
       if (interior) {
-        const float czl = l.cz - (float)za, cyl = l.cy - (float)oy, cxl = l.cx - (float)ox;   // (unused: see below)
-        (void)czl; (void)cyl; (void)cxl;
         const int base = -((za * BY + oy) * BX + ox);
         auto sample_in = [&](float fi, int& z0) -> float {   // same values as locate3 + lerp_planes, clamps are no-ops here
           const float z = fmaf(l.kz, fi, l.cz), y = fmaf(l.ky, fi, l.cy), x = fmaf(l.kx, fi, l.cx);

@@ -82,6 +82,8 @@ SIGNATURES = {
     'lnst_masked_accumulate': [vp, vp, vp, i32, i32, f32, vp, i64, vp],
     'lnst_temporal_gauss': [vp, vp, i32, i64, f32, vp],
     'lnst_axpy': [vp, vp, f32, i64, vp],
+    'lnst_sum_scale': [vp, i32, f32, vp, vp],
+    'lnst_zero': [vp, i64, vp],
     'lnst_clip_fwd': [vp, f32, f32, vp, i64, vp],
     'lnst_clip_bwd': [vp, vp, f32, f32, f32, vp, i64, vp],
     'lnst_mul_bcast': [vp, vp, i32, vp, i64, vp],

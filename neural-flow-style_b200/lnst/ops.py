@@ -185,10 +185,6 @@ def rotate_bwd(g_out, rot, g_vol=None):
     return g_vol
 
 
-def _u8(t):
-    return None if t is None else C.c_void_p(t.data_ptr())
-
-
 def ray_intervals(rot, shape, box, bricks, out=None):
     """int32 [n_views,H,W,2]: inclusive depth range of every ray that can touch the box / occupied bricks."""
     D, H, W = shape
@@ -387,6 +383,21 @@ def adam_iterate_dev(g_opt, grad, m, v, state, lr, gscale, mask, mask_stride, va
 def adam_step(var, grad, m, v, lr_t, gscale=1.0, beta1=0.9, beta2=0.999, eps=1e-8):
     _lib.get().call('lnst_adam_step', ptr(var), ptr(grad), ptr(m), ptr(v), var.numel(), float(lr_t), beta1, beta2,
                     eps, float(gscale), _s(var))
+
+
+def sum_scale(x, scale, out=None):
+    """out[0] = scale * sum(x) for a few loss slots -- no framework reduction kernel in the replayed step"""
+    if out is None:
+        out = torch.empty(1, dtype=f32, device=x.device)
+    _lib.get().call('lnst_sum_scale', ptr(x), x.numel(), float(scale), ptr(out), _s(x))
+    return out
+
+
+def zeros(n, device):
+    """fp32 [n] zeroed on the current stream by the library (a memset node in the step's graph)"""
+    x = torch.empty(n, dtype=f32, device=device)
+    _lib.get().call('lnst_zero', ptr(x), n, _s(x))
+    return x
 
 
 def iterate_accumulate(acc, var, first):

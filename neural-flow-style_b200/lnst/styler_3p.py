@@ -418,7 +418,7 @@ class Styler(StylerBase):
         with nvtx('lnst.render_fwd'):
             st = self._render(ds, rot, box, ws['bricks'], net_input=not gray_path, joint=group, touch=ws['touch'])
         nv = st['gray'].shape[0]
-        loss = torch.zeros(nv, dtype=f32, device=self.device)
+        loss = ops.zeros(nv, self.device)
         g_gray0 = None
         if gray_path:
             g_x = self.image_loss_and_grad(None, None, style_grams, loss, gray=st['gray'])
@@ -676,7 +676,7 @@ class Styler(StylerBase):
             gview = buf[:-1].view_as(g_opt_t) if buf is not None and 'd' in self.target_field else None
             if self._rot_mine is not None:
                 l, grad = self.loss_and_grad(fr, g_opt_t, ws, self._rot_mine, style_grams, grad_out=gview)
-                lsum = l.sum().reshape(1)
+                lsum = ops.sum_scale(l, 1.0)
             else:
                 grad = gview.zero_() if gview is not None else torch.zeros_like(g_opt_t)
                 lsum = torch.zeros(1, dtype=f32, device=dev)
@@ -687,7 +687,7 @@ class Styler(StylerBase):
                 torch.distributed.all_reduce(buf)
                 grad, lsum = buf[:-1].view_as(g_opt_t), buf[-1:]
             gscale = 1.0 / self.n_views
-            loss_t = lsum[0] / self.n_views
+            loss_t = ops.sum_scale(lsum, 1.0 / self.n_views)[0]
         else:                                                      # :354-357
             l, grad = self.loss_and_grad(fr, g_opt_t, ws, None, style_grams)
             loss_t = l[0]

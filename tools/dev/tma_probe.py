@@ -1,6 +1,6 @@
 """developer probe: run one TMA-tiled kernel in isolation (under compute-sanitizer) -- python tools/tma_probe.py smooth|rm"""
 import os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(ROOT, 'neural-flow-style_b200'))
 import torch
 from lnst import ops, _lib
