@@ -19,6 +19,10 @@ from .transform import rot_mat
 from .util import octave_sizes
 
 
+_GRAPH_POOLS = {}       # device index -> (pool handle, keeper graph, its buffer): see Styler._graph_pool
+_CAPTURE_STREAMS = {}   # device index -> the capture stream
+
+
 class _Adam:
     """Slots of one tf.compat.v1.train.AdamOptimizer (styler_3p.py:320-323): m, v per variable
     and the fp32 beta-power accumulators, kept across frames of the group and across octaves.
@@ -64,10 +68,21 @@ class StepRunner:
             lib = _lib.get()
             if self.graph is None:
                 n0 = lib.launches
-                torch.cuda.synchronize(st.device)
+                # capture_begin / capture_end directly: the torch.cuda.graph context manager empties the caching
+                # allocator (device and pinned host) before every capture, and the cudaFree / cudaMalloc round trips
+                # of the blocks this run keeps using cost 10-200 ms per capture -- more than the 20 iterations of a
+                # reference-sized run (tools/dev/run_phases.py)
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, pool=st._graph_pool()):
-                    self.out = st.frame_step(*self.args)
+                pool = st._graph_pool()
+                cap = st._capture_stream()
+                cap.wait_stream(torch.cuda.current_stream(st.device))
+                with torch.cuda.stream(cap):
+                    g.capture_begin(pool)
+                    try:
+                        self.out = st.frame_step(*self.args)
+                    finally:
+                        g.capture_end()
+                torch.cuda.current_stream(st.device).wait_stream(cap)
                 self.n_abi, lib.launches, self.graph = lib.launches - n0, n0, g
             self.graph.replay()
             lib.launches += self.n_abi
@@ -120,9 +135,34 @@ class Styler(StylerBase):
             self._upload_views()
 
     def _graph_pool(self):
+        """One graph memory pool per device for the whole process, kept alive by a one-kernel graph: the blocks of a
+        finished run's step graphs go back to this pool and the next run's captures take them from there.  With a pool per
+        Styler every run paid cudaMalloc for ~1.5 GB of step temporaries inside its capture (20-50 ms at C3, more than
+        the run's 20 replayed iterations) and left the old pool's memory parked until the allocator ran dry."""
         if self._pool is None:
-            self._pool = torch.cuda.graph_pool_handle()
+            key = self.device.index if self.device.index is not None else torch.cuda.current_device()
+            ent = _GRAPH_POOLS.get(key)
+            if ent is None:
+                handle = torch.cuda.graph_pool_handle()
+                keeper = torch.cuda.CUDAGraph()
+                cap = self._capture_stream()
+                cap.wait_stream(torch.cuda.current_stream(self.device))
+                with torch.cuda.stream(cap):
+                    keeper.capture_begin(handle)
+                    buf = torch.zeros(1, dtype=f32, device=self.device)
+                    keeper.capture_end()
+                torch.cuda.current_stream(self.device).wait_stream(cap)
+                ent = _GRAPH_POOLS[key] = (handle, keeper, buf)
+            self._pool = ent[0]
         return self._pool
+
+    def _capture_stream(self):
+        """The side stream every capture of this process runs on (the caching allocator only hands a freed block to
+        requests of the stream it was allocated on: a stream per Styler would strand the pool's blocks)."""
+        key = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        if key not in _CAPTURE_STREAMS:
+            _CAPTURE_STREAMS[key] = torch.cuda.Stream(self.device)
+        return _CAPTURE_STREAMS[key]
 
     def _upload_views(self):
         """Host view matrices -> the persistent device buffers the kernels (and graphs) read."""
@@ -820,21 +860,40 @@ class Styler(StylerBase):
         # final inference (:404-438)
         result = {'l': loss_history, 'd_intm': d_intm, 'v': None, 'c': None}
         res = oct_size[-1]
-        self._frame_cache = {}
-        ws = self._workspace(res, frames)
-        p_sty, v_sty, d_sty, r_sty = [], [], [], []
+        if self.octave_n < 1 or self.iter < 1 or tuple(ws['res']) != tuple(res):
+            self._frame_cache = {}                                 # else: the last octave's volumes, box and weight maps
+            ws = self._workspace(res, frames)
+        # results leave through ONE page-locked staging buffer (positions, variables, density and render of every
+        # frame, asynchronous copies, one synchronisation); the arrays handed back are views of it
+        D, H, W = res
+        V = D * H * W
+        psz = [int(frames[t]['p'].numel()) for t in range(nf)]
+        vsz = [int(g_opt[t].numel()) for t in range(nf)]
+        stage, views, img_shape = None, [], None
         for t in range(nf):
             p_out, d_out, d_img = self.infer(frames[t], g_opt[t], ws, eye)
             if inv is not None:                                    # back to the caller's particle order
                 p_out, g_opt[t] = p_out[inv], g_opt[t][inv]
-            p_sty.append(p_out.cpu().numpy())
-            v_sty.append(g_opt[t].cpu().numpy())
-            d_sty.append(d_out.cpu().numpy()[..., None])
-            r_sty.append(d_img.cpu().numpy().astype(np.uint8))
-        result['p'] = p_sty
+            if stage is None:
+                img_shape = tuple(d_img.shape)
+                isz = int(d_img.numel())
+                stage = torch.empty(sum(psz) + sum(vsz) + nf * (V + isz), dtype=f32, pin_memory=(dev.type == 'cuda'))
+                o_d, o_r = sum(psz) + sum(vsz), sum(psz) + sum(vsz) + nf * V
+            o_p = sum(psz[:t]) + sum(vsz[:t])
+            dst = (stage[o_p:o_p + psz[t]], stage[o_p + psz[t]:o_p + psz[t] + vsz[t]],
+                   stage[o_d + t * V:o_d + (t + 1) * V], stage[o_r + t * isz:o_r + (t + 1) * isz])
+            for x, y in zip(dst, (p_out, g_opt[t], d_out, d_img)):
+                x.copy_(y.reshape(-1).to(f32), non_blocking=True)
+            views.append((dst[0].numpy().reshape(tuple(p_out.shape)), dst[1].numpy().reshape(tuple(g_opt[t].shape))))
+        if dev.type == 'cuda':
+            torch.cuda.current_stream(dev).synchronize()
+        result['p'] = [v[0] for v in views]
         if 'p' in self.target_field:
-            result['v'] = v_sty
-        result['d'] = np.array(d_sty)
-        result['r'] = np.array(r_sty)
-        result['g_opt'] = [g.cpu().numpy() for g in g_opt]         # engine extra: final variables
+            result['v'] = [v[1] for v in views]
+        if stage is not None:
+            result['d'] = stage[o_d:o_d + nf * V].numpy().reshape(nf, D, H, W, 1)
+            result['r'] = stage[o_r:o_r + nf * isz].numpy().reshape((nf,) + img_shape).astype(np.uint8)
+        else:
+            result['d'], result['r'] = np.array([]), np.array([])
+        result['g_opt'] = [v[1] for v in views]                    # engine extra: final variables
         return result

@@ -8,6 +8,8 @@ and losses are fp32.
 ``split=True`` (``conv_math='bf16x3'``): the same kernels on [hi | lo] bf16 halves of every value -- three K passes per
 convolution, fp32-tolerance results (csrc/conv_tc.cu ConvShape; include/lnst_b200.h "bf16x3").  Activation tensors
 then have 2C physical channels."""
+import weakref
+
 import torch
 
 from . import ops
@@ -33,7 +35,9 @@ def _pack2(w):
 
 class TensorCoreConvs:
     def __init__(self, net, split=False):
-        self.net = net
+        # the network owns this object: a weak back-reference keeps the pair out of a reference cycle, so the
+        # packed weights (~0.3 GB for VGG-19) are released with the network instead of waiting for the cycle collector
+        self._net = weakref.ref(net)
         self.split = bool(split)
         pack = _pack2 if self.split else _pack
         self.wp, self.wdp = {}, {}
@@ -59,6 +63,10 @@ class TensorCoreConvs:
                 wdg[:, 0] = 255.0 * net.wd[name].to(torch.float32).permute(0, 1, 3, 2).reshape(9, 3, 64).sum(1)
                 self.wd16_gray = _hilo(wdg) if self.split else wdg.to(torch.bfloat16).contiguous()
                 self.wg_gray = wdg[:, 0].contiguous()              # fp32 [9,64]: the CUDA-core kernel's weights
+
+    @property
+    def net(self):
+        return self._net()
 
     # ---- network ----------------------------------------------------------------------------------
     def forward(self, x, layers, gray=None):
