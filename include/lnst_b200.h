@@ -234,6 +234,10 @@ int lnst_umma_probe(const void* x, const void* b, float* out, int32_t pitched, i
  * and read the 9 taps through descriptor offsets; 2 = every layer does (weights streamed when they do not
  * fit); 0 = one TMA tile per tap everywhere. */
 int lnst_set_conv_halo(int32_t on);
+/* Tuning switch (tests / microbenchmarks): 1 (default) = the gray data gradient of conv1_1 (lnst_conv_first_bwd_gray[_x3]_tc)
+ * runs as one GEMM per halo'd patch with the 9 taps as the N dimension plus a 9-term gather; 0 = the halo kernel with
+ * one MMA chain per tap. */
+int lnst_set_conv_first_col(int32_t on);
 /* Data gradient of conv1_1 on tensor cores: g bf16 [n,H,W,64], wd16 bf16 [9,16,64] (rows 0..2 = the
  * flipped/transposed 64->3 weights, rows 3..15 zero) -> gx fp32 [n,H,W,3]. */
 int lnst_conv_first_bwd_tc(const void* g, const void* wd16, float* gx, int32_t n, int32_t H, int32_t W,

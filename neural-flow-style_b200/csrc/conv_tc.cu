@@ -1745,6 +1745,156 @@ __global__ void __launch_bounds__(128) conv_first_bwd_k(const __nv_bfloat16* __r
   }
 }
 
+// ---- data gradient of conv1_1 for a gray render as ONE GEMM per patch + a 9-term gather -------------------
+// g_gray[p] = sum_tap sum_c g[p + tap, c] * w[tap, c].  The halo kernel above spends one M=128, N=16 MMA chain per
+// TAP on it (9 x 3 passes x 4 k-steps per tile, every one of them bound by the 4 KiB A operand it pulls out of shared
+// memory: 0.064 ms at C3 for 20 GFLOP).  Here the taps are the N dimension instead: Z[q, tap] = sum_c g[q, c] * w[tap, c]
+// for every pixel q of the halo'd 18 x 10 patch (two M=128 blocks over the patch rows as they lie in shared memory,
+// N = 16 of which 9 are used), i.e. each activation byte goes through the tensor pipe once per pass instead of nine
+// times, and the output pixel sums its nine Z[q + tap, tap] from a shared-memory copy of Z.
+// One tile per CTA, three CTAs per SM: loads, MMAs and the gather of neighbouring CTAs overlap.
+constexpr int CF_BTILE = 16 * 128;                          // one 64-channel chunk of the weights: 16 rows x 128 B
+template <bool SPLIT>
+__global__ void __launch_bounds__(128) conv_first_bwd_gray_col_k(const __grid_constant__ CUtensorMap map_g,
+                                                                  const __nv_bfloat16* __restrict__ wd16,
+                                                                  float* __restrict__ g_gray, int H, int W, int tiles_w,
+                                                                  int tiles_h, float scale) {
+  constexpr int NCH = SPLIT ? 2 : 1;                         // activation / weight chunks: [hi | lo]
+  constexpr int XC = 64 * NCH;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t smem_a = base;                              // NCH patches at PATCH_STRIDE; the second M block of the
+  const uint32_t a_end = smem_a + (NCH - 1) * PATCH_STRIDE + 256 * 128;   // last one reads (unused) rows up to here
+  const uint32_t smem_b = a_end;                             // NCH x 2 KiB
+  const uint32_t zbuf = smem_b + NCH * CF_BTILE;             // 180 x 9 floats
+  const uint32_t bars = zbuf + 180 * 9 * 4 + 8;
+  const uint32_t tmem_slot = bars + 16;
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));     // generic pointer to `base`
+  float* Z = reinterpret_cast<float*>(gen + (zbuf - base));
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(gen + (tmem_slot - base));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_sp = tiles_w * tiles_h;
+  const int img = blockIdx.x / tiles_sp, rem = blockIdx.x - img * tiles_sp;
+  const int th = rem / tiles_w, tw = rem - th * tiles_w;
+
+  // weights -> the K-major SWIZZLE_128B operand layout, by hand: row = tap (9 of 16, the rest zero), 16-byte piece j of
+  // row r sits at piece j ^ (r & 7) of its 128-byte line
+#pragma unroll
+  for (int ch = 0; ch < NCH; ++ch) {
+    const int r = threadIdx.x >> 3, j = threadIdx.x & 7;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (r < 9) v = *reinterpret_cast<const uint4*>(wd16 + ((size_t)r * 16) * XC + ch * 64 + j * 8);   // row 0 of tap r
+    st_shared_v4(smem_b + ch * CF_BTILE + r * 128 + ((j ^ (r & 7)) << 4), v);
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&map_g);
+    mbar_init(bars, 1);
+    mbar_init(bars + 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(32));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_d = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    const bool leader = elect_one();
+    if (leader) {
+      mbar_expect_tx(bars, NCH * PATCH_BYTES);
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch)
+        tma_load_4d(smem_a + ch * PATCH_STRIDE, &map_g, bars, ch * 64, tw * HTW - 1, th * HTH - 1, img);
+    }
+    mbar_wait(bars, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (leader) {
+      const uint32_t idesc = umma_idesc_bf16(BLOCK_M, 16);
+      const uint32_t hi = desc_hi_sw128(1024);
+      const uint32_t alo_base = desc_lo(smem_a, 16), blo_base = desc_lo(smem_b, 16);
+      constexpr int NP = SPLIT ? 3 : 1;                      // passes: hi*Whi, lo*Whi, hi*Wlo
+#pragma unroll
+      for (int m = 0; m < 2; ++m) {
+#pragma unroll
+        for (int ps = 0; ps < NP; ++ps) {
+          const int ac = (ps == 1) ? 1 : 0, bc = (ps == 2) ? 1 : 0;
+          const uint32_t alo = alo_base + ((ac * PATCH_STRIDE + m * 128 * 128) >> 4);
+          const uint32_t blo = blo_base + ((bc * CF_BTILE) >> 4);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+            umma_bf16_lh(tmem_d + m * 16, alo + k * 2, hi, blo + k * 2, hi, idesc, (ps | k) != 0 ? 1u : 0u);
+        }
+      }
+      umma_commit(bars + 8);
+    }
+  }
+  mbar_wait(bars + 8, 0);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  {
+    const int r = warp * 32 + lane;
+    uint32_t v[16];
+    tmem_ld16(tmem_d + ((uint32_t)(warp * 32) << 16), v);
+#pragma unroll
+    for (int t = 0; t < 9; ++t) Z[r * 9 + t] = __uint_as_float(v[t]);
+    tmem_ld16(tmem_d + ((uint32_t)(warp * 32) << 16) + 16, v);
+    if (128 + r < PATCH_ROWS) {
+#pragma unroll
+      for (int t = 0; t < 9; ++t) Z[(128 + r) * 9 + t] = __uint_as_float(v[t]);
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  {
+    const int r = threadIdx.x, py = r >> 3, px = r & 7;
+    const int hh = th * HTH + py, ww = tw * HTW + px;
+    float acc = 0.f;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) acc += Z[((py + ky) * (HTW + 2) + px + kx) * 9 + ky * 3 + kx];
+    if (hh < H && ww < W) g_gray[((int64_t)img * H + hh) * W + ww] = acc * scale;
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(32));
+  }
+}
+
+static int conv_first_col = 1;    // tuning switch: 1 = the one-GEMM-per-patch kernel above for the gray data gradient, 0 = halo kernel
+
+static int launch_first_bwd_col(const void* g, const void* wd16, float* g_gray, int n, int H, int W, int split,
+                                cudaStream_t stream) {
+  const int nch = split ? 2 : 1, xC = 64 * nch;
+  CUtensorMap mg;
+  const cuuint64_t dims[4] = {(cuuint64_t)xC, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n};
+  const cuuint64_t strides[3] = {(cuuint64_t)xC * 2, (cuuint64_t)W * xC * 2, (cuuint64_t)H * W * xC * 2};
+  const cuuint32_t box[4] = {(cuuint32_t)BLOCK_K, (cuuint32_t)(HTW + 2), (cuuint32_t)(HTH + 2), 1};
+  if (!make_map(&mg, g, 4, dims, strides, box)) return LNST_EARG;
+  const int smem = (nch - 1) * PATCH_STRIDE + 256 * 128 + nch * CF_BTILE + 180 * 9 * 4 + 8 + 16 + 16 + 1024;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_first_bwd_gray_col_k<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 68 * 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(conv_first_bwd_gray_col_k<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 68 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  const int tiles_w = (W + HTW - 1) / HTW, tiles_h = (H + HTH - 1) / HTH;
+  const unsigned grid = (unsigned)(tiles_w * tiles_h * n);
+  if (split)
+    conv_first_bwd_gray_col_k<true><<<grid, 128, smem, stream>>>(mg, (const __nv_bfloat16*)wd16, g_gray, H, W, tiles_w,
+                                                                 tiles_h, 1.0f);
+  else
+    conv_first_bwd_gray_col_k<false><<<grid, 128, smem, stream>>>(mg, (const __nv_bfloat16*)wd16, g_gray, H, W, tiles_w,
+                                                                  tiles_h, 1.0f);
+  return (int)cudaGetLastError();
+}
+
 }  // namespace tc
 
 // ---------------------------------------------------------------------------------------
@@ -1822,6 +1972,7 @@ extern "C" int lnst_conv_first_bwd_tc(const void* g, const void* wd16, float* gx
 extern "C" int lnst_conv_first_bwd_gray_tc(const void* g, const void* wd16, float* g_gray, int32_t n, int32_t H,
                                            int32_t W, void* stream) {
   if (!g || !wd16 || !g_gray || n < 1 || H < 1 || W < 1) return LNST_EARG;
+  if (tc::conv_first_col) return tc::launch_first_bwd_col(g, wd16, g_gray, n, H, W, 0, lnst_stream(stream));
   return tc::launch_halo<16, true>(g, wd16, nullptr, nullptr, nullptr, g_gray, n, H, W, 64, 16, 0, 1.0f,
                                    lnst_stream(stream), 1);
 }
@@ -1836,9 +1987,11 @@ extern "C" int lnst_conv_first_bwd_x3_tc(const void* g, const void* wd16, float*
 extern "C" int lnst_conv_first_bwd_gray_x3_tc(const void* g, const void* wd16, float* g_gray, int32_t n, int32_t H,
                                               int32_t W, void* stream) {
   if (!g || !wd16 || !g_gray || n < 1 || H < 1 || W < 1) return LNST_EARG;
+  if (tc::conv_first_col) return tc::launch_first_bwd_col(g, wd16, g_gray, n, H, W, 1, lnst_stream(stream));
   return tc::launch_halo<16, true>(g, wd16, nullptr, nullptr, nullptr, g_gray, n, H, W, 64, 16, 0, 1.0f,
                                    lnst_stream(stream), 1, 1);
 }
+extern "C" int lnst_set_conv_first_col(int32_t on) { tc::conv_first_col = on ? 1 : 0; return LNST_OK; }
 
 extern "C" int lnst_set_conv_persistent(int32_t on) { tc::conv_persistent = on ? 1 : 0; return LNST_OK; }
 

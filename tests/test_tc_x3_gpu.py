@@ -158,3 +158,32 @@ def test_styler_x3_holds_the_fp32_tolerance(view_mode):
     assert np.linalg.norm(g_new - g_ref) / np.linalg.norm(g_ref) < 2e-3
     # 27 Adam steps in sequential mode (9 per iteration): measured 2.0e-4 of the field maximum there
     assert np.abs(out["d"] - ref["d"]).max() <= (4e-4 if view_mode == "sequential" else 2e-4) * np.abs(ref["d"]).max()
+
+
+@pytest.mark.parametrize('n,H,W', [(2, 13, 9), (3, 50, 64), (1, 200, 200), (2, 16, 16), (1, 33, 47)])
+@pytest.mark.parametrize('split', [False, True])
+def test_conv_first_bwd_gray_one_gemm_per_patch(n, H, W, split):
+    """conv1_1's data gradient w.r.t. the gray render: the kernel with the 9 taps as the N dimension of one GEMM per halo'd
+    patch (default) against an fp64 transposed convolution of the same cotangent, and against the per-tap halo kernel."""
+    from lnst import _lib, synth, vgg
+    dev = torch.device('cuda:0')
+    gen = torch.Generator().manual_seed(H * 7 + W)
+    net = vgg.LossNet(synth.vgg_weights(), 'vgg_19', dev, math='bf16x3' if split else 'bf16')
+    w = net.w['conv1_1'].double().cpu()
+    g32 = torch.randn(n, H, W, 64, generator=gen)
+    g_dev = ops.to_split(g32.to(dev)) if split else g32.to(torch.bfloat16).to(dev)
+    g_val = ops.from_split(g_dev).cpu().double() if split else g_dev.float().cpu().double()
+    gx = torch.nn.functional.conv_transpose2d(g_val.permute(0, 3, 1, 2), w.permute(3, 2, 0, 1), padding=1)
+    want = 255.0 * gx.sum(1)
+    fn = ops.conv_first_bwd_gray_x3_tc if split else ops.conv_first_bwd_gray_tc
+    lib = _lib.get()
+    got = fn(g_dev, net.tc.wd16_gray).cpu().double()
+    lib.call('lnst_set_conv_first_col', 0)
+    try:
+        halo = fn(g_dev, net.tc.wd16_gray).cpu().double()
+    finally:
+        lib.call('lnst_set_conv_first_col', 1)
+    scale = want.abs().max().item()
+    tol = 5e-5 if split else 2e-2                      # split weights carry 16 mantissa bits, plain bf16 weights 8
+    assert (got - want).abs().max().item() <= tol * scale, ((got - want).abs().max().item(), scale)
+    assert (got - halo).abs().max().item() <= 2e-5 * scale, ((got - halo).abs().max().item(), scale)
