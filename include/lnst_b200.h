@@ -238,6 +238,9 @@ int lnst_set_conv_halo(int32_t on);
  * runs as one GEMM per halo'd patch with the 9 taps as the N dimension plus a 9-term gather; 0 = the halo kernel with
  * one MMA chain per tap. */
 int lnst_set_conv_first_col(int32_t on);
+/* Tuning switch (tests / microbenchmarks): 1 (default) = lnst_gram_diff_bf16x3_tc sums hi^T hi + hi^T lo + lo^T hi in one
+ * TMEM tile per 128 x 128 block (C % 128 == 0); 0 = the 2C x 2C Gram of the split rows plus a finishing pass. */
+int lnst_set_gram_split3(int32_t on);
 /* Data gradient of conv1_1 on tensor cores: g bf16 [n,H,W,64], wd16 bf16 [9,16,64] (rows 0..2 = the
  * flipped/transposed 64->3 weights, rows 3..15 zero) -> gx fp32 [n,H,W,3]. */
 int lnst_conv_first_bwd_tc(const void* g, const void* wd16, float* gx, int32_t n, int32_t H, int32_t W,

@@ -404,6 +404,8 @@ __device__ __forceinline__ void warp_rows_store(uint32_t stage, int lane, const 
   __syncwarp();
 }
 
+template <int BLOCK_N> struct PersistStages { static constexpr int value = (BLOCK_N == 128) ? 5 : 6; };
+
 template <int BLOCK_N>
 __global__ void __launch_bounds__(PERSIST_THREADS, 1)
 conv3x3_tc_persist_k(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
@@ -411,11 +413,12 @@ conv3x3_tc_persist_k(const __grid_constant__ CUtensorMap map_x, const __grid_con
                      const __nv_bfloat16* __restrict__ addend, __nv_bfloat16* __restrict__ y, ConvShape s,
                      int n_blocks_n, int n_tiles) {
   constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
-  constexpr int PSTAGES = (BLOCK_N == 128) ? 6 : 8;
+  constexpr int PSTAGES = PersistStages<BLOCK_N>::value;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t smem_a = base;
-  const uint32_t smem_b = base + PSTAGES * A_BYTES;
+  const uint32_t stage_base = base;                     // 8 epilogue warps x 4 KiB (fp32 accumulator chunks, transposed)
+  const uint32_t smem_a = base + 8 * 4096;
+  const uint32_t smem_b = smem_a + PSTAGES * A_BYTES;
   const uint32_t bars = smem_b + PSTAGES * B_BYTES;     // full[P], empty[P], tfull[2], tempty[2]
   const uint32_t bar_tfull = bars + 8 * (2 * PSTAGES);
   const uint32_t bar_tempty = bar_tfull + 16;
@@ -500,61 +503,55 @@ conv3x3_tc_persist_k(const __grid_constant__ CUtensorMap map_x, const __grid_con
     }
   } else {
     // ===== epilogue: warps 2..9.  TMEM sub-partition = warp % 4; warps 2-5 take the lower half of the tile's
-    // columns, warps 6-9 the upper half.  The epilogue's global traffic (addend and mask rows in, output rows
-    // out: 16-byte accesses issued by the row's owner) is latency-bound, and with four warps the data in
-    // flight per SM capped the Gram-gradient GEMM and the masked data gradients at ~2.4 TB/s chip-wide =====
+    // columns, warps 6-9 the upper half.  An accumulator row lives in ONE thread, but a row-per-thread access to the
+    // mask / addend / output rows touches 32 different 128-byte lines per instruction with 16 bytes each: the LSU
+    // serialised them (ncu: l1tex 74 %, tensor pipe 12 % on the Gram-gradient GEMM, ~10 000 wavefronts per tile).  So
+    // the fp32 accumulator chunk (32 rows x 32 columns per warp) goes through a swizzled shared-memory tile and ALL
+    // the arithmetic happens in the transposed layout, where 4 lanes cover 64 contiguous bytes of a row =====
     constexpr int EN = BLOCK_N / 2;
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
-    const int r = q * 32 + lane;
+    const uint32_t stage = stage_base + (uint32_t)(warp - 2) * 4096u;   // 32 rows x 128 B, 16-byte piece j of row r at j ^ (r & 7)
+    const int sub = lane >> 2, pj = lane & 3;                            // coalesced layout: row 8 i + sub, columns 8 pj .. 8 pj + 7
     uint32_t lt = 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++lt) {
       const int nb = t % n_blocks_n, sp = t / n_blocks_n;
       const int img = sp / tiles_sp, rem = sp - img * tiles_sp;
       const int th = rem / s.tiles_w, tw = rem - th * s.tiles_w;
       const int n0 = nb * BLOCK_N + half * EN;
-      const int ph_ = th * s.TH + r / s.TW, pw_ = tw * s.TW + r % s.TW;
-      const bool valid = ph_ < s.H && pw_ < s.W;
-      const int64_t pix = ((int64_t)img * s.H + ph_) * s.W + pw_;
-      uint32_t mbits[EN / 32];
+      int64_t pix[4];
+      bool valid[4];
 #pragma unroll
-      for (int c = 0; c < EN / 32; ++c) mbits[c] = 0xffffffffu;
-      if (mask && valid) {
-        const uint4* msk = reinterpret_cast<const uint4*>(mask + pix * s.ldm + n0);
-#pragma unroll
-        for (int c = 0; c < EN / 32; ++c) {
-          uint4 mv[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) mv[j] = msk[c * 4 + j];
-          uint32_t bits = 0;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const __nv_bfloat16* mh = reinterpret_cast<const __nv_bfloat16*>(&mv[j]);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) bits |= (__bfloat162float(mh[e]) > 0.f ? 1u : 0u) << (j * 8 + e);
-          }
-          mbits[c] = bits;
-        }
-      }
-      uint4 av[4], al[4];                                             // addend (hi) and its lo half (split)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) { av[j] = make_uint4(0, 0, 0, 0); al[j] = make_uint4(0, 0, 0, 0); }
-      const uint4* add = (addend && valid) ? reinterpret_cast<const uint4*>(addend + pix * s.ldy + n0) : nullptr;
-      const uint4* addl = (add && s.split) ? reinterpret_cast<const uint4*>(addend + pix * s.ldy + s.Cout + n0) : nullptr;
-      if (add) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) av[j] = add[j];
-      }
-      if (addl) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) al[j] = addl[j];
+      for (int i = 0; i < 4; ++i) {
+        const int rr = q * 32 + i * 8 + sub;
+        const int ph_ = th * s.TH + rr / s.TW, pw_ = tw * s.TW + rr % s.TW;
+        valid[i] = ph_ < s.H && pw_ < s.W;
+        pix[i] = ((int64_t)img * s.H + ph_) * s.W + pw_;
       }
       const uint32_t buf = lt & 1, bph = (lt >> 1) & 1;
-      mbar_wait(bar_tfull + 8 * buf, bph);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t acc = tmem_d + buf * BLOCK_N + half * EN + ((uint32_t)(q * 32) << 16);
 #pragma unroll
       for (int c = 0; c < EN / 32; ++c) {
+        const int co = n0 + c * 32 + pj * 8;                             // this lane's 8 output channels
+        // the chunk's mask / addend pieces, requested before the accumulator is waited for
+        uint4 mv[4], av[4], al[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          mv[i] = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);   // bf16 1.0: keep
+          av[i] = make_uint4(0, 0, 0, 0);
+          al[i] = make_uint4(0, 0, 0, 0);
+          if (valid[i]) {
+            if (mask) mv[i] = *reinterpret_cast<const uint4*>(mask + pix[i] * s.ldm + co);
+            if (addend) {
+              av[i] = *reinterpret_cast<const uint4*>(addend + pix[i] * s.ldy + co);
+              if (s.split) al[i] = *reinterpret_cast<const uint4*>(addend + pix[i] * s.ldy + s.Cout + co);
+            }
+          }
+        }
+        if (c == 0) {
+          mbar_wait(bar_tfull + 8 * buf, bph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
         uint32_t v[32];
         tmem_ld32(acc + (uint32_t)(c * 32), v);
         if (c == EN / 32 - 1) {
@@ -563,49 +560,45 @@ conv3x3_tc_persist_k(const __grid_constant__ CUtensorMap map_x, const __grid_con
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
         }
-        uint4 an[4], anl[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { an[j] = make_uint4(0, 0, 0, 0); anl[j] = make_uint4(0, 0, 0, 0); }
-        if (add && c + 1 < EN / 32) {
+        for (int j = 0; j < 8; ++j)
+          st_shared_v4(stage + lane * 128 + ((uint32_t)((j ^ lane) & 7) << 4),
+                       make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+        __syncwarp();
+        float bb[8];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) an[j] = add[(c + 1) * 4 + j];
-          if (addl) {
+        for (int e = 0; e < 8; ++e) bb[e] = bias ? bias[co + e] : 0.f;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) anl[j] = addl[(c + 1) * 4 + j];
+        for (int i = 0; i < 4; ++i) {
+          const int row = i * 8 + sub;
+          const uint4 x0 = ld_shared_v4(stage + row * 128 + ((uint32_t)(((2 * pj) ^ row) & 7) << 4));
+          const uint4 x1 = ld_shared_v4(stage + row * 128 + ((uint32_t)(((2 * pj + 1) ^ row) & 7) << 4));
+          const uint32_t xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+          const __nv_bfloat16* mh = reinterpret_cast<const __nv_bfloat16*>(&mv[i]);
+          const __nv_bfloat16* ah = reinterpret_cast<const __nv_bfloat16*>(&av[i]);
+          const __nv_bfloat16* alh = reinterpret_cast<const __nv_bfloat16*>(&al[i]);
+          uint4 ov, ol;
+          __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&ov);
+          __nv_bfloat162* ohl = reinterpret_cast<__nv_bfloat162*>(&ol);
+#pragma unroll
+          for (int e = 0; e < 8; e += 2) {
+            float f0 = __uint_as_float(xv[e]) * s.scale, f1 = __uint_as_float(xv[e + 1]) * s.scale;
+            if (addend) { f0 += __bfloat162float(ah[e]); f1 += __bfloat162float(ah[e + 1]); }
+            if (addend && s.split) { f0 += __bfloat162float(alh[e]); f1 += __bfloat162float(alh[e + 1]); }
+            if (bias) { f0 += bb[e]; f1 += bb[e + 1]; }
+            if (s.relu) { f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); }
+            if (!(__bfloat162float(mh[e]) > 0.f)) f0 = 0.f;
+            if (!(__bfloat162float(mh[e + 1]) > 0.f)) f1 = 0.f;
+            if (s.split) split2(f0, f1, oh[e >> 1], ohl[e >> 1]);
+            else oh[e >> 1] = __floats2bfloat162_rn(f0, f1);
+          }
+          if (valid[i]) {
+            __nv_bfloat16* dst = y + pix[i] * s.ldy + co;
+            *reinterpret_cast<uint4*>(dst) = ov;
+            if (s.split) *reinterpret_cast<uint4*>(dst + s.Cout) = ol;
           }
         }
-        if (valid) {
-          const int co = n0 + c * 32;
-          __nv_bfloat16* dst = y + pix * s.ldy + co;
-          uint4 ov[4], ol[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const __nv_bfloat16* ah = reinterpret_cast<const __nv_bfloat16*>(&av[j]);
-            const __nv_bfloat16* alh = reinterpret_cast<const __nv_bfloat16*>(&al[j]);
-            __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&ov[j]);
-            __nv_bfloat162* ohl = reinterpret_cast<__nv_bfloat162*>(&ol[j]);
-#pragma unroll
-            for (int e = 0; e < 8; e += 2) {
-              float f0 = __uint_as_float(v[j * 8 + e]) * s.scale, f1 = __uint_as_float(v[j * 8 + e + 1]) * s.scale;
-              if (addend) { f0 += __bfloat162float(ah[e]); f1 += __bfloat162float(ah[e + 1]); }
-              if (addl) { f0 += __bfloat162float(alh[e]); f1 += __bfloat162float(alh[e + 1]); }
-              if (bias) { f0 += bias[co + j * 8 + e]; f1 += bias[co + j * 8 + e + 1]; }
-              if (s.relu) { f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); }
-              if (!((mbits[c] >> (j * 8 + e)) & 1u)) f0 = 0.f;
-              if (!((mbits[c] >> (j * 8 + e + 1)) & 1u)) f1 = 0.f;
-              if (s.split) split2(f0, f1, oh[e >> 1], ohl[e >> 1]);
-              else oh[e >> 1] = __floats2bfloat162_rn(f0, f1);
-            }
-          }
-#pragma unroll
-          for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(dst + j * 8) = ov[j];
-          if (s.split) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(dst + s.Cout + j * 8) = ol[j];
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) { av[j] = an[j]; al[j] = anl[j]; }
+        __syncwarp();
       }
     }
   }
@@ -1134,6 +1127,172 @@ gram_tc_k(const __grid_constant__ CUtensorMap map_f, float* __restrict__ G, int 
   }
 }
 
+// Split features F' = [hi | lo] (bf16 [n, P, 2C]): G = hi^T hi + hi^T lo + lo^T hi accumulated in ONE TMEM tile (the lo^T lo
+// term, 2^-16 relative, is dropped like in the convolutions).  The 2C x 2C Gram of the split rows (gram_tc_k on F') costs
+// four 128 x 128 products per output tile, re-loads every slab once per product and leaves the sum to a finishing kernel
+// that reads mirrored blocks; here a k-block brings the hi and lo slabs of the row block (and of the column block off
+// the diagonal) ONCE -- 32 / 64 KiB per 64 pixels, three stages in flight -- and feeds 12 MMAs.  C % 128 == 0.
+// Output tile (i <= j) is stored transposed at rows of block j, columns of block i, like gram_tc_k (sym).
+constexpr int G3_STAGES = 3;
+constexpr int G3_STAGE_BYTES = 4 * G_OP_BYTES;    // hi_i, lo_i, hi_j, lo_j: 128 channels x 64 pixels each
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gram_split_tc_k(const __grid_constant__ CUtensorMap map_f, float* __restrict__ G, int P, int C, int tiles_n,
+                int k_per_split) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bars = base + G3_STAGES * G3_STAGE_BYTES;
+  const uint32_t tmem_slot = bars + 8 * (2 * G3_STAGES + 1);
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int bi = 0, rem = blockIdx.x;
+  while (rem >= tiles_n - bi) { rem -= tiles_n - bi; ++bi; }
+  const int m0 = bi * 128, n0 = (bi + rem) * 128;
+  const int img = blockIdx.z;
+  const int p_beg = blockIdx.y * k_per_split;
+  const int p_end = min(P, p_beg + k_per_split);
+  const int num_kb = (p_end - p_beg + 63) / 64;
+  const bool diag = (m0 == n0);
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&map_f);
+    for (int i = 0; i < G3_STAGES; ++i) {
+      mbar_init(bars + 8 * i, 1);
+      mbar_init(bars + 8 * (G3_STAGES + i), 1);
+    }
+    mbar_init(bars + 8 * (2 * G3_STAGES), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(128));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_d = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    const bool leader = elect_one();
+    uint32_t st = 0, ph = 0;
+    for (int kb = 0; kb < num_kb; ++kb) {
+      mbar_wait(bars + 8 * (G3_STAGES + st), ph ^ 1);
+      if (leader) {
+        const uint32_t full = bars + 8 * st;
+        const uint32_t dst = base + st * G3_STAGE_BYTES;
+        mbar_expect_tx(full, (diag ? 2 : 4) * G_OP_BYTES);
+        const int p0 = p_beg + kb * 64;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {                      // h = 0: hi (channels [0,C)), 1: lo ([C,2C))
+          tma_load_3d(dst + h * G_OP_BYTES, &map_f, full, h * C + m0, p0, img);
+          tma_load_3d(dst + h * G_OP_BYTES + G_BOX_BYTES, &map_f, full, h * C + m0 + 64, p0, img);
+          if (!diag) {
+            tma_load_3d(dst + (2 + h) * G_OP_BYTES, &map_f, full, h * C + n0, p0, img);
+            tma_load_3d(dst + (2 + h) * G_OP_BYTES + G_BOX_BYTES, &map_f, full, h * C + n0 + 64, p0, img);
+          }
+        }
+      }
+      if (++st == G3_STAGES) { st = 0; ph ^= 1; }
+    }
+  } else if (warp == 1) {
+    const bool leader = elect_one();
+    const uint32_t idesc = umma_idesc_bf16(128, 128) | (1u << 15) | (1u << 16);      // both operands MN-major
+    const uint32_t hi = desc_hi_sw128(1024);
+    uint32_t st = 0, ph = 0;
+    for (int kb = 0; kb < num_kb; ++kb) {
+      mbar_wait(bars + 8 * st, ph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (leader) {
+        const uint32_t a_hi = desc_lo(base + st * G3_STAGE_BYTES, G_BOX_BYTES);
+        const uint32_t a_lo = a_hi + (G_OP_BYTES >> 4);
+        const uint32_t b_hi = diag ? a_hi : a_hi + (2 * G_OP_BYTES >> 4);
+        const uint32_t b_lo = b_hi + (G_OP_BYTES >> 4);
+#pragma unroll
+        for (int k = 0; k < 64 / UMMA_K; ++k) {
+          const uint32_t o = k * (2048 >> 4);
+          umma_bf16_lh(tmem_d, a_hi + o, hi, b_hi + o, hi, idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_bf16_lh(tmem_d, a_hi + o, hi, b_lo + o, hi, idesc, 1u);
+          umma_bf16_lh(tmem_d, a_lo + o, hi, b_hi + o, hi, idesc, 1u);
+        }
+        umma_commit(bars + 8 * (G3_STAGES + st));
+      }
+      if (++st == G3_STAGES) { st = 0; ph ^= 1; }
+    }
+    if (leader) umma_commit(bars + 8 * (2 * G3_STAGES));
+  } else if (num_kb > 0) {
+    const int q = warp & 3;
+    const int m = m0 + q * 32 + lane;
+    mbar_wait(bars + 8 * (2 * G3_STAGES), 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    float* Gi = G + (int64_t)img * C * C;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      uint32_t v[32];
+      tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        atomicAdd(Gi + (int64_t)(n0 + c * 32 + j) * C + m, __uint_as_float(v[j]));     // transposed: G symmetric
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(128));
+  }
+}
+
+// finishing pass of gram_split_tc_k: Graw [n, C, C] holds the blocks with row block >= column block.  One block per 1024
+// elements (four independent loads per thread in flight), one loss atomic per block (per-warp atomics onto the nine
+// loss slots serialised: ~10 us for a 0.6-2.4 MB pass).
+__global__ void __launch_bounds__(256) gram_finish_split3_k(const float* __restrict__ Graw, float* __restrict__ G,
+                                                            const float* __restrict__ Gs, __nv_bfloat16* __restrict__ Gd2,
+                                                            int C, float inv_denom, float weight, float* __restrict__ loss) {
+  __shared__ float part[8];
+  const int img = blockIdx.y;
+  const int n_el = C * C;
+  const float* g = Graw + (int64_t)img * n_el;
+  float d[4];
+  int idx[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int i = blockIdx.x * 1024 + j * 256 + threadIdx.x;
+    idx[j] = i;
+    d[j] = 0.f;
+    if (i < n_el) {
+      const int r = i / C, c = i - r * C;
+      d[j] = (r >> 7) >= (c >> 7) ? g[i] : g[(int64_t)c * C + r];
+    }
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int i = idx[j];
+    if (i >= n_el) continue;
+    float v = d[j] * inv_denom;
+    if (Gs) { v -= Gs[i]; s += v * v; }
+    G[(int64_t)img * n_el + i] = v;
+    if (Gd2) {
+      const int r = i / C, c = i - r * C;
+      const int64_t a = (int64_t)r * 2 * C + c;
+      const __nv_bfloat16 h = __float2bfloat16_rn(v);
+      Gd2[(int64_t)img * 2 * n_el + a] = h;
+      Gd2[(int64_t)img * 2 * n_el + a + C] = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
+  }
+  if (loss && Gs) {                                     // uniform branch: every thread of the block takes it
+    s = lnst_warp_sum(s);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float tot = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) tot += part[w];
+      if (tot != 0.f) atomicAdd(loss + img, weight * tot);
+    }
+  }
+}
+
 // G <- G/denom - Gs (fp32, in place), bf16 copy for the gradient GEMM, loss[img] += weight * sum(G^2)
 __global__ void gram_finish_bf16_k(float* __restrict__ G, const float* __restrict__ Gs, __nv_bfloat16* __restrict__ Gd,
                                    int n_el, float inv_denom, float weight, float* __restrict__ loss) {
@@ -1220,8 +1379,8 @@ static int launch_conv(const CUtensorMap& mx, const CUtensorMap& mw, const float
     configured = true;
   }
   if (conv_persistent) {
-    constexpr int PSTAGES = (BLOCK_N == 128) ? 6 : 8;
-    const int psmem = PSTAGES * (A_BYTES + BLOCK_N * BLOCK_K * 2) + 8 * (2 * PSTAGES + 4) + 16 + 1024;
+    constexpr int PSTAGES = PersistStages<BLOCK_N>::value;
+    const int psmem = 8 * 4096 + PSTAGES * (A_BYTES + BLOCK_N * BLOCK_K * 2) + 8 * (2 * PSTAGES + 4) + 16 + 1024;
     static bool pconfigured = false;
     static int sms = 148;
     if (!pconfigured) {
@@ -2128,9 +2287,43 @@ extern "C" int lnst_gram_diff_bf16_tc(const void* F, int32_t n, int64_t P, int32
 // Split features F bf16 [n,P,2C]: the 2C x 2C Gram of the split rows (same tensor-core kernel) lands in the scratch G2
 // [n,2C,2C] fp32 and its four blocks are folded into F^T F (hi*hi + hi*lo + lo*hi + lo*lo); G [n,C,C] fp32 = that / denom
 // - Gs, Gd2 [n,C,2C] its split copy, loss[i] += weight * sum(G[i]^2).
+static int gram_split3 = 1;       // tuning switch: 1 = gram_split_tc_k (hi/lo products summed in TMEM), 0 = 2C x 2C Gram of the split rows
+extern "C" int lnst_set_gram_split3(int32_t on) { gram_split3 = on ? 1 : 0; return LNST_OK; }
 extern "C" int lnst_gram_diff_bf16x3_tc(const void* F, int32_t n, int64_t P, int32_t C, float denom, const float* Gs,
                                         float weight, float* G2, float* G, void* Gd2, float* loss, void* stream) {
   if (!F || !G2 || !G || n < 1 || P < 1 || C < 64 || C % 64 || !(denom > 0.f) || P > 0x7fffffff) return LNST_EARG;
+  if (C % 128 == 0 && gram_split3) {
+    using namespace tc;
+    cudaStream_t st = lnst_stream(stream);
+    CUtensorMap mf;
+    const cuuint64_t dims[3] = {(cuuint64_t)(2 * C), (cuuint64_t)P, (cuuint64_t)n};
+    const cuuint64_t strides[2] = {(cuuint64_t)(2 * C) * 2, (cuuint64_t)P * (2 * C) * 2};
+    const cuuint32_t box[3] = {64, 64, 1};
+    if (!make_map(&mf, F, 3, dims, strides, box)) return LNST_EARG;
+    const int tiles_n = C / 128, tiles = tiles_n * (tiles_n + 1) / 2;
+    int splits = (148 + tiles * n - 1) / (tiles * n);           // about one wave of CTAs
+    const int max_splits = (int)((P + 255) / 256);             // at least 4 k-blocks per CTA
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+    int kps = (int)((P + splits - 1) / splits);
+    kps = ((kps + 63) / 64) * 64;
+    splits = (int)((P + kps - 1) / kps);
+    const int smem = G3_STAGES * G3_STAGE_BYTES + 8 * (2 * G3_STAGES + 1) + 16 + 1024;
+    static bool configured = false;
+    if (!configured) {
+      cudaError_t e = cudaFuncSetAttribute(gram_split_tc_k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      if (e != cudaSuccess) return (int)e;
+      configured = true;
+    }
+    cudaMemsetAsync(G2, 0, sizeof(float) * (size_t)n * C * C, st);
+    gram_split_tc_k<<<dim3(tiles, splits, n), NUM_THREADS, smem, st>>>(mf, G2, (int)P, (int)C, tiles_n, kps);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+    const int n_el3 = C * C;
+    const unsigned nb3 = (unsigned)((n_el3 + 1023) / 1024);
+    gram_finish_split3_k<<<dim3(nb3, n), 256, 0, st>>>(G2, G, Gs, (__nv_bfloat16*)Gd2, (int)C, 1.f / denom, weight, loss);
+    return lnst_status();
+  }
   const int rc = gram_raw(F, n, P, 2 * C, G2, lnst_stream(stream), 1);     // symmetric: 10 of the 16 tiles at C = 256
   if (rc != 0) return rc;
   const int n_el = C * C;

@@ -187,3 +187,33 @@ def test_conv_first_bwd_gray_one_gemm_per_patch(n, H, W, split):
     tol = 5e-5 if split else 2e-2                      # split weights carry 16 mantissa bits, plain bf16 weights 8
     assert (got - want).abs().max().item() <= tol * scale, ((got - want).abs().max().item(), scale)
     assert (got - halo).abs().max().item() <= 2e-5 * scale, ((got - halo).abs().max().item(), scale)
+
+
+@pytest.mark.parametrize('n,h,w,ch', [(2, 50, 50, 256), (3, 100, 100, 128), (1, 13, 7, 512), (2, 9, 9, 384)])
+def test_gram_x3_tmem_summed_products_match_the_split_row_gram(n, h, w, ch):
+    """lnst_gram_diff_bf16x3_tc: hi^T hi + hi^T lo + lo^T hi summed in one TMEM tile (default) against the 2C x 2C Gram of
+    the split rows (which also carries lo^T lo, 2^-16 relative) and against fp64."""
+    dev = torch.device('cuda:0')
+    g = torch.Generator().manual_seed(h * 11 + ch)
+    F = torch.relu(torch.randn(n, h, w, ch, generator=g))
+    P, den = h * w, 2.0 * h * w * ch
+    Fsp = ops.to_split(F.to(dev))
+    Gs = torch.zeros(ch, ch, device=dev)
+    lib = _lib.get()
+    outs = []
+    for mode in (1, 0):
+        lib.call('lnst_set_gram_split3', mode)
+        try:
+            loss = torch.zeros(n, device=dev)
+            G, Gd2 = ops.gram_diff_bf16x3_tc(Fsp, den, Gs, 0.5, loss)
+            outs.append((G.cpu().double(), Gd2.cpu(), loss.cpu().double()))
+        finally:
+            lib.call('lnst_set_gram_split3', 1)
+    Fd = F.double().reshape(n, P, ch)
+    want = torch.einsum('npc,npd->ncd', Fd, Fd) / den
+    scale = want.abs().max()
+    assert (outs[0][0] - want).abs().max() <= TOL * scale
+    assert (outs[0][0] - outs[1][0]).abs().max() <= TOL * scale
+    assert (outs[0][0] - outs[0][0].transpose(1, 2)).abs().max() <= 2e-6 * scale   # symmetric up to the fp32 summation order
+    np.testing.assert_allclose(outs[0][2].numpy(), outs[1][2].numpy(), rtol=1e-4)
+    assert torch.equal(outs[0][1], _hilo(outs[0][0].float()))
