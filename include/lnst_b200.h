@@ -317,6 +317,11 @@ int lnst_raymarch_bwd_tma(const float* vol, const float* rot, int32_t n_views, i
  * meaning as the bf16 entry points above; `C`, `Cin`, `Cout` are LOGICAL channel counts. */
 int lnst_conv3x3_bf16x3_tc(const void* x, const void* w_packed2, const float* bias, const void* mask, void* y,
                            int32_t n, int32_t H, int32_t W, int32_t Cin, int32_t Cout, int32_t relu, void* stream);
+/* The same convolution with the 2x2 average pool that follows it in the network (vgg.py:96,102 `pool1`, `pool2`) written by
+ * the same epilogue: y_pool bf16 [n,H/2,W/2,2*Cout], bit-identical to lnst_avgpool2_bf16x3_fwd(y). */
+int lnst_conv3x3_pool_bf16x3_tc(const void* x, const void* w_packed2, const float* bias, const void* mask, void* y,
+                                void* y_pool, int32_t n, int32_t H, int32_t W, int32_t Cin, int32_t Cout, int32_t relu,
+                                void* stream);
 /* G2: fp32 scratch [n,2C,2C]; G fp32 [n,C,C] = F^T F/denom - Gs; Gd2 bf16 [n,C,2C] = split copy of G (may be NULL). */
 int lnst_gram_diff_bf16x3_tc(const void* F, int32_t n, int64_t P, int32_t C, float denom, const float* Gs, float weight,
                              float* G2, float* G, void* Gd2, float* loss, void* stream);

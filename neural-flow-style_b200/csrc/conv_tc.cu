@@ -660,11 +660,12 @@ template <int BLOCK_N> struct HaloAcc { static constexpr int value = (BLOCK_N >=
 // store staging: 128-byte row chunks (8 x 16 B) for the wide tiles, 64-byte ones where shared memory is tight
 template <int BLOCK_N> struct HaloStage { static constexpr int nv = 4; static constexpr int bytes = (BLOCK_N >= 128) ? 4 * nv * 512 : 0; };
 
-template <int BLOCK_N, bool OUT3, bool RES>
+template <int BLOCK_N, bool OUT3, bool RES, bool POOL = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv3x3_halo_k(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                const float* __restrict__ bias, const __nv_bfloat16* __restrict__ mask,
-               __nv_bfloat16* __restrict__ y, float* __restrict__ y3, ConvShape s, HaloCfg cfg) {
+               __nv_bfloat16* __restrict__ y, float* __restrict__ y3, ConvShape s, HaloCfg cfg,
+               __nv_bfloat16* __restrict__ ypool) {
   constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
   // accumulator ring in TMEM: the round trip MMA-complete -> tfull -> epilogue -> tempty -> next MMA costs about
   // 4000 cycles (measured: with two buffers every tile took >= 2000 cycles even with 1/9 of the MMAs and no
@@ -890,6 +891,49 @@ conv3x3_halo_k(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                 if (!((mbits[c] >> (j * 8 + e + 1)) & 1u)) f1 = 0.f;
                 if (s.split) split2(f0, f1, oh[e >> 1], ohl[e >> 1]);
                 else oh[e >> 1] = __floats2bfloat162_rn(f0, f1);
+              }
+            }
+            if (POOL && NV == 4) {
+              // fused 2x2 average pool of the split output (avgpool2_split_fwd_k): a warp is 4 tile rows x 8 columns, so
+              // a quad is lanes {l, l^1, l^8, l^9}.  Reduce-scatter over the quad: after the x step a lane keeps 16 of
+              // the chunk's 32 channels, after the y step 8, fully summed -- 24 shuffles per chunk instead of 64 -- and
+              // writes them.  Values are the ROUNDED ones (hi + lo), summed (a + b) + (c + d) like the stand-alone kernel.
+              float fr[32];
+#pragma unroll
+              for (int jj = 0; jj < NV; ++jj) {
+                const __nv_bfloat162* oh = reinterpret_cast<const __nv_bfloat162*>(&ov[jj]);
+                const __nv_bfloat162* ohl = reinterpret_cast<const __nv_bfloat162*>(&ol[jj]);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 h = __bfloat1622float2(oh[e]), l = __bfloat1622float2(ohl[e]);
+                  fr[jj * 8 + 2 * e] = h.x + l.x;
+                  fr[jj * 8 + 2 * e + 1] = h.y + l.y;
+                }
+              }
+              const bool dx = (lane & 1) != 0, dy = (lane & 8) != 0;
+              float k1[16], k2[8];
+#pragma unroll
+              for (int e = 0; e < 16; ++e) {
+                const float recv = __shfl_xor_sync(0xffffffffu, dx ? fr[e] : fr[16 + e], 1);
+                k1[e] = (dx ? fr[16 + e] : fr[e]) + recv;
+              }
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const float recv = __shfl_xor_sync(0xffffffffu, dy ? k1[e] : k1[8 + e], 8);
+                k2[e] = ((dy ? k1[8 + e] : k1[e]) + recv) * 0.25f;
+              }
+              const int OHp = s.H >> 1, OWp = s.W >> 1;
+              const int py = ph_ >> 1, px = pw_ >> 1;
+              if (py < OHp && px < OWp) {
+                uint4 ph4, pl4;
+                __nv_bfloat162* a = reinterpret_cast<__nv_bfloat162*>(&ph4);
+                __nv_bfloat162* b = reinterpret_cast<__nv_bfloat162*>(&pl4);
+#pragma unroll
+                for (int e = 0; e < 8; e += 2) split2(k2[e], k2[e + 1], a[e >> 1], b[e >> 1]);
+                __nv_bfloat16* dstp = ypool + (((int64_t)img * OHp + py) * OWp + px) * s.ldy + n0 + ck * 32 +
+                                      (dx ? 16 : 0) + (dy ? 8 : 0);
+                *reinterpret_cast<uint4*>(dstp) = ph4;
+                *reinterpret_cast<uint4*>(dstp + s.Cout) = pl4;
               }
             }
             if (BLOCK_N < 128) {                                     // narrow tiles: the direct stores keep up with the MMAs
@@ -1421,7 +1465,7 @@ static int conv_halo = 2;         // tuning switch: 0 = per-tap kernel, 1 = halo
 template <int BLOCK_N, bool OUT3>
 static int launch_halo(const void* x, const void* wmat, const float* bias, const __nv_bfloat16* mask,
                        __nv_bfloat16* y, float* y3, int n, int H, int W, int Cin, int Cout, int relu, float scale,
-                       cudaStream_t stream, int out_ch = 3, int split = 0) {
+                       cudaStream_t stream, int out_ch = 3, int split = 0, __nv_bfloat16* ypool = nullptr) {
   constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
   constexpr int MAX_SMEM = 232448;                        // 227 KiB opt-in limit per CTA
   const int budget = MAX_SMEM - 2048 - 1024 - 512 - HaloStage<BLOCK_N>::bytes - 128;   // static bias table, alignment slack, barriers, store staging
@@ -1477,10 +1521,32 @@ static int launch_halo(const void* x, const void* wmat, const float* bias, const
     configured = true;
   }
   const int grid = cfg.n_tiles < sms ? cfg.n_tiles : sms;
+  if (ypool != nullptr) {
+    // the pooled output is a separate instantiation: with the pool code behind a run-time test every halo kernel
+    // grew by 14-35 registers and ran 12-19 % slower (ncu launch lists, profiles/)
+    if (OUT3 || !split) return LNST_EARG;
+  }
+  if constexpr (!OUT3) if (ypool != nullptr) {
+    static bool pconfigured = false;
+    if (!pconfigured) {
+      cudaError_t e = cudaFuncSetAttribute(conv3x3_halo_k<BLOCK_N, false, true, true>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM - 2048);
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(conv3x3_halo_k<BLOCK_N, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 MAX_SMEM - 2048);
+      if (e != cudaSuccess) return (int)e;
+      pconfigured = true;
+    }
+    if (cfg.sb == 0)
+      conv3x3_halo_k<BLOCK_N, false, true, true><<<grid, NUM_THREADS, smem, stream>>>(mx, mw, bias, mask, y, y3, s, cfg, ypool);
+    else
+      conv3x3_halo_k<BLOCK_N, false, false, true><<<grid, NUM_THREADS, smem, stream>>>(mx, mw, bias, mask, y, y3, s, cfg, ypool);
+    return (int)cudaGetLastError();
+  }
   if (cfg.sb == 0)
-    conv3x3_halo_k<BLOCK_N, OUT3, true><<<grid, NUM_THREADS, smem, stream>>>(mx, mw, bias, mask, y, y3, s, cfg);
+    conv3x3_halo_k<BLOCK_N, OUT3, true><<<grid, NUM_THREADS, smem, stream>>>(mx, mw, bias, mask, y, y3, s, cfg, ypool);
   else
-    conv3x3_halo_k<BLOCK_N, OUT3, false><<<grid, NUM_THREADS, smem, stream>>>(mx, mw, bias, mask, y, y3, s, cfg);
+    conv3x3_halo_k<BLOCK_N, OUT3, false><<<grid, NUM_THREADS, smem, stream>>>(mx, mw, bias, mask, y, y3, s, cfg, ypool);
   return (int)cudaGetLastError();
 }
 
@@ -1567,7 +1633,7 @@ __global__ void avgpool2_split_fwd_k(const __nv_bfloat16* __restrict__ x, __nv_b
   float f0[8], f1[8], f2[8], f3[8], o[8];
   load8_split(b, C, f0); load8_split(b + R, C, f1); load8_split(b + (int64_t)W * R, C, f2); load8_split(b + (int64_t)W * R + R, C, f3);
 #pragma unroll
-  for (int e = 0; e < 8; ++e) o[e] = (f0[e] + f1[e] + f2[e] + f3[e]) * 0.25f;
+  for (int e = 0; e < 8; ++e) o[e] = ((f0[e] + f1[e]) + (f2[e] + f3[e])) * 0.25f;   // the order of the fused epilogue (conv3x3_halo_k)
   store8_split(y + (((int64_t)img * OH + oy) * OW + ox) * R + c, C, o);
 }
 __global__ void avgpool2_split_bwd_k(const __nv_bfloat16* __restrict__ gy, const __nv_bfloat16* __restrict__ mask,
@@ -2160,7 +2226,7 @@ extern "C" int lnst_tc_supported(void) { return tc::encode_fn() != nullptr ? 1 :
 // (taps = 1, one B matrix per image)
 static int run_tc_gemm(const void* x, const void* wmat, const float* bias, const void* mask, const void* addend,
                        void* y, int n, int H, int W, int Cin, int Cout, int relu, int taps, int w_img, float scale,
-                       void* stream, int split = 0) {
+                       void* stream, int split = 0, void* ypool = nullptr) {
   using namespace tc;
   if (!x || !wmat || !y || n < 1 || H < 1 || W < 1 || Cin < 64 || Cout < 64 || Cin % 64 || Cout % 64)
     return LNST_EARG;
@@ -2173,12 +2239,14 @@ static int run_tc_gemm(const void* x, const void* wmat, const float* bias, const
   const int wch = (split ? 2 : 1) * (Cin / 64);
   const bool resident = (Cout == bn_) && (9 * wch * bn_ * 128 + 3 * PATCH_STRIDE <= 232448 - 2048 - 1024 - 512 - (bn_ >= 128 ? 8192 : 0) - 128);
   if (taps == 9 && !w_img && !addend && (split || (conv_halo && (resident || conv_halo == 2)))) {
+    if (ypool && !split) return LNST_EARG;
     if (Cout % 128 == 0)
       return launch_halo<128, false>(x, wmat, bias, (const __nv_bfloat16*)mask, (__nv_bfloat16*)y, nullptr, n, H, W,
-                                     Cin, Cout, relu, scale, lnst_stream(stream), 3, split);
+                                     Cin, Cout, relu, scale, lnst_stream(stream), 3, split, (__nv_bfloat16*)ypool);
     return launch_halo<64, false>(x, wmat, bias, (const __nv_bfloat16*)mask, (__nv_bfloat16*)y, nullptr, n, H, W, Cin,
-                                  Cout, relu, scale, lnst_stream(stream), 3, split);
+                                  Cout, relu, scale, lnst_stream(stream), 3, split, (__nv_bfloat16*)ypool);
   }
+  if (ypool) return LNST_EARG;
   if (split && (!conv_persistent || taps != 1)) return LNST_EARG;    // split operands: halo kernel, or the persistent per-pixel GEMM
   ConvShape s;
   s.H = H; s.W = W; s.Cin = Cin; s.Cout = Cout; s.relu = relu;
@@ -2221,6 +2289,14 @@ extern "C" int lnst_conv3x3_bf16x3_tc(const void* x, const void* w_packed, const
                                       void* y, int32_t n, int32_t H, int32_t W, int32_t Cin, int32_t Cout,
                                       int32_t relu, void* stream) {
   return run_tc_gemm(x, w_packed, bias, mask, nullptr, y, n, H, W, Cin, Cout, relu, 9, 0, 1.0f, stream, 1);
+}
+// The same convolution, with the 2x2 average pool of its output (lnst_avgpool2_bf16x3_fwd) written by the same epilogue:
+// y_pool bf16 [n, H/2, W/2, 2*Cout].  Bit-identical to the two separate calls.
+extern "C" int lnst_conv3x3_pool_bf16x3_tc(const void* x, const void* w_packed, const float* bias, const void* mask,
+                                           void* y, void* y_pool, int32_t n, int32_t H, int32_t W, int32_t Cin,
+                                           int32_t Cout, int32_t relu, void* stream) {
+  if (!y_pool || H < 2 || W < 2) return LNST_EARG;
+  return run_tc_gemm(x, w_packed, bias, mask, nullptr, y, n, H, W, Cin, Cout, relu, 9, 0, 1.0f, stream, 1, y_pool);
 }
 // F split [n,H,W,2C], Gd2 bf16 [n,C,2C] = [hi | lo] of the (symmetric) Gram difference, addend / g split rows
 extern "C" int lnst_gram_bwd_bf16x3_tc(const void* F, const void* Gd2, float coef, const void* addend,

@@ -738,6 +738,17 @@ def conv3x3_bf16x3_tc(x, w_packed2, bias, relu, mask=None):
     return y
 
 
+def conv3x3_pool_bf16x3_tc(x, w_packed2, bias, relu, mask=None):
+    """conv3x3_bf16x3_tc plus the 2x2 average pool of its output from the same epilogue -> (y, y_pool [n,H/2,W/2,2*Cout])"""
+    n, H, W, c2 = x.shape
+    cout = w_packed2.shape[1]
+    y = torch.empty(n, H, W, 2 * cout, dtype=bf16, device=x.device)
+    yp = torch.empty(n, H // 2, W // 2, 2 * cout, dtype=bf16, device=x.device)
+    _lib.get().call('lnst_conv3x3_pool_bf16x3_tc', ptr(x), ptr(w_packed2), ptr(bias), ptr(mask), ptr(y), ptr(yp), n, H, W,
+                    c2 // 2, cout, int(relu), _s(x))
+    return y, yp
+
+
 def gram_diff_bf16x3_tc(F, denom, Gs, weight, loss):
     """F split bf16 [n,h,w,2C] -> (G fp32 [n,C,C] = F^T F/denom - Gs, Gd2 bf16 [n,C,2C] split); loss[n] += weight*sum(G^2)"""
     n, h, w, c2 = F.shape

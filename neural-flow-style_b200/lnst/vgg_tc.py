@@ -34,6 +34,8 @@ def _pack2(w):
 
 
 class TensorCoreConvs:
+    fuse_pool = True                                     # conv + 2x2 average pool from one epilogue (split mode)
+
     def __init__(self, net, split=False):
         # the network owns this object: a weak back-reference keeps the pair out of a reference cycle, so the
         # packed weights (~0.3 GB for VGG-19) are released with the network instead of waiting for the cycle collector
@@ -75,11 +77,16 @@ class TensorCoreConvs:
         acts = {}
         cur = x
         sp = self.split
-        for name in layers:
+        pooled = None                                   # output of a pool layer already written by the convolution before it
+        for i, name in enumerate(layers):
             if name.startswith('conv'):
                 if name in self.wp and cur.dtype == torch.bfloat16:
-                    cur = (ops.conv3x3_bf16x3_tc if sp else ops.conv3x3_bf16_tc)(cur, self.wp[name], self.net.b[name],
-                                                                               relu=True)
+                    nxt = layers[i + 1] if i + 1 < len(layers) else ''
+                    if sp and self.fuse_pool and nxt.startswith('pool') and cur.shape[1] >= 2 and cur.shape[2] >= 2:
+                        cur, pooled = ops.conv3x3_pool_bf16x3_tc(cur, self.wp[name], self.net.b[name], relu=True)
+                    else:
+                        cur = (ops.conv3x3_bf16x3_tc if sp else ops.conv3x3_bf16_tc)(cur, self.wp[name], self.net.b[name],
+                                                                                   relu=True)
                 elif gray is not None and name == layers[0] and tuple(self.net.w[name].shape[2:]) == (3, 64):
                     cur = (ops.conv_first_fwd_gray_x3 if sp else ops.conv_first_fwd_gray)(gray, *self.gray_w)
                 elif cur.dtype == torch.float32 and tuple(self.net.w[name].shape[2:]) == (3, 64):
@@ -88,6 +95,8 @@ class TensorCoreConvs:
                     raise NotImplementedError("conv_math='bf16x3' needs channel counts that are multiples of 64")
                 else:
                     cur = ops.conv3x3_mixed(cur, self.net.w[name], self.net.b[name], relu=True, out_bf16=True)
+            elif pooled is not None:
+                cur, pooled = pooled, None
             else:
                 cur = (ops.avgpool2_bf16x3_fwd if sp else ops.avgpool2_bf16_fwd)(cur)
             acts[name] = cur

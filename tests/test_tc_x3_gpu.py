@@ -217,3 +217,18 @@ def test_gram_x3_tmem_summed_products_match_the_split_row_gram(n, h, w, ch):
     assert (outs[0][0] - outs[0][0].transpose(1, 2)).abs().max() <= 2e-6 * scale   # symmetric up to the fp32 summation order
     np.testing.assert_allclose(outs[0][2].numpy(), outs[1][2].numpy(), rtol=1e-4)
     assert torch.equal(outs[0][1], _hilo(outs[0][0].float()))
+
+
+@pytest.mark.parametrize('n,H,W,cin,cout', [(2, 20, 24, 64, 64), (1, 33, 47, 64, 64), (3, 50, 50, 128, 128), (1, 17, 9, 64, 128),
+                                            (9, 200, 200, 64, 64)])
+def test_conv_with_fused_pool_is_bit_identical_to_conv_then_pool(n, H, W, cin, cout):
+    dev = torch.device('cuda:0')
+    g = torch.Generator().manual_seed(H * 3 + cout)
+    x = ops.to_split(torch.randn(n, H, W, cin, generator=g).to(dev))
+    w = _pack2(torch.randn(3, 3, cin, cout, generator=g) * 0.05).to(dev)
+    b = torch.randn(cout, generator=g).to(dev)
+    y0 = ops.conv3x3_bf16x3_tc(x, w, b, relu=True)
+    p0 = ops.avgpool2_bf16x3_fwd(y0)
+    y1, p1 = ops.conv3x3_pool_bf16x3_tc(x, w, b, relu=True)
+    assert torch.equal(y0, y1)
+    assert p1.shape == p0.shape and torch.equal(p0, p1)
