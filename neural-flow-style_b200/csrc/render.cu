@@ -9,7 +9,12 @@
 #include "render_common.cuh"
 
 #define RM_UNROLL 4
-#define RMB_UNROLL 2   // backward: two samples in flight keep the kernel at 64 registers (4 needed 96: 20 % occupancy)
+#ifndef RMB_UNROLL
+#define RMB_UNROLL 1   // backward: samples in flight per thread; 1 + __launch_bounds__(128, 8) = 64 registers, 8 CTAs per SM (2 needed 80: 6 CTAs)
+#endif
+#ifndef RMB_MINB
+#define RMB_MINB 8
+#endif
 
 struct VolDims {
   int D, H, W;
@@ -324,7 +329,7 @@ __global__ void __launch_bounds__(128) raymarch_rot_fwd_k(const float* __restric
 // together: 89 % of the lane-slots are live at C3 against 75 % for rows (tools/dev/iv_probe.py).  It also lets the y1 row
 // of a sample merge into the lane one row down (+8), like the x1 column merges into lane + 1.
 template <bool MERGE, bool PATCH>
-__global__ void __launch_bounds__(128) raymarch_rot_bwd_k(const float* __restrict__ vol, const float* __restrict__ rot,
+__global__ void __launch_bounds__(128, RMB_MINB) raymarch_rot_bwd_k(const float* __restrict__ vol, const float* __restrict__ rot,
                                                            RayGeo g, BoxF bf, const int2* __restrict__ iv,
                                                            float tau, float ntl2, int liquid,
                                                            const float* __restrict__ stot,

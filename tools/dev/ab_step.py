@@ -30,15 +30,36 @@ def main():
             lib.call('lnst_set_gram_split3', int(on))
         elif a.switch == 'first_col':
             lib.call('lnst_set_conv_first_col', int(on))
+        elif a.switch.startswith('lib:'):                   # default library (1) against a variant build (0)
+            _lib.set_for_testing(None if on else _lib.Lib(os.path.join(ROOT, a.switch[4:]), 'cuda'))
+            ctx.lib = _lib.get()
         elif a.switch == 'merge':
             lib.call('lnst_set_raymarch_merge', 2 if on else 1)
         else:
             raise SystemExit('unknown switch')
+    import threading
+    import time
+    import pynvml
+    pynvml.nvmlInit()
+    h = pynvml.nvmlDeviceGetHandleByIndex(0)
     for rnd in range(a.rounds):
         for on in (1, 0):
             set_switch(on)
+            samples, stop = [], threading.Event()
+
+            def sample():
+                while not stop.is_set():
+                    samples.append((pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM), pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0))
+                    time.sleep(0.004)
+            th = threading.Thread(target=sample, daemon=True)
+            th.start()
             m = bench.measure_step(ctx, 'C3', 'allreduce', 'bf16x3', a.steps, 5, full=False)
-            print('round %d  %s=%d  %.4f ms/step  (%.1f it/s)' % (rnd, a.switch, on, m['ms_step'], m['value']), flush=True)
+            stop.set()
+            th.join()
+            tail = samples[-max(1, int(a.steps * m['ms_step'] / 4.5)):]          # the samples of the timed region
+            clk = sorted(c for c, _ in tail)[len(tail) // 2]
+            pw = max(p for _, p in tail)
+            print('round %d  %s=%d  %.4f ms/step  (%.1f it/s)  sm %d MHz  power max %.0f W' % (rnd, a.switch, on, m['ms_step'], m['value'], clk, pw), flush=True)
             torch.cuda.empty_cache()
     set_switch(1)
 
