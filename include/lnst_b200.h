@@ -141,6 +141,18 @@ int lnst_raymarch_fwd_box(const float* vol, const float* rot, int32_t n_views, i
 int lnst_raymarch_bwd_box(const float* vol, const float* rot, int32_t n_views, int32_t D, int32_t H,
                           int32_t W, float tau, int32_t liquid, const LnstBox* box, const int32_t* intervals,
                           const float* stot, const float* g_img, float* g_vol, void* stream);
+/* Fused image glue for the smoke render (styler_3p.py:158 `d /= tf.reduce_max(d)`): the forward march also reduces
+ * stats[2*v] = max of view v (stats zero on entry; lnst_image_max's first pass), and the backward march takes the cotangent
+ * of the NORMALISED image and applies lnst_normalize_bwd's second pass while loading it (img = the un-normalised render,
+ * stats = {max, ties} per view, dots[v] = sum_p g_gray[v,p] * img[v,p]).  With stats == NULL they are the calls above.
+ * Rotated march only (view matrices given, every extent >= 2); same results as the separate calls. */
+int lnst_raymarch_fwd_max_box(const float* vol, const float* rot, int32_t n_views, int32_t D, int32_t H, int32_t W,
+                              float tau, int32_t liquid, const LnstBox* box, const int32_t* intervals, float* img,
+                              float* stot, float* stats, void* stream);
+int lnst_raymarch_bwd_norm_box(const float* vol, const float* rot, int32_t n_views, int32_t D, int32_t H, int32_t W,
+                               float tau, int32_t liquid, const LnstBox* box, const int32_t* intervals, const float* stot,
+                               const float* g_gray, const float* img, const float* stats, const float* dots, float* g_vol,
+                               void* stream);
 /* Ray intervals for a set of views: the slab test against `box`, then shrunk from both ends while the ray
  * runs through empty occupancy bricks.  `bricks` (may be NULL): one byte per 4x4x4-voxel brick,
  * [ceil(D/4), ceil(H/4), ceil(W/4)], non-zero where the brick or anything within two voxels plus one brick
@@ -162,6 +174,9 @@ int lnst_image_max(const float* img, int32_t n_img, int64_t n_pix, float* stats,
 /* gray[v,p] = img[v,p] / max_v  (smoke normalisation, :158). */
 int lnst_normalize_fwd(const float* img, const float* stats, int32_t n_img, int64_t n_pix, float* gray,
                        void* stream);
+/* lnst_normalize_fwd plus the ties count of lnst_image_max in one pass: stats[2*v] = max must be final
+ * (lnst_raymarch_fwd_max_*), stats[2*v+1] zero on entry. */
+int lnst_normalize_ties_fwd(const float* img, float* stats, int32_t n_img, int64_t n_pix, float* gray, void* stream);
 /* g_img from g_gray incl. the reduce_max gradient (split evenly among ties); `dots`
  * [n_img] is workspace. */
 int lnst_normalize_bwd(const float* img, const float* stats, const float* g_gray, int32_t n_img,
@@ -238,6 +253,10 @@ int lnst_set_conv_halo(int32_t on);
  * runs as one GEMM per halo'd patch with the 9 taps as the N dimension plus a 9-term gather; 0 = the halo kernel with
  * one MMA chain per tap. */
 int lnst_set_conv_first_col(int32_t on);
+/* lnst_conv_first_bwd_gray[_x3]_tc plus dots[i] += sum_p g_gray[i,p] * img[i,p] out of the same kernel (the reduction
+ * lnst_normalize_bwd starts with); dots [n] zero on entry, img fp32 [n,H,W] the un-normalised render. */
+int lnst_conv_first_bwd_gray_dot_tc(const void* g, const void* wd16, float* g_gray, const float* img, float* dots,
+                                    int32_t split, int32_t n, int32_t H, int32_t W, void* stream);
 /* Tuning switch (tests / microbenchmarks): 1 (default) = lnst_gram_diff_bf16x3_tc sums hi^T hi + hi^T lo + lo^T hi in one
  * TMEM tile per 128 x 128 block (C % 128 == 0); 0 = the 2C x 2C Gram of the split rows plus a finishing pass. */
 int lnst_set_gram_split3(int32_t on);
@@ -292,6 +311,10 @@ int lnst_splat_wavg_fwd_gather(const int32_t* cstart, const int32_t* order, cons
 int lnst_raymarch_fwd_tma(const float* vol, const float* rot, int32_t n_views, int32_t D, int32_t H, int32_t W, float tau,
                           int32_t liquid, const LnstBox* box, const int32_t* intervals, float* img, float* stot,
                           void* stream);
+/* lnst_raymarch_fwd_max_box on the TMA-staged kernel */
+int lnst_raymarch_fwd_max_tma(const float* vol, const float* rot, int32_t n_views, int32_t D, int32_t H, int32_t W,
+                              float tau, int32_t liquid, const LnstBox* box, const int32_t* intervals, float* img,
+                              float* stot, float* stats, void* stream);
 
 /* lnst_advect for a 3-D scalar field (dim = 3, C = 1): d [D,H,W], vel [D,H,W,3], out [D,H,W].  The source box of each
  * 8 x 8 x 32 output tile, grown by `reach` cells (1..4: the caller's bound on the back-trace length), is one TMA box;

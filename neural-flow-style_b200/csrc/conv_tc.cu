@@ -1983,8 +1983,10 @@ template <bool SPLIT>
 __global__ void __launch_bounds__(128) conv_first_bwd_gray_col_k(const __grid_constant__ CUtensorMap map_g,
                                                                   const __nv_bfloat16* __restrict__ wd16,
                                                                   float* __restrict__ g_gray, int H, int W, int tiles_w,
-                                                                  int tiles_h, float scale) {
+                                                                  int tiles_h, float scale, const float* __restrict__ dimg,
+                                                                  float* __restrict__ dots) {
   constexpr int NCH = SPLIT ? 2 : 1;                         // activation / weight chunks: [hi | lo]
+  __shared__ float s_part[4];
   constexpr int XC = 64 * NCH;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -2082,7 +2084,15 @@ __global__ void __launch_bounds__(128) conv_first_bwd_gray_col_k(const __grid_co
     for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
       for (int kx = 0; kx < 3; ++kx) acc += Z[((py + ky) * (HTW + 2) + px + kx) * 9 + ky * 3 + kx];
-    if (hh < H && ww < W) g_gray[((int64_t)img * H + hh) * W + ww] = acc * scale;
+    const bool ok = hh < H && ww < W;
+    const int64_t pix = ((int64_t)img * H + hh) * W + ww;
+    if (ok) g_gray[pix] = acc * scale;
+    if (dots != nullptr) {                                   // dots[img] += sum g_gray * image (lnst_normalize_bwd's first pass)
+      const float pr = lnst_warp_sum(ok ? acc * scale * dimg[pix] : 0.f);
+      if (lane == 0) s_part[warp] = pr;
+      __syncthreads();
+      if (threadIdx.x == 0) atomicAdd(dots + img, (s_part[0] + s_part[1]) + (s_part[2] + s_part[3]));
+    }
   }
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -2093,7 +2103,7 @@ __global__ void __launch_bounds__(128) conv_first_bwd_gray_col_k(const __grid_co
 static int conv_first_col = 1;    // tuning switch: 1 = the one-GEMM-per-patch kernel above for the gray data gradient, 0 = halo kernel
 
 static int launch_first_bwd_col(const void* g, const void* wd16, float* g_gray, int n, int H, int W, int split,
-                                cudaStream_t stream) {
+                                cudaStream_t stream, const float* dimg = nullptr, float* dots = nullptr) {
   const int nch = split ? 2 : 1, xC = 64 * nch;
   CUtensorMap mg;
   const cuuint64_t dims[4] = {(cuuint64_t)xC, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n};
@@ -2113,10 +2123,10 @@ static int launch_first_bwd_col(const void* g, const void* wd16, float* g_gray, 
   const unsigned grid = (unsigned)(tiles_w * tiles_h * n);
   if (split)
     conv_first_bwd_gray_col_k<true><<<grid, 128, smem, stream>>>(mg, (const __nv_bfloat16*)wd16, g_gray, H, W, tiles_w,
-                                                                 tiles_h, 1.0f);
+                                                                 tiles_h, 1.0f, dimg, dots);
   else
     conv_first_bwd_gray_col_k<false><<<grid, 128, smem, stream>>>(mg, (const __nv_bfloat16*)wd16, g_gray, H, W, tiles_w,
-                                                                  tiles_h, 1.0f);
+                                                                  tiles_h, 1.0f, dimg, dots);
   return (int)cudaGetLastError();
 }
 
@@ -2217,6 +2227,13 @@ extern "C" int lnst_conv_first_bwd_gray_x3_tc(const void* g, const void* wd16, f
                                    lnst_stream(stream), 1, 1);
 }
 extern "C" int lnst_set_conv_first_col(int32_t on) { tc::conv_first_col = on ? 1 : 0; return LNST_OK; }
+// The gray data gradient of conv1_1 plus dots[i] += sum_p g_gray[i,p] * img[i,p] from the same kernel (the reduction
+// lnst_normalize_bwd starts with; dots zero on entry).  split: g and wd16 carry [hi | lo] halves (bf16x3).
+extern "C" int lnst_conv_first_bwd_gray_dot_tc(const void* g, const void* wd16, float* g_gray, const float* img, float* dots,
+                                               int32_t split, int32_t n, int32_t H, int32_t W, void* stream) {
+  if (!g || !wd16 || !g_gray || !img || !dots || n < 1 || H < 1 || W < 1) return LNST_EARG;
+  return tc::launch_first_bwd_col(g, wd16, g_gray, n, H, W, split ? 1 : 0, lnst_stream(stream), img, dots);
+}
 
 extern "C" int lnst_set_conv_persistent(int32_t on) { tc::conv_persistent = on ? 1 : 0; return LNST_OK; }
 

@@ -265,9 +265,11 @@ __global__ void __launch_bounds__(128) ray_intervals_exact_k(const float* __rest
 __global__ void __launch_bounds__(128) raymarch_rot_fwd_k(const float* __restrict__ vol, const float* __restrict__ rot,
                                                            RayGeo g, BoxF bf, const int2* __restrict__ iv,
                                                            float ntl2, int liquid, float* __restrict__ img,
-                                                           float* __restrict__ stot) {
-  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
-  if (pix >= g.HW) return;
+                                                           float* __restrict__ stot, float* __restrict__ stats) {
+  const int pix0 = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool act = pix0 < g.HW;
+  if (!act && stats == nullptr) return;
+  const int pix = act ? pix0 : g.HW - 1;               // threads past the image only take part in the maximum
   const int view = blockIdx.y;
   const int h = pix / g.W, w = pix - h * g.W;
   const RayLine l = ray_line(rot + 9 * view, lin_coord(h, g.sH), lin_coord(w, g.sW), g);
@@ -279,6 +281,7 @@ __global__ void __launch_bounds__(128) raymarch_rot_fwd_k(const float* __restric
   } else {
     ray_interval(l, g, bf, i_lo, i0);                  // the density is zero outside [i_lo, i0]
   }
+  if (!act) { i_lo = 1; i0 = 0; }
   // marching towards the eye (descending i): sample i's near plane is sample i-1's far plane when the
   // anchor steps back by exactly one voxel in depth
   Plane4 near_prev;
@@ -319,8 +322,14 @@ __global__ void __launch_bounds__(128) raymarch_rot_fwd_k(const float* __restric
     idx_prev = c.idx;
   }
   if (liquid) I = 1.f - fast_exp2(S * ntl2);            // styler_3p.py:150-152
-  img[(int64_t)view * g.HW + pix] = I;
-  stot[(int64_t)view * g.HW + pix] = S;
+  if (act) {
+    img[(int64_t)view * g.HW + pix] = I;
+    stot[(int64_t)view * g.HW + pix] = S;
+  }
+  if (stats != nullptr) {                               // the view's maximum (image_max_k), one atomic per warp
+    const float m = lnst_warp_max(act ? I : 0.f);
+    if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(stats + 2 * view), __float_as_int(m));
+  }
 }
 
 // d I / d d_k = T_k - tau * sum_{i<=k} d_i T_i  (smoke);  tau * exp(-tau * S_total) (liquid)
@@ -334,7 +343,9 @@ __global__ void __launch_bounds__(128, RMB_MINB) raymarch_rot_bwd_k(const float*
                                                            float tau, float ntl2, int liquid,
                                                            const float* __restrict__ stot,
                                                            const float* __restrict__ g_img, float* __restrict__ g_vol,
-                                                           int tiles_w) {
+                                                           int tiles_w, const float* __restrict__ nimg,
+                                                           const float* __restrict__ nstats,
+                                                           const float* __restrict__ ndots) {
   const int view = blockIdx.y;
   const int lane = threadIdx.x & 31;
   int pix;
@@ -351,6 +362,12 @@ __global__ void __launch_bounds__(128, RMB_MINB) raymarch_rot_bwd_k(const float*
   float gI = 0.f, St = 0.f;
   if (active) {
     gI = g_img[(int64_t)view * g.HW + pix];
+    if (nstats != nullptr) {                             // g_img is d loss / d (img / max): normalize_bwd_k, inline
+      const float m = nstats[2 * view], ties = nstats[2 * view + 1];
+      const float x = nimg[(int64_t)view * g.HW + pix];
+      gI = gI / m;
+      if (x == m) gI -= ndots[view] / (m * m) / ties;
+    }
     St = stot[(int64_t)view * g.HW + pix];
     active = gI != 0.f;
   }
@@ -532,6 +549,21 @@ __global__ void normalize_fwd_k(const float* __restrict__ img, const float* __re
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_pix) return;
   gray[view * n_pix + i] = img[view * n_pix + i] / stats[2 * view];
+}
+// normalize_fwd_k + image_ties_k in one pass over the image (stats[2v] = max already final, stats[2v+1] zero on entry)
+__global__ void normalize_ties_fwd_k(const float* __restrict__ img, float* __restrict__ stats, int64_t n_pix,
+                                     float* __restrict__ gray) {
+  const int view = blockIdx.y;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const float m = stats[2 * view];
+  float c = 0.f;
+  if (i < n_pix) {
+    const float x = img[view * n_pix + i];
+    gray[view * n_pix + i] = x / m;
+    c = (x == m) ? 1.f : 0.f;
+  }
+  c = lnst_warp_sum(c);
+  if ((threadIdx.x & 31) == 0 && c != 0.f) atomicAdd(stats + 2 * view + 1, c);
 }
 __global__ void dot_k(const float* __restrict__ a, const float* __restrict__ b, int64_t n_pix,
                       float* __restrict__ dots) {
@@ -757,15 +789,24 @@ extern "C" int lnst_ray_intervals_exact(const float* rot, int32_t n_views, int32
 extern "C" int lnst_raymarch_fwd_box(const float* vol, const float* rot, int32_t n_views, int32_t D, int32_t H,
                                      int32_t W, float tau, int32_t liquid, const LnstBox* box,
                                      const int32_t* intervals, float* img, float* stot, void* stream) {
+  return lnst_raymarch_fwd_max_box(vol, rot, n_views, D, H, W, tau, liquid, box, intervals, img, stot, nullptr, stream);
+}
+
+// The same march; stats[2 v] = max over view v's pixels is reduced by the kernel itself (stats zero on entry, may be NULL).
+// Needs the rotated-march kernel: view matrices given, every extent >= 2.
+extern "C" int lnst_raymarch_fwd_max_box(const float* vol, const float* rot, int32_t n_views, int32_t D, int32_t H,
+                                         int32_t W, float tau, int32_t liquid, const LnstBox* box,
+                                         const int32_t* intervals, float* img, float* stot, float* stats, void* stream) {
   if (!vol || !img || !stot || n_views < 1 || D < 1 || H < 1 || W < 1 || !box_ok(box, D, H, W)) return LNST_EARG;
   if (!rot && n_views != 1) return LNST_EARG;
   if (rot && D >= 2 && H >= 2 && W >= 2 && (int64_t)D * H * W < 0x7fffffff) {
     const RayGeo g = make_geo(D, H, W);
     LNST_LAUNCH(raymarch_rot_fwd_k, dim3(lnst_blocks((int64_t)H * W, 128), n_views), dim3(128), 0,
                 lnst_stream(stream), vol, rot, g, make_boxf(box, D, H, W), reinterpret_cast<const int2*>(intervals),
-                -tau * 1.4426950408889634f, (int)liquid, img, stot);
+                -tau * 1.4426950408889634f, (int)liquid, img, stot, stats);
     return lnst_status();
   }
+  if (stats) return LNST_EARG;
   const VolDims v = make_dims(D, H, W);
   LNST_LAUNCH(raymarch_fwd_k, dim3(lnst_blocks((int64_t)H * W, 128), n_views), dim3(128), 0,
               lnst_stream(stream), vol, rot, v, make_subvol(box, D, H, W), tau, (int)liquid, img, stot);
@@ -782,8 +823,21 @@ extern "C" int lnst_raymarch_bwd_box(const float* vol, const float* rot, int32_t
                                      int32_t W, float tau, int32_t liquid, const LnstBox* box,
                                      const int32_t* intervals, const float* stot, const float* g_img,
                                      float* g_vol, void* stream) {
+  return lnst_raymarch_bwd_norm_box(vol, rot, n_views, D, H, W, tau, liquid, box, intervals, stot, g_img, nullptr, nullptr,
+                                    nullptr, g_vol, stream);
+}
+
+// The same backward march fed with the cotangent of the NORMALISED image gray = img / max(img): lnst_normalize_bwd's
+// second pass runs inside the kernel's prologue (img, stats = {max, ties} per view, dots[v] = sum g_gray * img).  With
+// stats == NULL this is lnst_raymarch_bwd_box.  Needs the rotated-march kernel.
+extern "C" int lnst_raymarch_bwd_norm_box(const float* vol, const float* rot, int32_t n_views, int32_t D, int32_t H,
+                                          int32_t W, float tau, int32_t liquid, const LnstBox* box,
+                                          const int32_t* intervals, const float* stot, const float* g_img,
+                                          const float* img, const float* stats, const float* dots, float* g_vol,
+                                          void* stream) {
   if (!vol || !stot || !g_img || !g_vol || n_views < 1 || D < 1 || H < 1 || W < 1 || !box_ok(box, D, H, W))
     return LNST_EARG;
+  if (stats && (!img || !dots)) return LNST_EARG;
   if (!rot && n_views != 1) return LNST_EARG;
   if (rot && D >= 2 && H >= 2 && W >= 2 && (int64_t)D * H * W < 0x7fffffff) {
     const RayGeo g = make_geo(D, H, W);
@@ -794,18 +848,19 @@ extern "C" int lnst_raymarch_bwd_box(const float* vol, const float* rot, int32_t
       const int tiles_w = (W + 31) / 32, tiles_h = (H + 3) / 4;
       auto k = raymarch_rot_bwd_k<true, true>;
       LNST_LAUNCH(k, dim3((unsigned)(tiles_w * tiles_h), n_views), dim3(128), 0, lnst_stream(stream), vol, rot, g, bf,
-                  br, tau, ntl2, (int)liquid, stot, g_img, g_vol, tiles_w);
+                  br, tau, ntl2, (int)liquid, stot, g_img, g_vol, tiles_w, img, stats, dots);
     } else if (lnst_raymarch_merge) {
       auto k = raymarch_rot_bwd_k<true, false>;
       LNST_LAUNCH(k, dim3(lnst_blocks((int64_t)H * W, 128), n_views), dim3(128), 0, lnst_stream(stream), vol, rot, g,
-                  bf, br, tau, ntl2, (int)liquid, stot, g_img, g_vol, 0);
+                  bf, br, tau, ntl2, (int)liquid, stot, g_img, g_vol, 0, img, stats, dots);
     } else {
       auto k = raymarch_rot_bwd_k<false, false>;
       LNST_LAUNCH(k, dim3(lnst_blocks((int64_t)H * W, 128), n_views), dim3(128), 0, lnst_stream(stream), vol, rot, g,
-                  bf, br, tau, ntl2, (int)liquid, stot, g_img, g_vol, 0);
+                  bf, br, tau, ntl2, (int)liquid, stot, g_img, g_vol, 0, img, stats, dots);
     }
     return lnst_status();
   }
+  if (stats) return LNST_EARG;
   const VolDims v = make_dims(D, H, W);
   LNST_LAUNCH(raymarch_bwd_k, dim3(lnst_blocks((int64_t)H * W, 128), n_views), dim3(128), 0,
               lnst_stream(stream), vol, rot, v, make_subvol(box, D, H, W), tau, (int)liquid, stot, g_img, g_vol, 0);
@@ -831,6 +886,16 @@ extern "C" int lnst_normalize_fwd(const float* img, const float* stats, int32_t 
                                   float* gray, void* stream) {
   if (!img || !stats || !gray || n_img < 1 || n_pix < 1) return LNST_EARG;
   LNST_LAUNCH(normalize_fwd_k, dim3(lnst_blocks(n_pix, 256), n_img), dim3(256), 0, lnst_stream(stream), img,
+              stats, n_pix, gray);
+  return lnst_status();
+}
+
+// gray = img / max and stats[2v+1] = number of pixels at the maximum, in one pass; stats[2v] = max must be final
+// (lnst_raymarch_fwd_max_*) and stats[2v+1] zero on entry.
+extern "C" int lnst_normalize_ties_fwd(const float* img, float* stats, int32_t n_img, int64_t n_pix, float* gray,
+                                       void* stream) {
+  if (!img || !stats || !gray || n_img < 1 || n_pix < 1) return LNST_EARG;
+  LNST_LAUNCH(normalize_ties_fwd_k, dim3(lnst_blocks(n_pix, 256), n_img), dim3(256), 0, lnst_stream(stream), img,
               stats, n_pix, gray);
   return lnst_status();
 }

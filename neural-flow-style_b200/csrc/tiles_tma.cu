@@ -394,7 +394,7 @@ __global__ void __launch_bounds__(rm::THREADS) raymarch_fwd_tma_k(const __grid_c
                                                                   const float* __restrict__ rot, RayGeo g, BoxF bf,
                                                                   const int2* __restrict__ iv, float ntl2, int liquid,
                                                                   float* __restrict__ img, float* __restrict__ stot,
-                                                                  int tiles_w) {
+                                                                  int tiles_w, float* __restrict__ stats) {
   using namespace rm;
   constexpr int SLAB = BZ * BY * BX;                         // floats per slab (a multiple of 32: 128-byte aligned buffers)
   extern __shared__ unsigned char smem_raw[];
@@ -536,6 +536,10 @@ __global__ void __launch_bounds__(rm::THREADS) raymarch_fwd_tma_k(const __grid_c
   if (valid) {
     img[(int64_t)view * g.HW + h * g.W + w] = I;
     stot[(int64_t)view * g.HW + h * g.W + w] = S;
+  }
+  if (stats != nullptr) {                                    // the view's maximum (image_max_k), one atomic per warp
+    const float m = lnst_warp_max(valid ? I : 0.f);
+    if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(stats + 2 * view), __float_as_int(m));
   }
 }
 
@@ -763,7 +767,8 @@ extern "C" int lnst_set_raymarch_slab(int32_t planes) {
 
 template <int BZ>
 static int launch_rm_fwd(const CUtensorMap& mv, const float* vol, const float* rot, int n_views, const RayGeo& g,
-                         const BoxF& bf, const int2* iv, float ntl2, int liquid, float* img, float* stot, cudaStream_t st) {
+                         const BoxF& bf, const int2* iv, float ntl2, int liquid, float* img, float* stot, cudaStream_t st,
+                         float* stats) {
   using namespace rm;
   const int tiles_h = (g.H + TH - 1) / TH, tiles_w = (g.W + TW - 1) / TW;
   const int smem = 2 * BZ * BY * BX * 4 + 128;
@@ -774,13 +779,21 @@ static int launch_rm_fwd(const CUtensorMap& mv, const float* vol, const float* r
     configured = true;
   }
   raymarch_fwd_tma_k<BZ><<<dim3((unsigned)(tiles_h * tiles_w), (unsigned)n_views), THREADS, smem, st>>>(
-      mv, vol, rot, g, bf, iv, ntl2, liquid, img, stot, tiles_w);
+      mv, vol, rot, g, bf, iv, ntl2, liquid, img, stot, tiles_w, stats);
   return (int)cudaGetLastError();
 }
 
 extern "C" int lnst_raymarch_fwd_tma(const float* vol, const float* rot, int32_t n_views, int32_t D, int32_t H,
                                      int32_t W, float tau, int32_t liquid, const LnstBox* box, const int32_t* intervals,
                                      float* img, float* stot, void* stream) {
+  return lnst_raymarch_fwd_max_tma(vol, rot, n_views, D, H, W, tau, liquid, box, intervals, img, stot, nullptr, stream);
+}
+
+// The same march; stats[2 v] = max over view v's pixels comes out of the kernel's last instructions (stats must be zero on
+// entry; lnst_image_max's first pass and its memset disappear).  stats may be NULL.
+extern "C" int lnst_raymarch_fwd_max_tma(const float* vol, const float* rot, int32_t n_views, int32_t D, int32_t H,
+                                         int32_t W, float tau, int32_t liquid, const LnstBox* box,
+                                         const int32_t* intervals, float* img, float* stot, float* stats, void* stream) {
   using namespace rm;
   if (!vol || !rot || !img || !stot || n_views < 1 || D < 2 || H < 2 || W < 2 || !box_ok(box, D, H, W)) return LNST_EARG;
   if ((int64_t)D * H * W >= 0x7fffffff) return LNST_EARG;
@@ -792,9 +805,9 @@ extern "C" int lnst_raymarch_fwd_tma(const float* vol, const float* rot, int32_t
   const int2* iv = reinterpret_cast<const int2*>(intervals);
   const float ntl2 = -tau * 1.4426950408889634f;
   cudaStream_t st = lnst_stream(stream);
-  if (bz == 8) return launch_rm_fwd<8>(mv, vol, rot, n_views, g, bf, iv, ntl2, (int)liquid, img, stot, st);
-  if (bz == 12) return launch_rm_fwd<12>(mv, vol, rot, n_views, g, bf, iv, ntl2, (int)liquid, img, stot, st);
-  return launch_rm_fwd<16>(mv, vol, rot, n_views, g, bf, iv, ntl2, (int)liquid, img, stot, st);
+  if (bz == 8) return launch_rm_fwd<8>(mv, vol, rot, n_views, g, bf, iv, ntl2, (int)liquid, img, stot, st, stats);
+  if (bz == 12) return launch_rm_fwd<12>(mv, vol, rot, n_views, g, bf, iv, ntl2, (int)liquid, img, stot, st, stats);
+  return launch_rm_fwd<16>(mv, vol, rot, n_views, g, bf, iv, ntl2, (int)liquid, img, stot, st, stats);
 }
 
 template <int BZ>

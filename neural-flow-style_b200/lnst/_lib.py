@@ -53,6 +53,9 @@ SIGNATURES = {
     'lnst_raymarch_bwd': [vp, vp, i32, i32, i32, i32, f32, i32, vp, vp, vp, vp],
     'lnst_raymarch_fwd_box': [vp, vp, i32, i32, i32, i32, f32, i32, BP, vp, vp, vp, vp],
     'lnst_raymarch_bwd_box': [vp, vp, i32, i32, i32, i32, f32, i32, BP, vp, vp, vp, vp, vp],
+    'lnst_raymarch_fwd_max_box': [vp, vp, i32, i32, i32, i32, f32, i32, BP, vp, vp, vp, vp, vp],
+    'lnst_raymarch_bwd_norm_box': [vp, vp, i32, i32, i32, i32, f32, i32, BP, vp, vp, vp, vp, vp, vp, vp, vp],
+    'lnst_normalize_ties_fwd': [vp, vp, i32, i64, vp, vp],
     'lnst_ray_intervals': [vp, i32, i32, i32, i32, BP, vp, vp, vp],
     'lnst_ray_intervals_exact': [vp, i32, i32, i32, i32, BP, vp, vp, vp],
     'lnst_set_raymarch_merge': [i32],
@@ -148,6 +151,8 @@ CUDA_ONLY = {
     'lnst_smooth3_relu_fwd_tma': [vp, vp, i32, i32, i32, i32, BP, vp],
     'lnst_smooth3_relu_bwd_tma': [vp, vp, vp, i32, i32, i32, i32, BP, vp],
     'lnst_raymarch_fwd_tma': [vp, vp, i32, i32, i32, i32, f32, i32, BP, vp, vp, vp, vp],
+    'lnst_raymarch_fwd_max_tma': [vp, vp, i32, i32, i32, i32, f32, i32, BP, vp, vp, vp, vp, vp],
+    'lnst_conv_first_bwd_gray_dot_tc': [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp],
     'lnst_raymarch_bwd_tma': [vp, vp, i32, i32, i32, i32, f32, BP, vp, vp, vp, vp, vp],
     'lnst_bf16_to_f32': [vp, vp, i64, vp],
 }

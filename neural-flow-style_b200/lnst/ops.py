@@ -205,28 +205,39 @@ def ray_intervals_exact(rot, shape, box, touch, out=None):
     return out
 
 
-def raymarch_fwd(vol, rot, tau, liquid, img, stot, box=None, intervals=None):
+def raymarch_fwd(vol, rot, tau, liquid, img, stot, box=None, intervals=None, stats=None):
+    """``stats`` [2 nv] (zero on entry): the kernel also reduces stats[2v] = max of view v (rotated march only)."""
     D, H, W = vol.shape
     nv = 1 if rot is None else rot.shape[0]
     if rot is not None and min(D, H, W) >= 2 and D * H * W < 2 ** 31 - 1 and _tma_ok(vol):
-        _lib.get().call('lnst_raymarch_fwd_tma', ptr(vol), ptr(rot), nv, D, H, W, float(tau), int(bool(liquid)), _b(box),
-                        _u8(intervals), ptr(img), ptr(stot), _s(vol))
+        _lib.get().call('lnst_raymarch_fwd_max_tma', ptr(vol), ptr(rot), nv, D, H, W, float(tau), int(bool(liquid)), _b(box),
+                        _u8(intervals), ptr(img), ptr(stot), ptr(stats), _s(vol))
         return img, stot
-    _lib.get().call('lnst_raymarch_fwd_box', ptr(vol), ptr(rot), nv, D, H, W, float(tau), int(bool(liquid)), _b(box),
-                    _u8(intervals), ptr(img), ptr(stot), _s(vol))
+    _lib.get().call('lnst_raymarch_fwd_max_box', ptr(vol), ptr(rot), nv, D, H, W, float(tau), int(bool(liquid)), _b(box),
+                    _u8(intervals), ptr(img), ptr(stot), ptr(stats), _s(vol))
     return img, stot
 
 
-def raymarch_bwd(vol, rot, tau, liquid, stot, g_img, g_vol, box=None, intervals=None):
+def raymarch_bwd(vol, rot, tau, liquid, stot, g_img, g_vol, box=None, intervals=None, norm=None):
+    """``norm`` = (img, stats, dots): g_img is the cotangent of img / max(img) and the kernel applies the normalisation's
+    gradient while loading it (rotated march only)."""
     D, H, W = vol.shape
     nv = 1 if rot is None else rot.shape[0]
-    if USE_TMA_BWD and rot is not None and not liquid and min(D, H, W) >= 2 and D * H * W < 2 ** 30 - 1 and _tma_ok(vol):
+    if norm is None and USE_TMA_BWD and rot is not None and not liquid and min(D, H, W) >= 2 and D * H * W < 2 ** 30 - 1 \
+            and _tma_ok(vol):
         _lib.get().call('lnst_raymarch_bwd_tma', ptr(vol), ptr(rot), nv, D, H, W, float(tau), _b(box), _u8(intervals),
                         ptr(stot), ptr(g_img), ptr(g_vol), _s(vol))
         return g_vol
-    _lib.get().call('lnst_raymarch_bwd_box', ptr(vol), ptr(rot), nv, D, H, W, float(tau), int(bool(liquid)), _b(box),
-                    _u8(intervals), ptr(stot), ptr(g_img), ptr(g_vol), _s(vol))
+    n_img, n_stats, n_dots = norm if norm is not None else (None, None, None)
+    _lib.get().call('lnst_raymarch_bwd_norm_box', ptr(vol), ptr(rot), nv, D, H, W, float(tau), int(bool(liquid)), _b(box),
+                    _u8(intervals), ptr(stot), ptr(g_img), ptr(n_img), ptr(n_stats), ptr(n_dots), ptr(g_vol), _s(vol))
     return g_vol
+
+
+def normalize_ties_fwd(img, stats, gray):
+    """gray = img / max and stats[2v+1] = ties in one pass (stats[2v] final, stats[2v+1] zero on entry)"""
+    _lib.get().call('lnst_normalize_ties_fwd', ptr(img), ptr(stats), img.shape[0], img[0].numel(), ptr(gray), _s(img))
+    return gray
 
 
 def image_max(img, stats):
@@ -795,6 +806,15 @@ def conv_first_bwd_gray_x3_tc(g, wd16_gray2):
     n, H, W, _ = g.shape
     gg = torch.empty(n, H, W, dtype=f32, device=g.device)
     _lib.get().call('lnst_conv_first_bwd_gray_x3_tc', ptr(g), ptr(wd16_gray2), ptr(gg), n, H, W, _s(g))
+    return gg
+
+
+def conv_first_bwd_gray_dot_tc(g, wd16_gray, split, img, dots):
+    """conv1_1's gray data gradient plus dots[v] += sum g_gray[v] * img[v] from the same kernel -> g_gray fp32 [n,H,W]"""
+    n, H, W, _ = g.shape
+    gg = torch.empty(n, H, W, dtype=f32, device=g.device)
+    _lib.get().call('lnst_conv_first_bwd_gray_dot_tc', ptr(g), ptr(wd16_gray), ptr(gg), ptr(img), ptr(dots), int(bool(split)),
+                    n, H, W, _s(g))
     return gg
 
 

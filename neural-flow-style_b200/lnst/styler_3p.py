@@ -363,7 +363,7 @@ class Styler(StylerBase):
             ws['box_cells'] = (hi[0] - lo[0] + 1) * (hi[1] - lo[1] + 1) * (hi[2] - lo[2] + 1)
         return ws
 
-    def _render(self, ds, rot, box=None, bricks=None, net_input=True, joint=False, touch=None):
+    def _render(self, ds, rot, box=None, bricks=None, net_input=True, joint=False, touch=None, glue=None):
         """ds [D,H,W] -> gray [nv,H,W,1] in [0,1] plus what the backward needs.  ``net_input=False``: the loss
         net starts from the gray image itself (``_gray_path``), d_img / x are not produced."""
         D, H, W = ds.shape
@@ -384,10 +384,16 @@ class Styler(StylerBase):
                     iv = ops.ray_intervals(rot, ds.shape, box, bricks)
                 if 'uniform' in self.sample_type:
                     self._iv_cache[key] = iv
-        ops.raymarch_fwd(ds, rot, self.transmit, self.render_liquid, img, stot, box, iv)
+        fused = glue is not None and not self.render_liquid and not joint and rot is not None and min(ds.shape) >= 2
+        ops.raymarch_fwd(ds, rot, self.transmit, self.render_liquid, img, stot, box, iv, stats=glue[0] if fused else None)
         st = {'img': img, 'stot': stot, 'rot': rot, 'box': box, 'iv': iv}
         if self.render_liquid:
             gray = img
+        elif fused:
+            # ``glue`` = (stats [2 nv], dots [nv]), zeroed by the caller: the march reduced the per-view maxima, one pass
+            # normalises and counts the ties, and the backward folds the rest into its neighbours (_render_bwd)
+            st['stats'], st['dots'], st['joint'] = glue[0], glue[1], False
+            gray = ops.normalize_ties_fwd(img, st['stats'], torch.empty_like(img))
         else:                                                     # styler_3p.py:158
             # `d /= tf.reduce_max(d)` is over the whole fed tensor: one maximum per view here, or -- ``joint``, a
             # v_batch group -- one for all views of the call (the views seen as a single nv*H x W image)
@@ -423,8 +429,15 @@ class Styler(StylerBase):
         g_gray = g_gray.reshape(nv, H, W)
         if g_gray0 is not None:
             g_gray = ops.axpy(g_gray.contiguous(), g_gray0, 1.0)
+        tc = getattr(self.net, 'tc', None)
         if self.render_liquid:
             g_img = g_gray
+        elif st.get('dots') is not None and tc is not None and tc.gray_dot_done and g_gray0 is None:
+            # sum(g_gray * img) came out of conv1_1's data-gradient kernel; the march applies the normalisation's gradient
+            tc.gray_dot_done = False
+            ops.raymarch_bwd(ds, st['rot'], self.transmit, False, st['stot'], g_gray.contiguous(), g_ds, st['box'], st['iv'],
+                             norm=(st['img'], st['stats'], st['dots']))
+            return
         else:
             imj, ggj = st['img'], g_gray.contiguous()
             if st.get('joint'):
@@ -455,12 +468,22 @@ class Styler(StylerBase):
         with nvtx('lnst.smooth_fwd'):
             ds = ops.smooth3_relu_fwd(d, ws['ds'], self.k, box)    # styler_3p.py:112-125
         gray_path = self._gray_path()
+        nv = 1 if rot is None else rot.shape[0]
+        # one zeroed block for the step's small accumulators: loss [nv] | per-view {max, ties} [2 nv] | dots [nv]
+        fuse = getattr(self, 'fuse_glue', True) and rot is not None and not self.render_liquid and not group
+        scal = ops.zeros(4 * nv if fuse else nv, self.device)
         with nvtx('lnst.render_fwd'):
-            st = self._render(ds, rot, box, ws['bricks'], net_input=not gray_path, joint=group, touch=ws['touch'])
-        nv = st['gray'].shape[0]
-        loss = ops.zeros(nv, self.device)
+            st = self._render(ds, rot, box, ws['bricks'], net_input=not gray_path, joint=group, touch=ws['touch'],
+                              glue=(scal[nv:3 * nv], scal[3 * nv:]) if fuse else None)
+        assert nv == st['gray'].shape[0]
+        loss = scal[:nv]
         g_gray0 = None
+        tc = getattr(self.net, 'tc', None)
+        if tc is not None:
+            tc.gray_dot, tc.gray_dot_done = None, False
         if gray_path:
+            if st.get('dots') is not None and tc is not None and tuple(st['gray'].shape[1:]) == tuple(st['hw']):
+                tc.gray_dot = (st['img'], st['dots'])
             g_x = self.image_loss_and_grad(None, None, style_grams, loss, gray=st['gray'])
         elif self.style_mask and self.w_style and style_grams is not None:
             # mask per style layer = TF-legacy bicubic resize of the render to the feature size; its cotangent comes

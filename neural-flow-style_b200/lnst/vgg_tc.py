@@ -35,6 +35,8 @@ def _pack2(w):
 
 class TensorCoreConvs:
     fuse_pool = True                                     # conv + 2x2 average pool from one epilogue (split mode)
+    gray_dot = None                                      # (image, dots): set by the styler for ONE backward pass
+    gray_dot_done = False
 
     def __init__(self, net, split=False):
         # the network owns this object: a weak back-reference keeps the pair out of a reference cycle, so the
@@ -122,6 +124,11 @@ class TensorCoreConvs:
                         # TMA-staged patch + CUDA cores with un-rounded fp32 weights: shared-memory-bandwidth bound
                         # (0.090 ms at C3 against 0.064 for the N = 16 MMA form), so not the default
                         g = ops.conv_first_bwd_gray_direct(g, sp, self.wg_gray)
+                    elif self.gray_dot is not None:
+                        # the render's normalisation needs sum(g_gray * image) next: reduced by the same kernel
+                        img, dots = self.gray_dot
+                        self.gray_dot, self.gray_dot_done = None, True
+                        g = ops.conv_first_bwd_gray_dot_tc(g, self.wd16_gray, sp, img, dots)
                     else:
                         g = (ops.conv_first_bwd_gray_x3_tc if sp else ops.conv_first_bwd_gray_tc)(g, self.wd16_gray)  # d loss / d gray
                 elif prev is None and tuple(self.net.w[name].shape[2:]) == (3, 64):

@@ -122,3 +122,45 @@ def test_exact_ray_intervals_leave_the_render_and_its_gradient_unchanged(dev, sh
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
     m = torch.tensor(occ)
     close(outs[1][2][m], outs[0][2][m], tol=1e-5, what='gradient on the support')
+
+
+@pytest.mark.parametrize('shape', [(9, 7, 8), (11, 6, 45), (14, 33, 37)])
+def test_fused_image_glue_equals_the_separate_calls(dev, shape):
+    """lnst_raymarch_fwd_max_* + lnst_normalize_ties_fwd against the march, lnst_image_max and lnst_normalize_fwd; and
+    lnst_raymarch_bwd_norm_box against lnst_normalize_bwd followed by the march: same maxima, ties, gray image, gradient."""
+    rng = np.random.RandomState(shape[2])
+    D, H, W = shape
+    vol_np = (rng.rand(D, H, W) * (rng.rand(D, H, W) > 0.4)).astype(np.float32)
+    vol = torch.tensor(vol_np).to(dev)
+    mats = [np.identity(3), np.matmul(T.rot_y_3d(5.0), T.rot_z_3d(-10.0)), np.matmul(T.rot_y_3d(-33.0), T.rot_z_3d(21.0))]
+    rot = torch.tensor(np.asarray(mats), dtype=torch.float32).reshape(-1, 9).to(dev)
+    nv, tau = len(mats), 0.3
+    img0, st0 = torch.empty(nv, H, W, device=dev), torch.empty(nv, H, W, device=dev)
+    ops.raymarch_fwd(vol, rot, tau, False, img0, st0)
+    stats0 = ops.image_max(img0, torch.empty(2 * nv, device=dev))
+    gray0 = ops.normalize_fwd(img0, stats0, torch.empty_like(img0))
+    img1, st1 = torch.empty(nv, H, W, device=dev), torch.empty(nv, H, W, device=dev)
+    stats1 = torch.zeros(2 * nv, device=dev)
+    ops.raymarch_fwd(vol, rot, tau, False, img1, st1, stats=stats1)
+    gray1 = ops.normalize_ties_fwd(img1, stats1, torch.empty_like(img1))
+    assert torch.equal(img0, img1) and torch.equal(st0, st1)
+    assert torch.equal(stats0, stats1), (stats0, stats1)
+    # ties: a hand-made image whose maximum is attained three times in view 1
+    im = torch.tensor(rng.rand(nv, H, W).astype(np.float32)).to(dev)
+    im[1, 0, 0] = im[1, H - 1, W - 1] = im[1, 2, 3] = 2.0
+    sa = ops.image_max(im, torch.empty(2 * nv, device=dev))
+    sb = torch.zeros(2 * nv, device=dev)
+    sb[0::2] = sa[0::2]
+    gb = ops.normalize_ties_fwd(im, sb, torch.empty_like(im))
+    assert torch.equal(sa, sb) and float(sb[3]) == 3.0
+    assert torch.equal(gb, ops.normalize_fwd(im, sa, torch.empty_like(im)))
+    assert torch.equal(gray0, gray1)
+    g_gray = torch.tensor(rng.randn(nv, H, W).astype(np.float32)).to(dev)
+    dots = torch.empty(nv, device=dev)
+    g_img = ops.normalize_bwd(img0, stats0, g_gray, dots, torch.empty_like(g_gray))
+    want = ops.raymarch_bwd(vol, rot, tau, False, st0, g_img, torch.zeros(D, H, W, device=dev))
+    got = ops.raymarch_bwd(vol, rot, tau, False, st0, g_gray, torch.zeros(D, H, W, device=dev), norm=(img0, stats0, dots))
+    if dev.type == 'cpu':
+        assert torch.equal(want, got)
+    else:                                                    # atomics: the summation order differs from launch to launch
+        close(got, want, tol=2e-6, what='fused normalisation gradient')

@@ -33,6 +33,9 @@ def main():
         elif a.switch.startswith('lib:'):                   # default library (1) against a variant build (0)
             _lib.set_for_testing(None if on else _lib.Lib(os.path.join(ROOT, a.switch[4:]), 'cuda'))
             ctx.lib = _lib.get()
+        elif a.switch == 'fuse_glue':
+            from lnst.styler_3p import Styler
+            Styler.fuse_glue = bool(on)
         elif a.switch == 'merge':
             lib.call('lnst_set_raymarch_merge', 2 if on else 1)
         else:
