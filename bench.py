@@ -217,15 +217,36 @@ def roofline_all(table, hbm_peak, tf_peak):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md's clocks line).  NVML is polled from a
+    thread every 2 ms -- `nvidia-smi -lms 100` saw nothing of a 20 ms timed region -- with nvidia-smi as the fallback."""
     Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
          'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
          'clocks_event_reasons.sw_power_cap')
+    BITS = {0x4: 'sw_power_cap', 0x8: 'hw_slowdown', 0x20: 'sw_thermal_slowdown', 0x40: 'hw_thermal_slowdown',
+            0x80: 'hw_power_brake_slowdown'}
 
     def __init__(self, index):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.proc, self.lines, self.nvml, self.samples = index, None, [], None, []
+        self._stop = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = None
+            try:                                            # CUDA_VISIBLE_DEVICES may renumber: find the device by UUID
+                uuid = str(torch.cuda.get_device_properties(index).uuid)
+                uuid = uuid if uuid.startswith('GPU-') else 'GPU-' + uuid
+                h = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode() if hasattr(uuid, 'encode') else uuid)
+            except Exception:
+                h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.nvml, self.h = pynvml, h
+        except Exception:
+            self.nvml = None
 
     def start(self):
+        if self.nvml is not None:
+            self.th = threading.Thread(target=self._poll, daemon=True)
+            self.th.start()
+            return
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
                                           '--format=csv,noheader,nounits', '-lms', '100'],
@@ -235,11 +256,37 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        while not self._stop.is_set():
+            try:
+                self.samples.append((n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM),
+                                     n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h), 0.0))
+            except Exception:
+                pass
+            time.sleep(0.001)
+
     def _read(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            self._stop.set()
+            self.th.join()
+            n = self.nvml
+            sm = [c for c, _, _ in self.samples]
+            reasons = set()
+            for _, bits, _ in self.samples:
+                for b, name in self.BITS.items():
+                    if bits & b:
+                        reasons.add(name)
+            try:
+                mx = float(n.nvmlDeviceGetMaxClockInfo(self.h, n.NVML_CLOCK_SM))
+            except Exception:
+                mx = None
+            return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': mx, 'reasons': sorted(reasons),
+                    'samples': len(sm), 'source': 'NVML polled during the timed region'}
         if self.proc is None:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
         time.sleep(0.15)
@@ -636,21 +683,22 @@ def run_engine(args):
             st = Styler(cfg, weights=synth.vgg_weights(), device=ctx.dev)
             st.style_img = sty
             return st
-        walls = []
-        for _ in range(2):                                   # the second call has the allocator's blocks of the first
+        walls, final_loss = [], None
+        for _ in range(3):                                   # later calls find the first one's device / pinned blocks cached
             st = mk(20)
             torch.cuda.synchronize()
             w0 = time.perf_counter()
             out_run = st.run({'p': p, 'r': r})
             torch.cuda.synchronize()
             walls.append(time.perf_counter() - w0)
-            del st
+            final_loss = float(out_run['l'][0][-1])
+            del st, out_run                                  # the result arrays are views of the run's pinned staging buffer
         wall = min(walls)
         extras['e2e_run'] = {'iters': 20, 'wall_s': wall, 'wall_s_each_call': walls, 'value': 20.0 / wall, 'unit': 'iters/s',
                              'what': 'Styler(config).run(params): upload + cell sort + weight maps + workspace + graph capture '
-                                     '+ 20 iterations (test_smokegun.py:143-146) + final inference + D2H of the results',
-                             'final_loss': float(out_run['l'][0][-1])}
-        del out_run
+                                     '+ 20 iterations (test_smokegun.py:143-146) + final inference + D2H of the results; '
+                                     'best of three calls (the first one pays cudaMalloc / cudaHostAlloc)',
+                             'final_loss': final_loss}
         torch.cuda.empty_cache()
         extras['configs'] = other_configs(ctx, conv_math, hbm_peak, tf_peak, src)
     if rank != 0:
