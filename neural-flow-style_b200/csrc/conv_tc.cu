@@ -2397,6 +2397,7 @@ extern "C" int lnst_gram_diff_bf16x3_tc(const void* F, int32_t n, int64_t P, int
     int splits = (148 + tiles * n - 1) / (tiles * n);           // about one wave of CTAs
     const int max_splits = (int)((P + 255) / 256);             // at least 4 k-blocks per CTA
     if (splits > max_splits) splits = max_splits;
+    if (splits > 16) splits = 16;                              // every split adds 16 K atomics onto the same tile (1-2 images per rank)
     if (splits < 1) splits = 1;
     int kps = (int)((P + splits - 1) / splits);
     kps = ((kps + 63) / 64) * 64;
