@@ -345,6 +345,15 @@ int lnst_conv3x3_bf16x3_tc(const void* x, const void* w_packed2, const float* bi
 int lnst_conv3x3_pool_bf16x3_tc(const void* x, const void* w_packed2, const float* bias, const void* mask, void* y,
                                 void* y_pool, int32_t n, int32_t H, int32_t W, int32_t Cin, int32_t Cout, int32_t relu,
                                 void* stream);
+/* Data gradient through a 3x3 convolution plus the Gram-loss gradient of the layer it lands on, masked together:
+ * y = relu_mask(F) * (x (*) w_packed2 + F x Gd2s), F split [n,H,W,2*Cout] (the layer's features), Gd2s split [n,Cout,2*Cout]
+ * from lnst_gram_diff_scaled_bf16x3_tc with gd_scale = the loss coefficient.  One kernel when Cout % 128 == 0 (the tile
+ * accumulates both products); otherwise the convolution followed by lnst_gram_bwd_bf16x3_tc.  styler_base.py:98-109. */
+int lnst_conv3x3_gram_bf16x3_tc(const void* x, const void* w_packed2, const void* F, const void* Gd2s, void* y, int32_t n,
+                                int32_t H, int32_t W, int32_t Cin, int32_t Cout, void* stream);
+/* lnst_gram_diff_bf16x3_tc with Gd2 = split(gd_scale * G); gd_scale != 1 needs C % 128 == 0. */
+int lnst_gram_diff_scaled_bf16x3_tc(const void* F, int32_t n, int64_t P, int32_t C, float denom, const float* Gs,
+                                    float weight, float gd_scale, float* G2, float* G, void* Gd2, float* loss, void* stream);
 /* G2: fp32 scratch [n,2C,2C]; G fp32 [n,C,C] = F^T F/denom - Gs; Gd2 bf16 [n,C,2C] = split copy of G (may be NULL). */
 int lnst_gram_diff_bf16x3_tc(const void* F, int32_t n, int64_t P, int32_t C, float denom, const float* Gs, float weight,
                              float* G2, float* G, void* Gd2, float* loss, void* stream);

@@ -181,13 +181,16 @@ struct ConvShape {
   // chunks per tap (Cin/64 or 2*Cin/64), kc = Cin/64; chunk c reads activation chunk xchunk(c) and weight chunk wchunk(c).
   int split, kc, nchunks, wchunks;
   int ldy, ldm;  // row strides (elements) of the output / mask / addend tensors: Cout, or 2*Cout when split
+  int gram_kc;   // halo kernel, GRAM: 64-channel chunks of the feature tensor whose Gram gradient joins the tile (else 0)
 };
 __device__ __forceinline__ int xchunk(const ConvShape& s, int c) { return (s.split && c >= 2 * s.kc) ? c - 2 * s.kc : c; }
 __device__ __forceinline__ int wchunk(const ConvShape& s, int c) { return (s.split && c >= s.kc) ? c - s.kc : c; }
 static inline void shape_plain(ConvShape& s) {
+  s.gram_kc = 0;
   s.split = 0; s.kc = s.Cin / 64; s.nchunks = s.kc; s.wchunks = s.kc; s.ldy = s.Cout; s.ldm = s.Cout;
 }
 static inline void shape_split(ConvShape& s) {
+  s.gram_kc = 0;
   s.split = 1; s.kc = s.Cin / 64; s.nchunks = 3 * s.kc; s.wchunks = 2 * s.kc; s.ldy = 2 * s.Cout; s.ldm = 2 * s.Cout;
 }
 // hi/lo split of an fp32 pair
@@ -660,12 +663,17 @@ template <int BLOCK_N> struct HaloAcc { static constexpr int value = (BLOCK_N >=
 // store staging: 128-byte row chunks (8 x 16 B) for the wide tiles, 64-byte ones where shared memory is tight
 template <int BLOCK_N> struct HaloStage { static constexpr int nv = 4; static constexpr int bytes = (BLOCK_N >= 128) ? 4 * nv * 512 : 0; };
 
-template <int BLOCK_N, bool OUT3, bool RES, bool POOL = false>
+// GRAM (streamed weights only): after the nine taps the tile also accumulates F x Gd -- the Gram-loss gradient of the layer
+// this data gradient lands on (vgg.py style layers; styler_base.py:98-109) -- from the layer's own features F (same
+// pixels: the centre tap of an F patch) and the per-image matrix Gd (pre-scaled by the loss coefficient), so the separate
+// per-pixel GEMM with its read-modify-write of the whole gradient tensor disappears.  s.gram_kc = C_F / 64.
+template <int BLOCK_N, bool OUT3, bool RES, bool POOL = false, bool GRAM = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv3x3_halo_k(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                const float* __restrict__ bias, const __nv_bfloat16* __restrict__ mask,
                __nv_bfloat16* __restrict__ y, float* __restrict__ y3, ConvShape s, HaloCfg cfg,
-               __nv_bfloat16* __restrict__ ypool) {
+               __nv_bfloat16* __restrict__ ypool, const __grid_constant__ CUtensorMap map_f,
+               const __grid_constant__ CUtensorMap map_g) {
   constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
   // accumulator ring in TMEM: the round trip MMA-complete -> tfull -> epilogue -> tempty -> next MMA costs about
   // 4000 cycles (measured: with two buffers every tile took >= 2000 cycles even with 1/9 of the MMAs and no
@@ -743,6 +751,25 @@ conv3x3_halo_k(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
           }
         }
       }
+      if (GRAM && !resident) {
+        // F_hi x Gd_hi, F_lo x Gd_hi, F_hi x Gd_lo: chunk c reads feature chunk fx(c) and matrix chunk gw(c)
+        const int gk = s.gram_kc;
+        for (int c = 0; c < 3 * gk; ++c) {
+          const int fx = c >= 2 * gk ? c - 2 * gk : c, gw = c >= gk ? c - gk : c;
+          mbar_wait(bar_aempty + 8 * sta, pha ^ 1);
+          if (leader) {
+            mbar_expect_tx(bar_afull + 8 * sta, PATCH_BYTES);
+            tma_load_4d(smem_a + sta * PATCH_STRIDE, &map_f, bar_afull + 8 * sta, fx * BLOCK_K, w0 - 1, h0 - 1, img);
+          }
+          if (++sta == (uint32_t)cfg.sa) { sta = 0; pha ^= 1; }
+          mbar_wait(bar_bempty + 8 * stb, phb ^ 1);
+          if (leader) {
+            mbar_expect_tx(bar_bfull + 8 * stb, B_BYTES);
+            tma_load_3d(smem_b + stb * B_BYTES, &map_g, bar_bfull + 8 * stb, gw * BLOCK_K, n0, img);
+          }
+          if (++stb == (uint32_t)cfg.sb) { stb = 0; phb ^= 1; }
+        }
+      }
     }
   } else if (warp == 1) {
     // ===== MMA issuer (whole warp in the loop, one elected lane issues) =====
@@ -800,6 +827,24 @@ conv3x3_halo_k(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         }
         if (leader) umma_commit(bar_aempty + 8 * sta);
         if (++sta == (uint32_t)cfg.sa) { sta = 0; pha ^= 1; }
+      }
+      if (GRAM && !resident) {
+        for (int c = 0; c < 3 * s.gram_kc; ++c) {
+          mbar_wait(bar_afull + 8 * sta, pha);
+          mbar_wait(bar_bfull + 8 * stb, phb);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t alo = alo_base + sta * (PATCH_STRIDE >> 4) + (((HTW + 2) + 1) * 128 >> 4);   // centre tap
+          const uint32_t blo = blo_base + stb * (B_BYTES >> 4);
+          if (leader) {
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+              umma_bf16_lh(acc, alo + k * 2, ahi, blo + k * 2, bhi, idesc, 1u);
+            umma_commit(bar_bempty + 8 * stb);
+            umma_commit(bar_aempty + 8 * sta);
+          }
+          if (++stb == (uint32_t)cfg.sb) { stb = 0; phb ^= 1; }
+          if (++sta == (uint32_t)cfg.sa) { sta = 0; pha ^= 1; }
+        }
       }
       if (leader) umma_commit(bar_tfull + 8 * buf);
       if (++buf == NACC) { buf = 0; bph ^= 1; }
@@ -1291,7 +1336,8 @@ gram_split_tc_k(const __grid_constant__ CUtensorMap map_f, float* __restrict__ G
 // loss slots serialised: ~10 us for a 0.6-2.4 MB pass).
 __global__ void __launch_bounds__(256) gram_finish_split3_k(const float* __restrict__ Graw, float* __restrict__ G,
                                                             const float* __restrict__ Gs, __nv_bfloat16* __restrict__ Gd2,
-                                                            int C, float inv_denom, float weight, float* __restrict__ loss) {
+                                                            int C, float inv_denom, float weight, float* __restrict__ loss,
+                                                            float gd_scale) {
   __shared__ float part[8];
   const int img = blockIdx.y;
   const int n_el = C * C;
@@ -1319,9 +1365,10 @@ __global__ void __launch_bounds__(256) gram_finish_split3_k(const float* __restr
     if (Gd2) {
       const int r = i / C, c = i - r * C;
       const int64_t a = (int64_t)r * 2 * C + c;
-      const __nv_bfloat16 h = __float2bfloat16_rn(v);
+      const float vs = v * gd_scale;                    // the operand of the gradient GEMM may carry the loss coefficient
+      const __nv_bfloat16 h = __float2bfloat16_rn(vs);
       Gd2[(int64_t)img * 2 * n_el + a] = h;
-      Gd2[(int64_t)img * 2 * n_el + a + C] = __float2bfloat16_rn(v - __bfloat162float(h));
+      Gd2[(int64_t)img * 2 * n_el + a + C] = __float2bfloat16_rn(vs - __bfloat162float(h));
     }
   }
   if (loss && Gs) {                                     // uniform branch: every thread of the block takes it
@@ -1465,7 +1512,8 @@ static int conv_halo = 2;         // tuning switch: 0 = per-tap kernel, 1 = halo
 template <int BLOCK_N, bool OUT3>
 static int launch_halo(const void* x, const void* wmat, const float* bias, const __nv_bfloat16* mask,
                        __nv_bfloat16* y, float* y3, int n, int H, int W, int Cin, int Cout, int relu, float scale,
-                       cudaStream_t stream, int out_ch = 3, int split = 0, __nv_bfloat16* ypool = nullptr) {
+                       cudaStream_t stream, int out_ch = 3, int split = 0, __nv_bfloat16* ypool = nullptr,
+                       const void* gram_f = nullptr, const void* gram_g = nullptr, int* gram_fused = nullptr) {
   constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
   constexpr int MAX_SMEM = 232448;                        // 227 KiB opt-in limit per CTA
   const int budget = MAX_SMEM - 2048 - 1024 - 512 - HaloStage<BLOCK_N>::bytes - 128;   // static bias table, alignment slack, barriers, store staging
@@ -1521,6 +1569,37 @@ static int launch_halo(const void* x, const void* wmat, const float* bias, const
     configured = true;
   }
   const int grid = cfg.n_tiles < sms ? cfg.n_tiles : sms;
+  if (gram_fused) *gram_fused = 0;
+  if constexpr (!OUT3 && BLOCK_N == 128) if (gram_f != nullptr && gram_g != nullptr && split && cfg.sb != 0 && ypool == nullptr) {
+    // Gram-loss gradient of the layer this data gradient lands on, accumulated by the same tiles (features F and the
+    // pre-scaled per-image matrix Gd: Cout logical channels each)
+    CUtensorMap mf, mg;
+    const int fC = 2 * Cout;
+    {
+      const cuuint64_t dims[4] = {(cuuint64_t)fC, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n};
+      const cuuint64_t strides[3] = {(cuuint64_t)fC * 2, (cuuint64_t)W * fC * 2, (cuuint64_t)H * W * fC * 2};
+      const cuuint32_t box[4] = {(cuuint32_t)BLOCK_K, (cuuint32_t)(HTW + 2), (cuuint32_t)(HTH + 2), 1};
+      if (!make_map(&mf, gram_f, 4, dims, strides, box)) return LNST_EARG;
+    }
+    {
+      const cuuint64_t dims[3] = {(cuuint64_t)fC, (cuuint64_t)Cout, (cuuint64_t)n};
+      const cuuint64_t strides[2] = {(cuuint64_t)fC * 2, (cuuint64_t)Cout * fC * 2};
+      const cuuint32_t box[3] = {(cuuint32_t)BLOCK_K, (cuuint32_t)BLOCK_N, 1};
+      if (!make_map(&mg, gram_g, 3, dims, strides, box)) return LNST_EARG;
+    }
+    static bool gconfigured = false;
+    if (!gconfigured) {
+      cudaError_t e = cudaFuncSetAttribute(conv3x3_halo_k<BLOCK_N, false, false, false, true>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM - 2048);
+      if (e != cudaSuccess) return (int)e;
+      gconfigured = true;
+    }
+    s.gram_kc = Cout / 64;
+    conv3x3_halo_k<BLOCK_N, false, false, false, true><<<grid, NUM_THREADS, smem, stream>>>(mx, mw, bias, mask, y, y3, s, cfg,
+                                                                                          nullptr, mf, mg);
+    if (gram_fused) *gram_fused = 1;
+    return (int)cudaGetLastError();
+  }
   if (ypool != nullptr) {
     // the pooled output is a separate instantiation: with the pool code behind a run-time test every halo kernel
     // grew by 14-35 registers and ran 12-19 % slower (ncu launch lists, profiles/)
@@ -1538,15 +1617,15 @@ static int launch_halo(const void* x, const void* wmat, const float* bias, const
       pconfigured = true;
     }
     if (cfg.sb == 0)
-      conv3x3_halo_k<BLOCK_N, false, true, true><<<grid, NUM_THREADS, smem, stream>>>(mx, mw, bias, mask, y, y3, s, cfg, ypool);
+      conv3x3_halo_k<BLOCK_N, false, true, true><<<grid, NUM_THREADS, smem, stream>>>(mx, mw, bias, mask, y, y3, s, cfg, ypool, mx, mw);
     else
-      conv3x3_halo_k<BLOCK_N, false, false, true><<<grid, NUM_THREADS, smem, stream>>>(mx, mw, bias, mask, y, y3, s, cfg, ypool);
+      conv3x3_halo_k<BLOCK_N, false, false, true><<<grid, NUM_THREADS, smem, stream>>>(mx, mw, bias, mask, y, y3, s, cfg, ypool, mx, mw);
     return (int)cudaGetLastError();
   }
   if (cfg.sb == 0)
-    conv3x3_halo_k<BLOCK_N, OUT3, true><<<grid, NUM_THREADS, smem, stream>>>(mx, mw, bias, mask, y, y3, s, cfg, ypool);
+    conv3x3_halo_k<BLOCK_N, OUT3, true><<<grid, NUM_THREADS, smem, stream>>>(mx, mw, bias, mask, y, y3, s, cfg, ypool, mx, mw);
   else
-    conv3x3_halo_k<BLOCK_N, OUT3, false><<<grid, NUM_THREADS, smem, stream>>>(mx, mw, bias, mask, y, y3, s, cfg, ypool);
+    conv3x3_halo_k<BLOCK_N, OUT3, false><<<grid, NUM_THREADS, smem, stream>>>(mx, mw, bias, mask, y, y3, s, cfg, ypool, mx, mw);
   return (int)cudaGetLastError();
 }
 
@@ -2243,7 +2322,8 @@ extern "C" int lnst_tc_supported(void) { return tc::encode_fn() != nullptr ? 1 :
 // (taps = 1, one B matrix per image)
 static int run_tc_gemm(const void* x, const void* wmat, const float* bias, const void* mask, const void* addend,
                        void* y, int n, int H, int W, int Cin, int Cout, int relu, int taps, int w_img, float scale,
-                       void* stream, int split = 0, void* ypool = nullptr) {
+                       void* stream, int split = 0, void* ypool = nullptr, const void* gram_f = nullptr,
+                       const void* gram_g = nullptr, int* gram_fused = nullptr) {
   using namespace tc;
   if (!x || !wmat || !y || n < 1 || H < 1 || W < 1 || Cin < 64 || Cout < 64 || Cin % 64 || Cout % 64)
     return LNST_EARG;
@@ -2259,7 +2339,8 @@ static int run_tc_gemm(const void* x, const void* wmat, const float* bias, const
     if (ypool && !split) return LNST_EARG;
     if (Cout % 128 == 0)
       return launch_halo<128, false>(x, wmat, bias, (const __nv_bfloat16*)mask, (__nv_bfloat16*)y, nullptr, n, H, W,
-                                     Cin, Cout, relu, scale, lnst_stream(stream), 3, split, (__nv_bfloat16*)ypool);
+                                     Cin, Cout, relu, scale, lnst_stream(stream), 3, split, (__nv_bfloat16*)ypool,
+                                     gram_f, gram_g, gram_fused);
     return launch_halo<64, false>(x, wmat, bias, (const __nv_bfloat16*)mask, (__nv_bfloat16*)y, nullptr, n, H, W, Cin,
                                   Cout, relu, scale, lnst_stream(stream), 3, split, (__nv_bfloat16*)ypool);
   }
@@ -2307,6 +2388,19 @@ extern "C" int lnst_conv3x3_bf16x3_tc(const void* x, const void* w_packed, const
                                       int32_t relu, void* stream) {
   return run_tc_gemm(x, w_packed, bias, mask, nullptr, y, n, H, W, Cin, Cout, relu, 9, 0, 1.0f, stream, 1);
 }
+// Data gradient through a 3x3 convolution PLUS the Gram-loss gradient of the layer it lands on, masked together:
+//   y = relu_mask(F) * ( x (*) w  +  F x Gd )      F split [n,H,W,2*Cout], Gd2s split [n,Cout,2*Cout] = coef * (G - Gs)
+// One kernel when the layer's weights are streamed (Cout % 128 == 0); otherwise the convolution followed by the per-pixel GEMM.
+extern "C" int lnst_conv3x3_gram_bf16x3_tc(const void* x, const void* w_packed, const void* F, const void* Gd2s, void* y,
+                                           int32_t n, int32_t H, int32_t W, int32_t Cin, int32_t Cout, void* stream) {
+  if (!F || !Gd2s) return LNST_EARG;
+  int fused = 0;
+  int rc = run_tc_gemm(x, w_packed, nullptr, F, nullptr, y, n, H, W, Cin, Cout, 0, 9, 0, 1.0f, stream, 1, nullptr, F, Gd2s,
+                       &fused);
+  if (rc != 0 || fused) return rc;
+  return run_tc_gemm(F, Gd2s, nullptr, F, y, y, n, H, W, Cout, Cout, 0, 1, 1, 1.0f, stream, 1);
+}
+
 // The same convolution, with the 2x2 average pool of its output (lnst_avgpool2_bf16x3_fwd) written by the same epilogue:
 // y_pool bf16 [n, H/2, W/2, 2*Cout].  Bit-identical to the two separate calls.
 extern "C" int lnst_conv3x3_pool_bf16x3_tc(const void* x, const void* w_packed, const float* bias, const void* mask,
@@ -2384,7 +2478,16 @@ static int gram_split3 = 1;       // tuning switch: 1 = gram_split_tc_k (hi/lo p
 extern "C" int lnst_set_gram_split3(int32_t on) { gram_split3 = on ? 1 : 0; return LNST_OK; }
 extern "C" int lnst_gram_diff_bf16x3_tc(const void* F, int32_t n, int64_t P, int32_t C, float denom, const float* Gs,
                                         float weight, float* G2, float* G, void* Gd2, float* loss, void* stream) {
+  return lnst_gram_diff_scaled_bf16x3_tc(F, n, P, C, denom, Gs, weight, 1.0f, G2, G, Gd2, loss, stream);
+}
+// The same with Gd2 = split(gd_scale * G): the gradient GEMM's operand carries the loss coefficient, so that F x Gd2 can be
+// accumulated next to other products (lnst_conv3x3_gram_bf16x3_tc).  gd_scale != 1 needs C % 128 == 0.
+extern "C" int lnst_gram_diff_scaled_bf16x3_tc(const void* F, int32_t n, int64_t P, int32_t C, float denom, const float* Gs,
+                                               float weight, float gd_scale, float* G2, float* G, void* Gd2, float* loss,
+                                               void* stream) {
+  const float gram_gd_scale = gd_scale;
   if (!F || !G2 || !G || n < 1 || P < 1 || C < 64 || C % 64 || !(denom > 0.f) || P > 0x7fffffff) return LNST_EARG;
+  if (gd_scale != 1.0f && !(C % 128 == 0 && gram_split3)) return LNST_EARG;
   if (C % 128 == 0 && gram_split3) {
     using namespace tc;
     cudaStream_t st = lnst_stream(stream);
@@ -2415,7 +2518,8 @@ extern "C" int lnst_gram_diff_bf16x3_tc(const void* F, int32_t n, int64_t P, int
     if (e != cudaSuccess) return (int)e;
     const int n_el3 = C * C;
     const unsigned nb3 = (unsigned)((n_el3 + 1023) / 1024);
-    gram_finish_split3_k<<<dim3(nb3, n), 256, 0, st>>>(G2, G, Gs, (__nv_bfloat16*)Gd2, (int)C, 1.f / denom, weight, loss);
+    gram_finish_split3_k<<<dim3(nb3, n), 256, 0, st>>>(G2, G, Gs, (__nv_bfloat16*)Gd2, (int)C, 1.f / denom, weight, loss,
+                                                       gram_gd_scale);
     return lnst_status();
   }
   const int rc = gram_raw(F, n, P, 2 * C, G2, lnst_stream(stream), 1);     // symmetric: 10 of the 16 tiles at C = 256

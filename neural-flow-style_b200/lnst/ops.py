@@ -760,16 +760,27 @@ def conv3x3_pool_bf16x3_tc(x, w_packed2, bias, relu, mask=None):
     return y, yp
 
 
-def gram_diff_bf16x3_tc(F, denom, Gs, weight, loss):
-    """F split bf16 [n,h,w,2C] -> (G fp32 [n,C,C] = F^T F/denom - Gs, Gd2 bf16 [n,C,2C] split); loss[n] += weight*sum(G^2)"""
+def gram_diff_bf16x3_tc(F, denom, Gs, weight, loss, gd_scale=1.0):
+    """F split bf16 [n,h,w,2C] -> (G fp32 [n,C,C] = F^T F/denom - Gs, Gd2 bf16 [n,C,2C] = split(gd_scale * G));
+    loss[n] += weight*sum(G^2)"""
     n, h, w, c2 = F.shape
     ch = c2 // 2
     G2 = torch.empty(n, c2, c2, dtype=f32, device=F.device)
     G = torch.empty(n, ch, ch, dtype=f32, device=F.device)
     Gd2 = torch.empty(n, ch, c2, dtype=bf16, device=F.device)
-    _lib.get().call('lnst_gram_diff_bf16x3_tc', ptr(F), n, h * w, ch, float(denom), ptr(Gs), float(weight), ptr(G2),
-                    ptr(G), ptr(Gd2), ptr(loss), _s(F))
+    _lib.get().call('lnst_gram_diff_scaled_bf16x3_tc', ptr(F), n, h * w, ch, float(denom), ptr(Gs), float(weight),
+                    float(gd_scale), ptr(G2), ptr(G), ptr(Gd2), ptr(loss), _s(F))
     return G, Gd2
+
+
+def conv3x3_gram_bf16x3_tc(x, w_packed2, F, Gd2s):
+    """relu_mask(F) * (x (*) w + F x Gd2s): a data gradient and the Gram-loss gradient of the layer it lands on -> split y"""
+    n, H, W, c2 = x.shape
+    cout = w_packed2.shape[1]
+    y = torch.empty(n, H, W, 2 * cout, dtype=bf16, device=x.device)
+    _lib.get().call('lnst_conv3x3_gram_bf16x3_tc', ptr(x), ptr(w_packed2), ptr(F), ptr(Gd2s), ptr(y), n, H, W, c2 // 2, cout,
+                    _s(x))
+    return y
 
 
 def gram_bwd_bf16x3_tc(F, Gd2, coef, addend, relu_mask, g=None):

@@ -37,6 +37,7 @@ class TensorCoreConvs:
     fuse_pool = True                                     # conv + 2x2 average pool from one epilogue (split mode)
     gray_dot = None                                      # (image, dots): set by the styler for ONE backward pass
     gray_dot_done = False
+    fuse_gram = True                                     # Gram-loss gradient accumulated by the data-gradient convolution above it
 
     def __init__(self, net, split=False):
         # the network owns this object: a weak back-reference keeps the pair out of a reference cycle, so the
@@ -79,6 +80,8 @@ class TensorCoreConvs:
         acts = {}
         cur = x
         sp = self.split
+        self._layers = list(layers)                     # what gram() may fuse into (the layer above a style layer)
+        self._gram_pending, self._gram_done = {}, set()
         pooled = None                                   # output of a pool layer already written by the convolution before it
         for i, name in enumerate(layers):
             if name.startswith('conv'):
@@ -117,7 +120,11 @@ class TensorCoreConvs:
             mask = prev_act if (prev is not None and prev.startswith('conv')) else None
             sp = self.split
             if name.startswith('conv'):
-                if name in self.wdp and prev is not None:
+                if name in self.wdp and prev is not None and sp and mask is not None and prev in self._gram_pending:
+                    # the Gram-loss gradient of `prev` joins this data gradient inside the kernel (same ReLU mask)
+                    g = ops.conv3x3_gram_bf16x3_tc(g, self.wdp[name], prev_act, self._gram_pending.pop(prev))
+                    self._gram_done.add(prev)
+                elif name in self.wdp and prev is not None:
                     g = (ops.conv3x3_bf16x3_tc if sp else ops.conv3x3_bf16_tc)(g, self.wdp[name], None, relu=False, mask=mask)
                 elif prev is None and gray and tuple(self.net.w[name].shape[2:]) == (3, 64):
                     if getattr(self, 'first_bwd_direct', False) and ops._tma_ok():
@@ -151,11 +158,25 @@ class TensorCoreConvs:
         if ch % 64:
             raise NotImplementedError('tensor-core Gram needs a channel count that is a multiple of 64')
         if self.split:
+            # a conv layer above `name` will compute the data gradient that lands here: it can carry F x Gd as well
+            # (Gd pre-scaled by the coefficient styler_base.add_loss_grad applies: weight * 4 / (2 P C))
+            layers = getattr(self, '_layers', [])
+            i = layers.index(name) if name in layers else -1
+            above = layers[i + 1] if 0 <= i < len(layers) - 1 else ''
+            if self.fuse_gram and ch % 128 == 0 and above in self.wdp and name.startswith('conv') and Gs is not None:
+                G, Gd2s = ops.gram_diff_bf16x3_tc(F, 2.0 * P * ch, Gs, weight, loss, gd_scale=weight * 4.0 / (2.0 * P * ch))
+                self._gram_pending[name] = Gd2s
+                return G, Gd2s
             return ops.gram_diff_bf16x3_tc(F, 2.0 * P * ch, Gs, weight, loss)
         return ops.gram_diff_bf16_tc(F, 2.0 * P * ch, Gs, weight, loss)
 
     def gram_grad(self, acts, name, handle, coef, g, relu_mask):
         if self.split:
+            if name in self._gram_done:                           # already inside g (conv3x3_gram_bf16x3_tc)
+                self._gram_done.discard(name)
+                return g
+            if name in self._gram_pending:                        # no gradient came from above: Gd2 carries the coefficient
+                return ops.gram_bwd_bf16x3_tc(acts.raw[name], self._gram_pending.pop(name), 1.0, g, relu_mask, g)
             return ops.gram_bwd_bf16x3_tc(acts.raw[name], handle[1], coef, g, relu_mask, g)
         return ops.gram_bwd_bf16_tc(acts.raw[name], handle[1], coef, g, relu_mask, g)
 

@@ -232,3 +232,33 @@ def test_conv_with_fused_pool_is_bit_identical_to_conv_then_pool(n, H, W, cin, c
     y1, p1 = ops.conv3x3_pool_bf16x3_tc(x, w, b, relu=True)
     assert torch.equal(y0, y1)
     assert p1.shape == p0.shape and torch.equal(p0, p1)
+
+
+@pytest.mark.parametrize('n,H,W,cin,cout', [(2, 20, 24, 128, 128), (1, 33, 47, 256, 128), (3, 50, 50, 128, 256), (9, 100, 100, 128, 128)])
+def test_data_gradient_with_fused_gram_gradient(n, H, W, cin, cout):
+    """lnst_conv3x3_gram_bf16x3_tc = the data-gradient convolution followed by lnst_gram_bwd_bf16x3_tc on its output."""
+    dev = torch.device('cuda:0')
+    g = torch.Generator().manual_seed(H * 5 + cin)
+    x = ops.to_split(torch.randn(n, H, W, cin, generator=g).to(dev))
+    w = _pack2(torch.randn(3, 3, cin, cout, generator=g) * 0.05).to(dev)
+    F32 = torch.relu(torch.randn(n, H, W, cout, generator=g))
+    F = ops.to_split(F32.to(dev))
+    Gs = (torch.randn(cout, cout, generator=g) * 0.01).to(dev)
+    Gs = (Gs + Gs.t()).contiguous()
+    den, weight = 2.0 * H * W * cout, 0.5
+    coef = weight * 4.0 / den
+    loss = torch.zeros(n, device=dev)
+    G, Gd2 = ops.gram_diff_bf16x3_tc(F, den, Gs, weight, loss)
+    _, Gd2s = ops.gram_diff_bf16x3_tc(F, den, Gs, weight, torch.zeros(n, device=dev), gd_scale=coef * 1e3)
+    y0 = ops.conv3x3_bf16x3_tc(x, w, None, relu=False, mask=F)
+    want = ops.from_split(ops.gram_bwd_bf16x3_tc(F, Gd2, coef * 1e3, y0, 1)).cpu().double()
+    got = ops.from_split(ops.conv3x3_gram_bf16x3_tc(x, w, F, Gd2s)).cpu().double()
+    # against fp64: mask * (conv + coef * F x G)
+    xd = ops.from_split(x).cpu().double()
+    wd = (w[..., :cin].double() + w[..., cin:].double()).cpu().reshape(3, 3, cout, cin).permute(0, 1, 3, 2)   # HWIO
+    conv = torch.nn.functional.conv2d(xd.permute(0, 3, 1, 2), wd.permute(3, 2, 0, 1), padding=1).permute(0, 2, 3, 1)
+    Fd = ops.from_split(F).cpu().double()
+    ref = (conv + coef * 1e3 * torch.einsum('nhwc,ncd->nhwd', Fd, G.cpu().double())) * (Fd > 0)
+    scale = ref.abs().max().item()
+    assert (got - ref).abs().max().item() <= TOL * scale, ((got - ref).abs().max().item(), scale)
+    assert (got - want).abs().max().item() <= TOL * scale, ((got - want).abs().max().item(), scale)
