@@ -351,6 +351,12 @@ int lnst_conv3x3_pool_bf16x3_tc(const void* x, const void* w_packed2, const floa
  * accumulates both products); otherwise the convolution followed by lnst_gram_bwd_bf16x3_tc.  styler_base.py:98-109. */
 int lnst_conv3x3_gram_bf16x3_tc(const void* x, const void* w_packed2, const void* F, const void* Gd2s, void* y, int32_t n,
                                 int32_t H, int32_t W, int32_t Cin, int32_t Cout, void* stream);
+/* Data gradient through a 3x3 convolution whose input is a 2x2 average pool's output, written at the pool's INPUT level:
+ * g_fine [n,2H,2W,2*Cout] = lnst_avgpool2_bf16x3_bwd(lnst_conv3x3_bf16x3_tc(x, ...), mask = fine_act), bit-identical, from
+ * the convolution's epilogue (vgg.py:96,102).  H, W = the coarse level.  LNST_EARG when the layer's weights are resident in
+ * shared memory (9 * 2*Cin * Cout * 2 B fit): then call the two separately. */
+int lnst_conv3x3_unpool_bf16x3_tc(const void* x, const void* w_packed2, const void* fine_act, void* g_fine, int32_t n,
+                                  int32_t H, int32_t W, int32_t Cin, int32_t Cout, void* stream);
 /* lnst_gram_diff_bf16x3_tc with Gd2 = split(gd_scale * G); gd_scale != 1 needs C % 128 == 0. */
 int lnst_gram_diff_scaled_bf16x3_tc(const void* F, int32_t n, int64_t P, int32_t C, float denom, const float* Gs,
                                     float weight, float gd_scale, float* G2, float* G, void* Gd2, float* loss, void* stream);

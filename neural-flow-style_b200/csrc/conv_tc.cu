@@ -667,13 +667,16 @@ template <int BLOCK_N> struct HaloStage { static constexpr int nv = 4; static co
 // this data gradient lands on (vgg.py style layers; styler_base.py:98-109) -- from the layer's own features F (same
 // pixels: the centre tap of an F patch) and the per-image matrix Gd (pre-scaled by the loss coefficient), so the separate
 // per-pixel GEMM with its read-modify-write of the whole gradient tensor disappears.  s.gram_kc = C_F / 64.
-template <int BLOCK_N, bool OUT3, bool RES, bool POOL = false, bool GRAM = false>
+// UPS: the output is the gradient of a 2x2 average pool's OUTPUT; the epilogue writes the pool's INPUT gradient instead
+// (lnst_avgpool2_bf16x3_bwd: 0.25 * value to the four pixels of the quad, each under the ReLU mask of the layer below),
+// through a transposed shared-memory tile so that 4 lanes cover 64 contiguous bytes of a row.  Even H and W at the fine level.
+template <int BLOCK_N, bool OUT3, bool RES, bool POOL = false, bool GRAM = false, bool UPS = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv3x3_halo_k(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                const float* __restrict__ bias, const __nv_bfloat16* __restrict__ mask,
                __nv_bfloat16* __restrict__ y, float* __restrict__ y3, ConvShape s, HaloCfg cfg,
                __nv_bfloat16* __restrict__ ypool, const __grid_constant__ CUtensorMap map_f,
-               const __grid_constant__ CUtensorMap map_g) {
+               const __grid_constant__ CUtensorMap map_g, const __nv_bfloat16* __restrict__ ups_mask) {
   constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
   // accumulator ring in TMEM: the round trip MMA-complete -> tfull -> epilogue -> tempty -> next MMA costs about
   // 4000 cycles (measured: with two buffers every tile took >= 2000 cycles even with 1/9 of the MMAs and no
@@ -981,7 +984,61 @@ conv3x3_halo_k(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                 *reinterpret_cast<uint4*>(dstp + s.Cout) = pl4;
               }
             }
-            if (BLOCK_N < 128) {                                     // narrow tiles: the direct stores keep up with the MMAs
+            if (UPS && NV == 4) {
+              // (hi + lo) * 0.25 per value, like the stand-alone kernel; y is the FINE-level gradient [n, 2H, 2W, 2 Cout]
+              const uint32_t stg = stage_base + (uint32_t)q * 4096u;
+#pragma unroll
+              for (int jj = 0; jj < NV; ++jj) {
+                const __nv_bfloat162* oh = reinterpret_cast<const __nv_bfloat162*>(&ov[jj]);
+                const __nv_bfloat162* ohl = reinterpret_cast<const __nv_bfloat162*>(&ol[jj]);
+                float fr[8];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 h = __bfloat1622float2(oh[e]), l = __bfloat1622float2(ohl[e]);
+                  fr[2 * e] = (h.x + l.x) * 0.25f;
+                  fr[2 * e + 1] = (h.y + l.y) * 0.25f;
+                }
+                st_shared_v4(stg + lane * 128 + ((uint32_t)(((2 * jj) ^ lane) & 7) << 4),
+                             make_uint4(__float_as_uint(fr[0]), __float_as_uint(fr[1]), __float_as_uint(fr[2]), __float_as_uint(fr[3])));
+                st_shared_v4(stg + lane * 128 + ((uint32_t)(((2 * jj + 1) ^ lane) & 7) << 4),
+                             make_uint4(__float_as_uint(fr[4]), __float_as_uint(fr[5]), __float_as_uint(fr[6]), __float_as_uint(fr[7])));
+              }
+              __syncwarp();
+              const int sub = lane >> 2, pj = lane & 3;
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int row = i * 8 + sub, rr = q * 32 + row;
+                const int plh = th * HTH + (rr >> 3), plw = tw * HTW + (rr & 7);
+                const uint4 x0 = ld_shared_v4(stg + row * 128 + ((uint32_t)(((2 * pj) ^ row) & 7) << 4));
+                const uint4 x1 = ld_shared_v4(stg + row * 128 + ((uint32_t)(((2 * pj + 1) ^ row) & 7) << 4));
+                const float xv[8] = {__uint_as_float(x0.x), __uint_as_float(x0.y), __uint_as_float(x0.z), __uint_as_float(x0.w),
+                                     __uint_as_float(x1.x), __uint_as_float(x1.y), __uint_as_float(x1.z), __uint_as_float(x1.w)};
+                if (plh < s.H && plw < s.W) {
+                  const int co = n0 + ck * 32 + pj * 8;
+                  uint4 mv[4];
+                  int64_t off[4];
+#pragma unroll
+                  for (int qd = 0; qd < 4; ++qd) {
+                    off[qd] = ((((int64_t)img * 2 * s.H + 2 * plh + (qd >> 1)) * (2 * s.W)) + 2 * plw + (qd & 1)) * s.ldy + co;
+                    mv[qd] = *reinterpret_cast<const uint4*>(ups_mask + off[qd]);      // hi half carries the sign
+                  }
+#pragma unroll
+                  for (int qd = 0; qd < 4; ++qd) {
+                    const __nv_bfloat16* mh = reinterpret_cast<const __nv_bfloat16*>(&mv[qd]);
+                    uint4 oh4, ol4;
+                    __nv_bfloat162* a = reinterpret_cast<__nv_bfloat162*>(&oh4);
+                    __nv_bfloat162* b = reinterpret_cast<__nv_bfloat162*>(&ol4);
+#pragma unroll
+                    for (int e = 0; e < 8; e += 2)
+                      split2(__bfloat162float(mh[e]) > 0.f ? xv[e] : 0.f, __bfloat162float(mh[e + 1]) > 0.f ? xv[e + 1] : 0.f,
+                             a[e >> 1], b[e >> 1]);
+                    *reinterpret_cast<uint4*>(y + off[qd]) = oh4;
+                    *reinterpret_cast<uint4*>(y + off[qd] + s.Cout) = ol4;
+                  }
+                }
+              }
+              __syncwarp();
+            } else if (BLOCK_N < 128) {                              // narrow tiles: the direct stores keep up with the MMAs
               if (valid) {
                 __nv_bfloat16* dst = y + pix * s.ldy + n0 + ck * NV * 8;
 #pragma unroll
@@ -1513,10 +1570,12 @@ template <int BLOCK_N, bool OUT3>
 static int launch_halo(const void* x, const void* wmat, const float* bias, const __nv_bfloat16* mask,
                        __nv_bfloat16* y, float* y3, int n, int H, int W, int Cin, int Cout, int relu, float scale,
                        cudaStream_t stream, int out_ch = 3, int split = 0, __nv_bfloat16* ypool = nullptr,
-                       const void* gram_f = nullptr, const void* gram_g = nullptr, int* gram_fused = nullptr) {
+                       const void* gram_f = nullptr, const void* gram_g = nullptr, int* gram_fused = nullptr,
+                       const __nv_bfloat16* ups_mask = nullptr) {
   constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
   constexpr int MAX_SMEM = 232448;                        // 227 KiB opt-in limit per CTA
-  const int budget = MAX_SMEM - 2048 - 1024 - 512 - HaloStage<BLOCK_N>::bytes - 128;   // static bias table, alignment slack, barriers, store staging
+  const int stage_bytes = ups_mask ? 4 * 4096 : HaloStage<BLOCK_N>::bytes;             // UPS: fp32 chunks, 4 KiB per epilogue warp
+  const int budget = MAX_SMEM - 2048 - 1024 - 512 - stage_bytes - 128;   // static bias table, alignment slack, barriers, store staging
   ConvShape s;
   s.H = H; s.W = W; s.Cin = Cin; s.Cout = Cout; s.relu = relu; s.taps = 9; s.w_img = 0; s.scale = scale; s.out_ch = out_ch;
   s.TH = HTH; s.TW = HTW;
@@ -1539,7 +1598,7 @@ static int launch_halo(const void* x, const void* wmat, const float* bias, const
   if (cfg.sa > 6) cfg.sa = 6;
   if (cfg.sa < 2) return LNST_EARG;
   const int n_wslots = cfg.sb == 0 ? 9 * kchunks : cfg.sb;
-  const int smem = cfg.sa * PATCH_STRIDE + n_wslots * B_BYTES + 8 * (2 * cfg.sa + 2 * (cfg.sb ? cfg.sb : 1) + 16) + 16 + 1024 + HaloStage<BLOCK_N>::bytes + 128;
+  const int smem = cfg.sa * PATCH_STRIDE + n_wslots * B_BYTES + 8 * (2 * cfg.sa + 2 * (cfg.sb ? cfg.sb : 1) + 16) + 16 + 1024 + stage_bytes + 128;
   CUtensorMap mx, mw;
   {
     const cuuint64_t dims[4] = {(cuuint64_t)xC, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n};
@@ -1570,6 +1629,19 @@ static int launch_halo(const void* x, const void* wmat, const float* bias, const
   }
   const int grid = cfg.n_tiles < sms ? cfg.n_tiles : sms;
   if (gram_fused) *gram_fused = 0;
+  if constexpr (!OUT3) if (ups_mask != nullptr) {
+    if (!split || cfg.sb == 0 || ypool != nullptr || gram_f != nullptr) return LNST_EARG;   // streamed-weight layers only
+    static bool uconfigured = false;
+    if (!uconfigured) {
+      cudaError_t e = cudaFuncSetAttribute(conv3x3_halo_k<BLOCK_N, false, false, false, false, true>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM - 2048);
+      if (e != cudaSuccess) return (int)e;
+      uconfigured = true;
+    }
+    conv3x3_halo_k<BLOCK_N, false, false, false, false, true><<<grid, NUM_THREADS, smem, stream>>>(
+        mx, mw, bias, mask, y, y3, s, cfg, nullptr, mx, mw, ups_mask);
+    return (int)cudaGetLastError();
+  }
   if constexpr (!OUT3 && BLOCK_N == 128) if (gram_f != nullptr && gram_g != nullptr && split && cfg.sb != 0 && ypool == nullptr) {
     // Gram-loss gradient of the layer this data gradient lands on, accumulated by the same tiles (features F and the
     // pre-scaled per-image matrix Gd: Cout logical channels each)
@@ -1596,7 +1668,7 @@ static int launch_halo(const void* x, const void* wmat, const float* bias, const
     }
     s.gram_kc = Cout / 64;
     conv3x3_halo_k<BLOCK_N, false, false, false, true><<<grid, NUM_THREADS, smem, stream>>>(mx, mw, bias, mask, y, y3, s, cfg,
-                                                                                          nullptr, mf, mg);
+                                                                                          nullptr, mf, mg, nullptr);
     if (gram_fused) *gram_fused = 1;
     return (int)cudaGetLastError();
   }
@@ -1617,15 +1689,15 @@ static int launch_halo(const void* x, const void* wmat, const float* bias, const
       pconfigured = true;
     }
     if (cfg.sb == 0)
-      conv3x3_halo_k<BLOCK_N, false, true, true><<<grid, NUM_THREADS, smem, stream>>>(mx, mw, bias, mask, y, y3, s, cfg, ypool, mx, mw);
+      conv3x3_halo_k<BLOCK_N, false, true, true><<<grid, NUM_THREADS, smem, stream>>>(mx, mw, bias, mask, y, y3, s, cfg, ypool, mx, mw, nullptr);
     else
-      conv3x3_halo_k<BLOCK_N, false, false, true><<<grid, NUM_THREADS, smem, stream>>>(mx, mw, bias, mask, y, y3, s, cfg, ypool, mx, mw);
+      conv3x3_halo_k<BLOCK_N, false, false, true><<<grid, NUM_THREADS, smem, stream>>>(mx, mw, bias, mask, y, y3, s, cfg, ypool, mx, mw, nullptr);
     return (int)cudaGetLastError();
   }
   if (cfg.sb == 0)
-    conv3x3_halo_k<BLOCK_N, OUT3, true><<<grid, NUM_THREADS, smem, stream>>>(mx, mw, bias, mask, y, y3, s, cfg, ypool, mx, mw);
+    conv3x3_halo_k<BLOCK_N, OUT3, true><<<grid, NUM_THREADS, smem, stream>>>(mx, mw, bias, mask, y, y3, s, cfg, ypool, mx, mw, nullptr);
   else
-    conv3x3_halo_k<BLOCK_N, OUT3, false><<<grid, NUM_THREADS, smem, stream>>>(mx, mw, bias, mask, y, y3, s, cfg, ypool, mx, mw);
+    conv3x3_halo_k<BLOCK_N, OUT3, false><<<grid, NUM_THREADS, smem, stream>>>(mx, mw, bias, mask, y, y3, s, cfg, ypool, mx, mw, nullptr);
   return (int)cudaGetLastError();
 }
 
@@ -2323,7 +2395,7 @@ extern "C" int lnst_tc_supported(void) { return tc::encode_fn() != nullptr ? 1 :
 static int run_tc_gemm(const void* x, const void* wmat, const float* bias, const void* mask, const void* addend,
                        void* y, int n, int H, int W, int Cin, int Cout, int relu, int taps, int w_img, float scale,
                        void* stream, int split = 0, void* ypool = nullptr, const void* gram_f = nullptr,
-                       const void* gram_g = nullptr, int* gram_fused = nullptr) {
+                       const void* gram_g = nullptr, int* gram_fused = nullptr, const void* ups_mask = nullptr) {
   using namespace tc;
   if (!x || !wmat || !y || n < 1 || H < 1 || W < 1 || Cin < 64 || Cout < 64 || Cin % 64 || Cout % 64)
     return LNST_EARG;
@@ -2340,11 +2412,12 @@ static int run_tc_gemm(const void* x, const void* wmat, const float* bias, const
     if (Cout % 128 == 0)
       return launch_halo<128, false>(x, wmat, bias, (const __nv_bfloat16*)mask, (__nv_bfloat16*)y, nullptr, n, H, W,
                                      Cin, Cout, relu, scale, lnst_stream(stream), 3, split, (__nv_bfloat16*)ypool,
-                                     gram_f, gram_g, gram_fused);
+                                     gram_f, gram_g, gram_fused, (const __nv_bfloat16*)ups_mask);
     return launch_halo<64, false>(x, wmat, bias, (const __nv_bfloat16*)mask, (__nv_bfloat16*)y, nullptr, n, H, W, Cin,
-                                  Cout, relu, scale, lnst_stream(stream), 3, split, (__nv_bfloat16*)ypool);
+                                  Cout, relu, scale, lnst_stream(stream), 3, split, (__nv_bfloat16*)ypool, nullptr, nullptr,
+                                  nullptr, (const __nv_bfloat16*)ups_mask);
   }
-  if (ypool) return LNST_EARG;
+  if (ypool || ups_mask) return LNST_EARG;
   if (split && (!conv_persistent || taps != 1)) return LNST_EARG;    // split operands: halo kernel, or the persistent per-pixel GEMM
   ConvShape s;
   s.H = H; s.W = W; s.Cin = Cin; s.Cout = Cout; s.relu = relu;
@@ -2399,6 +2472,17 @@ extern "C" int lnst_conv3x3_gram_bf16x3_tc(const void* x, const void* w_packed, 
                        &fused);
   if (rc != 0 || fused) return rc;
   return run_tc_gemm(F, Gd2s, nullptr, F, y, y, n, H, W, Cout, Cout, 0, 1, 1, 1.0f, stream, 1);
+}
+
+// Data gradient through a 3x3 convolution whose INPUT is the output of a 2x2 average pool: the epilogue writes the gradient
+// of the pool's input, g_fine [n, 2H, 2W, 2*Cout] = 0.25 * g under the ReLU mask of the layer below the pool (fine_act, same
+// shape) -- lnst_conv3x3_bf16x3_tc followed by lnst_avgpool2_bf16x3_bwd, bit-identical.  H, W: the coarse level.  Returns
+// LNST_EARG when the layer's weights are resident in shared memory (no room for the staging tile): call the two separately.
+extern "C" int lnst_conv3x3_unpool_bf16x3_tc(const void* x, const void* w_packed, const void* fine_act, void* g_fine,
+                                             int32_t n, int32_t H, int32_t W, int32_t Cin, int32_t Cout, void* stream) {
+  if (!fine_act || !g_fine) return LNST_EARG;
+  return run_tc_gemm(x, w_packed, nullptr, nullptr, nullptr, g_fine, n, H, W, Cin, Cout, 0, 9, 0, 1.0f, stream, 1, nullptr,
+                     nullptr, nullptr, nullptr, fine_act);
 }
 
 // The same convolution, with the 2x2 average pool of its output (lnst_avgpool2_bf16x3_fwd) written by the same epilogue:

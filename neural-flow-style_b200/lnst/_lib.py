@@ -132,6 +132,7 @@ CUDA_ONLY = {
     'lnst_conv3x3_bf16x3_tc': [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp],
     'lnst_conv3x3_pool_bf16x3_tc': [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp],
     'lnst_conv3x3_gram_bf16x3_tc': [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp],
+    'lnst_conv3x3_unpool_bf16x3_tc': [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp],
     'lnst_gram_diff_scaled_bf16x3_tc': [vp, i32, i64, i32, f32, vp, f32, f32, vp, vp, vp, vp, vp],
     'lnst_gram_diff_bf16x3_tc': [vp, i32, i64, i32, f32, vp, f32, vp, vp, vp, vp, vp],
     'lnst_gram_bwd_bf16x3_tc': [vp, vp, f32, vp, i32, vp, i32, i32, i32, i32, vp],

@@ -773,6 +773,17 @@ def gram_diff_bf16x3_tc(F, denom, Gs, weight, loss, gd_scale=1.0):
     return G, Gd2
 
 
+def conv3x3_unpool_bf16x3_tc(x, w_packed2, fine_act):
+    """data gradient through a conv whose input is a 2x2 average pool's output, written at the pool's input level under the
+    ReLU mask ``fine_act`` [n,2H,2W,2*Cout] -> g_fine (same shape)"""
+    n, H, W, c2 = x.shape
+    cout = w_packed2.shape[1]
+    g_fine = torch.empty_like(fine_act)
+    _lib.get().call('lnst_conv3x3_unpool_bf16x3_tc', ptr(x), ptr(w_packed2), ptr(fine_act), ptr(g_fine), n, H, W, c2 // 2, cout,
+                    _s(x))
+    return g_fine
+
+
 def conv3x3_gram_bf16x3_tc(x, w_packed2, F, Gd2s):
     """relu_mask(F) * (x (*) w + F x Gd2s): a data gradient and the Gram-loss gradient of the layer it lands on -> split y"""
     n, H, W, c2 = x.shape

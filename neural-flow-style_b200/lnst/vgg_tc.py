@@ -37,6 +37,9 @@ class TensorCoreConvs:
     fuse_pool = True                                     # conv + 2x2 average pool from one epilogue (split mode)
     gray_dot = None                                      # (image, dots): set by the styler for ONE backward pass
     gray_dot_done = False
+    # a pool's backward written by the data-gradient convolution above it: bit-identical, but the epilogue then writes four
+    # masked pixels per accumulator row and outlasts the tile's MMAs (+4..17 us per step at C3): opt-in
+    fuse_unpool = False
     fuse_gram = True                                     # Gram-loss gradient accumulated by the data-gradient convolution above it
 
     def __init__(self, net, split=False):
@@ -109,11 +112,15 @@ class TensorCoreConvs:
 
     def backward(self, x, acts, layers, add_loss_grad, loss_layers, gray=False):
         g = None                                   # bf16 gradient of the current end point
+        unpooled = False                           # the pool below was already handled by the convolution above it
         for i in range(len(layers) - 1, -1, -1):
             name = layers[i]
             if name in loss_layers:
                 g = add_loss_grad(name, g)
             if g is None:
+                continue
+            if unpooled:                           # `name` is that pool: g is already the gradient of its input
+                unpooled = False
                 continue
             prev = layers[i - 1] if i > 0 else None
             prev_act = acts.raw[prev] if prev is not None else None
@@ -124,6 +131,10 @@ class TensorCoreConvs:
                     # the Gram-loss gradient of `prev` joins this data gradient inside the kernel (same ReLU mask)
                     g = ops.conv3x3_gram_bf16x3_tc(g, self.wdp[name], prev_act, self._gram_pending.pop(prev))
                     self._gram_done.add(prev)
+                elif name in self.wdp and prev is not None and sp and self._can_unpool(layers, i, acts, g, loss_layers):
+                    # data gradient + the average pool's backward + the ReLU mask below it from one epilogue
+                    g = ops.conv3x3_unpool_bf16x3_tc(g, self.wdp[name], acts.raw[layers[i - 2]])
+                    unpooled = True
                 elif name in self.wdp and prev is not None:
                     g = (ops.conv3x3_bf16x3_tc if sp else ops.conv3x3_bf16_tc)(g, self.wdp[name], None, relu=False, mask=mask)
                 elif prev is None and gray and tuple(self.net.w[name].shape[2:]) == (3, 64):
@@ -150,6 +161,22 @@ class TensorCoreConvs:
             else:
                 g = (ops.avgpool2_bf16x3_bwd if sp else ops.avgpool2_bf16_bwd)(g, mask, prev_act.shape)
         return g
+
+    def _can_unpool(self, layers, i, acts, g, loss_layers):
+        """conv layer i sits on a 2x2 average pool whose input is a conv layer's (ReLU) output with even extents, the pool's
+        output carries no loss term of its own, and the layer's weights stream through shared memory (the kernel has
+        no room for the staging tile next to resident weights)."""
+        if not self.fuse_unpool or i < 2 or not layers[i - 1].startswith('pool') or not layers[i - 2].startswith('conv'):
+            return False
+        if layers[i - 1] in loss_layers:
+            return False
+        fine = acts.raw[layers[i - 2]]
+        if fine.dtype != torch.bfloat16 or fine.shape[1] != 2 * g.shape[1] or fine.shape[2] != 2 * g.shape[2]:
+            return False
+        cin, cout = g.shape[3] // 2, fine.shape[3] // 2
+        bn = 128 if cout % 128 == 0 else 64
+        resident = cout == bn and 9 * (2 * cin // 64) * bn * 128 + 3 * 23552 <= 232448 - 2048 - 1024 - 512 - 16384 - 128
+        return not resident
 
     # ---- losses -------------------------------------------------------------------------------------
     def gram(self, acts, name, Gs, weight, loss):

@@ -262,3 +262,18 @@ def test_data_gradient_with_fused_gram_gradient(n, H, W, cin, cout):
     scale = ref.abs().max().item()
     assert (got - ref).abs().max().item() <= TOL * scale, ((got - ref).abs().max().item(), scale)
     assert (got - want).abs().max().item() <= TOL * scale, ((got - want).abs().max().item(), scale)
+
+
+@pytest.mark.parametrize('n,H,W,cin,cout', [(2, 10, 12, 128, 64), (1, 25, 25, 256, 128), (3, 17, 9, 128, 128), (9, 100, 100, 128, 64)])
+def test_data_gradient_with_fused_pool_backward_is_bit_identical(n, H, W, cin, cout):
+    """lnst_conv3x3_unpool_bf16x3_tc = the data-gradient convolution, then the 2x2 average pool's backward under the ReLU
+    mask of the layer below the pool."""
+    dev = torch.device('cuda:0')
+    g = torch.Generator().manual_seed(H * 3 + cin)
+    x = ops.to_split(torch.randn(n, H, W, cin, generator=g).to(dev))
+    w = _pack2(torch.randn(3, 3, cin, cout, generator=g) * 0.05).to(dev)
+    fine = ops.to_split(torch.relu(torch.randn(n, 2 * H, 2 * W, cout, generator=g)).to(dev))
+    y = ops.conv3x3_bf16x3_tc(x, w, None, relu=False)
+    want = ops.avgpool2_bf16x3_bwd(y, fine, fine.shape)
+    got = ops.conv3x3_unpool_bf16x3_tc(x, w, fine)
+    assert got.shape == want.shape and torch.equal(got, want)

@@ -33,6 +33,8 @@ def main():
         elif a.switch.startswith('lib:'):                   # default library (1) against a variant build (0)
             _lib.set_for_testing(None if on else _lib.Lib(os.path.join(ROOT, a.switch[4:]), 'cuda'))
             ctx.lib = _lib.get()
+        elif a.switch == 'fuse_unpool':
+            vgg_tc.TensorCoreConvs.fuse_unpool = bool(on)
         elif a.switch == 'fuse_gram':
             vgg_tc.TensorCoreConvs.fuse_gram = bool(on)
         elif a.switch == 'fuse_glue':
