@@ -155,10 +155,34 @@ __global__ void fill_box_k(float* __restrict__ vol, int H, int W, SubVol sv, flo
   vol[((int64_t)z * H + y) * W + x] = value;
 }
 
+// one 16-byte piece of a row per thread: a float4 store where the piece lies inside the box, scalar stores at its x edges
+__global__ void fill_box4_k(float* __restrict__ vol, int H, int W, SubVol sv, int x4lo, int nx4, float value) {
+  const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (unsigned)(sv.ez * sv.ey * nx4)) return;
+  const unsigned q = t / (unsigned)nx4, zq = q / (unsigned)sv.ey;
+  const int x = (x4lo + (int)(t - q * (unsigned)nx4)) * 4, y = sv.oy + (int)(q - zq * (unsigned)sv.ey);
+  const int z = sv.oz + (int)zq;
+  float* p = vol + ((int64_t)z * H + y) * W + x;
+  if (x >= sv.ox && x + 3 < sv.ox + sv.ex) {
+    *reinterpret_cast<float4*>(p) = make_float4(value, value, value, value);
+  } else {
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      if (x + e >= sv.ox && x + e < sv.ox + sv.ex) p[e] = value;
+  }
+}
+
 extern "C" int lnst_fill_box(float* vol, int32_t D, int32_t H, int32_t W, const LnstBox* box, float value,
                              void* stream) {
   if (!vol || D < 1 || H < 1 || W < 1 || !box_ok(box, D, H, W)) return LNST_EARG;
   const SubVol sv = make_subvol(box, D, H, W);
+  if (W % 4 == 0 && (reinterpret_cast<uintptr_t>(vol) & 15u) == 0) {
+    const int x4lo = sv.ox / 4, nx4 = (sv.ox + sv.ex + 3) / 4 - x4lo;
+    const int64_t total4 = (int64_t)sv.ez * sv.ey * nx4;
+    LNST_LAUNCH(fill_box4_k, dim3(lnst_blocks(total4, 256)), dim3(256), 0, lnst_stream(stream), vol, (int)H, (int)W, sv,
+                x4lo, nx4, value);
+    return lnst_status();
+  }
   const int64_t total = (int64_t)sv.ez * sv.ey * sv.ex;
   LNST_LAUNCH(fill_box_k, dim3(lnst_blocks(total, 256)), dim3(256), 0, lnst_stream(stream), vol, (int)H, (int)W, sv,
               value);

@@ -72,6 +72,37 @@ __global__ void adam_iterate_dev_k(float* __restrict__ g_opt, const float* __res
   if (apply) g_opt[i] = x + d;
 }
 
+// the same, four elements per thread (16-byte accesses; n % 4 == 0, 16-byte aligned arrays)
+__global__ void adam_iterate_dev4_k(float* __restrict__ g_opt, const float* __restrict__ grad, float* __restrict__ m,
+                                    float* __restrict__ v, int64_t n, const float* __restrict__ state, float b1,
+                                    float b2, float eps, float gscale, const float* __restrict__ mask, int width,
+                                    int mask_stride, float* __restrict__ var_out, float* __restrict__ delta,
+                                    int apply) {
+  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i >= n) return;
+  const float lr_t = state[2];
+  const float4 x4 = *reinterpret_cast<const float4*>(g_opt + i), g4 = *reinterpret_cast<const float4*>(grad + i);
+  const float4 m4 = *reinterpret_cast<const float4*>(m + i), v4 = *reinterpret_cast<const float4*>(v + i);
+  const float x[4] = {x4.x, x4.y, x4.z, x4.w}, gg[4] = {g4.x, g4.y, g4.z, g4.w};
+  const float mo[4] = {m4.x, m4.y, m4.z, m4.w}, vo[4] = {v4.x, v4.y, v4.z, v4.w};
+  float mi[4], vi[4], var[4], d[4], xn[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float g = gg[e] * gscale;
+    mi[e] = mo[e] + (g - mo[e]) * (1.f - b1);
+    vi[e] = vo[e] + (g * g - vo[e]) * (1.f - b2);
+    var[e] = x[e] - lr_t * mi[e] / (sqrtf(vi[e]) + eps);
+    d[e] = lnst_nan_to_num(var[e]) - x[e];
+    if (mask) d[e] *= mask[((i + e) / width) * mask_stride];
+    xn[e] = x[e] + d[e];
+  }
+  *reinterpret_cast<float4*>(m + i) = make_float4(mi[0], mi[1], mi[2], mi[3]);
+  *reinterpret_cast<float4*>(v + i) = make_float4(vi[0], vi[1], vi[2], vi[3]);
+  *reinterpret_cast<float4*>(var_out + i) = make_float4(var[0], var[1], var[2], var[3]);
+  *reinterpret_cast<float4*>(delta + i) = make_float4(d[0], d[1], d[2], d[3]);
+  if (apply) *reinterpret_cast<float4*>(g_opt + i) = make_float4(xn[0], xn[1], xn[2], xn[3]);
+}
+
 __global__ void iterate_accumulate_k(float* __restrict__ acc, const float* __restrict__ var, int64_t n, int first) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -204,7 +235,14 @@ extern "C" int lnst_adam_iterate_dev(float* g_opt, const float* grad, float* m, 
                                      void* stream) {
   if (!state || n < 0 || width < 1 || (n > 0 && (!g_opt || !grad || !m || !v || !var_out || !delta))) return LNST_EARG;
   LNST_LAUNCH(adam_tick_k, dim3(1), dim3(32), 0, lnst_stream(stream), state, lr, beta1, beta2);
-  if (n > 0)
+  const bool vec4 = n % 4 == 0 && ((reinterpret_cast<uintptr_t>(g_opt) | reinterpret_cast<uintptr_t>(grad) |
+                                    reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v) |
+                                    reinterpret_cast<uintptr_t>(var_out) | reinterpret_cast<uintptr_t>(delta)) & 15u) == 0;
+  if (n > 0 && vec4)
+    LNST_LAUNCH(adam_iterate_dev4_k, dim3(lnst_blocks(n / 4, 256)), dim3(256), 0, lnst_stream(stream), g_opt, grad, m, v,
+                n, (const float*)state, beta1, beta2, eps, gscale, mask, (int)width, (int)mask_stride, var_out, delta,
+                (int)apply);
+  else if (n > 0)
     LNST_LAUNCH(adam_iterate_dev_k, dim3(lnst_blocks(n, 256)), dim3(256), 0, lnst_stream(stream), g_opt, grad, m, v,
                 n, (const float*)state, beta1, beta2, eps, gscale, mask, (int)width, (int)mask_stride, var_out, delta,
                 (int)apply);
