@@ -35,6 +35,8 @@ def main():
             ctx.lib = _lib.get()
         elif a.switch == 'fuse_unpool':
             vgg_tc.TensorCoreConvs.fuse_unpool = bool(on)
+        elif a.switch.startswith('slab'):                   # slab8 / slab16 against the default 12 planes
+            lib.call('lnst_set_raymarch_slab', 12 if on else int(a.switch[4:]))
         elif a.switch == 'fuse_gram':
             vgg_tc.TensorCoreConvs.fuse_gram = bool(on)
         elif a.switch == 'fuse_glue':
