@@ -136,6 +136,32 @@ __device__ __forceinline__ void umma_bf16_lh(uint32_t tmem_d, uint32_t alo, uint
       "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
       "}" ::"r"(tmem_d), "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "r"(accumulate) : "memory");
 }
+// The same MMA with the A operand kept in / taken from the collector buffer: two consecutive MMAs that share their A
+// slice (x_hi * W_hi, then x_hi * W_lo in the bf16x3 K loop) read it from shared memory once (SASS: A_KEEP / A_REUSE).
+__device__ __forceinline__ void umma_bf16_lh_keep(uint32_t tmem_d, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi,
+                                                  uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16.collector::a::fill [%0], da, db, %5, p;\n\t"
+      "}" ::"r"(tmem_d), "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_lh_reuse(uint32_t tmem_d, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi,
+                                                   uint32_t idesc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, 1, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16.collector::a::lastuse [%0], da, db, %5, p;\n\t"
+      "}" ::"r"(tmem_d), "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc) : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -687,8 +713,12 @@ conv3x3_halo_k(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
   __shared__ __align__(16) float sbias[512];              // the layer's bias, read as broadcast float4s
   if (bias)
     for (int i = threadIdx.x; i < s.Cout && i < 512; i += blockDim.x) sbias[i] = bias[i];
-  const int kchunks = s.nchunks;
   constexpr bool resident = RES;                        // weights resident in smem (cfg.sb == 0) or streamed
+  // resident + split: 2 kc patch loads per tile (hi and lo of every channel group), the MMAs of a hi chunk in pairs that
+  // share their A slice through the collector buffer; streamed weights keep the three-pass order (their ring runs 8 taps
+  // ahead, and pairing two weight tiles per tap halves that distance: +25 us per step when it was tried there)
+  const bool pairs = resident && s.split;
+  const int kchunks = pairs ? 2 * s.kc : s.nchunks;
   const int n_wslots = resident ? 9 * s.wchunks : cfg.sb;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t smem_a = base;
@@ -737,10 +767,12 @@ conv3x3_halo_k(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
       const int th = rem / s.tiles_w, tw = rem - th * s.tiles_w;
       const int h0 = th * HTH, w0 = tw * HTW, n0 = nb * BLOCK_N;
       for (int c = 0; c < kchunks; ++c) {
+        // resident weights, split operands: hi_0, lo_0, hi_1, lo_1, ... (a hi chunk meets W_hi and W_lo back to back)
+        const int xc = pairs ? ((c & 1) ? s.kc + (c >> 1) : (c >> 1)) : xchunk(s, c);
         mbar_wait(bar_aempty + 8 * sta, pha ^ 1);
         if (leader) {
           mbar_expect_tx(bar_afull + 8 * sta, PATCH_BYTES);
-          tma_load_4d(smem_a + sta * PATCH_STRIDE, &map_x, bar_afull + 8 * sta, xchunk(s, c) * BLOCK_K, w0 - 1, h0 - 1, img);
+          tma_load_4d(smem_a + sta * PATCH_STRIDE, &map_x, bar_afull + 8 * sta, xc * BLOCK_K, w0 - 1, h0 - 1, img);
         }
         if (++sta == (uint32_t)cfg.sa) { sta = 0; pha ^= 1; }
         if (!resident) {
@@ -800,15 +832,31 @@ conv3x3_halo_k(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
           // kernel at ~2000 cycles per chunk whatever the MMA count (knock-out experiments)
           if (leader) {
             const uint32_t bstep = (uint32_t)s.wchunks * (B_BYTES >> 4);
-            uint32_t blo = blo_base + wchunk(s, c) * (B_BYTES >> 4);  // slot tap * wchunks + wchunk(c)
+            const int wc = pairs ? (c >> 1) : wchunk(s, c);            // W_hi chunk of this channel group
+            uint32_t blo = blo_base + wc * (B_BYTES >> 4);             // slot tap * wchunks + wc
+            if (pairs && !(c & 1)) {                                   // hi chunk: x_hi * W_hi, x_hi * W_lo
+              const uint32_t lo_off = (uint32_t)s.kc * (B_BYTES >> 4);
 #pragma unroll
-            for (int tap = 0; tap < 9; ++tap) {
-              const int ky = tap / 3, kx = tap - 3 * ky;               // compile-time after unrolling
-              const uint32_t alo = alo0 + ((ky * (HTW + 2) + kx) * 128 >> 4);
+              for (int tap = 0; tap < 9; ++tap) {
+                const int ky = tap / 3, kx = tap - 3 * ky;             // compile-time after unrolling
+                const uint32_t alo = alo0 + ((ky * (HTW + 2) + kx) * 128 >> 4);
 #pragma unroll
-              for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-                umma_bf16_lh(acc, alo + k * 2, ahi, blo + k * 2, bhi, idesc, (tap | k) != 0 ? 1u : (c != 0 ? 1u : 0u));
-              blo += bstep;
+                for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                  umma_bf16_lh_keep(acc, alo + k * 2, ahi, blo + k * 2, bhi, idesc, (tap | k) != 0 ? 1u : (c != 0 ? 1u : 0u));
+                  umma_bf16_lh_reuse(acc, alo + k * 2, ahi, blo + lo_off + k * 2, bhi, idesc);
+                }
+                blo += bstep;
+              }
+            } else {
+#pragma unroll
+              for (int tap = 0; tap < 9; ++tap) {
+                const int ky = tap / 3, kx = tap - 3 * ky;             // compile-time after unrolling
+                const uint32_t alo = alo0 + ((ky * (HTW + 2) + kx) * 128 >> 4);
+#pragma unroll
+                for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+                  umma_bf16_lh(acc, alo + k * 2, ahi, blo + k * 2, bhi, idesc, (tap | k) != 0 ? 1u : (c != 0 ? 1u : 0u));
+                blo += bstep;
+              }
             }
           }
         } else {
