@@ -61,7 +61,8 @@ MMA_PASSES = {'lnst_conv3x3_bf16x3_tc': 3, 'lnst_gram_bwd_bf16x3_tc': 3,
 # entry points that are the same kernel with one more output: timed and counted under the base name
 ALIASES = {'lnst_conv3x3_pool_bf16x3_tc': 'lnst_conv3x3_bf16x3_tc', 'lnst_raymarch_fwd_max_tma': 'lnst_raymarch_fwd_tma',
            'lnst_raymarch_fwd_max_box': 'lnst_raymarch_fwd_box', 'lnst_raymarch_bwd_norm_box': 'lnst_raymarch_bwd_box',
-           'lnst_conv_first_bwd_gray_dot_tc': 'lnst_conv_first_bwd_gray_x3_tc'}
+           'lnst_conv_first_bwd_gray_dot_tc': 'lnst_conv_first_bwd_gray_x3_tc',
+           'lnst_conv3x3_gram_bf16x3_tc': 'lnst_conv3x3_bf16x3_tc', 'lnst_gram_diff_scaled_bf16x3_tc': 'lnst_gram_diff_bf16x3_tc'}
 
 
 def make_cfg(wl, view_mode, conv_math):
@@ -105,6 +106,10 @@ def algorithmic_units(name, a, nk=2):
     if name == 'lnst_conv3x3_pool_bf16x3_tc':            # + the pooled copy of the output
         n, H, W, ci, co = [v(x) for x in a[6:11]]
         return (4 * n * H * W * (ci + co) + 4 * n * (H // 2) * (W // 2) * co + 4 * 9 * ci * co, 2 * n * H * W * 9 * ci * co)
+    if name == 'lnst_conv3x3_gram_bf16x3_tc':            # data gradient + F x Gd of the layer it lands on
+        n, H, W, ci, co = [v(x) for x in a[5:10]]
+        return (4 * n * H * W * (ci + 2 * co) + 4 * 9 * ci * co + 4 * n * co * co,
+                2 * n * H * W * 9 * ci * co + 2 * n * H * W * co * co)
     if name == 'lnst_conv_first_bwd_gray_dot_tc':
         n, H, W = [v(x) for x in a[6:9]]
         return (n * H * W * (8 + 256), 2 * n * H * W * 9 * 64)
