@@ -305,42 +305,6 @@ __global__ void splat_wavg_combine_box_k(const float* __restrict__ wmap, float* 
   out[c] = s;
 }
 
-// four x-consecutive cells per thread (16-byte loads / stores where the piece lies inside the box; nk <= LNST_MAX_NK)
-__global__ void splat_wavg_combine_box4_k(const float* __restrict__ wmap, float* __restrict__ num, int nk, int64_t cells,
-                                          int H, int W, SubVol sv, int x4lo, int nx4, float* __restrict__ out) {
-  const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= (unsigned)(sv.ez * sv.ey * nx4)) return;
-  const unsigned q = t / (unsigned)nx4, zq = q / (unsigned)sv.ey;
-  const int x = (x4lo + (int)(t - q * (unsigned)nx4)) * 4, y = sv.oy + (int)(q - zq * (unsigned)sv.ey);
-  const int z = sv.oz + (int)zq;
-  const int64_t c = ((int64_t)z * H + y) * W + x;
-  if (x >= sv.ox && x + 3 < sv.ox + sv.ex) {
-    float s[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int k = 0; k < nk; ++k) {
-      const float4 w4 = *reinterpret_cast<const float4*>(wmap + k * cells + c);
-      float4* np = reinterpret_cast<float4*>(num + k * cells + c);
-      const float4 v4 = *np;
-      if (v4.x != 0.f || v4.y != 0.f || v4.z != 0.f || v4.w != 0.f) *np = make_float4(0.f, 0.f, 0.f, 0.f);
-      const float w[4] = {w4.x, w4.y, w4.z, w4.w}, v[4] = {v4.x, v4.y, v4.z, v4.w};
-#pragma unroll
-      for (int e = 0; e < 4; ++e) s[e] += (w[e] > 1e-6f) ? v[e] / w[e] : v[e];          // transform.py:1703
-    }
-    *reinterpret_cast<float4*>(out + c) = make_float4(s[0], s[1], s[2], s[3]);
-  } else {
-    for (int e = 0; e < 4; ++e) {
-      if (x + e < sv.ox || x + e >= sv.ox + sv.ex) continue;
-      float s = 0.f;
-      for (int k = 0; k < nk; ++k) {
-        const float w = wmap[k * cells + c + e];
-        const float v = num[k * cells + c + e];
-        if (v != 0.f) num[k * cells + c + e] = 0.f;
-        s += (w > 1e-6f) ? v / w : v;
-      }
-      out[c + e] = s;
-    }
-  }
-}
-
 template <int DIM>
 __global__ void splat_wavg_bwd_k(const float* __restrict__ p, const float* __restrict__ var, int64_t n,
                                  LnstGrid g, SplatKernels ks, int nk, int64_t cells,
@@ -514,14 +478,6 @@ extern "C" int lnst_splat_wavg_fwd_box(const float* p, const float* r, const flo
   }
   if (box) {
     const SubVol sv = make_subvol(box, Dz, g->res[1], g->res[2]);
-    const int Wc = g->res[2];
-    if (Wc % 4 == 0 && cells % 4 == 0 && ((reinterpret_cast<uintptr_t>(wmap) | reinterpret_cast<uintptr_t>(num) |
-                                           reinterpret_cast<uintptr_t>(out)) & 15u) == 0) {
-      const int x4lo = sv.ox / 4, nx4 = (sv.ox + sv.ex + 3) / 4 - x4lo;
-      LNST_LAUNCH(splat_wavg_combine_box4_k, dim3(lnst_blocks((int64_t)sv.ez * sv.ey * nx4, T)), dim3(T), 0,
-                  lnst_stream(stream), wmap, num, (int)nk, cells, (int)g->res[1], Wc, sv, x4lo, nx4, out);
-      return lnst_status();
-    }
     LNST_LAUNCH(splat_wavg_combine_box_k, dim3(lnst_blocks((int64_t)sv.ez * sv.ey * sv.ex, T)), dim3(T), 0,
                 lnst_stream(stream), wmap, num, (int)nk, cells, (int)g->res[1], (int)g->res[2], sv, out);
     return lnst_status();

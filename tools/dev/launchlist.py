@@ -17,7 +17,7 @@ def main():
     data = rows[hdr + 1:]
     names = [r[ki] for r in data]
     times = [float(r[vi]) / 1000.0 for r in data]
-    idx = [i for i, n in enumerate(names) if 'adam_iterate_dev_k' in n]
+    idx = [i for i, n in enumerate(names) if 'adam_iterate_dev' in n]
     steps = [(idx[i - 1] + 1, idx[i] + 1) for i in range(1, len(idx))]
     x3 = [s for s in steps if any('split' in n for n in names[s[0]:s[1]])]
     lo, hi = x3[-1]

@@ -21,7 +21,7 @@ KERNEL_TO_ENTRY = [
     ('raymarch_rot_bwd_k', 'lnst_raymarch_bwd_box'), ('raymarch_fwd_tma_k', 'lnst_raymarch_fwd_tma'),
     ('smooth3_tma_k<1>', 'lnst_smooth3_relu_bwd_tma'), ('smooth3_tma_k<0>', 'lnst_smooth3_relu_fwd_tma'),
     ('splat_wavg_num3_k', 'lnst_splat_wavg_fwd_box'), ('splat_wavg_combine_box_k', 'lnst_splat_wavg_fwd_box'),
-    ('splat_wavg_bwd3_k', 'lnst_splat_wavg_bwd_coef'), ('adam_iterate_dev_k', 'lnst_adam_iterate_dev'),
+    ('splat_wavg_bwd3_k', 'lnst_splat_wavg_bwd_coef'), ('adam_iterate_dev', 'lnst_adam_iterate_dev'),
 ]
 
 
