@@ -4,7 +4,7 @@
 # are covered by memcheck only (racecheck does not model TMA / mbarrier traffic).  Logs land in gpurun_out/.
 python -c "import __graft_entry__ as g; g.build()" > /dev/null 2>&1
 mkdir -p gpurun_out
-SEL='tests/test_kernel_parity.py tests/test_widen_graphnet_kernels.py tests/test_widen_resim.py tests/test_widen_style_mask.py'
+SEL='tests/test_kernel_parity.py tests/test_widen_graphnet_kernels.py tests/test_widen_resim.py tests/test_widen_style_mask.py tests/test_r2_boundary.py tests/test_tc_x3_gpu.py tests/test_tma_gpu.py'
 timeout 1200 compute-sanitizer --tool memcheck --error-exitcode 9 --log-file gpurun_out/sanitizer_memcheck.log \
     python -m pytest $SEL -m gpu -q -x --timeout=900 > gpurun_out/sanitizer_memcheck_pytest.log 2>&1
 echo "memcheck rc=$?" > gpurun_out/sanitizer_summary.txt
