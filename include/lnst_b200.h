@@ -385,6 +385,14 @@ int lnst_bf16x3_to_f32(const void* x, float* y, int64_t rows, int32_t C, void* s
  * loss[0] += weight * sum(G^2).  F [P,C].  Gs NULL => G = F^T F / denom (style-target pass). */
 int lnst_gram_diff(const float* F, int64_t P, int32_t C, float denom, const float* Gs, float weight,
                    float* G, float* loss, void* stream);
+/* lnst_gram_diff with the denominator on the device: denom = den_scale * den_dev[0] when den_dev != NULL (`denom` is then
+ * unused).  The 3-D style mask's Gram denominators are 2 C * area(mask) with the mask = the current render
+ * (styler_base.py:165-169): reading the area back would break the step's CUDA graph. */
+int lnst_gram_diff_dev(const float* F, int64_t P, int32_t C, float denom, const float* den_dev, float den_scale,
+                       const float* Gs, float weight, float* G, float* loss, void* stream);
+/* out[i] = x[i] * num / (den_scale * den_dev[0]): folds a coefficient with a device-resident denominator into the small
+ * operand it multiplies (the Gram difference ahead of lnst_gram_bwd, a loss scalar ahead of lnst_rowdot). */
+int lnst_scale_by_dev(const float* x, int64_t n, float num, const float* den_dev, float den_scale, float* out, void* stream);
 /* g_F = (beta*g_F + coef * F G) [* (F > 0) when relu_mask: F is a post-ReLU conv output and
  * g_F becomes the gradient w.r.t. the pre-activation] */
 int lnst_gram_bwd(const float* F, const float* G, int64_t P, int32_t C, float coef, float beta,

@@ -43,8 +43,12 @@ __global__ void avgpool2_bwd_k(const float* __restrict__ gy, const float* __rest
 
 // ---- losses ------------------------------------------------------------------------------
 // G = G/denom - Gs ; loss += weight * sum(G^2)
+// den_dev (may be NULL): the denominator lives on the device, denom = den_scale * den_dev[0] (style mask: 2 C * area of
+// the mask, which depends on the render -- styler_base.py:165-169 -- and must not be read back inside a CUDA graph)
 __global__ void gram_finish_k(float* __restrict__ G, const float* __restrict__ Gs, int n, float inv_denom,
-                              float weight, float* __restrict__ loss) {
+                              float weight, float* __restrict__ loss, const float* __restrict__ den_dev,
+                              float den_scale) {
+  if (den_dev) inv_denom = 1.f / (den_scale * den_dev[0]);
   float s = 0.f;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     float d = G[i] * inv_denom;
@@ -153,9 +157,31 @@ extern "C" int lnst_avgpool2_bwd(const float* g_y, const float* mask, float* g_x
   return lnst_status();
 }
 
+// out[i] = x[i] * (num / (den_scale * den_dev[0])): a coefficient that depends on a device-resident denominator,
+// folded into the small operand it multiplies (the Gram difference, a loss scalar)
+__global__ void scale_by_dev_k(const float* __restrict__ x, int64_t n, float num, const float* __restrict__ den_dev,
+                               float den_scale, float* __restrict__ out) {
+  const float c = num / (den_scale * den_dev[0]);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = x[i] * c;
+}
+extern "C" int lnst_scale_by_dev(const float* x, int64_t n, float num, const float* den_dev, float den_scale, float* out,
+                                 void* stream) {
+  if (!x || !out || !den_dev || n < 1) return LNST_EARG;
+  const unsigned nb = lnst_blocks(n, 256) > 256 ? 256 : lnst_blocks(n, 256);
+  LNST_LAUNCH(scale_by_dev_k, dim3(nb), dim3(256), 0, lnst_stream(stream), x, n, num, den_dev, den_scale, out);
+  return lnst_status();
+}
+
 extern "C" int lnst_gram_diff(const float* F, int64_t P, int32_t C, float denom, const float* Gs, float weight,
                               float* G, float* loss, void* stream) {
-  if (!F || !G || P < 1 || C < 1 || !(denom > 0.f) || P > 0x7fffffff) return LNST_EARG;
+  return lnst_gram_diff_dev(F, P, C, denom, nullptr, 1.f, Gs, weight, G, loss, stream);
+}
+
+// lnst_gram_diff with the denominator on the device when den_dev != NULL: denom = den_scale * den_dev[0] (`denom` unused)
+extern "C" int lnst_gram_diff_dev(const float* F, int64_t P, int32_t C, float denom, const float* den_dev, float den_scale,
+                                  const float* Gs, float weight, float* G, float* loss, void* stream) {
+  if (!F || !G || P < 1 || C < 1 || (!den_dev && !(denom > 0.f)) || P > 0x7fffffff) return LNST_EARG;
   cudaStream_t s = lnst_stream(stream);
   cudaMemsetAsync(G, 0, sizeof(float) * (int64_t)C * C, s);
   TransposedA A{F, (int)C};
@@ -168,7 +194,7 @@ extern "C" int lnst_gram_diff(const float* F, int64_t P, int32_t C, float denom,
   int rc = run_sgemm(A, B, ep, C, C, (int)P, splits, s);
   if (rc) return rc;
   LNST_LAUNCH(gram_finish_k, dim3(lnst_blocks((int64_t)C * C, 256) > 64 ? 64 : lnst_blocks((int64_t)C * C, 256)),
-              dim3(256), 0, s, G, Gs, (int)(C * C), 1.f / denom, weight, loss);
+              dim3(256), 0, s, G, Gs, (int)(C * C), den_dev ? 0.f : 1.f / denom, weight, loss, den_dev, den_scale);
   return lnst_status();
 }
 

@@ -73,6 +73,8 @@ SIGNATURES = {
     'lnst_avgpool2_fwd': [vp, vp, i32, i32, i32, i32, vp],
     'lnst_avgpool2_bwd': [vp, vp, vp, i32, i32, i32, i32, vp],
     'lnst_gram_diff': [vp, i64, i32, f32, vp, f32, vp, vp, vp],
+    'lnst_gram_diff_dev': [vp, i64, i32, f32, vp, f32, vp, f32, vp, vp, vp],
+    'lnst_scale_by_dev': [vp, i64, f32, vp, f32, vp, vp],
     'lnst_gram_bwd': [vp, vp, i64, i32, f32, f32, i32, vp, vp],
     'lnst_content_loss': [vp, i64, i32, i32, f32, vp, vp, f32, i32, vp],
     'lnst_content_mse': [vp, vp, i64, f32, f32, vp, vp, f32, i32, vp],

@@ -344,10 +344,22 @@ def avgpool2_bwd(g_y, mask, shape, g_x=None):
 
 # ---- losses --------------------------------------------------------------------------------
 def gram_diff(F, denom, Gs, weight, G, loss):
-    """F [P,C] (one image).  G = F^T F/denom - Gs; loss += weight*sum(G^2)."""
+    """F [P,C] (one image).  G = F^T F/denom - Gs; loss += weight*sum(G^2).  ``denom``: a host number, or
+    (den_dev [1] device tensor, den_scale): denom = den_scale * den_dev[0], never read back."""
     P, ch = F.shape
-    _lib.get().call('lnst_gram_diff', ptr(F), P, ch, float(denom), ptr(Gs), float(weight), ptr(G), ptr(loss), _s(F))
+    if isinstance(denom, tuple):
+        _lib.get().call('lnst_gram_diff_dev', ptr(F), P, ch, 0.0, ptr(denom[0]), float(denom[1]), ptr(Gs), float(weight),
+                        ptr(G), ptr(loss), _s(F))
+    else:
+        _lib.get().call('lnst_gram_diff', ptr(F), P, ch, float(denom), ptr(Gs), float(weight), ptr(G), ptr(loss), _s(F))
     return G
+
+
+def scale_by_dev(x, num, den):
+    """x * num / (den_scale * den_dev[0]) with den = (den_dev [1] device tensor, den_scale) -> new tensor like x"""
+    out = torch.empty_like(x)
+    _lib.get().call('lnst_scale_by_dev', ptr(x), x.numel(), float(num), ptr(den[0]), float(den[1]), ptr(out), _s(x))
+    return out
 
 
 def gram_bwd(F, G, coef, beta, relu_mask, g_F):

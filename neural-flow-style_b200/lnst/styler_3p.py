@@ -107,7 +107,8 @@ class Styler(StylerBase):
         if self.style_mask:                                        # styler_base.py:165-169 with d_gray = the render
             if 'vgg' not in self.model_path:
                 raise NotImplementedError('style_mask with a GraphDef loss network')
-            self.cuda_graphs = False        # the masked areas (Gram denominators) are read back every step
+            # the masked areas (Gram denominators 2 C * area) stay on the device (lnst_gram_diff_dev, lnst_scale_by_dev):
+            # the step replays from a CUDA graph like the unmasked one
         self.rot_mat_, self.views = None, None
         if self.rotate:                                            # styler_3p.py:137-145
             self.rot_mat_, self.views = rot_mat(self.phi0, self.phi1, self.phi_unit, self.theta0, self.theta1,
@@ -488,7 +489,8 @@ class Styler(StylerBase):
         elif self.style_mask and self.w_style and style_grams is not None:
             # mask per style layer = TF-legacy bicubic resize of the render to the feature size; its cotangent comes
             # back through the same resize and joins the render's gradient
-            masks, mg, side = self.style_masks_for(st['gray0'], (st['x'].shape[1], st['x'].shape[2])), {}, None
+            masks, mg, side = self.style_masks_for(st['gray0'], (st['x'].shape[1], st['x'].shape[2]),
+                                                   device_areas=getattr(self, 'mask_areas_on_device', True)), {}, None
             if self.style_mask_on_ref:                             # :171-173: the target is masked by the same render
                 by_layer, side = self.masked_style_grams(masks, per_image=True)
                 style_grams = [by_layer[l] for l in self.style_layer]

@@ -199,10 +199,11 @@ class StylerBase(object):
         return feat
 
     # ---- feature-space losses + their gradient w.r.t. the net input ---------------------------------
-    def style_masks_for(self, d_gray, net_hw):
+    def style_masks_for(self, d_gray, net_hw, device_areas=False):
         """Per style layer: (m [n,h,w], area [n]) with m = d_gray resized to the layer's feature size by
-        TF's legacy bicubic (styler_base.py:165-169).  d_gray [n,H,W] must not depend on the optimised
-        variable (2-D colour mode); the areas are read back once, here."""
+        TF's legacy bicubic (styler_base.py:165-169).  The areas are read back once, here (2-D colour mode: d_gray does not
+        depend on the optimised variable) -- or, ``device_areas``, stay a device tensor (3-D: the mask is the current
+        render; the Gram kernels take their denominators from the device so that the step stays graph-capturable)."""
         out = {}
         for l in self.style_layer:
             h, w = net_hw
@@ -211,7 +212,8 @@ class StylerBase(object):
                 h, w = h // 2, w // 2
             m = ops.resize_bicubic_fwd(d_gray.reshape(d_gray.shape[0], d_gray.shape[1], d_gray.shape[2], 1).contiguous(),
                                        h, w)[..., 0].contiguous()
-            out[l] = (m, [float(a) for a in m.sum(dim=(1, 2)).cpu().tolist()])
+            area = m.sum(dim=(1, 2))
+            out[l] = (m, area.contiguous() if device_areas else [float(a) for a in area.cpu().tolist()])
         return out
 
     def image_loss_and_grad(self, x, d_img, style_grams, loss, style_masks=None, gray=None, mask_grads=None, group=False,

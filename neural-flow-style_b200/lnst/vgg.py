@@ -199,7 +199,10 @@ class LossNet:
             Fv, den = f[v].reshape(P, ch), 2.0 * P * ch
             if mask is not None:
                 Fv = ops.mul_bcast(f[v], mask[0][v]).reshape(P, ch)
-                den = 2.0 * float(mask[1][v]) * ch
+                if torch.is_tensor(mask[1]):                   # area on the device (3-D style mask: it changes every step)
+                    den = (mask[1][v:v + 1], 2.0 * ch)
+                else:
+                    den = 2.0 * float(mask[1][v]) * ch
             Gs_v = Gs[v] if isinstance(Gs, (list, tuple)) else Gs     # per-image target (style_mask_on_ref)
             ops.gram_diff(Fv, den, Gs_v, weight, G, loss[v:v + 1] if loss is not None else None)
             out['G'].append(G)
@@ -222,12 +225,16 @@ class LossNet:
         if g is None:
             g, beta = torch.empty_like(f), 0.0
         for v in range(n):
-            cv = 4.0 * handle['weight'] / handle['den'][v]
+            den, Gv = handle['den'][v], handle['G'][v]
+            if isinstance(den, tuple):                         # device denominator: the coefficient rides on G
+                cv, Gv = 1.0, ops.scale_by_dev(Gv, 4.0 * handle['weight'], den)
+            else:
+                cv = 4.0 * handle['weight'] / den
             if handle['mask'] is None:
-                ops.gram_bwd(f[v].reshape(P, ch), handle['G'][v], cv, beta, relu_mask, g[v].reshape(P, ch))
+                ops.gram_bwd(f[v].reshape(P, ch), Gv, cv, beta, relu_mask, g[v].reshape(P, ch))
             else:
                 tmp = torch.empty(P, ch, dtype=torch.float32, device=self.device)
-                ops.gram_bwd(handle['Fm'][v], handle['G'][v], cv, 0.0, 0, tmp)
+                ops.gram_bwd(handle['Fm'][v], Gv, cv, 0.0, 0, tmp)
                 handle['tmp'][v] = tmp                             # d loss / d (F m), reused by gram_mask_grad
                 ops.masked_accumulate(tmp.reshape(f[v].shape), handle['mask'][0][v], f[v], relu_mask, g[v], beta)
         return g
@@ -250,12 +257,20 @@ class LossNet:
                 s = (D * D).sum().reshape(1)
             else:
                 s = (D * (D + Gs)).sum().reshape(1) if Gs is not None else (D * D).sum().reshape(1)
-            ops.rowdot(handle['tmp'][v], f[v].reshape(P, ch), dm[v].reshape(P), scalar=s,
-                       scale=-4.0 * handle['weight'] * ch / handle['den'][v])
+            den = handle['den'][v]
+            if isinstance(den, tuple):
+                ops.rowdot(handle['tmp'][v], f[v].reshape(P, ch), dm[v].reshape(P),
+                           scalar=ops.scale_by_dev(s, -4.0 * handle['weight'] * ch, den), scale=1.0)
+            else:
+                ops.rowdot(handle['tmp'][v], f[v].reshape(P, ch), dm[v].reshape(P), scalar=s,
+                           scale=-4.0 * handle['weight'] * ch / den)
             if style_side is not None:
                 fs, hs = style_side
                 tmp_s = torch.empty(P, ch, dtype=torch.float32, device=self.device)
-                ops.gram_bwd(hs[v]['Fm'][0], D, -4.0 * handle['weight'] / handle['den'][v], 0.0, 0, tmp_s)
+                if isinstance(den, tuple):
+                    ops.gram_bwd(hs[v]['Fm'][0], ops.scale_by_dev(D, -4.0 * handle['weight'], den), 1.0, 0.0, 0, tmp_s)
+                else:
+                    ops.gram_bwd(hs[v]['Fm'][0], D, -4.0 * handle['weight'] / den, 0.0, 0, tmp_s)
                 ops.rowdot(tmp_s, fs[0].reshape(P, ch), dm[v].reshape(P), accumulate=True)
         return dm
 

@@ -208,3 +208,28 @@ def test_engine_matches_reference_style_mask_on_ref_run(dev):
     st = Styler(cfg, weights=synth.vgg_weights(), device=dev)
     st.style_img = TR._style_targets(cfg)[0]
     TR._check(st.run(params), dict(np.load(os.path.join(GOLD, 'ref_%s.npz' % name))), '3d')
+
+
+def test_style_mask_denominators_stay_on_the_device(dev):
+    """3-D style mask: the Gram denominators 2 C * area(mask) are device tensors (no read-back per step), the step may
+    replay from a CUDA graph, and the results equal the host-denominator path."""
+    from helpers import smoke_cfg
+    from lnst import synth
+    from lnst.styler_3p import Styler
+    kw = dict(res=12, iter=4, rotate=False, style_mask=True, conv_math='fp32', style_layer=['conv1_2', 'conv2_1'],
+              w_style_layer=[0.5, 0.5])
+    p, r = synth.smoke_particles(700, 2)
+    sty = synth.style_image(12, 12)
+    outs = []
+    for on_device in (True, False):
+        st = Styler(smoke_cfg(**kw), weights=synth.vgg_weights(), device=dev)
+        assert getattr(st, 'cuda_graphs', True)                  # round 1 switched graphs off for style masks
+        st.mask_areas_on_device = on_device
+        if not on_device:
+            st.cuda_graphs = False                               # the host path reads the areas back every step
+        st.style_img = sty
+        masks = st.style_masks_for(torch.rand(1, 12, 12, device=dev), (12, 12), device_areas=on_device)
+        assert torch.is_tensor(masks['conv1_2'][1]) == on_device
+        outs.append(st.run({'p': p, 'r': r}))
+    np.testing.assert_allclose(outs[0]['l'][0], outs[1]['l'][0], rtol=2e-6)
+    assert np.abs(outs[0]['d'] - outs[1]['d']).max() <= 2e-6 * np.abs(outs[1]['d']).max()
