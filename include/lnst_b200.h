@@ -145,7 +145,7 @@ int lnst_raymarch_bwd_box(const float* vol, const float* rot, int32_t n_views, i
  * stats[2*v] = max of view v (stats zero on entry; lnst_image_max's first pass), and the backward march takes the cotangent
  * of the NORMALISED image and applies lnst_normalize_bwd's second pass while loading it (img = the un-normalised render,
  * stats = {max, ties} per view, dots[v] = sum_p g_gray[v,p] * img[v,p]).  With stats == NULL they are the calls above.
- * Rotated march only (view matrices given, every extent >= 2); same results as the separate calls. */
+ * Same results as the separate calls. */
 int lnst_raymarch_fwd_max_box(const float* vol, const float* rot, int32_t n_views, int32_t D, int32_t H, int32_t W,
                               float tau, int32_t liquid, const LnstBox* box, const int32_t* intervals, float* img,
                               float* stot, float* stats, void* stream);

@@ -112,10 +112,12 @@ __global__ void rotate_bwd_k(const float* __restrict__ g_out, const float* __res
 // one thread per pixel column (view, h, w); marches from the camera side (high D) down
 __global__ void raymarch_fwd_k(const float* __restrict__ vol, const float* __restrict__ rot, VolDims v,
                                SubVol sv, float tau, int liquid, float* __restrict__ img,
-                               float* __restrict__ stot) {
+                               float* __restrict__ stot, float* __restrict__ stats) {
   const int P = v.H * v.W;
-  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
-  if (pix >= P) return;
+  const int pix0 = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool act = pix0 < P;
+  if (!act && stats == nullptr) return;
+  const int pix = act ? pix0 : P - 1;            // threads past the image only take part in the maximum
   const int view = blockIdx.y;
   const int h = pix / v.W, w = pix % v.W;
   const float* R = rot ? rot + 9 * view : nullptr;
@@ -127,6 +129,7 @@ __global__ void raymarch_fwd_k(const float* __restrict__ vol, const float* __res
     i_lo = sv.oz; i_hi = sv.oz + sv.ez - 1;
     if (h < sv.oy || h >= sv.oy + sv.ey || w < sv.ox || w >= sv.ox + sv.ex) i_hi = i_lo - 1;
   }
+  if (!act) i_hi = i_lo - 1;
   // RM_UNROLL depth steps are sampled before any of them is consumed, so their (independent)
   // loads are in flight together; only the running transmittance is sequential.
   for (int i0 = i_hi; i0 >= i_lo; i0 -= RM_UNROLL) {
@@ -153,21 +156,34 @@ __global__ void raymarch_fwd_k(const float* __restrict__ vol, const float* __res
     }
   }
   if (liquid) I = 1.f - expf(-S * tau);         // styler_3p.py:150-152
-  img[(int64_t)view * P + pix] = I;
-  stot[(int64_t)view * P + pix] = S;
+  if (act) {
+    img[(int64_t)view * P + pix] = I;
+    stot[(int64_t)view * P + pix] = S;
+  }
+  if (stats != nullptr) {                       // the view's maximum (image_max_k), one atomic per warp
+    const float m = lnst_warp_max(act ? I : 0.f);
+    if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(stats + 2 * view), __float_as_int(m));
+  }
 }
 
 // d I / d d_k = T_k - tau * sum_{i<=k} d_i T_i  (smoke);  tau * exp(-tau * S_total) (liquid)
 __global__ void raymarch_bwd_k(const float* __restrict__ vol, const float* __restrict__ rot, VolDims v,
                                SubVol sv, float tau, int liquid, const float* __restrict__ stot,
-                               const float* __restrict__ g_img, float* __restrict__ g_vol, int use_atomic) {
+                               const float* __restrict__ g_img, float* __restrict__ g_vol, int use_atomic,
+                               const float* __restrict__ nimg, const float* __restrict__ nstats,
+                               const float* __restrict__ ndots) {
   const int P = v.H * v.W;
   const int pix = blockIdx.x * blockDim.x + threadIdx.x;
   if (pix >= P) return;
   const int view = blockIdx.y;
   const int h = pix / v.W, w = pix % v.W;
   const float* R = rot ? rot + 9 * view : nullptr;
-  const float gI = g_img[(int64_t)view * P + pix];
+  float gI = g_img[(int64_t)view * P + pix];
+  if (nstats != nullptr) {                       // g_img is d loss / d (img / max): normalize_bwd_k, inline
+    const float m = nstats[2 * view], ties = nstats[2 * view + 1];
+    gI = gI / m;
+    if (nimg[(int64_t)view * P + pix] == m) gI -= ndots[view] / (m * m) / ties;
+  }
   const float St = stot[(int64_t)view * P + pix];
   if (gI == 0.f) return;
   const float gh = lin_coord(h, v.sH), gw = lin_coord(w, v.sW);
@@ -793,7 +809,6 @@ extern "C" int lnst_raymarch_fwd_box(const float* vol, const float* rot, int32_t
 }
 
 // The same march; stats[2 v] = max over view v's pixels is reduced by the kernel itself (stats zero on entry, may be NULL).
-// Needs the rotated-march kernel: view matrices given, every extent >= 2.
 extern "C" int lnst_raymarch_fwd_max_box(const float* vol, const float* rot, int32_t n_views, int32_t D, int32_t H,
                                          int32_t W, float tau, int32_t liquid, const LnstBox* box,
                                          const int32_t* intervals, float* img, float* stot, float* stats, void* stream) {
@@ -806,10 +821,9 @@ extern "C" int lnst_raymarch_fwd_max_box(const float* vol, const float* rot, int
                 -tau * 1.4426950408889634f, (int)liquid, img, stot, stats);
     return lnst_status();
   }
-  if (stats) return LNST_EARG;
   const VolDims v = make_dims(D, H, W);
   LNST_LAUNCH(raymarch_fwd_k, dim3(lnst_blocks((int64_t)H * W, 128), n_views), dim3(128), 0,
-              lnst_stream(stream), vol, rot, v, make_subvol(box, D, H, W), tau, (int)liquid, img, stot);
+              lnst_stream(stream), vol, rot, v, make_subvol(box, D, H, W), tau, (int)liquid, img, stot, stats);
   return lnst_status();
 }
 
@@ -860,10 +874,10 @@ extern "C" int lnst_raymarch_bwd_norm_box(const float* vol, const float* rot, in
     }
     return lnst_status();
   }
-  if (stats) return LNST_EARG;
   const VolDims v = make_dims(D, H, W);
   LNST_LAUNCH(raymarch_bwd_k, dim3(lnst_blocks((int64_t)H * W, 128), n_views), dim3(128), 0,
-              lnst_stream(stream), vol, rot, v, make_subvol(box, D, H, W), tau, (int)liquid, stot, g_img, g_vol, 0);
+              lnst_stream(stream), vol, rot, v, make_subvol(box, D, H, W), tau, (int)liquid, stot, g_img, g_vol, 0, img,
+              stats, dots);
   return lnst_status();
 }
 

@@ -385,7 +385,7 @@ class Styler(StylerBase):
                     iv = ops.ray_intervals(rot, ds.shape, box, bricks)
                 if 'uniform' in self.sample_type:
                     self._iv_cache[key] = iv
-        fused = glue is not None and not self.render_liquid and not joint and rot is not None and min(ds.shape) >= 2
+        fused = glue is not None and not self.render_liquid and not joint
         ops.raymarch_fwd(ds, rot, self.transmit, self.render_liquid, img, stot, box, iv, stats=glue[0] if fused else None)
         st = {'img': img, 'stot': stot, 'rot': rot, 'box': box, 'iv': iv}
         if self.render_liquid:
@@ -471,7 +471,7 @@ class Styler(StylerBase):
         gray_path = self._gray_path()
         nv = 1 if rot is None else rot.shape[0]
         # one zeroed block for the step's small accumulators: loss [nv] | per-view {max, ties} [2 nv] | dots [nv]
-        fuse = getattr(self, 'fuse_glue', True) and rot is not None and not self.render_liquid and not group
+        fuse = getattr(self, 'fuse_glue', True) and not self.render_liquid and not group
         scal = ops.zeros(4 * nv if fuse else nv, self.device)
         with nvtx('lnst.render_fwd'):
             st = self._render(ds, rot, box, ws['bricks'], net_input=not gray_path, joint=group, touch=ws['touch'],

@@ -124,6 +124,34 @@ def test_exact_ray_intervals_leave_the_render_and_its_gradient_unchanged(dev, sh
     close(outs[1][2][m], outs[0][2][m], tol=1e-5, what='gradient on the support')
 
 
+def test_fused_image_glue_unrotated_march(dev):
+    """the same for the un-rotated march (rot = None: one view along z, box-limited)"""
+    rng = np.random.RandomState(5)
+    D, H, W = 10, 9, 12
+    vol = torch.tensor((rng.rand(D, H, W) * (rng.rand(D, H, W) > 0.4)).astype(np.float32)).to(dev)
+    tau = 0.3
+    for box in (None, _lib.make_box((1, 2, 3), (8, 7, 10))):
+        v = vol.clone()
+        if box is not None:                                  # density only inside the box, like the styler's volumes
+            keep = torch.zeros_like(v)
+            keep[1:9, 2:8, 3:11] = 1
+            v = v * keep
+        img0, st0 = torch.empty(1, H, W, device=dev), torch.empty(1, H, W, device=dev)
+        ops.raymarch_fwd(v, None, tau, False, img0, st0, box)
+        stats0 = ops.image_max(img0, torch.empty(2, device=dev))
+        gray0 = ops.normalize_fwd(img0, stats0, torch.empty_like(img0))
+        img1, st1, stats1 = torch.empty(1, H, W, device=dev), torch.empty(1, H, W, device=dev), torch.zeros(2, device=dev)
+        ops.raymarch_fwd(v, None, tau, False, img1, st1, box, stats=stats1)
+        gray1 = ops.normalize_ties_fwd(img1, stats1, torch.empty_like(img1))
+        assert torch.equal(img0, img1) and torch.equal(st0, st1) and torch.equal(stats0, stats1) and torch.equal(gray0, gray1)
+        g_gray = torch.tensor(rng.randn(1, H, W).astype(np.float32)).to(dev)
+        dots = torch.empty(1, device=dev)
+        g_img = ops.normalize_bwd(img0, stats0, g_gray, dots, torch.empty_like(g_gray))
+        want = ops.raymarch_bwd(v, None, tau, False, st0, g_img, torch.zeros(D, H, W, device=dev), box)
+        got = ops.raymarch_bwd(v, None, tau, False, st0, g_gray, torch.zeros(D, H, W, device=dev), box, norm=(img0, stats0, dots))
+        assert torch.equal(want, got)
+
+
 @pytest.mark.parametrize('shape', [(9, 7, 8), (11, 6, 45), (14, 33, 37)])
 def test_fused_image_glue_equals_the_separate_calls(dev, shape):
     """lnst_raymarch_fwd_max_* + lnst_normalize_ties_fwd against the march, lnst_image_max and lnst_normalize_fwd; and
