@@ -253,6 +253,10 @@ int lnst_set_conv_halo(int32_t on);
  * runs as one GEMM per halo'd patch with the 9 taps as the N dimension plus a 9-term gather; 0 = the halo kernel with
  * one MMA chain per tap. */
 int lnst_set_conv_first_col(int32_t on);
+/* Tuning switch (tests / microbenchmarks): 1 = lnst_conv_first_fwd_gray_x3 runs as one K = 64 GEMM per 128-pixel tile
+ * (gray values and weights split into three bf16 pieces, fp32-accurate); 0 (default) = the CUDA-core kernel, which is
+ * faster in the step. */
+int lnst_set_conv_first_mma(int32_t on);
 /* lnst_conv_first_bwd_gray[_x3]_tc plus dots[i] += sum_p g_gray[i,p] * img[i,p] out of the same kernel (the reduction
  * lnst_normalize_bwd starts with); dots [n] zero on entry, img fp32 [n,H,W] the un-normalised render. */
 int lnst_conv_first_bwd_gray_dot_tc(const void* g, const void* wd16, float* g_gray, const float* img, float* dots,

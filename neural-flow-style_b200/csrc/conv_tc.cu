@@ -2299,6 +2299,154 @@ __global__ void __launch_bounds__(128) conv_first_bwd_gray_col_k(const __grid_co
   }
 }
 
+// ---- conv1_1 of a gray render (bf16x3 output) as ONE K = 64 GEMM per 128-pixel tile ----------------------------------
+// y[p, co] = relu( sum_tap g[p + tap] * ws[tap, co] + bsum[co] (+ the mean terms of taps outside the image) ), the
+// arithmetic of conv_first_fwd_gray_k.  The CUDA-core kernel spends ~1200 instructions per pixel (576 FMAs + the split
+// epilogue) and runs at 35 us against a 14 us write floor.  Here the 9 taps are the K dimension: every gray value and every
+// weight is split into THREE bf16 pieces (24 mantissa bits) and the six products of total order <= 2 are laid side by side,
+//   A row (pixel):   [ g1 | g1 | g2 | g1 | g2 | g3 ] x 9 taps = 54 of 64 columns
+//   B row (channel): [ w1 | w2 | w1 | w3 | w2 | w1 ]
+// so four K = 16 MMAs give the fp32-accurate sum (fp32 accumulation in TMEM) and the threads only build the operand rows
+// and run the epilogue (bias, border terms, ReLU, hi/lo split, coalesced stores).  One 16 x 8-pixel tile per CTA.
+__device__ __forceinline__ void split3(float v, __nv_bfloat16& a, __nv_bfloat16& b, __nv_bfloat16& c) {
+  a = __float2bfloat16_rn(v);
+  const float r1 = v - __bfloat162float(a);
+  b = __float2bfloat16_rn(r1);
+  c = __float2bfloat16_rn(r1 - __bfloat162float(b));
+}
+__global__ void __launch_bounds__(128) conv_first_fwd_gray_mma_k(const float* __restrict__ gimg, const float* __restrict__ ws,
+                                                                 const float* __restrict__ wm, const float* __restrict__ bsum,
+                                                                 __nv_bfloat16* __restrict__ y, int H, int W, int tiles_w,
+                                                                 int tiles_h) {
+  // dynamic shared memory, aligned by hand to 1024 B (the operand swizzle is a function of the absolute address):
+  // A = 128 pixels x 64 bf16 (K-major SWIZZLE_128B), B = 64 channels x 64 bf16, then 4 x 2 KiB of store staging
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t s_a = sbase, s_b = sbase + 128 * 128, s_stage = s_b + 64 * 128;
+  __shared__ __align__(8) uint64_t s_bar;
+  __shared__ uint32_t s_tmem;
+  __shared__ float s_bias[64];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_sp = tiles_w * tiles_h;
+  const int img = blockIdx.x / tiles_sp, rem = blockIdx.x - img * tiles_sp;
+  const int th = rem / tiles_w, tw = rem - th * tiles_w;
+  const int r = threadIdx.x;                                // accumulator row = tile pixel (r >> 3, r & 7)
+  const int ph = th * HTH + (r >> 3), pw = tw * HTW + (r & 7);
+  const bool valid = ph < H && pw < W;
+
+  // ---- operand rows: the pixel's 9 neighbours (zero outside the image: x is padded, not g -- see the border terms) ----
+  {
+    __nv_bfloat16 p1[9], p2[9], p3[9];
+    const float* gi = gimg + (int64_t)img * H * W;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const int yy = ph + t / 3 - 1, xx = pw + t % 3 - 1;
+      const float g = (valid && yy >= 0 && yy < H && xx >= 0 && xx < W) ? gi[(int64_t)yy * W + xx] : 0.f;
+      split3(g, p1[t], p2[t], p3[t]);
+    }
+    __nv_bfloat16 row[64];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      row[t] = p1[t]; row[9 + t] = p1[t]; row[18 + t] = p2[t]; row[27 + t] = p1[t]; row[36 + t] = p2[t]; row[45 + t] = p3[t];
+    }
+#pragma unroll
+    for (int t = 54; t < 64; ++t) row[t] = __float2bfloat16_rn(0.f);
+    const uint32_t a0 = s_a + r * 128;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      st_shared_v4(a0 + ((uint32_t)((j ^ r) & 7) << 4), *reinterpret_cast<const uint4*>(&row[8 * j]));
+  }
+  if (r < 64) {
+    __nv_bfloat16 q1[9], q2[9], q3[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) split3(ws[t * 64 + r], q1[t], q2[t], q3[t]);
+    __nv_bfloat16 row[64];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      row[t] = q1[t]; row[9 + t] = q2[t]; row[18 + t] = q1[t]; row[27 + t] = q3[t]; row[36 + t] = q2[t]; row[45 + t] = q1[t];
+    }
+#pragma unroll
+    for (int t = 54; t < 64; ++t) row[t] = __float2bfloat16_rn(0.f);
+    const uint32_t b0 = s_b + r * 128;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      st_shared_v4(b0 + ((uint32_t)((j ^ r) & 7) << 4), *reinterpret_cast<const uint4*>(&row[8 * j]));
+    s_bias[r] = bsum[r];
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  const uint32_t bar = smem_u32(&s_bar);
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(64));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_d = s_tmem;
+  if (warp == 0) {
+    if (elect_one()) {
+      const uint32_t idesc = umma_idesc_bf16(BLOCK_M, 64);
+      const uint32_t hi = desc_hi_sw128(1024);
+      const uint32_t alo = desc_lo(s_a, 16), blo = desc_lo(s_b, 16);
+#pragma unroll
+      for (int k = 0; k < BLOCK_K / UMMA_K; ++k) umma_bf16_lh(tmem_d, alo + k * 2, hi, blo + k * 2, hi, idesc, k != 0 ? 1u : 0u);
+      umma_commit(bar);
+    }
+  }
+  mbar_wait(bar, 0);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  uint32_t v[64];
+  tmem_ld32_nowait(tmem_d + ((uint32_t)(warp * 32) << 16), v);
+  tmem_ld32_nowait(tmem_d + ((uint32_t)(warp * 32) << 16) + 32, v + 32);
+  tmem_ld_wait();
+  float f[64];
+#pragma unroll
+  for (int c = 0; c < 64; ++c) f[c] = __uint_as_float(v[c]) + s_bias[c];
+  if (valid && (ph == 0 || ph == H - 1 || pw == 0 || pw == W - 1)) {   // border: give back the mean terms of missing taps
+    for (int t = 0; t < 9; ++t) {
+      const int yy = ph + t / 3 - 1, xx = pw + t % 3 - 1;
+      if (yy < 0 || yy >= H || xx < 0 || xx >= W) {
+#pragma unroll
+        for (int c = 0; c < 64; ++c) f[c] += wm[t * 64 + c];
+      }
+    }
+  }
+#pragma unroll
+  for (int ck = 0; ck < 2; ++ck) {
+    uint4 ov[4], ol[4];
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&ov[jj]);
+      __nv_bfloat162* ohl = reinterpret_cast<__nv_bfloat162*>(&ol[jj]);
+#pragma unroll
+      for (int e = 0; e < 8; e += 2)
+        split2(fmaxf(f[ck * 32 + jj * 8 + e], 0.f), fmaxf(f[ck * 32 + jj * 8 + e + 1], 0.f), oh[e >> 1], ohl[e >> 1]);
+    }
+    auto rowptr = [&](int row, int half) -> __nv_bfloat16* {
+      const int rr = warp * 32 + row;
+      const int ph2 = th * HTH + (rr >> 3), pw2 = tw * HTW + (rr & 7);
+      if (ph2 >= H || pw2 >= W) return nullptr;
+      return y + (((int64_t)img * H + ph2) * W + pw2) * 128 + half * 64 + ck * 32;
+    };
+    warp_rows_store<4>(s_stage + (uint32_t)warp * 2048u, lane, ov, [&](int row) { return rowptr(row, 0); });
+    warp_rows_store<4>(s_stage + (uint32_t)warp * 2048u, lane, ol, [&](int row) { return rowptr(row, 1); });
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(64));
+  }
+}
+// tuning switch: 1 = the kernel above for lnst_conv_first_fwd_gray_x3, 0 (default) = the CUDA-core kernel.  Measured in the
+// C3 step: +13 us with the MMA form -- one tile per CTA serialises operand build, MMA and epilogue behind two block-wide
+// syncs and a TMEM allocation, and 112 registers leave 4 CTAs per SM; it would have to be persistent to win.
+static int conv_first_mma = 0;
+
 static int conv_first_col = 1;    // tuning switch: 1 = the one-GEMM-per-patch kernel above for the gray data gradient, 0 = halo kernel
 
 static int launch_first_bwd_col(const void* g, const void* wd16, float* g_gray, int n, int H, int W, int split,
@@ -2360,11 +2508,19 @@ extern "C" int lnst_conv_first_fwd_gray(const float* gray, const float* ws, cons
 extern "C" int lnst_conv_first_fwd_gray_x3(const float* gray, const float* ws, const float* wm, const float* bsum,
                                            void* y, int32_t n, int32_t H, int32_t W, void* stream) {
   if (!gray || !ws || !wm || !bsum || !y || n < 1 || H < 1 || W < 1) return LNST_EARG;
+  if (tc::conv_first_mma) {
+    const int tiles_w = (W + tc::HTW - 1) / tc::HTW, tiles_h = (H + tc::HTH - 1) / tc::HTH;
+    tc::conv_first_fwd_gray_mma_k<<<(unsigned)(tiles_w * tiles_h * n), 128, 128 * 128 + 64 * 128 + 4 * 2048 + 1024,
+                                    lnst_stream(stream)>>>(
+        gray, ws, wm, bsum, (__nv_bfloat16*)y, H, W, tiles_w, tiles_h);
+    return lnst_status();
+  }
   const int64_t threads = (int64_t)n * H * ((W + tc::FP - 1) / tc::FP) * 8;
   tc::conv_first_fwd_gray_k<<<lnst_blocks(threads, 256), 256, 0, lnst_stream(stream)>>>(gray, ws, wm, bsum,
                                                                                        (__nv_bfloat16*)y, n, H, W, 1);
   return lnst_status();
 }
+extern "C" int lnst_set_conv_first_mma(int32_t on) { tc::conv_first_mma = on ? 1 : 0; return LNST_OK; }
 
 extern "C" int lnst_conv_first_bwd(const void* g, const float* wd, float* gx, int32_t n, int32_t H, int32_t W,
                                    void* stream) {

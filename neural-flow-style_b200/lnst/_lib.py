@@ -118,6 +118,7 @@ CUDA_ONLY = {
     'lnst_set_conv_persistent': [i32],
     'lnst_set_conv_halo': [i32],
     'lnst_set_conv_first_col': [i32],
+    'lnst_set_conv_first_mma': [i32],
     'lnst_set_gram_split3': [i32],
     'lnst_conv_first_bwd_tc': [vp, vp, vp, i32, i32, i32, vp],
     'lnst_conv_first_fwd_gray': [vp, vp, vp, vp, vp, i32, i32, i32, vp],

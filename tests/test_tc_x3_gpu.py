@@ -277,3 +277,30 @@ def test_data_gradient_with_fused_pool_backward_is_bit_identical(n, H, W, cin, c
     want = ops.avgpool2_bf16x3_bwd(y, fine, fine.shape)
     got = ops.conv3x3_unpool_bf16x3_tc(x, w, fine)
     assert got.shape == want.shape and torch.equal(got, want)
+
+
+@pytest.mark.parametrize('n,H,W', [(2, 13, 9), (3, 50, 64), (1, 200, 200), (1, 33, 47), (2, 16, 8)])
+def test_conv_first_fwd_gray_as_one_gemm_per_tile(n, H, W):
+    """conv1_1 of a gray render in split form: the K = 64 MMA kernel (three bf16 pieces per gray value and weight, six
+    products) against the CUDA-core kernel and an fp64 convolution of x = 255 g - mean."""
+    from lnst import vgg
+    dev = torch.device('cuda:0')
+    gen = torch.Generator().manual_seed(H * 7 + W)
+    gray = torch.rand(n, H, W, generator=gen)
+    net = vgg.LossNet(synth.vgg_weights(), 'vgg_19', dev, math='bf16x3')
+    w, b = net.w['conv1_1'].double().cpu(), net.b['conv1_1'].double().cpu()
+    mean = torch.tensor([vgg._R_MEAN, vgg._G_MEAN, vgg._B_MEAN], dtype=torch.float64)
+    x = 255.0 * gray.double()[..., None] - mean
+    want = torch.relu(torch.nn.functional.conv2d(x.permute(0, 3, 1, 2), w.permute(3, 2, 0, 1), b, padding=1)).permute(0, 2, 3, 1)
+    lib = _lib.get()
+    cuda_core = ops.from_split(ops.conv_first_fwd_gray_x3(gray.to(dev), *net.tc.gray_w)).cpu().double()
+    lib.call('lnst_set_conv_first_mma', 1)
+    try:
+        got = ops.from_split(ops.conv_first_fwd_gray_x3(gray.to(dev), *net.tc.gray_w)).cpu().double()
+    finally:
+        lib.call('lnst_set_conv_first_mma', 0)
+    scale = want.abs().max().item()
+    # the split output carries 16 mantissa bits: 2^-17 relative per value, plus fp32 accumulation
+    assert (cuda_core - want).abs().max().item() <= 1.2e-5 * scale
+    assert (got - want).abs().max().item() <= 1.2e-5 * scale, ((got - want).abs().max().item(), scale)
+    assert (got - cuda_core).abs().max().item() <= 1.2e-5 * scale

@@ -28,6 +28,8 @@ def main():
             vgg_tc.TensorCoreConvs.fuse_pool = bool(on)
         elif a.switch == 'gram_split3':
             lib.call('lnst_set_gram_split3', int(on))
+        elif a.switch == 'first_mma':
+            lib.call('lnst_set_conv_first_mma', int(not on))      # the MMA form is the non-default arm
         elif a.switch == 'first_col':
             lib.call('lnst_set_conv_first_col', int(on))
         elif a.switch.startswith('lib:'):                   # default library (1) against a variant build (0)
