@@ -722,14 +722,14 @@ class Styler(StylerBase):
             var = g_opt_t.clone()                                  # :312 (device copy, no H2D)
             n_step_views = self.n_views // self.v_batch
             acc = torch.empty_like(var)
-            losses = []
-            for i in range(0, self.n_views, self.v_batch):
+            losses = torch.empty(n_step_views, dtype=f32, device=dev)
+            for j, i in enumerate(range(0, self.n_views, self.v_batch)):
                 l, grad = self.loss_and_grad(fr, var, ws, self._rot_all[i:i + self.v_batch], style_grams,
                                              group=self.v_batch > 1)
                 adam.step(var, grad, lr)
                 ops.iterate_accumulate(acc, var, i == 0)
-                losses.append(l.sum().reshape(1))                  # one total_loss per fed group
-            loss_t = torch.cat(losses).mean()                      # :342
+                ops.sum_scale(l, 1.0, out=losses[j:j + 1])         # one total_loss per fed group
+            loss_t = ops.sum_scale(losses, 1.0 / n_step_views)[0]  # :342 (library reductions: no framework kernels in the graph)
             delta = ops.iterate_delta(acc, 1.0 / n_step_views, g_opt_t, mask, mstride, torch.empty_like(var))  # :351-352
             return var, loss_t, delta
         # one Adam step per iteration: the forward/backward pass reads g_opt[t] itself (the reference's variable
