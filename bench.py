@@ -442,32 +442,35 @@ def measure_step(ctx, wl, view_mode, conv_math, steps, warmup, full=True):
     sg = torch.zeros(world * chunk, g_opt.shape[1], device=dev)
     cs = torch.cuda.Stream(device=dev)
     main = torch.cuda.current_stream(dev)
-    e2e_steps = max(3, min(steps, 10))
+    e2e_steps, e2e_warm = max(3, steps), 2               # K timed steps after two untimed ones (pipeline in steady state)
 
     def gather(full):
         if world > 1:
             ctx.dist.all_gather_into_tensor(full, full[rank * chunk:(rank + 1) * chunk])
 
     ctx.barrier()
-    w0 = time.perf_counter()
     uploaded, consumed = torch.cuda.Event(), torch.cuda.Event()
     with torch.cuda.stream(cs):
         sp[lo_r:hi_r].copy_(hp, non_blocking=True)
         sr[lo_r:hi_r].copy_(hr, non_blocking=True)
         uploaded.record(cs)
-    for i in range(e2e_steps):
+    w0 = None
+    for i in range(e2e_warm + e2e_steps):
+        if i == e2e_warm:                                # the timed region: exactly e2e_steps steps, each with its own
+            torch.cuda.synchronize()                     # H2D of p, r and the variable and its D2H of variable + loss
+            ctx.barrier()                                # (p, r of step i travel under step i - 1: one upload per timed step)
+            w0 = time.perf_counter()
         main.wait_event(uploaded)
         gather(sp)
         gather(sr)
         fr['p'].copy_(sp[:n_rows], non_blocking=True)
         fr['r'].copy_(sr[:n_rows], non_blocking=True)
         consumed.record(main)
-        if i + 1 < e2e_steps:                            # next step's particle upload, under this step
-            with torch.cuda.stream(cs):
-                cs.wait_event(consumed)
-                sp[lo_r:hi_r].copy_(hp, non_blocking=True)
-                sr[lo_r:hi_r].copy_(hr, non_blocking=True)
-                uploaded.record(cs)
+        with torch.cuda.stream(cs):                      # next step's particle upload, under this step
+            cs.wait_event(consumed)
+            sp[lo_r:hi_r].copy_(hp, non_blocking=True)
+            sr[lo_r:hi_r].copy_(hr, non_blocking=True)
+            uploaded.record(cs)
         sg[lo_r:hi_r].copy_(hg, non_blocking=True)
         gather(sg)
         g_opt.copy_(sg[:n_rows], non_blocking=True)
@@ -480,7 +483,7 @@ def measure_step(ctx, wl, view_mode, conv_math, steps, warmup, full=True):
     e2e_s = ctx.max_over_ranks(time.perf_counter() - w0)
     out['e2e'] = {'value': e2e_steps / e2e_s, 'unit': 'iters/s',
                   'h2d_bytes_per_step': world * (hp.numel() * 4 + hr.numel() * 4 + hg.numel() * 4),
-                  'd2h_bytes_per_step': world * (hg.numel() * 4 + 4), 'steps': e2e_steps,
+                  'd2h_bytes_per_step': world * (hg.numel() * 4 + 4), 'steps': e2e_steps, 'warmup': e2e_warm,
                   'per_rank': 'each rank moves 1/%d of the rows over PCIe; slices all-gathered over NVLink' % world if world > 1 else 'single rank',
                   'boundary': "the reference's sess.run boundary per step (styler_3p.py:312,331,334): p, r and the variable "
                               'uploaded from pinned host memory, variable + loss read back'}
